@@ -1,0 +1,247 @@
+/* pp_abi.h — C ABI of polypolish-b200 (libpolypolish_b200.so).
+ *
+ * The reference (rrwick/Polypolish v0.6.1) is a monolithic Rust binary with no plugin/FFI surface, so the
+ * drop-in boundary is cut at the function seams of its hot path; each entry point below
+ * names the reference function(s) it replaces.  Everything text-shaped (SAM/FASTA) stays on the host side of
+ * the boundary; everything from packed records to polished bytes runs as sm_100a kernels.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; the caller owns every host buffer; the library
+ * owns all device memory and streams inside pp_ctx; integer return codes (0 = ok, <0 = error) and
+ * pp_last_error() for the message; no exceptions or exit() cross the boundary.  A pp_ctx is single-threaded
+ * (the reference is single-threaded); multi-GPU = one ctx per GPU, one host thread (or process) each.
+ * There is no CPU fallback: every compute entry point fails with PP_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PP_ABI_H
+#define PP_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_OK 0
+#define PP_ERR_CUDA (-1)   /* CUDA runtime/driver failure, or no usable device */
+#define PP_ERR_ARG (-2)    /* malformed arguments (null pointers, sizes out of range, capacity too small) */
+#define PP_ERR_INPUT (-3)  /* the reference's quit_with_error / panic cases; message = the reference's text */
+#define PP_ERR_NOMEM (-4)
+#define PP_ERR_IO (-5)
+
+typedef struct pp_ctx pp_ctx; /* opaque; one per (host thread, GPU) */
+
+int pp_create(int device, pp_ctx** out);
+void pp_destroy(pp_ctx* ctx);
+const char* pp_last_error(const pp_ctx* ctx); /* ctx-owned, valid until the next call on ctx */
+const char* pp_version(void);                 /* "0.6.1-b200" : tracks main.rs:24-25 crate version */
+
+/* Pinned host memory for the SoA arrays (H2D at full PCIe rate). Plain malloc'd buffers also work. */
+void* pp_host_alloc(size_t bytes);
+void pp_host_free(void* p);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Packed alignments (struct-of-arrays), in SAM order: (file index, line index).  ORDER IS SEMANTICALLY
+ * SIGNIFICANT: the reference sums the f64 depth sequentially in this order (pileup.rs:64).
+ * Replaces the in-memory `Alignment` of alignment.rs:33-43 as produced by Alignment::new (alignment.rs:49-98).
+ * ---------------------------------------------------------------------------------------------------- */
+#define PP_CONTIG_UNKNOWN 0xFFFFFFFFu /* RNAME not in the assembly: an error only if the alignment is "good" (alignment.rs:298-300) */
+
+#define PP_FLAG_REVERSE 0x01 /* SAM flag 16 (alignment.rs:151-153) */
+#define PP_FLAG_ZPFAIL  0x02 /* a ZP:Z:fail tag was present (alignment.rs:72-74) */
+#define PP_FLAG_SEQSTAR 0x04 /* SEQ was "*": the sequence is the read group's source sequence (alignment.rs:290-295,311-322) */
+#define PP_FLAG_RC      0x08 /* use the reverse complement of the pooled sequence (alignment.rs:161-167) */
+#define PP_FLAG_NOSEQ   0x10 /* no record of the group carried a sequence (only legal when the group is skipped by --careful) */
+
+/* CIGAR op codes in cigar_ops (BAM numbering): len << 4 | op.  Zero-length ops are dropped by the packer
+ * (they contribute nothing to the expanded CIGAR of alignment.rs:325-346). */
+#define PP_OP_M 0
+#define PP_OP_I 1
+#define PP_OP_D 2
+#define PP_OP_N 3
+#define PP_OP_S 4
+#define PP_OP_H 5
+#define PP_OP_P 6
+#define PP_OP_EQ 7
+#define PP_OP_X 8
+
+#define PP_SEQ_BLOCK 32 /* every pooled sequence starts on a 32-base boundary (16 B in 4-bit mode) */
+
+typedef struct {
+  uint64_t n_aln;            /* aligned records (flag&4 == 0), all SAM files concatenated in CLI order        */
+  uint64_t n_reads;          /* number of read groups = max(read_id)+1                                        */
+  const uint32_t* contig;    /* [n_aln] contig index, or PP_CONTIG_UNKNOWN                                    */
+  const uint32_t* ref_start; /* [n_aln] 0-based (POS-1, POS 0 stays 0: alignment.rs:58-61)                    */
+  const uint32_t* read_id;   /* [n_aln] group id; a group = maximal run of consecutive equal QNAMEs
+                                (alignment.rs:255-263); ids are dense and non-decreasing                     */
+  const uint32_t* seq_off;   /* [n_aln] start of the sequence in seq_pool, in units of PP_SEQ_BLOCK bases     */
+  const uint16_t* seq_len;   /* [n_aln] bases                                                                 */
+  const uint32_t* cigar_off; /* [n_aln] first op in cigar_ops                                                 */
+  const uint16_t* n_cigar;   /* [n_aln] ops                                                                   */
+  const uint32_t* nm;        /* [n_aln] NM:i value (last one wins, alignment.rs:68-71)                        */
+  const uint8_t* flags;      /* [n_aln] PP_FLAG_*                                                             */
+  uint64_t n_cigar_ops;
+  const uint32_t* cigar_ops; /* pool                                                                          */
+  uint32_t seq_bits;         /* 4: BAM nibble codes "=ACMGRSVTWYHKDBN", 2 per byte, low nibble first, code 0
+                                never used; 8: upper-cased ASCII bytes (any read with a character outside the
+                                15 letters forces 8-bit mode so that parity holds for arbitrary SEQ bytes)   */
+  uint64_t seq_pool_bytes;
+  const uint8_t* seq_pool;   /* 16-byte aligned                                                               */
+} pp_alignments;
+
+/* The assembly: Pileup::new input (pileup.rs:178-187) as loaded by misc::load_fasta (misc.rs:38-167). */
+typedef struct {
+  uint32_t n_contigs;
+  const uint64_t* off;  /* [n_contigs+1] start of each contig in bases; off[n_contigs] = total bp (< 2^32-64) */
+  const uint8_t* bases; /* upper-cased ASCII, contigs concatenated                                            */
+} pp_contigs;
+
+/* polish options (main.rs:78-108; validation polish.rs:277-287 is done by the caller-facing layers) */
+typedef struct {
+  double fraction_invalid; /* -i, default 0.2 */
+  double fraction_valid;   /* -v, default 0.5 */
+  uint32_t max_errors;     /* -m, default 10  */
+  uint32_t min_depth;      /* -d, default 5   */
+  int32_t careful;         /* --careful       */
+} pp_polish_params;
+
+#define PP_N_STAGES 8
+typedef struct {
+  float total_ms;               /* CUDA-event time of the whole device path of this call            */
+  float stage_ms[PP_N_STAGES];  /* 0 reset, 1 classify (goodness+k), 2 scatter (CIGAR walk+pileup), 3 depth fix-up,
+                                   4 other-allele sort, 5 vote+compaction, 6 h2d, 7 d2h              */
+  uint32_t launches;            /* kernels of this library launched during the call                 */
+  uint32_t reserved;
+} pp_timing;
+
+typedef struct {
+  /* caller-allocated outputs (may be NULL to leave the result on the device; fetch later) */
+  uint64_t* out_off;    /* [n_contigs+1] start of each polished contig in out_bases                  */
+  uint8_t* out_bases;   /* polished bases, '-' already removed (polish.rs:188), contigs concatenated */
+  uint64_t out_cap;     /* capacity of out_bases in bytes                                            */
+  uint64_t* changed;    /* [n_contigs] positions with status Changed (polish.rs:173-176), may be NULL */
+  uint64_t* zero_depth; /* [n_contigs] positions with depth == 0 (polish.rs:178-180), may be NULL     */
+  /* filled by the library */
+  uint64_t out_len;     /* total polished bases (if > out_cap nothing was copied: PP_ERR_ARG)        */
+  uint64_t n_aln_used;  /* Σ good alignments (alignment.rs:304, polish.rs:121)                       */
+  int64_t error_aln;    /* for PP_ERR_INPUT raised by one alignment: its index, else -1              */
+  pp_timing timing;
+} pp_polish_result;
+
+/* One call = process_one_read for every group (alignment.rs:275-305) + Pileup::add_alignment for every good
+ * alignment (pileup.rs:189-200, alignment.rs:175-201,364-378) + PileupBase::get_polished_seq for every
+ * position (pileup.rs:67-134) + the '-' stripping join of polish_one_sequence (polish.rs:185-188).
+ * Host buffers in, host buffers out; H2D/D2H inside. */
+int pp_polish(pp_ctx* ctx, const pp_contigs* contigs, const pp_alignments* alns,
+              const pp_polish_params* params, pp_polish_result* result);
+
+/* Device-resident variant (kernel-path timing; repeated polishing with different options):
+ * upload once, polish many times, fetch when wanted. */
+int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* contigs, const pp_alignments* alns);
+int pp_polish_resident(pp_ctx* ctx, const pp_polish_params* params, pp_polish_result* result);
+
+
+/* ------------------------------------------------------------------------------------------------------
+ * filter (filter.rs).  One record per ALIGNED line of one mate's SAM file, in file order.
+ * Replaces get_insert_size_thresholds (filter.rs:148-186) and alignment_pass_qc (filter.rs:352-377).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint64_t n;
+  const uint32_t* name_id;   /* [n] id of QNAME, shared between the two mates (filter.rs:133-135,322-326) */
+  const uint32_t* contig;    /* [n] id of RNAME (string equality, filter.rs:161,369)                        */
+  const uint32_t* ref_start; /* [n] 0-based                                                                  */
+  const uint32_t* ref_end;   /* [n] Alignment::get_ref_end (alignment.rs:138-149)                            */
+  const uint8_t* flags;      /* [n] bit0 = reverse strand                                                     */
+} pp_filter_mate;
+
+typedef struct {
+  int32_t orientation;  /* -1 auto, 0 fr, 1 rf, 2 ff, 3 rr, 4 = any other user string (matches nothing) */
+  double low_pct;       /* --low, default 0.1  */
+  double high_pct;      /* --high, default 99.9 */
+  uint64_t n_names;     /* name ids are < n_names */
+} pp_filter_params;
+
+typedef struct {
+  uint8_t* pass1;       /* [m1.n] caller-allocated: 1 = line written verbatim, 0 = "\tZP:Z:fail" appended */
+  uint8_t* pass2;       /* [m2.n] */
+  uint32_t low, high;   /* insert-size thresholds (filter.rs:179-180) */
+  int32_t orientation;  /* chosen orientation 0..3 (or 4) */
+  uint64_t pairs[4];    /* fr, rf, ff, rr pair counts (filter.rs:223-226) */
+  uint64_t n_pass;      /* filter.rs:345 pass counts, both mates */
+  pp_timing timing;
+} pp_filter_result;
+
+int pp_filter(pp_ctx* ctx, const pp_filter_mate* m1, const pp_filter_mate* m2,
+              const pp_filter_params* params, pp_filter_result* result);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Host layer (text <-> packed), exported so that the CLI, the Python mirror and a Rust host share one
+ * implementation.  No GPU needed for these.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct pp_fasta pp_fasta;
+/* misc::load_fasta (misc.rs:38-167): plain or gzip (magic 1f 8b), upper-cased, checks of misc.rs:56-75. */
+pp_fasta* pp_fasta_load(const char* path, char* err, size_t errcap);
+void pp_fasta_free(pp_fasta* f);
+void pp_fasta_view(const pp_fasta* f, pp_contigs* out);
+const char* pp_fasta_name(const pp_fasta* f, uint32_t i);
+const char* pp_fasta_description(const pp_fasta* f, uint32_t i);
+
+typedef struct pp_pack pp_pack;
+/* SAM text -> pp_alignments.  Restates the text side of add_to_pileup (alignment.rs:225-272) and
+ * Alignment::new (alignment.rs:49-98): line skipping, column checks, NM / ZP tags, CIGAR validation,
+ * QNAME grouping, source sequence of SEQ="*" records. */
+pp_pack* pp_pack_create(const pp_fasta* f, int careful);
+void pp_pack_free(pp_pack* p);
+int pp_pack_add_sam_file(pp_pack* p, const char* path);                        /* PP_OK / PP_ERR_INPUT / PP_ERR_IO */
+int pp_pack_add_sam_text(pp_pack* p, const char* text, size_t len, const char* name_for_errors);
+/* one logical SAM file fed in chunks of whole lines (a host reading a pipe; the synthetic generator) */
+int pp_pack_stream_begin(pp_pack* p, const char* name_for_errors);
+int pp_pack_stream_feed(pp_pack* p, const char* text, size_t len);
+int pp_pack_stream_end(pp_pack* p);
+int pp_pack_finish(pp_pack* p, pp_alignments* out);                             /* arrays owned by p */
+const char* pp_pack_error(const pp_pack* p);
+/* name of the RNAME of alignment i when contig[i] == PP_CONTIG_UNKNOWN, and the QNAME of alignment i */
+const char* pp_pack_unknown_ref(const pp_pack* p, uint64_t aln);
+const char* pp_pack_read_name(const pp_pack* p, uint64_t aln);
+/* per file: aligned records and read groups (the stderr line of polish.rs:117-119) */
+int pp_pack_file_stats(const pp_pack* p, uint32_t file, uint64_t* alignments, uint64_t* reads);
+
+/* Whole commands (the functions the CLI calls; same behaviour, error text and exit status as the
+ * reference's polish::polish (polish.rs:26-38) and filter::filter (filter.rs:26-37)).
+ * out_fasta receives exactly what the reference prints to stdout; free with pp_free. */
+int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* const* sams, int n_sams,
+                    const pp_polish_params* params, const char* debug_path, char** out_fasta,
+                    uint64_t* out_len, int verbose /* 1: reference-style log on stderr */);
+int pp_filter_files(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2,
+                    const char* orientation, double low, double high, int verbose);
+void pp_free(void* p);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Synthetic inputs (measurement / test support).  Deterministic in `seed`.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint64_t seed;
+  uint32_t n_contigs;
+  uint32_t read_len;          /* 150 */
+  uint64_t contig_len;        /* truth bases per contig */
+  double depth;               /* mean read depth */
+  double insert_mean, insert_sd; /* 400, 40 (clipped to [200,700]) */
+  double draft_error_rate;    /* 1e-4 per bp: 50 % substitutions, 25 % / 25 % 1-bp indels */
+  double seq_sub_rate;        /* 2e-3 per base */
+  double seq_indel_rate;      /* 1e-4 per base */
+  double repeat_fraction;     /* 0.03 of the genome in repeat families with 7,5,3,2,4 copies */
+  double clip_rate, highnm_rate, unaligned_rate; /* 0.005 each */
+} pp_synth_params;
+typedef struct pp_synth pp_synth;
+pp_synth* pp_synth_create(const pp_synth_params* prm);
+void pp_synth_free(pp_synth* s);
+uint64_t pp_synth_total_bp(const pp_synth* s);    /* draft bases */
+uint64_t pp_synth_n_pairs(const pp_synth* s);
+int pp_synth_write_fasta(const pp_synth* s, const char* path, int truth /* 0 = draft */);
+int pp_synth_write_sam(const pp_synth* s, int mate /* 1 | 2 */, const char* path);
+pp_fasta* pp_synth_fasta(const pp_synth* s);      /* the draft as a loaded assembly (free with pp_fasta_free) */
+int pp_synth_feed_pack(const pp_synth* s, int mate, pp_pack* pack); /* same text, streamed into the packer */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PP_ABI_H */

@@ -1,0 +1,445 @@
+"""ctypes mirror of include/pp_abi.h.
+
+Names follow the reference's command surface (main.rs:44-109): `polish(...)` and `filter_sams(...)` take the same
+options with the same defaults and raise PolypolishError with the reference's error text.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PP_OK, PP_ERR_CUDA, PP_ERR_ARG, PP_ERR_INPUT, PP_ERR_NOMEM, PP_ERR_IO = 0, -1, -2, -3, -4, -5
+N_STAGES = 8
+STAGES = ["reset", "classify", "scatter", "fixup", "other_sort", "vote", "h2d", "d2h"]
+
+
+class PolypolishError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def lib_path():
+    return os.path.join(ROOT, "build", "libpolypolish_b200.so")
+
+
+class Alignments(C.Structure):
+    _fields_ = [("n_aln", C.c_uint64), ("n_reads", C.c_uint64),
+                ("contig", C.c_void_p), ("ref_start", C.c_void_p), ("read_id", C.c_void_p), ("seq_off", C.c_void_p),
+                ("seq_len", C.c_void_p), ("cigar_off", C.c_void_p), ("n_cigar", C.c_void_p), ("nm", C.c_void_p),
+                ("flags", C.c_void_p), ("n_cigar_ops", C.c_uint64), ("cigar_ops", C.c_void_p),
+                ("seq_bits", C.c_uint32), ("seq_pool_bytes", C.c_uint64), ("seq_pool", C.c_void_p)]
+
+
+class Contigs(C.Structure):
+    _fields_ = [("n_contigs", C.c_uint32), ("off", C.c_void_p), ("bases", C.c_void_p)]
+
+
+class PolishParams(C.Structure):
+    _fields_ = [("fraction_invalid", C.c_double), ("fraction_valid", C.c_double), ("max_errors", C.c_uint32),
+                ("min_depth", C.c_uint32), ("careful", C.c_int32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("stage_ms", C.c_float * N_STAGES), ("launches", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        d = {"total_ms": self.total_ms, "launches": self.launches}
+        d.update({STAGES[i] + "_ms": self.stage_ms[i] for i in range(N_STAGES)})
+        return d
+
+
+class PolishResult(C.Structure):
+    _fields_ = [("out_off", C.c_void_p), ("out_bases", C.c_void_p), ("out_cap", C.c_uint64), ("changed", C.c_void_p),
+                ("zero_depth", C.c_void_p), ("out_len", C.c_uint64), ("n_aln_used", C.c_uint64),
+                ("error_aln", C.c_int64), ("timing", Timing)]
+
+
+class FilterMate(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("name_id", C.c_void_p), ("contig", C.c_void_p), ("ref_start", C.c_void_p),
+                ("ref_end", C.c_void_p), ("flags", C.c_void_p)]
+
+
+class FilterParams(C.Structure):
+    _fields_ = [("orientation", C.c_int32), ("low_pct", C.c_double), ("high_pct", C.c_double),
+                ("n_names", C.c_uint64)]
+
+
+class FilterResult(C.Structure):
+    _fields_ = [("pass1", C.c_void_p), ("pass2", C.c_void_p), ("low", C.c_uint32), ("high", C.c_uint32),
+                ("orientation", C.c_int32), ("pairs", C.c_uint64 * 4), ("n_pass", C.c_uint64), ("timing", Timing)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library.  Fails loudly: there is no CPU path behind this package."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise PolypolishError(PP_ERR_CUDA, f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                           "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(p)
+    L.pp_version.restype = C.c_char_p
+    L.pp_last_error.restype = C.c_char_p
+    L.pp_last_error.argtypes = [C.c_void_p]
+    L.pp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.pp_destroy.argtypes = [C.c_void_p]
+    L.pp_host_alloc.restype = C.c_void_p
+    L.pp_host_alloc.argtypes = [C.c_size_t]
+    L.pp_host_free.argtypes = [C.c_void_p]
+    L.pp_polish.argtypes = [C.c_void_p, C.POINTER(Contigs), C.POINTER(Alignments), C.POINTER(PolishParams),
+                            C.POINTER(PolishResult)]
+    L.pp_dataset_upload.argtypes = [C.c_void_p, C.POINTER(Contigs), C.POINTER(Alignments)]
+    L.pp_polish_resident.argtypes = [C.c_void_p, C.POINTER(PolishParams), C.POINTER(PolishResult)]
+    L.pp_fasta_load.restype = C.c_void_p
+    L.pp_fasta_load.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+    L.pp_fasta_free.argtypes = [C.c_void_p]
+    L.pp_fasta_view.argtypes = [C.c_void_p, C.POINTER(Contigs)]
+    L.pp_fasta_name.restype = C.c_char_p
+    L.pp_fasta_name.argtypes = [C.c_void_p, C.c_uint32]
+    L.pp_fasta_description.restype = C.c_char_p
+    L.pp_fasta_description.argtypes = [C.c_void_p, C.c_uint32]
+    L.pp_pack_create.restype = C.c_void_p
+    L.pp_pack_create.argtypes = [C.c_void_p, C.c_int]
+    L.pp_pack_free.argtypes = [C.c_void_p]
+    L.pp_pack_add_sam_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.pp_pack_add_sam_text.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p]
+    L.pp_pack_finish.argtypes = [C.c_void_p, C.POINTER(Alignments)]
+    L.pp_pack_error.restype = C.c_char_p
+    L.pp_pack_error.argtypes = [C.c_void_p]
+    L.pp_pack_unknown_ref.restype = C.c_char_p
+    L.pp_pack_unknown_ref.argtypes = [C.c_void_p, C.c_uint64]
+    L.pp_pack_read_name.restype = C.c_char_p
+    L.pp_pack_read_name.argtypes = [C.c_void_p, C.c_uint64]
+    L.pp_pack_file_stats.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.pp_polish_files.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(PolishParams),
+                                  C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]
+    L.pp_free.argtypes = [C.c_void_p]
+    if hasattr(L, "pp_filter"):
+        L.pp_filter.argtypes = [C.c_void_p, C.POINTER(FilterMate), C.POINTER(FilterMate), C.POINTER(FilterParams),
+                                C.POINTER(FilterResult)]
+    if hasattr(L, "pp_filter_files"):
+        L.pp_filter_files.argtypes = [C.c_void_p] + [C.c_char_p] * 5 + [C.c_double, C.c_double, C.c_int]
+    _lib = L
+    return L
+
+
+def _params(fraction_invalid=0.2, fraction_valid=0.5, max_errors=10, min_depth=5, careful=False):
+    return PolishParams(fraction_invalid, fraction_valid, max_errors, min_depth, int(bool(careful)))
+
+
+class Fasta:
+    """misc::load_fasta (misc.rs:38-167) result, host side."""
+
+    def __init__(self, path):
+        L = lib()
+        err = C.create_string_buffer(1024)
+        self.h = L.pp_fasta_load(str(path).encode(), err, 1024)
+        if not self.h:
+            raise PolypolishError(PP_ERR_INPUT, err.value.decode())
+        self.view = Contigs()
+        L.pp_fasta_view(self.h, C.byref(self.view))
+        n = self.view.n_contigs
+        self.names = [L.pp_fasta_name(self.h, i).decode() for i in range(n)]
+        self.descriptions = [L.pp_fasta_description(self.h, i).decode() for i in range(n)]
+        self.off = np.ctypeslib.as_array(C.cast(self.view.off, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+
+    def sequence(self, i):
+        return C.string_at(self.view.bases + int(self.off[i]), int(self.off[i + 1] - self.off[i]))
+
+    def records(self):
+        return [(self.names[i], self.descriptions[i], self.sequence(i).decode("latin-1")) for i in range(len(self.names))]
+
+    def close(self):
+        if self.h:
+            lib().pp_fasta_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def load_fasta(path):
+    return Fasta(path)
+
+
+class Packed:
+    """SAM text -> pp_alignments (host side; sam_pack.cpp)."""
+
+    def __init__(self, fasta, careful=False):
+        self.fasta = fasta
+        self.h = lib().pp_pack_create(fasta.h, int(bool(careful)))
+        self.view = None
+
+    def _check(self, rc):
+        if rc != PP_OK:
+            raise PolypolishError(rc, lib().pp_pack_error(self.h).decode())
+
+    def add_file(self, path):
+        self._check(lib().pp_pack_add_sam_file(self.h, str(path).encode()))
+
+    def add_text(self, text, name="<memory>"):
+        if isinstance(text, str):
+            text = text.encode("latin-1")
+        self._check(lib().pp_pack_add_sam_text(self.h, text, len(text), name.encode()))
+
+    def finish(self):
+        self.view = Alignments()
+        self._check(lib().pp_pack_finish(self.h, C.byref(self.view)))
+        return self.view
+
+    def arrays(self):
+        """numpy views of the SoA arrays (valid while this object lives)."""
+        v = self.view
+        n = v.n_aln
+
+        def arr(ptr, ct, cnt):
+            if cnt == 0:
+                return np.zeros(0, dtype=ct)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(cnt,))
+        return dict(contig=arr(v.contig, C.c_uint32, n), ref_start=arr(v.ref_start, C.c_uint32, n),
+                    read_id=arr(v.read_id, C.c_uint32, n), seq_off=arr(v.seq_off, C.c_uint32, n),
+                    seq_len=arr(v.seq_len, C.c_uint16, n), cigar_off=arr(v.cigar_off, C.c_uint32, n),
+                    n_cigar=arr(v.n_cigar, C.c_uint16, n), nm=arr(v.nm, C.c_uint32, n), flags=arr(v.flags, C.c_uint8, n),
+                    cigar_ops=arr(v.cigar_ops, C.c_uint32, v.n_cigar_ops), seq_pool=arr(v.seq_pool, C.c_uint8, v.seq_pool_bytes),
+                    seq_bits=v.seq_bits, n_reads=v.n_reads)
+
+    def read_name(self, aln):
+        return lib().pp_pack_read_name(self.h, aln).decode()
+
+    def close(self):
+        if self.h:
+            lib().pp_pack_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pack_sams(fasta, sams, careful=False):
+    p = Packed(fasta, careful)
+    for s in sams:
+        p.add_file(s)
+    p.finish()
+    return p
+
+
+class Context:
+    """One pp_ctx = one GPU."""
+
+    def __init__(self, device=0):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.pp_create(device, C.byref(h))
+        if rc != PP_OK:
+            raise PolypolishError(rc, "pp_create failed: no usable sm_100 CUDA device (there is no CPU fallback)")
+        self.h = h
+
+    def _err(self, rc):
+        return PolypolishError(rc, lib().pp_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            lib().pp_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- packed level -------------------------------------------------------------------------------------
+    def _result(self, n_contigs, cap):
+        res = PolishResult()
+        keep = dict(off=np.zeros(n_contigs + 1, dtype=np.uint64), bases=np.zeros(max(1, cap), dtype=np.uint8),
+                    changed=np.zeros(n_contigs, dtype=np.uint64), zero=np.zeros(n_contigs, dtype=np.uint64))
+        res.out_off = keep["off"].ctypes.data
+        res.out_bases = keep["bases"].ctypes.data
+        res.out_cap = cap
+        res.changed = keep["changed"].ctypes.data
+        res.zero_depth = keep["zero"].ctypes.data
+        return res, keep
+
+    def _finish(self, res, keep, n_contigs):
+        off = keep["off"]
+        seqs = [keep["bases"][int(off[i]):int(off[i + 1])].tobytes() for i in range(n_contigs)]
+        return dict(sequences=seqs, changed=keep["changed"].tolist(), zero_depth=keep["zero"].tolist(),
+                    n_aln_used=res.n_aln_used, out_len=res.out_len, timing=res.timing.as_dict())
+
+    def polish_packed(self, contigs, alns, **opts):
+        """pp_polish: host SoA in, host bases out (H2D / D2H inside)."""
+        prm = _params(**opts)
+        G = int(np.ctypeslib.as_array(C.cast(contigs.off, C.POINTER(C.c_uint64)), shape=(contigs.n_contigs + 1,))[-1])
+        cap = G + (1 << 20)
+        for _ in range(2):
+            res, keep = self._result(contigs.n_contigs, cap)
+            rc = lib().pp_polish(self.h, C.byref(contigs), C.byref(alns), C.byref(prm), C.byref(res))
+            if rc == PP_ERR_ARG and res.out_len > cap:
+                cap = int(res.out_len)
+                continue
+            break
+        if rc != PP_OK:
+            e = self._err(rc)
+            e.error_aln = res.error_aln
+            raise e
+        return self._finish(res, keep, contigs.n_contigs)
+
+    def upload(self, contigs, alns):
+        rc = lib().pp_dataset_upload(self.h, C.byref(contigs), C.byref(alns))
+        if rc != PP_OK:
+            raise self._err(rc)
+        self._nc = contigs.n_contigs
+        self._G = int(np.ctypeslib.as_array(C.cast(contigs.off, C.POINTER(C.c_uint64)), shape=(contigs.n_contigs + 1,))[-1])
+
+    def polish_resident(self, fetch=True, **opts):
+        prm = _params(**opts)
+        cap = self._G + (1 << 20) if fetch else 0
+        for _ in range(2):
+            if fetch:
+                res, keep = self._result(self._nc, cap)
+            else:
+                res, keep = PolishResult(), None
+            rc = lib().pp_polish_resident(self.h, C.byref(prm), C.byref(res))
+            if fetch and rc == PP_ERR_ARG and res.out_len > cap:
+                cap = int(res.out_len)
+                continue
+            break
+        if rc != PP_OK:
+            raise self._err(rc)
+        if not fetch:
+            return dict(n_aln_used=res.n_aln_used, out_len=res.out_len, timing=res.timing.as_dict())
+        return self._finish(res, keep, self._nc)
+
+    # ---- file level (what the CLI does) ----------------------------------------------------------------------
+    def polish_files(self, assembly, sams, debug=None, verbose=False, **opts):
+        prm = _params(**opts)
+        arr = (C.c_char_p * max(1, len(sams)))(*[str(s).encode() for s in sams])
+        out = C.c_void_p()
+        n = C.c_uint64()
+        rc = lib().pp_polish_files(self.h, str(assembly).encode(), arr, len(sams), C.byref(prm),
+                                   str(debug).encode() if debug else None, C.byref(out), C.byref(n), int(verbose))
+        if rc != PP_OK:
+            raise self._err(rc)
+        data = C.string_at(out, n.value)
+        lib().pp_free(out)
+        return data
+
+    def filter_files(self, in1, in2, out1, out2, orientation="auto", low=0.1, high=99.9, verbose=False):
+        rc = lib().pp_filter_files(self.h, str(in1).encode(), str(in2).encode(), str(out1).encode(), str(out2).encode(),
+                                   orientation.encode(), low, high, int(verbose))
+        if rc != PP_OK:
+            raise self._err(rc)
+
+
+def polish_files(assembly, sams, device=0, **kw):
+    with Context(device) as ctx:
+        return ctx.polish_files(assembly, sams, **kw)
+
+
+def polish(assembly, sam, debug=None, fraction_invalid=0.2, fraction_valid=0.5, max_errors=10, min_depth=5,
+           careful=False, device=0):
+    """`polypolish polish` (main.rs:78-108, polish.rs:26-38): returns the bytes the reference prints to stdout."""
+    return polish_files(assembly, list(sam), device=device, debug=debug, fraction_invalid=fraction_invalid,
+                        fraction_valid=fraction_valid, max_errors=max_errors, min_depth=min_depth, careful=careful)
+
+
+def filter_sams(in1, in2, out1, out2, orientation="auto", low=0.1, high=99.9, device=0):
+    """`polypolish filter` (main.rs:47-75, filter.rs:26-37)."""
+    with Context(device) as ctx:
+        ctx.filter_files(in1, in2, out1, out2, orientation, low, high)
+
+
+# ---- synthetic inputs (measurement / test support; csrc/synth.cpp) -------------------------------------------
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_contigs", C.c_uint32), ("read_len", C.c_uint32), ("contig_len", C.c_uint64),
+                ("depth", C.c_double), ("insert_mean", C.c_double), ("insert_sd", C.c_double),
+                ("draft_error_rate", C.c_double), ("seq_sub_rate", C.c_double), ("seq_indel_rate", C.c_double),
+                ("repeat_fraction", C.c_double), ("clip_rate", C.c_double), ("highnm_rate", C.c_double),
+                ("unaligned_rate", C.c_double)]
+
+
+class Synth:
+    """Deterministic synthetic contigs + bwa-mem -a style paired SAM."""
+
+    def __init__(self, seed=1, n_contigs=1, contig_len=50_000, depth=100.0, read_len=150, insert_mean=400.0,
+                 insert_sd=40.0, draft_error_rate=1e-4, seq_sub_rate=2e-3, seq_indel_rate=1e-4, repeat_fraction=0.03,
+                 clip_rate=0.005, highnm_rate=0.005, unaligned_rate=0.005):
+        L = lib()
+        L.pp_synth_create.restype = C.c_void_p
+        L.pp_synth_create.argtypes = [C.POINTER(SynthParams)]
+        L.pp_synth_free.argtypes = [C.c_void_p]
+        L.pp_synth_total_bp.restype = C.c_uint64
+        L.pp_synth_total_bp.argtypes = [C.c_void_p]
+        L.pp_synth_n_pairs.restype = C.c_uint64
+        L.pp_synth_n_pairs.argtypes = [C.c_void_p]
+        L.pp_synth_write_fasta.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.pp_synth_write_sam.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        L.pp_synth_fasta.restype = C.c_void_p
+        L.pp_synth_fasta.argtypes = [C.c_void_p]
+        L.pp_synth_feed_pack.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        prm = SynthParams(seed, n_contigs, read_len, contig_len, depth, insert_mean, insert_sd, draft_error_rate,
+                          seq_sub_rate, seq_indel_rate, repeat_fraction, clip_rate, highnm_rate, unaligned_rate)
+        self.h = L.pp_synth_create(C.byref(prm))
+        if not self.h:
+            raise PolypolishError(PP_ERR_ARG, "pp_synth_create: bad parameters")
+        self.total_bp = L.pp_synth_total_bp(self.h)
+        self.n_pairs = L.pp_synth_n_pairs(self.h)
+
+    def write(self, directory):
+        """draft FASTA + one SAM per mate; returns (fasta, [sam1, sam2])."""
+        d = str(directory)
+        fa, s1, s2 = os.path.join(d, "draft.fasta"), os.path.join(d, "reads_1.sam"), os.path.join(d, "reads_2.sam")
+        for rc in (lib().pp_synth_write_fasta(self.h, fa.encode(), 0), lib().pp_synth_write_sam(self.h, 1, s1.encode()),
+                   lib().pp_synth_write_sam(self.h, 2, s2.encode())):
+            if rc != PP_OK:
+                raise PolypolishError(rc, "synthetic data could not be written")
+        return fa, [s1, s2]
+
+    def write_truth(self, path):
+        lib().pp_synth_write_fasta(self.h, str(path).encode(), 1)
+
+    def fasta(self):
+        f = Fasta.__new__(Fasta)
+        f.h = lib().pp_synth_fasta(self.h)
+        f.view = Contigs()
+        lib().pp_fasta_view(f.h, C.byref(f.view))
+        n = f.view.n_contigs
+        f.names = [lib().pp_fasta_name(f.h, i).decode() for i in range(n)]
+        f.descriptions = [lib().pp_fasta_description(f.h, i).decode() for i in range(n)]
+        f.off = np.ctypeslib.as_array(C.cast(f.view.off, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        return f
+
+    def pack(self, fasta=None, careful=False):
+        """The packed SoA of both mates (mate-1 file then mate-2 file) without materialising SAM text on disk."""
+        fasta = fasta or self.fasta()
+        p = Packed(fasta, careful)
+        for mate in (1, 2):
+            rc = lib().pp_synth_feed_pack(self.h, mate, p.h)
+            p._check(rc)
+        p.finish()
+        return p
+
+    def close(self):
+        if self.h:
+            lib().pp_synth_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

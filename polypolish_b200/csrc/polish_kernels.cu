@@ -1,0 +1,1222 @@
+// polish_kernels.cu — the polish hot path as sm_100a kernels + the C-ABI entry points that drive them.
+//
+// Replaces, on the device (reference = /root/reference/src):
+//   process_one_read            alignment.rs:275-305  -> k_classify (goodness, k = #good per read)
+//   get_read_bases_for_each_target_base + trim_bases_for_homopolymers
+//                               alignment.rs:175-201, 364-378 -> k_scatter (CIGAR walk, right-end trim)
+//   Pileup::add_alignment / PileupBase::add_seq   pileup.rs:189-200, 56-65 -> k_scatter (+ k_depth_fixup)
+//   PileupBase::get_polished_seq + bankers_rounding pileup.rs:67-134, misc.rs:208-215 -> k_vote
+//   polish_one_sequence's join + replace("-","")  polish.rs:185-188 -> k_vote (stream compaction)
+//
+// Design (DESIGN.md has the derivation): the reference adds one counter per aligned base (5e8 increments for
+// 5 Mbp x 100x), which on any GPU is bound by atomic throughput, not by HBM.  Here the pileup of a position is
+// kept in a form that needs ~3 atomics per ALIGNMENT instead of ~150:
+//   * cover[p]  = number of good alignments whose kept entries include p  -> interval add (+v at start,
+//     -v at end) into a difference array, prefix-summed inside k_vote;
+//   * explicit[p][allele] = entries whose allele differs from the draft base -> one atomic per mismatch
+//     (~0.3 % of bases); count[draft base] = cover - sum(explicit);
+//   * alleles other than A,C,G,T,"-" (N / IUPAC bases, insertions) -> appended as records, sorted by position,
+//     counted exactly (string compare) by the vote's slow path;
+//   * depth: where every covering alignment has k == 1 the f64 depth equals cover exactly; positions covered
+//     by a multi-mapped read (k != 1) get the reference's sequential f64 sum re-done in SAM order by
+//     k_depth_fixup (ordered walk over the alignments binned to that 128-position tile).
+// All of it is integer / byte work bounded by HBM bandwidth: no tensor cores.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "pp_internal.h"
+
+#define PP_TILE_SHIFT 7              // depth fix-up tile = 128 positions
+#define PP_TILE (1u << PP_TILE_SHIFT)
+#define SC_THREADS 256               // scatter CTA
+#define SC_STAGE 768                 // smem staging entries (fix list / other records) per CTA
+#define VT_THREADS 256
+#define VT_ITEMS 8
+#define VT_CHUNK (VT_THREADS * VT_ITEMS)
+
+enum : unsigned {
+    ERR_UNKNOWN_CONTIG = 1, ERR_SEQ_MISMATCH = 2, ERR_BAD_OP = 3, ERR_OOB = 4, ERR_NOSEQ = 5
+};
+enum : unsigned { FL_OTHER_OVF = 1, FL_FIX_OVF = 2, FL_COUNTER_OVF = 4, FL_OUT_OVF = 8 };
+
+struct DevStatus {
+    unsigned long long err;          // min over (aln << 8 | code); ~0 = none
+    unsigned long long other_len;    // sum of other-record lengths (bounds the output size)
+    unsigned long long n_used;       // good alignments
+    unsigned long long out_len;      // polished bases
+    unsigned int other_count, fix_count;
+    unsigned int flags;
+    unsigned int ticket;             // k_vote chunk ticket
+};
+
+struct DevData {                     // everything the kernels read, by value
+    // alignments
+    unsigned long long n_aln;
+    const uint32_t *contig, *ref_start, *read_id, *seq_off, *cigar_off, *nm, *cigar_ops;
+    const uint16_t *seq_len, *n_cigar;
+    const uint8_t *flags, *seq_pool;
+    // assembly
+    const uint8_t* draft;            // ASCII
+    const unsigned long long* contig_off;
+    uint32_t n_contigs;
+    uint32_t G;                      // total positions
+    // work
+    uint8_t* aux;                    // bit0 good, bit1 group has > 1 aligned record
+    uint32_t* k;                     // [n_reads] good alignments per read
+    unsigned long long* draft_nib;   // 4-bit draft codes, 16 per word
+    unsigned long long* diff;        // [G+1] lo32 cover, hi32 covering alignments with k != 1
+    unsigned long long* ex;          // [G] explicit A,C,G,T counts, 16 bits each
+    uint32_t* delother;              // [G] lo16 "-" count, hi16 other-allele record count
+    uint32_t* tileflag;              // bitmap, tiles that may hold k != 1 coverage
+    double* depth_fix;               // [G] ordered depth for flagged tiles
+    unsigned long long *fix_key, *fix_val;      // (tile<<32|aln) , (gstart<<32|n_kept)
+    uint32_t* oth_key;               // gpos
+    unsigned long long* oth_val;     // aln<<32 | start<<16 | len
+    uint32_t fix_cap, oth_cap;
+    DevStatus* st;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void report_error(DevStatus* st, unsigned long long aln, unsigned code) {
+    atomicMin(&st->err, (aln << 8) | code);
+}
+
+__constant__ uint8_t c_comp[256];      // misc.rs:170-182 complement_base on upper-cased bytes
+__constant__ char c_nib2asc[16] = {'=', 'A', 'C', 'M', 'G', 'R', 'S', 'V', 'T', 'W', 'Y', 'H', 'K', 'D', 'B', 'N'};
+
+__device__ __forceinline__ uint32_t brev4(uint32_t c) {   // complement of a BAM nibble = 4-bit reversal
+    return __brev(c) >> 28;
+}
+
+// Sequence access policies.  sym = 4-bit code (SEQ4) or upper-cased ASCII byte (SEQ8).
+template <int BITS> struct Seq;
+template <> struct Seq<4> {
+    static __device__ __forceinline__ uint32_t read_sym(const uint8_t* pool, uint32_t off_blk, uint32_t len, bool rc, uint32_t i) {
+        uint32_t j = rc ? (len - 1 - i) : i;
+        uint32_t b = pool[(size_t)off_blk * (PP_SEQ_BLOCK / 2) + (j >> 1)];
+        uint32_t c = (b >> ((j & 1) * 4)) & 15u;
+        return rc ? brev4(c) : c;
+    }
+    static __device__ __forceinline__ uint32_t draft_sym(const DevData& d, uint32_t pos) {
+        return (uint32_t)(d.draft_nib[pos >> 4] >> ((pos & 15) * 4)) & 15u;
+    }
+    static __device__ __forceinline__ bool is_del(uint32_t) { return false; }
+    static __device__ __forceinline__ int acgt(uint32_t s) { return s == 1 ? 0 : s == 2 ? 1 : s == 4 ? 2 : s == 8 ? 3 : -1; }
+    static __device__ __forceinline__ uint8_t ascii(uint32_t s) { return (uint8_t)c_nib2asc[s & 15]; }
+};
+template <> struct Seq<8> {
+    static __device__ __forceinline__ uint32_t read_sym(const uint8_t* pool, uint32_t off_blk, uint32_t len, bool rc, uint32_t i) {
+        uint32_t j = rc ? (len - 1 - i) : i;
+        uint32_t b = pool[(size_t)off_blk * PP_SEQ_BLOCK + j];
+        return rc ? c_comp[b] : b;
+    }
+    static __device__ __forceinline__ uint32_t draft_sym(const DevData& d, uint32_t pos) {
+        uint32_t b = d.draft[pos];
+        return b == '-' ? 0u : b;          // a '-' in the draft never "matches" a read base: both count as "-"
+    }
+    static __device__ __forceinline__ bool is_del(uint32_t s) { return s == '-'; }   // the 1-char string "-"
+    static __device__ __forceinline__ int acgt(uint32_t s) { return s == 'A' ? 0 : s == 'C' ? 1 : s == 'G' ? 2 : s == 'T' ? 3 : -1; }
+    static __device__ __forceinline__ uint8_t ascii(uint32_t s) { return (uint8_t)s; }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// k_draft_nib: ASCII draft -> 4-bit codes (0 = not one of the 15 letters: never equals a read code)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t asc2nib(uint32_t c) {
+    switch (c) {
+        case 'A': return 1; case 'C': return 2; case 'M': return 3; case 'G': return 4; case 'R': return 5;
+        case 'S': return 6; case 'V': return 7; case 'T': return 8; case 'W': return 9; case 'Y': return 10;
+        case 'H': return 11; case 'K': return 12; case 'D': return 13; case 'B': return 14; case 'N': return 15;
+        default: return 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_draft_nib(const uint8_t* __restrict__ draft, uint32_t G,
+                                                   unsigned long long* __restrict__ nib, uint32_t n_words) {
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+        size_t base = (size_t)w * 16;
+        unsigned long long v = 0;
+        if (base + 16 <= G) {
+            uint4 q = *reinterpret_cast<const uint4*>(draft + base);   // draft is 16 B aligned
+            uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v |= (unsigned long long)asc2nib((ws[i >> 2] >> ((i & 3) * 8)) & 255u) << (4 * i);
+        } else {
+            for (int i = 0; i < 16; ++i)
+                if (base + i < G) v |= (unsigned long long)asc2nib(draft[base + i]) << (4 * i);
+        }
+        nib[w] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_classify: one thread per alignment.  good (alignment.rs:283-287), k (:288), --careful (:277-279),
+// and the tile marks for groups with more than one aligned record (superset of k != 1 coverage).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_classify(DevData d, uint32_t max_errors, int careful) {
+    unsigned long long used = 0;
+    for (unsigned long long a = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; a < d.n_aln;
+         a += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t rid = d.read_id[a];
+        bool multi = (a > 0 && d.read_id[a - 1] == rid) || (a + 1 < d.n_aln && d.read_id[a + 1] == rid);
+        uint32_t co = d.cigar_off[a], nc = d.n_cigar[a];
+        if (nc == 0) { d.aux[a] = 0; report_error(d.st, a, ERR_BAD_OP); continue; }   // the packer never emits this
+        uint32_t f = d.cigar_ops[co] & 15u, l = d.cigar_ops[co + nc - 1] & 15u;
+        uint8_t fl = d.flags[a];
+        bool good = (f == PP_OP_M || f == PP_OP_EQ) && (l == PP_OP_M || l == PP_OP_EQ) &&
+                    d.nm[a] <= max_errors && !(fl & PP_FLAG_ZPFAIL) && !(careful && multi);
+        d.aux[a] = (uint8_t)((good ? 1 : 0) | (multi ? 2 : 0));
+        if (!good) continue;
+        used++;
+        atomicAdd(&d.k[rid], 1u);
+        if (multi) {
+            uint32_t c = d.contig[a];
+            if (c == PP_CONTIG_UNKNOWN) continue;              // reported by k_scatter
+            unsigned long long reflen = 0;
+            for (uint32_t i = 0; i < nc; ++i) {
+                uint32_t op = d.cigar_ops[co + i];
+                uint32_t o = op & 15u;
+                if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X || o == PP_OP_D) reflen += op >> 4;
+            }
+            unsigned long long gs = d.contig_off[c] + d.ref_start[a];
+            unsigned long long ge = gs + reflen;               // exclusive, before trimming
+            unsigned long long cend = d.contig_off[c + 1];
+            if (ge > cend) ge = cend;
+            if (gs >= ge) continue;
+            for (unsigned long long t = gs >> PP_TILE_SHIFT; t <= ((ge - 1) >> PP_TILE_SHIFT); ++t)
+                atomicOr(&d.tileflag[t >> 5], 1u << (t & 31));
+        }
+    }
+    // block reduce of `used`
+    __shared__ unsigned long long s_used;
+    if (threadIdx.x == 0) s_used = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) used += __shfl_down_sync(0xffffffffu, used, o);
+    if ((threadIdx.x & 31) == 0 && used) atomicAdd(&s_used, used);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_used) atomicAdd(&d.st->n_used, s_used);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_scatter
+// ------------------------------------------------------------------------------------------------------
+struct ScatterShared {
+    uint32_t gstart[SC_THREADS], cend[SC_THREADS], seqoff[SC_THREADS], cigoff[SC_THREADS];
+    uint16_t len[SC_THREADS], ncig[SC_THREADS];
+    uint8_t fl[SC_THREADS];                       // bit0 good, bit1 rc, bit2 k != 1
+    unsigned long long fix_key[SC_STAGE], fix_val[SC_STAGE];
+    unsigned long long oth_val[SC_STAGE];
+    uint32_t oth_key[SC_STAGE];
+    uint32_t n_fix, n_oth, base_fix, base_oth;
+    unsigned long long oth_len;
+};
+
+template <int BITS> struct Scatter {
+    const DevData& d;
+    ScatterShared& sh;
+
+    __device__ __forceinline__ void push_other(uint32_t pos, unsigned long long aln, uint32_t start, uint32_t len) {
+        atomicAdd(&d.delother[pos], 1u << 16);
+        atomicAdd(&sh.oth_len, (unsigned long long)len);
+        unsigned long long v = (aln << 32) | ((unsigned long long)(start & 0xFFFFu) << 16) | (len & 0xFFFFu);
+        uint32_t s = atomicAdd(&sh.n_oth, 1u);
+        if (s < SC_STAGE) { sh.oth_key[s] = pos; sh.oth_val[s] = v; return; }
+        uint32_t g = atomicAdd(&d.st->other_count, 1u);
+        if (g < d.oth_cap) { d.oth_key[g] = pos; d.oth_val[g] = v; }
+        else atomicOr(&d.st->flags, FL_OTHER_OVF);
+    }
+    __device__ __forceinline__ void push_fix(uint32_t tile, unsigned long long aln, uint32_t gstart, uint32_t nkept) {
+        unsigned long long k = ((unsigned long long)tile << 32) | aln;
+        unsigned long long v = ((unsigned long long)gstart << 32) | nkept;
+        uint32_t s = atomicAdd(&sh.n_fix, 1u);
+        if (s < SC_STAGE) { sh.fix_key[s] = k; sh.fix_val[s] = v; return; }
+        uint32_t g = atomicAdd(&d.st->fix_count, 1u);
+        if (g < d.fix_cap) { d.fix_key[g] = k; d.fix_val[g] = v; }
+        else atomicOr(&d.st->flags, FL_FIX_OVF);
+    }
+    // one single-base entry at reference position pos carrying read symbol s (read index ri)
+    __device__ __forceinline__ void count_base(uint32_t pos, uint32_t s, unsigned long long aln, uint32_t ri) {
+        if (Seq<BITS>::is_del(s)) { atomicAdd(&d.delother[pos], 1u); return; }
+        uint32_t ds = Seq<BITS>::draft_sym(d, pos);
+        if (s == ds) return;                                   // counted implicitly: cover - explicit
+        int c = Seq<BITS>::acgt(s);
+        if (c >= 0) atomicAdd(&d.ex[pos], 1ull << (16 * c));
+        else push_other(pos, aln, ri, 1);
+    }
+    // interval add + fix-list membership for an alignment that keeps entries [gstart, gstart + nkept)
+    __device__ __forceinline__ void add_interval(uint32_t lane8, unsigned long long aln, uint32_t gstart, uint32_t nkept, bool multi) {
+        if (nkept == 0) return;
+        if (lane8 == 0) {
+            unsigned long long v = 1ull | (multi ? (1ull << 32) : 0ull);
+            atomicAdd(&d.diff[gstart], v);
+            atomicAdd(&d.diff[gstart + nkept], 0ull - v);
+        }
+        uint32_t t0 = gstart >> PP_TILE_SHIFT, t1 = (gstart + nkept - 1) >> PP_TILE_SHIFT;
+        for (uint32_t t = t0 + lane8; t <= t1; t += 8)
+            if ((d.tileflag[t >> 5] >> (t & 31)) & 1u) push_fix(t, aln, gstart, nkept);
+    }
+};
+
+#define GROUP_MASK(lane) (0xFFu << ((lane) & 24))
+
+__device__ __forceinline__ unsigned long long shfl64(unsigned mask, unsigned long long v, int src) {
+    uint32_t lo = __shfl_sync(mask, (uint32_t)v, src, 8);
+    uint32_t hi = __shfl_sync(mask, (uint32_t)(v >> 32), src, 8);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+__device__ __forceinline__ unsigned long long nibble_nonzero(unsigned long long x) {   // bit 4j set iff nibble j != 0
+    return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x1111111111111111ull;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
+    __shared__ ScatterShared sh;
+    Scatter<BITS> S{d, sh};
+    const uint32_t tid = threadIdx.x, lane = tid & 31, lane8 = tid & 7, grp = tid >> 3;
+    const unsigned gmask = GROUP_MASK(lane);
+    const unsigned long long n_blocks = (d.n_aln + SC_THREADS - 1) / SC_THREADS;
+
+    for (unsigned long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        // ---- stage 1: coalesced metadata loads, one alignment per thread
+        if (tid == 0) { sh.n_fix = 0; sh.n_oth = 0; sh.oth_len = 0; }
+        unsigned long long a = blk * SC_THREADS + tid;
+        uint8_t f = 0;
+        if (a < d.n_aln && (d.aux[a] & 1)) {
+            uint32_t c = d.contig[a];
+            uint8_t fl = d.flags[a];
+            if (c == PP_CONTIG_UNKNOWN) report_error(d.st, a, ERR_UNKNOWN_CONTIG);
+            else if (fl & PP_FLAG_NOSEQ) report_error(d.st, a, ERR_NOSEQ);
+            else {
+                unsigned long long gs = d.contig_off[c] + d.ref_start[a];
+                unsigned long long ce = d.contig_off[c + 1];
+                if (gs >= ce) report_error(d.st, a, ERR_OOB);
+                else {
+                    sh.gstart[tid] = (uint32_t)gs;
+                    sh.cend[tid] = (uint32_t)ce;
+                    sh.seqoff[tid] = d.seq_off[a];
+                    sh.cigoff[tid] = d.cigar_off[a];
+                    sh.len[tid] = d.seq_len[a];
+                    sh.ncig[tid] = d.n_cigar[a];
+                    f = (uint8_t)(1 | ((fl & PP_FLAG_RC) ? 2 : 0) | (d.k[d.read_id[a]] != 1 ? 4 : 0));
+                }
+            }
+        }
+        sh.fl[tid] = f;
+        __syncthreads();
+
+        // ---- stage 2: 8 lanes per alignment, 8 alignments per lane group
+        for (uint32_t i = 0; i < 8; ++i) {
+            const uint32_t s = grp * 8 + i;
+            const uint32_t fl = sh.fl[s];
+            if (!(fl & 1)) continue;
+            const unsigned long long aln = blk * SC_THREADS + s;
+            const uint32_t gstart = sh.gstart[s], cend = sh.cend[s], seqoff = sh.seqoff[s], cigoff = sh.cigoff[s];
+            const uint32_t len = sh.len[s], ncig = sh.ncig[s];
+            const bool rc = fl & 2, multi = fl & 4;
+
+            if (BITS == 4 && ncig == 1 && !rc && len <= 256 && len > 0) {
+                // ================= fast path: one M/= run, stored strand, <= 256 bases =================
+                const uint32_t op0 = d.cigar_ops[cigoff];
+                if ((op0 >> 4) != len) { if (lane8 == 0) report_error(d.st, aln, ERR_SEQ_MISMATCH); continue; }
+                const uint32_t b0 = lane8 * 32;
+                unsigned long long r0 = 0, r1 = 0;
+                if (b0 < len) {
+                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(d.seq_pool + (size_t)seqoff * 16) + lane8);
+                    r0 = ((unsigned long long)q.y << 32) | q.x;
+                    r1 = ((unsigned long long)q.w << 32) | q.z;
+                }
+                // right-end homopolymer trim (alignment.rs:364-378): run of entries equal to the last base
+                const uint32_t li = len - 1;
+                uint32_t last = (uint32_t)(((li & 16) ? r1 : r0) >> ((li & 15) * 4)) & 15u;
+                last = __shfl_sync(gmask, last, li >> 5, 8);
+                const unsigned long long rep = 0x1111111111111111ull * last;
+                const unsigned long long nz0 = nibble_nonzero(r0 ^ rep), nz1 = nibble_nonzero(r1 ^ rep);
+                uint32_t run = 0;
+                {
+                    int sc = (int)(li >> 4);
+                    uint32_t idx = li & 15;
+                    for (;;) {
+                        unsigned long long w = shfl64(gmask, (sc & 1) ? nz1 : nz0, sc >> 1);
+                        unsigned long long m = (idx == 15) ? w : (w & ((1ull << (4 * (idx + 1))) - 1));
+                        if (m) { run += idx - (uint32_t)((63 - __clzll((long long)m)) >> 2); break; }
+                        run += idx + 1;
+                        if (sc == 0) break;
+                        --sc; idx = 15;
+                    }
+                }
+                const uint32_t nkept = (len - run >= 1) ? (len - run - 1) : 0;
+                if (gstart + nkept > cend) { if (lane8 == 0) report_error(d.st, aln, ERR_OOB); continue; }
+                S.add_interval(lane8, aln, gstart, nkept, multi);
+                // mismatches against the draft, 32 bases per lane
+                if (b0 < nkept) {
+                    const uint32_t o = gstart + b0;
+                    const unsigned long long* w = d.draft_nib + (o >> 4);
+                    const uint32_t shb = (o & 15) * 4;
+                    const unsigned long long w0 = w[0], w1 = w[1], w2 = w[2];
+                    const unsigned long long d0 = shb ? ((w0 >> shb) | (w1 << (64 - shb))) : w0;
+                    const unsigned long long d1 = shb ? ((w1 >> shb) | (w2 << (64 - shb))) : w1;
+                    const uint32_t vc = min(nkept - b0, 32u);
+                    unsigned long long m0 = nibble_nonzero(r0 ^ d0), m1 = nibble_nonzero(r1 ^ d1);
+                    if (vc < 16) { m0 &= (1ull << (4 * vc)) - 1; m1 = 0; }
+                    else if (vc < 32) m1 &= (1ull << (4 * (vc - 16))) - 1;
+                    while (m0) {
+                        const uint32_t j = (uint32_t)(__ffsll((long long)m0) - 1) >> 2;
+                        m0 &= m0 - 1;
+                        const uint32_t code = (uint32_t)(r0 >> (4 * j)) & 15u;
+                        const int c = Seq<4>::acgt(code);
+                        if (c >= 0) atomicAdd(&d.ex[o + j], 1ull << (16 * c));
+                        else S.push_other(o + j, aln, b0 + j, 1);
+                    }
+                    while (m1) {
+                        const uint32_t j = (uint32_t)(__ffsll((long long)m1) - 1) >> 2;
+                        m1 &= m1 - 1;
+                        const uint32_t code = (uint32_t)(r1 >> (4 * j)) & 15u;
+                        const int c = Seq<4>::acgt(code);
+                        if (c >= 0) atomicAdd(&d.ex[o + 16 + j], 1ull << (16 * c));
+                        else S.push_other(o + 16 + j, aln, b0 + 16 + j, 1);
+                    }
+                }
+                continue;
+            }
+
+            // ================= general path (indels, =/X runs, reverse-complemented SEQ="*", 8-bit pool) =====
+            // pass 1 (uniform over the 8 lanes): validate ops, E = entries, read bases consumed
+            const uint32_t* ops = d.cigar_ops + cigoff;
+            unsigned long long E = 0, R = 0;
+            bool bad = false;
+            for (uint32_t p = 0; p < ncig; ++p) {
+                const uint32_t op = ops[p], o = op & 15u, l = op >> 4;
+                if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X) { E += l; R += l; }
+                else if (o == PP_OP_I) R += l;
+                else if (o == PP_OP_D) E += l;
+                else bad = true;                                   // alignment.rs:187-193
+            }
+            if (bad) { if (lane8 == 0) report_error(d.st, aln, ERR_BAD_OP); continue; }
+            if (R != len) { if (lane8 == 0) report_error(d.st, aln, ERR_SEQ_MISMATCH); continue; }   // :195-198
+            // pass 2: trim.  Walk entries from the right; stop at the first entry that is not the single base `last`.
+            const uint32_t last = Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, len - 1);
+            unsigned long long run = 0;
+            {
+                uint32_t ri = len;            // read index just past the current entry's M-part
+                uint32_t pend = 0;            // inserted bases that extend the entry being visited
+                bool stop = false;
+                for (int p = (int)ncig - 1; p >= 0 && !stop; --p) {
+                    const uint32_t op = ops[p], o = op & 15u, l = op >> 4;
+                    if (o == PP_OP_I) { pend += l; ri -= l; continue; }
+                    if (o == PP_OP_D) {
+                        // entries (ri, ri + pend): only the rightmost can carry pend; equal to `last` iff pend == 1 and base == last
+                        for (uint32_t t = 0; t < l; ++t) {
+                            if (pend == 1 && Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri) == last) { run++; pend = 0; }
+                            else { stop = true; break; }
+                        }
+                        continue;
+                    }
+                    for (uint32_t t = 0; t < l; ++t) {                // M / = / X
+                        if (pend == 0 && Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri - 1) == last) { run++; ri--; }
+                        else { stop = true; break; }
+                    }
+                }
+            }
+            const unsigned long long nk64 = (E - run >= 1) ? (E - run - 1) : 0;
+            if ((unsigned long long)gstart + nk64 > cend) { if (lane8 == 0) report_error(d.st, aln, ERR_OOB); continue; }
+            const uint32_t nkept = (uint32_t)nk64;
+            S.add_interval(lane8, aln, gstart, nkept, multi);
+            // pass 3: emit entries e < nkept
+            uint32_t e = 0, ri = 0;
+            for (uint32_t p = 0; p < ncig && e < nkept; ++p) {
+                const uint32_t op = ops[p], o = op & 15u, l = op >> 4;
+                if (o == PP_OP_I) { ri += l; continue; }
+                uint32_t ins = 0;                                     // inserted bases right after this op
+                for (uint32_t q = p + 1; q < ncig && (ops[q] & 15u) == PP_OP_I; ++q) ins += ops[q] >> 4;
+                if (o == PP_OP_D) {
+                    const uint32_t plain = ins ? l - 1 : l;           // the last "-" entry absorbs a following insertion
+                    for (uint32_t t = lane8; t < plain && e + t < nkept; t += 8) atomicAdd(&d.delother[gstart + e + t], 1u);
+                    if (ins && lane8 == 0 && e + l - 1 < nkept) {
+                        const uint32_t pos = gstart + e + l - 1;
+                        if (ins == 1) S.count_base(pos, Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri), aln, ri);
+                        else S.push_other(pos, aln, ri, ins);
+                    }
+                    e += l;
+                    continue;
+                }
+                const uint32_t plain = ins ? l - 1 : l;               // M / = / X
+                for (uint32_t t = lane8; t < plain && e + t < nkept; t += 8)
+                    S.count_base(gstart + e + t, Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri + t), aln, ri + t);
+                if (ins && lane8 == 0 && e + l - 1 < nkept) S.push_other(gstart + e + l - 1, aln, ri + l - 1, 1 + ins);
+                e += l;
+                ri += l;
+            }
+        }
+        __syncthreads();
+        // ---- flush the staged fix-list entries and other-allele records
+        if (tid == 0) {
+            uint32_t nf = min(sh.n_fix, (uint32_t)SC_STAGE), no = min(sh.n_oth, (uint32_t)SC_STAGE);
+            sh.base_fix = nf ? atomicAdd(&d.st->fix_count, nf) : 0;
+            sh.base_oth = no ? atomicAdd(&d.st->other_count, no) : 0;
+            if (sh.oth_len) atomicAdd(&d.st->other_len, sh.oth_len);
+        }
+        __syncthreads();
+        {
+            const uint32_t nf = min(sh.n_fix, (uint32_t)SC_STAGE), no = min(sh.n_oth, (uint32_t)SC_STAGE);
+            for (uint32_t i = tid; i < nf; i += SC_THREADS) {
+                uint32_t g = sh.base_fix + i;
+                if (g < d.fix_cap) { d.fix_key[g] = sh.fix_key[i]; d.fix_val[g] = sh.fix_val[i]; }
+                else atomicOr(&d.st->flags, FL_FIX_OVF);
+            }
+            for (uint32_t i = tid; i < no; i += SC_THREADS) {
+                uint32_t g = sh.base_oth + i;
+                if (g < d.oth_cap) { d.oth_key[g] = sh.oth_key[i]; d.oth_val[g] = sh.oth_val[i]; }
+                else atomicOr(&d.st->flags, FL_OTHER_OVF);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_depth_fixup: the reference's sequential f64 depth sum (pileup.rs:64, alignment.rs:288) for every
+// position of a flagged tile, in SAM order (keys sorted by (tile, alignment index)).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lower_bound_u64(const unsigned long long* a, uint32_t n, unsigned long long key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(PP_TILE) k_depth_fixup(DevData d, const unsigned long long* __restrict__ keys,
+                                                         const unsigned long long* __restrict__ vals, uint32_t n) {
+    const uint32_t tile = blockIdx.x;
+    if (!((d.tileflag[tile >> 5] >> (tile & 31)) & 1u)) return;
+    __shared__ uint32_t s_lo, s_hi;
+    __shared__ uint32_t s_start[PP_TILE], s_end[PP_TILE];
+    __shared__ double s_inv[PP_TILE];
+    if (threadIdx.x == 0) s_lo = lower_bound_u64(keys, n, (unsigned long long)tile << 32);
+    if (threadIdx.x == 1) s_hi = lower_bound_u64(keys, n, (unsigned long long)(tile + 1) << 32);
+    __syncthreads();
+    const uint32_t lo = s_lo, hi = s_hi;
+    const uint32_t p = tile * PP_TILE + threadIdx.x;
+    double depth = 0.0;
+    for (uint32_t base = lo; base < hi; base += PP_TILE) {
+        const uint32_t i = base + threadIdx.x;
+        if (i < hi) {
+            const unsigned long long v = vals[i];
+            const uint32_t aln = (uint32_t)keys[i];
+            const uint32_t kk = d.k[d.read_id[aln]];
+            s_start[threadIdx.x] = (uint32_t)(v >> 32);
+            s_end[threadIdx.x] = (uint32_t)(v >> 32) + (uint32_t)v;
+            s_inv[threadIdx.x] = __ddiv_rn(1.0, (double)kk);      // 1.0 / good_alignments.len() as f64
+        }
+        __syncthreads();
+        const uint32_t cnt = min((uint32_t)PP_TILE, hi - base);
+        for (uint32_t j = 0; j < cnt; ++j)
+            if (p >= s_start[j] && p < s_end[j]) depth = __dadd_rn(depth, s_inv[j]);
+        __syncthreads();
+    }
+    if (p < d.G) d.depth_fix[p] = depth;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_vote: prefix sum of the difference array (decoupled look-back), the per-position vote, output compaction.
+// ------------------------------------------------------------------------------------------------------
+struct VoteParams {
+    double fv, fi;
+    uint32_t min_depth;
+    uint32_t n_chunks;
+    uint8_t* out;
+    unsigned long long out_cap;
+    unsigned long long* out_off;     // [n_contigs+1]
+    unsigned long long *changed, *zero_depth;   // [n_contigs]
+    // look-back descriptors
+    uint32_t* st1; unsigned long long *agg1, *inc1;
+    uint32_t* st2; unsigned long long *agg2, *inc2;
+    const uint32_t* oth_key; const unsigned long long* oth_val; uint32_t n_oth;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_cg64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_cg64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Exclusive prefix of chunk `c` over all earlier chunks; publishes this chunk's aggregate / inclusive prefix.
+// Called by warp 0 only (all 32 lanes).
+__device__ __forceinline__ unsigned long long lookback(uint32_t c, unsigned long long aggregate, uint32_t* st,
+                                                       unsigned long long* agg, unsigned long long* inc) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (c == 0) {
+        if (lane == 0) { st_cg64(&inc[0], aggregate); st_release(&st[0], 2u); }
+        return 0;
+    }
+    if (lane == 0) { st_cg64(&agg[c], aggregate); st_release(&st[c], 1u); }
+    unsigned long long prefix = 0;
+    int j = (int)c - 1;
+    for (;;) {
+        const int idx = j - (int)lane;
+        uint32_t s = 2;
+        if (idx >= 0) { do { s = ld_acquire(&st[idx]); } while (s == 0); }
+        unsigned long long v = 0;
+        if (idx >= 0) v = (s == 2) ? ld_cg64(&inc[idx]) : ld_cg64(&agg[idx]);
+        const unsigned m = __ballot_sync(0xffffffffu, s == 2);
+        const int first = __ffs(m) - 1;          // nearest predecessor with an inclusive prefix (m != 0 eventually: idx < 0 counts)
+        if (first >= 0 && (int)lane > first) v = 0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        prefix += v;
+        if (m) break;
+        j -= 32;
+    }
+    if (lane == 0) { st_cg64(&inc[c], prefix + aggregate); st_release(&st[c], 2u); }
+    return prefix;
+}
+
+// block-wide exclusive scan of one u64 per thread (VT_THREADS threads); returns exclusive prefix, total in *total
+__device__ __forceinline__ unsigned long long block_exscan(unsigned long long v, unsigned long long* s_warp, unsigned long long* total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = (lane < VT_THREADS / 32) ? s_warp[lane] : 0;
+        unsigned long long winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
+            if ((int)lane >= o) winc += t;
+        }
+        if (lane < VT_THREADS / 32) s_warp[lane] = winc - w;      // exclusive per-warp offsets
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    unsigned long long r = s_warp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// misc.rs:208-215 bankers_rounding on a non-negative finite double (depth * fraction)
+__device__ __forceinline__ uint32_t bankers_rounding(double x) {
+    uint32_t rd;
+    if (!(x == x) || x <= 0.0) rd = 0;
+    else if (x >= 4294967295.0) rd = 4294967295u;
+    else rd = (uint32_t)x;                                  // truncation
+    const double fr = __dsub_rn(x, trunc(x));
+    if (fr < 0.5) return rd;
+    if (fr > 0.5) return rd + 1;
+    return rd + (rd & 1u);
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+struct Verdict { uint32_t out_len; uint8_t ch; bool changed; bool slow_emit; uint32_t rec; };
+
+template <int BITS>
+__device__ __forceinline__ bool other_equal(const DevData& d, unsigned long long va, unsigned long long vb) {
+    const uint32_t la = (uint32_t)va & 0xFFFFu, lb = (uint32_t)vb & 0xFFFFu;
+    if (la != lb) return false;
+    const uint32_t aa = (uint32_t)(va >> 32), ab = (uint32_t)(vb >> 32);
+    const uint32_t sa = (uint32_t)(va >> 16) & 0xFFFFu, sb = (uint32_t)(vb >> 16) & 0xFFFFu;
+    const bool rca = d.flags[aa] & PP_FLAG_RC, rcb = d.flags[ab] & PP_FLAG_RC;
+    const uint32_t oa = d.seq_off[aa], ob = d.seq_off[ab], na = d.seq_len[aa], nb = d.seq_len[ab];
+    for (uint32_t i = 0; i < la; ++i)
+        if (Seq<BITS>::read_sym(d.seq_pool, oa, na, rca, sa + i) != Seq<BITS>::read_sym(d.seq_pool, ob, nb, rcb, sb + i)) return false;
+    return true;
+}
+
+// The vote of pileup.rs:67-134 for one position.  counts = A,C,G,T,"-" (draft base already folded in),
+// matched = entries equal to a non-ACGT draft base, n_other = other-allele records at this position.
+template <int BITS>
+__device__ Verdict vote_position(const DevData& d, const VoteParams& vp, uint32_t pos, uint8_t orig, double depth,
+                                 const uint32_t cnt[5], uint32_t matched, uint32_t n_other) {
+    const uint32_t vt = max(vp.min_depth, bankers_rounding(__dmul_rn(depth, vp.fv)));
+    const uint32_t it = bankers_rounding(__dmul_rn(depth, vp.fi));
+    uint32_t nvalid = 0, ninter = 0;
+    int which = -1;                 // 0..3 ACGT, 4 "-", 5 the draft's own non-ACGT base, 6 an other-allele record
+    uint32_t which_rec = 0;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        if (c == 4 && cnt[4] == 0) break;                   // "-" exists only if it was seen (HashMap entry)
+        if (cnt[c] >= vt) { nvalid++; which = c; }
+        else if (cnt[c] >= it) ninter++;
+    }
+    if (matched > 0) {                                       // the 1-char string of a non-ACGT draft base
+        if (matched >= vt) { nvalid++; which = 5; }
+        else if (matched >= it) ninter++;
+    }
+    if (n_other > 0) {
+        const uint32_t lo = lower_bound_u32(vp.oth_key, vp.n_oth, pos);
+        uint32_t hi = lo;
+        while (hi < vp.n_oth && vp.oth_key[hi] == pos) hi++;
+        for (uint32_t i = lo; i < hi; ++i) {
+            const unsigned long long vi = vp.oth_val[i];
+            bool rep = true;
+            for (uint32_t j = lo; j < i && rep; ++j) if (other_equal<BITS>(d, vp.oth_val[j], vi)) rep = false;
+            if (!rep) continue;
+            uint32_t c = 1;
+            for (uint32_t j = i + 1; j < hi; ++j) if (other_equal<BITS>(d, vp.oth_val[j], vi)) c++;
+            if (c >= vt) { nvalid++; which = 6; which_rec = i; }
+            else if (c >= it) ninter++;
+        }
+    }
+    Verdict v;
+    v.ch = orig; v.out_len = (orig == '-') ? 0 : 1; v.changed = false; v.slow_emit = false; v.rec = 0;
+    if (depth < (double)vp.min_depth) return v;               // DepthTooLow
+    if (nvalid != 1 || ninter > 0) return v;                  // none / multiple / too_close
+    if (which <= 3) {
+        const uint8_t nb = (uint8_t)("ACGT"[which]);
+        v.changed = nb != orig; v.ch = nb; v.out_len = 1;
+    } else if (which == 4) {
+        v.changed = orig != '-'; v.ch = '-'; v.out_len = 0;
+    } else if (which == 5) {
+        // original base kept
+    } else {
+        const unsigned long long val = vp.oth_val[which_rec];
+        const uint32_t aln = (uint32_t)(val >> 32), start = (uint32_t)(val >> 16) & 0xFFFFu, len = (uint32_t)val & 0xFFFFu;
+        const bool rc = d.flags[aln] & PP_FLAG_RC;
+        uint32_t n = 0;
+        for (uint32_t i = 0; i < len; ++i)
+            if (Seq<BITS>::ascii(Seq<BITS>::read_sym(d.seq_pool, d.seq_off[aln], d.seq_len[aln], rc, start + i)) != '-') n++;
+        v.changed = true;     // an other-allele string never equals the draft's 1-char string (those are "matched")
+        v.out_len = n; v.slow_emit = true; v.rec = which_rec;
+        if (len == 1) { v.ch = Seq<BITS>::ascii(Seq<BITS>::read_sym(d.seq_pool, d.seq_off[aln], d.seq_len[aln], rc, start)); v.slow_emit = false; }
+    }
+    return v;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(VT_THREADS) k_vote(DevData d, VoteParams vp) {
+    __shared__ unsigned long long s_warp[VT_THREADS / 32];
+    __shared__ unsigned long long s_total, s_prefix;
+    __shared__ uint32_t s_chunk;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) s_chunk = atomicAdd(&d.st->ticket, 1u);
+    __syncthreads();
+    const uint32_t chunk = s_chunk;
+    if (chunk >= vp.n_chunks) return;
+    const uint32_t p0 = chunk * VT_CHUNK + tid * VT_ITEMS;
+
+    // ---- 1. difference array -> cover / multi
+    unsigned long long dv[VT_ITEMS];
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int i = 0; i < VT_ITEMS; ++i) {
+        const uint32_t p = p0 + i;
+        dv[i] = (p < d.G) ? d.diff[p] : 0ull;
+        tsum += dv[i];
+        dv[i] = tsum;                       // thread-inclusive
+    }
+    unsigned long long total;
+    unsigned long long texcl = block_exscan(tsum, s_warp, &s_total);
+    total = s_total;
+    if (tid < 32) {
+        unsigned long long pre = lookback(chunk, total, vp.st1, vp.agg1, vp.inc1);
+        if (tid == 0) s_prefix = pre;
+    }
+    __syncthreads();
+    const unsigned long long base = s_prefix + texcl;
+
+    // ---- 2. vote
+    uint32_t olen[VT_ITEMS];
+    uint8_t och[VT_ITEMS];
+    uint32_t orec[VT_ITEMS];
+    uint32_t slowmask = 0;
+    unsigned long long tlen = 0;
+    uint32_t n_changed = 0, n_zero = 0;
+    // contig of the first position (binary search), advanced as positions cross contig boundaries
+    uint32_t ctg = 0;
+    if (p0 < d.G) {
+        uint32_t lo = 0, hi = d.n_contigs;           // largest c with contig_off[c] <= p0
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (d.contig_off[mid] <= p0) lo = mid; else hi = mid; }
+        ctg = lo;
+    }
+#pragma unroll
+    for (int i = 0; i < VT_ITEMS; ++i) {
+        const uint32_t p = p0 + i;
+        olen[i] = 0; och[i] = 0; orec[i] = 0;
+        if (p >= d.G) continue;
+        while (ctg + 1 < d.n_contigs && d.contig_off[ctg + 1] <= p) {
+            if (n_changed) atomicAdd(&vp.changed[ctg], (unsigned long long)n_changed);
+            if (n_zero) atomicAdd(&vp.zero_depth[ctg], (unsigned long long)n_zero);
+            n_changed = n_zero = 0;
+            ctg++;
+        }
+        const unsigned long long pv = base + dv[i];
+        const uint32_t cover = (uint32_t)pv, multi = (uint32_t)(pv >> 32);
+        const uint8_t orig = d.draft[p];
+        if (cover >= 65536u) atomicOr(&d.st->flags, FL_COUNTER_OVF);
+        if (cover == 0) {                                    // depth 0: always the original base
+            n_zero++;
+            olen[i] = (orig == '-') ? 0 : 1; och[i] = orig;
+            tlen += olen[i];
+            continue;
+        }
+        const unsigned long long ex = d.ex[p];
+        const uint32_t dl = d.delother[p];
+        uint32_t cnt[5] = {(uint32_t)ex & 0xFFFFu, (uint32_t)(ex >> 16) & 0xFFFFu, (uint32_t)(ex >> 32) & 0xFFFFu,
+                           (uint32_t)(ex >> 48) & 0xFFFFu, dl & 0xFFFFu};
+        const uint32_t n_other = dl >> 16;
+        uint32_t matched = cover - (cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4] + n_other);
+        const int oc = orig == 'A' ? 0 : orig == 'C' ? 1 : orig == 'G' ? 2 : orig == 'T' ? 3 : -1;
+        if (oc >= 0) { cnt[oc] += matched; matched = 0; }
+        const double depth = multi ? d.depth_fix[p] : (double)cover;
+        if (depth == 0.0) n_zero++;
+        const Verdict v = vote_position<BITS>(d, vp, p, orig, depth, cnt, matched, n_other);
+        olen[i] = v.out_len; och[i] = v.ch; orec[i] = v.rec;
+        if (v.slow_emit) slowmask |= 1u << i;
+        if (v.changed) n_changed++;
+        tlen += v.out_len;
+    }
+    if (n_changed) atomicAdd(&vp.changed[ctg], (unsigned long long)n_changed);
+    if (n_zero) atomicAdd(&vp.zero_depth[ctg], (unsigned long long)n_zero);
+
+    // ---- 3. output offsets (second look-back) and the compacted write
+    unsigned long long oexcl = block_exscan(tlen, s_warp, &s_total);
+    total = s_total;
+    if (tid < 32) {
+        unsigned long long pre = lookback(chunk, total, vp.st2, vp.agg2, vp.inc2);
+        if (tid == 0) s_prefix = pre;
+    }
+    __syncthreads();
+    unsigned long long o = s_prefix + oexcl;
+    if (chunk == vp.n_chunks - 1 && tid == VT_THREADS - 1) {
+        vp.out_off[d.n_contigs] = o + tlen;
+        d.st->out_len = o + tlen;
+    }
+    // out_off of contigs that start inside this thread's positions
+    if (p0 < d.G) {
+        uint32_t lo = 0, hi = d.n_contigs;           // first c with contig_off[c] >= p0
+        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (d.contig_off[mid] < p0) lo = mid + 1; else hi = mid; }
+        unsigned long long oo = o;
+        uint32_t c = lo;
+#pragma unroll
+        for (int i = 0; i < VT_ITEMS; ++i) {
+            const uint32_t p = p0 + i;
+            while (c < d.n_contigs && d.contig_off[c] == p) { vp.out_off[c] = oo; c++; }
+            oo += olen[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VT_ITEMS; ++i) {
+        if (olen[i] == 0) continue;
+        if (o + olen[i] > vp.out_cap) { atomicOr(&d.st->flags, FL_OUT_OVF); o += olen[i]; continue; }
+        if (!((slowmask >> i) & 1u)) { vp.out[o] = och[i]; o += 1; continue; }
+        const unsigned long long val = vp.oth_val[orec[i]];
+        const uint32_t aln = (uint32_t)(val >> 32), start = (uint32_t)(val >> 16) & 0xFFFFu, len = (uint32_t)val & 0xFFFFu;
+        const bool rc = d.flags[aln] & PP_FLAG_RC;
+        for (uint32_t t = 0; t < len; ++t) {
+            const uint8_t ch = Seq<BITS>::ascii(Seq<BITS>::read_sym(d.seq_pool, d.seq_off[aln], d.seq_len[aln], rc, start + t));
+            if (ch != '-') vp.out[o++] = ch;                 // polish.rs:188 replace("-", "")
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side: context, buffers, entry points
+// ------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+enum { B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL,
+       B_DRAFT, B_CTGOFF, B_AUX, B_K, B_NIB, B_DIFF, B_EX, B_DELOTHER, B_TILEFLAG, B_DEPTHFIX, B_FIXKEY, B_FIXVAL,
+       B_FIXKEY2, B_FIXVAL2, B_OTHKEY, B_OTHVAL, B_OTHKEY2, B_OTHVAL2, B_CUBTMP, B_OUT, B_OUTOFF, B_CHANGED, B_ZERO,
+       B_ST1, B_AGG1, B_INC1, B_ST2, B_AGG2, B_INC2, B_STATUS, B_COUNT };
+
+struct pp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    DevBuf b[B_COUNT];
+    cudaEvent_t ev[PP_N_STAGES + 2] = {};
+    DevStatus* h_status = nullptr;        // pinned
+    bool have_ds = false;
+    // dataset facts
+    uint64_t n_aln = 0, n_reads = 0, n_ops = 0, seq_bytes = 0, G = 0;
+    uint32_t n_contigs = 0, seq_bits = 4;
+    std::vector<uint64_t> contig_off;
+    int sm_count = 148;
+    uint32_t launches = 0;
+    uint64_t last_out_len = 0;
+    bool have_result = false;
+
+    int fail(int code, const std::string& m) { err = m; return code; }
+    int fail_cuda(cudaError_t e, const char* what, int line) {
+        err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what + " (polish_kernels.cu:" + std::to_string(line) + ")";
+        return PP_ERR_CUDA;
+    }
+};
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return ctx->fail_cuda(e_, #x, __LINE__); } while (0)
+
+static void init_comp_table(uint8_t* t) {
+    for (int i = 0; i < 256; ++i) t[i] = 'N';
+    const char* a = "ATGCNRYSWKMBVDH.-?";
+    const char* b = "TACGNYRSWMKVBHD.-?";
+    for (int i = 0; a[i]; ++i) t[(unsigned char)a[i]] = (uint8_t)b[i];
+}
+
+extern "C" const char* pp_version(void) { return "0.6.1-b200"; }
+
+extern "C" void* pp_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void pp_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int pp_create(int device, pp_ctx** out) {
+    if (!out) return PP_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0 || device < 0 || device >= n) { cudaGetLastError(); return PP_ERR_CUDA; }   // no CPU fallback
+    pp_ctx* ctx = new pp_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) { delete ctx; return PP_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    for (auto& ev : ctx->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    if (cudaHostAlloc((void**)&ctx->h_status, sizeof(DevStatus), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    uint8_t comp[256];
+    init_comp_table(comp);
+    if (cudaMemcpyToSymbol(c_comp, comp, 256) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    *out = ctx;
+    return PP_OK;
+}
+
+extern "C" void pp_destroy(pp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->b) b.release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* pp_last_error(const pp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+// internal (host_api.cpp): lets the text layer report its errors through the same channel
+int pp_ctx_fail(pp_ctx* ctx, int code, const char* msg) { ctx->err = msg; return code; }
+
+template <class T>
+static int upload(pp_ctx* ctx, int which, const T* src, size_t n, size_t pad_bytes = 64) {
+    CK(ctx->b[which].ensure(n * sizeof(T) + pad_bytes));
+    if (n) CK(cudaMemcpyAsync(ctx->b[which].p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return PP_OK;
+}
+
+extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alignments* a) {
+    if (!ctx) return PP_ERR_ARG;
+    if (!c || !a || !c->off || !c->bases || c->n_contigs == 0) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: null or empty contigs");
+    if (a->n_aln && (!a->contig || !a->ref_start || !a->read_id || !a->seq_off || !a->seq_len || !a->cigar_off ||
+                     !a->n_cigar || !a->nm || !a->flags || !a->cigar_ops))
+        return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: null alignment array");
+    if (a->seq_bits != 4 && a->seq_bits != 8) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: seq_bits must be 4 or 8");
+    const uint64_t G = c->off[c->n_contigs];
+    if (G == 0 || G >= 0xFFFFFFFFull - 64) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: total assembly length must be in [1, 2^32-64)");
+    if (a->n_aln >= 0xFFFFFFFFull) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: more than 2^32-1 alignments");
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_ds = false;
+    ctx->have_result = false;
+    int rc;
+    if ((rc = upload(ctx, B_CONTIG, a->contig, a->n_aln))) return rc;
+    if ((rc = upload(ctx, B_REFSTART, a->ref_start, a->n_aln))) return rc;
+    if ((rc = upload(ctx, B_READID, a->read_id, a->n_aln))) return rc;
+    if ((rc = upload(ctx, B_SEQOFF, a->seq_off, a->n_aln))) return rc;
+    if ((rc = upload(ctx, B_SEQLEN, a->seq_len, a->n_aln))) return rc;
+    if ((rc = upload(ctx, B_CIGOFF, a->cigar_off, a->n_aln))) return rc;
+    if ((rc = upload(ctx, B_NCIG, a->n_cigar, a->n_aln))) return rc;
+    if ((rc = upload(ctx, B_NM, a->nm, a->n_aln))) return rc;
+    if ((rc = upload(ctx, B_FLAGS, a->flags, a->n_aln))) return rc;
+    if ((rc = upload(ctx, B_CIGOPS, a->cigar_ops, a->n_cigar_ops))) return rc;
+    if ((rc = upload(ctx, B_SEQPOOL, a->seq_pool, a->seq_pool_bytes, 256))) return rc;
+    if ((rc = upload(ctx, B_DRAFT, c->bases, G, 256))) return rc;
+    if ((rc = upload(ctx, B_CTGOFF, c->off, (size_t)c->n_contigs + 1))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_aln = a->n_aln; ctx->n_reads = a->n_reads; ctx->n_ops = a->n_cigar_ops; ctx->seq_bytes = a->seq_pool_bytes;
+    ctx->seq_bits = a->seq_bits; ctx->G = G; ctx->n_contigs = c->n_contigs;
+    ctx->contig_off.assign(c->off, c->off + c->n_contigs + 1);
+    ctx->have_ds = true;
+    return PP_OK;
+}
+
+static const char* err_text(unsigned code) {
+    switch (code) {
+        case ERR_UNKNOWN_CONTIG: return "query name in SAM but not in assembly";
+        case ERR_SEQ_MISMATCH: return "CIGAR string does not match read sequence";
+        case ERR_BAD_OP: return "unexpected character (other than M, =, X, I or D) in CIGAR string - did you use BWA MEM to generate your alignments?";
+        case ERR_OOB: return "alignment extends past the end of its reference sequence";
+        case ERR_NOSEQ: return "no alignments for read contain sequence";
+        default: return "unknown device-side error";
+    }
+}
+
+template <int BITS>
+static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result* res, bool fetch) {
+    cudaStream_t s = ctx->stream;
+    const uint64_t G = ctx->G, n_aln = ctx->n_aln;
+    const uint32_t n_tiles = (uint32_t)((G + PP_TILE - 1) >> PP_TILE_SHIFT);
+    const uint32_t n_chunks = (uint32_t)((G + VT_CHUNK - 1) / VT_CHUNK);
+    const uint32_t nib_words = (uint32_t)((G + 15) / 16);
+    ctx->launches = 0;
+    ctx->have_result = false;
+
+    uint32_t fix_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, n_aln / 4 + 1024));
+    uint32_t oth_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, n_aln / 2 + 1024));
+    uint64_t out_cap = G + 4096;
+
+    CK(ctx->b[B_AUX].ensure(n_aln + 64));
+    CK(ctx->b[B_K].ensure((ctx->n_reads + 1) * 4));
+    CK(ctx->b[B_NIB].ensure(((size_t)nib_words + 8) * 8));
+    CK(ctx->b[B_DIFF].ensure((G + 2) * 8));
+    CK(ctx->b[B_EX].ensure((G + 1) * 8));
+    CK(ctx->b[B_DELOTHER].ensure((G + 1) * 4));
+    CK(ctx->b[B_TILEFLAG].ensure(((size_t)n_tiles / 32 + 2) * 4));
+    CK(ctx->b[B_DEPTHFIX].ensure(((size_t)n_tiles * PP_TILE + 1) * 8));
+    CK(ctx->b[B_OUTOFF].ensure(((size_t)ctx->n_contigs + 1) * 8));
+    CK(ctx->b[B_CHANGED].ensure((size_t)ctx->n_contigs * 8));
+    CK(ctx->b[B_ZERO].ensure((size_t)ctx->n_contigs * 8));
+    CK(ctx->b[B_ST1].ensure((size_t)n_chunks * 4)); CK(ctx->b[B_AGG1].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC1].ensure((size_t)n_chunks * 8));
+    CK(ctx->b[B_ST2].ensure((size_t)n_chunks * 4)); CK(ctx->b[B_AGG2].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC2].ensure((size_t)n_chunks * 8));
+    CK(ctx->b[B_STATUS].ensure(sizeof(DevStatus)));
+
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        CK(ctx->b[B_FIXKEY].ensure((size_t)fix_cap * 8)); CK(ctx->b[B_FIXVAL].ensure((size_t)fix_cap * 8));
+        CK(ctx->b[B_OTHKEY].ensure((size_t)oth_cap * 4)); CK(ctx->b[B_OTHVAL].ensure((size_t)oth_cap * 8));
+        CK(ctx->b[B_OUT].ensure(out_cap + 64));
+
+        DevData d;
+        d.n_aln = n_aln;
+        d.contig = ctx->b[B_CONTIG].as<uint32_t>(); d.ref_start = ctx->b[B_REFSTART].as<uint32_t>();
+        d.read_id = ctx->b[B_READID].as<uint32_t>(); d.seq_off = ctx->b[B_SEQOFF].as<uint32_t>();
+        d.cigar_off = ctx->b[B_CIGOFF].as<uint32_t>(); d.nm = ctx->b[B_NM].as<uint32_t>();
+        d.cigar_ops = ctx->b[B_CIGOPS].as<uint32_t>(); d.seq_len = ctx->b[B_SEQLEN].as<uint16_t>();
+        d.n_cigar = ctx->b[B_NCIG].as<uint16_t>(); d.flags = ctx->b[B_FLAGS].as<uint8_t>();
+        d.seq_pool = ctx->b[B_SEQPOOL].as<uint8_t>(); d.draft = ctx->b[B_DRAFT].as<uint8_t>();
+        d.contig_off = ctx->b[B_CTGOFF].as<unsigned long long>(); d.n_contigs = ctx->n_contigs; d.G = (uint32_t)G;
+        d.aux = ctx->b[B_AUX].as<uint8_t>(); d.k = ctx->b[B_K].as<uint32_t>();
+        d.draft_nib = ctx->b[B_NIB].as<unsigned long long>(); d.diff = ctx->b[B_DIFF].as<unsigned long long>();
+        d.ex = ctx->b[B_EX].as<unsigned long long>(); d.delother = ctx->b[B_DELOTHER].as<uint32_t>();
+        d.tileflag = ctx->b[B_TILEFLAG].as<uint32_t>(); d.depth_fix = ctx->b[B_DEPTHFIX].as<double>();
+        d.fix_key = ctx->b[B_FIXKEY].as<unsigned long long>(); d.fix_val = ctx->b[B_FIXVAL].as<unsigned long long>();
+        d.oth_key = ctx->b[B_OTHKEY].as<uint32_t>(); d.oth_val = ctx->b[B_OTHVAL].as<unsigned long long>();
+        d.fix_cap = fix_cap; d.oth_cap = oth_cap;
+        d.st = ctx->b[B_STATUS].as<DevStatus>();
+
+        // ---- stage 0: reset
+        CK(cudaEventRecord(ctx->ev[0], s));
+        CK(cudaMemsetAsync(d.k, 0, (ctx->n_reads + 1) * 4, s));
+        CK(cudaMemsetAsync(d.diff, 0, (G + 2) * 8, s));
+        CK(cudaMemsetAsync(d.ex, 0, (G + 1) * 8, s));
+        CK(cudaMemsetAsync(d.delother, 0, (G + 1) * 4, s));
+        CK(cudaMemsetAsync(d.tileflag, 0, ((size_t)n_tiles / 32 + 2) * 4, s));
+        CK(cudaMemsetAsync(ctx->b[B_ST1].p, 0, (size_t)n_chunks * 4, s));
+        CK(cudaMemsetAsync(ctx->b[B_ST2].p, 0, (size_t)n_chunks * 4, s));
+        CK(cudaMemsetAsync(ctx->b[B_CHANGED].p, 0, (size_t)ctx->n_contigs * 8, s));
+        CK(cudaMemsetAsync(ctx->b[B_ZERO].p, 0, (size_t)ctx->n_contigs * 8, s));
+        CK(cudaMemsetAsync(d.st, 0, sizeof(DevStatus), s));
+        CK(cudaMemsetAsync(&d.st->err, 0xFF, 8, s));
+        if (BITS == 4) {
+            CK(cudaMemsetAsync(d.draft_nib + nib_words, 0, 64, s));
+            k_draft_nib<<<std::min<uint32_t>((nib_words + 255) / 256, ctx->sm_count * 8), 256, 0, s>>>(d.draft, (uint32_t)G, d.draft_nib, nib_words);
+            ctx->launches++;
+        }
+        // ---- stage 1: classify
+        CK(cudaEventRecord(ctx->ev[1], s));
+        if (n_aln) {
+            uint32_t grid = (uint32_t)std::min<uint64_t>((n_aln + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            k_classify<<<grid, 256, 0, s>>>(d, prm->max_errors, prm->careful ? 1 : 0);
+            ctx->launches++;
+        }
+        // ---- stage 2: scatter
+        CK(cudaEventRecord(ctx->ev[2], s));
+        if (n_aln) {
+            uint32_t grid = (uint32_t)std::min<uint64_t>((n_aln + SC_THREADS - 1) / SC_THREADS, (uint64_t)ctx->sm_count * 8);
+            k_scatter<BITS><<<grid, SC_THREADS, 0, s>>>(d);
+            ctx->launches++;
+        }
+        CK(cudaEventRecord(ctx->ev[3], s));
+        CK(cudaMemcpyAsync(ctx->h_status, d.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        DevStatus hs = *ctx->h_status;
+        if (hs.err != ~0ull) {
+            res->error_aln = (int64_t)(hs.err >> 8);
+            return ctx->fail(PP_ERR_INPUT, std::string(err_text((unsigned)(hs.err & 0xFF))) + " (alignment " + std::to_string(hs.err >> 8) + ")");
+        }
+        if (hs.flags & (FL_FIX_OVF | FL_OTHER_OVF)) {
+            if (hs.flags & FL_FIX_OVF) fix_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, (uint64_t)hs.fix_count + hs.fix_count / 8 + 1024);
+            if (hs.flags & FL_OTHER_OVF) oth_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, (uint64_t)hs.other_count + hs.other_count / 8 + 1024);
+            continue;      // rerun with larger side buffers
+        }
+        out_cap = G + hs.other_len + 64;
+        CK(ctx->b[B_OUT].ensure(out_cap + 64));
+
+        // ---- stage 3: depth fix-up (ordered f64 sum where k != 1 coverage may exist)
+        const unsigned long long* fkeys = d.fix_key;
+        const unsigned long long* fvals = d.fix_val;
+        if (hs.fix_count) {
+            CK(ctx->b[B_FIXKEY2].ensure((size_t)hs.fix_count * 8)); CK(ctx->b[B_FIXVAL2].ensure((size_t)hs.fix_count * 8));
+            size_t tmp = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d.fix_key, ctx->b[B_FIXKEY2].as<unsigned long long>(), d.fix_val,
+                                               ctx->b[B_FIXVAL2].as<unsigned long long>(), (int)hs.fix_count, 0, 64, s));
+            CK(ctx->b[B_CUBTMP].ensure(tmp));
+            CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, tmp, d.fix_key, ctx->b[B_FIXKEY2].as<unsigned long long>(), d.fix_val,
+                                               ctx->b[B_FIXVAL2].as<unsigned long long>(), (int)hs.fix_count, 0, 64, s));
+            fkeys = ctx->b[B_FIXKEY2].as<unsigned long long>();
+            fvals = ctx->b[B_FIXVAL2].as<unsigned long long>();
+            k_depth_fixup<<<n_tiles, PP_TILE, 0, s>>>(d, fkeys, fvals, hs.fix_count);
+            ctx->launches++;
+        }
+        // ---- stage 4: sort other-allele records by position
+        CK(cudaEventRecord(ctx->ev[4], s));
+        const uint32_t* okeys = d.oth_key;
+        const unsigned long long* ovals = d.oth_val;
+        if (hs.other_count) {
+            CK(ctx->b[B_OTHKEY2].ensure((size_t)hs.other_count * 4)); CK(ctx->b[B_OTHVAL2].ensure((size_t)hs.other_count * 8));
+            size_t tmp = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d.oth_key, ctx->b[B_OTHKEY2].as<uint32_t>(), d.oth_val,
+                                               ctx->b[B_OTHVAL2].as<unsigned long long>(), (int)hs.other_count, 0, 32, s));
+            CK(ctx->b[B_CUBTMP].ensure(tmp));
+            CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, tmp, d.oth_key, ctx->b[B_OTHKEY2].as<uint32_t>(), d.oth_val,
+                                               ctx->b[B_OTHVAL2].as<unsigned long long>(), (int)hs.other_count, 0, 32, s));
+            okeys = ctx->b[B_OTHKEY2].as<uint32_t>();
+            ovals = ctx->b[B_OTHVAL2].as<unsigned long long>();
+        }
+        // ---- stage 5: vote + compaction
+        CK(cudaEventRecord(ctx->ev[5], s));
+        VoteParams vp;
+        vp.fv = prm->fraction_valid; vp.fi = prm->fraction_invalid; vp.min_depth = prm->min_depth; vp.n_chunks = n_chunks;
+        vp.out = ctx->b[B_OUT].as<uint8_t>(); vp.out_cap = out_cap;
+        vp.out_off = ctx->b[B_OUTOFF].as<unsigned long long>();
+        vp.changed = ctx->b[B_CHANGED].as<unsigned long long>(); vp.zero_depth = ctx->b[B_ZERO].as<unsigned long long>();
+        vp.st1 = ctx->b[B_ST1].as<uint32_t>(); vp.agg1 = ctx->b[B_AGG1].as<unsigned long long>(); vp.inc1 = ctx->b[B_INC1].as<unsigned long long>();
+        vp.st2 = ctx->b[B_ST2].as<uint32_t>(); vp.agg2 = ctx->b[B_AGG2].as<unsigned long long>(); vp.inc2 = ctx->b[B_INC2].as<unsigned long long>();
+        vp.oth_key = okeys; vp.oth_val = ovals; vp.n_oth = hs.other_count;
+        k_vote<BITS><<<n_chunks, VT_THREADS, 0, s>>>(d, vp);
+        ctx->launches++;
+        CK(cudaEventRecord(ctx->ev[6], s));
+        CK(cudaMemcpyAsync(ctx->h_status, d.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        hs = *ctx->h_status;
+        if (hs.flags & FL_COUNTER_OVF)
+            return ctx->fail(PP_ERR_INPUT, "a position is covered by 65536 or more alignments: not supported by this build's 16-bit allele counters");
+        if (hs.flags & FL_OUT_OVF) return ctx->fail(PP_ERR_CUDA, "internal error: output buffer overflow");
+
+        res->out_len = hs.out_len;
+        res->n_aln_used = hs.n_used;
+        res->error_aln = -1;
+        ctx->last_out_len = hs.out_len;
+        ctx->have_result = true;
+        memset(&res->timing, 0, sizeof res->timing);
+        float ms;
+        for (int i = 0; i < 6; ++i) {
+            if (i == 3 || i == 4) continue;
+            CK(cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+            res->timing.stage_ms[i] = ms;
+        }
+        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4])); res->timing.stage_ms[3] = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); res->timing.stage_ms[4] = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6])); res->timing.total_ms = ms;
+        res->timing.launches = ctx->launches;
+
+        if (fetch) {
+            if (res->out_bases) {
+                if (res->out_cap < hs.out_len) return ctx->fail(PP_ERR_ARG, "out_cap too small: need " + std::to_string(hs.out_len) + " bytes");
+                CK(cudaEventRecord(ctx->ev[7], s));
+                CK(cudaMemcpyAsync(res->out_bases, vp.out, hs.out_len, cudaMemcpyDeviceToHost, s));
+                if (res->out_off) CK(cudaMemcpyAsync(res->out_off, vp.out_off, ((size_t)ctx->n_contigs + 1) * 8, cudaMemcpyDeviceToHost, s));
+                if (res->changed) CK(cudaMemcpyAsync(res->changed, vp.changed, (size_t)ctx->n_contigs * 8, cudaMemcpyDeviceToHost, s));
+                if (res->zero_depth) CK(cudaMemcpyAsync(res->zero_depth, vp.zero_depth, (size_t)ctx->n_contigs * 8, cudaMemcpyDeviceToHost, s));
+                CK(cudaEventRecord(ctx->ev[8], s));
+                CK(cudaStreamSynchronize(s));
+                CK(cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]));
+                res->timing.stage_ms[7] = ms;
+            }
+        }
+        return PP_OK;
+    }
+    return ctx->fail(PP_ERR_NOMEM, "side buffers kept overflowing");
+}
+
+static int check_params(pp_ctx* ctx, const pp_polish_params* p) {
+    if (!p) return ctx->fail(PP_ERR_ARG, "null params");
+    // polish.rs:277-287 (the same text the reference prints)
+    if (!(p->fraction_valid > 0.0 && p->fraction_valid < 1.0)) return ctx->fail(PP_ERR_INPUT, "--fraction_valid must be between 0 and 1 (exclusive)");
+    if (!(p->fraction_invalid > 0.0 && p->fraction_invalid < 1.0)) return ctx->fail(PP_ERR_INPUT, "--fraction_invalid must be between 0 and 1 (exclusive)");
+    if (p->fraction_invalid >= p->fraction_valid) return ctx->fail(PP_ERR_INPUT, "--fraction_invalid must be less than --fraction_valid");
+    return PP_OK;
+}
+
+extern "C" int pp_polish_resident(pp_ctx* ctx, const pp_polish_params* params, pp_polish_result* result) {
+    if (!ctx) return PP_ERR_ARG;
+    if (!result) return ctx->fail(PP_ERR_ARG, "null result");
+    if (!ctx->have_ds) return ctx->fail(PP_ERR_ARG, "pp_polish_resident: no dataset uploaded");
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    result->error_aln = -1;
+    return ctx->seq_bits == 4 ? run_polish<4>(ctx, params, result, true) : run_polish<8>(ctx, params, result, true);
+}
+
+extern "C" int pp_polish(pp_ctx* ctx, const pp_contigs* contigs, const pp_alignments* alns,
+                         const pp_polish_params* params, pp_polish_result* result) {
+    if (!ctx) return PP_ERR_ARG;
+    if (!result) return ctx->fail(PP_ERR_ARG, "null result");
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev[9], ctx->stream));
+    rc = pp_dataset_upload(ctx, contigs, alns);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[8], ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev[8]));
+    float h2d = 0;
+    CK(cudaEventElapsedTime(&h2d, ctx->ev[9], ctx->ev[8]));
+    result->error_aln = -1;
+    rc = ctx->seq_bits == 4 ? run_polish<4>(ctx, params, result, true) : run_polish<8>(ctx, params, result, true);
+    if (rc == PP_OK) result->timing.stage_ms[6] = h2d;
+    return rc;
+}

@@ -1,0 +1,97 @@
+// pp_internal.h — shared host-side declarations of libpolypolish_b200 (not part of the ABI).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pp_abi.h"
+
+namespace pp {
+
+// Rust str::lines() over a byte buffer without allocating: split on '\n', strip one '\r' before it;
+// a final unterminated line is a line (alignment.rs:238, misc.rs:109).
+template <class F>
+inline void for_each_line(const char* data, size_t n, F&& f) {
+    size_t pos = 0;
+    while (pos < n) {
+        const char* nl = (const char*)memchr(data + pos, '\n', n - pos);
+        size_t end = nl ? (size_t)(nl - data) : n;
+        size_t e2 = end;
+        if (nl && e2 > pos && data[e2 - 1] == '\r') e2--;
+        if (!f(std::string_view(data + pos, e2 - pos))) return;
+        if (!nl) break;
+        pos = end + 1;
+    }
+}
+
+bool read_file(const std::string& path, std::string& out);
+bool read_gz_file(const std::string& path, std::string& out);
+bool file_exists(const std::string& path);
+
+// Rust "123".parse::<u32/usize>(): optional '+', >= 1 ASCII digit, overflow is an error.
+bool parse_uint(std::string_view s, uint64_t maxv, uint64_t& out);
+
+// Alignment::get_ref_end (alignment.rs:138-149): tolerant scan of \d+[MIDNSHP=X] tokens.
+bool cigar_ref_end(std::string_view cigar, uint64_t start, uint64_t& end);
+
+// 16-byte aligned growable byte buffer (sequence pool).
+struct AlignedBytes {
+    uint8_t* p = nullptr;
+    size_t n = 0, cap = 0;
+    ~AlignedBytes();
+    void reserve(size_t want);
+    void resize_zero(size_t want);  // grow to `want`, new bytes zeroed
+    void clear() { n = 0; }
+};
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+}  // namespace pp
+
+struct pp_fasta {
+    std::vector<std::string> names, descriptions;
+    std::vector<uint64_t> off;     // n+1
+    std::string bases;             // upper-cased, concatenated
+    std::unordered_map<std::string, uint32_t> index;
+};
+
+struct pp_pack {
+    const pp_fasta* fasta = nullptr;
+    bool careful = false;
+    int seq_bits = 4;
+    bool need8 = false;
+    std::string error;
+    int error_code = 0;
+
+    // SoA (pp_alignments)
+    std::vector<uint32_t> contig, ref_start, read_id, seq_off, cigar_off, nm;
+    std::vector<uint16_t> seq_len, n_cigar;
+    std::vector<uint8_t> flags;
+    std::vector<uint32_t> cigar_ops;
+    pp::AlignedBytes seq_pool;
+    uint64_t seq_blocks = 0;       // pool length in PP_SEQ_BLOCK units
+
+    // names for error messages
+    std::string name_pool;                 // QNAMEs, NUL separated
+    std::vector<uint64_t> group_name_off;  // [n_reads]
+    std::unordered_map<uint64_t, std::string> unknown_ref;
+
+    struct FileStat { std::string name; uint64_t alignments = 0, reads = 0; };
+    std::vector<FileStat> files;
+
+    // sources kept so that an 8-bit repack can re-run them
+    struct Source { bool is_file; std::string path_or_name; std::string text; };
+    std::vector<Source> sources;
+    bool replaying = false;
+    bool no_replay = false;
+    void* stream = nullptr;        // open streaming file (sam_pack.cpp)
+    std::string tmp;
+};
+
+int pp_ctx_fail(pp_ctx* ctx, int code, const char* msg);

@@ -1,0 +1,412 @@
+// sam_pack.cpp — SAM text -> packed struct-of-arrays alignments (pp_alignments) for the polish path.
+//
+// Host side of the boundary: restates the TEXT handling of the reference, nothing else.
+//   add_to_pileup   /root/reference/src/alignment.rs:225-272  (line loop, '@'/empty skipping, grouping)
+//   Alignment::new  /root/reference/src/alignment.rs:49-98    (columns, FLAG/POS, NM / ZP tags, CIGAR check)
+//   get_expanded_cigar :325-346 (validation only: the CIGAR is kept run-length encoded, never expanded)
+//   get_read_seq_from_alignments :311-322 and add_read_seq :161-167 (source sequence of SEQ="*" records)
+// Everything downstream (goodness, k, CIGAR walk, trim, pileup, vote) happens on the device.
+#include <cstdio>
+#include <cstdlib>
+
+#include "pp_internal.h"
+
+namespace {
+
+struct NibTable {
+    uint8_t t[256];
+    NibTable() {
+        memset(t, 0, sizeof t);
+        const char* codes = "=ACMGRSVTWYHKDBN";
+        for (int i = 1; i < 16; ++i) {
+            t[(unsigned char)codes[i]] = (uint8_t)i;
+            t[(unsigned char)(codes[i] + 32)] = (uint8_t)i;  // lower case: SEQ is upper-cased (alignment.rs:94)
+        }
+    }
+};
+const NibTable NIB;
+
+inline int op_code(char c) {
+    switch (c) {
+        case 'M': return PP_OP_M; case 'I': return PP_OP_I; case 'D': return PP_OP_D; case 'N': return PP_OP_N;
+        case 'S': return PP_OP_S; case 'H': return PP_OP_H; case 'P': return PP_OP_P; case '=': return PP_OP_EQ;
+        case 'X': return PP_OP_X; default: return -1;
+    }
+}
+
+inline bool eq_ignore_case(std::string_view a, const char* b, size_t n) {
+    if (a.size() != n) return false;
+    for (size_t i = 0; i < n; ++i) {
+        char x = a[i], y = b[i];
+        if (x >= 'A' && x <= 'Z') x = (char)(x + 32);
+        if (y >= 'A' && y <= 'Z') y = (char)(y + 32);
+        if (x != y) return false;
+    }
+    return true;
+}
+
+std::string rust_debug_str(std::string_view s) {  // {:?} of a str, common escapes only
+    std::string o = "\"";
+    for (char c : s) {
+        if (c == '"') o += "\\\""; else if (c == '\\') o += "\\\\"; else if (c == '\t') o += "\\t"; else o += c;
+    }
+    return o + "\"";
+}
+
+struct GroupState {
+    bool name_empty = true;          // current_read_name.is_empty() (alignment.rs:255)
+    std::string_view name;
+    uint64_t first_aln = 0, n = 0;   // alignments of the open group
+    bool have_src = false;
+    uint32_t src_off = 0;
+    uint16_t src_len = 0;
+    uint8_t src_rev = 0;
+};
+
+struct Packer {
+    pp_pack* P;
+    const std::string& fname;
+    GroupState g;
+    uint64_t line_count = 0, alignment_count = 0, read_count = 0;
+
+    bool fail(int code, const std::string& m) { P->error = m; P->error_code = code; return false; }
+
+    bool close_group() {
+        if (g.n == 0) return true;
+        read_count++;
+        uint64_t gid = P->group_name_off.size();
+        P->group_name_off.push_back(P->name_pool.size());
+        P->name_pool.append(g.name.data(), g.name.size());
+        P->name_pool.push_back('\0');
+        bool skipped = P->careful && g.n > 1;   // alignment.rs:277-279
+        if (!g.have_src && !skipped)
+            return fail(PP_ERR_INPUT, "no alignments for read " + std::string(g.name) + " contain sequence");
+        for (uint64_t a = g.first_aln; a < g.first_aln + g.n; ++a) {
+            P->read_id[a] = (uint32_t)gid;
+            if (P->flags[a] & PP_FLAG_SEQSTAR) {
+                if (g.have_src) {
+                    P->seq_off[a] = g.src_off;
+                    P->seq_len[a] = g.src_len;
+                    if ((P->flags[a] & PP_FLAG_REVERSE) != g.src_rev) P->flags[a] |= PP_FLAG_RC;
+                } else {
+                    P->flags[a] |= PP_FLAG_NOSEQ;
+                }
+            }
+        }
+        if (gid >= 0xFFFFFFFFull) return fail(PP_ERR_INPUT, "more than 2^32-1 reads in one call are not supported");
+        g.n = 0;
+        g.have_src = false;
+        return true;
+    }
+
+    // Stores one sequence in the pool; returns false on unsupported input.
+    bool store_seq(std::string_view seq, uint32_t& off) {
+        if (P->seq_blocks >= 0xFFFFFFFFull) return fail(PP_ERR_INPUT, "sequence pool exceeds 2^32 blocks");
+        off = (uint32_t)P->seq_blocks;
+        size_t len = seq.size();
+        size_t blocks = (len + PP_SEQ_BLOCK - 1) / PP_SEQ_BLOCK;
+        if (P->seq_bits == 4) {
+            size_t base = P->seq_blocks * (PP_SEQ_BLOCK / 2);
+            P->seq_pool.resize_zero(base + blocks * (PP_SEQ_BLOCK / 2));
+            uint8_t* d = P->seq_pool.p + base;
+            bool exotic = false;
+            for (size_t j = 0; j < len; ++j) {
+                uint8_t c = NIB.t[(unsigned char)seq[j]];
+                exotic |= (c == 0);
+                d[j >> 1] |= (uint8_t)(c << ((j & 1) * 4));
+            }
+            if (exotic) P->need8 = true;
+        } else {
+            size_t base = P->seq_blocks * PP_SEQ_BLOCK;
+            P->seq_pool.resize_zero(base + blocks * PP_SEQ_BLOCK);
+            uint8_t* d = P->seq_pool.p + base;
+            for (size_t j = 0; j < len; ++j) {
+                char c = seq[j];
+                d[j] = (uint8_t)((c >= 'a' && c <= 'z') ? c - 32 : c);
+            }
+        }
+        P->seq_blocks += blocks;
+        return true;
+    }
+
+    bool line(std::string_view s) {
+        line_count++;
+        if (s.empty() || s[0] == '@') return true;     // alignment.rs:241-242
+        // split('\t'): need fields 0,1,2,3,5,9 and everything from 11 on
+        std::string_view f[11];
+        size_t pos = 0, nf = 0;
+        while (nf < 11) {
+            const char* t = (const char*)memchr(s.data() + pos, '\t', s.size() - pos);
+            if (!t) { f[nf++] = s.substr(pos); pos = s.size() + 1; break; }
+            size_t e = (size_t)(t - s.data());
+            f[nf++] = s.substr(pos, e - pos);
+            pos = e + 1;
+        }
+        auto where = [&]() { return " in \"" + fname + "\" (line " + std::to_string(line_count) + ")"; };
+        if (nf < 11) return fail(PP_ERR_INPUT, "too few columns" + where());
+        uint64_t v;
+        if (!pp::parse_uint(f[1], 0xFFFFFFFFull, v)) return fail(PP_ERR_INPUT, "invalid FLAG field " + rust_debug_str(f[1]) + where());
+        uint32_t sam_flags = (uint32_t)v;
+        if (!pp::parse_uint(f[3], ~0ull, v)) return fail(PP_ERR_INPUT, "invalid POS field " + rust_debug_str(f[3]) + where());
+        uint64_t rstart = v > 0 ? v - 1 : 0;            // alignment.rs:58-61
+        std::string_view cigar = f[5], seq = f[9];
+
+        uint32_t mismatches = 0xFFFFFFFFu;
+        bool pass_qc = true;
+        while (pos <= s.size()) {                        // tags, alignment.rs:67-75
+            const char* t = (const char*)memchr(s.data() + pos, '\t', s.size() - pos);
+            size_t e = t ? (size_t)(t - s.data()) : s.size();
+            std::string_view p = s.substr(pos, e - pos);
+            if (p.size() >= 5 && memcmp(p.data(), "NM:i:", 5) == 0) {
+                if (!pp::parse_uint(p.substr(5), 0xFFFFFFFFull, v)) return fail(PP_ERR_INPUT, "invalid NM tag " + rust_debug_str(p) + where());
+                mismatches = (uint32_t)v;
+            }
+            if (eq_ignore_case(p, "ZP:Z:fail", 9)) pass_qc = false;
+            pos = e + 1;
+        }
+        bool aligned = (sam_flags & 4) == 0;
+        if (mismatches == 0xFFFFFFFFu && aligned) return fail(PP_ERR_INPUT, "missing NM tag" + where());
+
+        // CIGAR: must be "*" or a concatenation of \d+[MIDNSHP=X] tokens (alignment.rs:325-346)
+        size_t ops_begin = P->cigar_ops.size();
+        bool cigar_ok = true;
+        if (!(cigar.size() == 1 && cigar[0] == '*')) {
+            size_t i = 0, n = cigar.size();
+            while (i < n) {
+                uint64_t len = 0;
+                size_t j = i;
+                bool big = false;
+                while (j < n && cigar[j] >= '0' && cigar[j] <= '9') {
+                    len = len * 10 + (uint64_t)(cigar[j] - '0');
+                    if (len > 0xFFFFFFFFull) big = true;
+                    j++;
+                }
+                int op = (j < n && j > i) ? op_code(cigar[j]) : -1;
+                if (op < 0) { cigar_ok = false; break; }
+                if (big) { P->cigar_ops.resize(ops_begin); return fail(PP_ERR_INPUT, "CIGAR operation length does not fit u32 for read " + std::string(f[0])); }
+                if (len > 0 && aligned) {
+                    if (len >= (1ull << 28)) { P->cigar_ops.resize(ops_begin); return fail(PP_ERR_INPUT, "CIGAR operation longer than 2^28-1 is not supported (read " + std::string(f[0]) + ")"); }
+                    P->cigar_ops.push_back((uint32_t)(len << 4) | (uint32_t)op);
+                }
+                i = j + 1;
+            }
+        }
+        if (!cigar_ok) {
+            P->cigar_ops.resize(ops_begin);
+            return fail(PP_ERR_INPUT, "encountered an invalid CIGAR string for read " + std::string(f[0]) + ": " + rust_debug_str(cigar));
+        }
+        if (!aligned) { P->cigar_ops.resize(ops_begin); return true; }   // alignment.rs:250
+
+        alignment_count++;
+        size_t nops = P->cigar_ops.size() - ops_begin;
+        if (nops == 0)   // the reference panics in starts_and_ends_with_match (alignment.rs:156)
+            return fail(PP_ERR_INPUT, "aligned record of read " + std::string(f[0]) + " has an empty CIGAR" + where());
+        if (nops > 0xFFFF) return fail(PP_ERR_INPUT, "more than 65535 CIGAR operations in one record are not supported" + where());
+        if (ops_begin > 0xFFFFFFFFull) return fail(PP_ERR_INPUT, "CIGAR pool exceeds 2^32 operations");
+        if (rstart > 0xFFFFFFFEull) return fail(PP_ERR_INPUT, "alignment start beyond 2^32 is not supported" + where());
+
+        // grouping (alignment.rs:255-263)
+        std::string_view name = f[0];
+        if (!(g.name_empty || g.name == name)) {
+            if (!close_group()) return false;
+        }
+        if (g.n == 0) g.first_aln = P->contig.size();
+        g.name = name;
+        g.name_empty = name.empty();
+        g.n++;
+
+        uint32_t cidx = PP_CONTIG_UNKNOWN;
+        {
+            P->tmp.assign(f[2].data(), f[2].size());
+            auto it = P->fasta->index.find(P->tmp);
+            if (it != P->fasta->index.end()) cidx = it->second;
+            else P->unknown_ref.emplace(P->contig.size(), P->tmp);
+        }
+        uint8_t fl = 0;
+        if (sam_flags & 16) fl |= PP_FLAG_REVERSE;
+        if (!pass_qc) fl |= PP_FLAG_ZPFAIL;
+        uint32_t soff = 0;
+        uint16_t slen = 0;
+        if (seq.size() == 1 && seq[0] == '*') {
+            fl |= PP_FLAG_SEQSTAR;
+        } else {
+            if (seq.size() > 0xFFFF) return fail(PP_ERR_INPUT, "reads longer than 65535 bases are not supported" + where());
+            if (!store_seq(seq, soff)) return false;
+            slen = (uint16_t)seq.size();
+            if (!g.have_src) {                          // first record whose SEQ != "*" (alignment.rs:311-318)
+                g.have_src = true;
+                g.src_off = soff;
+                g.src_len = slen;
+                g.src_rev = fl & PP_FLAG_REVERSE;
+            }
+        }
+        P->contig.push_back(cidx);
+        P->ref_start.push_back((uint32_t)rstart);
+        P->read_id.push_back(0);
+        P->seq_off.push_back(soff);
+        P->seq_len.push_back(slen);
+        P->cigar_off.push_back((uint32_t)ops_begin);
+        P->n_cigar.push_back((uint16_t)nops);
+        P->nm.push_back(mismatches);
+        P->flags.push_back(fl);
+        return true;
+    }
+};
+
+int finish_file(pp_pack* P, Packer& pk, const std::string& fname) {
+    if (pk.alignment_count == 0) {     // alignment.rs:268-270
+        P->error = "no alignments in \"" + fname + "\"";
+        P->error_code = PP_ERR_INPUT;
+        return PP_ERR_INPUT;
+    }
+    if (!pk.close_group()) return P->error_code;
+    pp_pack::FileStat st;
+    st.name = fname;
+    st.alignments = pk.alignment_count;
+    st.reads = pk.read_count;
+    P->files.push_back(st);
+    return PP_OK;
+}
+
+int pack_text(pp_pack* P, const char* data, size_t n, const std::string& fname) {
+    Packer pk{P, fname};
+    bool ok = true;
+    pp::for_each_line(data, n, [&](std::string_view s) { ok = pk.line(s); return ok; });
+    if (!ok) return P->error_code;
+    return finish_file(P, pk, fname);
+}
+
+// Streaming variant: one logical SAM file fed in chunks of whole lines.  The QNAME of the open group must
+// outlive a chunk, so it is copied.
+struct Stream {
+    std::string fname;
+    Packer pk;
+    std::string open_name;
+    Stream(pp_pack* P, const char* n) : fname(n ? n : "<stream>"), pk{P, fname} {}
+};
+
+void clear_arrays(pp_pack* P) {
+    P->contig.clear(); P->ref_start.clear(); P->read_id.clear(); P->seq_off.clear(); P->cigar_off.clear();
+    P->nm.clear(); P->seq_len.clear(); P->n_cigar.clear(); P->flags.clear(); P->cigar_ops.clear();
+    P->seq_pool.clear(); P->seq_blocks = 0; P->name_pool.clear(); P->group_name_off.clear();
+    P->unknown_ref.clear(); P->files.clear();
+}
+
+}  // namespace
+
+extern "C" pp_pack* pp_pack_create(const pp_fasta* f, int careful) {
+    if (!f) return nullptr;
+    pp_pack* P = new pp_pack();
+    P->fasta = f;
+    P->careful = careful != 0;
+    return P;
+}
+
+extern "C" void pp_pack_free(pp_pack* p) { delete p; }
+
+extern "C" int pp_pack_add_sam_file(pp_pack* P, const char* path) {
+    if (!P || !path) return PP_ERR_ARG;
+    std::string data;
+    if (!pp::read_file(path, data)) {
+        P->error = std::string("unable to load alignments from \"") + path + "\"";   // alignment.rs:219
+        P->error_code = PP_ERR_IO;
+        return PP_ERR_IO;
+    }
+    if (!P->replaying) P->sources.push_back({true, path, std::string()});
+    return pack_text(P, data.data(), data.size(), path);
+}
+
+extern "C" int pp_pack_add_sam_text(pp_pack* P, const char* text, size_t len, const char* name_for_errors) {
+    if (!P || (!text && len)) return PP_ERR_ARG;
+    std::string nm = name_for_errors ? name_for_errors : "<memory>";
+    if (!P->replaying) P->sources.push_back({false, nm, std::string(text, len)});
+    return pack_text(P, text, len, nm);
+}
+
+extern "C" int pp_pack_stream_begin(pp_pack* P, const char* name_for_errors) {
+    if (!P || P->stream) return PP_ERR_ARG;
+    P->stream = new Stream(P, name_for_errors);
+    P->no_replay = true;                      // streamed text is not retained: an exotic SEQ byte is an error
+    return PP_OK;
+}
+
+extern "C" int pp_pack_stream_feed(pp_pack* P, const char* text, size_t len) {
+    if (!P || !P->stream) return PP_ERR_ARG;
+    Stream* S = (Stream*)P->stream;
+    bool ok = true;
+    pp::for_each_line(text, len, [&](std::string_view s) { ok = S->pk.line(s); return ok; });
+    if (!ok) return P->error_code;
+    // keep the open group's QNAME alive beyond this chunk
+    S->open_name.assign(S->pk.g.name.data(), S->pk.g.name.size());
+    S->pk.g.name = S->open_name;
+    return PP_OK;
+}
+
+extern "C" int pp_pack_stream_end(pp_pack* P) {
+    if (!P || !P->stream) return PP_ERR_ARG;
+    Stream* S = (Stream*)P->stream;
+    int rc = finish_file(P, S->pk, S->fname);
+    delete S;
+    P->stream = nullptr;
+    return rc;
+}
+
+extern "C" int pp_pack_finish(pp_pack* P, pp_alignments* out) {
+    if (!P || !out) return PP_ERR_ARG;
+    if (P->need8 && P->seq_bits == 4 && P->no_replay) {
+        P->error = "a streamed SAM contains a SEQ character outside ACMGRSVTWYHKDBN; feed it as a file or whole text";
+        P->error_code = PP_ERR_INPUT;
+        return PP_ERR_INPUT;
+    }
+    if (P->need8 && P->seq_bits == 4) {
+        // A read contains a character outside "ACMGRSVTWYHKDBN": repack everything with 8-bit sequences so
+        // that allele strings stay byte-exact (pileup.rs:62 counts arbitrary strings).
+        clear_arrays(P);
+        P->seq_bits = 8;
+        P->need8 = false;
+        P->replaying = true;
+        for (auto& s : P->sources) {
+            int rc = s.is_file ? pp_pack_add_sam_file(P, s.path_or_name.c_str())
+                               : pp_pack_add_sam_text(P, s.text.data(), s.text.size(), s.path_or_name.c_str());
+            if (rc != PP_OK) { P->replaying = false; return rc; }
+        }
+        P->replaying = false;
+    }
+    memset(out, 0, sizeof *out);
+    out->n_aln = P->contig.size();
+    out->n_reads = P->group_name_off.size();
+    out->contig = P->contig.data();
+    out->ref_start = P->ref_start.data();
+    out->read_id = P->read_id.data();
+    out->seq_off = P->seq_off.data();
+    out->seq_len = P->seq_len.data();
+    out->cigar_off = P->cigar_off.data();
+    out->n_cigar = P->n_cigar.data();
+    out->nm = P->nm.data();
+    out->flags = P->flags.data();
+    out->n_cigar_ops = P->cigar_ops.size();
+    out->cigar_ops = P->cigar_ops.data();
+    out->seq_bits = (uint32_t)P->seq_bits;
+    out->seq_pool_bytes = P->seq_pool.n;
+    out->seq_pool = P->seq_pool.p;
+    return PP_OK;
+}
+
+extern "C" const char* pp_pack_error(const pp_pack* p) { return p ? p->error.c_str() : "null packer"; }
+
+extern "C" const char* pp_pack_unknown_ref(const pp_pack* p, uint64_t aln) {
+    auto it = p->unknown_ref.find(aln);
+    return it == p->unknown_ref.end() ? "" : it->second.c_str();
+}
+
+extern "C" const char* pp_pack_read_name(const pp_pack* p, uint64_t aln) {
+    if (aln >= p->read_id.size()) return "";
+    return p->name_pool.c_str() + p->group_name_off[p->read_id[aln]];
+}
+
+extern "C" int pp_pack_file_stats(const pp_pack* p, uint32_t file, uint64_t* alignments, uint64_t* reads) {
+    if (!p || file >= p->files.size()) return PP_ERR_ARG;
+    if (alignments) *alignments = p->files[file].alignments;
+    if (reads) *reads = p->files[file].reads;
+    return PP_OK;
+}
