@@ -202,6 +202,7 @@ const char* pp_pack_error(const pp_pack* p);
 /* name of the RNAME of alignment i when contig[i] == PP_CONTIG_UNKNOWN, and the QNAME of alignment i */
 const char* pp_pack_unknown_ref(const pp_pack* p, uint64_t aln);
 const char* pp_pack_read_name(const pp_pack* p, uint64_t aln);
+int pp_pack_cigar_string(const pp_pack* p, uint64_t aln, char* out, size_t cap); /* rebuilt from the packed ops */
 /* per file: aligned records and read groups (the stderr line of polish.rs:117-119) */
 int pp_pack_file_stats(const pp_pack* p, uint32_t file, uint64_t* alignments, uint64_t* reads);
 

@@ -105,9 +105,12 @@ extern "C" int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* co
                 m = "query name " + std::string(pp_pack_unknown_ref(pk, (uint64_t)res.error_aln)) + " in SAM but not in assembly";
             else if (m.rfind("CIGAR string does not", 0) == 0)
                 m = "CIGAR string for read " + std::string(rn) + " does not match read sequence";
-            else if (m.rfind("unexpected character", 0) == 0)
+            else if (m.rfind("unexpected character", 0) == 0) {
+                char cg[4096];
+                pp_pack_cigar_string(pk, (uint64_t)res.error_aln, cg, sizeof cg);
                 m = "unexpected character (other than M, =, X, I or D) in CIGAR string for read " + std::string(rn) +
-                    " - did you use BWA MEM to generate your alignments?";
+                    ": \"" + cg + "\" - did you use BWA MEM to generate your alignments?";
+            }
             else
                 m += " (read " + std::string(rn) + ")";
             rc = pp_ctx_fail(ctx, rc, m.c_str());

@@ -404,6 +404,22 @@ extern "C" const char* pp_pack_read_name(const pp_pack* p, uint64_t aln) {
     return p->name_pool.c_str() + p->group_name_off[p->read_id[aln]];
 }
 
+// The CIGAR of alignment i as text (rebuilt from the packed ops; used only for error messages).
+extern "C" int pp_pack_cigar_string(const pp_pack* p, uint64_t aln, char* out, size_t cap) {
+    if (!p || !out || cap == 0 || aln >= p->cigar_off.size()) return PP_ERR_ARG;
+    std::string s;
+    static const char* L = "MIDNSHP=X";
+    for (uint32_t i = 0; i < p->n_cigar[aln]; ++i) {
+        uint32_t op = p->cigar_ops[p->cigar_off[aln] + i];
+        s += std::to_string(op >> 4);
+        s += L[(op & 15u) < 9 ? (op & 15u) : 0];
+    }
+    size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(out, s.data(), n);
+    out[n] = 0;
+    return PP_OK;
+}
+
 extern "C" int pp_pack_file_stats(const pp_pack* p, uint32_t file, uint64_t* alignments, uint64_t* reads) {
     if (!p || file >= p->files.size()) return PP_ERR_ARG;
     if (alignments) *alignments = p->files[file].alignments;
