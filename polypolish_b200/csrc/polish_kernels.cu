@@ -76,7 +76,8 @@ struct DevData {                     // everything the kernels read, by value
     uint32_t* tileflag;              // bitmap, tiles that may hold k != 1 coverage
     double* depth_fix;               // [G] ordered depth for flagged tiles
     unsigned long long *fix_key, *fix_val;      // (tile<<32|aln) , (gstart<<32|n_kept)
-    uint32_t* oth_key;               // gpos
+    unsigned long long* oth_key;     // gpos << 32 | mix32(signature)
+    unsigned long long* oth_sig;     // allele signature: exact content for short alleles (see make_sig)
     unsigned long long* oth_val;     // aln<<32 | start<<16 | len
     uint32_t fix_cap, oth_cap;
     DevStatus* st;
@@ -126,6 +127,32 @@ template <> struct Seq<8> {
     static __device__ __forceinline__ int acgt(uint32_t s) { return s == 'A' ? 0 : s == 'C' ? 1 : s == 'G' ? 2 : s == 'T' ? 3 : -1; }
     static __device__ __forceinline__ uint8_t ascii(uint32_t s) { return (uint8_t)s; }
 };
+
+// Allele signature of an "other" allele (anything that is not a single A/C/G/T or "-"): the whole string for
+// short alleles (4-bit: <= 15 bases, 8-bit: <= 7 bytes) with the length in the low field, else length field 0
+// and a hash of the content (equality then falls back to comparing the sequences themselves).
+template <int BITS> __device__ __forceinline__ bool sig_exact(unsigned long long sig) {
+    return BITS == 4 ? (sig & 15ull) != 0 : (sig & 255ull) != 0;
+}
+template <int BITS>
+__device__ __forceinline__ unsigned long long make_sig(const uint8_t* pool, uint32_t off_blk, uint32_t slen, bool rc,
+                                                        uint32_t start, uint32_t len) {
+    const uint32_t maxlen = BITS == 4 ? 15 : 7;
+    if (len <= maxlen) {
+        unsigned long long sig = len;
+        for (uint32_t i = 0; i < len; ++i)
+            sig |= (unsigned long long)Seq<BITS>::read_sym(pool, off_blk, slen, rc, start + i) << ((BITS == 4 ? 4 : 8) * (i + 1));
+        return sig;
+    }
+    unsigned long long h = 0xcbf29ce484222325ull;
+    for (uint32_t i = 0; i < len; ++i) { h ^= Seq<BITS>::read_sym(pool, off_blk, slen, rc, start + i); h *= 0x100000001b3ull; }
+    h ^= len;
+    return h << (BITS == 4 ? 4 : 8);
+}
+__device__ __forceinline__ uint32_t mix32(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (uint32_t)x;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // k_draft_nib: ASCII draft -> 4-bit codes (0 = not one of the 15 letters: never equals a read code)
@@ -213,8 +240,8 @@ struct ScatterShared {
     uint16_t len[SC_THREADS], ncig[SC_THREADS];
     uint8_t fl[SC_THREADS];                       // bit0 good, bit1 rc, bit2 k != 1
     unsigned long long fix_key[SC_STAGE], fix_val[SC_STAGE];
-    unsigned long long oth_val[SC_STAGE];
-    uint32_t oth_key[SC_STAGE];
+    unsigned long long oth_val[SC_STAGE], oth_sig[SC_STAGE];
+    uint32_t oth_pos[SC_STAGE];
     uint32_t n_fix, n_oth, base_fix, base_oth;
     unsigned long long oth_len;
 };
@@ -223,14 +250,14 @@ template <int BITS> struct Scatter {
     const DevData& d;
     ScatterShared& sh;
 
-    __device__ __forceinline__ void push_other(uint32_t pos, unsigned long long aln, uint32_t start, uint32_t len) {
+    __device__ __forceinline__ void push_other(uint32_t pos, unsigned long long aln, uint32_t start, uint32_t len, unsigned long long sig) {
         atomicAdd(&d.delother[pos], 1u << 16);
         atomicAdd(&sh.oth_len, (unsigned long long)len);
         unsigned long long v = (aln << 32) | ((unsigned long long)(start & 0xFFFFu) << 16) | (len & 0xFFFFu);
         uint32_t s = atomicAdd(&sh.n_oth, 1u);
-        if (s < SC_STAGE) { sh.oth_key[s] = pos; sh.oth_val[s] = v; return; }
+        if (s < SC_STAGE) { sh.oth_pos[s] = pos; sh.oth_val[s] = v; sh.oth_sig[s] = sig; return; }
         uint32_t g = atomicAdd(&d.st->other_count, 1u);
-        if (g < d.oth_cap) { d.oth_key[g] = pos; d.oth_val[g] = v; }
+        if (g < d.oth_cap) { d.oth_key[g] = ((unsigned long long)pos << 32) | mix32(sig); d.oth_val[g] = v; d.oth_sig[g] = sig; }
         else atomicOr(&d.st->flags, FL_OTHER_OVF);
     }
     __device__ __forceinline__ void push_fix(uint32_t tile, unsigned long long aln, uint32_t gstart, uint32_t nkept) {
@@ -249,7 +276,7 @@ template <int BITS> struct Scatter {
         if (s == ds) return;                                   // counted implicitly: cover - explicit
         int c = Seq<BITS>::acgt(s);
         if (c >= 0) atomicAdd(&d.ex[pos], 1ull << (16 * c));
-        else push_other(pos, aln, ri, 1);
+        else push_other(pos, aln, ri, 1, 1ull | ((unsigned long long)s << (BITS == 4 ? 4 : 8)));
     }
     // interval add + fix-list membership for an alignment that keeps entries [gstart, gstart + nkept)
     __device__ __forceinline__ void add_interval(uint32_t lane8, unsigned long long aln, uint32_t gstart, uint32_t nkept, bool multi) {
@@ -374,7 +401,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                         const uint32_t code = (uint32_t)(r0 >> (4 * j)) & 15u;
                         const int c = Seq<4>::acgt(code);
                         if (c >= 0) atomicAdd(&d.ex[o + j], 1ull << (16 * c));
-                        else S.push_other(o + j, aln, b0 + j, 1);
+                        else S.push_other(o + j, aln, b0 + j, 1, 1ull | ((unsigned long long)code << 4));
                     }
                     while (m1) {
                         const uint32_t j = (uint32_t)(__ffsll((long long)m1) - 1) >> 2;
@@ -382,7 +409,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                         const uint32_t code = (uint32_t)(r1 >> (4 * j)) & 15u;
                         const int c = Seq<4>::acgt(code);
                         if (c >= 0) atomicAdd(&d.ex[o + 16 + j], 1ull << (16 * c));
-                        else S.push_other(o + 16 + j, aln, b0 + 16 + j, 1);
+                        else S.push_other(o + 16 + j, aln, b0 + 16 + j, 1, 1ull | ((unsigned long long)code << 4));
                     }
                 }
                 continue;
@@ -443,7 +470,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                     if (ins && lane8 == 0 && e + l - 1 < nkept) {
                         const uint32_t pos = gstart + e + l - 1;
                         if (ins == 1) S.count_base(pos, Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri), aln, ri);
-                        else S.push_other(pos, aln, ri, ins);
+                        else S.push_other(pos, aln, ri, ins, make_sig<BITS>(d.seq_pool, seqoff, len, rc, ri, ins));
                     }
                     e += l;
                     continue;
@@ -451,7 +478,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                 const uint32_t plain = ins ? l - 1 : l;               // M / = / X
                 for (uint32_t t = lane8; t < plain && e + t < nkept; t += 8)
                     S.count_base(gstart + e + t, Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri + t), aln, ri + t);
-                if (ins && lane8 == 0 && e + l - 1 < nkept) S.push_other(gstart + e + l - 1, aln, ri + l - 1, 1 + ins);
+                if (ins && lane8 == 0 && e + l - 1 < nkept)
+                    S.push_other(gstart + e + l - 1, aln, ri + l - 1, 1 + ins, make_sig<BITS>(d.seq_pool, seqoff, len, rc, ri + l - 1, 1 + ins));
                 e += l;
                 ri += l;
             }
@@ -474,7 +502,11 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
             }
             for (uint32_t i = tid; i < no; i += SC_THREADS) {
                 uint32_t g = sh.base_oth + i;
-                if (g < d.oth_cap) { d.oth_key[g] = sh.oth_key[i]; d.oth_val[g] = sh.oth_val[i]; }
+                if (g < d.oth_cap) {
+                    d.oth_key[g] = ((unsigned long long)sh.oth_pos[i] << 32) | mix32(sh.oth_sig[i]);
+                    d.oth_val[g] = sh.oth_val[i];
+                    d.oth_sig[g] = sh.oth_sig[i];
+                }
                 else atomicOr(&d.st->flags, FL_OTHER_OVF);
             }
         }
@@ -538,7 +570,11 @@ struct VoteParams {
     // look-back descriptors
     uint32_t* st1; unsigned long long *agg1, *inc1;
     uint32_t* st2; unsigned long long *agg2, *inc2;
-    const uint32_t* oth_key; const unsigned long long* oth_val; uint32_t n_oth;
+    const unsigned long long* okey;   // sorted (pos << 32 | mix32(sig))
+    const uint32_t* oidx;             // record index of each sorted key
+    const unsigned long long* osig;   // by record index
+    const unsigned long long* oval;   // by record index
+    uint32_t n_oth;
 };
 
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
@@ -633,10 +669,18 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
     return lo;
 }
 
-struct Verdict { uint32_t out_len; uint8_t ch; bool changed; bool slow_emit; uint32_t rec; };
+// What the other-allele slow path needs, passed by value so that the kernel parameter structs are never
+// spilled to local memory for a call.
+struct OthCtx {
+    const unsigned long long *okey, *osig, *oval;
+    const uint32_t *oidx, *seq_off;
+    const uint16_t* seq_len;
+    const uint8_t *flags, *seq_pool;
+    uint32_t n_oth;
+};
 
 template <int BITS>
-__device__ __forceinline__ bool other_equal(const DevData& d, unsigned long long va, unsigned long long vb) {
+__device__ bool other_equal(const OthCtx& d, unsigned long long va, unsigned long long vb) {
     const uint32_t la = (uint32_t)va & 0xFFFFu, lb = (uint32_t)vb & 0xFFFFu;
     if (la != lb) return false;
     const uint32_t aa = (uint32_t)(va >> 32), ab = (uint32_t)(vb >> 32);
@@ -648,64 +692,97 @@ __device__ __forceinline__ bool other_equal(const DevData& d, unsigned long long
     return true;
 }
 
-// The vote of pileup.rs:67-134 for one position.  counts = A,C,G,T,"-" (draft base already folded in),
-// matched = entries equal to a non-ACGT draft base, n_other = other-allele records at this position.
+struct Tally { uint32_t nvalid, ninter; int which; uint32_t rec; };   // which: 0..3 ACGT, 4 "-", 5 draft's own non-ACGT base, 6 other record
+
+__device__ __forceinline__ void tally(Tally& t, uint32_t c, uint32_t vt, uint32_t it, int which, uint32_t rec) {
+    if (c >= vt) { t.nvalid++; t.which = which; t.rec = rec; }
+    else if (c >= it) t.ninter++;
+}
+
+// Other alleles at `pos` (pileup.rs:102-109): the records of a position are contiguous in the sorted key array and
+// grouped by the hash of their signature; a group whose signatures are all the same exact signature is one allele.
 template <int BITS>
-__device__ Verdict vote_position(const DevData& d, const VoteParams& vp, uint32_t pos, uint8_t orig, double depth,
-                                 const uint32_t cnt[5], uint32_t matched, uint32_t n_other) {
+__device__ __noinline__ Tally tally_others(OthCtx vp, uint32_t pos, uint32_t vt, uint32_t it, Tally t) {
+    const OthCtx& d = vp;
+    const uint32_t n = vp.n_oth;
+    uint32_t i = lower_bound_u64(vp.okey, n, (unsigned long long)pos << 32);
+    while (i < n && (uint32_t)(vp.okey[i] >> 32) == pos) {
+        const unsigned long long k = vp.okey[i];
+        uint32_t j = i + 1;
+        while (j < n && vp.okey[j] == k) j++;
+        const unsigned long long s0 = vp.osig[vp.oidx[i]];
+        bool uniform = sig_exact<BITS>(s0);
+        for (uint32_t q = i + 1; q < j && uniform; ++q) uniform = vp.osig[vp.oidx[q]] == s0;
+        if (uniform) {
+            tally(t, j - i, vt, it, 6, vp.oidx[i]);
+        } else {                                   // hash collision or long alleles: exact pairwise counting
+            for (uint32_t a = i; a < j; ++a) {
+                const uint32_t ia = vp.oidx[a];
+                const unsigned long long sa = vp.osig[ia];
+                bool rep = true;
+                uint32_t c = 0;
+                for (uint32_t b2 = i; b2 < j; ++b2) {
+                    const uint32_t ib = vp.oidx[b2];
+                    bool eq = vp.osig[ib] == sa && (sig_exact<BITS>(sa) || other_equal<BITS>(d, vp.oval[ia], vp.oval[ib]));
+                    if (eq) { if (b2 < a) { rep = false; break; } c++; }
+                }
+                if (rep) tally(t, c, vt, it, 6, ia);
+            }
+        }
+        i = j;
+    }
+    return t;
+}
+
+// Symbol t of other-allele record `rec` (from the exact signature when there is one, else from the read).
+template <int BITS>
+__device__ __forceinline__ uint8_t other_char(const OthCtx& vp, uint32_t rec, uint32_t t) {
+    const OthCtx& d = vp;
+    const unsigned long long sig = vp.osig[rec];
+    if (sig_exact<BITS>(sig)) return Seq<BITS>::ascii((uint32_t)(sig >> ((BITS == 4 ? 4 : 8) * (t + 1))) & (BITS == 4 ? 15u : 255u));
+    const unsigned long long val = vp.oval[rec];
+    const uint32_t aln = (uint32_t)(val >> 32), start = (uint32_t)(val >> 16) & 0xFFFFu;
+    return Seq<BITS>::ascii(Seq<BITS>::read_sym(d.seq_pool, d.seq_off[aln], d.seq_len[aln], d.flags[aln] & PP_FLAG_RC, start + t));
+}
+
+// Result of one position, packed: bits 0..15 output length, 16..23 output char (when length is 1 and not from a
+// multi-base record), bit 24 changed, bit 25 emit from record `rec`.
+struct PosOut { uint32_t packed; uint32_t rec; };
+
+// The vote of pileup.rs:67-134 for one covered position.
+template <int BITS>
+__device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const VoteParams& vp, uint32_t pos, uint32_t orig, double depth,
+                                                uint32_t cA, uint32_t cC, uint32_t cG, uint32_t cT, uint32_t cDel,
+                                                uint32_t matched, uint32_t n_other) {
     const uint32_t vt = max(vp.min_depth, bankers_rounding(__dmul_rn(depth, vp.fv)));
     const uint32_t it = bankers_rounding(__dmul_rn(depth, vp.fi));
-    uint32_t nvalid = 0, ninter = 0;
-    int which = -1;                 // 0..3 ACGT, 4 "-", 5 the draft's own non-ACGT base, 6 an other-allele record
-    uint32_t which_rec = 0;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        if (c == 4 && cnt[4] == 0) break;                   // "-" exists only if it was seen (HashMap entry)
-        if (cnt[c] >= vt) { nvalid++; which = c; }
-        else if (cnt[c] >= it) ninter++;
-    }
-    if (matched > 0) {                                       // the 1-char string of a non-ACGT draft base
-        if (matched >= vt) { nvalid++; which = 5; }
-        else if (matched >= it) ninter++;
-    }
-    if (n_other > 0) {
-        const uint32_t lo = lower_bound_u32(vp.oth_key, vp.n_oth, pos);
-        uint32_t hi = lo;
-        while (hi < vp.n_oth && vp.oth_key[hi] == pos) hi++;
-        for (uint32_t i = lo; i < hi; ++i) {
-            const unsigned long long vi = vp.oth_val[i];
-            bool rep = true;
-            for (uint32_t j = lo; j < i && rep; ++j) if (other_equal<BITS>(d, vp.oth_val[j], vi)) rep = false;
-            if (!rep) continue;
-            uint32_t c = 1;
-            for (uint32_t j = i + 1; j < hi; ++j) if (other_equal<BITS>(d, vp.oth_val[j], vi)) c++;
-            if (c >= vt) { nvalid++; which = 6; which_rec = i; }
-            else if (c >= it) ninter++;
-        }
-    }
-    Verdict v;
-    v.ch = orig; v.out_len = (orig == '-') ? 0 : 1; v.changed = false; v.slow_emit = false; v.rec = 0;
-    if (depth < (double)vp.min_depth) return v;               // DepthTooLow
-    if (nvalid != 1 || ninter > 0) return v;                  // none / multiple / too_close
-    if (which <= 3) {
-        const uint8_t nb = (uint8_t)("ACGT"[which]);
-        v.changed = nb != orig; v.ch = nb; v.out_len = 1;
-    } else if (which == 4) {
-        v.changed = orig != '-'; v.ch = '-'; v.out_len = 0;
-    } else if (which == 5) {
-        // original base kept
-    } else {
-        const unsigned long long val = vp.oth_val[which_rec];
-        const uint32_t aln = (uint32_t)(val >> 32), start = (uint32_t)(val >> 16) & 0xFFFFu, len = (uint32_t)val & 0xFFFFu;
-        const bool rc = d.flags[aln] & PP_FLAG_RC;
+    Tally t{0, 0, -1, 0};
+    tally(t, cA, vt, it, 0, 0);
+    tally(t, cC, vt, it, 1, 0);
+    tally(t, cG, vt, it, 2, 0);
+    tally(t, cT, vt, it, 3, 0);
+    if (cDel) tally(t, cDel, vt, it, 4, 0);                  // "-" exists only if it was seen (a HashMap entry)
+    if (matched) tally(t, matched, vt, it, 5, 0);            // the 1-char string of a non-ACGT draft base
+    if (n_other) t = tally_others<BITS>(oc, pos, vt, it, t);
+    PosOut o;
+    o.rec = 0;
+    o.packed = (orig == '-' ? 0u : 1u) | (orig << 16);
+    if (depth < (double)vp.min_depth) return o;                // low_depth
+    if (t.nvalid != 1 || t.ninter > 0) return o;               // none / multiple / too_close
+    if (t.which <= 3) {
+        const uint32_t nb = (uint32_t)"ACGT"[t.which];
+        o.packed = 1u | (nb << 16) | (nb != orig ? 1u << 24 : 0u);
+    } else if (t.which == 4) {
+        o.packed = 0u | ((uint32_t)'-' << 16) | (orig != '-' ? 1u << 24 : 0u);
+    } else if (t.which == 6) {
+        const uint32_t len = (uint32_t)oc.oval[t.rec] & 0xFFFFu;
         uint32_t n = 0;
-        for (uint32_t i = 0; i < len; ++i)
-            if (Seq<BITS>::ascii(Seq<BITS>::read_sym(d.seq_pool, d.seq_off[aln], d.seq_len[aln], rc, start + i)) != '-') n++;
-        v.changed = true;     // an other-allele string never equals the draft's 1-char string (those are "matched")
-        v.out_len = n; v.slow_emit = true; v.rec = which_rec;
-        if (len == 1) { v.ch = Seq<BITS>::ascii(Seq<BITS>::read_sym(d.seq_pool, d.seq_off[aln], d.seq_len[aln], rc, start)); v.slow_emit = false; }
+        for (uint32_t q = 0; q < len; ++q) n += other_char<BITS>(oc, t.rec, q) != '-';
+        // an other-allele string never equals the draft's own 1-char string (those entries are "matched")
+        o.packed = (n & 0xFFFFu) | (1u << 24) | (1u << 25);
+        o.rec = t.rec;
     }
-    return v;
+    return o;
 }
 
 template <int BITS>
@@ -720,85 +797,94 @@ __global__ void __launch_bounds__(VT_THREADS) k_vote(DevData d, VoteParams vp) {
     if (chunk >= vp.n_chunks) return;
     const uint32_t p0 = chunk * VT_CHUNK + tid * VT_ITEMS;
 
-    // ---- 1. difference array -> cover / multi
+    // ---- 1. difference array -> cover / multi (arrays are padded to a whole number of chunks)
     unsigned long long dv[VT_ITEMS];
+    {
+        const ulonglong2* q = reinterpret_cast<const ulonglong2*>(d.diff + p0);
+#pragma unroll
+        for (int i = 0; i < VT_ITEMS / 2; ++i) { const ulonglong2 v = q[i]; dv[2 * i] = v.x; dv[2 * i + 1] = v.y; }
+    }
     unsigned long long tsum = 0;
 #pragma unroll
-    for (int i = 0; i < VT_ITEMS; ++i) {
-        const uint32_t p = p0 + i;
-        dv[i] = (p < d.G) ? d.diff[p] : 0ull;
-        tsum += dv[i];
-        dv[i] = tsum;                       // thread-inclusive
-    }
-    unsigned long long total;
-    unsigned long long texcl = block_exscan(tsum, s_warp, &s_total);
-    total = s_total;
+    for (int i = 0; i < VT_ITEMS; ++i) { tsum += dv[i]; dv[i] = tsum; }     // thread-inclusive
+    const unsigned long long texcl = block_exscan(tsum, s_warp, &s_total);
+    unsigned long long total = s_total;
     if (tid < 32) {
-        unsigned long long pre = lookback(chunk, total, vp.st1, vp.agg1, vp.inc1);
+        const unsigned long long pre = lookback(chunk, total, vp.st1, vp.agg1, vp.inc1);
         if (tid == 0) s_prefix = pre;
     }
     __syncthreads();
     const unsigned long long base = s_prefix + texcl;
 
     // ---- 2. vote
-    uint32_t olen[VT_ITEMS];
-    uint8_t och[VT_ITEMS];
-    uint32_t orec[VT_ITEMS];
-    uint32_t slowmask = 0;
+    unsigned long long exv[VT_ITEMS];
+    uint32_t dlv[VT_ITEMS];
+    {
+        const ulonglong2* q = reinterpret_cast<const ulonglong2*>(d.ex + p0);
+#pragma unroll
+        for (int i = 0; i < VT_ITEMS / 2; ++i) { const ulonglong2 v = q[i]; exv[2 * i] = v.x; exv[2 * i + 1] = v.y; }
+        const uint4* r = reinterpret_cast<const uint4*>(d.delother + p0);
+#pragma unroll
+        for (int i = 0; i < VT_ITEMS / 4; ++i) { const uint4 v = r[i]; dlv[4 * i] = v.x; dlv[4 * i + 1] = v.y; dlv[4 * i + 2] = v.z; dlv[4 * i + 3] = v.w; }
+    }
+    const uint2 dr = *reinterpret_cast<const uint2*>(d.draft + p0);
+    OthCtx oc;
+    oc.okey = vp.okey; oc.osig = vp.osig; oc.oval = vp.oval; oc.oidx = vp.oidx; oc.seq_off = d.seq_off; oc.seq_len = d.seq_len;
+    oc.flags = d.flags; oc.seq_pool = d.seq_pool; oc.n_oth = vp.n_oth;
+    PosOut po[VT_ITEMS];
     unsigned long long tlen = 0;
     uint32_t n_changed = 0, n_zero = 0;
-    // contig of the first position (binary search), advanced as positions cross contig boundaries
     uint32_t ctg = 0;
     if (p0 < d.G) {
         uint32_t lo = 0, hi = d.n_contigs;           // largest c with contig_off[c] <= p0
-        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (d.contig_off[mid] <= p0) lo = mid; else hi = mid; }
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (d.contig_off[mid] <= p0) lo = mid; else hi = mid; }
         ctg = lo;
     }
+    uint32_t next_start = (ctg + 1 < d.n_contigs) ? (uint32_t)d.contig_off[ctg + 1] : 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < VT_ITEMS; ++i) {
         const uint32_t p = p0 + i;
-        olen[i] = 0; och[i] = 0; orec[i] = 0;
+        po[i].packed = 0; po[i].rec = 0;
         if (p >= d.G) continue;
-        while (ctg + 1 < d.n_contigs && d.contig_off[ctg + 1] <= p) {
+        while (p >= next_start) {
             if (n_changed) atomicAdd(&vp.changed[ctg], (unsigned long long)n_changed);
             if (n_zero) atomicAdd(&vp.zero_depth[ctg], (unsigned long long)n_zero);
             n_changed = n_zero = 0;
             ctg++;
+            next_start = (ctg + 1 < d.n_contigs) ? (uint32_t)d.contig_off[ctg + 1] : 0xFFFFFFFFu;
         }
         const unsigned long long pv = base + dv[i];
         const uint32_t cover = (uint32_t)pv, multi = (uint32_t)(pv >> 32);
-        const uint8_t orig = d.draft[p];
-        if (cover >= 65536u) atomicOr(&d.st->flags, FL_COUNTER_OVF);
+        const uint32_t orig = ((i < 4 ? dr.x : dr.y) >> ((i & 3) * 8)) & 255u;
         if (cover == 0) {                                    // depth 0: always the original base
             n_zero++;
-            olen[i] = (orig == '-') ? 0 : 1; och[i] = orig;
-            tlen += olen[i];
+            po[i].packed = (orig == '-' ? 0u : 1u) | (orig << 16);
+            tlen += po[i].packed & 0xFFFFu;
             continue;
         }
-        const unsigned long long ex = d.ex[p];
-        const uint32_t dl = d.delother[p];
-        uint32_t cnt[5] = {(uint32_t)ex & 0xFFFFu, (uint32_t)(ex >> 16) & 0xFFFFu, (uint32_t)(ex >> 32) & 0xFFFFu,
-                           (uint32_t)(ex >> 48) & 0xFFFFu, dl & 0xFFFFu};
-        const uint32_t n_other = dl >> 16;
-        uint32_t matched = cover - (cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4] + n_other);
-        const int oc = orig == 'A' ? 0 : orig == 'C' ? 1 : orig == 'G' ? 2 : orig == 'T' ? 3 : -1;
-        if (oc >= 0) { cnt[oc] += matched; matched = 0; }
+        if (cover >= 65536u) atomicOr(&d.st->flags, FL_COUNTER_OVF);
+        const unsigned long long ex = exv[i];
+        uint32_t cA = (uint32_t)ex & 0xFFFFu, cC = (uint32_t)(ex >> 16) & 0xFFFFu, cG = (uint32_t)(ex >> 32) & 0xFFFFu,
+                 cT = (uint32_t)(ex >> 48) & 0xFFFFu;
+        const uint32_t cDel = dlv[i] & 0xFFFFu, n_other = dlv[i] >> 16;
+        uint32_t matched = cover - (cA + cC + cG + cT + cDel + n_other);
+        if (orig == 'A') { cA += matched; matched = 0; }
+        else if (orig == 'C') { cC += matched; matched = 0; }
+        else if (orig == 'G') { cG += matched; matched = 0; }
+        else if (orig == 'T') { cT += matched; matched = 0; }
         const double depth = multi ? d.depth_fix[p] : (double)cover;
-        if (depth == 0.0) n_zero++;
-        const Verdict v = vote_position<BITS>(d, vp, p, orig, depth, cnt, matched, n_other);
-        olen[i] = v.out_len; och[i] = v.ch; orec[i] = v.rec;
-        if (v.slow_emit) slowmask |= 1u << i;
-        if (v.changed) n_changed++;
-        tlen += v.out_len;
+        po[i] = vote_position<BITS>(oc, vp, p, orig, depth, cA, cC, cG, cT, cDel, matched, n_other);
+        n_changed += (po[i].packed >> 24) & 1u;
+        tlen += po[i].packed & 0xFFFFu;
     }
     if (n_changed) atomicAdd(&vp.changed[ctg], (unsigned long long)n_changed);
     if (n_zero) atomicAdd(&vp.zero_depth[ctg], (unsigned long long)n_zero);
 
     // ---- 3. output offsets (second look-back) and the compacted write
-    unsigned long long oexcl = block_exscan(tlen, s_warp, &s_total);
+    const unsigned long long oexcl = block_exscan(tlen, s_warp, &s_total);
     total = s_total;
     if (tid < 32) {
-        unsigned long long pre = lookback(chunk, total, vp.st2, vp.agg2, vp.inc2);
+        const unsigned long long pre = lookback(chunk, total, vp.st2, vp.agg2, vp.inc2);
         if (tid == 0) s_prefix = pre;
     }
     __syncthreads();
@@ -810,29 +896,34 @@ __global__ void __launch_bounds__(VT_THREADS) k_vote(DevData d, VoteParams vp) {
     // out_off of contigs that start inside this thread's positions
     if (p0 < d.G) {
         uint32_t lo = 0, hi = d.n_contigs;           // first c with contig_off[c] >= p0
-        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (d.contig_off[mid] < p0) lo = mid + 1; else hi = mid; }
-        unsigned long long oo = o;
-        uint32_t c = lo;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (d.contig_off[mid] < p0) lo = mid + 1; else hi = mid; }
+        if (lo < d.n_contigs && d.contig_off[lo] < (unsigned long long)p0 + VT_ITEMS) {
+            unsigned long long oo = o;
+            uint32_t c = lo;
 #pragma unroll
-        for (int i = 0; i < VT_ITEMS; ++i) {
-            const uint32_t p = p0 + i;
-            while (c < d.n_contigs && d.contig_off[c] == p) { vp.out_off[c] = oo; c++; }
-            oo += olen[i];
+            for (int i = 0; i < VT_ITEMS; ++i) {
+                const uint32_t p = p0 + i;
+                while (c < d.n_contigs && d.contig_off[c] == p) { vp.out_off[c] = oo; c++; }
+                oo += po[i].packed & 0xFFFFu;
+            }
         }
     }
+    if (o + tlen > vp.out_cap) { atomicOr(&d.st->flags, FL_OUT_OVF); return; }
 #pragma unroll
     for (int i = 0; i < VT_ITEMS; ++i) {
-        if (olen[i] == 0) continue;
-        if (o + olen[i] > vp.out_cap) { atomicOr(&d.st->flags, FL_OUT_OVF); o += olen[i]; continue; }
-        if (!((slowmask >> i) & 1u)) { vp.out[o] = och[i]; o += 1; continue; }
-        const unsigned long long val = vp.oth_val[orec[i]];
-        const uint32_t aln = (uint32_t)(val >> 32), start = (uint32_t)(val >> 16) & 0xFFFFu, len = (uint32_t)val & 0xFFFFu;
-        const bool rc = d.flags[aln] & PP_FLAG_RC;
-        for (uint32_t t = 0; t < len; ++t) {
-            const uint8_t ch = Seq<BITS>::ascii(Seq<BITS>::read_sym(d.seq_pool, d.seq_off[aln], d.seq_len[aln], rc, start + t));
+        const uint32_t len = po[i].packed & 0xFFFFu;
+        if (len == 0) continue;
+        if (!((po[i].packed >> 25) & 1u)) { vp.out[o] = (uint8_t)(po[i].packed >> 16); o += 1; continue; }
+        const uint32_t rlen = (uint32_t)vp.oval[po[i].rec] & 0xFFFFu;
+        for (uint32_t t = 0; t < rlen; ++t) {
+            const uint8_t ch = other_char<BITS>(oc, po[i].rec, t);
             if (ch != '-') vp.out[o++] = ch;                 // polish.rs:188 replace("-", "")
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_iota(uint32_t* a, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = i;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -855,9 +946,9 @@ struct DevBuf {
 };
 
 enum { B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL,
-       B_DRAFT, B_CTGOFF, B_AUX, B_K, B_NIB, B_DIFF, B_EX, B_DELOTHER, B_TILEFLAG, B_DEPTHFIX, B_FIXKEY, B_FIXVAL,
-       B_FIXKEY2, B_FIXVAL2, B_OTHKEY, B_OTHVAL, B_OTHKEY2, B_OTHVAL2, B_CUBTMP, B_OUT, B_OUTOFF, B_CHANGED, B_ZERO,
-       B_ST1, B_AGG1, B_INC1, B_ST2, B_AGG2, B_INC2, B_STATUS, B_COUNT };
+       B_DRAFT, B_CTGOFF, B_AUX, B_NIB, B_ZEROPOOL, B_DEPTHFIX, B_FIXKEY, B_FIXVAL,
+       B_FIXKEY2, B_FIXVAL2, B_OTHKEY, B_OTHVAL, B_OTHSIG, B_OTHIDX, B_OTHKEY2, B_OTHIDX2, B_CUBTMP, B_OUT, B_OUTOFF,
+       B_AGG1, B_INC1, B_AGG2, B_INC2, B_COUNT };
 
 struct pp_ctx {
     int device = 0;
@@ -936,8 +1027,20 @@ extern "C" void pp_destroy(pp_ctx* ctx) {
 
 extern "C" const char* pp_last_error(const pp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-// internal (host_api.cpp): lets the text layer report its errors through the same channel
+// internal (host_api.cpp, filter_kernels.cu): shared access to the context
 int pp_ctx_fail(pp_ctx* ctx, int code, const char* msg) { ctx->err = msg; return code; }
+int pp_ctx_device(pp_ctx* ctx) { return ctx->device; }
+cudaStream_t pp_ctx_stream(pp_ctx* ctx) { return ctx->stream; }
+cudaEvent_t pp_ctx_event(pp_ctx* ctx, int i) { return ctx->ev[i]; }
+void pp_ctx_count_launches(pp_ctx* ctx, uint32_t n) { ctx->launches = n; }
+int pp_ctx_fail_cuda(pp_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
+    ctx->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what + " (" + file + ":" + std::to_string(line) + ")";
+    return PP_ERR_CUDA;
+}
+void* pp_ctx_scratch(pp_ctx* ctx, size_t bytes) {
+    if (ctx->b[B_CUBTMP].ensure(bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return ctx->b[B_CUBTMP].p;
+}
 
 template <class T>
 static int upload(pp_ctx* ctx, int which, const T* src, size_t n, size_t pad_bytes = 64) {
@@ -971,7 +1074,7 @@ extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alig
     if ((rc = upload(ctx, B_FLAGS, a->flags, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_CIGOPS, a->cigar_ops, a->n_cigar_ops))) return rc;
     if ((rc = upload(ctx, B_SEQPOOL, a->seq_pool, a->seq_pool_bytes, 256))) return rc;
-    if ((rc = upload(ctx, B_DRAFT, c->bases, G, 256))) return rc;
+    if ((rc = upload(ctx, B_DRAFT, c->bases, G, VT_CHUNK + 256))) return rc;
     if ((rc = upload(ctx, B_CTGOFF, c->off, (size_t)c->n_contigs + 1))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_aln = a->n_aln; ctx->n_reads = a->n_reads; ctx->n_ops = a->n_cigar_ops; ctx->seq_bytes = a->seq_pool_bytes;
@@ -1006,24 +1109,26 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
     uint32_t oth_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, n_aln / 2 + 1024));
     uint64_t out_cap = G + 4096;
 
+    const size_t padG = (size_t)n_chunks * VT_CHUNK + 16;      // k_vote reads whole chunks with vector loads
     CK(ctx->b[B_AUX].ensure(n_aln + 64));
-    CK(ctx->b[B_K].ensure((ctx->n_reads + 1) * 4));
     CK(ctx->b[B_NIB].ensure(((size_t)nib_words + 8) * 8));
-    CK(ctx->b[B_DIFF].ensure((G + 2) * 8));
-    CK(ctx->b[B_EX].ensure((G + 1) * 8));
-    CK(ctx->b[B_DELOTHER].ensure((G + 1) * 4));
-    CK(ctx->b[B_TILEFLAG].ensure(((size_t)n_tiles / 32 + 2) * 4));
     CK(ctx->b[B_DEPTHFIX].ensure(((size_t)n_tiles * PP_TILE + 1) * 8));
     CK(ctx->b[B_OUTOFF].ensure(((size_t)ctx->n_contigs + 1) * 8));
-    CK(ctx->b[B_CHANGED].ensure((size_t)ctx->n_contigs * 8));
-    CK(ctx->b[B_ZERO].ensure((size_t)ctx->n_contigs * 8));
-    CK(ctx->b[B_ST1].ensure((size_t)n_chunks * 4)); CK(ctx->b[B_AGG1].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC1].ensure((size_t)n_chunks * 8));
-    CK(ctx->b[B_ST2].ensure((size_t)n_chunks * 4)); CK(ctx->b[B_AGG2].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC2].ensure((size_t)n_chunks * 8));
-    CK(ctx->b[B_STATUS].ensure(sizeof(DevStatus)));
+    CK(ctx->b[B_AGG1].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC1].ensure((size_t)n_chunks * 8));
+    CK(ctx->b[B_AGG2].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC2].ensure((size_t)n_chunks * 8));
+    // everything that must be zero at the start of a call lives in one pool: one memset
+    size_t zoff = 0;
+    auto carve = [&](size_t bytes) { size_t o = zoff; zoff += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_diff = carve(padG * 8), o_ex = carve(padG * 8), o_del = carve(padG * 4), o_k = carve((ctx->n_reads + 1) * 4),
+                 o_tile = carve(((size_t)n_tiles / 32 + 2) * 4), o_st1 = carve((size_t)n_chunks * 4), o_st2 = carve((size_t)n_chunks * 4),
+                 o_chg = carve((size_t)ctx->n_contigs * 8), o_zero = carve((size_t)ctx->n_contigs * 8), o_status = carve(sizeof(DevStatus));
+    CK(ctx->b[B_ZEROPOOL].ensure(zoff));
+    uint8_t* zp = ctx->b[B_ZEROPOOL].as<uint8_t>();
 
     for (int attempt = 0; attempt < 6; ++attempt) {
         CK(ctx->b[B_FIXKEY].ensure((size_t)fix_cap * 8)); CK(ctx->b[B_FIXVAL].ensure((size_t)fix_cap * 8));
-        CK(ctx->b[B_OTHKEY].ensure((size_t)oth_cap * 4)); CK(ctx->b[B_OTHVAL].ensure((size_t)oth_cap * 8));
+        CK(ctx->b[B_OTHKEY].ensure((size_t)oth_cap * 8)); CK(ctx->b[B_OTHVAL].ensure((size_t)oth_cap * 8));
+        CK(ctx->b[B_OTHSIG].ensure((size_t)oth_cap * 8));
         CK(ctx->b[B_OUT].ensure(out_cap + 64));
 
         DevData d;
@@ -1035,27 +1140,19 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         d.n_cigar = ctx->b[B_NCIG].as<uint16_t>(); d.flags = ctx->b[B_FLAGS].as<uint8_t>();
         d.seq_pool = ctx->b[B_SEQPOOL].as<uint8_t>(); d.draft = ctx->b[B_DRAFT].as<uint8_t>();
         d.contig_off = ctx->b[B_CTGOFF].as<unsigned long long>(); d.n_contigs = ctx->n_contigs; d.G = (uint32_t)G;
-        d.aux = ctx->b[B_AUX].as<uint8_t>(); d.k = ctx->b[B_K].as<uint32_t>();
-        d.draft_nib = ctx->b[B_NIB].as<unsigned long long>(); d.diff = ctx->b[B_DIFF].as<unsigned long long>();
-        d.ex = ctx->b[B_EX].as<unsigned long long>(); d.delother = ctx->b[B_DELOTHER].as<uint32_t>();
-        d.tileflag = ctx->b[B_TILEFLAG].as<uint32_t>(); d.depth_fix = ctx->b[B_DEPTHFIX].as<double>();
+        d.aux = ctx->b[B_AUX].as<uint8_t>(); d.k = (uint32_t*)(zp + o_k);
+        d.draft_nib = ctx->b[B_NIB].as<unsigned long long>(); d.diff = (unsigned long long*)(zp + o_diff);
+        d.ex = (unsigned long long*)(zp + o_ex); d.delother = (uint32_t*)(zp + o_del);
+        d.tileflag = (uint32_t*)(zp + o_tile); d.depth_fix = ctx->b[B_DEPTHFIX].as<double>();
         d.fix_key = ctx->b[B_FIXKEY].as<unsigned long long>(); d.fix_val = ctx->b[B_FIXVAL].as<unsigned long long>();
-        d.oth_key = ctx->b[B_OTHKEY].as<uint32_t>(); d.oth_val = ctx->b[B_OTHVAL].as<unsigned long long>();
+        d.oth_key = ctx->b[B_OTHKEY].as<unsigned long long>(); d.oth_val = ctx->b[B_OTHVAL].as<unsigned long long>();
+        d.oth_sig = ctx->b[B_OTHSIG].as<unsigned long long>();
         d.fix_cap = fix_cap; d.oth_cap = oth_cap;
-        d.st = ctx->b[B_STATUS].as<DevStatus>();
+        d.st = (DevStatus*)(zp + o_status);
 
         // ---- stage 0: reset
         CK(cudaEventRecord(ctx->ev[0], s));
-        CK(cudaMemsetAsync(d.k, 0, (ctx->n_reads + 1) * 4, s));
-        CK(cudaMemsetAsync(d.diff, 0, (G + 2) * 8, s));
-        CK(cudaMemsetAsync(d.ex, 0, (G + 1) * 8, s));
-        CK(cudaMemsetAsync(d.delother, 0, (G + 1) * 4, s));
-        CK(cudaMemsetAsync(d.tileflag, 0, ((size_t)n_tiles / 32 + 2) * 4, s));
-        CK(cudaMemsetAsync(ctx->b[B_ST1].p, 0, (size_t)n_chunks * 4, s));
-        CK(cudaMemsetAsync(ctx->b[B_ST2].p, 0, (size_t)n_chunks * 4, s));
-        CK(cudaMemsetAsync(ctx->b[B_CHANGED].p, 0, (size_t)ctx->n_contigs * 8, s));
-        CK(cudaMemsetAsync(ctx->b[B_ZERO].p, 0, (size_t)ctx->n_contigs * 8, s));
-        CK(cudaMemsetAsync(d.st, 0, sizeof(DevStatus), s));
+        CK(cudaMemsetAsync(zp, 0, zoff, s));
         CK(cudaMemsetAsync(&d.st->err, 0xFF, 8, s));
         if (BITS == 4) {
             CK(cudaMemsetAsync(d.draft_nib + nib_words, 0, 64, s));
@@ -1109,20 +1206,25 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
             k_depth_fixup<<<n_tiles, PP_TILE, 0, s>>>(d, fkeys, fvals, hs.fix_count);
             ctx->launches++;
         }
-        // ---- stage 4: sort other-allele records by position
+        // ---- stage 4: sort other-allele records by (position, signature hash)
         CK(cudaEventRecord(ctx->ev[4], s));
-        const uint32_t* okeys = d.oth_key;
-        const unsigned long long* ovals = d.oth_val;
+        const unsigned long long* okeys = d.oth_key;
+        const uint32_t* oidx = nullptr;
         if (hs.other_count) {
-            CK(ctx->b[B_OTHKEY2].ensure((size_t)hs.other_count * 4)); CK(ctx->b[B_OTHVAL2].ensure((size_t)hs.other_count * 8));
+            CK(ctx->b[B_OTHKEY2].ensure((size_t)hs.other_count * 8));
+            CK(ctx->b[B_OTHIDX].ensure((size_t)hs.other_count * 4)); CK(ctx->b[B_OTHIDX2].ensure((size_t)hs.other_count * 4));
+            k_iota<<<std::min<uint32_t>((hs.other_count + 255) / 256, ctx->sm_count * 4), 256, 0, s>>>(ctx->b[B_OTHIDX].as<uint32_t>(), hs.other_count);
+            ctx->launches++;
+            int pos_bits = 1;
+            while ((1ull << pos_bits) < G) pos_bits++;
             size_t tmp = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d.oth_key, ctx->b[B_OTHKEY2].as<uint32_t>(), d.oth_val,
-                                               ctx->b[B_OTHVAL2].as<unsigned long long>(), (int)hs.other_count, 0, 32, s));
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d.oth_key, ctx->b[B_OTHKEY2].as<unsigned long long>(), ctx->b[B_OTHIDX].as<uint32_t>(),
+                                               ctx->b[B_OTHIDX2].as<uint32_t>(), (int)hs.other_count, 0, 32 + pos_bits, s));
             CK(ctx->b[B_CUBTMP].ensure(tmp));
-            CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, tmp, d.oth_key, ctx->b[B_OTHKEY2].as<uint32_t>(), d.oth_val,
-                                               ctx->b[B_OTHVAL2].as<unsigned long long>(), (int)hs.other_count, 0, 32, s));
-            okeys = ctx->b[B_OTHKEY2].as<uint32_t>();
-            ovals = ctx->b[B_OTHVAL2].as<unsigned long long>();
+            CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, tmp, d.oth_key, ctx->b[B_OTHKEY2].as<unsigned long long>(), ctx->b[B_OTHIDX].as<uint32_t>(),
+                                               ctx->b[B_OTHIDX2].as<uint32_t>(), (int)hs.other_count, 0, 32 + pos_bits, s));
+            okeys = ctx->b[B_OTHKEY2].as<unsigned long long>();
+            oidx = ctx->b[B_OTHIDX2].as<uint32_t>();
         }
         // ---- stage 5: vote + compaction
         CK(cudaEventRecord(ctx->ev[5], s));
@@ -1130,10 +1232,10 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         vp.fv = prm->fraction_valid; vp.fi = prm->fraction_invalid; vp.min_depth = prm->min_depth; vp.n_chunks = n_chunks;
         vp.out = ctx->b[B_OUT].as<uint8_t>(); vp.out_cap = out_cap;
         vp.out_off = ctx->b[B_OUTOFF].as<unsigned long long>();
-        vp.changed = ctx->b[B_CHANGED].as<unsigned long long>(); vp.zero_depth = ctx->b[B_ZERO].as<unsigned long long>();
-        vp.st1 = ctx->b[B_ST1].as<uint32_t>(); vp.agg1 = ctx->b[B_AGG1].as<unsigned long long>(); vp.inc1 = ctx->b[B_INC1].as<unsigned long long>();
-        vp.st2 = ctx->b[B_ST2].as<uint32_t>(); vp.agg2 = ctx->b[B_AGG2].as<unsigned long long>(); vp.inc2 = ctx->b[B_INC2].as<unsigned long long>();
-        vp.oth_key = okeys; vp.oth_val = ovals; vp.n_oth = hs.other_count;
+        vp.changed = (unsigned long long*)(zp + o_chg); vp.zero_depth = (unsigned long long*)(zp + o_zero);
+        vp.st1 = (uint32_t*)(zp + o_st1); vp.agg1 = ctx->b[B_AGG1].as<unsigned long long>(); vp.inc1 = ctx->b[B_INC1].as<unsigned long long>();
+        vp.st2 = (uint32_t*)(zp + o_st2); vp.agg2 = ctx->b[B_AGG2].as<unsigned long long>(); vp.inc2 = ctx->b[B_INC2].as<unsigned long long>();
+        vp.okey = okeys; vp.oidx = oidx; vp.osig = d.oth_sig; vp.oval = d.oth_val; vp.n_oth = hs.other_count;
         k_vote<BITS><<<n_chunks, VT_THREADS, 0, s>>>(d, vp);
         ctx->launches++;
         CK(cudaEventRecord(ctx->ev[6], s));
