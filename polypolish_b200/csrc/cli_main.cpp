@@ -1,0 +1,139 @@
+// cli_main.cpp — the `polypolish` command line, drop-in for the reference's (main.rs:23-126).
+//
+// Same subcommands, flag names (note the underscores), defaults and validation messages:
+//   polypolish filter --in1 F --in2 F --out1 F --out2 F [--orientation auto] [--low 0.1] [--high 99.9]
+//   polypolish polish [--debug F] [-i|--fraction_invalid 0.2] [-v|--fraction_valid 0.5] [-m|--max_errors 10]
+//                     [-d|--min_depth 5] [--careful] <ASSEMBLY> [SAM]...
+// Polished FASTA on stdout, log on stderr, "Error: <msg>" + exit 1 on user errors (misc.rs:29-33).
+// Additive flags: --device N (which GPU), --quiet.  All compute happens in libpolypolish_b200.so on the GPU.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pp_abi.h"
+
+static const char* BANNER =
+    "  _____        _                       _  _       _     \n"
+    " |  __ \\      | |                     | |(_)     | |    \n"
+    " | |__) |___  | | _   _  _ __    ___  | | _  ___ | |__  \n"
+    " |  ___// _ \\ | || | | || '_ \\  / _ \\ | || |/ __|| '_ \\ \n"
+    " | |   | (_) || || |_| || |_) || (_) || || |\\__ \\| | | |\n"
+    " |_|    \\___/ |_| \\__, || .__/  \\___/ |_||_||___/|_| |_|\n"
+    "                   __/ || |                             \n"
+    "                  |___/ |_|                             \n";
+
+[[noreturn]] static void quit_with_error(const std::string& text) {   // misc.rs:29-33
+    fprintf(stderr, "\nError: %s\n", text.c_str());
+    exit(1);
+}
+
+[[noreturn]] static void usage_error(const std::string& text) {      // clap argument errors exit with 2
+    fprintf(stderr, "error: %s\n\nFor more information, try '--help'.\n", text.c_str());
+    exit(2);
+}
+
+static void help() {
+    fputs(BANNER, stdout);
+    puts("short-read polishing of long-read assemblies (B200-native build)\ngithub.com/rrwick/Polypolish\n");
+    puts("Usage: polypolish <COMMAND>\n");
+    puts("Commands:\n  filter  filter paired-end alignments based on insert size\n  polish  polish a long-read assembly using short-read alignments\n");
+    puts("Options:\n  -h, --help     Print help\n  -V, --version  Print version");
+    puts("\npolypolish filter --in1 <IN1> --in2 <IN2> --out1 <OUT1> --out2 <OUT2> [--orientation <auto>] [--low <0.1>] [--high <99.9>]");
+    puts("polypolish polish [--debug <DEBUG>] [-i|--fraction_invalid <0.2>] [-v|--fraction_valid <0.5>] [-m|--max_errors <10>]");
+    puts("                  [-d|--min_depth <5>] [--careful] <ASSEMBLY> [SAM]...");
+    puts("Additive: --device <N> (GPU index, default 0), --quiet");
+}
+
+static double parse_f64(const char* flag, const char* s) {
+    char* end = nullptr;
+    double v = strtod(s, &end);
+    if (!s[0] || (end && *end)) usage_error(std::string("invalid value '") + s + "' for '" + flag + "': invalid float literal");
+    return v;
+}
+static uint32_t parse_u32(const char* flag, const char* s) {
+    char* end = nullptr;
+    if (s[0] == '-') usage_error(std::string("invalid value '") + s + "' for '" + flag + "': invalid digit found in string");
+    unsigned long long v = strtoull(s, &end, 10);
+    if (!s[0] || (end && *end) || v > 0xFFFFFFFFull) usage_error(std::string("invalid value '") + s + "' for '" + flag + "'");
+    return (uint32_t)v;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { help(); return 2; }
+    std::string cmd = argv[1];
+    if (cmd == "-h" || cmd == "--help") { help(); return 0; }
+    if (cmd == "-V" || cmd == "--version") { puts("Polypolish v0.6.1"); return 0; }
+    int device = 0;
+    bool quiet = false;
+    auto need = [&](int& i, const char* flag) -> const char* {
+        if (i + 1 >= argc) usage_error(std::string("a value is required for '") + flag + "' but none was supplied");
+        return argv[++i];
+    };
+    if (cmd == "polish") {
+        pp_polish_params prm{0.2, 0.5, 10, 5, 0};
+        std::string debug;
+        std::vector<std::string> pos;
+        for (int i = 2; i < argc; ++i) {
+            std::string a = argv[i];
+            if (a == "-h" || a == "--help") { help(); return 0; }
+            else if (a == "-V" || a == "--version") { puts("Polypolish-polish v0.6.1"); return 0; }
+            else if (a == "--debug") debug = need(i, "--debug <DEBUG>");
+            else if (a == "-i" || a == "--fraction_invalid") prm.fraction_invalid = parse_f64("--fraction_invalid <FRACTION_INVALID>", need(i, "--fraction_invalid"));
+            else if (a == "-v" || a == "--fraction_valid") prm.fraction_valid = parse_f64("--fraction_valid <FRACTION_VALID>", need(i, "--fraction_valid"));
+            else if (a == "-m" || a == "--max_errors") prm.max_errors = parse_u32("--max_errors <MAX_ERRORS>", need(i, "--max_errors"));
+            else if (a == "-d" || a == "--min_depth") prm.min_depth = parse_u32("--min_depth <MIN_DEPTH>", need(i, "--min_depth"));
+            else if (a == "--careful") prm.careful = 1;
+            else if (a == "--device") device = (int)parse_u32("--device", need(i, "--device"));
+            else if (a == "--quiet") quiet = true;
+            else if (a.size() > 1 && a[0] == '-' && a != "-") usage_error("unexpected argument '" + a + "' found");
+            else pos.push_back(a);
+        }
+        if (pos.empty()) usage_error("the following required arguments were not provided:\n  <ASSEMBLY>");
+        pp_ctx* ctx = nullptr;
+        if (pp_create(device, &ctx) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
+        std::vector<const char*> sams;
+        for (size_t i = 1; i < pos.size(); ++i) sams.push_back(pos[i].c_str());
+        char* out = nullptr;
+        uint64_t n = 0;
+        if (!quiet) fprintf(stderr, "Starting Polypolish polish (B200 build %s)\n\n", pp_version());
+        int rc = pp_polish_files(ctx, pos[0].c_str(), sams.data(), (int)sams.size(), &prm, debug.empty() ? nullptr : debug.c_str(), &out, &n, quiet ? 0 : 1);
+        if (rc != PP_OK) { std::string m = pp_last_error(ctx); pp_destroy(ctx); quit_with_error(m); }
+        fwrite(out, 1, n, stdout);
+        fflush(stdout);
+        pp_free(out);
+        pp_destroy(ctx);
+        if (!quiet) fprintf(stderr, "Finished!\n");
+        return 0;
+    }
+    if (cmd == "filter") {
+        std::string in1, in2, out1, out2, orientation = "auto";
+        double low = 0.1, high = 99.9;
+        for (int i = 2; i < argc; ++i) {
+            std::string a = argv[i];
+            if (a == "-h" || a == "--help") { help(); return 0; }
+            else if (a == "--in1") in1 = need(i, "--in1 <IN1>");
+            else if (a == "--in2") in2 = need(i, "--in2 <IN2>");
+            else if (a == "--out1") out1 = need(i, "--out1 <OUT1>");
+            else if (a == "--out2") out2 = need(i, "--out2 <OUT2>");
+            else if (a == "--orientation") orientation = need(i, "--orientation <ORIENTATION>");
+            else if (a == "--low") low = parse_f64("--low <LOW>", need(i, "--low"));
+            else if (a == "--high") high = parse_f64("--high <HIGH>", need(i, "--high"));
+            else if (a == "--device") device = (int)parse_u32("--device", need(i, "--device"));
+            else if (a == "--quiet") quiet = true;
+            else usage_error("unexpected argument '" + a + "' found");
+        }
+        if (in1.empty() || in2.empty() || out1.empty() || out2.empty())
+            usage_error("the following required arguments were not provided:\n  --in1 <IN1>\n  --in2 <IN2>\n  --out1 <OUT1>\n  --out2 <OUT2>");
+        pp_ctx* ctx = nullptr;
+        if (pp_create(device, &ctx) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
+        if (!quiet) fprintf(stderr, "Starting Polypolish filter (B200 build %s)\n\n", pp_version());
+        int rc = pp_filter_files(ctx, in1.c_str(), in2.c_str(), out1.c_str(), out2.c_str(), orientation.c_str(), low, high, quiet ? 0 : 1);
+        if (rc != PP_OK) { std::string m = pp_last_error(ctx); pp_destroy(ctx); quit_with_error(m); }
+        pp_destroy(ctx);
+        if (!quiet) fprintf(stderr, "Finished!\n");
+        return 0;
+    }
+    usage_error("unrecognized subcommand '" + cmd + "'");
+}

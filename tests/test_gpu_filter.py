@@ -1,0 +1,155 @@
+"""GPU parity tests for `polypolish filter`: thresholds, orientation and the re-streamed SAM files against the
+CPU oracle, byte for byte."""
+import random
+
+import pytest
+
+import polypolish_b200 as pp
+from polypolish_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import __graft_entry__ as g
+    g.build()
+    c = pp.Context(0)
+    yield c
+    c.close()
+
+
+def run_both(ctx, oracle, in1, in2, tmp_path, **kw):
+    o1, o2 = tmp_path / "o1.sam", tmp_path / "o2.sam"
+    try:
+        exp = ("ok", oracle.filter(in1, in2, out1=o1, out2=o2, **kw))
+    except Exception as e:
+        exp = ("err", e.msg)
+    try:
+        ctx.filter_files(in1, in2, o1, o2, **kw)
+        got = ("ok", dict(out1=open(o1, "rb").read(), out2=open(o2, "rb").read()))
+    except pp.PolypolishError as e:
+        got = ("err", e.msg)
+    assert exp[0] == got[0], (exp, got if got[0] == "err" else "")
+    if exp[0] == "ok":
+        assert got[1]["out1"] == exp[1]["out1"]
+        assert got[1]["out2"] == exp[1]["out2"]
+    else:
+        assert got[1] == exp[1]
+    return exp
+
+
+def random_pairs(seed, n_pairs=300, orient="fr", eol="\n", shuffle_groups=False):
+    """Small paired SAMs: unique pairs (insert ~ N(300,30)) plus multi-mapped reads whose mates sit at good and bad
+    distances / strands / contigs; unaligned records; reads present in one file only."""
+    rng = random.Random(seed)
+    refs = ["ctgA", "ctgB"]
+    f = [["@HD\tVN:1.6", "@SQ\tSN:ctgA\tLN:100000", "@SQ\tSN:ctgB\tLN:100000"], ["@HD\tVN:1.6"]]
+
+    def rec(name, flag, ref, pos, cigar="100M", extra=()):
+        return "\t".join([name, str(flag), ref, str(pos), "60", cigar, "*", "0", "0", "ACGT", "IIII", "NM:i:0", *extra])
+
+    def pair_flags():
+        if orient == "fr":
+            return 0, 16
+        if orient == "rf":
+            return 16, 0
+        if orient == "ff":
+            return 0, 0
+        return 16, 16
+    for i in range(n_pairs):
+        name = f"p{i}"
+        ref = rng.choice(refs)
+        a = rng.randint(1, 90000)
+        ins = max(150, int(rng.gauss(300, 30)))
+        fa, fb = pair_flags()
+        left, right = a, a + ins - 100
+        r = rng.random()
+        recs1, recs2 = [rec(name, fa, ref, left, rng.choice(["100M", "50M2D50M", "40M3I57M", "5S95M"]))], [rec(name, fb, ref, right)]
+        if r < 0.25:                                           # mate 1 multi-mapped: one good, some bad locations
+            for _ in range(rng.randint(1, 4)):
+                recs1.append(rec(name, 256 | rng.choice([0, 16]), rng.choice(refs), rng.randint(1, 90000)))
+        elif r < 0.4:                                          # both multi-mapped
+            for _ in range(rng.randint(1, 3)):
+                recs1.append(rec(name, 256 | fa, ref, left + rng.choice([0, 1000, -50, 5])))
+                recs2.append(rec(name, 256 | fb, ref, right + rng.choice([0, 1000, 3, 20000])))
+        elif r < 0.45:
+            recs2 = []                                         # mate missing entirely
+        elif r < 0.5:
+            recs2 = [rec(name, 4, "*", 0, "*")]                # mate unaligned
+        elif r < 0.55:
+            recs1.append(rec(name, 4, "*", 0, "*"))
+        if rng.random() < 0.5:
+            rng.shuffle(recs1)
+        f[0].extend(recs1)
+        f[1].extend(recs2)
+    if shuffle_groups:                                         # names not consecutive: the reference groups by name anyway
+        body = f[0][3:]
+        rng.shuffle(body)
+        f[0] = f[0][:3] + body
+    return eol.join(f[0]) + eol, eol.join(f[1]) + eol
+
+
+@pytest.mark.parametrize("seed,orient", [(1, "fr"), (2, "rf"), (3, "ff"), (4, "rr"), (5, "fr"), (6, "fr")])
+def test_random_pairs(ctx, oracle, tmp_path, seed, orient):
+    t1, t2 = random_pairs(seed, orient=orient, eol="\r\n" if seed == 5 else "\n", shuffle_groups=(seed == 6))
+    i1, i2 = tmp_path / "i1.sam", tmp_path / "i2.sam"
+    i1.write_bytes(t1.encode()); i2.write_bytes(t2.encode())
+    exp = run_both(ctx, oracle, i1, i2, tmp_path)
+    assert exp[0] == "ok" and exp[1]["orientation"] == orient
+    assert exp[1]["before_count"] > exp[1]["after_count"] > 0
+
+
+@pytest.mark.parametrize("kw", [dict(orientation="rf"), dict(orientation="bogus"), dict(low=5.0, high=95.0),
+                                dict(low=0.0), dict(high=100.0), dict(low=49.9, high=50.1)])
+def test_options_and_errors(ctx, oracle, tmp_path, kw):
+    t1, t2 = random_pairs(11)
+    i1, i2 = tmp_path / "i1.sam", tmp_path / "i2.sam"
+    i1.write_text(t1); i2.write_text(t2)
+    run_both(ctx, oracle, i1, i2, tmp_path, **kw)
+
+
+def test_text_errors(ctx, oracle, tmp_path):
+    good1, good2 = random_pairs(12, n_pairs=20)
+    cases = [("@HD\n\n", good2), ("@HD\nr1\t4\t*\t0\t0\t*\t*\t0\t0\tAC\tII\n", "@HD\nr1\t4\t*\t0\t0\t*\t*\t0\t0\tAC\tII\n"),
+             ("r1\t0\tc\t1\t60\t4M\n", good2), (good1, good2.replace("\n", "\n\n", 1))]
+    for k, (a, b) in enumerate(cases):
+        d = tmp_path / f"c{k}"
+        d.mkdir()
+        i1, i2 = d / "i1.sam", d / "i2.sam"
+        i1.write_text(a); i2.write_text(b)
+        exp = run_both(ctx, oracle, i1, i2, d)
+        assert exp[0] == "err"
+    # all four paths must differ
+    i1, i2 = tmp_path / "i1.sam", tmp_path / "i2.sam"
+    i1.write_text(good1); i2.write_text(good2)
+    with pytest.raises(pp.PolypolishError) as e:
+        ctx.filter_files(i1, i2, i1, tmp_path / "o2.sam")
+    assert "must all have unique values" in e.value.msg
+
+
+def test_auto_orientation_tie_is_an_error(ctx, oracle, tmp_path):
+    a1, a2 = random_pairs(21, n_pairs=10, orient="fr")
+    b1, b2 = random_pairs(21, n_pairs=10, orient="ff")
+    strip = lambda t: "\n".join(l for l in t.split("\n") if l and not l.startswith("@"))
+    rename = lambda t: t.replace("p", "q")
+    i1, i2 = tmp_path / "i1.sam", tmp_path / "i2.sam"
+    i1.write_text(strip(a1) + "\n" + rename(strip(b1)) + "\n")
+    i2.write_text(strip(a2) + "\n" + rename(strip(b2)) + "\n")
+    exp = run_both(ctx, oracle, i1, i2, tmp_path)
+    # (either an exact tie -> error, or a unique winner: parity is what matters)
+    run_both(ctx, oracle, i1, i2, tmp_path, orientation="ff")
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_synth_filter_then_polish(ctx, oracle, tmp_path, seed):
+    """BASELINE config 3 in miniature: filter (insert size) then polish, both stages against the oracle."""
+    syn = api.Synth(seed=seed, contig_len=60_000, depth=60)
+    fa, sams = syn.write(tmp_path)
+    exp = run_both(ctx, oracle, sams[0], sams[1], tmp_path)
+    assert exp[1]["orientation"] == "fr" and 200 <= exp[1]["low"] < exp[1]["high"] <= 700
+    f1, f2 = tmp_path / "f1.sam", tmp_path / "f2.sam"
+    ctx.filter_files(sams[0], sams[1], f1, f2)
+    assert b"ZP:Z:fail" in open(f1, "rb").read()
+    got = ctx.polish_files(fa, [f1, f2])
+    assert got == oracle.polish(fa, [f1, f2])["fasta"]
