@@ -30,6 +30,7 @@
 #include <string>
 #include <vector>
 
+#include "nib_utils.h"
 #include "pp_internal.h"
 
 #define PP_TILE_SHIFT 7              // depth fix-up tile = 128 positions
@@ -67,7 +68,6 @@ struct DevData {                     // everything the kernels read, by value
     uint32_t n_contigs;
     uint32_t G;                      // total positions
     // work
-    uint8_t* aux;                    // bit0 good, bit1 group has > 1 aligned record
     uint32_t* k;                     // [n_reads] good alignments per read
     unsigned long long* draft_nib;   // 4-bit draft codes, 16 per word
     unsigned long long* diff;        // [G+1] lo32 cover, hi32 covering alignments with k != 1
@@ -75,11 +75,14 @@ struct DevData {                     // everything the kernels read, by value
     uint32_t* delother;              // [G] lo16 "-" count, hi16 other-allele record count
     uint32_t* tileflag;              // bitmap, tiles that may hold k != 1 coverage
     double* depth_fix;               // [G] ordered depth for flagged tiles
-    unsigned long long *fix_key, *fix_val;      // (tile<<32|aln) , (gstart<<32|n_kept)
+    unsigned long long *fix_key, *fix_val;      // (tile << aln_bits | aln) , (gstart<<32|n_kept)
+    uint32_t aln_bits;               // bits needed for an alignment index
     unsigned long long* oth_key;     // gpos << 32 | mix32(signature)
     unsigned long long* oth_sig;     // allele signature: exact content for short alleles (see make_sig)
     unsigned long long* oth_val;     // aln<<32 | start<<16 | len
     uint32_t fix_cap, oth_cap;
+    uint32_t max_errors;             // -m
+    int careful;                     // --careful
     DevStatus* st;
 };
 
@@ -185,51 +188,45 @@ __global__ void __launch_bounds__(256) k_draft_nib(const uint8_t* __restrict__ d
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_classify: one thread per alignment.  good (alignment.rs:283-287), k (:288), --careful (:277-279),
-// and the tile marks for groups with more than one aligned record (superset of k != 1 coverage).
+// Goodness (alignment.rs:283-287) and --careful (:277-279) of one alignment.  `multi` = its read group has more
+// than one aligned record.  Shared by k_classify_multi and k_scatter so that both see the same answer.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_classify(DevData d, uint32_t max_errors, int careful) {
-    unsigned long long used = 0;
+__device__ __forceinline__ bool group_is_multi(const DevData& d, unsigned long long a, uint32_t rid) {
+    return (a > 0 && d.read_id[a - 1] == rid) || (a + 1 < d.n_aln && d.read_id[a + 1] == rid);
+}
+__device__ __forceinline__ bool alignment_is_good(const DevData& d, unsigned long long a, bool multi, uint32_t co, uint32_t nc, uint8_t fl) {
+    if (nc == 0) { report_error(d.st, a, ERR_BAD_OP); return false; }       // the packer never emits this
+    const uint32_t f = d.cigar_ops[co] & 15u, l = d.cigar_ops[co + nc - 1] & 15u;
+    return (f == PP_OP_M || f == PP_OP_EQ) && (l == PP_OP_M || l == PP_OP_EQ) && d.nm[a] <= d.max_errors &&
+           !(fl & PP_FLAG_ZPFAIL) && !(d.careful && multi);
+}
+
+// k_classify_multi: only alignments of multi-record groups need a pre-pass: k = #good of the group (alignment.rs:288)
+// and the tile marks for the ordered-depth fix-up (a superset of where k != 1 coverage can occur).  Singletons
+// (the vast majority) have k = 1 and are classified inside k_scatter.
+__global__ void __launch_bounds__(256) k_classify_multi(DevData d) {
     for (unsigned long long a = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; a < d.n_aln;
          a += (unsigned long long)gridDim.x * blockDim.x) {
-        uint32_t rid = d.read_id[a];
-        bool multi = (a > 0 && d.read_id[a - 1] == rid) || (a + 1 < d.n_aln && d.read_id[a + 1] == rid);
-        uint32_t co = d.cigar_off[a], nc = d.n_cigar[a];
-        if (nc == 0) { d.aux[a] = 0; report_error(d.st, a, ERR_BAD_OP); continue; }   // the packer never emits this
-        uint32_t f = d.cigar_ops[co] & 15u, l = d.cigar_ops[co + nc - 1] & 15u;
-        uint8_t fl = d.flags[a];
-        bool good = (f == PP_OP_M || f == PP_OP_EQ) && (l == PP_OP_M || l == PP_OP_EQ) &&
-                    d.nm[a] <= max_errors && !(fl & PP_FLAG_ZPFAIL) && !(careful && multi);
-        d.aux[a] = (uint8_t)((good ? 1 : 0) | (multi ? 2 : 0));
-        if (!good) continue;
-        used++;
+        const uint32_t rid = d.read_id[a];
+        if (!group_is_multi(d, a, rid)) continue;
+        const uint32_t co = d.cigar_off[a], nc = d.n_cigar[a];
+        if (!alignment_is_good(d, a, true, co, nc, d.flags[a])) continue;
         atomicAdd(&d.k[rid], 1u);
-        if (multi) {
-            uint32_t c = d.contig[a];
-            if (c == PP_CONTIG_UNKNOWN) continue;              // reported by k_scatter
-            unsigned long long reflen = 0;
-            for (uint32_t i = 0; i < nc; ++i) {
-                uint32_t op = d.cigar_ops[co + i];
-                uint32_t o = op & 15u;
-                if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X || o == PP_OP_D) reflen += op >> 4;
-            }
-            unsigned long long gs = d.contig_off[c] + d.ref_start[a];
-            unsigned long long ge = gs + reflen;               // exclusive, before trimming
-            unsigned long long cend = d.contig_off[c + 1];
-            if (ge > cend) ge = cend;
-            if (gs >= ge) continue;
-            for (unsigned long long t = gs >> PP_TILE_SHIFT; t <= ((ge - 1) >> PP_TILE_SHIFT); ++t)
-                atomicOr(&d.tileflag[t >> 5], 1u << (t & 31));
+        const uint32_t c = d.contig[a];
+        if (c == PP_CONTIG_UNKNOWN) continue;                  // reported by k_scatter
+        unsigned long long reflen = 0;
+        for (uint32_t i = 0; i < nc; ++i) {
+            const uint32_t op = d.cigar_ops[co + i], o = op & 15u;
+            if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X || o == PP_OP_D) reflen += op >> 4;
         }
+        const unsigned long long gs = d.contig_off[c] + d.ref_start[a];
+        unsigned long long ge = gs + reflen;                   // exclusive, before trimming
+        const unsigned long long cend = d.contig_off[c + 1];
+        if (ge > cend) ge = cend;
+        if (gs >= ge) continue;
+        for (unsigned long long t = gs >> PP_TILE_SHIFT; t <= ((ge - 1) >> PP_TILE_SHIFT); ++t)
+            atomicOr(&d.tileflag[t >> 5], 1u << (t & 31));
     }
-    // block reduce of `used`
-    __shared__ unsigned long long s_used;
-    if (threadIdx.x == 0) s_used = 0;
-    __syncthreads();
-    for (int o = 16; o > 0; o >>= 1) used += __shfl_down_sync(0xffffffffu, used, o);
-    if ((threadIdx.x & 31) == 0 && used) atomicAdd(&s_used, used);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_used) atomicAdd(&d.st->n_used, s_used);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -242,7 +239,7 @@ struct ScatterShared {
     unsigned long long fix_key[SC_STAGE], fix_val[SC_STAGE];
     unsigned long long oth_val[SC_STAGE], oth_sig[SC_STAGE];
     uint32_t oth_pos[SC_STAGE];
-    uint32_t n_fix, n_oth, base_fix, base_oth;
+    uint32_t n_fix, n_oth, base_fix, base_oth, next, n_good;
     unsigned long long oth_len;
 };
 
@@ -261,7 +258,7 @@ template <int BITS> struct Scatter {
         else atomicOr(&d.st->flags, FL_OTHER_OVF);
     }
     __device__ __forceinline__ void push_fix(uint32_t tile, unsigned long long aln, uint32_t gstart, uint32_t nkept) {
-        unsigned long long k = ((unsigned long long)tile << 32) | aln;
+        unsigned long long k = ((unsigned long long)tile << d.aln_bits) | aln;
         unsigned long long v = ((unsigned long long)gstart << 32) | nkept;
         uint32_t s = atomicAdd(&sh.n_fix, 1u);
         if (s < SC_STAGE) { sh.fix_key[s] = k; sh.fix_val[s] = v; return; }
@@ -290,6 +287,31 @@ template <int BITS> struct Scatter {
         for (uint32_t t = t0 + lane8; t <= t1; t += 8)
             if ((d.tileflag[t >> 5] >> (t & 31)) & 1u) push_fix(t, aln, gstart, nkept);
     }
+    // 4-bit only: `vc` (<= 32) single-base entries whose read codes are the low nibbles of r0:r1, at reference
+    // positions pos0.. ; ri0 = read index of the first one.  One explicit count per base that differs from the draft.
+    __device__ __forceinline__ void scan_mismatches(unsigned long long r0, unsigned long long r1, uint32_t vc, uint32_t pos0,
+                                                    unsigned long long aln, uint32_t ri0) {
+        unsigned long long d0, d1;
+        load_nib32(d.draft_nib, pos0, d0, d1);
+        unsigned long long m0, m1;
+        mismatch_masks(r0, r1, d0, d1, vc, m0, m1);
+        while (m0) {
+            const uint32_t j = (uint32_t)(__ffsll((long long)m0) - 1) >> 2;
+            m0 &= m0 - 1;
+            const uint32_t code = (uint32_t)(r0 >> (4 * j)) & 15u;
+            const int c = Seq<4>::acgt(code);
+            if (c >= 0) atomicAdd(&d.ex[pos0 + j], 1ull << (16 * c));
+            else push_other(pos0 + j, aln, ri0 + j, 1, 1ull | ((unsigned long long)code << 4));
+        }
+        while (m1) {
+            const uint32_t j = (uint32_t)(__ffsll((long long)m1) - 1) >> 2;
+            m1 &= m1 - 1;
+            const uint32_t code = (uint32_t)(r1 >> (4 * j)) & 15u;
+            const int c = Seq<4>::acgt(code);
+            if (c >= 0) atomicAdd(&d.ex[pos0 + 16 + j], 1ull << (16 * c));
+            else push_other(pos0 + 16 + j, aln, ri0 + 16 + j, 1, 1ull | ((unsigned long long)code << 4));
+        }
+    }
 };
 
 #define GROUP_MASK(lane) (0xFFu << ((lane) & 24))
@@ -300,49 +322,55 @@ __device__ __forceinline__ unsigned long long shfl64(unsigned mask, unsigned lon
     return ((unsigned long long)hi << 32) | lo;
 }
 
-__device__ __forceinline__ unsigned long long nibble_nonzero(unsigned long long x) {   // bit 4j set iff nibble j != 0
-    return (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x1111111111111111ull;
-}
-
 template <int BITS>
 __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
     __shared__ ScatterShared sh;
     Scatter<BITS> S{d, sh};
-    const uint32_t tid = threadIdx.x, lane = tid & 31, lane8 = tid & 7, grp = tid >> 3;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, lane8 = tid & 7;
     const unsigned gmask = GROUP_MASK(lane);
     const unsigned long long n_blocks = (d.n_aln + SC_THREADS - 1) / SC_THREADS;
+    unsigned long long used = 0;
 
     for (unsigned long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        // ---- stage 1: coalesced metadata loads, one alignment per thread
-        if (tid == 0) { sh.n_fix = 0; sh.n_oth = 0; sh.oth_len = 0; }
-        unsigned long long a = blk * SC_THREADS + tid;
+        // ---- stage 1: coalesced metadata loads + goodness, one alignment per thread
+        if (tid == 0) { sh.n_fix = 0; sh.n_oth = 0; sh.oth_len = 0; sh.next = 0; }
+        const unsigned long long a = blk * SC_THREADS + tid;
         uint8_t f = 0;
-        if (a < d.n_aln && (d.aux[a] & 1)) {
-            uint32_t c = d.contig[a];
-            uint8_t fl = d.flags[a];
-            if (c == PP_CONTIG_UNKNOWN) report_error(d.st, a, ERR_UNKNOWN_CONTIG);
-            else if (fl & PP_FLAG_NOSEQ) report_error(d.st, a, ERR_NOSEQ);
-            else {
-                unsigned long long gs = d.contig_off[c] + d.ref_start[a];
-                unsigned long long ce = d.contig_off[c + 1];
-                if (gs >= ce) report_error(d.st, a, ERR_OOB);
+        if (a < d.n_aln) {
+            const uint32_t rid = d.read_id[a];
+            const bool multi = group_is_multi(d, a, rid);
+            const uint32_t co = d.cigar_off[a], nc = d.n_cigar[a];
+            const uint8_t fl = d.flags[a];
+            if (alignment_is_good(d, a, multi, co, nc, fl)) {
+                used++;
+                const uint32_t c = d.contig[a];
+                if (c == PP_CONTIG_UNKNOWN) report_error(d.st, a, ERR_UNKNOWN_CONTIG);
+                else if (fl & PP_FLAG_NOSEQ) report_error(d.st, a, ERR_NOSEQ);
                 else {
-                    sh.gstart[tid] = (uint32_t)gs;
-                    sh.cend[tid] = (uint32_t)ce;
-                    sh.seqoff[tid] = d.seq_off[a];
-                    sh.cigoff[tid] = d.cigar_off[a];
-                    sh.len[tid] = d.seq_len[a];
-                    sh.ncig[tid] = d.n_cigar[a];
-                    f = (uint8_t)(1 | ((fl & PP_FLAG_RC) ? 2 : 0) | (d.k[d.read_id[a]] != 1 ? 4 : 0));
+                    const unsigned long long gs = d.contig_off[c] + d.ref_start[a];
+                    const unsigned long long ce = d.contig_off[c + 1];
+                    if (gs >= ce) report_error(d.st, a, ERR_OOB);
+                    else {
+                        sh.gstart[tid] = (uint32_t)gs;
+                        sh.cend[tid] = (uint32_t)ce;
+                        sh.seqoff[tid] = d.seq_off[a];
+                        sh.cigoff[tid] = co;
+                        sh.len[tid] = d.seq_len[a];
+                        sh.ncig[tid] = (uint16_t)nc;
+                        f = (uint8_t)(1 | ((fl & PP_FLAG_RC) ? 2 : 0) | ((multi && d.k[rid] != 1) ? 4 : 0));
+                    }
                 }
             }
         }
         sh.fl[tid] = f;
         __syncthreads();
 
-        // ---- stage 2: 8 lanes per alignment, 8 alignments per lane group
-        for (uint32_t i = 0; i < 8; ++i) {
-            const uint32_t s = grp * 8 + i;
+        // ---- stage 2: 8 lanes per alignment; lane groups pull the next alignment from a shared counter
+        for (;;) {
+            uint32_t s = 0;
+            if (lane8 == 0) s = atomicAdd(&sh.next, 1u);
+            s = __shfl_sync(gmask, s, 0, 8);
+            if (s >= SC_THREADS) break;
             const uint32_t fl = sh.fl[s];
             if (!(fl & 1)) continue;
             const unsigned long long aln = blk * SC_THREADS + s;
@@ -383,35 +411,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                 const uint32_t nkept = (len - run >= 1) ? (len - run - 1) : 0;
                 if (gstart + nkept > cend) { if (lane8 == 0) report_error(d.st, aln, ERR_OOB); continue; }
                 S.add_interval(lane8, aln, gstart, nkept, multi);
-                // mismatches against the draft, 32 bases per lane
-                if (b0 < nkept) {
-                    const uint32_t o = gstart + b0;
-                    const unsigned long long* w = d.draft_nib + (o >> 4);
-                    const uint32_t shb = (o & 15) * 4;
-                    const unsigned long long w0 = w[0], w1 = w[1], w2 = w[2];
-                    const unsigned long long d0 = shb ? ((w0 >> shb) | (w1 << (64 - shb))) : w0;
-                    const unsigned long long d1 = shb ? ((w1 >> shb) | (w2 << (64 - shb))) : w1;
-                    const uint32_t vc = min(nkept - b0, 32u);
-                    unsigned long long m0 = nibble_nonzero(r0 ^ d0), m1 = nibble_nonzero(r1 ^ d1);
-                    if (vc < 16) { m0 &= (1ull << (4 * vc)) - 1; m1 = 0; }
-                    else if (vc < 32) m1 &= (1ull << (4 * (vc - 16))) - 1;
-                    while (m0) {
-                        const uint32_t j = (uint32_t)(__ffsll((long long)m0) - 1) >> 2;
-                        m0 &= m0 - 1;
-                        const uint32_t code = (uint32_t)(r0 >> (4 * j)) & 15u;
-                        const int c = Seq<4>::acgt(code);
-                        if (c >= 0) atomicAdd(&d.ex[o + j], 1ull << (16 * c));
-                        else S.push_other(o + j, aln, b0 + j, 1, 1ull | ((unsigned long long)code << 4));
-                    }
-                    while (m1) {
-                        const uint32_t j = (uint32_t)(__ffsll((long long)m1) - 1) >> 2;
-                        m1 &= m1 - 1;
-                        const uint32_t code = (uint32_t)(r1 >> (4 * j)) & 15u;
-                        const int c = Seq<4>::acgt(code);
-                        if (c >= 0) atomicAdd(&d.ex[o + 16 + j], 1ull << (16 * c));
-                        else S.push_other(o + 16 + j, aln, b0 + 16 + j, 1, 1ull | ((unsigned long long)code << 4));
-                    }
-                }
+                if (b0 < nkept) S.scan_mismatches(r0, r1, min(nkept - b0, 32u), gstart + b0, aln, b0);
                 continue;
             }
 
@@ -475,9 +475,17 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                     e += l;
                     continue;
                 }
-                const uint32_t plain = ins ? l - 1 : l;               // M / = / X
-                for (uint32_t t = lane8; t < plain && e + t < nkept; t += 8)
-                    S.count_base(gstart + e + t, Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri + t), aln, ri + t);
+                const uint32_t plain = min(ins ? l - 1 : l, nkept - e);   // single-base entries of this M / = / X run that are kept
+                if (BITS == 4) {
+                    for (uint32_t c0 = lane8 * 32; c0 < plain; c0 += 256) {
+                        unsigned long long r0, r1;
+                        load_read32(reinterpret_cast<const unsigned long long*>(d.seq_pool + (size_t)seqoff * 16), len, rc, ri + c0, r0, r1);
+                        S.scan_mismatches(r0, r1, min(plain - c0, 32u), gstart + e + c0, aln, ri + c0);
+                    }
+                } else {
+                    for (uint32_t t = lane8; t < plain; t += 8)
+                        S.count_base(gstart + e + t, Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri + t), aln, ri + t);
+                }
                 if (ins && lane8 == 0 && e + l - 1 < nkept)
                     S.push_other(gstart + e + l - 1, aln, ri + l - 1, 1 + ins, make_sig<BITS>(d.seq_pool, seqoff, len, rc, ri + l - 1, 1 + ins));
                 e += l;
@@ -512,6 +520,13 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
         }
         __syncthreads();
     }
+    // good alignments (alignment.rs:304): block reduce, one atomic per CTA
+    if (tid == 0) sh.n_good = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) used += __shfl_down_sync(0xffffffffu, used, o);
+    if (lane == 0 && used) atomicAdd(&sh.n_good, (uint32_t)used);
+    __syncthreads();
+    if (tid == 0 && sh.n_good) atomicAdd(&d.st->n_used, (unsigned long long)sh.n_good);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -531,8 +546,8 @@ __global__ void __launch_bounds__(PP_TILE) k_depth_fixup(DevData d, const unsign
     __shared__ uint32_t s_lo, s_hi;
     __shared__ uint32_t s_start[PP_TILE], s_end[PP_TILE];
     __shared__ double s_inv[PP_TILE];
-    if (threadIdx.x == 0) s_lo = lower_bound_u64(keys, n, (unsigned long long)tile << 32);
-    if (threadIdx.x == 1) s_hi = lower_bound_u64(keys, n, (unsigned long long)(tile + 1) << 32);
+    if (threadIdx.x == 0) s_lo = lower_bound_u64(keys, n, (unsigned long long)tile << d.aln_bits);
+    if (threadIdx.x == 1) s_hi = lower_bound_u64(keys, n, (unsigned long long)(tile + 1) << d.aln_bits);
     __syncthreads();
     const uint32_t lo = s_lo, hi = s_hi;
     const uint32_t p = tile * PP_TILE + threadIdx.x;
@@ -541,8 +556,9 @@ __global__ void __launch_bounds__(PP_TILE) k_depth_fixup(DevData d, const unsign
         const uint32_t i = base + threadIdx.x;
         if (i < hi) {
             const unsigned long long v = vals[i];
-            const uint32_t aln = (uint32_t)keys[i];
-            const uint32_t kk = d.k[d.read_id[aln]];
+            const uint32_t aln = (uint32_t)(keys[i] & ((1ull << d.aln_bits) - 1));
+            // k is only accumulated for multi-record groups (k_classify_multi); a singleton in this list is good, so k = 1
+            const uint32_t kk = max(d.k[d.read_id[aln]], 1u);
             s_start[threadIdx.x] = (uint32_t)(v >> 32);
             s_end[threadIdx.x] = (uint32_t)(v >> 32) + (uint32_t)v;
             s_inv[threadIdx.x] = __ddiv_rn(1.0, (double)kk);      // 1.0 / good_alignments.len() as f64
@@ -567,9 +583,13 @@ struct VoteParams {
     unsigned long long out_cap;
     unsigned long long* out_off;     // [n_contigs+1]
     unsigned long long *changed, *zero_depth;   // [n_contigs]
-    // look-back descriptors
+    // look-back descriptors of the difference-array prefix sum
     uint32_t* st1; unsigned long long *agg1, *inc1;
-    uint32_t* st2; unsigned long long *agg2, *inc2;
+    // per-position verdicts handed from k_vote to k_compact
+    uint16_t* res;                    // [padG] low byte = character, high byte = output length (255: see rec_len)
+    uint32_t* rec_at;                 // [G] other-allele record to emit at a position (only where res says so)
+    long long* chunk_delta;           // [n_chunks] sum(output length) - positions of the chunk
+    const uint32_t* ofirst;           // [G] index of the first sorted record of a position (only where records exist)
     const unsigned long long* okey;   // sorted (pos << 32 | mix32(sig))
     const uint32_t* oidx;             // record index of each sorted key
     const unsigned long long* osig;   // by record index
@@ -673,7 +693,7 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
 // spilled to local memory for a call.
 struct OthCtx {
     const unsigned long long *okey, *osig, *oval;
-    const uint32_t *oidx, *seq_off;
+    const uint32_t *oidx, *ofirst, *seq_off;
     const uint16_t* seq_len;
     const uint8_t *flags, *seq_pool;
     uint32_t n_oth;
@@ -705,7 +725,7 @@ template <int BITS>
 __device__ __noinline__ Tally tally_others(OthCtx vp, uint32_t pos, uint32_t vt, uint32_t it, Tally t) {
     const OthCtx& d = vp;
     const uint32_t n = vp.n_oth;
-    uint32_t i = lower_bound_u64(vp.okey, n, (unsigned long long)pos << 32);
+    uint32_t i = vp.ofirst[pos];
     while (i < n && (uint32_t)(vp.okey[i] >> 32) == pos) {
         const unsigned long long k = vp.okey[i];
         uint32_t j = i + 1;
@@ -829,7 +849,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_vote(DevData d, VoteParams vp) {
     }
     const uint2 dr = *reinterpret_cast<const uint2*>(d.draft + p0);
     OthCtx oc;
-    oc.okey = vp.okey; oc.osig = vp.osig; oc.oval = vp.oval; oc.oidx = vp.oidx; oc.seq_off = d.seq_off; oc.seq_len = d.seq_len;
+    oc.okey = vp.okey; oc.osig = vp.osig; oc.oval = vp.oval; oc.oidx = vp.oidx; oc.ofirst = vp.ofirst; oc.seq_off = d.seq_off; oc.seq_len = d.seq_len;
     oc.flags = d.flags; oc.seq_pool = d.seq_pool; oc.n_oth = vp.n_oth;
     PosOut po[VT_ITEMS];
     unsigned long long tlen = 0;
@@ -880,45 +900,136 @@ __global__ void __launch_bounds__(VT_THREADS) k_vote(DevData d, VoteParams vp) {
     if (n_changed) atomicAdd(&vp.changed[ctg], (unsigned long long)n_changed);
     if (n_zero) atomicAdd(&vp.zero_depth[ctg], (unsigned long long)n_zero);
 
-    // ---- 3. output offsets (second look-back) and the compacted write
-    const unsigned long long oexcl = block_exscan(tlen, s_warp, &s_total);
-    total = s_total;
-    if (tid < 32) {
-        const unsigned long long pre = lookback(chunk, total, vp.st2, vp.agg2, vp.inc2);
-        if (tid == 0) s_prefix = pre;
+    // ---- 3. hand the verdicts to k_compact: 2 bytes per position + this chunk's length delta
+    {
+        uint32_t w[VT_ITEMS / 2];
+#pragma unroll
+        for (int i = 0; i < VT_ITEMS; ++i) {
+            const uint32_t len = po[i].packed & 0xFFFFu;
+            uint32_t h;
+            if ((po[i].packed >> 25) & 1u) { h = 255u << 8; if (p0 + i < d.G) vp.rec_at[p0 + i] = po[i].rec; }
+            else h = (len << 8) | ((po[i].packed >> 16) & 255u);
+            if (i & 1) w[i >> 1] |= h << 16; else w[i >> 1] = h;
+        }
+        *reinterpret_cast<uint4*>(vp.res + p0) = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    const uint32_t npos = (p0 < d.G) ? min((uint32_t)VT_ITEMS, d.G - p0) : 0u;
+    long long delta = (long long)tlen - (long long)npos;
+    for (int o = 16; o > 0; o >>= 1) delta += __shfl_down_sync(0xffffffffu, delta, o);
+    __shared__ long long s_delta[VT_THREADS / 32];
+    if ((tid & 31) == 0) s_delta[tid >> 5] = delta;
     __syncthreads();
-    unsigned long long o = s_prefix + oexcl;
-    if (chunk == vp.n_chunks - 1 && tid == VT_THREADS - 1) {
-        vp.out_off[d.n_contigs] = o + tlen;
-        d.st->out_len = o + tlen;
+    if (tid == 0) {
+        long long t = 0;
+        for (int i = 0; i < VT_THREADS / 32; ++i) t += s_delta[i];
+        vp.chunk_delta[chunk] = t;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_compact: polish.rs:185-188 (push_str of every position's allele, then replace("-", "")).  Chunk c writes its
+// characters at c * VT_CHUNK + sum(chunk_delta[0..c)); no inter-CTA dependency.
+// ------------------------------------------------------------------------------------------------------
+#define CP_STAGE (VT_CHUNK + 2048)
+template <int BITS>
+__global__ void __launch_bounds__(VT_THREADS) k_compact(DevData d, VoteParams vp) {
+    __shared__ unsigned long long s_warp[VT_THREADS / 32];
+    __shared__ unsigned long long s_total;
+    __shared__ long long s_red[VT_THREADS / 32];
+    __shared__ long long s_base;
+    __shared__ __align__(16) uint8_t s_out[CP_STAGE];
+    const uint32_t tid = threadIdx.x, chunk = blockIdx.x;
+    const uint32_t p0 = chunk * VT_CHUNK + tid * VT_ITEMS;
+    // base offset of this chunk
+    long long acc = 0;
+    for (uint32_t j = tid; j < chunk; j += VT_THREADS) acc += vp.chunk_delta[j];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) s_red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        long long t = 0;
+        for (int i = 0; i < VT_THREADS / 32; ++i) t += s_red[i];
+        s_base = (long long)chunk * VT_CHUNK + t;
+    }
+    // verdicts
+    const uint4 rv = *reinterpret_cast<const uint4*>(vp.res + p0);
+    const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+    uint32_t len[VT_ITEMS];
+    unsigned long long tlen = 0;
+    OthCtx oc;
+    oc.okey = vp.okey; oc.osig = vp.osig; oc.oval = vp.oval; oc.oidx = vp.oidx; oc.ofirst = vp.ofirst; oc.seq_off = d.seq_off; oc.seq_len = d.seq_len;
+    oc.flags = d.flags; oc.seq_pool = d.seq_pool; oc.n_oth = vp.n_oth;
+#pragma unroll
+    for (int i = 0; i < VT_ITEMS; ++i) {
+        const uint32_t h = (w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+        uint32_t l = h >> 8;
+        if (p0 + i >= d.G) l = 0;
+        else if (l == 255) {                                      // a multi-base allele: count its non-'-' characters
+            const uint32_t rec = vp.rec_at[p0 + i];
+            const uint32_t rlen = (uint32_t)vp.oval[rec] & 0xFFFFu;
+            l = 0;
+            for (uint32_t t = 0; t < rlen; ++t) l += other_char<BITS>(oc, rec, t) != '-';
+        }
+        len[i] = l;
+        tlen += l;
+    }
+    const unsigned long long oexcl = block_exscan(tlen, s_warp, &s_total);
+    const unsigned long long total = s_total;
+    const unsigned long long base = (unsigned long long)s_base;
+    if (chunk == vp.n_chunks - 1 && tid == 0) { vp.out_off[d.n_contigs] = base + total; d.st->out_len = base + total; }
     // out_off of contigs that start inside this thread's positions
     if (p0 < d.G) {
         uint32_t lo = 0, hi = d.n_contigs;           // first c with contig_off[c] >= p0
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (d.contig_off[mid] < p0) lo = mid + 1; else hi = mid; }
         if (lo < d.n_contigs && d.contig_off[lo] < (unsigned long long)p0 + VT_ITEMS) {
-            unsigned long long oo = o;
+            unsigned long long oo = base + oexcl;
             uint32_t c = lo;
 #pragma unroll
             for (int i = 0; i < VT_ITEMS; ++i) {
-                const uint32_t p = p0 + i;
-                while (c < d.n_contigs && d.contig_off[c] == p) { vp.out_off[c] = oo; c++; }
-                oo += po[i].packed & 0xFFFFu;
+                while (c < d.n_contigs && d.contig_off[c] == p0 + i) { vp.out_off[c] = oo; c++; }
+                oo += len[i];
             }
         }
     }
-    if (o + tlen > vp.out_cap) { atomicOr(&d.st->flags, FL_OUT_OVF); return; }
+    if (base + total > vp.out_cap) { if (tid == 0) atomicOr(&d.st->flags, FL_OUT_OVF); return; }
+    const bool staged = total <= CP_STAGE;
+    uint8_t* dst = staged ? s_out : vp.out + base;
+    unsigned long long o = oexcl;
 #pragma unroll
     for (int i = 0; i < VT_ITEMS; ++i) {
-        const uint32_t len = po[i].packed & 0xFFFFu;
-        if (len == 0) continue;
-        if (!((po[i].packed >> 25) & 1u)) { vp.out[o] = (uint8_t)(po[i].packed >> 16); o += 1; continue; }
-        const uint32_t rlen = (uint32_t)vp.oval[po[i].rec] & 0xFFFFu;
+        if (len[i] == 0) continue;
+        const uint32_t h = (w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+        if ((h >> 8) != 255) { dst[o++] = (uint8_t)h; continue; }
+        const uint32_t rec = vp.rec_at[p0 + i];
+        const uint32_t rlen = (uint32_t)vp.oval[rec] & 0xFFFFu;
         for (uint32_t t = 0; t < rlen; ++t) {
-            const uint8_t ch = other_char<BITS>(oc, po[i].rec, t);
-            if (ch != '-') vp.out[o++] = ch;                 // polish.rs:188 replace("-", "")
+            const uint8_t ch = other_char<BITS>(oc, rec, t);
+            if (ch != '-') dst[o++] = ch;                          // polish.rs:188 replace("-", "")
         }
+    }
+    if (!staged) return;
+    __syncthreads();
+    // coalesced copy of the staged bytes: head to a 16-byte boundary, body as uint4, tail
+    uint8_t* g = vp.out + base;
+    const uint32_t n = (uint32_t)total;
+    const uint32_t head = min(n, (uint32_t)((16 - ((size_t)g & 15)) & 15));
+    for (uint32_t i = tid; i < head; i += VT_THREADS) g[i] = s_out[i];
+    const uint32_t nvec = (n - head) / 16;
+    for (uint32_t i = tid; i < nvec; i += VT_THREADS) {
+        const uint8_t* sp = s_out + head + i * 16;
+        uint32_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = sp[4 * k] | (sp[4 * k + 1] << 8) | (sp[4 * k + 2] << 16) | ((uint32_t)sp[4 * k + 3] << 24);
+        reinterpret_cast<uint4*>(g + head)[i] = make_uint4(x[0], x[1], x[2], x[3]);
+    }
+    for (uint32_t i = head + nvec * 16 + tid; i < n; i += VT_THREADS) g[i] = s_out[i];
+}
+
+// first sorted record of every position that has other-allele records
+__global__ void __launch_bounds__(256) k_oth_first(const unsigned long long* __restrict__ okey, uint32_t n, uint32_t* __restrict__ ofirst) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pos = (uint32_t)(okey[i] >> 32);
+        if (i == 0 || (uint32_t)(okey[i - 1] >> 32) != pos) ofirst[pos] = i;
     }
 }
 
@@ -946,9 +1057,9 @@ struct DevBuf {
 };
 
 enum { B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL,
-       B_DRAFT, B_CTGOFF, B_AUX, B_NIB, B_ZEROPOOL, B_DEPTHFIX, B_FIXKEY, B_FIXVAL,
+       B_DRAFT, B_CTGOFF, B_NIB, B_ZEROPOOL, B_DEPTHFIX, B_FIXKEY, B_FIXVAL,
        B_FIXKEY2, B_FIXVAL2, B_OTHKEY, B_OTHVAL, B_OTHSIG, B_OTHIDX, B_OTHKEY2, B_OTHIDX2, B_CUBTMP, B_OUT, B_OUTOFF,
-       B_AGG1, B_INC1, B_AGG2, B_INC2, B_COUNT };
+       B_AGG1, B_INC1, B_RES, B_RECAT, B_CHUNKDELTA, B_OFIRST, B_COUNT };
 
 struct pp_ctx {
     int device = 0;
@@ -1110,17 +1221,17 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
     uint64_t out_cap = G + 4096;
 
     const size_t padG = (size_t)n_chunks * VT_CHUNK + 16;      // k_vote reads whole chunks with vector loads
-    CK(ctx->b[B_AUX].ensure(n_aln + 64));
     CK(ctx->b[B_NIB].ensure(((size_t)nib_words + 8) * 8));
     CK(ctx->b[B_DEPTHFIX].ensure(((size_t)n_tiles * PP_TILE + 1) * 8));
     CK(ctx->b[B_OUTOFF].ensure(((size_t)ctx->n_contigs + 1) * 8));
     CK(ctx->b[B_AGG1].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC1].ensure((size_t)n_chunks * 8));
-    CK(ctx->b[B_AGG2].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC2].ensure((size_t)n_chunks * 8));
+    CK(ctx->b[B_RES].ensure(padG * 2)); CK(ctx->b[B_RECAT].ensure((G + 1) * 4)); CK(ctx->b[B_CHUNKDELTA].ensure((size_t)n_chunks * 8));
+    CK(ctx->b[B_OFIRST].ensure((G + 1) * 4));
     // everything that must be zero at the start of a call lives in one pool: one memset
     size_t zoff = 0;
     auto carve = [&](size_t bytes) { size_t o = zoff; zoff += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_diff = carve(padG * 8), o_ex = carve(padG * 8), o_del = carve(padG * 4), o_k = carve((ctx->n_reads + 1) * 4),
-                 o_tile = carve(((size_t)n_tiles / 32 + 2) * 4), o_st1 = carve((size_t)n_chunks * 4), o_st2 = carve((size_t)n_chunks * 4),
+                 o_tile = carve(((size_t)n_tiles / 32 + 2) * 4), o_st1 = carve((size_t)n_chunks * 4),
                  o_chg = carve((size_t)ctx->n_contigs * 8), o_zero = carve((size_t)ctx->n_contigs * 8), o_status = carve(sizeof(DevStatus));
     CK(ctx->b[B_ZEROPOOL].ensure(zoff));
     uint8_t* zp = ctx->b[B_ZEROPOOL].as<uint8_t>();
@@ -1140,7 +1251,8 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         d.n_cigar = ctx->b[B_NCIG].as<uint16_t>(); d.flags = ctx->b[B_FLAGS].as<uint8_t>();
         d.seq_pool = ctx->b[B_SEQPOOL].as<uint8_t>(); d.draft = ctx->b[B_DRAFT].as<uint8_t>();
         d.contig_off = ctx->b[B_CTGOFF].as<unsigned long long>(); d.n_contigs = ctx->n_contigs; d.G = (uint32_t)G;
-        d.aux = ctx->b[B_AUX].as<uint8_t>(); d.k = (uint32_t*)(zp + o_k);
+        d.k = (uint32_t*)(zp + o_k);
+        d.max_errors = prm->max_errors; d.careful = prm->careful ? 1 : 0;
         d.draft_nib = ctx->b[B_NIB].as<unsigned long long>(); d.diff = (unsigned long long*)(zp + o_diff);
         d.ex = (unsigned long long*)(zp + o_ex); d.delother = (uint32_t*)(zp + o_del);
         d.tileflag = (uint32_t*)(zp + o_tile); d.depth_fix = ctx->b[B_DEPTHFIX].as<double>();
@@ -1148,6 +1260,11 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         d.oth_key = ctx->b[B_OTHKEY].as<unsigned long long>(); d.oth_val = ctx->b[B_OTHVAL].as<unsigned long long>();
         d.oth_sig = ctx->b[B_OTHSIG].as<unsigned long long>();
         d.fix_cap = fix_cap; d.oth_cap = oth_cap;
+        d.aln_bits = 1;
+        while ((1ull << d.aln_bits) < n_aln) d.aln_bits++;
+        int tile_bits = 1;
+        while ((1ull << tile_bits) < n_tiles) tile_bits++;
+        const int fix_end_bit = std::min(64, (int)d.aln_bits + tile_bits);
         d.st = (DevStatus*)(zp + o_status);
 
         // ---- stage 0: reset
@@ -1163,7 +1280,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         CK(cudaEventRecord(ctx->ev[1], s));
         if (n_aln) {
             uint32_t grid = (uint32_t)std::min<uint64_t>((n_aln + 255) / 256, (uint64_t)ctx->sm_count * 8);
-            k_classify<<<grid, 256, 0, s>>>(d, prm->max_errors, prm->careful ? 1 : 0);
+            k_classify_multi<<<grid, 256, 0, s>>>(d);
             ctx->launches++;
         }
         // ---- stage 2: scatter
@@ -1197,10 +1314,10 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
             CK(ctx->b[B_FIXKEY2].ensure((size_t)hs.fix_count * 8)); CK(ctx->b[B_FIXVAL2].ensure((size_t)hs.fix_count * 8));
             size_t tmp = 0;
             CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d.fix_key, ctx->b[B_FIXKEY2].as<unsigned long long>(), d.fix_val,
-                                               ctx->b[B_FIXVAL2].as<unsigned long long>(), (int)hs.fix_count, 0, 64, s));
+                                               ctx->b[B_FIXVAL2].as<unsigned long long>(), (int)hs.fix_count, 0, fix_end_bit, s));
             CK(ctx->b[B_CUBTMP].ensure(tmp));
             CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, tmp, d.fix_key, ctx->b[B_FIXKEY2].as<unsigned long long>(), d.fix_val,
-                                               ctx->b[B_FIXVAL2].as<unsigned long long>(), (int)hs.fix_count, 0, 64, s));
+                                               ctx->b[B_FIXVAL2].as<unsigned long long>(), (int)hs.fix_count, 0, fix_end_bit, s));
             fkeys = ctx->b[B_FIXKEY2].as<unsigned long long>();
             fvals = ctx->b[B_FIXVAL2].as<unsigned long long>();
             k_depth_fixup<<<n_tiles, PP_TILE, 0, s>>>(d, fkeys, fvals, hs.fix_count);
@@ -1225,6 +1342,8 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
                                                ctx->b[B_OTHIDX2].as<uint32_t>(), (int)hs.other_count, 0, 32 + pos_bits, s));
             okeys = ctx->b[B_OTHKEY2].as<unsigned long long>();
             oidx = ctx->b[B_OTHIDX2].as<uint32_t>();
+            k_oth_first<<<std::min<uint32_t>((hs.other_count + 255) / 256, ctx->sm_count * 4), 256, 0, s>>>(okeys, hs.other_count, ctx->b[B_OFIRST].as<uint32_t>());
+            ctx->launches++;
         }
         // ---- stage 5: vote + compaction
         CK(cudaEventRecord(ctx->ev[5], s));
@@ -1234,10 +1353,12 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         vp.out_off = ctx->b[B_OUTOFF].as<unsigned long long>();
         vp.changed = (unsigned long long*)(zp + o_chg); vp.zero_depth = (unsigned long long*)(zp + o_zero);
         vp.st1 = (uint32_t*)(zp + o_st1); vp.agg1 = ctx->b[B_AGG1].as<unsigned long long>(); vp.inc1 = ctx->b[B_INC1].as<unsigned long long>();
-        vp.st2 = (uint32_t*)(zp + o_st2); vp.agg2 = ctx->b[B_AGG2].as<unsigned long long>(); vp.inc2 = ctx->b[B_INC2].as<unsigned long long>();
+        vp.res = ctx->b[B_RES].as<uint16_t>(); vp.rec_at = ctx->b[B_RECAT].as<uint32_t>();
+        vp.chunk_delta = ctx->b[B_CHUNKDELTA].as<long long>(); vp.ofirst = ctx->b[B_OFIRST].as<uint32_t>();
         vp.okey = okeys; vp.oidx = oidx; vp.osig = d.oth_sig; vp.oval = d.oth_val; vp.n_oth = hs.other_count;
         k_vote<BITS><<<n_chunks, VT_THREADS, 0, s>>>(d, vp);
-        ctx->launches++;
+        k_compact<BITS><<<n_chunks, VT_THREADS, 0, s>>>(d, vp);
+        ctx->launches += 2;
         CK(cudaEventRecord(ctx->ev[6], s));
         CK(cudaMemcpyAsync(ctx->h_status, d.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
