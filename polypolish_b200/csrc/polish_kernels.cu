@@ -36,7 +36,8 @@
 #define PP_TILE_SHIFT 7              // depth fix-up tile = 128 positions
 #define PP_TILE (1u << PP_TILE_SHIFT)
 #define SC_THREADS 256               // scatter CTA
-#define SC_STAGE 768                 // smem staging entries (fix list / other records) per CTA
+#define SC_STAGE 320                 // smem staging entries (fix list / other records) per CTA
+#define SC_SEQ_BYTES 24576           // smem window for the block's slice of the sequence pool (4-bit mode)
 #define VT_THREADS 256
 #define VT_ITEMS 8
 #define VT_CHUNK (VT_THREADS * VT_ITEMS)
@@ -233,14 +234,13 @@ __global__ void __launch_bounds__(256) k_classify_multi(DevData d) {
 // k_scatter
 // ------------------------------------------------------------------------------------------------------
 struct ScatterShared {
-    uint32_t gstart[SC_THREADS], cend[SC_THREADS], seqoff[SC_THREADS], cigoff[SC_THREADS];
-    uint16_t len[SC_THREADS], ncig[SC_THREADS];
-    uint8_t fl[SC_THREADS];                       // bit0 good, bit1 rc, bit2 k != 1
     unsigned long long fix_key[SC_STAGE], fix_val[SC_STAGE];
     unsigned long long oth_val[SC_STAGE], oth_sig[SC_STAGE];
     uint32_t oth_pos[SC_STAGE];
-    uint32_t n_fix, n_oth, base_fix, base_oth, next, n_good;
+    uint32_t n_fix, n_oth, base_fix, base_oth, n_good;
+    uint32_t seq_lo, seq_hi;                      // byte range of the sequence pool used by this block's good alignments
     unsigned long long oth_len;
+    __align__(16) uint8_t seq[SC_SEQ_BYTES + 64]; // staged [seq_lo, seq_lo + SC_SEQ_BYTES) (+ slack for the 3-word window reads)
 };
 
 template <int BITS> struct Scatter {
@@ -276,15 +276,13 @@ template <int BITS> struct Scatter {
         else push_other(pos, aln, ri, 1, 1ull | ((unsigned long long)s << (BITS == 4 ? 4 : 8)));
     }
     // interval add + fix-list membership for an alignment that keeps entries [gstart, gstart + nkept)
-    __device__ __forceinline__ void add_interval(uint32_t lane8, unsigned long long aln, uint32_t gstart, uint32_t nkept, bool multi) {
+    __device__ __forceinline__ void add_interval(unsigned long long aln, uint32_t gstart, uint32_t nkept, bool multi) {
         if (nkept == 0) return;
-        if (lane8 == 0) {
-            unsigned long long v = 1ull | (multi ? (1ull << 32) : 0ull);
-            atomicAdd(&d.diff[gstart], v);
-            atomicAdd(&d.diff[gstart + nkept], 0ull - v);
-        }
-        uint32_t t0 = gstart >> PP_TILE_SHIFT, t1 = (gstart + nkept - 1) >> PP_TILE_SHIFT;
-        for (uint32_t t = t0 + lane8; t <= t1; t += 8)
+        const unsigned long long v = 1ull | (multi ? (1ull << 32) : 0ull);
+        atomicAdd(&d.diff[gstart], v);
+        atomicAdd(&d.diff[gstart + nkept], 0ull - v);
+        const uint32_t t0 = gstart >> PP_TILE_SHIFT, t1 = (gstart + nkept - 1) >> PP_TILE_SHIFT;
+        for (uint32_t t = t0; t <= t1; ++t)
             if ((d.tileflag[t >> 5] >> (t & 31)) & 1u) push_fix(t, aln, gstart, nkept);
     }
     // 4-bit only: `vc` (<= 32) single-base entries whose read codes are the low nibbles of r0:r1, at reference
@@ -314,110 +312,74 @@ template <int BITS> struct Scatter {
     }
 };
 
-#define GROUP_MASK(lane) (0xFFu << ((lane) & 24))
-
-__device__ __forceinline__ unsigned long long shfl64(unsigned mask, unsigned long long v, int src) {
-    uint32_t lo = __shfl_sync(mask, (uint32_t)v, src, 8);
-    uint32_t hi = __shfl_sync(mask, (uint32_t)(v >> 32), src, 8);
-    return ((unsigned long long)hi << 32) | lo;
-}
-
+// One THREAD per alignment (consecutive alignments on consecutive threads): every per-alignment array is read
+// coalesced, there is no intra-warp cooperation to fall out of step, and simple and indel-bearing alignments run the
+// same code with slightly different trip counts.  The block's slice of the 4-bit sequence pool is staged in shared
+// memory by a coalesced cooperative copy; the draft is compared 32 bases at a time on 128-bit words.
 template <int BITS>
 __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
     __shared__ ScatterShared sh;
     Scatter<BITS> S{d, sh};
-    const uint32_t tid = threadIdx.x, lane = tid & 31, lane8 = tid & 7;
-    const unsigned gmask = GROUP_MASK(lane);
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
     const unsigned long long n_blocks = (d.n_aln + SC_THREADS - 1) / SC_THREADS;
     unsigned long long used = 0;
 
     for (unsigned long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        // ---- stage 1: coalesced metadata loads + goodness, one alignment per thread
-        if (tid == 0) { sh.n_fix = 0; sh.n_oth = 0; sh.oth_len = 0; sh.next = 0; }
-        const unsigned long long a = blk * SC_THREADS + tid;
-        uint8_t f = 0;
-        if (a < d.n_aln) {
-            const uint32_t rid = d.read_id[a];
-            const bool multi = group_is_multi(d, a, rid);
-            const uint32_t co = d.cigar_off[a], nc = d.n_cigar[a];
-            const uint8_t fl = d.flags[a];
-            if (alignment_is_good(d, a, multi, co, nc, fl)) {
+        if (tid == 0) { sh.n_fix = 0; sh.n_oth = 0; sh.oth_len = 0; sh.seq_lo = 0xFFFFFFFFu; sh.seq_hi = 0; }
+        __syncthreads();
+        // ---- stage 1: metadata + goodness (alignment.rs:283-287), one alignment per thread
+        const unsigned long long aln = blk * SC_THREADS + tid;
+        bool good = false, rc = false, multi = false;
+        uint32_t gstart = 0, cend = 0, seqoff = 0, cigoff = 0, len = 0, ncig = 0;
+        if (aln < d.n_aln) {
+            const uint32_t rid = d.read_id[aln];
+            const bool grp = group_is_multi(d, aln, rid);
+            cigoff = d.cigar_off[aln];
+            ncig = d.n_cigar[aln];
+            const uint8_t fl = d.flags[aln];
+            if (alignment_is_good(d, aln, grp, cigoff, ncig, fl)) {
                 used++;
-                const uint32_t c = d.contig[a];
-                if (c == PP_CONTIG_UNKNOWN) report_error(d.st, a, ERR_UNKNOWN_CONTIG);
-                else if (fl & PP_FLAG_NOSEQ) report_error(d.st, a, ERR_NOSEQ);
+                const uint32_t c = d.contig[aln];
+                if (c == PP_CONTIG_UNKNOWN) report_error(d.st, aln, ERR_UNKNOWN_CONTIG);
+                else if (fl & PP_FLAG_NOSEQ) report_error(d.st, aln, ERR_NOSEQ);
                 else {
-                    const unsigned long long gs = d.contig_off[c] + d.ref_start[a];
+                    const unsigned long long gs = d.contig_off[c] + d.ref_start[aln];
                     const unsigned long long ce = d.contig_off[c + 1];
-                    if (gs >= ce) report_error(d.st, a, ERR_OOB);
+                    if (gs >= ce) report_error(d.st, aln, ERR_OOB);
                     else {
-                        sh.gstart[tid] = (uint32_t)gs;
-                        sh.cend[tid] = (uint32_t)ce;
-                        sh.seqoff[tid] = d.seq_off[a];
-                        sh.cigoff[tid] = co;
-                        sh.len[tid] = d.seq_len[a];
-                        sh.ncig[tid] = (uint16_t)nc;
-                        f = (uint8_t)(1 | ((fl & PP_FLAG_RC) ? 2 : 0) | ((multi && d.k[rid] != 1) ? 4 : 0));
+                        good = true;
+                        gstart = (uint32_t)gs; cend = (uint32_t)ce;
+                        seqoff = d.seq_off[aln]; len = d.seq_len[aln];
+                        rc = fl & PP_FLAG_RC;
+                        multi = grp && d.k[rid] != 1;
+                        if (BITS == 4) {
+                            const unsigned long long b0 = (unsigned long long)seqoff * 16, b1 = b0 + (((unsigned long long)len + 31) / 32) * 16;
+                            if (b1 < 0xFFFFFFFFull) { atomicMin(&sh.seq_lo, (uint32_t)b0); atomicMax(&sh.seq_hi, (uint32_t)b1); }
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(d.draft_nib + (gs >> 4)));
+                        }
                     }
                 }
             }
         }
-        sh.fl[tid] = f;
         __syncthreads();
+        // ---- stage 1b: coalesced copy of the block's sequence bytes into shared memory
+        const uint32_t seq_lo = sh.seq_lo;
+        const uint32_t seq_hi = (sh.seq_hi > seq_lo) ? (uint32_t)min((unsigned long long)sh.seq_hi, (unsigned long long)seq_lo + SC_SEQ_BYTES) : seq_lo;
+        if (BITS == 4) {
+            for (unsigned long long off = (unsigned long long)seq_lo + tid * 16; off < seq_hi; off += SC_THREADS * 16)
+                *reinterpret_cast<uint4*>(sh.seq + (off - seq_lo)) = __ldg(reinterpret_cast<const uint4*>(d.seq_pool + off));
+            __syncthreads();
+        }
 
-        // ---- stage 2: 8 lanes per alignment; lane groups pull the next alignment from a shared counter
-        for (;;) {
-            uint32_t s = 0;
-            if (lane8 == 0) s = atomicAdd(&sh.next, 1u);
-            s = __shfl_sync(gmask, s, 0, 8);
-            if (s >= SC_THREADS) break;
-            const uint32_t fl = sh.fl[s];
-            if (!(fl & 1)) continue;
-            const unsigned long long aln = blk * SC_THREADS + s;
-            const uint32_t gstart = sh.gstart[s], cend = sh.cend[s], seqoff = sh.seqoff[s], cigoff = sh.cigoff[s];
-            const uint32_t len = sh.len[s], ncig = sh.ncig[s];
-            const bool rc = fl & 2, multi = fl & 4;
-
-            if (BITS == 4 && ncig == 1 && !rc && len <= 256 && len > 0) {
-                // ================= fast path: one M/= run, stored strand, <= 256 bases =================
-                const uint32_t op0 = d.cigar_ops[cigoff];
-                if ((op0 >> 4) != len) { if (lane8 == 0) report_error(d.st, aln, ERR_SEQ_MISMATCH); continue; }
-                const uint32_t b0 = lane8 * 32;
-                unsigned long long r0 = 0, r1 = 0;
-                if (b0 < len) {
-                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(d.seq_pool + (size_t)seqoff * 16) + lane8);
-                    r0 = ((unsigned long long)q.y << 32) | q.x;
-                    r1 = ((unsigned long long)q.w << 32) | q.z;
-                }
-                // right-end homopolymer trim (alignment.rs:364-378): run of entries equal to the last base
-                const uint32_t li = len - 1;
-                uint32_t last = (uint32_t)(((li & 16) ? r1 : r0) >> ((li & 15) * 4)) & 15u;
-                last = __shfl_sync(gmask, last, li >> 5, 8);
-                const unsigned long long rep = 0x1111111111111111ull * last;
-                const unsigned long long nz0 = nibble_nonzero(r0 ^ rep), nz1 = nibble_nonzero(r1 ^ rep);
-                uint32_t run = 0;
-                {
-                    int sc = (int)(li >> 4);
-                    uint32_t idx = li & 15;
-                    for (;;) {
-                        unsigned long long w = shfl64(gmask, (sc & 1) ? nz1 : nz0, sc >> 1);
-                        unsigned long long m = (idx == 15) ? w : (w & ((1ull << (4 * (idx + 1))) - 1));
-                        if (m) { run += idx - (uint32_t)((63 - __clzll((long long)m)) >> 2); break; }
-                        run += idx + 1;
-                        if (sc == 0) break;
-                        --sc; idx = 15;
-                    }
-                }
-                const uint32_t nkept = (len - run >= 1) ? (len - run - 1) : 0;
-                if (gstart + nkept > cend) { if (lane8 == 0) report_error(d.st, aln, ERR_OOB); continue; }
-                S.add_interval(lane8, aln, gstart, nkept, multi);
-                if (b0 < nkept) S.scan_mismatches(r0, r1, min(nkept - b0, 32u), gstart + b0, aln, b0);
-                continue;
+        // ---- stage 2: the CIGAR walk of this thread's alignment (alignment.rs:175-201, 364-378; pileup.rs:189-200)
+        if (good) do {
+            const uint8_t* seqp = d.seq_pool + (size_t)seqoff * (BITS == 4 ? 16 : 32);
+            if (BITS == 4) {
+                const unsigned long long b0 = (unsigned long long)seqoff * 16, b1 = b0 + (((unsigned long long)len + 31) / 32) * 16;
+                if (b0 >= seq_lo && b1 <= seq_hi) seqp = sh.seq + (b0 - seq_lo);
             }
-
-            // ================= general path (indels, =/X runs, reverse-complemented SEQ="*", 8-bit pool) =====
-            // pass 1 (uniform over the 8 lanes): validate ops, E = entries, read bases consumed
             const uint32_t* ops = d.cigar_ops + cigoff;
+            // pass 1: validate ops, E = entries, R = read bases consumed
             unsigned long long E = 0, R = 0;
             bool bad = false;
             for (uint32_t p = 0; p < ncig; ++p) {
@@ -427,10 +389,10 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                 else if (o == PP_OP_D) E += l;
                 else bad = true;                                   // alignment.rs:187-193
             }
-            if (bad) { if (lane8 == 0) report_error(d.st, aln, ERR_BAD_OP); continue; }
-            if (R != len) { if (lane8 == 0) report_error(d.st, aln, ERR_SEQ_MISMATCH); continue; }   // :195-198
+            if (bad) { report_error(d.st, aln, ERR_BAD_OP); break; }
+            if (R != len) { report_error(d.st, aln, ERR_SEQ_MISMATCH); break; }   // :195-198
             // pass 2: trim.  Walk entries from the right; stop at the first entry that is not the single base `last`.
-            const uint32_t last = Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, len - 1);
+            const uint32_t last = Seq<BITS>::read_sym(seqp, 0, len, rc, len - 1);
             unsigned long long run = 0;
             {
                 uint32_t ri = len;            // read index just past the current entry's M-part
@@ -442,21 +404,21 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                     if (o == PP_OP_D) {
                         // entries (ri, ri + pend): only the rightmost can carry pend; equal to `last` iff pend == 1 and base == last
                         for (uint32_t t = 0; t < l; ++t) {
-                            if (pend == 1 && Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri) == last) { run++; pend = 0; }
+                            if (pend == 1 && Seq<BITS>::read_sym(seqp, 0, len, rc, ri) == last) { run++; pend = 0; }
                             else { stop = true; break; }
                         }
                         continue;
                     }
                     for (uint32_t t = 0; t < l; ++t) {                // M / = / X
-                        if (pend == 0 && Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri - 1) == last) { run++; ri--; }
+                        if (pend == 0 && Seq<BITS>::read_sym(seqp, 0, len, rc, ri - 1) == last) { run++; ri--; }
                         else { stop = true; break; }
                     }
                 }
             }
             const unsigned long long nk64 = (E - run >= 1) ? (E - run - 1) : 0;
-            if ((unsigned long long)gstart + nk64 > cend) { if (lane8 == 0) report_error(d.st, aln, ERR_OOB); continue; }
+            if ((unsigned long long)gstart + nk64 > cend) { report_error(d.st, aln, ERR_OOB); break; }
             const uint32_t nkept = (uint32_t)nk64;
-            S.add_interval(lane8, aln, gstart, nkept, multi);
+            S.add_interval(aln, gstart, nkept, multi);
             // pass 3: emit entries e < nkept
             uint32_t e = 0, ri = 0;
             for (uint32_t p = 0; p < ncig && e < nkept; ++p) {
@@ -465,33 +427,33 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                 uint32_t ins = 0;                                     // inserted bases right after this op
                 for (uint32_t q = p + 1; q < ncig && (ops[q] & 15u) == PP_OP_I; ++q) ins += ops[q] >> 4;
                 if (o == PP_OP_D) {
-                    const uint32_t plain = ins ? l - 1 : l;           // the last "-" entry absorbs a following insertion
-                    for (uint32_t t = lane8; t < plain && e + t < nkept; t += 8) atomicAdd(&d.delother[gstart + e + t], 1u);
-                    if (ins && lane8 == 0 && e + l - 1 < nkept) {
+                    const uint32_t plain = min(ins ? l - 1 : l, nkept - e);   // the last "-" entry absorbs a following insertion
+                    for (uint32_t t = 0; t < plain; ++t) atomicAdd(&d.delother[gstart + e + t], 1u);
+                    if (ins && e + l - 1 < nkept) {
                         const uint32_t pos = gstart + e + l - 1;
-                        if (ins == 1) S.count_base(pos, Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri), aln, ri);
-                        else S.push_other(pos, aln, ri, ins, make_sig<BITS>(d.seq_pool, seqoff, len, rc, ri, ins));
+                        if (ins == 1) S.count_base(pos, Seq<BITS>::read_sym(seqp, 0, len, rc, ri), aln, ri);
+                        else S.push_other(pos, aln, ri, ins, make_sig<BITS>(seqp, 0, len, rc, ri, ins));
                     }
                     e += l;
                     continue;
                 }
                 const uint32_t plain = min(ins ? l - 1 : l, nkept - e);   // single-base entries of this M / = / X run that are kept
                 if (BITS == 4) {
-                    for (uint32_t c0 = lane8 * 32; c0 < plain; c0 += 256) {
+                    for (uint32_t c0 = 0; c0 < plain; c0 += 32) {
                         unsigned long long r0, r1;
-                        load_read32(reinterpret_cast<const unsigned long long*>(d.seq_pool + (size_t)seqoff * 16), len, rc, ri + c0, r0, r1);
+                        load_read32(reinterpret_cast<const unsigned long long*>(seqp), len, rc, ri + c0, r0, r1);
                         S.scan_mismatches(r0, r1, min(plain - c0, 32u), gstart + e + c0, aln, ri + c0);
                     }
                 } else {
-                    for (uint32_t t = lane8; t < plain; t += 8)
-                        S.count_base(gstart + e + t, Seq<BITS>::read_sym(d.seq_pool, seqoff, len, rc, ri + t), aln, ri + t);
+                    for (uint32_t t = 0; t < plain; ++t)
+                        S.count_base(gstart + e + t, Seq<BITS>::read_sym(seqp, 0, len, rc, ri + t), aln, ri + t);
                 }
-                if (ins && lane8 == 0 && e + l - 1 < nkept)
-                    S.push_other(gstart + e + l - 1, aln, ri + l - 1, 1 + ins, make_sig<BITS>(d.seq_pool, seqoff, len, rc, ri + l - 1, 1 + ins));
+                if (ins && e + l - 1 < nkept)
+                    S.push_other(gstart + e + l - 1, aln, ri + l - 1, 1 + ins, make_sig<BITS>(seqp, 0, len, rc, ri + l - 1, 1 + ins));
                 e += l;
                 ri += l;
             }
-        }
+        } while (false);
         __syncthreads();
         // ---- flush the staged fix-list entries and other-allele records
         if (tid == 0) {
@@ -806,7 +768,7 @@ __device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const VotePara
 }
 
 template <int BITS>
-__global__ void __launch_bounds__(VT_THREADS) k_vote(DevData d, VoteParams vp) {
+__global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp) {
     __shared__ unsigned long long s_warp[VT_THREADS / 32];
     __shared__ unsigned long long s_total, s_prefix;
     __shared__ uint32_t s_chunk;
