@@ -1,12 +1,12 @@
 // polish_kernels.cu — the polish hot path as sm_100a kernels + the C-ABI entry points that drive them.
 //
 // Replaces, on the device (reference = /root/reference/src):
-//   process_one_read            alignment.rs:275-305  -> k_classify (goodness, k = #good per read)
+//   process_one_read            alignment.rs:275-305  -> k_scatter stage 1 (goodness, k = #good per read group)
 //   get_read_bases_for_each_target_base + trim_bases_for_homopolymers
-//                               alignment.rs:175-201, 364-378 -> k_scatter (CIGAR walk, right-end trim)
-//   Pileup::add_alignment / PileupBase::add_seq   pileup.rs:189-200, 56-65 -> k_scatter (+ k_depth_fixup)
+//                               alignment.rs:175-201, 364-378 -> k_scatter stage 2 (CIGAR walk, right-end trim)
+//   Pileup::add_alignment / PileupBase::add_seq   pileup.rs:189-200, 56-65 -> k_scatter (+ k_collect / k_depth_fixup)
 //   PileupBase::get_polished_seq + bankers_rounding pileup.rs:67-134, misc.rs:208-215 -> k_vote
-//   polish_one_sequence's join + replace("-","")  polish.rs:185-188 -> k_vote (stream compaction)
+//   polish_one_sequence's join + replace("-","")  polish.rs:185-188 -> k_compact
 //
 // Design (DESIGN.md has the derivation): the reference adds one counter per aligned base (5e8 increments for
 // 5 Mbp x 100x), which on any GPU is bound by atomic throughput, not by HBM.  Here the pileup of a position is
@@ -15,12 +15,13 @@
 //     -v at end) into a difference array, prefix-summed inside k_vote;
 //   * explicit[p][allele] = entries whose allele differs from the draft base -> one atomic per mismatch
 //     (~0.3 % of bases); count[draft base] = cover - sum(explicit);
-//   * alleles other than A,C,G,T,"-" (N / IUPAC bases, insertions) -> appended as records, sorted by position,
-//     counted exactly (string compare) by the vote's slow path;
+//   * alleles other than A,C,G,T,"-" (N / IUPAC bases, insertions) -> one node per distinct (position, allele) in a
+//     per-position chain with an exact count (the reference's HashMap<String,u32>, pileup.rs:40,62);
 //   * depth: where every covering alignment has k == 1 the f64 depth equals cover exactly; positions covered
 //     by a multi-mapped read (k != 1) get the reference's sequential f64 sum re-done in SAM order by
 //     k_depth_fixup (ordered walk over the alignments binned to that 128-position tile).
-// All of it is integer / byte work bounded by HBM bandwidth: no tensor cores.
+// The whole call is one stream of kernels with no host round trip in the middle.  All of it is integer / byte work
+// bounded by HBM bandwidth: no tensor cores.
 #include <cuda_runtime.h>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -35,26 +36,45 @@
 
 #define PP_TILE_SHIFT 7              // depth fix-up tile = 128 positions
 #define PP_TILE (1u << PP_TILE_SHIFT)
-#define SC_THREADS 256               // scatter CTA
-#define SC_STAGE 320                 // smem staging entries (fix list / other records) per CTA
+#define SC_THREADS 256               // scatter CTA: one alignment per thread
 #define SC_SEQ_BYTES 24576           // smem window for the block's slice of the sequence pool (4-bit mode)
+#define SC_GROUP_SCAN_LIMIT 8192     // alignments of one read group a thread will scan outside its block for k
+#define CL_THREADS 256               // collect CTA
+#define CL_ITEMS 4
+#define CL_CHUNK (CL_THREADS * CL_ITEMS)
 #define VT_THREADS 256
 #define VT_ITEMS 8
 #define VT_CHUNK (VT_THREADS * VT_ITEMS)
+#define NONE32 0xFFFFFFFFu
 
 enum : unsigned {
     ERR_UNKNOWN_CONTIG = 1, ERR_SEQ_MISMATCH = 2, ERR_BAD_OP = 3, ERR_OOB = 4, ERR_NOSEQ = 5
 };
-enum : unsigned { FL_OTHER_OVF = 1, FL_FIX_OVF = 2, FL_COUNTER_OVF = 4, FL_OUT_OVF = 8 };
+enum : unsigned { FL_NODE_OVF = 1, FL_FIX_OVF = 2, FL_COUNTER_OVF = 4, FL_OUT_OVF = 8, FL_BIGGROUP = 16 };
 
 struct DevStatus {
     unsigned long long err;          // min over (aln << 8 | code); ~0 = none
-    unsigned long long other_len;    // sum of other-record lengths (bounds the output size)
     unsigned long long n_used;       // good alignments
     unsigned long long out_len;      // polished bases
-    unsigned int other_count, fix_count;
+    unsigned long long fix_count;    // (alignment, flagged tile) pairs found by k_collect
+    unsigned int node_count;         // other-allele nodes allocated
     unsigned int flags;
-    unsigned int ticket;             // k_vote chunk ticket
+    unsigned int ticket_vote, ticket_collect;
+};
+
+struct DevParams {                   // pp_polish_params, device resident (refreshed by a memcpy before each call)
+    double fv, fi;
+    uint32_t min_depth, max_errors;
+    int careful;
+    int pad;
+};
+
+// One distinct other allele at one position (the reference's HashMap<String,u32> entry, pileup.rs:40,62).
+struct OthNode {
+    unsigned long long sig;          // allele signature (see make_sig)
+    unsigned long long val;          // where to read the allele: aln << 32 | start << 16 | len
+    uint32_t count;
+    uint32_t next;                   // next node of the same position, NONE32 = end
 };
 
 struct DevData {                     // everything the kernels read, by value
@@ -68,22 +88,23 @@ struct DevData {                     // everything the kernels read, by value
     const unsigned long long* contig_off;
     uint32_t n_contigs;
     uint32_t G;                      // total positions
+    uint32_t n_tiles;
     // work
-    uint32_t* k;                     // [n_reads] good alignments per read
+    uint32_t* k;                     // [n_reads] good alignments per read (only in the global-k fallback mode)
     unsigned long long* draft_nib;   // 4-bit draft codes, 16 per word
     unsigned long long* diff;        // [G+1] lo32 cover, hi32 covering alignments with k != 1
     unsigned long long* ex;          // [G] explicit A,C,G,T counts, 16 bits each
-    uint32_t* delother;              // [G] lo16 "-" count, hi16 other-allele record count
-    uint32_t* tileflag;              // bitmap, tiles that may hold k != 1 coverage
-    double* depth_fix;               // [G] ordered depth for flagged tiles
-    unsigned long long *fix_key, *fix_val;      // (tile << aln_bits | aln) , (gstart<<32|n_kept)
-    uint32_t aln_bits;               // bits needed for an alignment index
-    unsigned long long* oth_key;     // gpos << 32 | mix32(signature)
-    unsigned long long* oth_sig;     // allele signature: exact content for short alleles (see make_sig)
-    unsigned long long* oth_val;     // aln<<32 | start<<16 | len
-    uint32_t fix_cap, oth_cap;
-    uint32_t max_errors;             // -m
-    int careful;                     // --careful
+    uint32_t* delother;              // [G] lo16 "-" count, hi16 other-allele entry count
+    uint32_t* oth_head;              // [G] 1 + index of the first OthNode of the position, 0 = none
+    OthNode* nodes;
+    uint32_t node_cap;
+    uint32_t* tileflag;              // bitmap, tiles that hold k != 1 coverage
+    unsigned long long* rec_gn;      // [n_aln] gstart << 32 | kept entries (0 = contributes nothing)
+    uint32_t* rec_k;                 // [n_aln] k of the alignment's read group
+    double* depth_fix;               // [n_tiles * 128] ordered depth, valid for flagged tiles
+    uint32_t *fix_key, *fix_val;     // (tile + 1, alignment) pairs of flagged tiles; 0 keys = unused slots
+    uint32_t fix_cap;
+    const DevParams* prm;
     DevStatus* st;
 };
 
@@ -190,7 +211,7 @@ __global__ void __launch_bounds__(256) k_draft_nib(const uint8_t* __restrict__ d
 
 // ------------------------------------------------------------------------------------------------------
 // Goodness (alignment.rs:283-287) and --careful (:277-279) of one alignment.  `multi` = its read group has more
-// than one aligned record.  Shared by k_classify_multi and k_scatter so that both see the same answer.
+// than one aligned record.
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool group_is_multi(const DevData& d, unsigned long long a, uint32_t rid) {
     return (a > 0 && d.read_id[a - 1] == rid) || (a + 1 < d.n_aln && d.read_id[a + 1] == rid);
@@ -198,35 +219,77 @@ __device__ __forceinline__ bool group_is_multi(const DevData& d, unsigned long l
 __device__ __forceinline__ bool alignment_is_good(const DevData& d, unsigned long long a, bool multi, uint32_t co, uint32_t nc, uint8_t fl) {
     if (nc == 0) { report_error(d.st, a, ERR_BAD_OP); return false; }       // the packer never emits this
     const uint32_t f = d.cigar_ops[co] & 15u, l = d.cigar_ops[co + nc - 1] & 15u;
-    return (f == PP_OP_M || f == PP_OP_EQ) && (l == PP_OP_M || l == PP_OP_EQ) && d.nm[a] <= d.max_errors &&
-           !(fl & PP_FLAG_ZPFAIL) && !(d.careful && multi);
+    return (f == PP_OP_M || f == PP_OP_EQ) && (l == PP_OP_M || l == PP_OP_EQ) && d.nm[a] <= d.prm->max_errors &&
+           !(fl & PP_FLAG_ZPFAIL) && !(d.prm->careful && multi);
 }
 
-// k_classify_multi: only alignments of multi-record groups need a pre-pass: k = #good of the group (alignment.rs:288)
-// and the tile marks for the ordered-depth fix-up (a superset of where k != 1 coverage can occur).  Singletons
-// (the vast majority) have k = 1 and are classified inside k_scatter.
+// k_classify_multi: FALLBACK pre-pass, only launched when a read group was too large for k_scatter's in-kernel scan
+// (FL_BIGGROUP): k = #good of every multi-record group into a global array (alignment.rs:288).
 __global__ void __launch_bounds__(256) k_classify_multi(DevData d) {
     for (unsigned long long a = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; a < d.n_aln;
          a += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t rid = d.read_id[a];
         if (!group_is_multi(d, a, rid)) continue;
-        const uint32_t co = d.cigar_off[a], nc = d.n_cigar[a];
-        if (!alignment_is_good(d, a, true, co, nc, d.flags[a])) continue;
-        atomicAdd(&d.k[rid], 1u);
-        const uint32_t c = d.contig[a];
-        if (c == PP_CONTIG_UNKNOWN) continue;                  // reported by k_scatter
-        unsigned long long reflen = 0;
-        for (uint32_t i = 0; i < nc; ++i) {
-            const uint32_t op = d.cigar_ops[co + i], o = op & 15u;
-            if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X || o == PP_OP_D) reflen += op >> 4;
+        if (alignment_is_good(d, a, true, d.cigar_off[a], d.n_cigar[a], d.flags[a])) atomicAdd(&d.k[rid], 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Other alleles: find-or-insert into the per-position chain.  Nodes are written completely, fenced, then linked
+// with a CAS on the head; readers load head and node fields through L2 (ld.cg), so a linked node is always whole.
+// ------------------------------------------------------------------------------------------------------
+struct SeqRef {                      // where an alignment's bases live, for comparing long alleles
+    const uint8_t* seq_pool;
+    const uint32_t* seq_off;
+    const uint16_t* seq_len;
+    const uint8_t* flags;
+};
+
+template <int BITS>
+__device__ __forceinline__ uint32_t allele_sym(const SeqRef& r, unsigned long long val, uint32_t t) {
+    const uint32_t aln = (uint32_t)(val >> 32), start = (uint32_t)(val >> 16) & 0xFFFFu;
+    return Seq<BITS>::read_sym(r.seq_pool, r.seq_off[aln], r.seq_len[aln], r.flags[aln] & PP_FLAG_RC, start + t);
+}
+template <int BITS>
+__device__ bool allele_equal(const SeqRef& r, unsigned long long va, unsigned long long vb) {
+    const uint32_t la = (uint32_t)va & 0xFFFFu, lb = (uint32_t)vb & 0xFFFFu;
+    if (la != lb) return false;
+    for (uint32_t i = 0; i < la; ++i)
+        if (allele_sym<BITS>(r, va, i) != allele_sym<BITS>(r, vb, i)) return false;
+    return true;
+}
+
+template <int BITS>
+__device__ void other_insert(const DevData& d, uint32_t pos, unsigned long long val, unsigned long long sig) {
+    atomicAdd(&d.delother[pos], 1u << 16);                     // entries (not distinct alleles): feeds `matched`
+    const SeqRef sr{d.seq_pool, d.seq_off, d.seq_len, d.flags};
+    uint32_t mine = NONE32;
+    uint32_t h = __ldcg(&d.oth_head[pos]);                      // 1 + node index, 0 = empty
+    uint32_t stop = 0;
+    for (;;) {
+        for (uint32_t n = h; n != stop;) {
+            const OthNode* nd = &d.nodes[n - 1];
+            const unsigned long long nsig = __ldcg(&nd->sig);
+            if (nsig == sig && (sig_exact<BITS>(sig) || allele_equal<BITS>(sr, __ldcg(&nd->val), val))) {
+                atomicAdd(&d.nodes[n - 1].count, 1u);
+                return;                                         // (a node allocated on an earlier round stays unlinked)
+            }
+            const uint32_t nx = __ldcg(&nd->next);
+            n = (nx == NONE32) ? 0 : nx + 1;
         }
-        const unsigned long long gs = d.contig_off[c] + d.ref_start[a];
-        unsigned long long ge = gs + reflen;                   // exclusive, before trimming
-        const unsigned long long cend = d.contig_off[c + 1];
-        if (ge > cend) ge = cend;
-        if (gs >= ge) continue;
-        for (unsigned long long t = gs >> PP_TILE_SHIFT; t <= ((ge - 1) >> PP_TILE_SHIFT); ++t)
-            atomicOr(&d.tileflag[t >> 5], 1u << (t & 31));
+        if (mine == NONE32) {
+            mine = atomicAdd(&d.st->node_count, 1u);
+            if (mine >= d.node_cap) { atomicOr(&d.st->flags, FL_NODE_OVF); return; }
+            d.nodes[mine].sig = sig;
+            d.nodes[mine].val = val;
+            d.nodes[mine].count = 1;
+        }
+        d.nodes[mine].next = (h == 0) ? NONE32 : h - 1;
+        __threadfence();
+        const uint32_t old = atomicCAS(&d.oth_head[pos], h, mine + 1);
+        if (old == h) return;
+        stop = h;                                               // someone linked new nodes in front: look only at those
+        h = old;
     }
 }
 
@@ -234,37 +297,18 @@ __global__ void __launch_bounds__(256) k_classify_multi(DevData d) {
 // k_scatter
 // ------------------------------------------------------------------------------------------------------
 struct ScatterShared {
-    unsigned long long fix_key[SC_STAGE], fix_val[SC_STAGE];
-    unsigned long long oth_val[SC_STAGE], oth_sig[SC_STAGE];
-    uint32_t oth_pos[SC_STAGE];
-    uint32_t n_fix, n_oth, base_fix, base_oth, n_good;
+    uint32_t rid[SC_THREADS];
+    uint8_t good[SC_THREADS];
+    uint32_t n_good;
     uint32_t seq_lo, seq_hi;                      // byte range of the sequence pool used by this block's good alignments
-    unsigned long long oth_len;
     __align__(16) uint8_t seq[SC_SEQ_BYTES + 64]; // staged [seq_lo, seq_lo + SC_SEQ_BYTES) (+ slack for the 3-word window reads)
 };
 
 template <int BITS> struct Scatter {
     const DevData& d;
-    ScatterShared& sh;
 
     __device__ __forceinline__ void push_other(uint32_t pos, unsigned long long aln, uint32_t start, uint32_t len, unsigned long long sig) {
-        atomicAdd(&d.delother[pos], 1u << 16);
-        atomicAdd(&sh.oth_len, (unsigned long long)len);
-        unsigned long long v = (aln << 32) | ((unsigned long long)(start & 0xFFFFu) << 16) | (len & 0xFFFFu);
-        uint32_t s = atomicAdd(&sh.n_oth, 1u);
-        if (s < SC_STAGE) { sh.oth_pos[s] = pos; sh.oth_val[s] = v; sh.oth_sig[s] = sig; return; }
-        uint32_t g = atomicAdd(&d.st->other_count, 1u);
-        if (g < d.oth_cap) { d.oth_key[g] = ((unsigned long long)pos << 32) | mix32(sig); d.oth_val[g] = v; d.oth_sig[g] = sig; }
-        else atomicOr(&d.st->flags, FL_OTHER_OVF);
-    }
-    __device__ __forceinline__ void push_fix(uint32_t tile, unsigned long long aln, uint32_t gstart, uint32_t nkept) {
-        unsigned long long k = ((unsigned long long)tile << d.aln_bits) | aln;
-        unsigned long long v = ((unsigned long long)gstart << 32) | nkept;
-        uint32_t s = atomicAdd(&sh.n_fix, 1u);
-        if (s < SC_STAGE) { sh.fix_key[s] = k; sh.fix_val[s] = v; return; }
-        uint32_t g = atomicAdd(&d.st->fix_count, 1u);
-        if (g < d.fix_cap) { d.fix_key[g] = k; d.fix_val[g] = v; }
-        else atomicOr(&d.st->flags, FL_FIX_OVF);
+        other_insert<BITS>(d, pos, (aln << 32) | ((unsigned long long)(start & 0xFFFFu) << 16) | (len & 0xFFFFu), sig);
     }
     // one single-base entry at reference position pos carrying read symbol s (read index ri)
     __device__ __forceinline__ void count_base(uint32_t pos, uint32_t s, unsigned long long aln, uint32_t ri) {
@@ -275,15 +319,17 @@ template <int BITS> struct Scatter {
         if (c >= 0) atomicAdd(&d.ex[pos], 1ull << (16 * c));
         else push_other(pos, aln, ri, 1, 1ull | ((unsigned long long)s << (BITS == 4 ? 4 : 8)));
     }
-    // interval add + fix-list membership for an alignment that keeps entries [gstart, gstart + nkept)
-    __device__ __forceinline__ void add_interval(unsigned long long aln, uint32_t gstart, uint32_t nkept, bool multi) {
+    // interval add for an alignment that keeps entries [gstart, gstart + nkept); alignments of reads with k != 1 also
+    // mark the 128-position tiles they cover (those get the ordered depth sum)
+    __device__ __forceinline__ void add_interval(uint32_t gstart, uint32_t nkept, bool multi) {
         if (nkept == 0) return;
         const unsigned long long v = 1ull | (multi ? (1ull << 32) : 0ull);
         atomicAdd(&d.diff[gstart], v);
         atomicAdd(&d.diff[gstart + nkept], 0ull - v);
-        const uint32_t t0 = gstart >> PP_TILE_SHIFT, t1 = (gstart + nkept - 1) >> PP_TILE_SHIFT;
-        for (uint32_t t = t0; t <= t1; ++t)
-            if ((d.tileflag[t >> 5] >> (t & 31)) & 1u) push_fix(t, aln, gstart, nkept);
+        if (multi) {
+            const uint32_t t0 = gstart >> PP_TILE_SHIFT, t1 = (gstart + nkept - 1) >> PP_TILE_SHIFT;
+            for (uint32_t t = t0; t <= t1; ++t) atomicOr(&d.tileflag[t >> 5], 1u << (t & 31));
+        }
     }
     // 4-bit only: `vc` (<= 32) single-base entries whose read codes are the low nibbles of r0:r1, at reference
     // positions pos0.. ; ri0 = read index of the first one.  One explicit count per base that differs from the draft.
@@ -316,47 +362,84 @@ template <int BITS> struct Scatter {
 // coalesced, there is no intra-warp cooperation to fall out of step, and simple and indel-bearing alignments run the
 // same code with slightly different trip counts.  The block's slice of the 4-bit sequence pool is staged in shared
 // memory by a coalesced cooperative copy; the draft is compared 32 bases at a time on 128-bit words.
-template <int BITS>
+// GLOBALK = false: k of a multi-record group is counted right here (its records are consecutive alignments);
+// GLOBALK = true : k comes from k_classify_multi (fallback for huge groups).
+template <int BITS, bool GLOBALK>
 __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
     __shared__ ScatterShared sh;
-    Scatter<BITS> S{d, sh};
+    Scatter<BITS> S{d};
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const unsigned long long n_blocks = (d.n_aln + SC_THREADS - 1) / SC_THREADS;
     unsigned long long used = 0;
 
     for (unsigned long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        if (tid == 0) { sh.n_fix = 0; sh.n_oth = 0; sh.oth_len = 0; sh.seq_lo = 0xFFFFFFFFu; sh.seq_hi = 0; }
-        __syncthreads();
+        if (tid == 0) { sh.seq_lo = 0xFFFFFFFFu; sh.seq_hi = 0; }
         // ---- stage 1: metadata + goodness (alignment.rs:283-287), one alignment per thread
-        const unsigned long long aln = blk * SC_THREADS + tid;
-        bool good = false, rc = false, multi = false;
-        uint32_t gstart = 0, cend = 0, seqoff = 0, cigoff = 0, len = 0, ncig = 0;
+        const unsigned long long blk0 = blk * SC_THREADS;
+        const unsigned long long aln = blk0 + tid;
+        const uint32_t nvalid = (uint32_t)min((unsigned long long)SC_THREADS, d.n_aln - blk0);
+        bool good = false, grp = false;
+        uint32_t rid = 0, cigoff = 0, ncig = 0;
+        uint8_t fl = 0;
         if (aln < d.n_aln) {
-            const uint32_t rid = d.read_id[aln];
-            const bool grp = group_is_multi(d, aln, rid);
+            rid = d.read_id[aln];
+            grp = group_is_multi(d, aln, rid);
             cigoff = d.cigar_off[aln];
             ncig = d.n_cigar[aln];
-            const uint8_t fl = d.flags[aln];
-            if (alignment_is_good(d, aln, grp, cigoff, ncig, fl)) {
-                used++;
-                const uint32_t c = d.contig[aln];
-                if (c == PP_CONTIG_UNKNOWN) report_error(d.st, aln, ERR_UNKNOWN_CONTIG);
-                else if (fl & PP_FLAG_NOSEQ) report_error(d.st, aln, ERR_NOSEQ);
+            fl = d.flags[aln];
+            good = alignment_is_good(d, aln, grp, cigoff, ncig, fl);
+        }
+        sh.rid[tid] = rid;
+        sh.good[tid] = good ? 1 : 0;
+        __syncthreads();
+        // k = number of good alignments of the read group (alignment.rs:288)
+        uint32_t k = 1;
+        if (good && grp) {
+            if (GLOBALK) k = d.k[rid];
+            else {
+                uint32_t count = 1, steps = 0;
+                int i = (int)tid;
+                while (i > 0 && sh.rid[i - 1] == rid) { --i; count += sh.good[i]; }
+                if (i == 0) {
+                    for (unsigned long long a2 = blk0; a2 > 0 && d.read_id[a2 - 1] == rid;) {
+                        --a2;
+                        count += alignment_is_good(d, a2, true, d.cigar_off[a2], d.n_cigar[a2], d.flags[a2]) ? 1 : 0;
+                        if (++steps > SC_GROUP_SCAN_LIMIT) { atomicOr(&d.st->flags, FL_BIGGROUP); break; }
+                    }
+                }
+                i = (int)tid;
+                while (i + 1 < (int)nvalid && sh.rid[i + 1] == rid) { ++i; count += sh.good[i]; }
+                if (i == (int)nvalid - 1) {
+                    for (unsigned long long a2 = blk0 + nvalid - 1; a2 + 1 < d.n_aln && d.read_id[a2 + 1] == rid;) {
+                        ++a2;
+                        count += alignment_is_good(d, a2, true, d.cigar_off[a2], d.n_cigar[a2], d.flags[a2]) ? 1 : 0;
+                        if (++steps > SC_GROUP_SCAN_LIMIT) { atomicOr(&d.st->flags, FL_BIGGROUP); break; }
+                    }
+                }
+                k = count;
+            }
+        }
+        bool rc = false;
+        uint32_t gstart = 0, cend = 0, seqoff = 0, len = 0;
+        if (good) {
+            used++;
+            good = false;
+            const uint32_t c = d.contig[aln];
+            if (c == PP_CONTIG_UNKNOWN) report_error(d.st, aln, ERR_UNKNOWN_CONTIG);
+            else if (fl & PP_FLAG_NOSEQ) report_error(d.st, aln, ERR_NOSEQ);
+            else {
+                const unsigned long long gs = d.contig_off[c] + d.ref_start[aln];
+                const unsigned long long ce = d.contig_off[c + 1];
+                if (gs >= ce) report_error(d.st, aln, ERR_OOB);
                 else {
-                    const unsigned long long gs = d.contig_off[c] + d.ref_start[aln];
-                    const unsigned long long ce = d.contig_off[c + 1];
-                    if (gs >= ce) report_error(d.st, aln, ERR_OOB);
-                    else {
-                        good = true;
-                        gstart = (uint32_t)gs; cend = (uint32_t)ce;
-                        seqoff = d.seq_off[aln]; len = d.seq_len[aln];
-                        rc = fl & PP_FLAG_RC;
-                        multi = grp && d.k[rid] != 1;
-                        if (BITS == 4) {
-                            const unsigned long long b0 = (unsigned long long)seqoff * 16, b1 = b0 + (((unsigned long long)len + 31) / 32) * 16;
-                            if (b1 < 0xFFFFFFFFull) { atomicMin(&sh.seq_lo, (uint32_t)b0); atomicMax(&sh.seq_hi, (uint32_t)b1); }
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(d.draft_nib + (gs >> 4)));
-                        }
+                    good = true;
+                    gstart = (uint32_t)gs; cend = (uint32_t)ce;
+                    seqoff = d.seq_off[aln]; len = d.seq_len[aln];
+                    rc = fl & PP_FLAG_RC;
+                    if (BITS == 4) {
+                        const unsigned long long b0 = (unsigned long long)seqoff * 16, b1 = b0 + (((unsigned long long)len + 31) / 32) * 16;
+                        if (b1 < 0xFFFFFFFFull) { atomicMin(&sh.seq_lo, (uint32_t)b0); atomicMax(&sh.seq_hi, (uint32_t)b1); }
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.draft_nib + (gs >> 4)));
                     }
                 }
             }
@@ -372,6 +455,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
         }
 
         // ---- stage 2: the CIGAR walk of this thread's alignment (alignment.rs:175-201, 364-378; pileup.rs:189-200)
+        uint32_t nkept = 0;
         if (good) do {
             const uint8_t* seqp = d.seq_pool + (size_t)seqoff * (BITS == 4 ? 16 : 32);
             if (BITS == 4) {
@@ -417,8 +501,8 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
             }
             const unsigned long long nk64 = (E - run >= 1) ? (E - run - 1) : 0;
             if ((unsigned long long)gstart + nk64 > cend) { report_error(d.st, aln, ERR_OOB); break; }
-            const uint32_t nkept = (uint32_t)nk64;
-            S.add_interval(aln, gstart, nkept, multi);
+            nkept = (uint32_t)nk64;
+            S.add_interval(gstart, nkept, k != 1);
             // pass 3: emit entries e < nkept
             uint32_t e = 0, ri = 0;
             for (uint32_t p = 0; p < ncig && e < nkept; ++p) {
@@ -454,31 +538,10 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
                 ri += l;
             }
         } while (false);
-        __syncthreads();
-        // ---- flush the staged fix-list entries and other-allele records
-        if (tid == 0) {
-            uint32_t nf = min(sh.n_fix, (uint32_t)SC_STAGE), no = min(sh.n_oth, (uint32_t)SC_STAGE);
-            sh.base_fix = nf ? atomicAdd(&d.st->fix_count, nf) : 0;
-            sh.base_oth = no ? atomicAdd(&d.st->other_count, no) : 0;
-            if (sh.oth_len) atomicAdd(&d.st->other_len, sh.oth_len);
-        }
-        __syncthreads();
-        {
-            const uint32_t nf = min(sh.n_fix, (uint32_t)SC_STAGE), no = min(sh.n_oth, (uint32_t)SC_STAGE);
-            for (uint32_t i = tid; i < nf; i += SC_THREADS) {
-                uint32_t g = sh.base_fix + i;
-                if (g < d.fix_cap) { d.fix_key[g] = sh.fix_key[i]; d.fix_val[g] = sh.fix_val[i]; }
-                else atomicOr(&d.st->flags, FL_FIX_OVF);
-            }
-            for (uint32_t i = tid; i < no; i += SC_THREADS) {
-                uint32_t g = sh.base_oth + i;
-                if (g < d.oth_cap) {
-                    d.oth_key[g] = ((unsigned long long)sh.oth_pos[i] << 32) | mix32(sh.oth_sig[i]);
-                    d.oth_val[g] = sh.oth_val[i];
-                    d.oth_sig[g] = sh.oth_sig[i];
-                }
-                else atomicOr(&d.st->flags, FL_OTHER_OVF);
-            }
+        // what k_collect / k_depth_fixup need to know about this alignment
+        if (aln < d.n_aln) {
+            d.rec_gn[aln] = nkept ? (((unsigned long long)gstart << 32) | nkept) : 0ull;
+            d.rec_k[aln] = k;
         }
         __syncthreads();
     }
@@ -490,74 +553,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
     __syncthreads();
     if (tid == 0 && sh.n_good) atomicAdd(&d.st->n_used, (unsigned long long)sh.n_good);
 }
-
-// ------------------------------------------------------------------------------------------------------
-// k_depth_fixup: the reference's sequential f64 depth sum (pileup.rs:64, alignment.rs:288) for every
-// position of a flagged tile, in SAM order (keys sorted by (tile, alignment index)).
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lower_bound_u64(const unsigned long long* a, uint32_t n, unsigned long long key) {
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
-    return lo;
-}
-
-__global__ void __launch_bounds__(PP_TILE) k_depth_fixup(DevData d, const unsigned long long* __restrict__ keys,
-                                                         const unsigned long long* __restrict__ vals, uint32_t n) {
-    const uint32_t tile = blockIdx.x;
-    if (!((d.tileflag[tile >> 5] >> (tile & 31)) & 1u)) return;
-    __shared__ uint32_t s_lo, s_hi;
-    __shared__ uint32_t s_start[PP_TILE], s_end[PP_TILE];
-    __shared__ double s_inv[PP_TILE];
-    if (threadIdx.x == 0) s_lo = lower_bound_u64(keys, n, (unsigned long long)tile << d.aln_bits);
-    if (threadIdx.x == 1) s_hi = lower_bound_u64(keys, n, (unsigned long long)(tile + 1) << d.aln_bits);
-    __syncthreads();
-    const uint32_t lo = s_lo, hi = s_hi;
-    const uint32_t p = tile * PP_TILE + threadIdx.x;
-    double depth = 0.0;
-    for (uint32_t base = lo; base < hi; base += PP_TILE) {
-        const uint32_t i = base + threadIdx.x;
-        if (i < hi) {
-            const unsigned long long v = vals[i];
-            const uint32_t aln = (uint32_t)(keys[i] & ((1ull << d.aln_bits) - 1));
-            // k is only accumulated for multi-record groups (k_classify_multi); a singleton in this list is good, so k = 1
-            const uint32_t kk = max(d.k[d.read_id[aln]], 1u);
-            s_start[threadIdx.x] = (uint32_t)(v >> 32);
-            s_end[threadIdx.x] = (uint32_t)(v >> 32) + (uint32_t)v;
-            s_inv[threadIdx.x] = __ddiv_rn(1.0, (double)kk);      // 1.0 / good_alignments.len() as f64
-        }
-        __syncthreads();
-        const uint32_t cnt = min((uint32_t)PP_TILE, hi - base);
-        for (uint32_t j = 0; j < cnt; ++j)
-            if (p >= s_start[j] && p < s_end[j]) depth = __dadd_rn(depth, s_inv[j]);
-        __syncthreads();
-    }
-    if (p < d.G) d.depth_fix[p] = depth;
-}
-
-// ------------------------------------------------------------------------------------------------------
-// k_vote: prefix sum of the difference array (decoupled look-back), the per-position vote, output compaction.
-// ------------------------------------------------------------------------------------------------------
-struct VoteParams {
-    double fv, fi;
-    uint32_t min_depth;
-    uint32_t n_chunks;
-    uint8_t* out;
-    unsigned long long out_cap;
-    unsigned long long* out_off;     // [n_contigs+1]
-    unsigned long long *changed, *zero_depth;   // [n_contigs]
-    // look-back descriptors of the difference-array prefix sum
-    uint32_t* st1; unsigned long long *agg1, *inc1;
-    // per-position verdicts handed from k_vote to k_compact
-    uint16_t* res;                    // [padG] low byte = character, high byte = output length (255: see rec_len)
-    uint32_t* rec_at;                 // [G] other-allele record to emit at a position (only where res says so)
-    long long* chunk_delta;           // [n_chunks] sum(output length) - positions of the chunk
-    const uint32_t* ofirst;           // [G] index of the first sorted record of a position (only where records exist)
-    const unsigned long long* okey;   // sorted (pos << 32 | mix32(sig))
-    const uint32_t* oidx;             // record index of each sorted key
-    const unsigned long long* osig;   // by record index
-    const unsigned long long* oval;   // by record index
-    uint32_t n_oth;
-};
 
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
     uint32_t v;
@@ -645,99 +640,167 @@ __device__ __forceinline__ uint32_t bankers_rounding(double x) {
     return rd + (rd & 1u);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// k_collect: every (alignment, flagged tile) pair, written IN ALIGNMENT ORDER by an order-preserving compaction
+// (block scan + decoupled look-back).  A stable sort by tile then leaves each tile's list in SAM order, which is
+// the order the reference adds depth contributions in (pileup.rs:64).
+// ------------------------------------------------------------------------------------------------------
+struct CollectParams { uint32_t n_chunks; uint32_t* st; unsigned long long *agg, *inc; };
+
+__global__ void __launch_bounds__(CL_THREADS) k_collect(DevData d, CollectParams cp) {
+    __shared__ unsigned long long s_warp[CL_THREADS / 32];
+    __shared__ unsigned long long s_total, s_prefix;
+    __shared__ uint32_t s_chunk;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) s_chunk = atomicAdd(&d.st->ticket_collect, 1u);
+    __syncthreads();
+    const uint32_t chunk = s_chunk;
+    if (chunk >= cp.n_chunks) return;
+    const unsigned long long a0 = (unsigned long long)chunk * CL_CHUNK + tid * CL_ITEMS;
+    unsigned long long gn[CL_ITEMS];
+    {
+        const ulonglong2* q = reinterpret_cast<const ulonglong2*>(d.rec_gn + a0);     // rec_gn is padded to whole chunks
+#pragma unroll
+        for (int i = 0; i < CL_ITEMS / 2; ++i) { const ulonglong2 v = q[i]; gn[2 * i] = v.x; gn[2 * i + 1] = v.y; }
+    }
+    unsigned long long cnt = 0;
+#pragma unroll
+    for (int i = 0; i < CL_ITEMS; ++i) {
+        if (a0 + i >= d.n_aln) gn[i] = 0;
+        const uint32_t nk = (uint32_t)gn[i];
+        if (!nk) continue;
+        const uint32_t gs = (uint32_t)(gn[i] >> 32);
+        for (uint32_t t = gs >> PP_TILE_SHIFT; t <= ((gs + nk - 1) >> PP_TILE_SHIFT); ++t)
+            cnt += (d.tileflag[t >> 5] >> (t & 31)) & 1u;
+    }
+    const unsigned long long excl = block_exscan(cnt, s_warp, &s_total);
+    const unsigned long long total = s_total;
+    if (tid < 32) {
+        const unsigned long long pre = lookback(chunk, total, cp.st, cp.agg, cp.inc);
+        if (tid == 0) s_prefix = pre;
+    }
+    __syncthreads();
+    unsigned long long o = s_prefix + excl;
+    if (chunk == cp.n_chunks - 1 && tid == CL_THREADS - 1) {
+        d.st->fix_count = o + cnt;
+        if (o + cnt > d.fix_cap) atomicOr(&d.st->flags, FL_FIX_OVF);
+    }
+    if (!cnt) return;
+#pragma unroll
+    for (int i = 0; i < CL_ITEMS; ++i) {
+        const uint32_t nk = (uint32_t)gn[i];
+        if (!nk) continue;
+        const uint32_t gs = (uint32_t)(gn[i] >> 32);
+        for (uint32_t t = gs >> PP_TILE_SHIFT; t <= ((gs + nk - 1) >> PP_TILE_SHIFT); ++t)
+            if ((d.tileflag[t >> 5] >> (t & 31)) & 1u) {
+                if (o < d.fix_cap) { d.fix_key[o] = t + 1; d.fix_val[o] = (uint32_t)(a0 + i); }
+                o++;
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_depth_fixup: the reference's sequential f64 depth sum (pileup.rs:64, alignment.rs:288) for every
+// position of a flagged tile, in SAM order.  keys = tile + 1 sorted ascending (unused slots are 0 and sort first).
+// ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t key) {
     uint32_t lo = 0, hi = n;
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
     return lo;
 }
 
+__global__ void __launch_bounds__(PP_TILE) k_depth_fixup(DevData d, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals) {
+    __shared__ uint32_t s_lo, s_hi;
+    __shared__ uint32_t s_start[PP_TILE], s_end[PP_TILE];
+    __shared__ double s_inv[PP_TILE];
+    for (uint32_t tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
+        if (!((d.tileflag[tile >> 5] >> (tile & 31)) & 1u)) continue;
+        if (threadIdx.x == 0) s_lo = lower_bound_u32(keys, d.fix_cap, tile + 1);
+        if (threadIdx.x == 1) s_hi = lower_bound_u32(keys, d.fix_cap, tile + 2);
+        __syncthreads();
+        const uint32_t lo = s_lo, hi = s_hi;
+        const uint32_t p = tile * PP_TILE + threadIdx.x;
+        double depth = 0.0;
+        for (uint32_t base = lo; base < hi; base += PP_TILE) {
+            const uint32_t i = base + threadIdx.x;
+            if (i < hi) {
+                const uint32_t aln = vals[i];
+                const unsigned long long v = d.rec_gn[aln];
+                s_start[threadIdx.x] = (uint32_t)(v >> 32);
+                s_end[threadIdx.x] = (uint32_t)(v >> 32) + (uint32_t)v;
+                s_inv[threadIdx.x] = __ddiv_rn(1.0, (double)d.rec_k[aln]);      // 1.0 / good_alignments.len() as f64
+            }
+            __syncthreads();
+            const uint32_t cnt = min((uint32_t)PP_TILE, hi - base);
+            for (uint32_t j = 0; j < cnt; ++j)
+                if (p >= s_start[j] && p < s_end[j]) depth = __dadd_rn(depth, s_inv[j]);
+            __syncthreads();
+        }
+        d.depth_fix[p] = depth;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_vote: prefix sum of the difference array (decoupled look-back) and the per-position vote.
+// ------------------------------------------------------------------------------------------------------
+struct VoteParams {
+    uint32_t n_chunks;
+    uint8_t* out;
+    unsigned long long out_cap;
+    unsigned long long* out_off;     // [n_contigs+1]
+    unsigned long long *changed, *zero_depth;   // [n_contigs]
+    uint32_t* st1; unsigned long long *agg1, *inc1;   // look-back descriptors of the difference-array prefix sum
+    // per-position verdicts handed from k_vote to k_compact
+    uint16_t* res;                    // [padG] low byte = character, high byte = output length (255: see rec_at)
+    uint32_t* rec_at;                 // [G] other-allele node to emit at a position (only where res says so)
+    long long* chunk_delta;           // [n_chunks] sum(output length) - positions of the chunk
+};
+
 // What the other-allele slow path needs, passed by value so that the kernel parameter structs are never
 // spilled to local memory for a call.
 struct OthCtx {
-    const unsigned long long *okey, *osig, *oval;
-    const uint32_t *oidx, *ofirst, *seq_off;
-    const uint16_t* seq_len;
-    const uint8_t *flags, *seq_pool;
-    uint32_t n_oth;
+    const OthNode* nodes;
+    const uint32_t* head;
+    SeqRef sr;
 };
 
-template <int BITS>
-__device__ bool other_equal(const OthCtx& d, unsigned long long va, unsigned long long vb) {
-    const uint32_t la = (uint32_t)va & 0xFFFFu, lb = (uint32_t)vb & 0xFFFFu;
-    if (la != lb) return false;
-    const uint32_t aa = (uint32_t)(va >> 32), ab = (uint32_t)(vb >> 32);
-    const uint32_t sa = (uint32_t)(va >> 16) & 0xFFFFu, sb = (uint32_t)(vb >> 16) & 0xFFFFu;
-    const bool rca = d.flags[aa] & PP_FLAG_RC, rcb = d.flags[ab] & PP_FLAG_RC;
-    const uint32_t oa = d.seq_off[aa], ob = d.seq_off[ab], na = d.seq_len[aa], nb = d.seq_len[ab];
-    for (uint32_t i = 0; i < la; ++i)
-        if (Seq<BITS>::read_sym(d.seq_pool, oa, na, rca, sa + i) != Seq<BITS>::read_sym(d.seq_pool, ob, nb, rcb, sb + i)) return false;
-    return true;
-}
-
-struct Tally { uint32_t nvalid, ninter; int which; uint32_t rec; };   // which: 0..3 ACGT, 4 "-", 5 draft's own non-ACGT base, 6 other record
+struct Tally { uint32_t nvalid, ninter; int which; uint32_t rec; };   // which: 0..3 ACGT, 4 "-", 5 draft's own non-ACGT base, 6 other node
 
 __device__ __forceinline__ void tally(Tally& t, uint32_t c, uint32_t vt, uint32_t it, int which, uint32_t rec) {
     if (c >= vt) { t.nvalid++; t.which = which; t.rec = rec; }
     else if (c >= it) t.ninter++;
 }
 
-// Other alleles at `pos` (pileup.rs:102-109): the records of a position are contiguous in the sorted key array and
-// grouped by the hash of their signature; a group whose signatures are all the same exact signature is one allele.
-template <int BITS>
-__device__ __noinline__ Tally tally_others(OthCtx vp, uint32_t pos, uint32_t vt, uint32_t it, Tally t) {
-    const OthCtx& d = vp;
-    const uint32_t n = vp.n_oth;
-    uint32_t i = vp.ofirst[pos];
-    while (i < n && (uint32_t)(vp.okey[i] >> 32) == pos) {
-        const unsigned long long k = vp.okey[i];
-        uint32_t j = i + 1;
-        while (j < n && vp.okey[j] == k) j++;
-        const unsigned long long s0 = vp.osig[vp.oidx[i]];
-        bool uniform = sig_exact<BITS>(s0);
-        for (uint32_t q = i + 1; q < j && uniform; ++q) uniform = vp.osig[vp.oidx[q]] == s0;
-        if (uniform) {
-            tally(t, j - i, vt, it, 6, vp.oidx[i]);
-        } else {                                   // hash collision or long alleles: exact pairwise counting
-            for (uint32_t a = i; a < j; ++a) {
-                const uint32_t ia = vp.oidx[a];
-                const unsigned long long sa = vp.osig[ia];
-                bool rep = true;
-                uint32_t c = 0;
-                for (uint32_t b2 = i; b2 < j; ++b2) {
-                    const uint32_t ib = vp.oidx[b2];
-                    bool eq = vp.osig[ib] == sa && (sig_exact<BITS>(sa) || other_equal<BITS>(d, vp.oval[ia], vp.oval[ib]));
-                    if (eq) { if (b2 < a) { rep = false; break; } c++; }
-                }
-                if (rep) tally(t, c, vt, it, 6, ia);
-            }
-        }
-        i = j;
+// Other alleles at `pos` (pileup.rs:102-109): one chain node per distinct allele, count already exact.
+__device__ __noinline__ Tally tally_others(OthCtx oc, uint32_t pos, uint32_t vt, uint32_t it, Tally t) {
+    for (uint32_t n = oc.head[pos]; n != 0;) {
+        const OthNode& nd = oc.nodes[n - 1];
+        tally(t, nd.count, vt, it, 6, n - 1);
+        n = (nd.next == NONE32) ? 0 : nd.next + 1;
     }
     return t;
 }
 
-// Symbol t of other-allele record `rec` (from the exact signature when there is one, else from the read).
+// Character t of other-allele node `rec` (from the exact signature when there is one, else from the read).
 template <int BITS>
-__device__ __forceinline__ uint8_t other_char(const OthCtx& vp, uint32_t rec, uint32_t t) {
-    const OthCtx& d = vp;
-    const unsigned long long sig = vp.osig[rec];
+__device__ __forceinline__ uint8_t other_char(const OthCtx& oc, uint32_t rec, uint32_t t) {
+    const unsigned long long sig = oc.nodes[rec].sig;
     if (sig_exact<BITS>(sig)) return Seq<BITS>::ascii((uint32_t)(sig >> ((BITS == 4 ? 4 : 8) * (t + 1))) & (BITS == 4 ? 15u : 255u));
-    const unsigned long long val = vp.oval[rec];
-    const uint32_t aln = (uint32_t)(val >> 32), start = (uint32_t)(val >> 16) & 0xFFFFu;
-    return Seq<BITS>::ascii(Seq<BITS>::read_sym(d.seq_pool, d.seq_off[aln], d.seq_len[aln], d.flags[aln] & PP_FLAG_RC, start + t));
+    return Seq<BITS>::ascii(allele_sym<BITS>(oc.sr, oc.nodes[rec].val, t));
 }
 
 // Result of one position, packed: bits 0..15 output length, 16..23 output char (when length is 1 and not from a
-// multi-base record), bit 24 changed, bit 25 emit from record `rec`.
+// multi-base node), bit 24 changed, bit 25 emit from node `rec`.
 struct PosOut { uint32_t packed; uint32_t rec; };
 
 // The vote of pileup.rs:67-134 for one covered position.
 template <int BITS>
-__device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const VoteParams& vp, uint32_t pos, uint32_t orig, double depth,
+__device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const DevParams& prm, uint32_t pos, uint32_t orig, double depth,
                                                 uint32_t cA, uint32_t cC, uint32_t cG, uint32_t cT, uint32_t cDel,
                                                 uint32_t matched, uint32_t n_other) {
-    const uint32_t vt = max(vp.min_depth, bankers_rounding(__dmul_rn(depth, vp.fv)));
-    const uint32_t it = bankers_rounding(__dmul_rn(depth, vp.fi));
+    const uint32_t vt = max(prm.min_depth, bankers_rounding(__dmul_rn(depth, prm.fv)));
+    const uint32_t it = bankers_rounding(__dmul_rn(depth, prm.fi));
     Tally t{0, 0, -1, 0};
     tally(t, cA, vt, it, 0, 0);
     tally(t, cC, vt, it, 1, 0);
@@ -745,11 +808,11 @@ __device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const VotePara
     tally(t, cT, vt, it, 3, 0);
     if (cDel) tally(t, cDel, vt, it, 4, 0);                  // "-" exists only if it was seen (a HashMap entry)
     if (matched) tally(t, matched, vt, it, 5, 0);            // the 1-char string of a non-ACGT draft base
-    if (n_other) t = tally_others<BITS>(oc, pos, vt, it, t);
+    if (n_other) t = tally_others(oc, pos, vt, it, t);
     PosOut o;
     o.rec = 0;
     o.packed = (orig == '-' ? 0u : 1u) | (orig << 16);
-    if (depth < (double)vp.min_depth) return o;                // low_depth
+    if (depth < (double)prm.min_depth) return o;               // low_depth
     if (t.nvalid != 1 || t.ninter > 0) return o;               // none / multiple / too_close
     if (t.which <= 3) {
         const uint32_t nb = (uint32_t)"ACGT"[t.which];
@@ -757,7 +820,7 @@ __device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const VotePara
     } else if (t.which == 4) {
         o.packed = 0u | ((uint32_t)'-' << 16) | (orig != '-' ? 1u << 24 : 0u);
     } else if (t.which == 6) {
-        const uint32_t len = (uint32_t)oc.oval[t.rec] & 0xFFFFu;
+        const uint32_t len = (uint32_t)oc.nodes[t.rec].val & 0xFFFFu;
         uint32_t n = 0;
         for (uint32_t q = 0; q < len; ++q) n += other_char<BITS>(oc, t.rec, q) != '-';
         // an other-allele string never equals the draft's own 1-char string (those entries are "matched")
@@ -771,13 +834,15 @@ template <int BITS>
 __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp) {
     __shared__ unsigned long long s_warp[VT_THREADS / 32];
     __shared__ unsigned long long s_total, s_prefix;
+    __shared__ long long s_delta[VT_THREADS / 32];
     __shared__ uint32_t s_chunk;
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) s_chunk = atomicAdd(&d.st->ticket, 1u);
+    if (tid == 0) s_chunk = atomicAdd(&d.st->ticket_vote, 1u);
     __syncthreads();
     const uint32_t chunk = s_chunk;
     if (chunk >= vp.n_chunks) return;
     const uint32_t p0 = chunk * VT_CHUNK + tid * VT_ITEMS;
+    const DevParams prm = *d.prm;
 
     // ---- 1. difference array -> cover / multi (arrays are padded to a whole number of chunks)
     unsigned long long dv[VT_ITEMS];
@@ -790,7 +855,7 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
 #pragma unroll
     for (int i = 0; i < VT_ITEMS; ++i) { tsum += dv[i]; dv[i] = tsum; }     // thread-inclusive
     const unsigned long long texcl = block_exscan(tsum, s_warp, &s_total);
-    unsigned long long total = s_total;
+    const unsigned long long total = s_total;
     if (tid < 32) {
         const unsigned long long pre = lookback(chunk, total, vp.st1, vp.agg1, vp.inc1);
         if (tid == 0) s_prefix = pre;
@@ -811,8 +876,8 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
     }
     const uint2 dr = *reinterpret_cast<const uint2*>(d.draft + p0);
     OthCtx oc;
-    oc.okey = vp.okey; oc.osig = vp.osig; oc.oval = vp.oval; oc.oidx = vp.oidx; oc.ofirst = vp.ofirst; oc.seq_off = d.seq_off; oc.seq_len = d.seq_len;
-    oc.flags = d.flags; oc.seq_pool = d.seq_pool; oc.n_oth = vp.n_oth;
+    oc.nodes = d.nodes; oc.head = d.oth_head;
+    oc.sr = SeqRef{d.seq_pool, d.seq_off, d.seq_len, d.flags};
     PosOut po[VT_ITEMS];
     unsigned long long tlen = 0;
     uint32_t n_changed = 0, n_zero = 0;
@@ -855,7 +920,7 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
         else if (orig == 'G') { cG += matched; matched = 0; }
         else if (orig == 'T') { cT += matched; matched = 0; }
         const double depth = multi ? d.depth_fix[p] : (double)cover;
-        po[i] = vote_position<BITS>(oc, vp, p, orig, depth, cA, cC, cG, cT, cDel, matched, n_other);
+        po[i] = vote_position<BITS>(oc, prm, p, orig, depth, cA, cC, cG, cT, cDel, matched, n_other);
         n_changed += (po[i].packed >> 24) & 1u;
         tlen += po[i].packed & 0xFFFFu;
     }
@@ -878,7 +943,6 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
     const uint32_t npos = (p0 < d.G) ? min((uint32_t)VT_ITEMS, d.G - p0) : 0u;
     long long delta = (long long)tlen - (long long)npos;
     for (int o = 16; o > 0; o >>= 1) delta += __shfl_down_sync(0xffffffffu, delta, o);
-    __shared__ long long s_delta[VT_THREADS / 32];
     if ((tid & 31) == 0) s_delta[tid >> 5] = delta;
     __syncthreads();
     if (tid == 0) {
@@ -919,8 +983,8 @@ __global__ void __launch_bounds__(VT_THREADS) k_compact(DevData d, VoteParams vp
     uint32_t len[VT_ITEMS];
     unsigned long long tlen = 0;
     OthCtx oc;
-    oc.okey = vp.okey; oc.osig = vp.osig; oc.oval = vp.oval; oc.oidx = vp.oidx; oc.ofirst = vp.ofirst; oc.seq_off = d.seq_off; oc.seq_len = d.seq_len;
-    oc.flags = d.flags; oc.seq_pool = d.seq_pool; oc.n_oth = vp.n_oth;
+    oc.nodes = d.nodes; oc.head = d.oth_head;
+    oc.sr = SeqRef{d.seq_pool, d.seq_off, d.seq_len, d.flags};
 #pragma unroll
     for (int i = 0; i < VT_ITEMS; ++i) {
         const uint32_t h = (w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
@@ -928,7 +992,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_compact(DevData d, VoteParams vp
         if (p0 + i >= d.G) l = 0;
         else if (l == 255) {                                      // a multi-base allele: count its non-'-' characters
             const uint32_t rec = vp.rec_at[p0 + i];
-            const uint32_t rlen = (uint32_t)vp.oval[rec] & 0xFFFFu;
+            const uint32_t rlen = (uint32_t)oc.nodes[rec].val & 0xFFFFu;
             l = 0;
             for (uint32_t t = 0; t < rlen; ++t) l += other_char<BITS>(oc, rec, t) != '-';
         }
@@ -963,7 +1027,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_compact(DevData d, VoteParams vp
         const uint32_t h = (w[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
         if ((h >> 8) != 255) { dst[o++] = (uint8_t)h; continue; }
         const uint32_t rec = vp.rec_at[p0 + i];
-        const uint32_t rlen = (uint32_t)vp.oval[rec] & 0xFFFFu;
+        const uint32_t rlen = (uint32_t)oc.nodes[rec].val & 0xFFFFu;
         for (uint32_t t = 0; t < rlen; ++t) {
             const uint8_t ch = other_char<BITS>(oc, rec, t);
             if (ch != '-') dst[o++] = ch;                          // polish.rs:188 replace("-", "")
@@ -987,18 +1051,6 @@ __global__ void __launch_bounds__(VT_THREADS) k_compact(DevData d, VoteParams vp
     for (uint32_t i = head + nvec * 16 + tid; i < n; i += VT_THREADS) g[i] = s_out[i];
 }
 
-// first sorted record of every position that has other-allele records
-__global__ void __launch_bounds__(256) k_oth_first(const unsigned long long* __restrict__ okey, uint32_t n, uint32_t* __restrict__ ofirst) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t pos = (uint32_t)(okey[i] >> 32);
-        if (i == 0 || (uint32_t)(okey[i - 1] >> 32) != pos) ofirst[pos] = i;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_iota(uint32_t* a, uint32_t n) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = i;
-}
-
 // ------------------------------------------------------------------------------------------------------
 // host side: context, buffers, entry points
 // ------------------------------------------------------------------------------------------------------
@@ -1019,26 +1071,27 @@ struct DevBuf {
 };
 
 enum { B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL,
-       B_DRAFT, B_CTGOFF, B_NIB, B_ZEROPOOL, B_DEPTHFIX, B_FIXKEY, B_FIXVAL,
-       B_FIXKEY2, B_FIXVAL2, B_OTHKEY, B_OTHVAL, B_OTHSIG, B_OTHIDX, B_OTHKEY2, B_OTHIDX2, B_CUBTMP, B_OUT, B_OUTOFF,
-       B_AGG1, B_INC1, B_RES, B_RECAT, B_CHUNKDELTA, B_OFIRST, B_COUNT };
+       B_DRAFT, B_CTGOFF, B_NIB, B_ZEROPOOL, B_DEPTHFIX, B_RECGN, B_RECK, B_NODES, B_FIXKEY2, B_FIXVAL2, B_CUBTMP, B_OUT,
+       B_OUTOFF, B_AGG1, B_INC1, B_AGGC, B_INCC, B_RES, B_RECAT, B_CHUNKDELTA, B_PARAMS, B_SCRATCH, B_COUNT };
 
 struct pp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
     DevBuf b[B_COUNT];
-    cudaEvent_t ev[PP_N_STAGES + 2] = {};
+    cudaEvent_t ev[PP_N_STAGES + 4] = {};
     DevStatus* h_status = nullptr;        // pinned
+    DevParams* h_params = nullptr;        // pinned
     bool have_ds = false;
     // dataset facts
     uint64_t n_aln = 0, n_reads = 0, n_ops = 0, seq_bytes = 0, G = 0;
     uint32_t n_contigs = 0, seq_bits = 4;
-    std::vector<uint64_t> contig_off;
     int sm_count = 148;
     uint32_t launches = 0;
-    uint64_t last_out_len = 0;
-    bool have_result = false;
+    // sizes that adapt when a call overflows them (kept across calls on the same dataset)
+    uint32_t node_cap = 0, fix_cap = 0;
+    uint64_t out_cap = 0;
+    bool global_k = false;
 
     int fail(int code, const std::string& m) { err = m; return code; }
     int fail_cuda(cudaError_t e, const char* what, int line) {
@@ -1080,6 +1133,7 @@ extern "C" int pp_create(int device, pp_ctx** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     for (auto& ev : ctx->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     if (cudaHostAlloc((void**)&ctx->h_status, sizeof(DevStatus), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    if (cudaHostAlloc((void**)&ctx->h_params, sizeof(DevParams), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     uint8_t comp[256];
     init_comp_table(comp);
     if (cudaMemcpyToSymbol(c_comp, comp, 256) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
@@ -1094,6 +1148,7 @@ extern "C" void pp_destroy(pp_ctx* ctx) {
     for (auto& b : ctx->b) b.release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_params) cudaFreeHost(ctx->h_params);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1111,8 +1166,8 @@ int pp_ctx_fail_cuda(pp_ctx* ctx, cudaError_t e, const char* what, const char* f
     return PP_ERR_CUDA;
 }
 void* pp_ctx_scratch(pp_ctx* ctx, size_t bytes) {
-    if (ctx->b[B_CUBTMP].ensure(bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return ctx->b[B_CUBTMP].p;
+    if (ctx->b[B_SCRATCH].ensure(bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return ctx->b[B_SCRATCH].p;
 }
 
 template <class T>
@@ -1130,11 +1185,10 @@ extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alig
         return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: null alignment array");
     if (a->seq_bits != 4 && a->seq_bits != 8) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: seq_bits must be 4 or 8");
     const uint64_t G = c->off[c->n_contigs];
-    if (G == 0 || G >= 0xFFFFFFFFull - 64) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: total assembly length must be in [1, 2^32-64)");
-    if (a->n_aln >= 0xFFFFFFFFull) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: more than 2^32-1 alignments");
+    if (G == 0 || G >= 0xFFFFFFFFull - 2 * VT_CHUNK) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: total assembly length must be in [1, 2^32-4096)");
+    if (a->n_aln >= 0xFFFFFFFFull - 2 * CL_CHUNK) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: more than 2^32-2048 alignments");
     CK(cudaSetDevice(ctx->device));
     ctx->have_ds = false;
-    ctx->have_result = false;
     int rc;
     if ((rc = upload(ctx, B_CONTIG, a->contig, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_REFSTART, a->ref_start, a->n_aln))) return rc;
@@ -1152,7 +1206,11 @@ extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alig
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_aln = a->n_aln; ctx->n_reads = a->n_reads; ctx->n_ops = a->n_cigar_ops; ctx->seq_bytes = a->seq_pool_bytes;
     ctx->seq_bits = a->seq_bits; ctx->G = G; ctx->n_contigs = c->n_contigs;
-    ctx->contig_off.assign(c->off, c->off + c->n_contigs + 1);
+    // first guesses; a call that overflows one of them grows it and repeats itself
+    ctx->node_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, a->n_aln / 8 + G / 64));
+    ctx->fix_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, a->n_aln / 4));
+    ctx->out_cap = G + G / 16 + (1u << 20);
+    ctx->global_k = false;
     ctx->have_ds = true;
     return PP_OK;
 }
@@ -1169,40 +1227,51 @@ static const char* err_text(unsigned code) {
 }
 
 template <int BITS>
-static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result* res, bool fetch) {
+static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result* res) {
     cudaStream_t s = ctx->stream;
     const uint64_t G = ctx->G, n_aln = ctx->n_aln;
     const uint32_t n_tiles = (uint32_t)((G + PP_TILE - 1) >> PP_TILE_SHIFT);
     const uint32_t n_chunks = (uint32_t)((G + VT_CHUNK - 1) / VT_CHUNK);
+    const uint32_t n_cchunks = (uint32_t)((n_aln + CL_CHUNK - 1) / CL_CHUNK);
     const uint32_t nib_words = (uint32_t)((G + 15) / 16);
-    ctx->launches = 0;
-    ctx->have_result = false;
-
-    uint32_t fix_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, n_aln / 4 + 1024));
-    uint32_t oth_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, n_aln / 2 + 1024));
-    uint64_t out_cap = G + 4096;
-
     const size_t padG = (size_t)n_chunks * VT_CHUNK + 16;      // k_vote reads whole chunks with vector loads
+    const size_t padA = (size_t)n_cchunks * CL_CHUNK + 16;     // k_collect likewise
+    int tile_bits = 1;
+    while ((1ull << tile_bits) < (uint64_t)n_tiles + 2) tile_bits++;
+
     CK(ctx->b[B_NIB].ensure(((size_t)nib_words + 8) * 8));
     CK(ctx->b[B_DEPTHFIX].ensure(((size_t)n_tiles * PP_TILE + 1) * 8));
+    CK(ctx->b[B_RECGN].ensure(padA * 8)); CK(ctx->b[B_RECK].ensure(padA * 4));
     CK(ctx->b[B_OUTOFF].ensure(((size_t)ctx->n_contigs + 1) * 8));
     CK(ctx->b[B_AGG1].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC1].ensure((size_t)n_chunks * 8));
+    CK(ctx->b[B_AGGC].ensure((size_t)n_cchunks * 8 + 8)); CK(ctx->b[B_INCC].ensure((size_t)n_cchunks * 8 + 8));
     CK(ctx->b[B_RES].ensure(padG * 2)); CK(ctx->b[B_RECAT].ensure((G + 1) * 4)); CK(ctx->b[B_CHUNKDELTA].ensure((size_t)n_chunks * 8));
-    CK(ctx->b[B_OFIRST].ensure((G + 1) * 4));
-    // everything that must be zero at the start of a call lives in one pool: one memset
-    size_t zoff = 0;
-    auto carve = [&](size_t bytes) { size_t o = zoff; zoff += (bytes + 255) & ~size_t(255); return o; };
-    const size_t o_diff = carve(padG * 8), o_ex = carve(padG * 8), o_del = carve(padG * 4), o_k = carve((ctx->n_reads + 1) * 4),
-                 o_tile = carve(((size_t)n_tiles / 32 + 2) * 4), o_st1 = carve((size_t)n_chunks * 4),
-                 o_chg = carve((size_t)ctx->n_contigs * 8), o_zero = carve((size_t)ctx->n_contigs * 8), o_status = carve(sizeof(DevStatus));
-    CK(ctx->b[B_ZEROPOOL].ensure(zoff));
-    uint8_t* zp = ctx->b[B_ZEROPOOL].as<uint8_t>();
+    CK(ctx->b[B_PARAMS].ensure(sizeof(DevParams)));
 
-    for (int attempt = 0; attempt < 6; ++attempt) {
-        CK(ctx->b[B_FIXKEY].ensure((size_t)fix_cap * 8)); CK(ctx->b[B_FIXVAL].ensure((size_t)fix_cap * 8));
-        CK(ctx->b[B_OTHKEY].ensure((size_t)oth_cap * 8)); CK(ctx->b[B_OTHVAL].ensure((size_t)oth_cap * 8));
-        CK(ctx->b[B_OTHSIG].ensure((size_t)oth_cap * 8));
+    ctx->h_params->fv = prm->fraction_valid; ctx->h_params->fi = prm->fraction_invalid;
+    ctx->h_params->min_depth = prm->min_depth; ctx->h_params->max_errors = prm->max_errors;
+    ctx->h_params->careful = prm->careful ? 1 : 0; ctx->h_params->pad = 0;
+
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        const uint32_t fix_cap = ctx->fix_cap, node_cap = ctx->node_cap;
+        const uint64_t out_cap = ctx->out_cap;
+        // everything that must be zero at the start of a call lives in one pool: one memset
+        size_t zoff = 0;
+        auto carve = [&](size_t bytes) { size_t o = zoff; zoff += (bytes + 255) & ~size_t(255); return o; };
+        const size_t o_diff = carve(padG * 8), o_ex = carve(padG * 8), o_del = carve(padG * 4), o_head = carve((G + 1) * 4),
+                     o_tile = carve(((size_t)n_tiles / 32 + 2) * 4), o_st1 = carve((size_t)n_chunks * 4), o_stc = carve((size_t)n_cchunks * 4 + 4),
+                     o_chg = carve((size_t)ctx->n_contigs * 8), o_zero = carve((size_t)ctx->n_contigs * 8), o_status = carve(sizeof(DevStatus)),
+                     o_fkey = carve((size_t)fix_cap * 4), o_fval = carve((size_t)fix_cap * 4),
+                     o_k = carve(ctx->global_k ? (ctx->n_reads + 1) * 4 : 4);
+        CK(ctx->b[B_ZEROPOOL].ensure(zoff));
+        uint8_t* zp = ctx->b[B_ZEROPOOL].as<uint8_t>();
+        CK(ctx->b[B_NODES].ensure((size_t)node_cap * sizeof(OthNode)));
+        CK(ctx->b[B_FIXKEY2].ensure((size_t)fix_cap * 4)); CK(ctx->b[B_FIXVAL2].ensure((size_t)fix_cap * 4));
         CK(ctx->b[B_OUT].ensure(out_cap + 64));
+        size_t cub_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                           (uint32_t*)nullptr, (int)fix_cap, 0, tile_bits, s));
+        CK(ctx->b[B_CUBTMP].ensure(cub_bytes));
 
         DevData d;
         d.n_aln = n_aln;
@@ -1212,25 +1281,22 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         d.cigar_ops = ctx->b[B_CIGOPS].as<uint32_t>(); d.seq_len = ctx->b[B_SEQLEN].as<uint16_t>();
         d.n_cigar = ctx->b[B_NCIG].as<uint16_t>(); d.flags = ctx->b[B_FLAGS].as<uint8_t>();
         d.seq_pool = ctx->b[B_SEQPOOL].as<uint8_t>(); d.draft = ctx->b[B_DRAFT].as<uint8_t>();
-        d.contig_off = ctx->b[B_CTGOFF].as<unsigned long long>(); d.n_contigs = ctx->n_contigs; d.G = (uint32_t)G;
+        d.contig_off = ctx->b[B_CTGOFF].as<unsigned long long>(); d.n_contigs = ctx->n_contigs; d.G = (uint32_t)G; d.n_tiles = n_tiles;
         d.k = (uint32_t*)(zp + o_k);
-        d.max_errors = prm->max_errors; d.careful = prm->careful ? 1 : 0;
         d.draft_nib = ctx->b[B_NIB].as<unsigned long long>(); d.diff = (unsigned long long*)(zp + o_diff);
         d.ex = (unsigned long long*)(zp + o_ex); d.delother = (uint32_t*)(zp + o_del);
-        d.tileflag = (uint32_t*)(zp + o_tile); d.depth_fix = ctx->b[B_DEPTHFIX].as<double>();
-        d.fix_key = ctx->b[B_FIXKEY].as<unsigned long long>(); d.fix_val = ctx->b[B_FIXVAL].as<unsigned long long>();
-        d.oth_key = ctx->b[B_OTHKEY].as<unsigned long long>(); d.oth_val = ctx->b[B_OTHVAL].as<unsigned long long>();
-        d.oth_sig = ctx->b[B_OTHSIG].as<unsigned long long>();
-        d.fix_cap = fix_cap; d.oth_cap = oth_cap;
-        d.aln_bits = 1;
-        while ((1ull << d.aln_bits) < n_aln) d.aln_bits++;
-        int tile_bits = 1;
-        while ((1ull << tile_bits) < n_tiles) tile_bits++;
-        const int fix_end_bit = std::min(64, (int)d.aln_bits + tile_bits);
+        d.oth_head = (uint32_t*)(zp + o_head); d.nodes = ctx->b[B_NODES].as<OthNode>(); d.node_cap = node_cap;
+        d.tileflag = (uint32_t*)(zp + o_tile);
+        d.rec_gn = ctx->b[B_RECGN].as<unsigned long long>(); d.rec_k = ctx->b[B_RECK].as<uint32_t>();
+        d.depth_fix = ctx->b[B_DEPTHFIX].as<double>();
+        d.fix_key = (uint32_t*)(zp + o_fkey); d.fix_val = (uint32_t*)(zp + o_fval); d.fix_cap = fix_cap;
+        d.prm = ctx->b[B_PARAMS].as<DevParams>();
         d.st = (DevStatus*)(zp + o_status);
+        ctx->launches = 0;
 
-        // ---- stage 0: reset
+        // ---- stage 0: reset + derived 4-bit draft plane
         CK(cudaEventRecord(ctx->ev[0], s));
+        CK(cudaMemcpyAsync(ctx->b[B_PARAMS].p, ctx->h_params, sizeof(DevParams), cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(zp, 0, zoff, s));
         CK(cudaMemsetAsync(&d.st->err, 0xFF, 8, s));
         if (BITS == 4) {
@@ -1238,128 +1304,93 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
             k_draft_nib<<<std::min<uint32_t>((nib_words + 255) / 256, ctx->sm_count * 8), 256, 0, s>>>(d.draft, (uint32_t)G, d.draft_nib, nib_words);
             ctx->launches++;
         }
-        // ---- stage 1: classify
+        // ---- stage 1: (fallback only) global k of multi-record groups
         CK(cudaEventRecord(ctx->ev[1], s));
-        if (n_aln) {
-            uint32_t grid = (uint32_t)std::min<uint64_t>((n_aln + 255) / 256, (uint64_t)ctx->sm_count * 8);
-            k_classify_multi<<<grid, 256, 0, s>>>(d);
+        if (n_aln && ctx->global_k) {
+            k_classify_multi<<<(uint32_t)std::min<uint64_t>((n_aln + 255) / 256, (uint64_t)ctx->sm_count * 8), 256, 0, s>>>(d);
             ctx->launches++;
         }
         // ---- stage 2: scatter
         CK(cudaEventRecord(ctx->ev[2], s));
         if (n_aln) {
-            uint32_t grid = (uint32_t)std::min<uint64_t>((n_aln + SC_THREADS - 1) / SC_THREADS, (uint64_t)ctx->sm_count * 8);
-            k_scatter<BITS><<<grid, SC_THREADS, 0, s>>>(d);
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((n_aln + SC_THREADS - 1) / SC_THREADS, (uint64_t)ctx->sm_count * 8);
+            if (ctx->global_k) k_scatter<BITS, true><<<grid, SC_THREADS, 0, s>>>(d);
+            else k_scatter<BITS, false><<<grid, SC_THREADS, 0, s>>>(d);
             ctx->launches++;
         }
+        // ---- stage 3: ordered depth where k != 1 coverage exists: collect -> stable sort by tile -> ordered walk
         CK(cudaEventRecord(ctx->ev[3], s));
-        CK(cudaMemcpyAsync(ctx->h_status, d.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        CK(cudaGetLastError());
-        DevStatus hs = *ctx->h_status;
-        if (hs.err != ~0ull) {
-            res->error_aln = (int64_t)(hs.err >> 8);
-            return ctx->fail(PP_ERR_INPUT, std::string(err_text((unsigned)(hs.err & 0xFF))) + " (alignment " + std::to_string(hs.err >> 8) + ")");
+        if (n_aln) {
+            CollectParams cp;
+            cp.n_chunks = n_cchunks; cp.st = (uint32_t*)(zp + o_stc);
+            cp.agg = ctx->b[B_AGGC].as<unsigned long long>(); cp.inc = ctx->b[B_INCC].as<unsigned long long>();
+            k_collect<<<n_cchunks, CL_THREADS, 0, s>>>(d, cp);
+            CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, cub_bytes, d.fix_key, ctx->b[B_FIXKEY2].as<uint32_t>(), d.fix_val,
+                                               ctx->b[B_FIXVAL2].as<uint32_t>(), (int)fix_cap, 0, tile_bits, s));
+            k_depth_fixup<<<std::min<uint32_t>(n_tiles, ctx->sm_count * 16), PP_TILE, 0, s>>>(d, ctx->b[B_FIXKEY2].as<uint32_t>(), ctx->b[B_FIXVAL2].as<uint32_t>());
+            ctx->launches += 2;
         }
-        if (hs.flags & (FL_FIX_OVF | FL_OTHER_OVF)) {
-            if (hs.flags & FL_FIX_OVF) fix_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, (uint64_t)hs.fix_count + hs.fix_count / 8 + 1024);
-            if (hs.flags & FL_OTHER_OVF) oth_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, (uint64_t)hs.other_count + hs.other_count / 8 + 1024);
-            continue;      // rerun with larger side buffers
-        }
-        out_cap = G + hs.other_len + 64;
-        CK(ctx->b[B_OUT].ensure(out_cap + 64));
-
-        // ---- stage 3: depth fix-up (ordered f64 sum where k != 1 coverage may exist)
-        const unsigned long long* fkeys = d.fix_key;
-        const unsigned long long* fvals = d.fix_val;
-        if (hs.fix_count) {
-            CK(ctx->b[B_FIXKEY2].ensure((size_t)hs.fix_count * 8)); CK(ctx->b[B_FIXVAL2].ensure((size_t)hs.fix_count * 8));
-            size_t tmp = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d.fix_key, ctx->b[B_FIXKEY2].as<unsigned long long>(), d.fix_val,
-                                               ctx->b[B_FIXVAL2].as<unsigned long long>(), (int)hs.fix_count, 0, fix_end_bit, s));
-            CK(ctx->b[B_CUBTMP].ensure(tmp));
-            CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, tmp, d.fix_key, ctx->b[B_FIXKEY2].as<unsigned long long>(), d.fix_val,
-                                               ctx->b[B_FIXVAL2].as<unsigned long long>(), (int)hs.fix_count, 0, fix_end_bit, s));
-            fkeys = ctx->b[B_FIXKEY2].as<unsigned long long>();
-            fvals = ctx->b[B_FIXVAL2].as<unsigned long long>();
-            k_depth_fixup<<<n_tiles, PP_TILE, 0, s>>>(d, fkeys, fvals, hs.fix_count);
-            ctx->launches++;
-        }
-        // ---- stage 4: sort other-allele records by (position, signature hash)
+        // ---- stage 5: vote; stage 4: compaction
         CK(cudaEventRecord(ctx->ev[4], s));
-        const unsigned long long* okeys = d.oth_key;
-        const uint32_t* oidx = nullptr;
-        if (hs.other_count) {
-            CK(ctx->b[B_OTHKEY2].ensure((size_t)hs.other_count * 8));
-            CK(ctx->b[B_OTHIDX].ensure((size_t)hs.other_count * 4)); CK(ctx->b[B_OTHIDX2].ensure((size_t)hs.other_count * 4));
-            k_iota<<<std::min<uint32_t>((hs.other_count + 255) / 256, ctx->sm_count * 4), 256, 0, s>>>(ctx->b[B_OTHIDX].as<uint32_t>(), hs.other_count);
-            ctx->launches++;
-            int pos_bits = 1;
-            while ((1ull << pos_bits) < G) pos_bits++;
-            size_t tmp = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, d.oth_key, ctx->b[B_OTHKEY2].as<unsigned long long>(), ctx->b[B_OTHIDX].as<uint32_t>(),
-                                               ctx->b[B_OTHIDX2].as<uint32_t>(), (int)hs.other_count, 0, 32 + pos_bits, s));
-            CK(ctx->b[B_CUBTMP].ensure(tmp));
-            CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, tmp, d.oth_key, ctx->b[B_OTHKEY2].as<unsigned long long>(), ctx->b[B_OTHIDX].as<uint32_t>(),
-                                               ctx->b[B_OTHIDX2].as<uint32_t>(), (int)hs.other_count, 0, 32 + pos_bits, s));
-            okeys = ctx->b[B_OTHKEY2].as<unsigned long long>();
-            oidx = ctx->b[B_OTHIDX2].as<uint32_t>();
-            k_oth_first<<<std::min<uint32_t>((hs.other_count + 255) / 256, ctx->sm_count * 4), 256, 0, s>>>(okeys, hs.other_count, ctx->b[B_OFIRST].as<uint32_t>());
-            ctx->launches++;
-        }
-        // ---- stage 5: vote + compaction
-        CK(cudaEventRecord(ctx->ev[5], s));
         VoteParams vp;
-        vp.fv = prm->fraction_valid; vp.fi = prm->fraction_invalid; vp.min_depth = prm->min_depth; vp.n_chunks = n_chunks;
+        vp.n_chunks = n_chunks;
         vp.out = ctx->b[B_OUT].as<uint8_t>(); vp.out_cap = out_cap;
         vp.out_off = ctx->b[B_OUTOFF].as<unsigned long long>();
         vp.changed = (unsigned long long*)(zp + o_chg); vp.zero_depth = (unsigned long long*)(zp + o_zero);
         vp.st1 = (uint32_t*)(zp + o_st1); vp.agg1 = ctx->b[B_AGG1].as<unsigned long long>(); vp.inc1 = ctx->b[B_INC1].as<unsigned long long>();
         vp.res = ctx->b[B_RES].as<uint16_t>(); vp.rec_at = ctx->b[B_RECAT].as<uint32_t>();
-        vp.chunk_delta = ctx->b[B_CHUNKDELTA].as<long long>(); vp.ofirst = ctx->b[B_OFIRST].as<uint32_t>();
-        vp.okey = okeys; vp.oidx = oidx; vp.osig = d.oth_sig; vp.oval = d.oth_val; vp.n_oth = hs.other_count;
+        vp.chunk_delta = ctx->b[B_CHUNKDELTA].as<long long>();
         k_vote<BITS><<<n_chunks, VT_THREADS, 0, s>>>(d, vp);
+        CK(cudaEventRecord(ctx->ev[5], s));
         k_compact<BITS><<<n_chunks, VT_THREADS, 0, s>>>(d, vp);
         ctx->launches += 2;
         CK(cudaEventRecord(ctx->ev[6], s));
         CK(cudaMemcpyAsync(ctx->h_status, d.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
-        hs = *ctx->h_status;
+        const DevStatus hs = *ctx->h_status;
+        if (hs.err != ~0ull) {
+            res->error_aln = (int64_t)(hs.err >> 8);
+            return ctx->fail(PP_ERR_INPUT, std::string(err_text((unsigned)(hs.err & 0xFF))) + " (alignment " + std::to_string(hs.err >> 8) + ")");
+        }
+        // a side buffer was too small or a read group too large for the in-kernel scan: grow / switch mode and repeat
+        bool again = false;
+        if (hs.flags & FL_BIGGROUP) { if (ctx->global_k) return ctx->fail(PP_ERR_CUDA, "internal error: FL_BIGGROUP in global-k mode"); ctx->global_k = true; again = true; }
+        if (hs.flags & FL_NODE_OVF) { ctx->node_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, (uint64_t)hs.node_count + hs.node_count / 4 + 1024); again = true; }
+        if (hs.flags & FL_FIX_OVF) {
+            if (hs.fix_count >= 0x7FFFFFFFull) return ctx->fail(PP_ERR_NOMEM, "too many multi-mapped (alignment, tile) pairs for one call");
+            ctx->fix_cap = (uint32_t)(hs.fix_count + hs.fix_count / 8 + 1024); again = true;
+        }
+        if (!again && (hs.flags & FL_OUT_OVF)) { ctx->out_cap = hs.out_len + 64; again = true; }
+        if (again) continue;
         if (hs.flags & FL_COUNTER_OVF)
             return ctx->fail(PP_ERR_INPUT, "a position is covered by 65536 or more alignments: not supported by this build's 16-bit allele counters");
-        if (hs.flags & FL_OUT_OVF) return ctx->fail(PP_ERR_CUDA, "internal error: output buffer overflow");
 
         res->out_len = hs.out_len;
         res->n_aln_used = hs.n_used;
         res->error_aln = -1;
-        ctx->last_out_len = hs.out_len;
-        ctx->have_result = true;
         memset(&res->timing, 0, sizeof res->timing);
         float ms;
-        for (int i = 0; i < 6; ++i) {
-            if (i == 3 || i == 4) continue;
-            CK(cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
-            res->timing.stage_ms[i] = ms;
-        }
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); res->timing.stage_ms[0] = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); res->timing.stage_ms[1] = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); res->timing.stage_ms[2] = ms;
         CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4])); res->timing.stage_ms[3] = ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); res->timing.stage_ms[4] = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); res->timing.stage_ms[5] = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6])); res->timing.stage_ms[4] = ms;
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6])); res->timing.total_ms = ms;
         res->timing.launches = ctx->launches;
 
-        if (fetch) {
-            if (res->out_bases) {
-                if (res->out_cap < hs.out_len) return ctx->fail(PP_ERR_ARG, "out_cap too small: need " + std::to_string(hs.out_len) + " bytes");
-                CK(cudaEventRecord(ctx->ev[7], s));
-                CK(cudaMemcpyAsync(res->out_bases, vp.out, hs.out_len, cudaMemcpyDeviceToHost, s));
-                if (res->out_off) CK(cudaMemcpyAsync(res->out_off, vp.out_off, ((size_t)ctx->n_contigs + 1) * 8, cudaMemcpyDeviceToHost, s));
-                if (res->changed) CK(cudaMemcpyAsync(res->changed, vp.changed, (size_t)ctx->n_contigs * 8, cudaMemcpyDeviceToHost, s));
-                if (res->zero_depth) CK(cudaMemcpyAsync(res->zero_depth, vp.zero_depth, (size_t)ctx->n_contigs * 8, cudaMemcpyDeviceToHost, s));
-                CK(cudaEventRecord(ctx->ev[8], s));
-                CK(cudaStreamSynchronize(s));
-                CK(cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]));
-                res->timing.stage_ms[7] = ms;
-            }
+        if (res->out_bases) {
+            if (res->out_cap < hs.out_len) return ctx->fail(PP_ERR_ARG, "out_cap too small: need " + std::to_string(hs.out_len) + " bytes");
+            CK(cudaEventRecord(ctx->ev[7], s));
+            CK(cudaMemcpyAsync(res->out_bases, vp.out, hs.out_len, cudaMemcpyDeviceToHost, s));
+            if (res->out_off) CK(cudaMemcpyAsync(res->out_off, vp.out_off, ((size_t)ctx->n_contigs + 1) * 8, cudaMemcpyDeviceToHost, s));
+            if (res->changed) CK(cudaMemcpyAsync(res->changed, vp.changed, (size_t)ctx->n_contigs * 8, cudaMemcpyDeviceToHost, s));
+            if (res->zero_depth) CK(cudaMemcpyAsync(res->zero_depth, vp.zero_depth, (size_t)ctx->n_contigs * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(ctx->ev[8], s));
+            CK(cudaStreamSynchronize(s));
+            CK(cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]));
+            res->timing.stage_ms[7] = ms;
         }
         return PP_OK;
     }
@@ -1383,7 +1414,7 @@ extern "C" int pp_polish_resident(pp_ctx* ctx, const pp_polish_params* params, p
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     result->error_aln = -1;
-    return ctx->seq_bits == 4 ? run_polish<4>(ctx, params, result, true) : run_polish<8>(ctx, params, result, true);
+    return ctx->seq_bits == 4 ? run_polish<4>(ctx, params, result) : run_polish<8>(ctx, params, result);
 }
 
 extern "C" int pp_polish(pp_ctx* ctx, const pp_contigs* contigs, const pp_alignments* alns,
@@ -1396,12 +1427,12 @@ extern "C" int pp_polish(pp_ctx* ctx, const pp_contigs* contigs, const pp_alignm
     CK(cudaEventRecord(ctx->ev[9], ctx->stream));
     rc = pp_dataset_upload(ctx, contigs, alns);
     if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev[8], ctx->stream));
-    CK(cudaEventSynchronize(ctx->ev[8]));
+    CK(cudaEventRecord(ctx->ev[10], ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev[10]));
     float h2d = 0;
-    CK(cudaEventElapsedTime(&h2d, ctx->ev[9], ctx->ev[8]));
+    CK(cudaEventElapsedTime(&h2d, ctx->ev[9], ctx->ev[10]));
     result->error_aln = -1;
-    rc = ctx->seq_bits == 4 ? run_polish<4>(ctx, params, result, true) : run_polish<8>(ctx, params, result, true);
+    rc = ctx->seq_bits == 4 ? run_polish<4>(ctx, params, result) : run_polish<8>(ctx, params, result);
     if (rc == PP_OK) result->timing.stage_ms[6] = h2d;
     return rc;
 }
