@@ -710,34 +710,46 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
     return lo;
 }
 
-__global__ void __launch_bounds__(PP_TILE) k_depth_fixup(DevData d, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals) {
-    __shared__ uint32_t s_lo, s_hi;
-    __shared__ uint32_t s_start[PP_TILE], s_end[PP_TILE];
-    __shared__ double s_inv[PP_TILE];
-    for (uint32_t tile = blockIdx.x; tile < d.n_tiles; tile += gridDim.x) {
+#define FX_WARPS 4
+__global__ void __launch_bounds__(FX_WARPS * 32) k_depth_fixup(DevData d, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals) {
+    // One WARP per flagged tile, four consecutive positions per lane (four independent dependent-add chains); the
+    // tile's list is staged 32 entries at a time in the warp's own shared-memory slice.
+    __shared__ uint2 s_rng[FX_WARPS][32];        // (start, length) of each staged entry
+    __shared__ double s_inv[FX_WARPS][32];       // 1.0 / k
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = blockIdx.x * FX_WARPS + wib, n_warps = gridDim.x * FX_WARPS;
+    for (uint32_t tile = warp; tile < d.n_tiles; tile += n_warps) {
         if (!((d.tileflag[tile >> 5] >> (tile & 31)) & 1u)) continue;
-        if (threadIdx.x == 0) s_lo = lower_bound_u32(keys, d.fix_cap, tile + 1);
-        if (threadIdx.x == 1) s_hi = lower_bound_u32(keys, d.fix_cap, tile + 2);
-        __syncthreads();
-        const uint32_t lo = s_lo, hi = s_hi;
-        const uint32_t p = tile * PP_TILE + threadIdx.x;
-        double depth = 0.0;
-        for (uint32_t base = lo; base < hi; base += PP_TILE) {
-            const uint32_t i = base + threadIdx.x;
+        uint32_t lo = 0, hi = 0;
+        if (lane == 0) lo = lower_bound_u32(keys, d.fix_cap, tile + 1);
+        if (lane == 1) hi = lower_bound_u32(keys, d.fix_cap, tile + 2);
+        lo = __shfl_sync(0xffffffffu, lo, 0);
+        hi = __shfl_sync(0xffffffffu, hi, 1);
+        const uint32_t p = tile * PP_TILE + lane * 4;
+        double dep0 = 0.0, dep1 = 0.0, dep2 = 0.0, dep3 = 0.0;
+        for (uint32_t base = lo; base < hi; base += 32) {
+            const uint32_t i = base + lane;
             if (i < hi) {
                 const uint32_t aln = vals[i];
                 const unsigned long long v = d.rec_gn[aln];
-                s_start[threadIdx.x] = (uint32_t)(v >> 32);
-                s_end[threadIdx.x] = (uint32_t)(v >> 32) + (uint32_t)v;
-                s_inv[threadIdx.x] = __ddiv_rn(1.0, (double)d.rec_k[aln]);      // 1.0 / good_alignments.len() as f64
+                s_rng[wib][lane] = make_uint2((uint32_t)(v >> 32), (uint32_t)v);
+                s_inv[wib][lane] = __ddiv_rn(1.0, (double)d.rec_k[aln]);      // 1.0 / good_alignments.len() as f64
             }
-            __syncthreads();
-            const uint32_t cnt = min((uint32_t)PP_TILE, hi - base);
-            for (uint32_t j = 0; j < cnt; ++j)
-                if (p >= s_start[j] && p < s_end[j]) depth = __dadd_rn(depth, s_inv[j]);
-            __syncthreads();
+            __syncwarp();
+            const uint32_t cnt = min(32u, hi - base);
+#pragma unroll 4
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const uint2 r = s_rng[wib][j];
+                const double inv = s_inv[wib][j];
+                const uint32_t off = p - r.x;                       // position p + q is covered iff (off + q) < length (unsigned)
+                if (off < r.y) dep0 = __dadd_rn(dep0, inv);
+                if (off + 1u < r.y) dep1 = __dadd_rn(dep1, inv);
+                if (off + 2u < r.y) dep2 = __dadd_rn(dep2, inv);
+                if (off + 3u < r.y) dep3 = __dadd_rn(dep3, inv);
+            }
+            __syncwarp();
         }
-        d.depth_fix[p] = depth;
+        *reinterpret_cast<double4*>(d.depth_fix + p) = make_double4(dep0, dep1, dep2, dep3);
     }
 }
 
@@ -1087,6 +1099,7 @@ struct pp_ctx {
     uint64_t n_aln = 0, n_reads = 0, n_ops = 0, seq_bytes = 0, G = 0;
     uint32_t n_contigs = 0, seq_bits = 4;
     int sm_count = 148;
+    size_t l2_persist_max = 0, l2_window_max = 0;
     uint32_t launches = 0;
     // sizes that adapt when a call overflows them (kept across calls on the same dataset)
     uint32_t node_cap = 0, fix_cap = 0;
@@ -1130,6 +1143,9 @@ extern "C" int pp_create(int device, pp_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) { delete ctx; return PP_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (ctx->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     for (auto& ev : ctx->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     if (cudaHostAlloc((void**)&ctx->h_status, sizeof(DevStatus), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
@@ -1294,6 +1310,20 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         d.st = (DevStatus*)(zp + o_status);
         ctx->launches = 0;
 
+        // The per-position counters take ~3 atomics per alignment at random positions: keep as much of them as the
+        // hardware allows resident in L2 (persisting access-policy window) while the alignment arrays stream through.
+        if (ctx->l2_persist_max && ctx->l2_window_max) {
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            const size_t want = o_del - o_diff;                                   // diff + ex
+            const size_t bytes = std::min(want, ctx->l2_window_max);
+            av.accessPolicyWindow.base_ptr = zp + o_diff;
+            av.accessPolicyWindow.num_bytes = bytes;
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ctx->l2_persist_max / (double)bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
+        }
         // ---- stage 0: reset + derived 4-bit draft plane
         CK(cudaEventRecord(ctx->ev[0], s));
         CK(cudaMemcpyAsync(ctx->b[B_PARAMS].p, ctx->h_params, sizeof(DevParams), cudaMemcpyHostToDevice, s));
@@ -1313,7 +1343,11 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         // ---- stage 2: scatter
         CK(cudaEventRecord(ctx->ev[2], s));
         if (n_aln) {
-            const uint32_t grid = (uint32_t)std::min<uint64_t>((n_aln + SC_THREADS - 1) / SC_THREADS, (uint64_t)ctx->sm_count * 8);
+            // persistent kernel: exactly as many CTAs as fit on the chip at once (no partial second wave)
+            int occ = 1;
+            if (ctx->global_k) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scatter<BITS, true>, SC_THREADS, 0));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scatter<BITS, false>, SC_THREADS, 0));
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((n_aln + SC_THREADS - 1) / SC_THREADS, (uint64_t)ctx->sm_count * std::max(occ, 1));
             if (ctx->global_k) k_scatter<BITS, true><<<grid, SC_THREADS, 0, s>>>(d);
             else k_scatter<BITS, false><<<grid, SC_THREADS, 0, s>>>(d);
             ctx->launches++;
@@ -1327,7 +1361,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
             k_collect<<<n_cchunks, CL_THREADS, 0, s>>>(d, cp);
             CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, cub_bytes, d.fix_key, ctx->b[B_FIXKEY2].as<uint32_t>(), d.fix_val,
                                                ctx->b[B_FIXVAL2].as<uint32_t>(), (int)fix_cap, 0, tile_bits, s));
-            k_depth_fixup<<<std::min<uint32_t>(n_tiles, ctx->sm_count * 16), PP_TILE, 0, s>>>(d, ctx->b[B_FIXKEY2].as<uint32_t>(), ctx->b[B_FIXVAL2].as<uint32_t>());
+            k_depth_fixup<<<std::min<uint32_t>((n_tiles + FX_WARPS - 1) / FX_WARPS, ctx->sm_count * 16), FX_WARPS * 32, 0, s>>>(d, ctx->b[B_FIXKEY2].as<uint32_t>(), ctx->b[B_FIXVAL2].as<uint32_t>());
             ctx->launches += 2;
         }
         // ---- stage 5: vote; stage 4: compaction
