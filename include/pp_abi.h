@@ -51,6 +51,8 @@ void pp_host_free(void* p);
 #define PP_FLAG_SEQSTAR 0x04 /* SEQ was "*": the sequence is the read group's source sequence (alignment.rs:290-295,311-322) */
 #define PP_FLAG_RC      0x08 /* use the reverse complement of the pooled sequence (alignment.rs:161-167) */
 #define PP_FLAG_NOSEQ   0x10 /* no record of the group carried a sequence (only legal when the group is skipped by --careful) */
+#define PP_FLAG_GHOST   0x20 /* record of a read that lives on another GPU's contigs: counts for goodness / k / --careful,
+                                adds nothing to the pileup (contig sharding, pp_shards_build) */
 
 /* CIGAR op codes in cigar_ops (BAM numbering): len << 4 | op.  Zero-length ops are dropped by the packer
  * (they contribute nothing to the expanded CIGAR of alignment.rs:325-346). */
@@ -206,12 +208,24 @@ int pp_pack_cigar_string(const pp_pack* p, uint64_t aln, char* out, size_t cap);
 /* per file: aligned records and read groups (the stderr line of polish.rs:117-119) */
 int pp_pack_file_stats(const pp_pack* p, uint32_t file, uint64_t* alignments, uint64_t* reads);
 
+/* Contig sharding across GPUs (one pp_ctx per GPU, no collective): whole contigs per shard, each with its alignments
+ * in SAM order; reads that also map to another shard's contigs keep their k through PP_FLAG_GHOST records. */
+typedef struct pp_shards pp_shards;
+pp_shards* pp_shards_build(const pp_contigs* contigs, const pp_alignments* alns, uint32_t n_shards);
+int pp_shards_get(const pp_shards* s, uint32_t i, pp_contigs* contigs, pp_alignments* alns,
+                  const uint32_t** contig_map /* original index of each shard contig */, uint64_t* n_home);
+void pp_shards_free(pp_shards* s);
+
 /* Whole commands (the functions the CLI calls; same behaviour, error text and exit status as the
  * reference's polish::polish (polish.rs:26-38) and filter::filter (filter.rs:26-37)).
  * out_fasta receives exactly what the reference prints to stdout; free with pp_free. */
 int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* const* sams, int n_sams,
                     const pp_polish_params* params, const char* debug_path, char** out_fasta,
                     uint64_t* out_len, int verbose /* 1: reference-style log on stderr */);
+/* the same command over several GPUs of one box: contigs shard across ctxs[0..n_ctx) (one host thread per GPU) */
+int pp_polish_files_multi(pp_ctx* const* ctxs, int n_ctx, const char* assembly, const char* const* sams, int n_sams,
+                          const pp_polish_params* params, const char* debug_path, char** out_fasta,
+                          uint64_t* out_len, int verbose);
 int pp_filter_files(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2,
                     const char* orientation, double low, double high, int verbose);
 void pp_free(void* p);

@@ -443,3 +443,80 @@ class Synth:
             self.close()
         except Exception:
             pass
+
+
+# ---- contig sharding across GPUs (csrc/shard.cpp) ---------------------------------------------------------------
+class Shards:
+    """pp_shards_build: whole contigs per shard, alignments in SAM order, foreign records of a read as ghosts."""
+
+    def __init__(self, contigs, alns, n_shards):
+        L = lib()
+        L.pp_shards_build.restype = C.c_void_p
+        L.pp_shards_build.argtypes = [C.POINTER(Contigs), C.POINTER(Alignments), C.c_uint32]
+        L.pp_shards_free.argtypes = [C.c_void_p]
+        L.pp_shards_get.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(Contigs), C.POINTER(Alignments),
+                                    C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
+        self.n = n_shards
+        self.h = L.pp_shards_build(C.byref(contigs), C.byref(alns), n_shards)
+        if not self.h:
+            raise PolypolishError(PP_ERR_ARG, "pp_shards_build failed")
+
+    def get(self, i):
+        """(contigs view, alignments view, original contig indices, number of home alignments)"""
+        c, a = Contigs(), Alignments()
+        cmap = C.POINTER(C.c_uint32)()
+        nh = C.c_uint64()
+        rc = lib().pp_shards_get(self.h, i, C.byref(c), C.byref(a), C.byref(cmap), C.byref(nh))
+        if rc != PP_OK:
+            raise PolypolishError(rc, "pp_shards_get failed")
+        return c, a, [cmap[k] for k in range(c.n_contigs)], nh.value
+
+    def close(self):
+        if self.h:
+            lib().pp_shards_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def view_arrays(v):
+    """numpy views of a pp_alignments view (valid while its owner lives)."""
+    n = v.n_aln
+
+    def arr(ptr, ct, cnt):
+        if cnt == 0 or not ptr:
+            return np.zeros(0, dtype=ct)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(cnt,))
+    return dict(contig=arr(v.contig, C.c_uint32, n), ref_start=arr(v.ref_start, C.c_uint32, n),
+                read_id=arr(v.read_id, C.c_uint32, n), seq_off=arr(v.seq_off, C.c_uint32, n),
+                seq_len=arr(v.seq_len, C.c_uint16, n), cigar_off=arr(v.cigar_off, C.c_uint32, n),
+                n_cigar=arr(v.n_cigar, C.c_uint16, n), nm=arr(v.nm, C.c_uint32, n), flags=arr(v.flags, C.c_uint8, n),
+                cigar_ops=arr(v.cigar_ops, C.c_uint32, v.n_cigar_ops), seq_pool=arr(v.seq_pool, C.c_uint8, v.seq_pool_bytes),
+                seq_bits=v.seq_bits, n_reads=v.n_reads)
+
+
+def polish_files_multi(assembly, sams, devices, verbose=False, **opts):
+    """pp_polish_files_multi: contigs shard over one context per entry of `devices` (entries may repeat)."""
+    L = lib()
+    L.pp_polish_files_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_int,
+                                        C.POINTER(PolishParams), C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]
+    ctxs = [Context(d) for d in devices]
+    try:
+        arr_ctx = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        prm = _params(**opts)
+        arr = (C.c_char_p * max(1, len(sams)))(*[str(s).encode() for s in sams])
+        out, n = C.c_void_p(), C.c_uint64()
+        rc = L.pp_polish_files_multi(arr_ctx, len(ctxs), str(assembly).encode(), arr, len(sams), C.byref(prm), None,
+                                     C.byref(out), C.byref(n), int(verbose))
+        if rc != PP_OK:
+            raise ctxs[0]._err(rc)
+        data = C.string_at(out, n.value)
+        L.pp_free(out)
+        return data
+    finally:
+        for c in ctxs:
+            c.close()

@@ -5,7 +5,7 @@
 //   polypolish polish [--debug F] [-i|--fraction_invalid 0.2] [-v|--fraction_valid 0.5] [-m|--max_errors 10]
 //                     [-d|--min_depth 5] [--careful] <ASSEMBLY> [SAM]...
 // Polished FASTA on stdout, log on stderr, "Error: <msg>" + exit 1 on user errors (misc.rs:29-33).
-// Additive flags: --device N (which GPU), --quiet.  All compute happens in libpolypolish_b200.so on the GPU.
+// Additive flags: --device N (first GPU), --gpus N (polish: contigs shard across N GPUs), --quiet.  All compute happens in libpolypolish_b200.so on the GPU.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,7 +43,7 @@ static void help() {
     puts("\npolypolish filter --in1 <IN1> --in2 <IN2> --out1 <OUT1> --out2 <OUT2> [--orientation <auto>] [--low <0.1>] [--high <99.9>]");
     puts("polypolish polish [--debug <DEBUG>] [-i|--fraction_invalid <0.2>] [-v|--fraction_valid <0.5>] [-m|--max_errors <10>]");
     puts("                  [-d|--min_depth <5>] [--careful] <ASSEMBLY> [SAM]...");
-    puts("Additive: --device <N> (GPU index, default 0), --quiet");
+    puts("Additive: --device <N> (first GPU, default 0), --gpus <N> (polish: shard contigs over N GPUs), --quiet");
 }
 
 static double parse_f64(const char* flag, const char* s) {
@@ -65,7 +65,7 @@ int main(int argc, char** argv) {
     std::string cmd = argv[1];
     if (cmd == "-h" || cmd == "--help") { help(); return 0; }
     if (cmd == "-V" || cmd == "--version") { puts("Polypolish v0.6.1"); return 0; }
-    int device = 0;
+    int device = 0, gpus = 1;
     bool quiet = false;
     auto need = [&](int& i, const char* flag) -> const char* {
         if (i + 1 >= argc) usage_error(std::string("a value is required for '") + flag + "' but none was supplied");
@@ -86,24 +86,27 @@ int main(int argc, char** argv) {
             else if (a == "-d" || a == "--min_depth") prm.min_depth = parse_u32("--min_depth <MIN_DEPTH>", need(i, "--min_depth"));
             else if (a == "--careful") prm.careful = 1;
             else if (a == "--device") device = (int)parse_u32("--device", need(i, "--device"));
+            else if (a == "--gpus") gpus = (int)parse_u32("--gpus", need(i, "--gpus"));
             else if (a == "--quiet") quiet = true;
             else if (a.size() > 1 && a[0] == '-' && a != "-") usage_error("unexpected argument '" + a + "' found");
             else pos.push_back(a);
         }
         if (pos.empty()) usage_error("the following required arguments were not provided:\n  <ASSEMBLY>");
-        pp_ctx* ctx = nullptr;
-        if (pp_create(device, &ctx) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
+        if (gpus < 1) gpus = 1;
+        std::vector<pp_ctx*> ctxs(gpus, nullptr);
+        for (int g = 0; g < gpus; ++g)
+            if (pp_create(device + g, &ctxs[g]) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
         std::vector<const char*> sams;
         for (size_t i = 1; i < pos.size(); ++i) sams.push_back(pos[i].c_str());
         char* out = nullptr;
         uint64_t n = 0;
-        if (!quiet) fprintf(stderr, "Starting Polypolish polish (B200 build %s)\n\n", pp_version());
-        int rc = pp_polish_files(ctx, pos[0].c_str(), sams.data(), (int)sams.size(), &prm, debug.empty() ? nullptr : debug.c_str(), &out, &n, quiet ? 0 : 1);
-        if (rc != PP_OK) { std::string m = pp_last_error(ctx); pp_destroy(ctx); quit_with_error(m); }
+        if (!quiet) fprintf(stderr, "Starting Polypolish polish (B200 build %s, %d GPU%s)\n\n", pp_version(), gpus, gpus > 1 ? "s" : "");
+        int rc = pp_polish_files_multi(ctxs.data(), gpus, pos[0].c_str(), sams.data(), (int)sams.size(), &prm, debug.empty() ? nullptr : debug.c_str(), &out, &n, quiet ? 0 : 1);
+        if (rc != PP_OK) { std::string m = pp_last_error(ctxs[0]); for (auto c : ctxs) pp_destroy(c); quit_with_error(m); }
         fwrite(out, 1, n, stdout);
         fflush(stdout);
         pp_free(out);
-        pp_destroy(ctx);
+        for (auto c : ctxs) pp_destroy(c);
         if (!quiet) fprintf(stderr, "Finished!\n");
         return 0;
     }

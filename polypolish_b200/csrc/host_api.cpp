@@ -8,7 +8,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "pp_internal.h"
@@ -29,10 +32,45 @@ std::string fmt_thousands(uint64_t v) {      // num_format Locale::en
 
 extern "C" void pp_free(void* p) { free(p); }
 
-extern "C" int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* const* sams, int n_sams,
-                               const pp_polish_params* prm, const char* debug_path, char** out_fasta,
-                               uint64_t* out_len, int verbose) {
-    if (!ctx) return PP_ERR_ARG;
+// One shard on one GPU (run by its own host thread when there are several).
+struct ShardJob {
+    pp_ctx* ctx = nullptr;
+    pp_contigs contigs;
+    pp_alignments alns;
+    const uint32_t* contig_map = nullptr;
+    std::vector<uint64_t> out_off, changed, zero;
+    std::vector<uint8_t> bases;
+    pp_polish_result res;
+    int rc = PP_OK;
+    std::string err;
+};
+
+static void run_shard(ShardJob* j, const pp_polish_params* prm) {
+    const uint64_t G = j->contigs.off[j->contigs.n_contigs];
+    j->out_off.assign(j->contigs.n_contigs + 1, 0);
+    j->changed.assign(j->contigs.n_contigs, 0);
+    j->zero.assign(j->contigs.n_contigs, 0);
+    memset(&j->res, 0, sizeof j->res);
+    // Output is at most G + inserted bases; start with G + 1 MiB and retry once with the exact size.
+    uint64_t cap = G + (1u << 20);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        j->bases.resize(cap);
+        j->res.out_off = j->out_off.data();
+        j->res.out_bases = j->bases.data();
+        j->res.out_cap = cap;
+        j->res.changed = j->changed.data();
+        j->res.zero_depth = j->zero.data();
+        j->rc = pp_polish(j->ctx, &j->contigs, &j->alns, prm, &j->res);
+        if (j->rc == PP_ERR_ARG && j->res.out_len > cap) { cap = j->res.out_len; continue; }
+        break;
+    }
+    if (j->rc != PP_OK) j->err = pp_last_error(j->ctx);
+}
+
+// polish::polish (polish.rs:26-38) over one or several GPUs (contigs shard across them).
+static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembly, const char* const* sams, int n_sams,
+                             const pp_polish_params* prm, const char* debug_path, char** out_fasta, uint64_t* out_len, int verbose) {
+    pp_ctx* ctx = ctxs[0];
     if (!assembly || !prm || !out_fasta || !out_len || n_sams < 0) return pp_ctx_fail(ctx, PP_ERR_ARG, "pp_polish_files: bad arguments");
     *out_fasta = nullptr;
     *out_len = 0;
@@ -78,85 +116,121 @@ extern "C" int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* co
         return rc;
     }
 
-    const uint64_t G = contigs.off[contigs.n_contigs];
-    std::vector<uint64_t> out_off(contigs.n_contigs + 1), changed(contigs.n_contigs), zero(contigs.n_contigs);
-    std::vector<uint8_t> bases;
-    pp_polish_result res;
-    memset(&res, 0, sizeof res);
-    // Output is at most G + inserted bases; start with G + 1 MiB and retry once with the exact size.
-    uint64_t cap = G + (1u << 20);
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        bases.resize(cap);
-        res.out_off = out_off.data();
-        res.out_bases = bases.data();
-        res.out_cap = cap;
-        res.changed = changed.data();
-        res.zero_depth = zero.data();
-        rc = pp_polish(ctx, &contigs, &alns, prm, &res);
-        if (rc == PP_ERR_ARG && res.out_len > cap) { cap = res.out_len; continue; }
-        break;
+    // one job per GPU; with one GPU the job is the whole assembly
+    const uint32_t n_shards = (uint32_t)std::max(1, std::min<int>(n_ctx, (int)contigs.n_contigs));
+    pp_shards* shards = nullptr;
+    std::vector<ShardJob> jobs(n_shards);
+    if (n_shards == 1) {
+        jobs[0].ctx = ctx; jobs[0].contigs = contigs; jobs[0].alns = alns;
+    } else {
+        shards = pp_shards_build(&contigs, &alns, n_shards);
+        for (uint32_t s = 0; s < n_shards; ++s) {
+            jobs[s].ctx = ctxs[s];
+            pp_shards_get(shards, s, &jobs[s].contigs, &jobs[s].alns, &jobs[s].contig_map, nullptr);
+        }
     }
-    if (rc != PP_OK) {
-        if (rc == PP_ERR_INPUT && res.error_aln >= 0) {
+    {
+        std::vector<std::thread> th;
+        for (uint32_t s = 1; s < n_shards; ++s) th.emplace_back(run_shard, &jobs[s], prm);
+        run_shard(&jobs[0], prm);
+        for (auto& t : th) t.join();
+    }
+    uint64_t n_used = 0;
+    for (uint32_t s = 0; s < n_shards && rc == PP_OK; ++s) {
+        ShardJob& j = jobs[s];
+        n_used += j.res.n_aln_used;
+        if (j.rc == PP_OK) continue;
+        rc = j.rc;
+        std::string m = j.err;
+        if (rc == PP_ERR_INPUT && j.res.error_aln >= 0 && n_shards == 1) {
             // re-word device-detected errors with the names the reference prints (alignment.rs:190-198,298-300)
-            std::string m = pp_last_error(ctx);
-            const char* rn = pp_pack_read_name(pk, (uint64_t)res.error_aln);
+            const char* rn = pp_pack_read_name(pk, (uint64_t)j.res.error_aln);
             if (m.rfind("query name", 0) == 0)
-                m = "query name " + std::string(pp_pack_unknown_ref(pk, (uint64_t)res.error_aln)) + " in SAM but not in assembly";
+                m = "query name " + std::string(pp_pack_unknown_ref(pk, (uint64_t)j.res.error_aln)) + " in SAM but not in assembly";
             else if (m.rfind("CIGAR string does not", 0) == 0)
                 m = "CIGAR string for read " + std::string(rn) + " does not match read sequence";
             else if (m.rfind("unexpected character", 0) == 0) {
                 char cg[4096];
-                pp_pack_cigar_string(pk, (uint64_t)res.error_aln, cg, sizeof cg);
+                pp_pack_cigar_string(pk, (uint64_t)j.res.error_aln, cg, sizeof cg);
                 m = "unexpected character (other than M, =, X, I or D) in CIGAR string for read " + std::string(rn) +
                     ": \"" + cg + "\" - did you use BWA MEM to generate your alignments?";
-            }
-            else
+            } else
                 m += " (read " + std::string(rn) + ")";
-            rc = pp_ctx_fail(ctx, rc, m.c_str());
         }
+        pp_ctx_fail(ctx, rc, m.c_str());
+    }
+    if (rc != PP_OK) {
+        if (shards) pp_shards_free(shards);
         pp_pack_free(pk);
         pp_fasta_free(fa);
         return rc;
     }
     if (verbose) {
         fprintf(stderr, "\nFiltering for high-quality end-to-end alignments%s:\n", prm->careful ? " from reads with only one alignment" : "");
-        fprintf(stderr, "  %s alignments kept\n", fmt_thousands(res.n_aln_used).c_str());
-        fprintf(stderr, "  %s alignments discarded\n\n", fmt_thousands(alns.n_aln - res.n_aln_used).c_str());
+        fprintf(stderr, "  %s alignments kept\n", fmt_thousands(n_used).c_str());
+        fprintf(stderr, "  %s alignments discarded\n\n", fmt_thousands(alns.n_aln - n_used).c_str());
     }
 
-    // print_seq_to_stdout polish.rs:196-203
+    // where each input contig's polished bases are: (job, local contig)
+    std::vector<std::pair<uint32_t, uint32_t>> where(contigs.n_contigs);
+    for (uint32_t s = 0; s < n_shards; ++s)
+        for (uint32_t lc = 0; lc < jobs[s].contigs.n_contigs; ++lc)
+            where[n_shards == 1 ? lc : jobs[s].contig_map[lc]] = {s, lc};
+    // print_seq_to_stdout polish.rs:196-203, contigs in input order (polish.rs:147-152)
     std::string out;
-    out.reserve(res.out_len + 128 * (size_t)contigs.n_contigs);
+    uint64_t total = 0;
+    for (auto& j : jobs) total += j.res.out_len;
+    out.reserve(total + 128 * (size_t)contigs.n_contigs);
     for (uint32_t i = 0; i < contigs.n_contigs; ++i) {
+        const ShardJob& j = jobs[where[i].first];
+        const uint32_t lc = where[i].second;
         out += '>';
         out += pp_fasta_name(fa, i);
         const char* d = pp_fasta_description(fa, i);
         if (d[0]) { out += ' '; out += d; }
         out += " polypolish\n";
-        out.append((const char*)bases.data() + out_off[i], out_off[i + 1] - out_off[i]);
+        out.append((const char*)j.bases.data() + j.out_off[lc], j.out_off[lc + 1] - j.out_off[lc]);
         out += '\n';
         if (verbose) {
             uint64_t len = contigs.off[i + 1] - contigs.off[i];
             fprintf(stderr, "Polishing %s (%s bp):\n", pp_fasta_name(fa, i), fmt_thousands(len).c_str());
-            fprintf(stderr, "  %s bp %s a depth of zero (%.4f%% coverage)\n", fmt_thousands(zero[i]).c_str(), zero[i] == 1 ? "has" : "have",
-                    100.0 * (double)(len - zero[i]) / (double)len);
-            fprintf(stderr, "  %s %s changed (%.4f%% of total positions)\n\n", fmt_thousands(changed[i]).c_str(),
-                    changed[i] == 1 ? "position" : "positions", 100.0 * (double)changed[i] / (double)len);
+            fprintf(stderr, "  %s bp %s a depth of zero (%.4f%% coverage)\n", fmt_thousands(j.zero[lc]).c_str(), j.zero[lc] == 1 ? "has" : "have",
+                    100.0 * (double)(len - j.zero[lc]) / (double)len);
+            fprintf(stderr, "  %s %s changed (%.4f%% of total positions)\n\n", fmt_thousands(j.changed[lc]).c_str(),
+                    j.changed[lc] == 1 ? "position" : "positions", 100.0 * (double)j.changed[lc] / (double)len);
         }
     }
     if (verbose) {
-        fprintf(stderr, "device path: %.3f ms total (h2d %.3f, classify %.3f, scatter %.3f, fix-up %.3f, vote %.3f, d2h %.3f), %u kernels\n",
-                res.timing.total_ms, res.timing.stage_ms[6], res.timing.stage_ms[1], res.timing.stage_ms[2], res.timing.stage_ms[3],
-                res.timing.stage_ms[5], res.timing.stage_ms[7], res.timing.launches);
+        for (uint32_t s = 0; s < n_shards; ++s) {
+            const pp_timing& t = jobs[s].res.timing;
+            fprintf(stderr, "GPU job %u: %u contigs, %s alignments; device path %.3f ms (h2d %.3f, scatter %.3f, fix-up %.3f, vote %.3f, compact %.3f, d2h %.3f), %u kernels\n",
+                    s, jobs[s].contigs.n_contigs, fmt_thousands(jobs[s].alns.n_aln).c_str(), t.total_ms, t.stage_ms[6], t.stage_ms[2], t.stage_ms[3],
+                    t.stage_ms[5], t.stage_ms[4], t.stage_ms[7], t.launches);
+        }
     }
     char* buf = (char*)malloc(out.size() + 1);
-    if (!buf) { pp_pack_free(pk); pp_fasta_free(fa); return pp_ctx_fail(ctx, PP_ERR_NOMEM, "out of memory"); }
+    if (shards) pp_shards_free(shards);
+    pp_pack_free(pk);
+    pp_fasta_free(fa);
+    if (!buf) return pp_ctx_fail(ctx, PP_ERR_NOMEM, "out of memory");
     memcpy(buf, out.data(), out.size());
     buf[out.size()] = 0;
     *out_fasta = buf;
     *out_len = out.size();
-    pp_pack_free(pk);
-    pp_fasta_free(fa);
     return PP_OK;
+}
+
+extern "C" int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* const* sams, int n_sams,
+                               const pp_polish_params* prm, const char* debug_path, char** out_fasta,
+                               uint64_t* out_len, int verbose) {
+    if (!ctx) return PP_ERR_ARG;
+    return polish_files_impl(&ctx, 1, assembly, sams, n_sams, prm, debug_path, out_fasta, out_len, verbose);
+}
+
+// Several GPUs of one box: contigs shard across the contexts (one host thread each); errors are reported on ctxs[0].
+extern "C" int pp_polish_files_multi(pp_ctx* const* ctxs, int n_ctx, const char* assembly, const char* const* sams, int n_sams,
+                                     const pp_polish_params* prm, const char* debug_path, char** out_fasta,
+                                     uint64_t* out_len, int verbose) {
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return PP_ERR_ARG;
+    return polish_files_impl(ctxs, n_ctx, assembly, sams, n_sams, prm, debug_path, out_fasta, out_len, verbose);
 }

@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
         }
         bool rc = false;
         uint32_t gstart = 0, cend = 0, seqoff = 0, len = 0;
+        if (fl & PP_FLAG_GHOST) good = false;                   // another shard scatters it; it only counted towards k
         if (good) {
             used++;
             good = false;

@@ -188,3 +188,62 @@ def test_full_size_properties(ctx):
     r3 = ctx.polish_resident()
     assert r3["sequences"] == r1["sequences"]
     assert sum(r1["changed"]) > 100
+
+
+@pytest.mark.parametrize("seed,n_shards", [(20, 2), (21, 3), (22, 2), (23, 5)])
+def test_contig_sharding_invariance(ctx, oracle, tmp_path, seed, n_shards):
+    """polishing each contig shard on its own (with ghost records keeping k) == polishing everything."""
+    case = fuzzgen.make_case(seed, n_contigs=3, multimap=0.6, opts=dict(careful=(seed == 22)))
+    fa, sams = case.write(tmp_path)
+    exp = oracle.polish(fa, sams, **case.opts)
+    f = pp.load_fasta(fa)
+    p = pp.pack_sams(f, sams, careful=case.opts["careful"])
+    sh = api.Shards(f.view, p.view, n_shards)
+    seqs, used = [None] * 3, 0
+    for s in range(n_shards):
+        c, a, cmap, n_home = sh.get(s)
+        if c.n_contigs == 0:
+            assert a.n_aln == 0
+            continue
+        r = ctx.polish_packed(c, a, **case.opts)
+        for lc, oc in enumerate(cmap):
+            seqs[oc] = r["sequences"][lc]
+        used += r["n_aln_used"]
+    fasta = b"".join(b">" + f.names[i].encode() + ((b" " + f.descriptions[i].encode()) if f.descriptions[i] else b"") +
+                     b" polypolish\n" + seqs[i] + b"\n" for i in range(3))
+    assert fasta == exp["fasta"]
+    assert used == exp["used_total"]
+
+
+def test_multi_context_file_path(oracle, tmp_path):
+    """pp_polish_files_multi with two contexts (both on GPU 0 here): host threads, sharding, merge in input order."""
+    case = fuzzgen.make_case(31, n_contigs=3, multimap=0.5, opts=dict(careful=False))
+    fa, sams = case.write(tmp_path)
+    exp = oracle.polish(fa, sams, **case.opts)["fasta"]
+    assert api.polish_files_multi(fa, sams, devices=[0, 0], **case.opts) == exp
+    assert api.polish_files_multi(fa, sams, devices=[0, 0, 0, 0], **case.opts) == exp
+    syn = api.Synth(seed=9, n_contigs=4, contig_len=30_000, depth=50)
+    d2 = tmp_path / "syn"
+    d2.mkdir()
+    fa2, sams2 = syn.write(d2)
+    assert api.polish_files_multi(fa2, sams2, devices=[0, 0, 0]) == oracle.polish(fa2, sams2)["fasta"]
+
+
+def test_cli_binary(oracle, tmp_path):
+    """The drop-in command line: same flags as the reference, FASTA on stdout, Error + exit 1 on user errors."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "polypolish")
+    syn = api.Synth(seed=4, contig_len=30_000, depth=40)
+    fa, sams = syn.write(tmp_path)
+    r = subprocess.run([exe, "polish", "-m", "8", "--min_depth", "4", fa] + sams, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == oracle.polish(fa, sams, max_errors=8, min_depth=4)["fasta"]
+    r = subprocess.run([exe, "polish", "-i", "0.6", fa] + sams, capture_output=True)
+    assert r.returncode == 1 and b"Error: --fraction_invalid must be less than --fraction_valid" in r.stderr
+    r = subprocess.run([exe, "-V"], capture_output=True)
+    assert r.stdout.strip() == b"Polypolish v0.6.1"
+    o1, o2 = tmp_path / "f1.sam", tmp_path / "f2.sam"
+    r = subprocess.run([exe, "filter", "--in1", sams[0], "--in2", sams[1], "--out1", str(o1), "--out2", str(o2)], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    ef = oracle.filter(sams[0], sams[1])
+    assert open(o1, "rb").read() == ef["out1"] and open(o2, "rb").read() == ef["out2"]
