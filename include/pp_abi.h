@@ -142,6 +142,31 @@ int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* contigs, const pp_alignment
 int pp_polish_resident(pp_ctx* ctx, const pp_polish_params* params, pp_polish_result* result);
 
 
+/* Per-position record of the last polish on ctx, for the --debug TSV (polish.rs:230-266, pileup.rs:137-166).
+ * Recording is off by default (it costs 56 B per position); switch it on before the polish call. */
+typedef struct {
+  double depth;                 /* pileup.rs:31 */
+  uint32_t valid_threshold, invalid_threshold;  /* pileup.rs:70-72 */
+  uint32_t count[6];            /* A, C, G, T, "-", and the draft's own base when it is not A/C/G/T */
+  uint32_t n_other;             /* entries carrying any other allele (their distinct strings: pp_polish_debug_alleles) */
+  uint32_t new_node;            /* node index of the emitted allele when it is an "other" allele, else 0xFFFFFFFF */
+  uint8_t original;             /* pileup.rs:30 */
+  uint8_t status;               /* 0 low_depth 1 none 2 multiple 3 too_close 4 kept 5 changed (pileup.rs:18-25,156-163) */
+  uint8_t new_char;             /* emitted single character ('-' for a deletion) when new_node == 0xFFFFFFFF */
+  uint8_t pad[5];
+} pp_debug_pos;
+typedef struct {                /* one distinct "other" allele of one position */
+  uint64_t sig;                 /* 4-bit mode: low nibble = length (1..15) then one BAM code per nibble; 8-bit mode: low byte =
+                                   length (1..7) then one byte per base; length field 0 = too long, read it through val */
+  uint64_t val;                 /* alignment index << 32 | start in the (strand-corrected) read << 16 | length */
+  uint32_t count;
+  uint32_t next;                /* next node of the same position, 0xFFFFFFFF = end */
+} pp_debug_node;
+int pp_polish_set_debug(pp_ctx* ctx, int on /* 1 record, 2 stop recording but keep the last records, 0 off */);
+int pp_polish_debug_fetch(pp_ctx* ctx, uint64_t first_pos, uint64_t n_pos, pp_debug_pos* out);
+/* head[p] = 1 + index of the first node of global position p (0 = none); nodes[0..*n_nodes) */
+int pp_polish_debug_alleles(pp_ctx* ctx, uint32_t* head /* [total bp] */, pp_debug_node* nodes, uint64_t node_cap, uint64_t* n_nodes);
+
 /* ------------------------------------------------------------------------------------------------------
  * filter (filter.rs).  One record per ALIGNED line of one mate's SAM file, in file order.
  * Replaces get_insert_size_thresholds (filter.rs:148-186) and alignment_pass_qc (filter.rs:352-377).

@@ -32,6 +32,97 @@ std::string fmt_thousands(uint64_t v) {      // num_format Locale::en
 
 extern "C" void pp_free(void* p) { free(p); }
 
+// misc.rs:170-182 complement_base (upper-case input)
+static char complement_char(char b) {
+    switch (b) {
+        case 'A': return 'T'; case 'T': return 'A'; case 'G': return 'C'; case 'C': return 'G'; case 'N': return 'N';
+        case 'R': return 'Y'; case 'Y': return 'R'; case 'S': return 'S'; case 'W': return 'W'; case 'K': return 'M'; case 'M': return 'K';
+        case 'B': return 'V'; case 'V': return 'B'; case 'D': return 'H'; case 'H': return 'D';
+        case '.': return '.'; case '-': return '-'; case '?': return '?';
+        default: return 'N';
+    }
+}
+
+// The string of one "other" allele node (pileup.rs:62 key).
+static std::string node_allele(const pp_debug_node& nd, const pp_alignments* a) {
+    static const char* NIB = "=ACMGRSVTWYHKDBN";
+    std::string out;
+    if (a->seq_bits == 4 && (nd.sig & 15)) {
+        for (uint32_t i = 0; i < (nd.sig & 15); ++i) out += NIB[(nd.sig >> (4 * (i + 1))) & 15];
+        return out;
+    }
+    if (a->seq_bits == 8 && (nd.sig & 255)) {
+        for (uint32_t i = 0; i < (nd.sig & 255); ++i) out += (char)((nd.sig >> (8 * (i + 1))) & 255);
+        return out;
+    }
+    const uint32_t aln = (uint32_t)(nd.val >> 32), start = (uint32_t)(nd.val >> 16) & 0xFFFFu, len = (uint32_t)nd.val & 0xFFFFu;
+    const bool rc = a->flags[aln] & PP_FLAG_RC;
+    const uint32_t n = a->seq_len[aln];
+    for (uint32_t i = 0; i < len; ++i) {
+        const uint32_t e = start + i, j = rc ? (n - 1 - e) : e;
+        char ch;
+        if (a->seq_bits == 4) {
+            const uint8_t b = a->seq_pool[(size_t)a->seq_off[aln] * (PP_SEQ_BLOCK / 2) + (j >> 1)];
+            ch = NIB[(b >> ((j & 1) * 4)) & 15];
+        } else {
+            ch = (char)a->seq_pool[(size_t)a->seq_off[aln] * PP_SEQ_BLOCK + j];
+        }
+        out += rc ? complement_char(ch) : ch;
+    }
+    return out;
+}
+
+// write_debug_header / write_debug_line (polish.rs:247-266) + get_debug_line / get_count_str (pileup.rs:137-166)
+static int write_debug_tsv(pp_ctx* ctx, const pp_fasta* fa, const pp_contigs* contigs, const pp_alignments* alns, FILE* f) {
+    static const char* STATUS[6] = {"low_depth", "none", "multiple", "too_close", "kept", "changed"};
+    const uint64_t G = contigs->off[contigs->n_contigs];
+    std::vector<uint32_t> head(G);
+    uint64_t n_nodes = 0;
+    pp_polish_debug_alleles(ctx, nullptr, nullptr, 0, &n_nodes);           // size query (reports the node count, then fails on the null buffers)
+    std::vector<pp_debug_node> nodes(n_nodes + 1);
+    int rc = pp_polish_debug_alleles(ctx, head.data(), nodes.data(), n_nodes, &n_nodes);
+    if (rc != PP_OK) return rc;
+    if (fputs("name\tpos\tbase\tdepth\tinvalid\tvalid\tpileup\tstatus\tnew_base\n", f) < 0) return PP_ERR_IO;
+    const uint64_t CH = 1 << 18;
+    std::vector<pp_debug_pos> recs(CH);
+    std::string buf;
+    std::vector<std::string> counts;
+    char tmp[64];
+    for (uint32_t c = 0; c < contigs->n_contigs; ++c) {
+        const char* name = pp_fasta_name(fa, c);
+        for (uint64_t p0 = contigs->off[c]; p0 < contigs->off[c + 1]; p0 += CH) {
+            const uint64_t n = std::min<uint64_t>(CH, contigs->off[c + 1] - p0);
+            rc = pp_polish_debug_fetch(ctx, p0, n, recs.data());
+            if (rc != PP_OK) return rc;
+            buf.clear();
+            for (uint64_t i = 0; i < n; ++i) {
+                const pp_debug_pos& r = recs[i];
+                const uint64_t gp = p0 + i;
+                counts.clear();
+                static const char* ACGT = "ACGT";
+                for (int b = 0; b < 4; ++b) if (r.count[b]) counts.push_back(std::string(1, ACGT[b]) + "x" + std::to_string(r.count[b]));
+                if (r.count[4]) counts.push_back("-x" + std::to_string(r.count[4]));
+                if (r.count[5]) counts.push_back(std::string(1, (char)r.original) + "x" + std::to_string(r.count[5]));
+                for (uint32_t nd = head[gp]; nd != 0;) {
+                    const pp_debug_node& node = nodes[nd - 1];
+                    counts.push_back(node_allele(node, alns) + "x" + std::to_string(node.count));
+                    nd = node.next == 0xFFFFFFFFu ? 0 : node.next + 1;
+                }
+                std::sort(counts.begin(), counts.end());
+                buf += name; buf += '\t'; buf += std::to_string(gp - contigs->off[c]); buf += '\t'; buf += (char)r.original; buf += '\t';
+                snprintf(tmp, sizeof tmp, "%.1f", r.depth);          // Rust {:.1}: both round the exact binary value
+                buf += tmp; buf += '\t'; buf += std::to_string(r.invalid_threshold); buf += '\t'; buf += std::to_string(r.valid_threshold); buf += '\t';
+                for (size_t k = 0; k < counts.size(); ++k) { if (k) buf += ','; buf += counts[k]; }
+                buf += '\t'; buf += STATUS[r.status < 6 ? r.status : 0]; buf += '\t';
+                if (r.new_node != 0xFFFFFFFFu) buf += node_allele(nodes[r.new_node], alns); else buf += (char)r.new_char;
+                buf += '\n';
+            }
+            if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) return PP_ERR_IO;
+        }
+    }
+    return PP_OK;
+}
+
 // One shard on one GPU (run by its own host thread when there are several).
 struct ShardJob {
     pp_ctx* ctx = nullptr;
@@ -82,8 +173,13 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     if (!pp::file_exists(assembly)) return pp_ctx_fail(ctx, PP_ERR_INPUT, ("\"" + std::string(assembly) + "\" file does not exist").c_str());
     for (int i = 0; i < n_sams; ++i)
         if (!pp::file_exists(sams[i])) return pp_ctx_fail(ctx, PP_ERR_INPUT, ("\"" + std::string(sams[i]) + "\" file does not exist").c_str());
-    if (debug_path && debug_path[0])
-        return pp_ctx_fail(ctx, PP_ERR_ARG, "--debug (per-base TSV, polish.rs:230-266) is not implemented in this build");
+    const bool debug = debug_path && debug_path[0];
+    FILE* debug_file = nullptr;
+    if (debug) {                                          // create_debug_file polish.rs:230-244
+        debug_file = fopen(debug_path, "wb");
+        if (!debug_file) return pp_ctx_fail(ctx, PP_ERR_IO, ("unable to create \"" + std::string(debug_path) + "\"").c_str());
+    }
+    struct FileCloser { FILE*& f; ~FileCloser() { if (f) fclose(f); } } closer{debug_file};
 
     char ebuf[1024];
     pp_fasta* fa = pp_fasta_load(assembly, ebuf, sizeof ebuf);
@@ -117,7 +213,8 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     }
 
     // one job per GPU; with one GPU the job is the whole assembly
-    const uint32_t n_shards = (uint32_t)std::max(1, std::min<int>(n_ctx, (int)contigs.n_contigs));
+    const uint32_t n_shards = debug ? 1u : (uint32_t)std::max(1, std::min<int>(n_ctx, (int)contigs.n_contigs));   // the debug TSV is written from one GPU
+    if (debug) pp_polish_set_debug(ctx, 1);
     pp_shards* shards = nullptr;
     std::vector<ShardJob> jobs(n_shards);
     if (n_shards == 1) {
@@ -158,6 +255,11 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
                 m += " (read " + std::string(rn) + ")";
         }
         pp_ctx_fail(ctx, rc, m.c_str());
+    }
+    if (debug) pp_polish_set_debug(ctx, 0 + (rc == PP_OK ? 2 : 0));      // keep the recorded data readable, stop recording
+    if (rc == PP_OK && debug) {
+        rc = write_debug_tsv(ctx, fa, &contigs, &alns, debug_file);
+        if (rc != PP_OK && rc != PP_ERR_CUDA) rc = pp_ctx_fail(ctx, PP_ERR_IO, ("unable to write to file \"" + std::string(debug_path) + "\"").c_str());
     }
     if (rc != PP_OK) {
         if (shards) pp_shards_free(shards);

@@ -768,6 +768,7 @@ struct VoteParams {
     uint16_t* res;                    // [padG] low byte = character, high byte = output length (255: see rec_at)
     uint32_t* rec_at;                 // [G] other-allele node to emit at a position (only where res says so)
     long long* chunk_delta;           // [n_chunks] sum(output length) - positions of the chunk
+    pp_debug_pos* dbg;                // [G] per-position debug records, or nullptr
 };
 
 // What the other-allele slow path needs, passed by value so that the kernel parameter structs are never
@@ -807,11 +808,11 @@ __device__ __forceinline__ uint8_t other_char(const OthCtx& oc, uint32_t rec, ui
 // multi-base node), bit 24 changed, bit 25 emit from node `rec`.
 struct PosOut { uint32_t packed; uint32_t rec; };
 
-// The vote of pileup.rs:67-134 for one covered position.
+// The vote of pileup.rs:67-134 for one covered position.  packed bits 26..28 carry the BaseStatus.
 template <int BITS>
 __device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const DevParams& prm, uint32_t pos, uint32_t orig, double depth,
                                                 uint32_t cA, uint32_t cC, uint32_t cG, uint32_t cT, uint32_t cDel,
-                                                uint32_t matched, uint32_t n_other) {
+                                                uint32_t matched, uint32_t n_other, pp_debug_pos* dbg) {
     const uint32_t vt = max(prm.min_depth, bankers_rounding(__dmul_rn(depth, prm.fv)));
     const uint32_t it = bankers_rounding(__dmul_rn(depth, prm.fi));
     Tally t{0, 0, -1, 0};
@@ -825,20 +826,38 @@ __device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const DevParam
     PosOut o;
     o.rec = 0;
     o.packed = (orig == '-' ? 0u : 1u) | (orig << 16);
-    if (depth < (double)prm.min_depth) return o;               // low_depth
-    if (t.nvalid != 1 || t.ninter > 0) return o;               // none / multiple / too_close
-    if (t.which <= 3) {
-        const uint32_t nb = (uint32_t)"ACGT"[t.which];
-        o.packed = 1u | (nb << 16) | (nb != orig ? 1u << 24 : 0u);
-    } else if (t.which == 4) {
-        o.packed = 0u | ((uint32_t)'-' << 16) | (orig != '-' ? 1u << 24 : 0u);
-    } else if (t.which == 6) {
-        const uint32_t len = (uint32_t)oc.nodes[t.rec].val & 0xFFFFu;
-        uint32_t n = 0;
-        for (uint32_t q = 0; q < len; ++q) n += other_char<BITS>(oc, t.rec, q) != '-';
-        // an other-allele string never equals the draft's own 1-char string (those entries are "matched")
-        o.packed = (n & 0xFFFFu) | (1u << 24) | (1u << 25);
-        o.rec = t.rec;
+    uint32_t status;                                          // 0 low_depth 1 none 2 multiple 3 too_close 4 kept 5 changed
+    if (depth < (double)prm.min_depth) status = 0;
+    else if (t.nvalid == 0) status = 1;
+    else if (t.nvalid > 1) status = 2;
+    else if (t.ninter > 0) status = 3;
+    else {
+        status = 4;
+        if (t.which <= 3) {
+            const uint32_t nb = (uint32_t)"ACGT"[t.which];
+            if (nb != orig) status = 5;
+            o.packed = 1u | (nb << 16) | (nb != orig ? 1u << 24 : 0u);
+        } else if (t.which == 4) {
+            if (orig != '-') status = 5;
+            o.packed = 0u | ((uint32_t)'-' << 16) | (orig != '-' ? 1u << 24 : 0u);
+        } else if (t.which == 6) {
+            const uint32_t len = (uint32_t)oc.nodes[t.rec].val & 0xFFFFu;
+            uint32_t n = 0;
+            for (uint32_t q = 0; q < len; ++q) n += other_char<BITS>(oc, t.rec, q) != '-';
+            // an other-allele string never equals the draft's own 1-char string (those entries are "matched")
+            status = 5;
+            o.packed = (n & 0xFFFFu) | (1u << 24) | (1u << 25);
+            o.rec = t.rec;
+        }
+    }
+    o.packed |= status << 26;
+    if (dbg) {
+        dbg->depth = depth; dbg->valid_threshold = vt; dbg->invalid_threshold = it;
+        dbg->count[0] = cA; dbg->count[1] = cC; dbg->count[2] = cG; dbg->count[3] = cT; dbg->count[4] = cDel; dbg->count[5] = matched;
+        dbg->n_other = n_other;
+        dbg->new_node = ((o.packed >> 25) & 1u) ? o.rec : 0xFFFFFFFFu;
+        dbg->original = (uint8_t)orig; dbg->status = (uint8_t)status;
+        dbg->new_char = ((o.packed >> 25) & 1u) ? 0 : (((o.packed & 0xFFFFu) == 0 && orig != '-') ? (uint8_t)'-' : (uint8_t)(o.packed >> 16));
     }
     return o;
 }
@@ -920,6 +939,13 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
             n_zero++;
             po[i].packed = (orig == '-' ? 0u : 1u) | (orig << 16);
             tlen += po[i].packed & 0xFFFFu;
+            if (vp.dbg) {                                    // min_depth > 0: low_depth; min_depth == 0: A,C,G,T all "valid" -> multiple
+                pp_debug_pos r;
+                memset(&r, 0, sizeof r);
+                r.valid_threshold = prm.min_depth; r.new_node = 0xFFFFFFFFu; r.original = (uint8_t)orig;
+                r.status = prm.min_depth > 0 ? 0 : 2; r.new_char = (uint8_t)orig;
+                vp.dbg[p] = r;
+            }
             continue;
         }
         if (cover >= 65536u) atomicOr(&d.st->flags, FL_COUNTER_OVF);
@@ -933,7 +959,7 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
         else if (orig == 'G') { cG += matched; matched = 0; }
         else if (orig == 'T') { cT += matched; matched = 0; }
         const double depth = multi ? d.depth_fix[p] : (double)cover;
-        po[i] = vote_position<BITS>(oc, prm, p, orig, depth, cA, cC, cG, cT, cDel, matched, n_other);
+        po[i] = vote_position<BITS>(oc, prm, p, orig, depth, cA, cC, cG, cT, cDel, matched, n_other, vp.dbg ? vp.dbg + p : nullptr);
         n_changed += (po[i].packed >> 24) & 1u;
         tlen += po[i].packed & 0xFFFFu;
     }
@@ -1085,7 +1111,7 @@ struct DevBuf {
 
 enum { B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL,
        B_DRAFT, B_CTGOFF, B_NIB, B_ZEROPOOL, B_DEPTHFIX, B_RECGN, B_RECK, B_NODES, B_FIXKEY2, B_FIXVAL2, B_CUBTMP, B_OUT,
-       B_OUTOFF, B_AGG1, B_INC1, B_AGGC, B_INCC, B_RES, B_RECAT, B_CHUNKDELTA, B_PARAMS, B_SCRATCH, B_COUNT };
+       B_OUTOFF, B_DEBUG, B_AGG1, B_INC1, B_AGGC, B_INCC, B_RES, B_RECAT, B_CHUNKDELTA, B_PARAMS, B_SCRATCH, B_COUNT };
 
 struct pp_ctx {
     int device = 0;
@@ -1106,6 +1132,9 @@ struct pp_ctx {
     uint32_t node_cap = 0, fix_cap = 0;
     uint64_t out_cap = 0;
     bool global_k = false;
+    bool debug_on = false, have_debug = false;
+    const uint32_t* last_head = nullptr;
+    uint32_t last_nodes = 0;
 
     int fail(int code, const std::string& m) { err = m; return code; }
     int fail_cuda(cudaError_t e, const char* what, int line) {
@@ -1375,6 +1404,8 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         vp.st1 = (uint32_t*)(zp + o_st1); vp.agg1 = ctx->b[B_AGG1].as<unsigned long long>(); vp.inc1 = ctx->b[B_INC1].as<unsigned long long>();
         vp.res = ctx->b[B_RES].as<uint16_t>(); vp.rec_at = ctx->b[B_RECAT].as<uint32_t>();
         vp.chunk_delta = ctx->b[B_CHUNKDELTA].as<long long>();
+        vp.dbg = nullptr;
+        if (ctx->debug_on) { CK(ctx->b[B_DEBUG].ensure((G + 1) * sizeof(pp_debug_pos))); vp.dbg = ctx->b[B_DEBUG].as<pp_debug_pos>(); }
         k_vote<BITS><<<n_chunks, VT_THREADS, 0, s>>>(d, vp);
         CK(cudaEventRecord(ctx->ev[5], s));
         k_compact<BITS><<<n_chunks, VT_THREADS, 0, s>>>(d, vp);
@@ -1401,6 +1432,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         if (hs.flags & FL_COUNTER_OVF)
             return ctx->fail(PP_ERR_INPUT, "a position is covered by 65536 or more alignments: not supported by this build's 16-bit allele counters");
 
+        ctx->have_debug = ctx->debug_on; ctx->last_head = d.oth_head; ctx->last_nodes = std::min(hs.node_count, node_cap);
         res->out_len = hs.out_len;
         res->n_aln_used = hs.n_used;
         res->error_aln = -1;
@@ -1470,4 +1502,35 @@ extern "C" int pp_polish(pp_ctx* ctx, const pp_contigs* contigs, const pp_alignm
     rc = ctx->seq_bits == 4 ? run_polish<4>(ctx, params, result) : run_polish<8>(ctx, params, result);
     if (rc == PP_OK) result->timing.stage_ms[6] = h2d;
     return rc;
+}
+
+extern "C" int pp_polish_set_debug(pp_ctx* ctx, int on) {
+    if (!ctx) return PP_ERR_ARG;
+    ctx->debug_on = on == 1;            // 2 = stop recording but keep the last call's records readable
+    if (on == 0) ctx->have_debug = false;
+    return PP_OK;
+}
+
+extern "C" int pp_polish_debug_fetch(pp_ctx* ctx, uint64_t first_pos, uint64_t n_pos, pp_debug_pos* out) {
+    if (!ctx) return PP_ERR_ARG;
+    if (!ctx->have_debug) return ctx->fail(PP_ERR_ARG, "pp_polish_debug_fetch: the last polish did not record debug positions (pp_polish_set_debug)");
+    if (!out || first_pos + n_pos > ctx->G) return ctx->fail(PP_ERR_ARG, "pp_polish_debug_fetch: range outside the assembly");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->b[B_DEBUG].as<pp_debug_pos>() + first_pos, n_pos * sizeof(pp_debug_pos), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PP_OK;
+}
+
+extern "C" int pp_polish_debug_alleles(pp_ctx* ctx, uint32_t* head, pp_debug_node* nodes, uint64_t node_cap, uint64_t* n_nodes) {
+    if (!ctx) return PP_ERR_ARG;
+    if (!ctx->have_debug || !ctx->last_head) return ctx->fail(PP_ERR_ARG, "pp_polish_debug_alleles: no debug polish on this context");
+    if (n_nodes) *n_nodes = ctx->last_nodes;
+    if (!head && !nodes && node_cap == 0) return PP_ERR_ARG;       // size query
+    if (!head || (ctx->last_nodes && !nodes) || node_cap < ctx->last_nodes) return ctx->fail(PP_ERR_ARG, "pp_polish_debug_alleles: buffers too small");
+    static_assert(sizeof(pp_debug_node) == sizeof(OthNode), "debug node layout");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(head, ctx->last_head, ctx->G * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->last_nodes) CK(cudaMemcpyAsync(nodes, ctx->b[B_NODES].p, (size_t)ctx->last_nodes * sizeof(OthNode), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PP_OK;
 }

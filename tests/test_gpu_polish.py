@@ -247,3 +247,27 @@ def test_cli_binary(oracle, tmp_path):
     assert r.returncode == 0, r.stderr.decode()
     ef = oracle.filter(sams[0], sams[1])
     assert open(o1, "rb").read() == ef["out1"] and open(o2, "rb").read() == ef["out2"]
+
+
+@pytest.mark.parametrize("seed", [100, 101, 104, 105, 300, 303])
+def test_debug_tsv_parity(ctx, oracle, tmp_path, seed):
+    """--debug per-base TSV (polish.rs:230-266): depth, thresholds, sorted allele counts, status, new base."""
+    kw = dict(n_contigs=2, contig_len=(200, 400), depth=(150, 300), multimap=0.8, opts=dict(careful=False)) if seed >= 300 else {}
+    case = fuzzgen.make_case(seed, exotic=0.5 if seed % 4 == 0 else 0.0, **kw)
+    fa, sams = case.write(tmp_path)
+    exp = oracle.polish(fa, sams, debug=True, **case.opts)
+    dbg = tmp_path / "debug.tsv"
+    got = ctx.polish_files(fa, sams, debug=dbg, **case.opts)
+    assert got == exp["fasta"]
+    assert dbg.read_bytes() == exp["debug_tsv"]
+    # recording is off again afterwards and the plain path still works
+    assert ctx.polish_files(fa, sams, **case.opts) == exp["fasta"]
+
+
+def test_debug_tsv_synth(ctx, oracle, tmp_path):
+    syn = api.Synth(seed=6, n_contigs=2, contig_len=40_000, depth=60)
+    fa, sams = syn.write(tmp_path)
+    exp = oracle.polish(fa, sams, debug=True)
+    dbg = tmp_path / "debug.tsv"
+    assert ctx.polish_files(fa, sams, debug=dbg) == exp["fasta"]
+    assert dbg.read_bytes() == exp["debug_tsv"]
