@@ -59,7 +59,7 @@ struct DevStatus {
     unsigned long long fix_count;    // (alignment, flagged tile) pairs found by k_collect
     unsigned int node_count;         // other-allele nodes allocated
     unsigned int flags;
-    unsigned int ticket_vote, ticket_collect;
+    unsigned int ticket_vote, ticket_collect, ticket_fix, pad1;
 };
 
 struct DevParams {                   // pp_polish_params, device resident (refreshed by a memcpy before each call)
@@ -712,14 +712,20 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
 }
 
 #define FX_WARPS 4
+#define FX_BATCH 128                 // list entries staged per round (4 per lane, their gathers in flight together)
 __global__ void __launch_bounds__(FX_WARPS * 32) k_depth_fixup(DevData d, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals) {
     // One WARP per flagged tile, four consecutive positions per lane (four independent dependent-add chains); the
-    // tile's list is staged 32 entries at a time in the warp's own shared-memory slice.
-    __shared__ uint2 s_rng[FX_WARPS][32];        // (start, length) of each staged entry
-    __shared__ double s_inv[FX_WARPS][32];       // 1.0 / k
+    // tile's list is staged FX_BATCH entries at a time in the warp's own shared-memory slice.
+    __shared__ uint2 s_rng[FX_WARPS][FX_BATCH];        // (start, length) of each staged entry
+    __shared__ double s_inv[FX_WARPS][FX_BATCH];       // 1.0 / k
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t warp = blockIdx.x * FX_WARPS + wib, n_warps = gridDim.x * FX_WARPS;
-    for (uint32_t tile = warp; tile < d.n_tiles; tile += n_warps) {
+    for (;;) {
+        // warps pull tiles from a shared ticket so that the few heavy (flagged, long-list) tiles spread over the chip;
+        // neighbouring tiles of one repeat land on different warps
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&d.st->ticket_fix, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= d.n_tiles) break;
         if (!((d.tileflag[tile >> 5] >> (tile & 31)) & 1u)) continue;
         uint32_t lo = 0, hi = 0;
         if (lane == 0) lo = lower_bound_u32(keys, d.fix_cap, tile + 1);
@@ -728,16 +734,21 @@ __global__ void __launch_bounds__(FX_WARPS * 32) k_depth_fixup(DevData d, const 
         hi = __shfl_sync(0xffffffffu, hi, 1);
         const uint32_t p = tile * PP_TILE + lane * 4;
         double dep0 = 0.0, dep1 = 0.0, dep2 = 0.0, dep3 = 0.0;
-        for (uint32_t base = lo; base < hi; base += 32) {
-            const uint32_t i = base + lane;
-            if (i < hi) {
-                const uint32_t aln = vals[i];
-                const unsigned long long v = d.rec_gn[aln];
-                s_rng[wib][lane] = make_uint2((uint32_t)(v >> 32), (uint32_t)v);
-                s_inv[wib][lane] = __ddiv_rn(1.0, (double)d.rec_k[aln]);      // 1.0 / good_alignments.len() as f64
+        for (uint32_t base = lo; base < hi; base += FX_BATCH) {
+            uint32_t aln[FX_BATCH / 32];
+            unsigned long long gn[FX_BATCH / 32];
+            uint32_t kk[FX_BATCH / 32];
+#pragma unroll
+            for (int q = 0; q < FX_BATCH / 32; ++q) { const uint32_t i = base + q * 32 + lane; aln[q] = (i < hi) ? vals[i] : 0u; }
+#pragma unroll
+            for (int q = 0; q < FX_BATCH / 32; ++q) { const uint32_t i = base + q * 32 + lane; gn[q] = (i < hi) ? d.rec_gn[aln[q]] : 0ull; kk[q] = (i < hi) ? d.rec_k[aln[q]] : 1u; }
+#pragma unroll
+            for (int q = 0; q < FX_BATCH / 32; ++q) {
+                s_rng[wib][q * 32 + lane] = make_uint2((uint32_t)(gn[q] >> 32), (uint32_t)gn[q]);
+                s_inv[wib][q * 32 + lane] = __ddiv_rn(1.0, (double)kk[q]);      // 1.0 / good_alignments.len() as f64
             }
             __syncwarp();
-            const uint32_t cnt = min(32u, hi - base);
+            const uint32_t cnt = min((uint32_t)FX_BATCH, hi - base);
 #pragma unroll 4
             for (uint32_t j = 0; j < cnt; ++j) {
                 const uint2 r = s_rng[wib][j];
@@ -950,6 +961,13 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
         }
         if (cover >= 65536u) atomicOr(&d.st->flags, FL_COUNTER_OVF);
         const unsigned long long ex = exv[i];
+        if (ex == 0 && dlv[i] == 0 && !vp.dbg) {
+            // every covering entry equals the draft base: the only allele with a non-zero count is the draft's own, so
+            // whatever the thresholds say (kept, too_close, low_depth, ...) the emitted base is the original
+            po[i].packed = (orig == '-' ? 0u : 1u) | (orig << 16);
+            tlen += po[i].packed & 0xFFFFu;
+            continue;
+        }
         uint32_t cA = (uint32_t)ex & 0xFFFFu, cC = (uint32_t)(ex >> 16) & 0xFFFFu, cG = (uint32_t)(ex >> 32) & 0xFFFFu,
                  cT = (uint32_t)(ex >> 48) & 0xFFFFu;
         const uint32_t cDel = dlv[i] & 0xFFFFu, n_other = dlv[i] >> 16;
