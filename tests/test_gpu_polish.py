@@ -271,3 +271,12 @@ def test_debug_tsv_synth(ctx, oracle, tmp_path):
     dbg = tmp_path / "debug.tsv"
     assert ctx.polish_files(fa, sams, debug=dbg) == exp["fasta"]
     assert dbg.read_bytes() == exp["debug_tsv"]
+
+
+@pytest.mark.skipif(not os.environ.get("PP_FULL"), reason="set PP_FULL=1 for the BASELINE-size runs")
+def test_depth_1000_parity(ctx, oracle, tmp_path):
+    """BASELINE config 4 in miniature (1000x depth: counter / atomic stress, long fix-up lists), against the oracle."""
+    syn = api.Synth(seed=4, contig_len=200_000, depth=1000)
+    fa, sams = syn.write(tmp_path)
+    exp = oracle.polish(fa, sams)
+    assert ctx.polish_files(fa, sams) == exp["fasta"]
