@@ -36,8 +36,8 @@
 
 #define PP_TILE_SHIFT 7              // depth fix-up tile = 128 positions
 #define PP_TILE (1u << PP_TILE_SHIFT)
-#define SC_THREADS 256               // scatter CTA: one alignment per thread
-#define SC_SEQ_BYTES 24576           // smem window for the block's slice of the sequence pool (4-bit mode)
+#define SC_THREADS 128               // scatter CTA: one alignment per thread
+#define SC_SEQ_BYTES 12288           // smem window for the block's slice of the sequence pool (4-bit mode)
 #define SC_GROUP_SCAN_LIMIT 8192     // alignments of one read group a thread will scan outside its block for k
 #define CL_THREADS 256               // collect CTA
 #define CL_ITEMS 4
