@@ -219,6 +219,8 @@ typedef struct pp_pack pp_pack;
 pp_pack* pp_pack_create(const pp_fasta* f, int careful);
 void pp_pack_free(pp_pack* p);
 int pp_pack_add_sam_file(pp_pack* p, const char* path);                        /* PP_OK / PP_ERR_INPUT / PP_ERR_IO */
+/* big files are parsed by several host threads (same result, same errors); 0 threads = one per hardware thread */
+int pp_pack_set_threads(pp_pack* p, uint32_t n_threads, uint64_t min_chunk_bytes);
 int pp_pack_add_sam_text(pp_pack* p, const char* text, size_t len, const char* name_for_errors);
 /* one logical SAM file fed in chunks of whole lines (a host reading a pipe; the synthetic generator) */
 int pp_pack_stream_begin(pp_pack* p, const char* name_for_errors);

@@ -185,6 +185,11 @@ class Packed:
         if rc != PP_OK:
             raise PolypolishError(rc, lib().pp_pack_error(self.h).decode())
 
+    def set_threads(self, n_threads, min_chunk_bytes=8 << 20):
+        L = lib()
+        L.pp_pack_set_threads.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
+        L.pp_pack_set_threads(self.h, n_threads, min_chunk_bytes)
+
     def add_file(self, path):
         self._check(lib().pp_pack_add_sam_file(self.h, str(path).encode()))
 

@@ -90,6 +90,8 @@ struct pp_pack {
     std::vector<Source> sources;
     bool replaying = false;
     bool no_replay = false;
+    unsigned threads = 0;          // parsing threads for files (0 = hardware)
+    size_t min_chunk = 8u << 20;   // smallest chunk of a file one parsing thread gets
     void* stream = nullptr;        // open streaming file (sam_pack.cpp)
     std::string tmp;
 };

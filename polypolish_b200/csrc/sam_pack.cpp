@@ -6,8 +6,10 @@
 //   get_expanded_cigar :325-346 (validation only: the CIGAR is kept run-length encoded, never expanded)
 //   get_read_seq_from_alignments :311-322 and add_read_seq :161-167 (source sequence of SEQ="*" records)
 // Everything downstream (goodness, k, CIGAR walk, trim, pileup, vote) happens on the device.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 
 #include "pp_internal.h"
 
@@ -58,42 +60,57 @@ struct GroupState {
     std::string_view name;
     uint64_t first_aln = 0, n = 0;   // alignments of the open group
     bool have_src = false;
-    uint32_t src_off = 0;
-    uint16_t src_len = 0;
-    uint8_t src_rev = 0;
+    uint64_t src_aln = 0;            // first record of the group whose SEQ is not "*" (alignment.rs:311-318)
 };
+
+// Closes a read group (process_one_read's text side, alignment.rs:275-295): read id, and for SEQ="*" records the group's
+// source sequence (copy or reverse complement by strand).  Returns false on the reference's "no sequence" error.
+bool finalize_group(pp_pack* P, const GroupState& g, std::string& err) {
+    const uint64_t gid = P->group_name_off.size();
+    if (gid >= 0xFFFFFFFFull) { err = "more than 2^32-1 reads in one call are not supported"; return false; }
+    P->group_name_off.push_back(P->name_pool.size());
+    P->name_pool.append(g.name.data(), g.name.size());
+    P->name_pool.push_back('\0');
+    const bool skipped = P->careful && g.n > 1;   // alignment.rs:277-279
+    if (!g.have_src && !skipped) { err = "no alignments for read " + std::string(g.name) + " contain sequence"; return false; }
+    const uint32_t src_off = g.have_src ? P->seq_off[g.src_aln] : 0;
+    const uint16_t src_len = g.have_src ? P->seq_len[g.src_aln] : 0;
+    const uint8_t src_rev = g.have_src ? (P->flags[g.src_aln] & PP_FLAG_REVERSE) : 0;
+    for (uint64_t a = g.first_aln; a < g.first_aln + g.n; ++a) {
+        P->read_id[a] = (uint32_t)gid;
+        if (P->flags[a] & PP_FLAG_SEQSTAR) {
+            if (g.have_src) {
+                P->seq_off[a] = src_off;
+                P->seq_len[a] = src_len;
+                if ((P->flags[a] & PP_FLAG_REVERSE) != src_rev) P->flags[a] |= PP_FLAG_RC;
+            } else {
+                P->flags[a] |= PP_FLAG_NOSEQ;
+            }
+        }
+    }
+    return true;
+}
+
+struct DeferredGroup { std::string_view name; uint64_t first, n; bool have_src; uint64_t src_aln; };
 
 struct Packer {
     pp_pack* P;
     const std::string& fname;
     GroupState g;
     uint64_t line_count = 0, alignment_count = 0, read_count = 0;
+    std::vector<DeferredGroup>* deferred = nullptr;   // chunk mode: groups are only recorded; the merge closes them
 
     bool fail(int code, const std::string& m) { P->error = m; P->error_code = code; return false; }
 
     bool close_group() {
         if (g.n == 0) return true;
-        read_count++;
-        uint64_t gid = P->group_name_off.size();
-        P->group_name_off.push_back(P->name_pool.size());
-        P->name_pool.append(g.name.data(), g.name.size());
-        P->name_pool.push_back('\0');
-        bool skipped = P->careful && g.n > 1;   // alignment.rs:277-279
-        if (!g.have_src && !skipped)
-            return fail(PP_ERR_INPUT, "no alignments for read " + std::string(g.name) + " contain sequence");
-        for (uint64_t a = g.first_aln; a < g.first_aln + g.n; ++a) {
-            P->read_id[a] = (uint32_t)gid;
-            if (P->flags[a] & PP_FLAG_SEQSTAR) {
-                if (g.have_src) {
-                    P->seq_off[a] = g.src_off;
-                    P->seq_len[a] = g.src_len;
-                    if ((P->flags[a] & PP_FLAG_REVERSE) != g.src_rev) P->flags[a] |= PP_FLAG_RC;
-                } else {
-                    P->flags[a] |= PP_FLAG_NOSEQ;
-                }
-            }
+        if (deferred) {
+            deferred->push_back({g.name, g.first_aln, g.n, g.have_src, g.src_aln});
+        } else {
+            read_count++;
+            std::string err;
+            if (!finalize_group(P, g, err)) return fail(PP_ERR_INPUT, err);
         }
-        if (gid >= 0xFFFFFFFFull) return fail(PP_ERR_INPUT, "more than 2^32-1 reads in one call are not supported");
         g.n = 0;
         g.have_src = false;
         return true;
@@ -235,9 +252,7 @@ struct Packer {
             slen = (uint16_t)seq.size();
             if (!g.have_src) {                          // first record whose SEQ != "*" (alignment.rs:311-318)
                 g.have_src = true;
-                g.src_off = soff;
-                g.src_len = slen;
-                g.src_rev = fl & PP_FLAG_REVERSE;
+                g.src_aln = P->contig.size();
             }
         }
         P->contig.push_back(cidx);
@@ -292,6 +307,126 @@ void clear_arrays(pp_pack* P) {
     P->unknown_ref.clear(); P->files.clear();
 }
 
+
+// ---- parallel parse of one SAM file -----------------------------------------------------------------------------
+// The text is cut into chunks at line starts; each chunk is parsed by its own thread into private arrays with its
+// read groups only RECORDED; the merge then walks the chunks in file order, appends their arrays (rebasing pool
+// offsets), re-applies the reference's grouping rule across every chunk seam (a group continues into the next chunk iff
+// the open name is empty or equals the next record's QNAME, alignment.rs:255) and closes the groups exactly as the
+// sequential path does.  Errors keep file order: the first chunk with a text error ends the file there.
+struct ChunkOut {
+    pp_pack tmp;
+    std::vector<DeferredGroup> groups;
+    uint64_t first_line = 0, n_lines = 0, alignments = 0;
+    bool ok = true;
+};
+
+uint64_t count_lines(const char* p, size_t n) {
+    uint64_t c = 0;
+    const char* e = p + n;
+    while (p < e) { const char* q = (const char*)memchr(p, '\n', (size_t)(e - p)); if (!q) { c++; break; } c++; p = q + 1; }
+    return c;
+}
+
+template <class T> void append_vec(std::vector<T>& dst, const std::vector<T>& src) { dst.insert(dst.end(), src.begin(), src.end()); }
+
+int pack_text_parallel(pp_pack* P, const char* data, size_t n, const std::string& fname, unsigned n_threads, size_t min_chunk) {
+    // chunk boundaries at line starts
+    std::vector<size_t> cut{0};
+    const size_t want = std::max(min_chunk, n / n_threads + 1);
+    while (cut.back() < n) {
+        size_t nxt = cut.back() + want;
+        if (nxt >= n) { cut.push_back(n); break; }
+        const char* q = (const char*)memchr(data + nxt, '\n', n - nxt);
+        cut.push_back(q ? (size_t)(q - data) + 1 : n);
+    }
+    const size_t nc = cut.size() - 1;
+    std::vector<ChunkOut> out(nc);
+    {   // line numbers of chunk starts (error messages carry file line numbers)
+        std::vector<std::thread> th;
+        for (size_t c = 0; c < nc; ++c) th.emplace_back([&, c] { out[c].n_lines = count_lines(data + cut[c], cut[c + 1] - cut[c]); });
+        for (auto& t : th) t.join();
+        uint64_t base = 0;
+        for (size_t c = 0; c < nc; ++c) { out[c].first_line = base; base += out[c].n_lines; }
+    }
+    {
+        std::vector<std::thread> th;
+        for (size_t c = 0; c < nc; ++c) th.emplace_back([&, c] {
+            ChunkOut& o = out[c];
+            o.tmp.fasta = P->fasta; o.tmp.careful = P->careful; o.tmp.seq_bits = P->seq_bits;
+            Packer pk{&o.tmp, fname};
+            pk.deferred = &o.groups;
+            pk.line_count = o.first_line;
+            bool ok = true;
+            pp::for_each_line(data + cut[c], cut[c + 1] - cut[c], [&](std::string_view s) { ok = pk.line(s); return ok; });
+            if (ok) pk.close_group();              // records the chunk's last (possibly still open) group
+            o.ok = ok;
+            o.alignments = pk.alignment_count;
+        });
+        for (auto& t : th) t.join();
+    }
+    // merge in file order
+    GroupState carry;                              // the open group of the stream so far
+    uint64_t reads = 0, alignments = 0;
+    auto close_carry = [&]() -> bool {
+        if (carry.n == 0) return true;
+        reads++;
+        std::string err;
+        if (!finalize_group(P, carry, err)) { P->error = err; P->error_code = PP_ERR_INPUT; return false; }
+        carry.n = 0; carry.have_src = false;
+        return true;
+    };
+    for (size_t c = 0; c < nc; ++c) {
+        ChunkOut& o = out[c];
+        pp_pack& t = o.tmp;
+        const uint64_t aln_base = P->contig.size(), cig_base = P->cigar_ops.size(), blk_base = P->seq_blocks;
+        if (cig_base + t.cigar_ops.size() > 0xFFFFFFFFull) { P->error = "CIGAR pool exceeds 2^32 operations"; P->error_code = PP_ERR_INPUT; return PP_ERR_INPUT; }
+        if (blk_base + t.seq_blocks > 0xFFFFFFFFull) { P->error = "sequence pool exceeds 2^32 blocks"; P->error_code = PP_ERR_INPUT; return PP_ERR_INPUT; }
+        append_vec(P->contig, t.contig); append_vec(P->ref_start, t.ref_start); append_vec(P->read_id, t.read_id);
+        append_vec(P->seq_len, t.seq_len); append_vec(P->n_cigar, t.n_cigar); append_vec(P->nm, t.nm); append_vec(P->flags, t.flags);
+        append_vec(P->cigar_ops, t.cigar_ops);
+        const size_t a0 = P->seq_off.size();
+        append_vec(P->seq_off, t.seq_off); append_vec(P->cigar_off, t.cigar_off);
+        for (size_t a = a0; a < P->seq_off.size(); ++a) {
+            P->cigar_off[a] += (uint32_t)cig_base;
+            if (!(P->flags[a] & PP_FLAG_SEQSTAR)) P->seq_off[a] += (uint32_t)blk_base;
+        }
+        const size_t pool0 = P->seq_pool.n;
+        P->seq_pool.resize_zero(pool0 + t.seq_pool.n);
+        if (t.seq_pool.n) memcpy(P->seq_pool.p + pool0, t.seq_pool.p, t.seq_pool.n);
+        P->seq_blocks += t.seq_blocks;
+        for (auto& kv : t.unknown_ref) P->unknown_ref.emplace(kv.first + aln_base, kv.second);
+        if (t.need8) P->need8 = true;
+        alignments += o.alignments;
+        for (size_t gi = 0; gi < o.groups.size(); ++gi) {
+            const DeferredGroup& dg = o.groups[gi];
+            const bool joins = carry.n > 0 && gi == 0 && (carry.name_empty || carry.name == dg.name);   // alignment.rs:255
+            if (!joins && !close_carry()) return P->error_code;
+            if (carry.n == 0) { carry.first_aln = dg.first + aln_base; carry.have_src = false; }
+            // (a joined group is contiguous: chunk arrays are appended back to back)
+            if (!carry.have_src && dg.have_src) { carry.have_src = true; carry.src_aln = dg.src_aln + aln_base; }
+            carry.n += dg.n;
+            carry.name = dg.name;
+            carry.name_empty = dg.name.empty();
+            // inside a chunk every recorded group but the last is already complete
+            if (gi + 1 < o.groups.size() && !close_carry()) return P->error_code;
+        }
+        if (!o.ok) { P->error = t.error; P->error_code = t.error_code; return P->error_code; }
+    }
+    if (alignments == 0) {     // alignment.rs:268-270
+        P->error = "no alignments in \"" + fname + "\"";
+        P->error_code = PP_ERR_INPUT;
+        return PP_ERR_INPUT;
+    }
+    if (!close_carry()) return P->error_code;
+    pp_pack::FileStat st;
+    st.name = fname;
+    st.alignments = alignments;
+    st.reads = reads;
+    P->files.push_back(st);
+    return PP_OK;
+}
+
 }  // namespace
 
 extern "C" pp_pack* pp_pack_create(const pp_fasta* f, int careful) {
@@ -313,7 +448,17 @@ extern "C" int pp_pack_add_sam_file(pp_pack* P, const char* path) {
         return PP_ERR_IO;
     }
     if (!P->replaying) P->sources.push_back({true, path, std::string()});
+    unsigned nt = P->threads ? P->threads : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (nt > 1 && data.size() >= 2 * P->min_chunk) return pack_text_parallel(P, data.data(), data.size(), path, nt, P->min_chunk);
     return pack_text(P, data.data(), data.size(), path);
+}
+
+// Parsing threads for pp_pack_add_sam_file (0 = one per hardware thread, at most 16) and the smallest chunk a thread gets.
+extern "C" int pp_pack_set_threads(pp_pack* P, uint32_t n_threads, uint64_t min_chunk_bytes) {
+    if (!P) return PP_ERR_ARG;
+    P->threads = n_threads;
+    P->min_chunk = min_chunk_bytes ? (size_t)min_chunk_bytes : (size_t)(8u << 20);
+    return PP_OK;
 }
 
 extern "C" int pp_pack_add_sam_text(pp_pack* P, const char* text, size_t len, const char* name_for_errors) {

@@ -183,3 +183,50 @@ def test_synth_deterministic_and_stream_equals_file(tmp_path):
     n1 = [l.split("\t")[0] for l in open(sams1[0]) if not l.startswith("@")]
     n2 = [l.split("\t")[0] for l in open(sams1[1]) if not l.startswith("@")]
     assert list(dict.fromkeys(n1)) == list(dict.fromkeys(n2))
+
+
+def _pack_with(fa, sams, threads, chunk, careful=False):
+    f = pp.load_fasta(fa)
+    p = api.Packed(f, careful)
+    p.set_threads(threads, chunk)
+    for s in sams:
+        p.add_file(s)
+    p.finish()
+    return f, p
+
+
+@pytest.mark.parametrize("seed", range(40, 56))
+def test_parallel_pack_equals_sequential(oracle, tmp_path, seed):
+    """The multi-threaded file parser (chunks of ~2 KB here, so nearly every read group straddles a seam somewhere)
+    must give exactly the sequential arrays, and the same error text on bad input."""
+    case = fuzzgen.make_case(seed, exotic=0.5 if seed % 4 == 0 else 0.0, multimap=0.6)
+    fa, sams = case.write(tmp_path)
+    careful = case.opts["careful"]
+    f1, p1 = _pack_with(fa, sams, 1, 1 << 30, careful)
+    f2, p2 = _pack_with(fa, sams, 4, 2048, careful)
+    a1, a2 = p1.arrays(), p2.arrays()
+    for k, v in a1.items():
+        if isinstance(v, np.ndarray):
+            assert np.array_equal(v, a2[k]), k
+        else:
+            assert v == a2[k], k
+    for i in range(0, len(a1["contig"]), 17):
+        assert p1.read_name(i) == p2.read_name(i)
+
+
+@pytest.mark.parametrize("sam", BAD_SAMS)
+def test_parallel_pack_errors(oracle, tmp_path, sam):
+    fa = tmp_path / "a.fasta"
+    fa.write_text(">c1\nAAAAAAAAAAAAAAAAAAAA\n")
+    good = "".join(f"g{i}\t0\tc1\t1\t60\t4M\t*\t0\t0\tACGT\tIIII\tNM:i:0\n" for i in range(200))
+    s = tmp_path / "s0.sam"
+    s.write_text(good + sam + good if "no alignments" not in sam and "@HD" not in sam else sam)
+    with pytest.raises(Exception) as eo:
+        oracle.polish(fa, [s])
+    f = pp.load_fasta(fa)
+    p = api.Packed(f, False)
+    p.set_threads(4, 512)
+    with pytest.raises(pp.PolypolishError) as ei:
+        p.add_file(s)
+        p.finish()
+    assert ei.value.msg == eo.value.msg
