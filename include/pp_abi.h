@@ -235,6 +235,40 @@ int pp_pack_cigar_string(const pp_pack* p, uint64_t aln, char* out, size_t cap);
 /* per file: aligned records and read groups (the stderr line of polish.rs:117-119) */
 int pp_pack_file_stats(const pp_pack* p, uint32_t file, uint64_t* alignments, uint64_t* reads);
 
+/* ------------------------------------------------------------------------------------------------------
+ * SAM text -> packed alignments ON THE DEVICE.  Same result as pp_pack_* + pp_dataset_upload, bit for bit
+ * (Alignment::new alignment.rs:49-98, get_expanded_cigar :325-346, the grouping of add_to_pileup :238-263 and the
+ * SEQ="*" handling of process_one_read :275-295), but the parse runs in HBM: the host only streams the file's bytes.
+ *   pp_tok_begin(ctx, assembly, careful, 4)  ->  pp_tok_add_file / pp_tok_add_text per SAM, in order  ->  pp_tok_finish
+ *   ->  pp_polish_resident.
+ * Return values beyond PP_OK / PP_ERR_*:
+ *   PP_TOK_HOST   the text holds something the device tokeniser leaves to the host packer (a malformed line, a read group
+ *                 without SEQ, an empty file, a size limit): run pp_pack_* on the same input, which yields the result
+ *                 or the reference's own error message.  Not an error by itself.
+ *   PP_TOK_NEED8  a SEQ character outside "ACMGRSVTWYHKDBN" while seq_bits == 4: start again with seq_bits = 8.
+ * After either, the construction is abandoned (pp_tok_begin starts a new one).
+ * ---------------------------------------------------------------------------------------------------- */
+#define PP_TOK_HOST 1
+#define PP_TOK_NEED8 2
+typedef struct {
+  uint64_t lines, alignments, reads;   /* of this file (alignment.rs:266-271's log line) */
+  float h2d_ms;                        /* wall time of getting the text into HBM (file read + pinned staging + PCIe) */
+  float device_ms;                     /* CUDA-event time of the tokeniser kernels */
+  uint32_t launches;
+} pp_tok_stats;
+int pp_tok_begin(pp_ctx* ctx, const pp_fasta* assembly, int careful, int seq_bits /* 4 | 8 */);
+int pp_tok_add_text(pp_ctx* ctx, const char* text, size_t len, pp_tok_stats* stats /* may be NULL */);
+int pp_tok_add_file(pp_ctx* ctx, const char* path, pp_tok_stats* stats /* may be NULL */);
+int pp_tok_finish(pp_ctx* ctx);        /* the tokenised alignments + the assembly become the resident dataset */
+/* Which parser pp_polish_files uses for its SAM files: 0 (default) the device tokeniser, with the host packer taking over
+ * on PP_TOK_HOST and for --debug / multi-GPU runs; 1 the host packer only.  Both give the same bytes. */
+int pp_set_parser(pp_ctx* ctx, int mode);
+int pp_get_parser(const pp_ctx* ctx);
+/* The resident dataset read back (tests: equality with the host packer's arrays).  pp_dataset_sizes fills the counts of
+ * `out`; pp_dataset_download copies into the caller's arrays (same counts; NULL pointers are skipped). */
+int pp_dataset_sizes(pp_ctx* ctx, pp_alignments* out);
+int pp_dataset_download(pp_ctx* ctx, const pp_alignments* into);
+
 /* Contig sharding across GPUs (one pp_ctx per GPU, no collective): whole contigs per shard, each with its alignments
  * in SAM order; reads that also map to another shard's contigs keep their k through PP_FLAG_GHOST records. */
 typedef struct pp_shards pp_shards;

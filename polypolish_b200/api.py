@@ -73,6 +73,17 @@ class FilterResult(C.Structure):
                 ("orientation", C.c_int32), ("pairs", C.c_uint64 * 4), ("n_pass", C.c_uint64), ("timing", Timing)]
 
 
+class TokStats(C.Structure):
+    _fields_ = [("lines", C.c_uint64), ("alignments", C.c_uint64), ("reads", C.c_uint64), ("h2d_ms", C.c_float),
+                ("device_ms", C.c_float), ("launches", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+PP_TOK_HOST = 1
+PP_TOK_NEED8 = 2
+
 _lib = None
 
 
@@ -122,6 +133,14 @@ def lib():
     L.pp_polish_files.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(PolishParams),
                                   C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]
     L.pp_free.argtypes = [C.c_void_p]
+    L.pp_tok_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.pp_tok_add_text.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(TokStats)]
+    L.pp_tok_add_file.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(TokStats)]
+    L.pp_tok_finish.argtypes = [C.c_void_p]
+    L.pp_set_parser.argtypes = [C.c_void_p, C.c_int]
+    L.pp_get_parser.argtypes = [C.c_void_p]
+    L.pp_dataset_sizes.argtypes = [C.c_void_p, C.POINTER(Alignments)]
+    L.pp_dataset_download.argtypes = [C.c_void_p, C.POINTER(Alignments)]
     if hasattr(L, "pp_filter"):
         L.pp_filter.argtypes = [C.c_void_p, C.POINTER(FilterMate), C.POINTER(FilterMate), C.POINTER(FilterParams),
                                 C.POINTER(FilterResult)]
@@ -328,6 +347,58 @@ class Context:
         if not fetch:
             return dict(n_aln_used=res.n_aln_used, out_len=res.out_len, timing=res.timing.as_dict())
         return self._finish(res, keep, self._nc)
+
+    # ---- device SAM tokeniser (tok_kernels.cu) ------------------------------------------------------------------
+    def tokenise(self, fasta, sources, careful=False, seq_bits=4):
+        """SAM texts (bytes) or files (paths) -> resident dataset, parsed on the device.  Returns (rc, [stats]) where rc is
+        PP_OK, PP_TOK_HOST or PP_TOK_NEED8; errors raise."""
+        L = lib()
+        rc = L.pp_tok_begin(self.h, fasta.h, int(bool(careful)), seq_bits)
+        if rc != PP_OK:
+            raise self._err(rc)
+        stats = []
+        for src in sources:
+            st = TokStats()
+            if isinstance(src, (bytes, bytearray)):
+                rc = L.pp_tok_add_text(self.h, bytes(src), len(src), C.byref(st))
+            else:
+                rc = L.pp_tok_add_file(self.h, str(src).encode(), C.byref(st))
+            if rc < 0:
+                raise self._err(rc)
+            stats.append(st.as_dict())
+            if rc != PP_OK:
+                return rc, stats
+        rc = L.pp_tok_finish(self.h)
+        if rc != PP_OK:
+            raise self._err(rc)
+        self._nc = fasta.view.n_contigs
+        self._G = int(fasta.off[-1])
+        return PP_OK, stats
+
+    def dataset_arrays(self):
+        """The resident dataset copied back to the host (same keys as Packed.arrays())."""
+        L = lib()
+        v = Alignments()
+        rc = L.pp_dataset_sizes(self.h, C.byref(v))
+        if rc != PP_OK:
+            raise self._err(rc)
+        n = v.n_aln
+        a = dict(contig=np.zeros(n, np.uint32), ref_start=np.zeros(n, np.uint32), read_id=np.zeros(n, np.uint32),
+                 seq_off=np.zeros(n, np.uint32), seq_len=np.zeros(n, np.uint16), cigar_off=np.zeros(n, np.uint32),
+                 n_cigar=np.zeros(n, np.uint16), nm=np.zeros(n, np.uint32), flags=np.zeros(n, np.uint8),
+                 cigar_ops=np.zeros(v.n_cigar_ops, np.uint32), seq_pool=np.zeros(v.seq_pool_bytes, np.uint8))
+        for k, arr in a.items():
+            setattr(v, k, arr.ctypes.data)
+        rc = L.pp_dataset_download(self.h, C.byref(v))
+        if rc != PP_OK:
+            raise self._err(rc)
+        a["seq_bits"] = v.seq_bits
+        a["n_reads"] = v.n_reads
+        return a
+
+    def set_parser(self, mode):
+        """0: pp_polish_files parses SAM on the device (default); 1: on the host."""
+        lib().pp_set_parser(self.h, int(mode))
 
     # ---- file level (what the CLI does) ----------------------------------------------------------------------
     def polish_files(self, assembly, sams, debug=None, verbose=False, **opts):

@@ -17,7 +17,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function,-ffp-contract=off",
           "-fmad=false"]   # IEEE double semantics: no FMA contraction anywhere near the vote
 
-LIB_SOURCES = ["polish_kernels.cu", "filter_kernels.cu", "fasta.cpp", "sam_pack.cpp", "filter_pack.cpp",
+LIB_SOURCES = ["polish_kernels.cu", "filter_kernels.cu", "tok_kernels.cu", "fasta.cpp", "sam_pack.cpp", "filter_pack.cpp",
                "host_api.cpp", "synth.cpp", "shard.cpp"]
 CLI_SOURCES = ["cli_main.cpp"]
 
@@ -26,7 +26,8 @@ def _stale(target, sources):
     if not os.path.exists(target):
         return True
     t = os.path.getmtime(target)
-    deps = list(sources) + [os.path.join(CSRC, "pp_internal.h"), os.path.join(CSRC, "nib_utils.h"), os.path.join(ROOT, "include", "pp_abi.h"),
+    deps = list(sources) + [os.path.join(CSRC, "pp_internal.h"), os.path.join(CSRC, "nib_utils.h"), os.path.join(CSRC, "pp_ctx.cuh"),
+                            os.path.join(CSRC, "tok_line.h"), os.path.join(CSRC, "tok_table.h"), os.path.join(ROOT, "include", "pp_abi.h"),
                             os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 

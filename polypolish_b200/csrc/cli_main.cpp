@@ -5,7 +5,8 @@
 //   polypolish polish [--debug F] [-i|--fraction_invalid 0.2] [-v|--fraction_valid 0.5] [-m|--max_errors 10]
 //                     [-d|--min_depth 5] [--careful] <ASSEMBLY> [SAM]...
 // Polished FASTA on stdout, log on stderr, "Error: <msg>" + exit 1 on user errors (misc.rs:29-33).
-// Additive flags: --device N (first GPU), --gpus N (polish: contigs shard across N GPUs), --quiet.  All compute happens in libpolypolish_b200.so on the GPU.
+// Additive flags: --device N (first GPU), --gpus N (polish: contigs shard across N GPUs), --quiet, --host-parse (polish: parse the
+// SAM text on the host instead of on the device; same output).  All compute happens in libpolypolish_b200.so on the GPU.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,7 +44,7 @@ static void help() {
     puts("\npolypolish filter --in1 <IN1> --in2 <IN2> --out1 <OUT1> --out2 <OUT2> [--orientation <auto>] [--low <0.1>] [--high <99.9>]");
     puts("polypolish polish [--debug <DEBUG>] [-i|--fraction_invalid <0.2>] [-v|--fraction_valid <0.5>] [-m|--max_errors <10>]");
     puts("                  [-d|--min_depth <5>] [--careful] <ASSEMBLY> [SAM]...");
-    puts("Additive: --device <N> (first GPU, default 0), --gpus <N> (polish: shard contigs over N GPUs), --quiet");
+    puts("Additive: --device <N> (first GPU, default 0), --gpus <N> (polish: shard contigs over N GPUs), --quiet, --host-parse");
 }
 
 static double parse_f64(const char* flag, const char* s) {
@@ -66,7 +67,7 @@ int main(int argc, char** argv) {
     if (cmd == "-h" || cmd == "--help") { help(); return 0; }
     if (cmd == "-V" || cmd == "--version") { puts("Polypolish v0.6.1"); return 0; }
     int device = 0, gpus = 1;
-    bool quiet = false;
+    bool quiet = false, host_parse = false;
     auto need = [&](int& i, const char* flag) -> const char* {
         if (i + 1 >= argc) usage_error(std::string("a value is required for '") + flag + "' but none was supplied");
         return argv[++i];
@@ -88,6 +89,7 @@ int main(int argc, char** argv) {
             else if (a == "--device") device = (int)parse_u32("--device", need(i, "--device"));
             else if (a == "--gpus") gpus = (int)parse_u32("--gpus", need(i, "--gpus"));
             else if (a == "--quiet") quiet = true;
+            else if (a == "--host-parse") host_parse = true;
             else if (a.size() > 1 && a[0] == '-' && a != "-") usage_error("unexpected argument '" + a + "' found");
             else pos.push_back(a);
         }
@@ -96,6 +98,7 @@ int main(int argc, char** argv) {
         std::vector<pp_ctx*> ctxs(gpus, nullptr);
         for (int g = 0; g < gpus; ++g)
             if (pp_create(device + g, &ctxs[g]) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
+        if (host_parse) pp_set_parser(ctxs[0], 1);
         std::vector<const char*> sams;
         for (size_t i = 1; i < pos.size(); ++i) sams.push_back(pos[i].c_str());
         char* out = nullptr;

@@ -129,6 +129,7 @@ struct ShardJob {
     pp_contigs contigs;
     pp_alignments alns;
     const uint32_t* contig_map = nullptr;
+    bool resident = false;               // the dataset is already on the device (device tokeniser)
     std::vector<uint64_t> out_off, changed, zero;
     std::vector<uint8_t> bases;
     pp_polish_result res;
@@ -151,11 +152,39 @@ static void run_shard(ShardJob* j, const pp_polish_params* prm) {
         j->res.out_cap = cap;
         j->res.changed = j->changed.data();
         j->res.zero_depth = j->zero.data();
-        j->rc = pp_polish(j->ctx, &j->contigs, &j->alns, prm, &j->res);
+        j->rc = j->resident ? pp_polish_resident(j->ctx, prm, &j->res) : pp_polish(j->ctx, &j->contigs, &j->alns, prm, &j->res);
         if (j->rc == PP_ERR_ARG && j->res.out_len > cap) { cap = j->res.out_len; continue; }
         break;
     }
     if (j->rc != PP_OK) j->err = pp_last_error(j->ctx);
+}
+
+// SAM files -> resident dataset through the device tokeniser (tok_kernels.cu).  PP_OK, PP_TOK_HOST (the host packer must
+// look at the text), or an error.  `log` collects the per-file lines add_to_pileup prints (alignment.rs:266-271).
+static int tokenise_files(pp_ctx* ctx, const pp_fasta* fa, const char* const* sams, int n_sams, bool careful, std::string& log,
+                          std::string& timing, uint64_t* n_aln) {
+    int bits = 4;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        log.clear(); timing.clear();
+        *n_aln = 0;
+        int rc = pp_tok_begin(ctx, fa, careful ? 1 : 0, bits);
+        for (int i = 0; i < n_sams && rc == PP_OK; ++i) {
+            pp_tok_stats st;
+            rc = pp_tok_add_file(ctx, sams[i], &st);
+            if (rc != PP_OK) break;
+            *n_aln += st.alignments;
+            log += std::string(sams[i]) + ": " + fmt_thousands(st.alignments) + " alignments from " + fmt_thousands(st.reads) + " reads\n";
+            char tmp[256];
+            snprintf(tmp, sizeof tmp, "SAM tokeniser %s: %s lines, text to HBM %.3f ms, %u kernels %.3f ms\n", sams[i], fmt_thousands(st.lines).c_str(),
+                     st.h2d_ms, st.launches, st.device_ms);
+            timing += tmp;
+        }
+        if (rc == PP_TOK_NEED8 && bits == 4) { bits = 8; continue; }
+        if (rc == PP_TOK_NEED8) rc = PP_TOK_HOST;
+        if (rc == PP_OK) rc = pp_tok_finish(ctx);
+        return rc;
+    }
+    return PP_TOK_HOST;
 }
 
 // polish::polish (polish.rs:26-38) over one or several GPUs (contigs shard across them).
@@ -193,40 +222,71 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
         fprintf(stderr, "\nLoading alignments\n");
     }
 
-    pp_pack* pk = pp_pack_create(fa, prm->careful);
-    int rc = PP_OK;
-    for (int i = 0; i < n_sams && rc == PP_OK; ++i) {
-        rc = pp_pack_add_sam_file(pk, sams[i]);
-        if (rc == PP_OK && verbose) {
-            uint64_t na = 0, nr = 0;
-            pp_pack_file_stats(pk, (uint32_t)i, &na, &nr);
-            fprintf(stderr, "%s: %s alignments from %s reads\n", sams[i], fmt_thousands(na).c_str(), fmt_thousands(nr).c_str());
-        }
-    }
-    pp_alignments alns;
-    if (rc == PP_OK) rc = pp_pack_finish(pk, &alns);
-    if (rc != PP_OK) {
-        rc = pp_ctx_fail(ctx, rc, pp_pack_error(pk));
-        pp_pack_free(pk);
-        pp_fasta_free(fa);
-        return rc;
-    }
-
     // one job per GPU; with one GPU the job is the whole assembly
     const uint32_t n_shards = debug ? 1u : (uint32_t)std::max(1, std::min<int>(n_ctx, (int)contigs.n_contigs));   // the debug TSV is written from one GPU
-    if (debug) pp_polish_set_debug(ctx, 1);
-    pp_shards* shards = nullptr;
     std::vector<ShardJob> jobs(n_shards);
-    if (n_shards == 1) {
-        jobs[0].ctx = ctx; jobs[0].contigs = contigs; jobs[0].alns = alns;
-    } else {
-        shards = pp_shards_build(&contigs, &alns, n_shards);
-        for (uint32_t s = 0; s < n_shards; ++s) {
-            jobs[s].ctx = ctxs[s];
-            pp_shards_get(shards, s, &jobs[s].contigs, &jobs[s].alns, &jobs[s].contig_map, nullptr);
+    int rc = PP_OK;
+    pp_alignments alns;
+    memset(&alns, 0, sizeof alns);
+    pp_pack* pk = nullptr;
+    bool resident = false;
+    std::string tok_timing;
+    if (n_shards == 1 && !debug && n_sams > 0 && pp_get_parser(ctx) == 0) {
+        // Fast path: the SAM text is parsed in HBM.  Anything unusual (PP_TOK_HOST, or a data error the polish kernels raise,
+        // whose message needs read / reference names) is handed to the host packer below, which decides.
+        std::string log;
+        uint64_t n_aln = 0;
+        rc = tokenise_files(ctx, fa, sams, n_sams, prm->careful != 0, log, tok_timing, &n_aln);
+        if (rc == PP_OK) {
+            jobs[0].ctx = ctx; jobs[0].contigs = contigs; jobs[0].resident = true; jobs[0].alns.n_aln = n_aln;
+            run_shard(&jobs[0], prm);
+            if (jobs[0].rc == PP_OK) {
+                resident = true;
+                alns.n_aln = n_aln;
+                if (verbose) fputs(log.c_str(), stderr);
+            } else if (jobs[0].rc != PP_ERR_INPUT) {
+                rc = pp_ctx_fail(ctx, jobs[0].rc, jobs[0].err.c_str());
+                pp_fasta_free(fa);
+                return rc;
+            }
+        } else if (rc != PP_TOK_HOST) {
+            pp_fasta_free(fa);
+            return rc;
+        }
+        rc = PP_OK;
+    }
+    if (!resident) {
+        jobs[0] = ShardJob();
+        pk = pp_pack_create(fa, prm->careful);
+        for (int i = 0; i < n_sams && rc == PP_OK; ++i) {
+            rc = pp_pack_add_sam_file(pk, sams[i]);
+            if (rc == PP_OK && verbose) {
+                uint64_t na = 0, nr = 0;
+                pp_pack_file_stats(pk, (uint32_t)i, &na, &nr);
+                fprintf(stderr, "%s: %s alignments from %s reads\n", sams[i], fmt_thousands(na).c_str(), fmt_thousands(nr).c_str());
+            }
+        }
+        if (rc == PP_OK) rc = pp_pack_finish(pk, &alns);
+        if (rc != PP_OK) {
+            rc = pp_ctx_fail(ctx, rc, pp_pack_error(pk));
+            pp_pack_free(pk);
+            pp_fasta_free(fa);
+            return rc;
         }
     }
-    {
+
+    if (debug) pp_polish_set_debug(ctx, 1);
+    pp_shards* shards = nullptr;
+    if (!resident) {
+        if (n_shards == 1) {
+            jobs[0].ctx = ctx; jobs[0].contigs = contigs; jobs[0].alns = alns;
+        } else {
+            shards = pp_shards_build(&contigs, &alns, n_shards);
+            for (uint32_t s = 0; s < n_shards; ++s) {
+                jobs[s].ctx = ctxs[s];
+                pp_shards_get(shards, s, &jobs[s].contigs, &jobs[s].alns, &jobs[s].contig_map, nullptr);
+            }
+        }
         std::vector<std::thread> th;
         for (uint32_t s = 1; s < n_shards; ++s) th.emplace_back(run_shard, &jobs[s], prm);
         run_shard(&jobs[0], prm);
@@ -263,7 +323,7 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     }
     if (rc != PP_OK) {
         if (shards) pp_shards_free(shards);
-        pp_pack_free(pk);
+        if (pk) pp_pack_free(pk);
         pp_fasta_free(fa);
         return rc;
     }
@@ -303,6 +363,7 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
         }
     }
     if (verbose) {
+        fputs(tok_timing.c_str(), stderr);
         for (uint32_t s = 0; s < n_shards; ++s) {
             const pp_timing& t = jobs[s].res.timing;
             fprintf(stderr, "GPU job %u: %u contigs, %s alignments; device path %.3f ms (h2d %.3f, scatter %.3f, fix-up %.3f, vote %.3f, compact %.3f, d2h %.3f), %u kernels\n",
@@ -312,7 +373,7 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     }
     char* buf = (char*)malloc(out.size() + 1);
     if (shards) pp_shards_free(shards);
-    pp_pack_free(pk);
+    if (pk) pp_pack_free(pk);
     pp_fasta_free(fa);
     if (!buf) return pp_ctx_fail(ctx, PP_ERR_NOMEM, "out of memory");
     memcpy(buf, out.data(), out.size());

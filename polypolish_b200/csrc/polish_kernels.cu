@@ -33,6 +33,7 @@
 
 #include "nib_utils.h"
 #include "pp_internal.h"
+#include "pp_ctx.cuh"
 
 #define PP_TILE_SHIFT 7              // depth fix-up tile = 128 positions
 #define PP_TILE (1u << PP_TILE_SHIFT)
@@ -1111,57 +1112,7 @@ __global__ void __launch_bounds__(VT_THREADS) k_compact(DevData d, VoteParams vp
 // ------------------------------------------------------------------------------------------------------
 // host side: context, buffers, entry points
 // ------------------------------------------------------------------------------------------------------
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T* as() const { return (T*)p; }
-};
-
-enum { B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL,
-       B_DRAFT, B_CTGOFF, B_NIB, B_ZEROPOOL, B_DEPTHFIX, B_RECGN, B_RECK, B_NODES, B_FIXKEY2, B_FIXVAL2, B_CUBTMP, B_OUT,
-       B_OUTOFF, B_DEBUG, B_AGG1, B_INC1, B_AGGC, B_INCC, B_RES, B_RECAT, B_CHUNKDELTA, B_PARAMS, B_SCRATCH, B_COUNT };
-
-struct pp_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    DevBuf b[B_COUNT];
-    cudaEvent_t ev[PP_N_STAGES + 4] = {};
-    DevStatus* h_status = nullptr;        // pinned
-    DevParams* h_params = nullptr;        // pinned
-    bool have_ds = false;
-    // dataset facts
-    uint64_t n_aln = 0, n_reads = 0, n_ops = 0, seq_bytes = 0, G = 0;
-    uint32_t n_contigs = 0, seq_bits = 4;
-    int sm_count = 148;
-    size_t l2_persist_max = 0, l2_window_max = 0;
-    uint32_t launches = 0;
-    // sizes that adapt when a call overflows them (kept across calls on the same dataset)
-    uint32_t node_cap = 0, fix_cap = 0;
-    uint64_t out_cap = 0;
-    bool global_k = false;
-    bool debug_on = false, have_debug = false;
-    const uint32_t* last_head = nullptr;
-    uint32_t last_nodes = 0;
-
-    int fail(int code, const std::string& m) { err = m; return code; }
-    int fail_cuda(cudaError_t e, const char* what, int line) {
-        err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what + " (polish_kernels.cu:" + std::to_string(line) + ")";
-        return PP_ERR_CUDA;
-    }
-};
-
-#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return ctx->fail_cuda(e_, #x, __LINE__); } while (0)
+// (DevBuf, the buffer ids and pp_ctx live in pp_ctx.cuh, shared with tok_kernels.cu)
 
 static void init_comp_table(uint8_t* t) {
     for (int i = 0; i < 256; ++i) t[i] = 'N';
@@ -1209,6 +1160,7 @@ extern "C" void pp_destroy(pp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pp_tok_release(ctx);
     for (auto& b : ctx->b) b.release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -1241,6 +1193,31 @@ static int upload(pp_ctx* ctx, int which, const T* src, size_t n, size_t pad_byt
     return PP_OK;
 }
 
+// Draft bases + contig offsets onto the device (shared by pp_dataset_upload and the SAM tokeniser).
+int pp_ctx_upload_contigs(pp_ctx* ctx, const pp_contigs* c) {
+    if (!c || !c->off || !c->bases || c->n_contigs == 0) return ctx->fail(PP_ERR_ARG, "null or empty contigs");
+    const uint64_t G = c->off[c->n_contigs];
+    if (G == 0 || G >= 0xFFFFFFFFull - 2 * VT_CHUNK) return ctx->fail(PP_ERR_ARG, "total assembly length must be in [1, 2^32-4096)");
+    int rc;
+    if ((rc = upload(ctx, B_DRAFT, c->bases, G, VT_CHUNK + 256))) return rc;
+    if ((rc = upload(ctx, B_CTGOFF, c->off, (size_t)c->n_contigs + 1))) return rc;
+    ctx->G = G; ctx->n_contigs = c->n_contigs;
+    return PP_OK;
+}
+
+// The alignment arrays in ctx->b[B_CONTIG..B_SEQPOOL] become the resident dataset.
+int pp_ctx_commit_dataset(pp_ctx* ctx, uint64_t n_aln, uint64_t n_reads, uint64_t n_ops, uint64_t seq_bytes, uint32_t seq_bits) {
+    if (n_aln >= 0xFFFFFFFFull - 2 * CL_CHUNK) return ctx->fail(PP_ERR_ARG, "more than 2^32-2048 alignments");
+    ctx->n_aln = n_aln; ctx->n_reads = n_reads; ctx->n_ops = n_ops; ctx->seq_bytes = seq_bytes; ctx->seq_bits = seq_bits;
+    // first guesses; a call that overflows one of them grows it and repeats itself
+    ctx->node_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, n_aln / 8 + ctx->G / 64));
+    ctx->fix_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, n_aln / 4));
+    ctx->out_cap = ctx->G + ctx->G / 16 + (1u << 20);
+    ctx->global_k = false;
+    ctx->have_ds = true;
+    return PP_OK;
+}
+
 extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alignments* a) {
     if (!ctx) return PP_ERR_ARG;
     if (!c || !a || !c->off || !c->bases || c->n_contigs == 0) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: null or empty contigs");
@@ -1248,8 +1225,6 @@ extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alig
                      !a->n_cigar || !a->nm || !a->flags || !a->cigar_ops))
         return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: null alignment array");
     if (a->seq_bits != 4 && a->seq_bits != 8) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: seq_bits must be 4 or 8");
-    const uint64_t G = c->off[c->n_contigs];
-    if (G == 0 || G >= 0xFFFFFFFFull - 2 * VT_CHUNK) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: total assembly length must be in [1, 2^32-4096)");
     if (a->n_aln >= 0xFFFFFFFFull - 2 * CL_CHUNK) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: more than 2^32-2048 alignments");
     CK(cudaSetDevice(ctx->device));
     ctx->have_ds = false;
@@ -1265,18 +1240,9 @@ extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alig
     if ((rc = upload(ctx, B_FLAGS, a->flags, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_CIGOPS, a->cigar_ops, a->n_cigar_ops))) return rc;
     if ((rc = upload(ctx, B_SEQPOOL, a->seq_pool, a->seq_pool_bytes, 256))) return rc;
-    if ((rc = upload(ctx, B_DRAFT, c->bases, G, VT_CHUNK + 256))) return rc;
-    if ((rc = upload(ctx, B_CTGOFF, c->off, (size_t)c->n_contigs + 1))) return rc;
+    if ((rc = pp_ctx_upload_contigs(ctx, c))) { ctx->err = "pp_dataset_upload: " + ctx->err; return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->n_aln = a->n_aln; ctx->n_reads = a->n_reads; ctx->n_ops = a->n_cigar_ops; ctx->seq_bytes = a->seq_pool_bytes;
-    ctx->seq_bits = a->seq_bits; ctx->G = G; ctx->n_contigs = c->n_contigs;
-    // first guesses; a call that overflows one of them grows it and repeats itself
-    ctx->node_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, a->n_aln / 8 + G / 64));
-    ctx->fix_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, a->n_aln / 4));
-    ctx->out_cap = G + G / 16 + (1u << 20);
-    ctx->global_k = false;
-    ctx->have_ds = true;
-    return PP_OK;
+    return pp_ctx_commit_dataset(ctx, a->n_aln, a->n_reads, a->n_cigar_ops, a->seq_pool_bytes, a->seq_bits);
 }
 
 static const char* err_text(unsigned code) {

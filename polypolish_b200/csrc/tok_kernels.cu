@@ -1,0 +1,580 @@
+// tok_kernels.cu — SAM text -> packed alignments ON THE DEVICE ("GPU SAM tokeniser / packer").
+//
+// The text of one SAM file is streamed into HBM (pinned double buffers, several reader threads) and turned into exactly the
+// arrays the host packer (sam_pack.cpp) would have produced, so that `polypolish polish` spends its time on PCIe instead
+// of on a host parse:
+//
+//   k_tok_count   newlines per 16 KiB tile                                   text read once      (HBM-bound)
+//   (cub scan)    tile offsets
+//   k_tok_index   line starts                                                text read once
+//   k_tok_parse   one thread per line: columns, FLAG/POS/NM/ZP, CIGAR check, RNAME -> contig     text read once
+//   (cub scans)   alignment index, CIGAR-pool offset, sequence-pool offset of every line
+//   k_tok_emit    one thread per aligned line: record arrays, CIGAR ops, 4-bit (or 8-bit) bases   CIGAR+SEQ read again
+//   k_tok_heads   one thread per alignment: does it open a read group (QNAME compare with its predecessor)
+//   (cub scan)    read ids
+//   k_tok_groups  one thread per group head: SEQ="*" records take the group's source sequence
+//
+// Per-item logic lives in tok_line.h (host+device, CPU-tested against the host packer).  The host packer stays the
+// authority on everything unusual: a malformed line, a limit, a group without sequence make the call return PP_TOK_HOST and
+// the caller runs pp_pack_* on the same text, which yields the result or the reference's own error message
+// (alignment.rs:49-98, 225-346).
+#include <cuda_runtime.h>
+
+#include <cub/block/block_reduce.cuh>
+#include <cub/block/block_scan.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "pp_ctx.cuh"
+#include "tok_line.h"
+#include "tok_table.h"
+
+namespace {
+
+constexpr int TK_TILE = 16384;        // bytes of text per CTA in the newline passes
+constexpr int TK_THREADS = 256;
+constexpr int TK_LINE_THREADS = 128;  // threads (= lines) per CTA in the per-line passes
+constexpr int TK_READERS = 4;         // host threads streaming a file into the device
+constexpr size_t TK_SLOT = 8u << 20;  // pinned bytes per slot (two slots per reader)
+
+struct TokStatus {
+    unsigned long long first_bad;     // smallest line index the device does not accept (~0 = none)
+    unsigned int need8;               // a SEQ byte outside the 4-bit alphabet
+    unsigned int group_err;           // a read group without any sequence (alignment.rs:319-321)
+};
+
+struct TokTable {                     // device pointers of the contig-name table and the nibble table
+    tok::ContigTable ct;
+    const uint8_t* nibtab;
+};
+
+__device__ __forceinline__ uint32_t newline_mask(uint32_t w) { return __vcmpeq4(w, 0x0A0A0A0Au); }
+
+__global__ void __launch_bounds__(TK_THREADS) k_tok_count(const uint8_t* __restrict__ text, uint64_t n16, unsigned long long* __restrict__ tile_cnt) {
+    const uint64_t t0 = (uint64_t)blockIdx.x * TK_TILE;
+    uint32_t c = 0;
+    for (uint32_t off = threadIdx.x * 16; off < TK_TILE; off += TK_THREADS * 16) {
+        const uint64_t p = t0 + off;
+        if (p < n16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + p));
+            c += __popc(newline_mask(v.x) & 0x01010101u) + __popc(newline_mask(v.y) & 0x01010101u) +
+                 __popc(newline_mask(v.z) & 0x01010101u) + __popc(newline_mask(v.w) & 0x01010101u);
+        }
+    }
+    typedef cub::BlockReduce<uint32_t, TK_THREADS> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const uint32_t s = BR(tmp).Sum(c);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = s;
+}
+
+// line_start[i] = offset of the first byte of line i; line_start[0] = 0, line_start[k+1] = position after newline k.
+__global__ void __launch_bounds__(TK_THREADS) k_tok_index(const uint8_t* __restrict__ text, uint64_t n16, const unsigned long long* __restrict__ tile_off,
+                                                          unsigned long long* __restrict__ line_start) {
+    typedef cub::BlockScan<uint32_t, TK_THREADS> BS;
+    __shared__ typename BS::TempStorage tmp;
+    const uint64_t t0 = (uint64_t)blockIdx.x * TK_TILE;
+    unsigned long long run = tile_off[blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0) line_start[0] = 0;
+    for (uint32_t it = 0; it < TK_TILE / (TK_THREADS * 16); ++it) {
+        const uint64_t p = t0 + (uint64_t)it * TK_THREADS * 16 + threadIdx.x * 16;
+        uint32_t m[4] = {0, 0, 0, 0};
+        if (p < n16) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + p));
+            m[0] = newline_mask(v.x) & 0x01010101u; m[1] = newline_mask(v.y) & 0x01010101u;
+            m[2] = newline_mask(v.z) & 0x01010101u; m[3] = newline_mask(v.w) & 0x01010101u;
+        }
+        const uint32_t cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+        uint32_t ex, total;
+        BS(tmp).ExclusiveSum(cnt, ex, total);
+        __syncthreads();
+        unsigned long long o = run + ex;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t mk = m[k];
+            while (mk) {
+                const uint32_t b = (uint32_t)(__ffs((int)mk) - 1) >> 3;
+                line_start[++o] = p + (uint32_t)k * 4 + b + 1;
+                mk &= mk - 1;
+            }
+        }
+        run += total;
+    }
+}
+
+struct ParseArgs {
+    const uint8_t* text;
+    uint64_t n;                       // text bytes
+    const unsigned long long* line_start;
+    uint64_t n_lines;
+    int unterminated;                 // the last line has no '\n' (and so keeps a trailing '\r', misc str::lines semantics)
+    TokTable tb;
+    tok::LineRec* recs;
+    unsigned long long *s_al, *s_ops, *s_blk;   // [n_lines + 1] scan inputs: aligned?, CIGAR ops, sequence blocks
+    TokStatus* st;
+};
+
+__device__ __forceinline__ void line_span(const ParseArgs& a, tok::Txt& x, uint64_t i, uint64_t& s, uint64_t& e) {
+    s = a.line_start[i];
+    if (i + 1 == a.n_lines && a.unterminated) { e = a.n; return; }
+    e = a.line_start[i + 1] - 1;
+    if (e > s && x.at(e - 1) == '\r') e--;
+}
+
+__global__ void __launch_bounds__(TK_LINE_THREADS) k_tok_parse(ParseArgs a) {
+    __shared__ uint8_t s_nib[256];
+    for (int k = threadIdx.x; k < 256; k += TK_LINE_THREADS) s_nib[k] = a.tb.nibtab[k];
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * TK_LINE_THREADS + threadIdx.x;
+    if (i > a.n_lines) return;
+    if (i == a.n_lines) { a.s_al[i] = 0; a.s_ops[i] = 0; a.s_blk[i] = 0; return; }
+    tok::Txt x(a.text);
+    uint64_t s, e;
+    line_span(a, x, i, s, e);
+    tok::LineRec r;
+    const uint8_t kind = tok::parse_line(x, s, e, a.tb.ct, s_nib, r);
+    r.kind = kind;
+    a.recs[i] = r;
+    const bool al = kind == tok::LK_ALIGNED;
+    a.s_al[i] = al ? 1 : 0;
+    a.s_ops[i] = al ? r.nops : 0;
+    a.s_blk[i] = al ? tok::seq_blocks(r) : 0;
+    if (kind == tok::LK_HOST) atomicMin(&a.st->first_bad, (unsigned long long)i);
+    if (al && r.need8) a.st->need8 = 1;
+}
+
+struct EmitArgs {
+    ParseArgs p;
+    uint64_t aln_base, ops_base, blk_base;
+    uint32_t *contig, *ref_start, *seq_off, *cigar_off, *nm, *cigar_ops;
+    uint16_t *seq_len, *n_cigar;
+    uint8_t *flags, *seq_pool;
+    unsigned long long* name_pos;     // [alignments of this file] text offset of the QNAME
+    uint32_t* name_len;
+};
+
+template <int BITS>
+__global__ void __launch_bounds__(TK_LINE_THREADS) k_tok_emit(EmitArgs a) {
+    __shared__ uint8_t s_nib[256];
+    for (int k = threadIdx.x; k < 256; k += TK_LINE_THREADS) s_nib[k] = a.p.tb.nibtab[k];
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * TK_LINE_THREADS + threadIdx.x;
+    if (i >= a.p.n_lines) return;
+    const tok::LineRec r = a.p.recs[i];
+    if (r.kind != tok::LK_ALIGNED) return;
+    const uint64_t s = a.p.line_start[i];
+    const uint64_t la = a.p.s_al[i], A = a.aln_base + la;
+    const uint64_t co = a.ops_base + a.p.s_ops[i], bo = a.blk_base + a.p.s_blk[i];
+    const bool star = r.flags & PP_FLAG_SEQSTAR;
+    a.contig[A] = r.contig;
+    a.ref_start[A] = r.ref_start;
+    a.seq_off[A] = star ? 0u : (uint32_t)bo;
+    a.seq_len[A] = (uint16_t)r.slen;
+    a.cigar_off[A] = (uint32_t)co;
+    a.n_cigar[A] = (uint16_t)r.nops;
+    a.nm[A] = r.nm;
+    a.flags[A] = r.flags;
+    a.name_pos[la] = s;
+    a.name_len[la] = r.name_len;
+    tok::Txt x(a.p.text);
+    tok::emit_cigar(x, s, r, a.cigar_ops + co);
+    tok::emit_seq<BITS>(x, s, r, s_nib, a.seq_pool + bo * (BITS == 4 ? 16 : 32));
+}
+
+__global__ void __launch_bounds__(TK_LINE_THREADS) k_tok_heads(const uint8_t* __restrict__ text, uint64_t n_al, const unsigned long long* __restrict__ name_pos,
+                                                               const uint32_t* __restrict__ name_len, uint32_t* __restrict__ head) {
+    const uint64_t a = (uint64_t)blockIdx.x * TK_LINE_THREADS + threadIdx.x;
+    if (a >= n_al) return;
+    tok::Txt x(text);
+    head[a] = tok::group_head(x, a, 0, reinterpret_cast<const uint64_t*>(name_pos), name_len) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(TK_LINE_THREADS) k_tok_groups(uint64_t n_al, const uint32_t* __restrict__ head, const uint32_t* __restrict__ rs, uint64_t read_base,
+                                                                int careful, uint32_t* __restrict__ read_id, uint32_t* seq_off, uint16_t* seq_len, uint8_t* flags,
+                                                                TokStatus* st) {
+    const uint64_t a = (uint64_t)blockIdx.x * TK_LINE_THREADS + threadIdx.x;
+    if (a >= n_al) return;
+    read_id[a] = (uint32_t)(read_base + rs[a] - 1);
+    if (head[a] && !tok::close_group(a, n_al, head, careful != 0, seq_off, seq_len, flags)) st->group_err = 1;
+}
+
+}  // namespace
+
+struct TokState {
+    const pp_fasta* fasta = nullptr;
+    bool careful = false, active = false;
+    int seq_bits = 4;
+    uint64_t aln_base = 0, ops_base = 0, blk_base = 0, read_base = 0;   // dataset under construction
+    TokTable tb{};
+    TokStatus* h_st = nullptr;            // pinned
+    unsigned long long* h_tot = nullptr;  // pinned [4]
+    TokStatus* d_st = nullptr;
+    // file streaming
+    uint8_t* pin[TK_READERS][2] = {};
+    cudaStream_t rstream[TK_READERS] = {};
+    cudaEvent_t rev[TK_READERS][2] = {};
+    bool ring = false;
+    DevBuf cub;
+};
+
+void pp_tok_release(pp_ctx* ctx) {
+    TokState* T = ctx->tok;
+    if (!T) return;
+    for (int r = 0; r < TK_READERS; ++r) {
+        for (int k = 0; k < 2; ++k) {
+            if (T->pin[r][k]) cudaFreeHost(T->pin[r][k]);
+            if (T->rev[r][k]) cudaEventDestroy(T->rev[r][k]);
+        }
+        if (T->rstream[r]) cudaStreamDestroy(T->rstream[r]);
+    }
+    if (T->h_st) cudaFreeHost(T->h_st);
+    if (T->h_tot) cudaFreeHost(T->h_tot);
+    if (T->d_st) cudaFree(T->d_st);
+    T->cub.release();
+    delete T;
+    ctx->tok = nullptr;
+}
+
+static int tok_state(pp_ctx* ctx, TokState** out) {
+    if (!ctx->tok) {
+        TokState* T = new TokState();
+        ctx->tok = T;
+        CK(cudaHostAlloc((void**)&T->h_st, sizeof(TokStatus), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&T->h_tot, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&T->d_st, sizeof(TokStatus)));
+    }
+    *out = ctx->tok;
+    return PP_OK;
+}
+
+// Grows a dataset buffer keeping its first `keep` bytes (the alignments of the files tokenised so far).
+static int ensure_keep(pp_ctx* ctx, int which, size_t bytes, size_t keep) {
+    DevBuf& b = ctx->b[which];
+    if (bytes <= b.cap) return PP_OK;
+    if (keep == 0) { CK(b.ensure(bytes)); return PP_OK; }
+    void* np = nullptr;
+    const size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&np, want));
+    cudaError_t e = cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(np); CK(e); }
+    cudaFree(b.p);
+    b.p = np;
+    b.cap = want;
+    return PP_OK;
+}
+
+int pp_ctx_upload_contigs(pp_ctx* ctx, const pp_contigs* c);
+int pp_ctx_commit_dataset(pp_ctx* ctx, uint64_t n_aln, uint64_t n_reads, uint64_t n_ops, uint64_t seq_bytes, uint32_t seq_bits);
+
+extern "C" int pp_tok_begin(pp_ctx* ctx, const pp_fasta* fa, int careful, int seq_bits) {
+    if (!ctx) return PP_ERR_ARG;
+    if (!fa || (seq_bits != 4 && seq_bits != 8)) return ctx->fail(PP_ERR_ARG, "pp_tok_begin: null assembly or seq_bits not 4 / 8");
+    CK(cudaSetDevice(ctx->device));
+    TokState* T = nullptr;
+    int rc = tok_state(ctx, &T);
+    if (rc) return rc;
+    ctx->have_ds = false;
+    pp_contigs contigs;
+    pp_fasta_view(fa, &contigs);
+    if ((rc = pp_ctx_upload_contigs(ctx, &contigs))) return rc;
+    tok::TableImage im;
+    tok::build_table_image(fa->names, im);
+    CK(ctx->b[B_TOKNAMES].ensure(im.bytes.size()));
+    CK(cudaMemcpyAsync(ctx->b[B_TOKNAMES].p, im.bytes.data(), im.bytes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));              // `im` is pageable and about to go away
+    const uint8_t* base = ctx->b[B_TOKNAMES].as<uint8_t>();
+    T->tb.ct = tok::table_view(im, base);
+    T->tb.nibtab = base + im.o_nib;
+    T->fasta = fa; T->careful = careful != 0; T->seq_bits = seq_bits;
+    T->aln_base = T->ops_base = T->blk_base = T->read_base = 0;
+    T->active = true;
+    return PP_OK;
+}
+
+// The text is in ctx->b[B_TEXT] (n bytes, zero padded).  Appends its alignments to the dataset under construction.
+static int tok_process(pp_ctx* ctx, TokState* T, uint64_t n, bool unterminated, pp_tok_stats* stats) {
+    cudaStream_t s = ctx->stream;
+    const uint8_t* text = ctx->b[B_TEXT].as<uint8_t>();
+    uint32_t launches = 0;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    // ---- lines
+    const uint64_t n16 = (n + 15) & ~15ull;
+    const uint64_t n_tiles = (n16 + TK_TILE - 1) / TK_TILE;
+    if (n_tiles >= 0x7FFFFFFFull) return PP_TOK_HOST;
+    size_t cub_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int64_t)std::max<uint64_t>(n_tiles + 1, 1)));
+    CK(T->cub.ensure(cub_bytes + 256));
+    CK(ctx->b[B_TOKLINE].ensure((n_tiles + 2) * 8));
+    unsigned long long* tile_cnt = ctx->b[B_TOKLINE].as<unsigned long long>();
+    uint64_t n_lines = 0;
+    if (n_tiles) {
+        CK(cudaMemsetAsync(tile_cnt + n_tiles, 0, 8, s));
+        k_tok_count<<<(unsigned)n_tiles, TK_THREADS, 0, s>>>(text, n16, tile_cnt);
+        size_t tb = T->cub.cap;
+        CK(cub::DeviceScan::ExclusiveSum(T->cub.p, tb, tile_cnt, tile_cnt, (int64_t)(n_tiles + 1), s));
+        CK(cudaMemcpyAsync(T->h_tot, tile_cnt + n_tiles, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        launches += 3;
+        n_lines = T->h_tot[0] + (unterminated ? 1 : 0);
+    }
+    if (stats) stats->lines = n_lines;
+    if (n_lines == 0) return PP_TOK_HOST;                    // "no alignments in <file>": the host packer words it
+    if (n_lines >= 0xFFFFFFF0ull) return PP_TOK_HOST;
+
+    // scratch: line starts | line records | three scan arrays
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_ls = carve((n_lines + 2) * 8), o_rec = carve(n_lines * sizeof(tok::LineRec)), o_al = carve((n_lines + 1) * 8),
+                 o_ops = carve((n_lines + 1) * 8), o_blk = carve((n_lines + 1) * 8);
+    CK(ctx->b[B_TOKTMP].ensure(off));
+    uint8_t* tmp = ctx->b[B_TOKTMP].as<uint8_t>();
+    ParseArgs pa;
+    pa.text = text; pa.n = n; pa.line_start = (unsigned long long*)(tmp + o_ls); pa.n_lines = n_lines; pa.unterminated = unterminated ? 1 : 0;
+    pa.tb = T->tb; pa.recs = (tok::LineRec*)(tmp + o_rec);
+    pa.s_al = (unsigned long long*)(tmp + o_al); pa.s_ops = (unsigned long long*)(tmp + o_ops); pa.s_blk = (unsigned long long*)(tmp + o_blk);
+    pa.st = T->d_st;
+    T->h_st->first_bad = ~0ull; T->h_st->need8 = 0; T->h_st->group_err = 0;
+    CK(cudaMemcpyAsync(T->d_st, T->h_st, sizeof(TokStatus), cudaMemcpyHostToDevice, s));
+    k_tok_index<<<(unsigned)n_tiles, TK_THREADS, 0, s>>>(text, n16, tile_cnt, (unsigned long long*)(tmp + o_ls));
+    const unsigned line_grid = (unsigned)((n_lines + 1 + TK_LINE_THREADS - 1) / TK_LINE_THREADS);
+    k_tok_parse<<<line_grid, TK_LINE_THREADS, 0, s>>>(pa);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, pa.s_al, pa.s_al, (int64_t)(n_lines + 1)));
+    CK(T->cub.ensure(cub_bytes + 256));
+    for (unsigned long long* arr : {pa.s_al, pa.s_ops, pa.s_blk}) {
+        size_t tb = T->cub.cap;
+        CK(cub::DeviceScan::ExclusiveSum(T->cub.p, tb, arr, arr, (int64_t)(n_lines + 1), s));
+    }
+    CK(cudaMemcpyAsync(T->h_tot + 0, pa.s_al + n_lines, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(T->h_tot + 1, pa.s_ops + n_lines, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(T->h_tot + 2, pa.s_blk + n_lines, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(T->h_st, T->d_st, sizeof(TokStatus), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    launches += 5;
+    const uint64_t n_al = T->h_tot[0], n_ops = T->h_tot[1], n_blk = T->h_tot[2];
+    if (stats) stats->alignments = n_al;
+    if (T->h_st->first_bad != ~0ull) return PP_TOK_HOST;
+    if (T->h_st->need8 && T->seq_bits == 4) return PP_TOK_NEED8;
+    if (n_al == 0) return PP_TOK_HOST;                       // alignment.rs:268-270
+    if (T->aln_base + n_al >= 0xFFFFFFFFull - 4096 || T->ops_base + n_ops > 0xFFFFFFFFull || T->blk_base + n_blk > 0xFFFFFFFFull) return PP_TOK_HOST;
+
+    // ---- dataset arrays (kept across files)
+    const uint64_t A0 = T->aln_base, A1 = A0 + n_al;
+    const size_t blk_bytes = T->seq_bits == 4 ? 16 : 32;
+    int rc;
+    for (int w : {B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_CIGOFF, B_NM})
+        if ((rc = ensure_keep(ctx, w, A1 * 4 + 64, A0 * 4))) return rc;
+    for (int w : {B_SEQLEN, B_NCIG})
+        if ((rc = ensure_keep(ctx, w, A1 * 2 + 64, A0 * 2))) return rc;
+    if ((rc = ensure_keep(ctx, B_FLAGS, A1 + 64, A0))) return rc;
+    if ((rc = ensure_keep(ctx, B_CIGOPS, (T->ops_base + n_ops) * 4 + 64, T->ops_base * 4))) return rc;
+    if ((rc = ensure_keep(ctx, B_SEQPOOL, (T->blk_base + n_blk) * blk_bytes + 256, T->blk_base * blk_bytes))) return rc;
+    // per-alignment scratch of this file: QNAME position / length, group heads, their running count
+    size_t off2 = 0;
+    auto carve2 = [&](size_t bytes) { size_t o = off2; off2 += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_np = carve2(n_al * 8), o_nl = carve2(n_al * 4), o_hd = carve2(n_al * 4), o_rs = carve2(n_al * 4);
+    CK(ctx->b[B_SCRATCH].ensure(off2));
+    uint8_t* sc = ctx->b[B_SCRATCH].as<uint8_t>();
+
+    EmitArgs ea;
+    ea.p = pa; ea.aln_base = A0; ea.ops_base = T->ops_base; ea.blk_base = T->blk_base;
+    ea.contig = ctx->b[B_CONTIG].as<uint32_t>(); ea.ref_start = ctx->b[B_REFSTART].as<uint32_t>(); ea.seq_off = ctx->b[B_SEQOFF].as<uint32_t>();
+    ea.cigar_off = ctx->b[B_CIGOFF].as<uint32_t>(); ea.nm = ctx->b[B_NM].as<uint32_t>(); ea.cigar_ops = ctx->b[B_CIGOPS].as<uint32_t>();
+    ea.seq_len = ctx->b[B_SEQLEN].as<uint16_t>(); ea.n_cigar = ctx->b[B_NCIG].as<uint16_t>();
+    ea.flags = ctx->b[B_FLAGS].as<uint8_t>(); ea.seq_pool = ctx->b[B_SEQPOOL].as<uint8_t>();
+    ea.name_pos = (unsigned long long*)(sc + o_np); ea.name_len = (uint32_t*)(sc + o_nl);
+    const unsigned emit_grid = (unsigned)((n_lines + TK_LINE_THREADS - 1) / TK_LINE_THREADS);
+    if (T->seq_bits == 4) k_tok_emit<4><<<emit_grid, TK_LINE_THREADS, 0, s>>>(ea);
+    else k_tok_emit<8><<<emit_grid, TK_LINE_THREADS, 0, s>>>(ea);
+    uint32_t* head = (uint32_t*)(sc + o_hd);
+    uint32_t* rs = (uint32_t*)(sc + o_rs);
+    const unsigned aln_grid = (unsigned)((n_al + TK_LINE_THREADS - 1) / TK_LINE_THREADS);
+    k_tok_heads<<<aln_grid, TK_LINE_THREADS, 0, s>>>(text, n_al, ea.name_pos, ea.name_len, head);
+    CK(cub::DeviceScan::InclusiveSum(nullptr, cub_bytes, head, rs, (int64_t)n_al));
+    CK(T->cub.ensure(cub_bytes + 256));
+    {
+        size_t tb = T->cub.cap;
+        CK(cub::DeviceScan::InclusiveSum(T->cub.p, tb, head, rs, (int64_t)n_al, s));
+    }
+    k_tok_groups<<<aln_grid, TK_LINE_THREADS, 0, s>>>(n_al, head, rs, T->read_base, T->careful ? 1 : 0, ctx->b[B_READID].as<uint32_t>() + A0,
+                                                       ea.seq_off + A0, ea.seq_len + A0, ea.flags + A0, T->d_st);
+    uint32_t* h_reads = (uint32_t*)(T->h_tot + 3);
+    CK(cudaMemcpyAsync(h_reads, rs + (n_al - 1), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(T->h_st, T->d_st, sizeof(TokStatus), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[1], s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    launches += 4;
+    if (T->h_st->group_err) return PP_TOK_HOST;
+    const uint64_t n_reads = *h_reads;
+    if (T->read_base + n_reads >= 0xFFFFFFFFull) return PP_TOK_HOST;
+    T->aln_base = A1; T->ops_base += n_ops; T->blk_base += n_blk; T->read_base += n_reads;
+    if (stats) {
+        stats->reads = n_reads;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        stats->device_ms = ms;
+        stats->launches = launches;
+    }
+    return PP_OK;
+}
+
+static int text_buffer(pp_ctx* ctx, uint64_t n) {
+    CK(ctx->b[B_TEXT].ensure(n + 64));
+    const uint64_t n16 = (n + 15) & ~15ull;
+    CK(cudaMemsetAsync(ctx->b[B_TEXT].as<uint8_t>() + n, 0, (size_t)(n16 + 32 - n), ctx->stream));
+    return PP_OK;
+}
+
+extern "C" int pp_tok_add_text(pp_ctx* ctx, const char* text, size_t len, pp_tok_stats* stats) {
+    if (!ctx) return PP_ERR_ARG;
+    TokState* T = ctx->tok;
+    if (!T || !T->active) return ctx->fail(PP_ERR_ARG, "pp_tok_add_text: no pp_tok_begin");
+    if (!text && len) return ctx->fail(PP_ERR_ARG, "pp_tok_add_text: null text");
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    int rc = text_buffer(ctx, len);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (len) CK(cudaMemcpyAsync(ctx->b[B_TEXT].p, text, len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (stats) stats->h2d_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    rc = tok_process(ctx, T, len, len > 0 && text[len - 1] != '\n', stats);
+    if (rc != PP_OK) T->active = false;
+    return rc;
+}
+
+// Streams a file into ctx->b[B_TEXT]: TK_READERS threads, each pread()s its slices into its two pinned slots and sends
+// them on its own stream, so that disk/page-cache reads, pinned staging and PCIe overlap.
+static int upload_file(pp_ctx* ctx, TokState* T, int fd, uint64_t n, uint8_t* last_byte) {
+    if (!T->ring) {
+        for (int r = 0; r < TK_READERS; ++r) {
+            CK(cudaStreamCreateWithFlags(&T->rstream[r], cudaStreamNonBlocking));
+            for (int k = 0; k < 2; ++k) {
+                CK(cudaHostAlloc((void**)&T->pin[r][k], TK_SLOT, cudaHostAllocDefault));
+                CK(cudaEventCreateWithFlags(&T->rev[r][k], cudaEventDisableTiming));
+            }
+        }
+        T->ring = true;
+    }
+    uint8_t* dst = ctx->b[B_TEXT].as<uint8_t>();
+    const uint64_t n_slices = (n + TK_SLOT - 1) / TK_SLOT;
+    std::atomic<int> err{0};           // 1 = read error, 2 = CUDA error
+    std::atomic<int> cuda_err{0};
+    const int device = ctx->device;
+    auto work = [&](int r) {
+        if (cudaSetDevice(device) != cudaSuccess) { err = 2; return; }
+        uint64_t k = 0;
+        for (uint64_t sl = (uint64_t)r; sl < n_slices && !err; sl += TK_READERS, ++k) {
+            const int slot = (int)(k & 1);
+            if (k >= 2) {
+                cudaError_t e = cudaEventSynchronize(T->rev[r][slot]);
+                if (e != cudaSuccess) { cuda_err = (int)e; err = 2; return; }
+            }
+            const uint64_t o = sl * TK_SLOT, len = std::min<uint64_t>(TK_SLOT, n - o);
+            uint64_t got = 0;
+            while (got < len) {
+                const ssize_t g = pread(fd, T->pin[r][slot] + got, (size_t)(len - got), (off_t)(o + got));
+                if (g <= 0) { err = 1; return; }
+                got += (uint64_t)g;
+            }
+            if (o + len == n) *last_byte = T->pin[r][slot][len - 1];
+            cudaError_t e = cudaMemcpyAsync(dst + o, T->pin[r][slot], (size_t)len, cudaMemcpyHostToDevice, T->rstream[r]);
+            if (e == cudaSuccess) e = cudaEventRecord(T->rev[r][slot], T->rstream[r]);
+            if (e != cudaSuccess) { cuda_err = (int)e; err = 2; return; }
+        }
+        cudaError_t e = cudaStreamSynchronize(T->rstream[r]);
+        if (e != cudaSuccess) { cuda_err = (int)e; err = 2; }
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < TK_READERS; ++r) th.emplace_back(work, r);
+    work(0);
+    for (auto& t : th) t.join();
+    if (err == 1) return PP_ERR_IO;
+    if (err == 2) return ctx->fail_cuda((cudaError_t)cuda_err.load(), "SAM text upload", __FILE__, __LINE__);
+    return PP_OK;
+}
+
+extern "C" int pp_tok_add_file(pp_ctx* ctx, const char* path, pp_tok_stats* stats) {
+    if (!ctx) return PP_ERR_ARG;
+    TokState* T = ctx->tok;
+    if (!T || !T->active) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: no pp_tok_begin");
+    if (!path) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: null path");
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    const int fd = open(path, O_RDONLY);
+    struct stat sb;
+    if (fd < 0 || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
+        if (fd >= 0) close(fd);
+        T->active = false;
+        return PP_TOK_HOST;                                  // not a plain readable file: the host path reports it
+    }
+    const uint64_t n = (uint64_t)sb.st_size;
+    int rc = text_buffer(ctx, n);
+    if (rc == PP_OK) rc = (cudaStreamSynchronize(ctx->stream) == cudaSuccess) ? PP_OK : ctx->fail(PP_ERR_CUDA, "CUDA error before the SAM upload");
+    uint8_t last = '\n';
+    const auto t0 = std::chrono::steady_clock::now();
+    if (rc == PP_OK && n) rc = upload_file(ctx, T, fd, n, &last);
+    close(fd);
+    if (rc == PP_ERR_IO) { T->active = false; return PP_TOK_HOST; }
+    if (rc != PP_OK) { T->active = false; return rc; }
+    const float h2d = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    rc = tok_process(ctx, T, n, n > 0 && last != '\n', stats);
+    if (stats) stats->h2d_ms = h2d;
+    if (rc != PP_OK) T->active = false;
+    return rc;
+}
+
+extern "C" int pp_set_parser(pp_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 1) return PP_ERR_ARG;
+    ctx->parser = mode;
+    return PP_OK;
+}
+extern "C" int pp_get_parser(const pp_ctx* ctx) { return ctx ? ctx->parser : 0; }
+
+extern "C" int pp_tok_finish(pp_ctx* ctx) {
+    if (!ctx) return PP_ERR_ARG;
+    TokState* T = ctx->tok;
+    if (!T || !T->active) return ctx->fail(PP_ERR_ARG, "pp_tok_finish: no tokenised text");
+    T->active = false;
+    return pp_ctx_commit_dataset(ctx, T->aln_base, T->read_base, T->ops_base, T->blk_base * (T->seq_bits == 4 ? 16 : 32), (uint32_t)T->seq_bits);
+}
+
+// ---- the resident dataset, read back (tests compare it with the host packer's arrays)
+extern "C" int pp_dataset_sizes(pp_ctx* ctx, pp_alignments* out) {
+    if (!ctx || !out) return PP_ERR_ARG;
+    if (!ctx->have_ds) return ctx->fail(PP_ERR_ARG, "pp_dataset_sizes: no resident dataset");
+    memset(out, 0, sizeof *out);
+    out->n_aln = ctx->n_aln; out->n_reads = ctx->n_reads; out->n_cigar_ops = ctx->n_ops; out->seq_pool_bytes = ctx->seq_bytes;
+    out->seq_bits = ctx->seq_bits;
+    return PP_OK;
+}
+
+extern "C" int pp_dataset_download(pp_ctx* ctx, const pp_alignments* into) {
+    if (!ctx || !into) return PP_ERR_ARG;
+    if (!ctx->have_ds) return ctx->fail(PP_ERR_ARG, "pp_dataset_download: no resident dataset");
+    if (into->n_aln != ctx->n_aln || into->n_cigar_ops != ctx->n_ops || into->seq_pool_bytes != ctx->seq_bytes)
+        return ctx->fail(PP_ERR_ARG, "pp_dataset_download: sizes differ from pp_dataset_sizes");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t n = (size_t)ctx->n_aln;
+    auto get = [&](const void* dst, int which, size_t bytes) -> cudaError_t {
+        if (!dst || !bytes) return cudaSuccess;
+        return cudaMemcpyAsync(const_cast<void*>(dst), ctx->b[which].p, bytes, cudaMemcpyDeviceToHost, s);
+    };
+    CK(get(into->contig, B_CONTIG, n * 4)); CK(get(into->ref_start, B_REFSTART, n * 4)); CK(get(into->read_id, B_READID, n * 4));
+    CK(get(into->seq_off, B_SEQOFF, n * 4)); CK(get(into->seq_len, B_SEQLEN, n * 2)); CK(get(into->cigar_off, B_CIGOFF, n * 4));
+    CK(get(into->n_cigar, B_NCIG, n * 2)); CK(get(into->nm, B_NM, n * 4)); CK(get(into->flags, B_FLAGS, n));
+    CK(get(into->cigar_ops, B_CIGOPS, (size_t)ctx->n_ops * 4)); CK(get(into->seq_pool, B_SEQPOOL, (size_t)ctx->seq_bytes));
+    CK(cudaStreamSynchronize(s));
+    return PP_OK;
+}
