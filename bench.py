@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="5Mbp_x100", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-t3", action="store_true", help="skip the SAM-text-on-disk -> FASTA measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -246,6 +247,37 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     d2h_bytes = int(e["out_len"]) + 8 * (3 * n_c + 1)
 
+    # ---------------- T3: the whole command, SAM/FASTA text on disk (page cache warm) -> polished FASTA bytes ----------------
+    t3 = None
+    if rank == 0 and world == 1 and not args.no_t3 and G * depth <= 6e8:
+        import shutil
+        shm = "/dev/shm"
+        base = shm if os.path.isdir(shm) and shutil.disk_usage(shm).free > 4 * (1 << 30) else None
+        d = tempfile.mkdtemp(prefix="pp_t3_", dir=base)
+        try:
+            fa_path, sam_paths = syn.write(d)
+            sam_bytes = sum(os.path.getsize(x) for x in sam_paths)
+            outs, best = {}, {}
+            for mode, name, reps in ((0, "device_tokeniser", 4), (1, "host_packer", 2)):
+                ctx.set_parser(mode)
+                ts = []
+                for _ in range(reps):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    outs[name] = ctx.polish_files(fa_path, sam_paths)
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                best[name] = min(ts)
+            ctx.set_parser(0)
+            rc_tok, tok_stats = ctx.tokenise(fasta, sam_paths)
+            t3 = {"value": G / 1e6 / (best["device_tokeniser"] / 1e3), "unit": "Mbp/s", "ms": best["device_tokeniser"],
+                  "host_packer_ms": best["host_packer"], "sam_text_bytes": int(sam_bytes), "files": len(sam_paths), "host_cores": os.cpu_count(),
+                  "identical_output": outs["device_tokeniser"] == outs["host_packer"],
+                  "tokeniser": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()} for st in tok_stats],
+                  "api": "pp_polish_files (FASTA + SAM paths in, FASTA bytes out), best of 4; host_packer = same call with pp_set_parser(1)"}
+            ctx.upload(fasta.view, packed.view)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+
     # ---------------- max over ranks ----------------
     t = torch.tensor([ms_step, wall_ms / args.steps, e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
@@ -280,6 +312,8 @@ def main():
             "stages_ms": {k: v / args.steps for k, v in sorted(stage.items())},
             "wall_ms_per_step": wall_step_max, "clocks": clocks, "setup_s": t_gen,
         }
+        if t3 is not None:
+            line["t3"] = t3
         if not args.no_cpu_baseline:
             v, dt, phases, bp = cpu_baseline(min(clen, 1_000_000), depth, seed=2)
             line["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": 1, "kind": "port",

@@ -264,6 +264,8 @@ int pp_tok_finish(pp_ctx* ctx);        /* the tokenised alignments + the assembl
  * on PP_TOK_HOST and for --debug / multi-GPU runs; 1 the host packer only.  Both give the same bytes. */
 int pp_set_parser(pp_ctx* ctx, int mode);
 int pp_get_parser(const pp_ctx* ctx);
+/* Host threads pp_tok_add_file uses to stream a file into HBM (pread -> pinned slot -> PCIe); 0 = a quarter of the cores, 2..16. */
+int pp_tok_set_readers(pp_ctx* ctx, int n);
 /* The resident dataset read back (tests: equality with the host packer's arrays).  pp_dataset_sizes fills the counts of
  * `out`; pp_dataset_download copies into the caller's arrays (same counts; NULL pointers are skipped). */
 int pp_dataset_sizes(pp_ctx* ctx, pp_alignments* out);

@@ -139,6 +139,7 @@ def lib():
     L.pp_tok_finish.argtypes = [C.c_void_p]
     L.pp_set_parser.argtypes = [C.c_void_p, C.c_int]
     L.pp_get_parser.argtypes = [C.c_void_p]
+    L.pp_tok_set_readers.argtypes = [C.c_void_p, C.c_int]
     L.pp_dataset_sizes.argtypes = [C.c_void_p, C.POINTER(Alignments)]
     L.pp_dataset_download.argtypes = [C.c_void_p, C.POINTER(Alignments)]
     if hasattr(L, "pp_filter"):
@@ -395,6 +396,10 @@ class Context:
         a["seq_bits"] = v.seq_bits
         a["n_reads"] = v.n_reads
         return a
+
+    def set_readers(self, n):
+        """Host threads streaming a SAM file into HBM (0 = automatic)."""
+        lib().pp_tok_set_readers(self.h, int(n))
 
     def set_parser(self, mode):
         """0: pp_polish_files parses SAM on the device (default); 1: on the host."""

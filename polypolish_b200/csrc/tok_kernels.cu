@@ -44,8 +44,8 @@ namespace {
 constexpr int TK_TILE = 16384;        // bytes of text per CTA in the newline passes
 constexpr int TK_THREADS = 256;
 constexpr int TK_LINE_THREADS = 128;  // threads (= lines) per CTA in the per-line passes
-constexpr int TK_READERS = 4;         // host threads streaming a file into the device
-constexpr size_t TK_SLOT = 8u << 20;  // pinned bytes per slot (two slots per reader)
+constexpr int TK_READERS = 16;        // at most this many host threads stream a file into the device
+constexpr size_t TK_SLOT = 4u << 20;  // pinned bytes per slot (two slots per reader)
 
 struct TokStatus {
     unsigned long long first_bad;     // smallest line index the device does not accept (~0 = none)
@@ -222,7 +222,8 @@ struct TokState {
     uint8_t* pin[TK_READERS][2] = {};
     cudaStream_t rstream[TK_READERS] = {};
     cudaEvent_t rev[TK_READERS][2] = {};
-    bool ring = false;
+    int readers = 0;                      // threads in use (pp_tok_set_readers, default from the core count)
+    int ring = 0;                         // readers whose slots / stream exist
     DevBuf cub;
 };
 
@@ -456,15 +457,18 @@ extern "C" int pp_tok_add_text(pp_ctx* ctx, const char* text, size_t len, pp_tok
 // Streams a file into ctx->b[B_TEXT]: TK_READERS threads, each pread()s its slices into its two pinned slots and sends
 // them on its own stream, so that disk/page-cache reads, pinned staging and PCIe overlap.
 static int upload_file(pp_ctx* ctx, TokState* T, int fd, uint64_t n, uint8_t* last_byte) {
-    if (!T->ring) {
-        for (int r = 0; r < TK_READERS; ++r) {
-            CK(cudaStreamCreateWithFlags(&T->rstream[r], cudaStreamNonBlocking));
-            for (int k = 0; k < 2; ++k) {
-                CK(cudaHostAlloc((void**)&T->pin[r][k], TK_SLOT, cudaHostAllocDefault));
-                CK(cudaEventCreateWithFlags(&T->rev[r][k], cudaEventDisableTiming));
-            }
+    if (T->readers <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        T->readers = (int)std::min<unsigned>(TK_READERS, std::max<unsigned>(2, hw / 4));
+    }
+    const int R = T->readers;
+    for (int r = T->ring; r < R; ++r) {
+        CK(cudaStreamCreateWithFlags(&T->rstream[r], cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaHostAlloc((void**)&T->pin[r][k], TK_SLOT, cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&T->rev[r][k], cudaEventDisableTiming));
         }
-        T->ring = true;
+        T->ring = r + 1;
     }
     uint8_t* dst = ctx->b[B_TEXT].as<uint8_t>();
     const uint64_t n_slices = (n + TK_SLOT - 1) / TK_SLOT;
@@ -474,7 +478,7 @@ static int upload_file(pp_ctx* ctx, TokState* T, int fd, uint64_t n, uint8_t* la
     auto work = [&](int r) {
         if (cudaSetDevice(device) != cudaSuccess) { err = 2; return; }
         uint64_t k = 0;
-        for (uint64_t sl = (uint64_t)r; sl < n_slices && !err; sl += TK_READERS, ++k) {
+        for (uint64_t sl = (uint64_t)r; sl < n_slices && !err; sl += (uint64_t)R, ++k) {
             const int slot = (int)(k & 1);
             if (k >= 2) {
                 cudaError_t e = cudaEventSynchronize(T->rev[r][slot]);
@@ -496,7 +500,7 @@ static int upload_file(pp_ctx* ctx, TokState* T, int fd, uint64_t n, uint8_t* la
         if (e != cudaSuccess) { cuda_err = (int)e; err = 2; }
     };
     std::vector<std::thread> th;
-    for (int r = 1; r < TK_READERS; ++r) th.emplace_back(work, r);
+    for (int r = 1; r < R; ++r) th.emplace_back(work, r);
     work(0);
     for (auto& t : th) t.join();
     if (err == 1) return PP_ERR_IO;
@@ -540,6 +544,16 @@ extern "C" int pp_set_parser(pp_ctx* ctx, int mode) {
     return PP_OK;
 }
 extern "C" int pp_get_parser(const pp_ctx* ctx) { return ctx ? ctx->parser : 0; }
+
+// Host threads that stream a SAM file into the device (0 = from the core count: a quarter of them, 2..16).
+extern "C" int pp_tok_set_readers(pp_ctx* ctx, int n) {
+    if (!ctx || n < 0 || n > TK_READERS) return PP_ERR_ARG;
+    TokState* T = nullptr;
+    int rc = tok_state(ctx, &T);
+    if (rc) return rc;
+    T->readers = n;
+    return PP_OK;
+}
 
 extern "C" int pp_tok_finish(pp_ctx* ctx) {
     if (!ctx) return PP_ERR_ARG;
