@@ -159,6 +159,24 @@ static void run_shard(ShardJob* j, const pp_polish_params* prm) {
     if (j->rc != PP_OK) j->err = pp_last_error(j->ctx);
 }
 
+// The resident dataset of a context copied back into host vectors (pp_dataset_download).
+struct HostCopy {
+    std::vector<uint32_t> contig, ref_start, read_id, seq_off, cigar_off, nm, cigar_ops;
+    std::vector<uint16_t> seq_len, n_cigar;
+    std::vector<uint8_t> flags, seq_pool;
+    int fetch(pp_ctx* ctx, pp_alignments* v) {
+        int rc = pp_dataset_sizes(ctx, v);
+        if (rc != PP_OK) return rc;
+        const size_t n = (size_t)v->n_aln;
+        contig.resize(n); ref_start.resize(n); read_id.resize(n); seq_off.resize(n); cigar_off.resize(n); nm.resize(n);
+        seq_len.resize(n); n_cigar.resize(n); flags.resize(n); cigar_ops.resize((size_t)v->n_cigar_ops); seq_pool.resize((size_t)v->seq_pool_bytes + 64);
+        v->contig = contig.data(); v->ref_start = ref_start.data(); v->read_id = read_id.data(); v->seq_off = seq_off.data();
+        v->cigar_off = cigar_off.data(); v->nm = nm.data(); v->seq_len = seq_len.data(); v->n_cigar = n_cigar.data(); v->flags = flags.data();
+        v->cigar_ops = cigar_ops.data(); v->seq_pool = seq_pool.data();
+        return pp_dataset_download(ctx, v);
+    }
+};
+
 // SAM files -> resident dataset through the device tokeniser (tok_kernels.cu).  PP_OK, PP_TOK_HOST (the host packer must
 // look at the text), or an error.  `log` collects the per-file lines add_to_pileup prints (alignment.rs:266-271).
 static int tokenise_files(pp_ctx* ctx, const pp_fasta* fa, const char* const* sams, int n_sams, bool careful, std::string& log,
@@ -224,62 +242,50 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
 
     // one job per GPU; with one GPU the job is the whole assembly
     const uint32_t n_shards = debug ? 1u : (uint32_t)std::max(1, std::min<int>(n_ctx, (int)contigs.n_contigs));   // the debug TSV is written from one GPU
-    std::vector<ShardJob> jobs(n_shards);
+    std::vector<ShardJob> jobs;
     int rc = PP_OK;
     pp_alignments alns;
-    memset(&alns, 0, sizeof alns);
     pp_pack* pk = nullptr;
-    bool resident = false;
+    pp_shards* shards = nullptr;
     std::string tok_timing;
-    if (n_shards == 1 && !debug && n_sams > 0 && pp_get_parser(ctx) == 0) {
-        // Fast path: the SAM text is parsed in HBM.  Anything unusual (PP_TOK_HOST, or a data error the polish kernels raise,
-        // whose message needs read / reference names) is handed to the host packer below, which decides.
+    HostCopy tok_copy;                       // the tokenised arrays back on the host (several GPUs: the sharder works there)
+    if (debug) pp_polish_set_debug(ctx, 1);
+    // Pass 0 parses the SAM text in HBM (tok_kernels.cu).  Anything unusual - PP_TOK_HOST, or a data error raised by the polish
+    // kernels, whose message needs read / reference names - repeats the load with the host packer (pass 1), which decides.
+    for (int pass = (!debug && n_sams > 0 && pp_get_parser(ctx) == 0) ? 0 : 1; pass < 2; ++pass) {
+        jobs.assign(n_shards, ShardJob());
+        memset(&alns, 0, sizeof alns);
+        bool resident = false;
+        rc = PP_OK;
         std::string log;
-        uint64_t n_aln = 0;
-        rc = tokenise_files(ctx, fa, sams, n_sams, prm->careful != 0, log, tok_timing, &n_aln);
-        if (rc == PP_OK) {
-            jobs[0].ctx = ctx; jobs[0].contigs = contigs; jobs[0].resident = true; jobs[0].alns.n_aln = n_aln;
-            run_shard(&jobs[0], prm);
-            if (jobs[0].rc == PP_OK) {
-                resident = true;
-                alns.n_aln = n_aln;
-                if (verbose) fputs(log.c_str(), stderr);
-            } else if (jobs[0].rc != PP_ERR_INPUT) {
-                rc = pp_ctx_fail(ctx, jobs[0].rc, jobs[0].err.c_str());
+        if (pass == 0) {
+            uint64_t n_aln = 0;
+            rc = tokenise_files(ctx, fa, sams, n_sams, prm->careful != 0, log, tok_timing, &n_aln);
+            if (rc == PP_TOK_HOST) continue;
+            if (rc == PP_OK && n_shards > 1) rc = tok_copy.fetch(ctx, &alns);
+            if (rc != PP_OK) { pp_fasta_free(fa); return rc; }
+            resident = n_shards == 1;
+            alns.n_aln = n_aln;
+        } else {
+            pk = pp_pack_create(fa, prm->careful);
+            for (int i = 0; i < n_sams && rc == PP_OK; ++i) {
+                rc = pp_pack_add_sam_file(pk, sams[i]);
+                if (rc == PP_OK && verbose) {
+                    uint64_t na = 0, nr = 0;
+                    pp_pack_file_stats(pk, (uint32_t)i, &na, &nr);
+                    fprintf(stderr, "%s: %s alignments from %s reads\n", sams[i], fmt_thousands(na).c_str(), fmt_thousands(nr).c_str());
+                }
+            }
+            if (rc == PP_OK) rc = pp_pack_finish(pk, &alns);
+            if (rc != PP_OK) {
+                rc = pp_ctx_fail(ctx, rc, pp_pack_error(pk));
+                pp_pack_free(pk);
                 pp_fasta_free(fa);
                 return rc;
             }
-        } else if (rc != PP_TOK_HOST) {
-            pp_fasta_free(fa);
-            return rc;
         }
-        rc = PP_OK;
-    }
-    if (!resident) {
-        jobs[0] = ShardJob();
-        pk = pp_pack_create(fa, prm->careful);
-        for (int i = 0; i < n_sams && rc == PP_OK; ++i) {
-            rc = pp_pack_add_sam_file(pk, sams[i]);
-            if (rc == PP_OK && verbose) {
-                uint64_t na = 0, nr = 0;
-                pp_pack_file_stats(pk, (uint32_t)i, &na, &nr);
-                fprintf(stderr, "%s: %s alignments from %s reads\n", sams[i], fmt_thousands(na).c_str(), fmt_thousands(nr).c_str());
-            }
-        }
-        if (rc == PP_OK) rc = pp_pack_finish(pk, &alns);
-        if (rc != PP_OK) {
-            rc = pp_ctx_fail(ctx, rc, pp_pack_error(pk));
-            pp_pack_free(pk);
-            pp_fasta_free(fa);
-            return rc;
-        }
-    }
-
-    if (debug) pp_polish_set_debug(ctx, 1);
-    pp_shards* shards = nullptr;
-    if (!resident) {
         if (n_shards == 1) {
-            jobs[0].ctx = ctx; jobs[0].contigs = contigs; jobs[0].alns = alns;
+            jobs[0].ctx = ctx; jobs[0].contigs = contigs; jobs[0].alns = alns; jobs[0].resident = resident;
         } else {
             shards = pp_shards_build(&contigs, &alns, n_shards);
             for (uint32_t s = 0; s < n_shards; ++s) {
@@ -291,6 +297,15 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
         for (uint32_t s = 1; s < n_shards; ++s) th.emplace_back(run_shard, &jobs[s], prm);
         run_shard(&jobs[0], prm);
         for (auto& t : th) t.join();
+        bool data_error = false;
+        for (auto& j : jobs) data_error |= j.rc == PP_ERR_INPUT;
+        if (pass == 0 && data_error) {
+            if (shards) { pp_shards_free(shards); shards = nullptr; }
+            tok_timing.clear();
+            continue;
+        }
+        if (verbose) fputs(log.c_str(), stderr);
+        break;
     }
     uint64_t n_used = 0;
     for (uint32_t s = 0; s < n_shards && rc == PP_OK; ++s) {
@@ -299,7 +314,7 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
         if (j.rc == PP_OK) continue;
         rc = j.rc;
         std::string m = j.err;
-        if (rc == PP_ERR_INPUT && j.res.error_aln >= 0 && n_shards == 1) {
+        if (rc == PP_ERR_INPUT && j.res.error_aln >= 0 && n_shards == 1 && pk) {
             // re-word device-detected errors with the names the reference prints (alignment.rs:190-198,298-300)
             const char* rn = pp_pack_read_name(pk, (uint64_t)j.res.error_aln);
             if (m.rfind("query name", 0) == 0)
