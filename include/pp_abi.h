@@ -259,6 +259,13 @@ typedef struct {
 int pp_tok_begin(pp_ctx* ctx, const pp_fasta* assembly, int careful, int seq_bits /* 4 | 8 */);
 int pp_tok_add_text(pp_ctx* ctx, const char* text, size_t len, pp_tok_stats* stats /* may be NULL */);
 int pp_tok_add_file(pp_ctx* ctx, const char* path, pp_tok_stats* stats /* may be NULL */);
+/* Several files in order, pipelined: file i+1 streams into a second text buffer while file i is tokenised. */
+int pp_tok_add_files(pp_ctx* ctx, const char* const* paths, int n_paths, pp_tok_stats* stats /* [n_paths] or NULL */);
+/* Optional, any time after pp_create: start streaming `path` into HBM in the background (one outstanding upload);
+ * the next pp_tok_add_file(s) that starts with the same path picks it up.  Lets the upload overlap the FASTA load. */
+int pp_tok_prefetch(pp_ctx* ctx, const char* path);
+/* Optional, after pp_tok_begin: total bytes of all the files to come, so that the arrays are sized once. */
+int pp_tok_expect(pp_ctx* ctx, uint64_t total_text_bytes);
 int pp_tok_finish(pp_ctx* ctx);        /* the tokenised alignments + the assembly become the resident dataset */
 /* Which parser pp_polish_files uses for its SAM files: 0 (default) the device tokeniser, with the host packer taking over
  * on PP_TOK_HOST and for --debug / multi-GPU runs; 1 the host packer only.  Both give the same bytes. */

@@ -137,6 +137,9 @@ def lib():
     L.pp_tok_add_text.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(TokStats)]
     L.pp_tok_add_file.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(TokStats)]
     L.pp_tok_finish.argtypes = [C.c_void_p]
+    L.pp_tok_add_files.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(TokStats)]
+    L.pp_tok_prefetch.argtypes = [C.c_void_p, C.c_char_p]
+    L.pp_tok_expect.argtypes = [C.c_void_p, C.c_uint64]
     L.pp_set_parser.argtypes = [C.c_void_p, C.c_int]
     L.pp_get_parser.argtypes = [C.c_void_p]
     L.pp_tok_set_readers.argtypes = [C.c_void_p, C.c_int]
@@ -358,17 +361,20 @@ class Context:
         if rc != PP_OK:
             raise self._err(rc)
         stats = []
-        for src in sources:
-            st = TokStats()
-            if isinstance(src, (bytes, bytearray)):
-                rc = L.pp_tok_add_text(self.h, bytes(src), len(src), C.byref(st))
-            else:
-                rc = L.pp_tok_add_file(self.h, str(src).encode(), C.byref(st))
+        if sources and not any(isinstance(x, (bytes, bytearray)) for x in sources):
+            # files: the pipelined call (file i+1 streams in while file i is tokenised)
+            L.pp_tok_expect(self.h, sum(os.path.getsize(str(x)) for x in sources if os.path.exists(str(x))))
+            arr = (C.c_char_p * len(sources))(*[str(x).encode() for x in sources])
+            sts = (TokStats * len(sources))()
+            rc = L.pp_tok_add_files(self.h, arr, len(sources), sts)
             if rc < 0:
                 raise self._err(rc)
-            stats.append(st.as_dict())
+            stats = [st.as_dict() for st in sts]
             if rc != PP_OK:
                 return rc, stats
+            sources = []
+        for src in sources:
+            st = TokStats()
         rc = L.pp_tok_finish(self.h)
         if rc != PP_OK:
             raise self._err(rc)

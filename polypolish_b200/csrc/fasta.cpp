@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <unordered_set>
 
+#include <sys/stat.h>
+
 #include "pp_internal.h"
 
 namespace pp {
@@ -52,6 +54,11 @@ bool file_exists(const std::string& path) {
     if (!f) return false;
     fclose(f);
     return true;
+}
+
+uint64_t file_size(const std::string& path) {
+    struct stat sb;
+    return stat(path.c_str(), &sb) == 0 ? (uint64_t)sb.st_size : 0;
 }
 
 bool parse_uint(std::string_view s, uint64_t maxv, uint64_t& out) {

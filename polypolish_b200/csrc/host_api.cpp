@@ -186,15 +186,17 @@ static int tokenise_files(pp_ctx* ctx, const pp_fasta* fa, const char* const* sa
         log.clear(); timing.clear();
         *n_aln = 0;
         int rc = pp_tok_begin(ctx, fa, careful ? 1 : 0, bits);
+        uint64_t total = 0;
+        for (int i = 0; i < n_sams; ++i) total += pp::file_size(sams[i]);
+        if (rc == PP_OK) rc = pp_tok_expect(ctx, total);
+        std::vector<pp_tok_stats> st((size_t)n_sams);
+        if (rc == PP_OK) rc = pp_tok_add_files(ctx, sams, n_sams, st.data());
         for (int i = 0; i < n_sams && rc == PP_OK; ++i) {
-            pp_tok_stats st;
-            rc = pp_tok_add_file(ctx, sams[i], &st);
-            if (rc != PP_OK) break;
-            *n_aln += st.alignments;
-            log += std::string(sams[i]) + ": " + fmt_thousands(st.alignments) + " alignments from " + fmt_thousands(st.reads) + " reads\n";
+            *n_aln += st[i].alignments;
+            log += std::string(sams[i]) + ": " + fmt_thousands(st[i].alignments) + " alignments from " + fmt_thousands(st[i].reads) + " reads\n";
             char tmp[256];
-            snprintf(tmp, sizeof tmp, "SAM tokeniser %s: %s lines, text to HBM %.3f ms, %u kernels %.3f ms\n", sams[i], fmt_thousands(st.lines).c_str(),
-                     st.h2d_ms, st.launches, st.device_ms);
+            snprintf(tmp, sizeof tmp, "SAM tokeniser %s: %s lines, text to HBM %.3f ms, %u kernels %.3f ms\n", sams[i], fmt_thousands(st[i].lines).c_str(),
+                     st[i].h2d_ms, st[i].launches, st[i].device_ms);
             timing += tmp;
         }
         if (rc == PP_TOK_NEED8 && bits == 4) { bits = 8; continue; }
@@ -228,6 +230,8 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     }
     struct FileCloser { FILE*& f; ~FileCloser() { if (f) fclose(f); } } closer{debug_file};
 
+    // the first SAM file starts streaming into HBM while the assembly is loaded
+    if (!debug && n_sams > 0 && pp_get_parser(ctx) == 0) pp_tok_prefetch(ctx, sams[0]);
     char ebuf[1024];
     pp_fasta* fa = pp_fasta_load(assembly, ebuf, sizeof ebuf);
     if (!fa) return pp_ctx_fail(ctx, PP_ERR_INPUT, ebuf);

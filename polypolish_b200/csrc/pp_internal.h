@@ -30,6 +30,7 @@ inline void for_each_line(const char* data, size_t n, F&& f) {
 bool read_file(const std::string& path, std::string& out);
 bool read_gz_file(const std::string& path, std::string& out);
 bool file_exists(const std::string& path);
+uint64_t file_size(const std::string& path);   // 0 when it cannot be stat'ed
 
 // Rust "123".parse::<u32/usize>(): optional '+', >= 1 ASCII digit, overflow is an error.
 bool parse_uint(std::string_view s, uint64_t maxv, uint64_t& out);

@@ -224,12 +224,29 @@ struct TokState {
     cudaEvent_t rev[TK_READERS][2] = {};
     int readers = 0;                      // threads in use (pp_tok_set_readers, default from the core count)
     int ring = 0;                         // readers whose slots / stream exist
+    // text buffers: one being tokenised, one being filled by the background upload of the next file
+    DevBuf text[2];
+    int next_buf = 0;
+    uint64_t expect_total = 0;            // pp_tok_expect: bytes of all the files of this dataset (sizes the arrays once)
+    struct Prefetch {
+        std::thread th;
+        bool active = false;
+        std::string path;
+        int buf = 0;
+        uint64_t n = 0;
+        uint8_t last = '\n';
+        int rc = PP_OK;                   // PP_OK, PP_ERR_IO, PP_ERR_CUDA
+        int cuda_err = 0;
+        float ms = 0;
+    } pf;
     DevBuf cub;
 };
 
 void pp_tok_release(pp_ctx* ctx) {
     TokState* T = ctx->tok;
     if (!T) return;
+    if (T->pf.active && T->pf.th.joinable()) T->pf.th.join();
+    T->text[0].release(); T->text[1].release();
     for (int r = 0; r < TK_READERS; ++r) {
         for (int k = 0; k < 2; ++k) {
             if (T->pin[r][k]) cudaFreeHost(T->pin[r][k]);
@@ -298,14 +315,14 @@ extern "C" int pp_tok_begin(pp_ctx* ctx, const pp_fasta* fa, int careful, int se
     T->tb.nibtab = base + im.o_nib;
     T->fasta = fa; T->careful = careful != 0; T->seq_bits = seq_bits;
     T->aln_base = T->ops_base = T->blk_base = T->read_base = 0;
+    T->expect_total = 0;
     T->active = true;
     return PP_OK;
 }
 
-// The text is in ctx->b[B_TEXT] (n bytes, zero padded).  Appends its alignments to the dataset under construction.
-static int tok_process(pp_ctx* ctx, TokState* T, uint64_t n, bool unterminated, pp_tok_stats* stats) {
+// The text is on the device (n bytes, zero padded).  Appends its alignments to the dataset under construction.
+static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n, bool unterminated, pp_tok_stats* stats) {
     cudaStream_t s = ctx->stream;
-    const uint8_t* text = ctx->b[B_TEXT].as<uint8_t>();
     uint32_t launches = 0;
     CK(cudaEventRecord(ctx->ev[0], s));
     // ---- lines
@@ -371,14 +388,18 @@ static int tok_process(pp_ctx* ctx, TokState* T, uint64_t n, bool unterminated, 
     // ---- dataset arrays (kept across files)
     const uint64_t A0 = T->aln_base, A1 = A0 + n_al;
     const size_t blk_bytes = T->seq_bits == 4 ? 16 : 32;
+    // first file of a dataset whose total text size is known: size the arrays for all of it (no regrowth, no cudaFree later)
+    double grow = 1.0;
+    if (A0 == 0 && T->expect_total > n && n > 0) grow = std::min(64.0, 1.03 * (double)T->expect_total / (double)n);
+    auto want = [&](uint64_t items, size_t each) { return (size_t)((double)items * grow) * each; };
     int rc;
     for (int w : {B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_CIGOFF, B_NM})
-        if ((rc = ensure_keep(ctx, w, A1 * 4 + 64, A0 * 4))) return rc;
+        if ((rc = ensure_keep(ctx, w, std::max<size_t>(A1 * 4, want(n_al, 4)) + 64, A0 * 4))) return rc;
     for (int w : {B_SEQLEN, B_NCIG})
-        if ((rc = ensure_keep(ctx, w, A1 * 2 + 64, A0 * 2))) return rc;
-    if ((rc = ensure_keep(ctx, B_FLAGS, A1 + 64, A0))) return rc;
-    if ((rc = ensure_keep(ctx, B_CIGOPS, (T->ops_base + n_ops) * 4 + 64, T->ops_base * 4))) return rc;
-    if ((rc = ensure_keep(ctx, B_SEQPOOL, (T->blk_base + n_blk) * blk_bytes + 256, T->blk_base * blk_bytes))) return rc;
+        if ((rc = ensure_keep(ctx, w, std::max<size_t>(A1 * 2, want(n_al, 2)) + 64, A0 * 2))) return rc;
+    if ((rc = ensure_keep(ctx, B_FLAGS, std::max<size_t>(A1, want(n_al, 1)) + 64, A0))) return rc;
+    if ((rc = ensure_keep(ctx, B_CIGOPS, std::max<size_t>((T->ops_base + n_ops) * 4, want(n_ops, 4)) + 64, T->ops_base * 4))) return rc;
+    if ((rc = ensure_keep(ctx, B_SEQPOOL, std::max<size_t>((T->blk_base + n_blk) * blk_bytes, want(n_blk, blk_bytes)) + 256, T->blk_base * blk_bytes))) return rc;
     // per-alignment scratch of this file: QNAME position / length, group heads, their running count
     size_t off2 = 0;
     auto carve2 = [&](size_t bytes) { size_t o = off2; off2 += (bytes + 255) & ~size_t(255); return o; };
@@ -429,10 +450,10 @@ static int tok_process(pp_ctx* ctx, TokState* T, uint64_t n, bool unterminated, 
     return PP_OK;
 }
 
-static int text_buffer(pp_ctx* ctx, uint64_t n) {
-    CK(ctx->b[B_TEXT].ensure(n + 64));
+static int text_buffer(pp_ctx* ctx, DevBuf& tb, uint64_t n) {
+    CK(tb.ensure(n + 64));
     const uint64_t n16 = (n + 15) & ~15ull;
-    CK(cudaMemsetAsync(ctx->b[B_TEXT].as<uint8_t>() + n, 0, (size_t)(n16 + 32 - n), ctx->stream));
+    CK(cudaMemsetAsync(tb.as<uint8_t>() + n, 0, (size_t)(n16 + 32 - n), ctx->stream));   // the copies never touch [n, ...)
     return PP_OK;
 }
 
@@ -443,38 +464,29 @@ extern "C" int pp_tok_add_text(pp_ctx* ctx, const char* text, size_t len, pp_tok
     if (!text && len) return ctx->fail(PP_ERR_ARG, "pp_tok_add_text: null text");
     CK(cudaSetDevice(ctx->device));
     if (stats) memset(stats, 0, sizeof *stats);
-    int rc = text_buffer(ctx, len);
+    if (T->pf.active) { if (T->pf.th.joinable()) T->pf.th.join(); T->pf.active = false; }
+    DevBuf& tb = T->text[T->next_buf];
+    T->next_buf ^= 1;
+    int rc = text_buffer(ctx, tb, len);
     if (rc) return rc;
     const auto t0 = std::chrono::steady_clock::now();
-    if (len) CK(cudaMemcpyAsync(ctx->b[B_TEXT].p, text, len, cudaMemcpyHostToDevice, ctx->stream));
+    if (len) CK(cudaMemcpyAsync(tb.p, text, len, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (stats) stats->h2d_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    rc = tok_process(ctx, T, len, len > 0 && text[len - 1] != '\n', stats);
+    const float h2d = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    rc = tok_process(ctx, T, tb.as<uint8_t>(), len, len > 0 && text[len - 1] != '\n', stats);
+    if (stats) stats->h2d_ms = h2d;
     if (rc != PP_OK) T->active = false;
     return rc;
 }
 
-// Streams a file into ctx->b[B_TEXT]: TK_READERS threads, each pread()s its slices into its two pinned slots and sends
-// them on its own stream, so that disk/page-cache reads, pinned staging and PCIe overlap.
-static int upload_file(pp_ctx* ctx, TokState* T, int fd, uint64_t n, uint8_t* last_byte) {
-    if (T->readers <= 0) {
-        const unsigned hw = std::thread::hardware_concurrency();
-        T->readers = (int)std::min<unsigned>(TK_READERS, std::max<unsigned>(2, hw / 4));
-    }
+// Streams a file into dst: T->readers host threads, each pread()s its slices into its two pinned slots and sends them on
+// its own stream, so that page-cache reads, pinned staging and PCIe overlap.  Runs on the caller's thread or on the
+// prefetch thread; touches neither ctx->err nor ctx->stream.  Returns PP_OK / PP_ERR_IO / PP_ERR_CUDA (+ *cuda_err).
+static int upload_file(int device, TokState* T, uint8_t* dst, int fd, uint64_t n, uint8_t* last_byte, int* cuda_err) {
     const int R = T->readers;
-    for (int r = T->ring; r < R; ++r) {
-        CK(cudaStreamCreateWithFlags(&T->rstream[r], cudaStreamNonBlocking));
-        for (int k = 0; k < 2; ++k) {
-            CK(cudaHostAlloc((void**)&T->pin[r][k], TK_SLOT, cudaHostAllocDefault));
-            CK(cudaEventCreateWithFlags(&T->rev[r][k], cudaEventDisableTiming));
-        }
-        T->ring = r + 1;
-    }
-    uint8_t* dst = ctx->b[B_TEXT].as<uint8_t>();
     const uint64_t n_slices = (n + TK_SLOT - 1) / TK_SLOT;
     std::atomic<int> err{0};           // 1 = read error, 2 = CUDA error
-    std::atomic<int> cuda_err{0};
-    const int device = ctx->device;
+    std::atomic<int> cerr{0};
     auto work = [&](int r) {
         if (cudaSetDevice(device) != cudaSuccess) { err = 2; return; }
         uint64_t k = 0;
@@ -482,7 +494,7 @@ static int upload_file(pp_ctx* ctx, TokState* T, int fd, uint64_t n, uint8_t* la
             const int slot = (int)(k & 1);
             if (k >= 2) {
                 cudaError_t e = cudaEventSynchronize(T->rev[r][slot]);
-                if (e != cudaSuccess) { cuda_err = (int)e; err = 2; return; }
+                if (e != cudaSuccess) { cerr = (int)e; err = 2; return; }
             }
             const uint64_t o = sl * TK_SLOT, len = std::min<uint64_t>(TK_SLOT, n - o);
             uint64_t got = 0;
@@ -494,48 +506,130 @@ static int upload_file(pp_ctx* ctx, TokState* T, int fd, uint64_t n, uint8_t* la
             if (o + len == n) *last_byte = T->pin[r][slot][len - 1];
             cudaError_t e = cudaMemcpyAsync(dst + o, T->pin[r][slot], (size_t)len, cudaMemcpyHostToDevice, T->rstream[r]);
             if (e == cudaSuccess) e = cudaEventRecord(T->rev[r][slot], T->rstream[r]);
-            if (e != cudaSuccess) { cuda_err = (int)e; err = 2; return; }
+            if (e != cudaSuccess) { cerr = (int)e; err = 2; return; }
         }
         cudaError_t e = cudaStreamSynchronize(T->rstream[r]);
-        if (e != cudaSuccess) { cuda_err = (int)e; err = 2; }
+        if (e != cudaSuccess) { cerr = (int)e; err = 2; }
     };
     std::vector<std::thread> th;
     for (int r = 1; r < R; ++r) th.emplace_back(work, r);
     work(0);
     for (auto& t : th) t.join();
-    if (err == 1) return PP_ERR_IO;
-    if (err == 2) return ctx->fail_cuda((cudaError_t)cuda_err.load(), "SAM text upload", __FILE__, __LINE__);
+    *cuda_err = cerr.load();
+    return err == 1 ? PP_ERR_IO : err == 2 ? PP_ERR_CUDA : PP_OK;
+}
+
+static int ring_ready(pp_ctx* ctx, TokState* T) {
+    if (T->readers <= 0) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        T->readers = (int)std::min<unsigned>(TK_READERS, std::max<unsigned>(2, hw / 4));
+    }
+    for (int r = T->ring; r < T->readers; ++r) {
+        CK(cudaStreamCreateWithFlags(&T->rstream[r], cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaHostAlloc((void**)&T->pin[r][k], TK_SLOT, cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&T->rev[r][k], cudaEventDisableTiming));
+        }
+        T->ring = r + 1;
+    }
     return PP_OK;
 }
 
-extern "C" int pp_tok_add_file(pp_ctx* ctx, const char* path, pp_tok_stats* stats) {
-    if (!ctx) return PP_ERR_ARG;
-    TokState* T = ctx->tok;
-    if (!T || !T->active) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: no pp_tok_begin");
-    if (!path) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: null path");
-    CK(cudaSetDevice(ctx->device));
-    if (stats) memset(stats, 0, sizeof *stats);
+// Starts streaming `path` into the next text buffer on a background thread.  PP_OK, PP_TOK_HOST (not a plain readable
+// file) or an error.
+static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path) {
     const int fd = open(path, O_RDONLY);
     struct stat sb;
     if (fd < 0 || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
         if (fd >= 0) close(fd);
-        T->active = false;
-        return PP_TOK_HOST;                                  // not a plain readable file: the host path reports it
+        return PP_TOK_HOST;
     }
     const uint64_t n = (uint64_t)sb.st_size;
-    int rc = text_buffer(ctx, n);
-    if (rc == PP_OK) rc = (cudaStreamSynchronize(ctx->stream) == cudaSuccess) ? PP_OK : ctx->fail(PP_ERR_CUDA, "CUDA error before the SAM upload");
-    uint8_t last = '\n';
-    const auto t0 = std::chrono::steady_clock::now();
-    if (rc == PP_OK && n) rc = upload_file(ctx, T, fd, n, &last);
-    close(fd);
-    if (rc == PP_ERR_IO) { T->active = false; return PP_TOK_HOST; }
-    if (rc != PP_OK) { T->active = false; return rc; }
-    const float h2d = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    rc = tok_process(ctx, T, n, n > 0 && last != '\n', stats);
-    if (stats) stats->h2d_ms = h2d;
-    if (rc != PP_OK) T->active = false;
-    return rc;
+    const int buf = T->next_buf;
+    int rc = ring_ready(ctx, T);
+    if (rc == PP_OK) rc = text_buffer(ctx, T->text[buf], n);
+    if (rc != PP_OK) { close(fd); return rc; }
+    T->next_buf ^= 1;
+    TokState::Prefetch& pf = T->pf;
+    pf.active = true; pf.path = path; pf.buf = buf; pf.n = n; pf.last = '\n'; pf.rc = PP_OK; pf.cuda_err = 0; pf.ms = 0;
+    uint8_t* dst = T->text[buf].as<uint8_t>();
+    const int device = ctx->device;
+    pf.th = std::thread([T, dst, fd, n, device] {
+        TokState::Prefetch& q = T->pf;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (n) q.rc = upload_file(device, T, dst, fd, n, &q.last, &q.cuda_err);
+        close(fd);
+        q.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    });
+    return PP_OK;
+}
+
+// Waits for the text of `path` (starting its upload now if nobody asked for it before).
+static int prefetch_wait(pp_ctx* ctx, TokState* T, const char* path) {
+    TokState::Prefetch& pf = T->pf;
+    if (pf.active && pf.path != path) {                       // something else was prefetched: let it finish, drop it
+        if (pf.th.joinable()) pf.th.join();
+        pf.active = false;
+    }
+    if (!pf.active) {
+        const int rc = prefetch_start(ctx, T, path);
+        if (rc != PP_OK) return rc;
+    }
+    if (pf.th.joinable()) pf.th.join();
+    pf.active = false;
+    if (pf.rc == PP_ERR_IO) return PP_TOK_HOST;               // the host path reports unreadable files
+    if (pf.rc == PP_ERR_CUDA) return ctx->fail_cuda((cudaError_t)pf.cuda_err, "SAM text upload", __FILE__, __LINE__);
+    return PP_OK;
+}
+
+extern "C" int pp_tok_prefetch(pp_ctx* ctx, const char* path) {
+    if (!ctx || !path) return PP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    TokState* T = nullptr;
+    int rc = tok_state(ctx, &T);
+    if (rc) return rc;
+    if (T->pf.active) return PP_OK;                            // one outstanding upload at a time
+    rc = prefetch_start(ctx, T, path);
+    return rc == PP_TOK_HOST ? PP_OK : rc;                     // pp_tok_add_file(s) will say so
+}
+
+extern "C" int pp_tok_expect(pp_ctx* ctx, uint64_t total_text_bytes) {
+    if (!ctx) return PP_ERR_ARG;
+    TokState* T = nullptr;
+    int rc = tok_state(ctx, &T);
+    if (rc) return rc;
+    T->expect_total = total_text_bytes;
+    return PP_OK;
+}
+
+extern "C" int pp_tok_add_files(pp_ctx* ctx, const char* const* paths, int n_paths, pp_tok_stats* stats) {
+    if (!ctx) return PP_ERR_ARG;
+    TokState* T = ctx->tok;
+    if (!T || !T->active) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: no pp_tok_begin");
+    if (!paths || n_paths < 0) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: null paths");
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof(pp_tok_stats) * (size_t)n_paths);
+    for (int i = 0; i < n_paths; ++i) {
+        if (!paths[i]) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: null path");
+        int rc = prefetch_wait(ctx, T, paths[i]);
+        if (rc != PP_OK) { T->active = false; return rc; }
+        const int buf = T->pf.buf;
+        const uint64_t n = T->pf.n;
+        const bool unterminated = n > 0 && T->pf.last != '\n';
+        const float h2d = T->pf.ms;
+        if (i + 1 < n_paths && paths[i + 1]) {                 // the next file streams in while this one is tokenised
+            rc = prefetch_start(ctx, T, paths[i + 1]);
+            if (rc < 0) { T->active = false; return rc; }
+        }
+        rc = tok_process(ctx, T, T->text[buf].as<uint8_t>(), n, unterminated, stats ? stats + i : nullptr);
+        if (stats) stats[i].h2d_ms = h2d;
+        if (rc != PP_OK) { T->active = false; return rc; }
+    }
+    return PP_OK;
+}
+
+extern "C" int pp_tok_add_file(pp_ctx* ctx, const char* path, pp_tok_stats* stats) {
+    return pp_tok_add_files(ctx, &path, 1, stats);
 }
 
 extern "C" int pp_set_parser(pp_ctx* ctx, int mode) {
