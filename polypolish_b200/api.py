@@ -375,6 +375,15 @@ class Context:
             sources = []
         for src in sources:
             st = TokStats()
+            if isinstance(src, (bytes, bytearray)):
+                rc = L.pp_tok_add_text(self.h, bytes(src), len(src), C.byref(st))
+            else:
+                rc = L.pp_tok_add_file(self.h, str(src).encode(), C.byref(st))
+            if rc < 0:
+                raise self._err(rc)
+            stats.append(st.as_dict())
+            if rc != PP_OK:
+                return rc, stats
         rc = L.pp_tok_finish(self.h)
         if rc != PP_OK:
             raise self._err(rc)
