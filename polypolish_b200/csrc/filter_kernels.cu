@@ -29,15 +29,7 @@ cudaEvent_t pp_ctx_event(pp_ctx* ctx, int i);
 
 #define CKF(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return pp_ctx_fail_cuda(ctx, e_, #x, "filter_kernels.cu", __LINE__); } while (0)
 
-struct Mate {
-    const uint32_t *name_id, *contig, *ref_start, *ref_end;
-    const uint8_t* flags;
-    uint32_t* cnt;     // [n_names] aligned records per name
-    uint32_t* head;    // [n_names] list head (record index) or 0xFFFFFFFF
-    uint32_t* next;    // [n] next record of the same name
-    uint8_t* pass;     // [n]
-    uint32_t n;
-};
+#include "filter_dev.h"
 
 struct FilterDev {
     Mate m[2];
@@ -49,7 +41,7 @@ struct FilterDev {
     uint32_t* hist;            // [2][256]
     uint32_t* sel_prefix;      // [2]
     unsigned long long* sel_rank; // [2] remaining rank (1-based) inside the current prefix
-    unsigned long long* n_pass;
+    unsigned long long* n_pass;   // [2] passing records per mate
 };
 
 // filter.rs:189-218.  Orientation codes: 0 fr, 1 rf, 2 ff, 3 rr.
@@ -158,7 +150,7 @@ __global__ void __launch_bounds__(256) k_f_pass(FilterDev f, int which, uint32_t
         npass += pass;
     }
     for (int o = 16; o > 0; o >>= 1) npass += __shfl_down_sync(0xffffffffu, npass, o);
-    if ((threadIdx.x & 31) == 0 && npass) atomicAdd(f.n_pass, npass);
+    if ((threadIdx.x & 31) == 0 && npass) atomicAdd(f.n_pass + which, npass);
 }
 
 // filter.rs:249-259: rank = max(1, ceil(p / 100 * n) as usize)
@@ -172,35 +164,21 @@ static unsigned long long nearest_rank(double percentile, unsigned long long n) 
     return rank < 1 ? 1 : rank;
 }
 
-extern "C" int pp_filter(pp_ctx* ctx, const pp_filter_mate* m1, const pp_filter_mate* m2, const pp_filter_params* prm,
-                         pp_filter_result* res) {
-    if (!ctx) return PP_ERR_ARG;
-    if (!m1 || !m2 || !prm || !res) return pp_ctx_fail(ctx, PP_ERR_ARG, "pp_filter: null argument");
-    if (m1->n >= 0xFFFFFFFFull || m2->n >= 0xFFFFFFFFull || prm->n_names >= 0xFFFFFFFFull)
-        return pp_ctx_fail(ctx, PP_ERR_ARG, "pp_filter: more than 2^32-1 records or names");
-    if ((m1->n && !res->pass1) || (m2->n && !res->pass2)) return pp_ctx_fail(ctx, PP_ERR_ARG, "pp_filter: null pass array");
-    // filter.rs:47-52
-    if (!(prm->low_pct > 0.0 && prm->low_pct < 50.0)) return pp_ctx_fail(ctx, PP_ERR_INPUT, "--low must be greater than 0 and less than 50");
-    if (!(prm->high_pct > 50.0 && prm->high_pct < 100.0)) return pp_ctx_fail(ctx, PP_ERR_INPUT, "--high must be greater than 50 and less than 100");
-    CKF(cudaSetDevice(pp_ctx_device(ctx)));
+// The filter proper on device-resident mate arrays (in[k].name_id / contig / ref_start / ref_end / flags and n set by the
+// caller; host arrays are uploaded by pp_filter, the device SAM path of tok_kernels.cu builds them in place).
+// res->pass1/pass2 may be null: the flags then stay on the device only (d_pass[k], inside the context's scratch buffer,
+// valid until the next call that uses it).  n_pass_mate[k] = passing records of mate k.
+int pp_filter_core(pp_ctx* ctx, const Mate in[2], const pp_filter_params* prm, pp_filter_result* res, const uint8_t* d_pass[2],
+                   uint64_t n_pass_mate[2]) {
     cudaStream_t s = pp_ctx_stream(ctx);
-    const pp_filter_mate* hm[2] = {m1, m2};
     const uint32_t nn = (uint32_t)prm->n_names;
-
-    // carve one scratch buffer
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
-    size_t o_in[2][5], o_cnt[2], o_head[2], o_next[2], o_pass[2];
-    for (int k = 0; k < 2; ++k) {
-        const size_t n = hm[k]->n;
-        for (int a = 0; a < 4; ++a) o_in[k][a] = carve(n * 4);
-        o_in[k][4] = carve(n);
-        o_next[k] = carve(n * 4);
-        o_pass[k] = carve(n);
-    }
+    size_t o_cnt[2], o_head[2], o_next[2], o_pass[2];
+    for (int k = 0; k < 2; ++k) { o_next[k] = carve((size_t)in[k].n * 4); o_pass[k] = carve((size_t)in[k].n + 1); }
     const size_t zero_begin = off;                       // zero-initialised block
     for (int k = 0; k < 2; ++k) o_cnt[k] = carve((size_t)nn * 4);
-    const size_t o_pairs = carve(32), o_hist = carve(512 * 4), o_selp = carve(8), o_selr = carve(16), o_np = carve(8);
+    const size_t o_pairs = carve(32), o_hist = carve(512 * 4), o_selp = carve(8), o_selr = carve(16), o_np = carve(16);
     const size_t zero_end = off;
     for (int k = 0; k < 2; ++k) o_head[k] = carve((size_t)nn * 4);   // 0xFF-initialised block
     const size_t ff_end = off;
@@ -208,19 +186,11 @@ extern "C" int pp_filter(pp_ctx* ctx, const pp_filter_mate* m1, const pp_filter_
     uint8_t* base = (uint8_t*)pp_ctx_scratch(ctx, off + 256);
     if (!base) return pp_ctx_fail(ctx, PP_ERR_NOMEM, "pp_filter: device allocation failed");
 
-    CKF(cudaEventRecord(pp_ctx_event(ctx, 0), s));
     FilterDev f;
     for (int k = 0; k < 2; ++k) {
-        const pp_filter_mate* h = hm[k];
-        const void* src[5] = {h->name_id, h->contig, h->ref_start, h->ref_end, h->flags};
-        for (int a = 0; a < 5; ++a)
-            if (h->n) CKF(cudaMemcpyAsync(base + o_in[k][a], src[a], h->n * (a < 4 ? 4 : 1), cudaMemcpyHostToDevice, s));
-        f.m[k].name_id = (const uint32_t*)(base + o_in[k][0]); f.m[k].contig = (const uint32_t*)(base + o_in[k][1]);
-        f.m[k].ref_start = (const uint32_t*)(base + o_in[k][2]); f.m[k].ref_end = (const uint32_t*)(base + o_in[k][3]);
-        f.m[k].flags = base + o_in[k][4];
+        f.m[k] = in[k];
         f.m[k].cnt = (uint32_t*)(base + o_cnt[k]); f.m[k].head = (uint32_t*)(base + o_head[k]);
         f.m[k].next = (uint32_t*)(base + o_next[k]); f.m[k].pass = base + o_pass[k];
-        f.m[k].n = (uint32_t)h->n;
     }
     f.n_names = nn;
     f.ins = (uint32_t*)(base + o_ins); f.ori = base + o_ori;
@@ -234,7 +204,7 @@ extern "C" int pp_filter(pp_ctx* ctx, const pp_filter_mate* m1, const pp_filter_
     auto grid = [&](size_t n) { return (unsigned)std::min<size_t>(std::max<size_t>((n + 255) / 256, 1), 148 * 8); };
     uint32_t launches = 0;
     for (int k = 0; k < 2; ++k)
-        if (hm[k]->n) { k_f_build<<<grid(hm[k]->n), 256, 0, s>>>(f, k); launches++; }
+        if (in[k].n) { k_f_build<<<grid(in[k].n), 256, 0, s>>>(f, k); launches++; }
     k_f_pairs<<<grid(nn), 256, 0, s>>>(f);
     launches++;
     unsigned long long pairs[4];
@@ -276,16 +246,18 @@ extern "C" int pp_filter(pp_ctx* ctx, const pp_filter_mate* m1, const pp_filter_
     res->high = in_range[1] ? thr[1] : 0;
 
     for (int k = 0; k < 2; ++k)
-        if (hm[k]->n) { k_f_pass<<<grid(hm[k]->n), 256, 0, s>>>(f, k, res->low, res->high, (uint32_t)chosen); launches++; }
+        if (in[k].n) { k_f_pass<<<grid(in[k].n), 256, 0, s>>>(f, k, res->low, res->high, (uint32_t)chosen); launches++; }
     CKF(cudaEventRecord(pp_ctx_event(ctx, 2), s));
-    if (m1->n) CKF(cudaMemcpyAsync(res->pass1, f.m[0].pass, m1->n, cudaMemcpyDeviceToHost, s));
-    if (m2->n) CKF(cudaMemcpyAsync(res->pass2, f.m[1].pass, m2->n, cudaMemcpyDeviceToHost, s));
-    unsigned long long np = 0;
-    CKF(cudaMemcpyAsync(&np, f.n_pass, 8, cudaMemcpyDeviceToHost, s));
+    if (in[0].n && res->pass1) CKF(cudaMemcpyAsync(res->pass1, f.m[0].pass, in[0].n, cudaMemcpyDeviceToHost, s));
+    if (in[1].n && res->pass2) CKF(cudaMemcpyAsync(res->pass2, f.m[1].pass, in[1].n, cudaMemcpyDeviceToHost, s));
+    unsigned long long np[2] = {0, 0};
+    CKF(cudaMemcpyAsync(np, f.n_pass, 16, cudaMemcpyDeviceToHost, s));
     CKF(cudaEventRecord(pp_ctx_event(ctx, 3), s));
     CKF(cudaStreamSynchronize(s));
     CKF(cudaGetLastError());
-    res->n_pass = np;
+    res->n_pass = np[0] + np[1];
+    if (n_pass_mate) { n_pass_mate[0] = np[0]; n_pass_mate[1] = np[1]; }
+    if (d_pass) { d_pass[0] = f.m[0].pass; d_pass[1] = f.m[1].pass; }
     memset(&res->timing, 0, sizeof res->timing);
     float ms;
     CKF(cudaEventElapsedTime(&ms, pp_ctx_event(ctx, 0), pp_ctx_event(ctx, 1))); res->timing.stage_ms[6] = ms;
@@ -295,4 +267,44 @@ extern "C" int pp_filter(pp_ctx* ctx, const pp_filter_mate* m1, const pp_filter_
     res->timing.launches = launches;
     pp_ctx_count_launches(ctx, launches);
     return PP_OK;
+}
+
+void* pp_ctx_scratch2(pp_ctx* ctx, size_t bytes);      // a second ctx-owned device buffer (inputs of pp_filter)
+
+extern "C" int pp_filter(pp_ctx* ctx, const pp_filter_mate* m1, const pp_filter_mate* m2, const pp_filter_params* prm,
+                         pp_filter_result* res) {
+    if (!ctx) return PP_ERR_ARG;
+    if (!m1 || !m2 || !prm || !res) return pp_ctx_fail(ctx, PP_ERR_ARG, "pp_filter: null argument");
+    if (m1->n >= 0xFFFFFFFFull || m2->n >= 0xFFFFFFFFull || prm->n_names >= 0xFFFFFFFFull)
+        return pp_ctx_fail(ctx, PP_ERR_ARG, "pp_filter: more than 2^32-1 records or names");
+    if ((m1->n && !res->pass1) || (m2->n && !res->pass2)) return pp_ctx_fail(ctx, PP_ERR_ARG, "pp_filter: null pass array");
+    // filter.rs:47-52
+    if (!(prm->low_pct > 0.0 && prm->low_pct < 50.0)) return pp_ctx_fail(ctx, PP_ERR_INPUT, "--low must be greater than 0 and less than 50");
+    if (!(prm->high_pct > 50.0 && prm->high_pct < 100.0)) return pp_ctx_fail(ctx, PP_ERR_INPUT, "--high must be greater than 50 and less than 100");
+    CKF(cudaSetDevice(pp_ctx_device(ctx)));
+    cudaStream_t s = pp_ctx_stream(ctx);
+    const pp_filter_mate* hm[2] = {m1, m2};
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    size_t o_in[2][5];
+    for (int k = 0; k < 2; ++k) {
+        for (int a = 0; a < 4; ++a) o_in[k][a] = carve(hm[k]->n * 4);
+        o_in[k][4] = carve(hm[k]->n);
+    }
+    uint8_t* base = (uint8_t*)pp_ctx_scratch2(ctx, off + 256);
+    if (!base) return pp_ctx_fail(ctx, PP_ERR_NOMEM, "pp_filter: device allocation failed");
+    CKF(cudaEventRecord(pp_ctx_event(ctx, 0), s));
+    Mate in[2];
+    for (int k = 0; k < 2; ++k) {
+        const pp_filter_mate* h = hm[k];
+        const void* src[5] = {h->name_id, h->contig, h->ref_start, h->ref_end, h->flags};
+        for (int a = 0; a < 5; ++a)
+            if (h->n) CKF(cudaMemcpyAsync(base + o_in[k][a], src[a], h->n * (a < 4 ? 4 : 1), cudaMemcpyHostToDevice, s));
+        in[k].name_id = (const uint32_t*)(base + o_in[k][0]); in[k].contig = (const uint32_t*)(base + o_in[k][1]);
+        in[k].ref_start = (const uint32_t*)(base + o_in[k][2]); in[k].ref_end = (const uint32_t*)(base + o_in[k][3]);
+        in[k].flags = base + o_in[k][4];
+        in[k].cnt = nullptr; in[k].head = nullptr; in[k].next = nullptr; in[k].pass = nullptr;
+        in[k].n = (uint32_t)h->n;
+    }
+    return pp_filter_core(ctx, in, prm, res, nullptr, nullptr);
 }

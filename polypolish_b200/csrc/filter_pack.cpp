@@ -128,6 +128,46 @@ extern "C" int pp_filter_files(pp_ctx* ctx, const char* in1, const char* in2, co
     if (!(low > 0.0 && low < 50.0)) return pp_ctx_fail(ctx, PP_ERR_INPUT, "--low must be greater than 0 and less than 50");
     if (!(high > 50.0 && high < 100.0)) return pp_ctx_fail(ctx, PP_ERR_INPUT, "--high must be greater than 50 and less than 100");
 
+    pp_filter_params prm;
+    std::string o = orientation;
+    prm.orientation = o == "auto" ? -1 : o == "fr" ? 0 : o == "rf" ? 1 : o == "ff" ? 2 : o == "rr" ? 3 : 4;
+    prm.low_pct = low;
+    prm.high_pct = high;
+    prm.n_names = 0;
+    pp_filter_result res;
+    memset(&res, 0, sizeof res);
+    const char* ins[2] = {in1, in2};
+    const char* outs[2] = {out1, out2};
+    const char* nm[4] = {"fr", "rf", "ff", "rr"};
+    auto log_thresholds = [&]() {
+        for (int i = 0; i < 4; ++i) fprintf(stderr, "%s: %s pairs\n", nm[i], thousands(res.pairs[i]).c_str());
+        fprintf(stderr, "\n%s correct orientation: %s\n\n", prm.orientation < 0 ? "Automatically determined" : "User-specified",
+                res.orientation < 4 ? nm[res.orientation] : orientation);
+        fprintf(stderr, "Low threshold:  %u\nHigh threshold: %u\n\n", res.low, res.high);
+    };
+
+    // Fast path: the SAM text never leaves the device between parse and write (tok_kernels.cu).  PP_TOK_HOST = something the
+    // device path leaves to the host code below (malformed line, empty file, ...), which words the reference's messages.
+    if (pp_get_parser(ctx) == 0) {
+        pp_filter_file_stats fs;
+        int rc = pp_filter_files_device(ctx, in1, in2, out1, out2, &prm, &res, &fs);
+        if (rc == PP_OK) {
+            if (verbose) {
+                for (int k = 0; k < 2; ++k) fprintf(stderr, "%s: %s alignments\n", ins[k], thousands(fs.alignments[k]).c_str());
+                log_thresholds();
+                for (int k = 0; k < 2; ++k)
+                    fprintf(stderr, "Filtering %s:\n  %s pass\n  %s fail\n\n", ins[k], thousands(fs.pass[k]).c_str(), thousands(fs.fail[k]).c_str());
+                fprintf(stderr, "Alignments before filtering: %s\nAlignments after filtering:  %s\n\n", thousands(fs.alignments[0] + fs.alignments[1]).c_str(),
+                        thousands(fs.pass[0] + fs.pass[1]).c_str());
+                fprintf(stderr, "device text path: %.3f ms (SAM to HBM %.3f ms, filtered SAM to files %.3f ms), %u kernels; filter kernels %.3f ms\n", fs.total_ms,
+                        fs.h2d_ms, fs.d2h_ms, fs.launches, res.timing.total_ms);
+            }
+            return PP_OK;
+        }
+        if (rc != PP_TOK_HOST) return rc;
+        memset(&res, 0, sizeof res);
+    }
+
     MateFile m[2];
     m[0].path = in1;
     m[1].path = in2;
@@ -146,28 +186,14 @@ extern "C" int pp_filter_files(pp_ctx* ctx, const char* in1, const char* in2, co
         fm[k].name_id = m[k].name_id.data(); fm[k].contig = m[k].contig.data(); fm[k].ref_start = m[k].ref_start.data();
         fm[k].ref_end = m[k].ref_end.data(); fm[k].flags = m[k].flags.data();
     }
-    pp_filter_params prm;
-    std::string o = orientation;
-    prm.orientation = o == "auto" ? -1 : o == "fr" ? 0 : o == "rf" ? 1 : o == "ff" ? 2 : o == "rr" ? 3 : 4;
-    prm.low_pct = low;
-    prm.high_pct = high;
     prm.n_names = names.reads.size();
     std::vector<uint8_t> pass1(fm[0].n + 1), pass2(fm[1].n + 1);
-    pp_filter_result res;
-    memset(&res, 0, sizeof res);
     res.pass1 = pass1.data();
     res.pass2 = pass2.data();
     int rc = pp_filter(ctx, &fm[0], &fm[1], &prm, &res);
     if (rc != PP_OK) return rc;
-    if (verbose) {
-        const char* nm[4] = {"fr", "rf", "ff", "rr"};
-        for (int i = 0; i < 4; ++i) fprintf(stderr, "%s: %s pairs\n", nm[i], thousands(res.pairs[i]).c_str());
-        fprintf(stderr, "\n%s correct orientation: %s\n\n", prm.orientation < 0 ? "Automatically determined" : "User-specified",
-                res.orientation < 4 ? nm[res.orientation] : orientation);
-        fprintf(stderr, "Low threshold:  %u\nHigh threshold: %u\n\n", res.low, res.high);
-    }
+    if (verbose) log_thresholds();
     uint64_t before = fm[0].n + fm[1].n, after = 0;
-    const char* outs[2] = {out1, out2};
     const uint8_t* passes[2] = {pass1.data(), pass2.data()};
     for (int k = 0; k < 2; ++k) {
         uint64_t np, nf;

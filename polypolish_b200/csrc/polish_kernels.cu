@@ -1181,6 +1181,10 @@ int pp_ctx_fail_cuda(pp_ctx* ctx, cudaError_t e, const char* what, const char* f
     ctx->err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what + " (" + file + ":" + std::to_string(line) + ")";
     return PP_ERR_CUDA;
 }
+void* pp_ctx_scratch2(pp_ctx* ctx, size_t bytes) {
+    if (ctx->b[B_SCRATCH2].ensure(bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return ctx->b[B_SCRATCH2].p;
+}
 void* pp_ctx_scratch(pp_ctx* ctx, size_t bytes) {
     if (ctx->b[B_SCRATCH].ensure(bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return ctx->b[B_SCRATCH].p;

@@ -98,3 +98,12 @@ struct pp_pack {
 };
 
 int pp_ctx_fail(pp_ctx* ctx, int code, const char* msg);
+
+// `polypolish filter` with the SAM text handled on the device (tok_kernels.cu); what the log of pp_filter_files prints.
+struct pp_filter_file_stats {
+    uint64_t alignments[2], pass[2], fail[2], text_bytes[2], out_bytes[2];
+    float h2d_ms, d2h_ms, total_ms;
+    uint32_t launches;
+};
+int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2, const pp_filter_params* prm,
+                           pp_filter_result* res, pp_filter_file_stats* fs);

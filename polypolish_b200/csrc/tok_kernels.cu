@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(TK_LINE_THREADS) k_tok_groups(uint64_t n_al, c
 
 }  // namespace
 
+struct TokFilterBufs;
+
 struct TokState {
     const pp_fasta* fasta = nullptr;
     bool careful = false, active = false;
@@ -240,11 +242,15 @@ struct TokState {
         float ms = 0;
     } pf;
     DevBuf cub;
+    TokFilterBufs* fbufs = nullptr;   // device buffers of the filter text path
 };
+
+static void free_filter_bufs(TokFilterBufs* b);
 
 void pp_tok_release(pp_ctx* ctx) {
     TokState* T = ctx->tok;
     if (!T) return;
+    if (T->fbufs) { free_filter_bufs(T->fbufs); T->fbufs = nullptr; }
     if (T->pf.active && T->pf.th.joinable()) T->pf.th.join();
     T->text[0].release(); T->text[1].release();
     for (int r = 0; r < TK_READERS; ++r) {
@@ -684,5 +690,404 @@ extern "C" int pp_dataset_download(pp_ctx* ctx, const pp_alignments* into) {
     CK(get(into->n_cigar, B_NCIG, n * 2)); CK(get(into->nm, B_NM, n * 4)); CK(get(into->flags, B_FLAGS, n));
     CK(get(into->cigar_ops, B_CIGOPS, (size_t)ctx->n_ops * 4)); CK(get(into->seq_pool, B_SEQPOOL, (size_t)ctx->seq_bytes));
     CK(cudaStreamSynchronize(s));
+    return PP_OK;
+}
+
+// =====================================================================================================================
+// `polypolish filter` on SAM text in HBM: both files are streamed in, parsed (Alignment::new_quick,
+// alignment.rs:102-128), their QNAMEs and RNAMEs interned in one device hash table (the reference's
+// HashMap<String, Vec<Alignment>> keys, filter.rs:110-145), the filter proper runs on the arrays where they are
+// (filter_kernels.cu), and the output SAM text (filter_sam, filter.rs:296-349: every line verbatim, "\tZP:Z:fail" appended to
+// failing aligned records, '\n' line ends) is assembled on the device and streamed back into the output files.
+// Anything unusual (a line the quick parse rejects, a file without alignments, a 64-bit hash collision between different
+// strings, a size limit) answers PP_TOK_HOST and filter_pack.cpp does the job on the host, with the reference's messages.
+// =====================================================================================================================
+#include "filter_dev.h"
+
+namespace {
+
+struct FileDev {                       // one SAM file on the device
+    const uint8_t* text;
+    uint64_t n, n_lines;
+    int unterminated;
+    const unsigned long long* line_start;   // [n_lines + 1]
+    tok::FLineRec* recs;                    // [n_lines]
+    unsigned long long* s_al;               // [n_lines + 1] exclusive scan of "aligned"
+    uint32_t *name_slot, *ref_slot;         // [n_lines] interned ids (aligned lines)
+};
+
+struct InternTable {
+    unsigned long long* key;           // [cap] 0 = empty
+    unsigned long long* rep;           // [cap] smallest (kind << 62 | file << 40 | line) that claimed the slot
+    uint32_t mask;
+};
+
+struct FStatus {
+    unsigned long long first_bad[2];   // per file: smallest line index the quick parse leaves to the host
+    unsigned int collision;            // different strings with one 64-bit key, or a full table
+    unsigned int pad;
+};
+
+__device__ __forceinline__ void fline_span(const FileDev& f, tok::Txt& x, uint64_t i, uint64_t& s, uint64_t& e) {
+    s = f.line_start[i];
+    if (i + 1 == f.n_lines && f.unterminated) { e = f.n; return; }
+    e = f.line_start[i + 1] - 1;
+    if (e > s && x.at(e - 1) == '\r') e--;
+}
+
+__global__ void __launch_bounds__(TK_LINE_THREADS) k_ftok_parse(FileDev f, int which, FStatus* st) {
+    const uint64_t i = (uint64_t)blockIdx.x * TK_LINE_THREADS + threadIdx.x;
+    if (i > f.n_lines) return;
+    if (i == f.n_lines) { f.s_al[i] = 0; return; }
+    tok::Txt x(f.text);
+    uint64_t s, e;
+    fline_span(f, x, i, s, e);
+    tok::FLineRec r;
+    const uint8_t kind = tok::parse_line_quick(x, s, e, r);
+    r.kind = kind;
+    f.recs[i] = r;
+    f.s_al[i] = kind == tok::FK_ALIGNED ? 1 : 0;
+    if (kind == tok::FK_HOST) atomicMin(&st->first_bad[which], (unsigned long long)i);
+}
+
+constexpr unsigned long long REF_DOMAIN = 0x9E3779B97F4A7C15ull;
+
+// Claims the slot of `key` (insert-only linear probing: a key sits in the first slot of its probe sequence that was empty
+// when it arrived, and slots never empty again, so every later arrival of the same key finds it).
+__device__ __forceinline__ uint32_t intern(const InternTable& t, unsigned long long key, unsigned long long who, FStatus* st) {
+    if (key == 0) key = 1;
+    uint32_t sl = (uint32_t)(key ^ (key >> 32)) & t.mask;
+    for (uint32_t probes = 0; probes <= t.mask; ++probes, sl = (sl + 1) & t.mask) {
+        unsigned long long cur = t.key[sl];
+        if (cur == 0) cur = atomicCAS(&t.key[sl], 0ull, key);
+        if (cur == 0 || cur == key) {
+            if (t.rep[sl] > who) atomicMin(&t.rep[sl], who);
+            return sl;
+        }
+    }
+    st->collision = 1;                 // table full
+    return 0;
+}
+
+__global__ void __launch_bounds__(TK_LINE_THREADS) k_ftok_intern(FileDev f, int which, InternTable t, FStatus* st) {
+    const uint64_t i = (uint64_t)blockIdx.x * TK_LINE_THREADS + threadIdx.x;
+    if (i >= f.n_lines) return;
+    const tok::FLineRec r = f.recs[i];
+    if (r.kind != tok::FK_ALIGNED) return;
+    const unsigned long long who = ((unsigned long long)which << 40) | i;
+    f.name_slot[i] = intern(t, r.name_hash, who, st);
+    f.ref_slot[i] = intern(t, r.ref_hash ^ REF_DOMAIN, (1ull << 62) | who, st);
+}
+
+// Every record confirms, byte by byte, that the string that owns its slot is its own string.
+__global__ void __launch_bounds__(TK_LINE_THREADS) k_ftok_verify(FileDev f0, FileDev f1, int which, InternTable t, FStatus* st) {
+    const FileDev& f = which ? f1 : f0;
+    const uint64_t i = (uint64_t)blockIdx.x * TK_LINE_THREADS + threadIdx.x;
+    if (i >= f.n_lines) return;
+    const tok::FLineRec r = f.recs[i];
+    if (r.kind != tok::FK_ALIGNED) return;
+    const uint64_t s = f.line_start[i];
+    tok::Txt x(f.text);
+    for (int kind = 0; kind < 2; ++kind) {
+        const unsigned long long rep = t.rep[kind ? f.ref_slot[i] : f.name_slot[i]];
+        const int rk = (int)(rep >> 62), rf = (int)((rep >> 40) & 1);
+        const uint64_t rl = rep & ((1ull << 40) - 1);
+        bool same = rk == kind;
+        if (same) {
+            const FileDev& g = rf ? f1 : f0;
+            const tok::FLineRec q = g.recs[rl];
+            const uint64_t qs = g.line_start[rl];
+            tok::Txt y(g.text);
+            if (kind == 0) same = q.name_len == r.name_len && tok::same_bytes(x, s, y, qs, r.name_len);
+            else same = q.ref_len == r.ref_len && tok::same_bytes(x, s + r.ref_rel, y, qs + q.ref_rel, r.ref_len);
+        }
+        if (!same) st->collision = 1;
+    }
+}
+
+struct MateOut { uint32_t *name_id, *contig, *ref_start, *ref_end; uint8_t* flags; };
+
+__global__ void __launch_bounds__(TK_LINE_THREADS) k_ftok_emit(FileDev f, MateOut m) {
+    const uint64_t i = (uint64_t)blockIdx.x * TK_LINE_THREADS + threadIdx.x;
+    if (i >= f.n_lines) return;
+    const tok::FLineRec r = f.recs[i];
+    if (r.kind != tok::FK_ALIGNED) return;
+    const uint64_t a = f.s_al[i];
+    m.name_id[a] = f.name_slot[i];
+    m.contig[a] = f.ref_slot[i];
+    m.ref_start[a] = r.ref_start;
+    m.ref_end[a] = r.ref_end;
+    m.flags[a] = r.rev;
+}
+
+// filter_sam (filter.rs:296-349): bytes of every output line.
+__global__ void __launch_bounds__(TK_LINE_THREADS) k_ftok_outlen(FileDev f, const uint8_t* __restrict__ pass, unsigned long long* __restrict__ out_off) {
+    const uint64_t i = (uint64_t)blockIdx.x * TK_LINE_THREADS + threadIdx.x;
+    if (i > f.n_lines) return;
+    if (i == f.n_lines) { out_off[i] = 0; return; }
+    tok::Txt x(f.text);
+    uint64_t s, e;
+    fline_span(f, x, i, s, e);
+    const bool fail = f.recs[i].kind == tok::FK_ALIGNED && !pass[f.s_al[i]];
+    out_off[i] = (e - s) + 1 + (fail ? 10 : 0);
+}
+
+// One warp per line: the line's bytes, the tag for failing records, '\n'.
+__global__ void __launch_bounds__(256) k_ftok_copy(FileDev f, const uint8_t* __restrict__ pass, const unsigned long long* __restrict__ out_off,
+                                                   uint8_t* __restrict__ out) {
+    const uint64_t i = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (i >= f.n_lines) return;
+    uint64_t s = f.line_start[i], e;
+    if (i + 1 == f.n_lines && f.unterminated) e = f.n;
+    else { e = f.line_start[i + 1] - 1; if (e > s && f.text[e - 1] == '\r') e--; }
+    const bool fail = f.recs[i].kind == tok::FK_ALIGNED && !pass[f.s_al[i]];
+    uint8_t* d = out + out_off[i];
+    const uint64_t len = e - s;
+    for (uint64_t k = lane; k < len; k += 32) d[k] = f.text[s + k];
+    if (fail) { if (lane < 10) d[len + lane] = (uint8_t)"\tZP:Z:fail"[lane]; }
+    if (lane == 0) d[len + (fail ? 10 : 0)] = '\n';
+}
+
+}  // namespace
+
+// Streams n device bytes into fd (the mirror image of upload_file): each thread copies its slices into its pinned slots
+// and pwrite()s them.  PP_OK / PP_ERR_IO / PP_ERR_CUDA.
+static int download_file(int device, TokState* T, const uint8_t* src, int fd, uint64_t n, int* cuda_err) {
+    const int R = T->readers;
+    const uint64_t n_slices = (n + TK_SLOT - 1) / TK_SLOT;
+    std::atomic<int> err{0}, cerr{0};
+    auto work = [&](int r) {
+        if (cudaSetDevice(device) != cudaSuccess) { err = 2; return; }
+        uint64_t k = 0, prev_o = 0, prev_len = 0;
+        bool have_prev = false;
+        auto flush_prev = [&](int slot) -> bool {
+            cudaError_t e = cudaEventSynchronize(T->rev[r][slot]);
+            if (e != cudaSuccess) { cerr = (int)e; err = 2; return false; }
+            uint64_t put = 0;
+            while (put < prev_len) {
+                const ssize_t g = pwrite(fd, T->pin[r][slot] + put, (size_t)(prev_len - put), (off_t)(prev_o + put));
+                if (g <= 0) { err = 1; return false; }
+                put += (uint64_t)g;
+            }
+            return true;
+        };
+        for (uint64_t sl = (uint64_t)r; sl < n_slices && !err; sl += (uint64_t)R, ++k) {
+            const int slot = (int)(k & 1);
+            const uint64_t o = sl * TK_SLOT, len = std::min<uint64_t>(TK_SLOT, n - o);
+            cudaError_t e = cudaMemcpyAsync(T->pin[r][slot], src + o, (size_t)len, cudaMemcpyDeviceToHost, T->rstream[r]);
+            if (e == cudaSuccess) e = cudaEventRecord(T->rev[r][slot], T->rstream[r]);
+            if (e != cudaSuccess) { cerr = (int)e; err = 2; return; }
+            if (have_prev && !flush_prev(slot ^ 1)) return;
+            prev_o = o; prev_len = len; have_prev = true;
+        }
+        if (have_prev && !err) flush_prev((int)((k - 1) & 1));
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < R; ++r) th.emplace_back(work, r);
+    work(0);
+    for (auto& t : th) t.join();
+    *cuda_err = cerr.load();
+    return err == 1 ? PP_ERR_IO : err == 2 ? PP_ERR_CUDA : PP_OK;
+}
+
+// Line index + quick parse of one file whose text is on the device.  Fills fd; PP_OK / PP_TOK_HOST / error.
+static int ftok_lines(pp_ctx* ctx, TokState* T, int which, const uint8_t* text, uint64_t n, bool unterminated, DevBuf& lines, DevBuf& tmp, FStatus* d_st,
+                      FileDev* fd, uint32_t* launches) {
+    cudaStream_t s = ctx->stream;
+    const uint64_t n16 = (n + 15) & ~15ull;
+    const uint64_t n_tiles = (n16 + TK_TILE - 1) / TK_TILE;
+    if (n_tiles == 0 || n_tiles >= 0x7FFFFFFFull) return PP_TOK_HOST;
+    size_t cub_bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int64_t)(n_tiles + 1)));
+    CK(T->cub.ensure(cub_bytes + 256));
+    CK(ctx->b[B_TOKLINE].ensure((n_tiles + 2) * 8));
+    unsigned long long* tile_cnt = ctx->b[B_TOKLINE].as<unsigned long long>();
+    CK(cudaMemsetAsync(tile_cnt + n_tiles, 0, 8, s));
+    k_tok_count<<<(unsigned)n_tiles, TK_THREADS, 0, s>>>(text, n16, tile_cnt);
+    {
+        size_t tb = T->cub.cap;
+        CK(cub::DeviceScan::ExclusiveSum(T->cub.p, tb, tile_cnt, tile_cnt, (int64_t)(n_tiles + 1), s));
+    }
+    CK(cudaMemcpyAsync(T->h_tot, tile_cnt + n_tiles, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t n_lines = T->h_tot[0] + (unterminated ? 1 : 0);
+    if (n_lines == 0 || n_lines >= 0xFFFFFFF0ull) return PP_TOK_HOST;
+    CK(lines.ensure((n_lines + 2) * 8));
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_rec = carve(n_lines * sizeof(tok::FLineRec)), o_al = carve((n_lines + 1) * 8), o_ns = carve(n_lines * 4), o_rs = carve(n_lines * 4);
+    CK(tmp.ensure(off));
+    uint8_t* b = tmp.as<uint8_t>();
+    fd->text = text; fd->n = n; fd->n_lines = n_lines; fd->unterminated = unterminated ? 1 : 0;
+    fd->line_start = lines.as<unsigned long long>();
+    fd->recs = (tok::FLineRec*)(b + o_rec); fd->s_al = (unsigned long long*)(b + o_al);
+    fd->name_slot = (uint32_t*)(b + o_ns); fd->ref_slot = (uint32_t*)(b + o_rs);
+    k_tok_index<<<(unsigned)n_tiles, TK_THREADS, 0, s>>>(text, n16, tile_cnt, lines.as<unsigned long long>());
+    k_ftok_parse<<<(unsigned)((n_lines + 1 + TK_LINE_THREADS - 1) / TK_LINE_THREADS), TK_LINE_THREADS, 0, s>>>(*fd, which, d_st);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, fd->s_al, fd->s_al, (int64_t)(n_lines + 1)));
+    CK(T->cub.ensure(cub_bytes + 256));
+    {
+        size_t tb = T->cub.cap;
+        CK(cub::DeviceScan::ExclusiveSum(T->cub.p, tb, fd->s_al, fd->s_al, (int64_t)(n_lines + 1), s));
+    }
+    *launches += 7;
+    return PP_OK;
+}
+
+struct TokFilterBufs {                 // device buffers of the filter text path, kept in the tokeniser state
+    DevBuf lines[2], tmp[2], mate[2], table, out, status;
+};
+
+static void free_filter_bufs(TokFilterBufs* b) {
+    for (int k = 0; k < 2; ++k) { b->lines[k].release(); b->tmp[k].release(); b->mate[k].release(); }
+    b->table.release(); b->out.release(); b->status.release();
+    delete b;
+}
+
+// `polypolish filter` with the SAM text handled on the device.  PP_OK, PP_TOK_HOST (the host path must do it) or an error
+// (the filter's own: no usable pairs, ambiguous orientation; I/O; CUDA).
+int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2, const pp_filter_params* prm_in,
+                           pp_filter_result* res, pp_filter_file_stats* fs) {
+    CK(cudaSetDevice(ctx->device));
+    TokState* T = nullptr;
+    int rc = tok_state(ctx, &T);
+    if (rc) return rc;
+    if (!T->fbufs) T->fbufs = new TokFilterBufs();
+    TokFilterBufs& B = *T->fbufs;
+    cudaStream_t s = ctx->stream;
+    const char* ins[2] = {in1, in2};
+    const char* outs[2] = {out1, out2};
+    memset(fs, 0, sizeof *fs);
+    const auto t_begin = std::chrono::steady_clock::now();
+
+    CK(B.status.ensure(sizeof(FStatus)));
+    FStatus* d_st = B.status.as<FStatus>();
+    FStatus h_st;
+    h_st.first_bad[0] = h_st.first_bad[1] = ~0ull; h_st.collision = 0; h_st.pad = 0;
+    CK(cudaMemcpyAsync(d_st, &h_st, sizeof h_st, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+
+    // ---- both texts into HBM; the second streams in while the first is indexed and parsed
+    FileDev fd[2];
+    uint32_t launches = 0;
+    float h2d_ms = 0;
+    if (T->pf.active && T->pf.path != in1) { if (T->pf.th.joinable()) T->pf.th.join(); T->pf.active = false; }
+    for (int k = 0; k < 2; ++k) {
+        rc = prefetch_wait(ctx, T, ins[k]);
+        if (rc != PP_OK) return rc;
+        const int buf = T->pf.buf;
+        const uint64_t n = T->pf.n;
+        const bool unterminated = n > 0 && T->pf.last != '\n';
+        h2d_ms += T->pf.ms;
+        fs->text_bytes[k] = n;
+        if (k == 0) {
+            rc = prefetch_start(ctx, T, ins[1]);
+            if (rc != PP_OK) return rc;
+        }
+        rc = ftok_lines(ctx, T, k, T->text[buf].as<uint8_t>(), n, unterminated, B.lines[k], B.tmp[k], d_st, &fd[k], &launches);
+        if (rc != PP_OK) {
+            if (T->pf.active) { if (T->pf.th.joinable()) T->pf.th.join(); T->pf.active = false; }
+            return rc;
+        }
+    }
+    CK(cudaMemcpyAsync(T->h_tot + 0, fd[0].s_al + fd[0].n_lines, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(T->h_tot + 1, fd[1].s_al + fd[1].n_lines, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&h_st, d_st, sizeof h_st, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    const uint64_t n_al[2] = {T->h_tot[0], T->h_tot[1]};
+    fs->alignments[0] = n_al[0]; fs->alignments[1] = n_al[1];
+    if (h_st.first_bad[0] != ~0ull || h_st.first_bad[1] != ~0ull) return PP_TOK_HOST;
+    if (n_al[0] == 0 || n_al[1] == 0) return PP_TOK_HOST;               // "no alignments found in ..." is worded by the host path
+    if (n_al[0] >= 0x7FFFFFFFull || n_al[1] >= 0x7FFFFFFFull) return PP_TOK_HOST;
+
+    // ---- intern QNAMEs and RNAMEs
+    uint64_t cap = 1024;
+    while (cap < 3 * (n_al[0] + n_al[1]) + 1024) cap <<= 1;
+    if (cap > (1ull << 31)) return PP_TOK_HOST;
+    CK(B.table.ensure(cap * 16));
+    InternTable tb;
+    tb.key = B.table.as<unsigned long long>(); tb.rep = tb.key + cap; tb.mask = (uint32_t)(cap - 1);
+    CK(cudaMemsetAsync(tb.key, 0, cap * 8, s));
+    CK(cudaMemsetAsync(tb.rep, 0xFF, cap * 8, s));
+    for (int k = 0; k < 2; ++k)
+        k_ftok_intern<<<(unsigned)((fd[k].n_lines + TK_LINE_THREADS - 1) / TK_LINE_THREADS), TK_LINE_THREADS, 0, s>>>(fd[k], k, tb, d_st);
+    Mate mates[2];
+    for (int k = 0; k < 2; ++k) {
+        k_ftok_verify<<<(unsigned)((fd[k].n_lines + TK_LINE_THREADS - 1) / TK_LINE_THREADS), TK_LINE_THREADS, 0, s>>>(fd[0], fd[1], k, tb, d_st);
+        const size_t na = (size_t)n_al[k];
+        CK(B.mate[k].ensure(na * 17 + 5 * 256));
+        uint8_t* mb = B.mate[k].as<uint8_t>();
+        auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+        MateOut mo;
+        mo.name_id = (uint32_t*)mb; mo.contig = (uint32_t*)(mb + up(na * 4)); mo.ref_start = (uint32_t*)(mb + 2 * up(na * 4));
+        mo.ref_end = (uint32_t*)(mb + 3 * up(na * 4)); mo.flags = mb + 4 * up(na * 4);
+        k_ftok_emit<<<(unsigned)((fd[k].n_lines + TK_LINE_THREADS - 1) / TK_LINE_THREADS), TK_LINE_THREADS, 0, s>>>(fd[k], mo);
+        mates[k].name_id = mo.name_id; mates[k].contig = mo.contig; mates[k].ref_start = mo.ref_start; mates[k].ref_end = mo.ref_end;
+        mates[k].flags = mo.flags; mates[k].cnt = nullptr; mates[k].head = nullptr; mates[k].next = nullptr; mates[k].pass = nullptr;
+        mates[k].n = (uint32_t)na;
+    }
+    launches += 6;
+    CK(cudaMemcpyAsync(&h_st, d_st, sizeof h_st, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (h_st.collision) return PP_TOK_HOST;
+
+    // ---- the filter proper (filter_kernels.cu), flags stay on the device
+    pp_filter_params prm = *prm_in;
+    prm.n_names = cap;
+    res->pass1 = nullptr; res->pass2 = nullptr;
+    const uint8_t* d_pass[2] = {nullptr, nullptr};
+    uint64_t np[2] = {0, 0};
+    CK(cudaEventRecord(ctx->ev[0], s));
+    rc = pp_filter_core(ctx, mates, &prm, res, d_pass, np);
+    if (rc != PP_OK) return rc;
+    launches += res->timing.launches;
+
+    // ---- output text, file by file: lengths -> offsets -> bytes -> the output file
+    float d2h_ms = 0;
+    for (int k = 0; k < 2; ++k) {
+        const uint64_t nl = fd[k].n_lines;
+        DevBuf& offs = B.table;                                                 // the intern table is done with: reuse it
+        CK(offs.ensure((nl + 2) * 8));
+        unsigned long long* out_off = offs.as<unsigned long long>();
+        k_ftok_outlen<<<(unsigned)((nl + 1 + TK_LINE_THREADS - 1) / TK_LINE_THREADS), TK_LINE_THREADS, 0, s>>>(fd[k], d_pass[k], out_off);
+        size_t cub_bytes = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, out_off, out_off, (int64_t)(nl + 1)));
+        CK(T->cub.ensure(cub_bytes + 256));
+        {
+            size_t tbb = T->cub.cap;
+            CK(cub::DeviceScan::ExclusiveSum(T->cub.p, tbb, out_off, out_off, (int64_t)(nl + 1), s));
+        }
+        CK(cudaMemcpyAsync(T->h_tot, out_off + nl, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const uint64_t out_n = T->h_tot[0];
+        CK(B.out.ensure(out_n + 64));
+        k_ftok_copy<<<(unsigned)((nl * 32 + 255) / 256), 256, 0, s>>>(fd[k], d_pass[k], out_off, B.out.as<uint8_t>());
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        launches += 4;
+        const int ofd = open(outs[k], O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (ofd < 0) return ctx->fail(PP_ERR_IO, std::string("unable to write alignments to \"") + outs[k] + "\"");
+        const auto t0 = std::chrono::steady_clock::now();
+        int cuda_err = 0;
+        int wrc = PP_OK;
+        if (out_n) {
+            if (ftruncate(ofd, (off_t)out_n) != 0) wrc = PP_ERR_IO;
+            if (wrc == PP_OK) wrc = download_file(ctx->device, T, B.out.as<uint8_t>(), ofd, out_n, &cuda_err);
+        }
+        if (close(ofd) != 0 && wrc == PP_OK) wrc = PP_ERR_IO;
+        d2h_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (wrc == PP_ERR_IO) return ctx->fail(PP_ERR_IO, std::string("unable to write alignments to \"") + outs[k] + "\"");
+        if (wrc == PP_ERR_CUDA) return ctx->fail_cuda((cudaError_t)cuda_err, "filtered SAM download", __FILE__, __LINE__);
+        fs->pass[k] = np[k];
+        fs->fail[k] = n_al[k] - np[k];
+        fs->out_bytes[k] = out_n;
+    }
+    fs->h2d_ms = h2d_ms;
+    fs->d2h_ms = d2h_ms;
+    fs->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    fs->launches = launches;
     return PP_OK;
 }

@@ -324,4 +324,118 @@ TK_HD bool close_group(uint64_t a, uint64_t file_end, const uint32_t* head, bool
     return true;
 }
 
+
+// ---- `polypolish filter`: the quick parse (Alignment::new_quick alignment.rs:102-128 as used by filter.rs:110-145) ----------
+enum : uint8_t { FK_VERBATIM = 0, FK_ALIGNED = 1, FK_HOST = 2 };   // header / unaligned line; keyed record; host decides
+
+struct alignas(8) FLineRec {   // 40 bytes
+    uint64_t name_hash, ref_hash;          // FNV-1a of QNAME / RNAME (interned on the device, confirmed byte by byte)
+    uint32_t name_len, ref_rel, ref_len;   // QNAME starts the line; RNAME at ref_rel
+    uint32_t ref_start, ref_end;           // 0-based start; get_ref_end (alignment.rs:138-149)
+    uint8_t rev, kind, pad[2];
+};
+
+TK_HD bool is_ref_op(uint8_t c) { return c == 'M' || c == 'D' || c == 'N' || c == '=' || c == 'X'; }
+
+// Alignment::get_ref_end: tolerant scan of \d+[MIDNSHP=X] tokens in [p, fe); false when a token's length overflows u64.
+TK_HD bool cigar_ref_end(Txt& x, uint64_t p, uint64_t fe, uint64_t start, uint64_t& end) {
+    uint64_t ref_end = start, i = p;
+    while (i < fe) {
+        uint8_t c = x.at(i);
+        if ((unsigned)c - '0' <= 9u) {
+            uint64_t j = i, v = 0;
+            bool ovf = false;
+            while (j < fe && (unsigned)(c = x.at(j)) - '0' <= 9u) {
+                const uint64_t d = c - '0';
+                if (v > 1844674407370955160ull && v > (~0ull - d) / 10) ovf = true;
+                v = v * 10 + d;
+                j++;
+            }
+            if (j < fe && op_code(x.at(j)) >= 0) {
+                if (ovf) return false;
+                if (is_ref_op(x.at(j))) ref_end += v;
+                i = j + 1;
+            } else {
+                i = j;
+            }
+        } else {
+            i++;
+        }
+    }
+    end = ref_end;
+    return true;
+}
+
+// One text line [s, e) of a SAM file given to `polypolish filter` (filter.rs:122-137): '@' lines are headers; every other
+// line needs 11 columns, a FLAG and a POS; unaligned records are passed through; aligned ones are keyed by QNAME.
+TK_HD uint8_t parse_line_quick(Txt& x, uint64_t s, uint64_t e, FLineRec& r) {
+    r.name_hash = 0; r.ref_hash = 0; r.name_len = 0; r.ref_rel = 0; r.ref_len = 0; r.ref_start = 0; r.ref_end = 0;
+    r.rev = 0; r.kind = FK_VERBATIM; r.pad[0] = r.pad[1] = 0;
+    if (e > s && x.at(s) == '@') return FK_VERBATIM;
+    if (e - s >= 0x7FFFFFFFull) return FK_HOST;
+    uint64_t p = s, fe, v;
+    // 0 QNAME
+    uint64_t h = FNV_BASIS;
+    for (fe = p; fe < e; ++fe) {
+        const uint8_t c = x.at(fe);
+        if (c == '\t') break;
+        h = (h ^ c) * FNV_PRIME;
+    }
+    if (fe == e) return FK_HOST;                                        // too few columns (an empty line too)
+    r.name_hash = h;
+    r.name_len = (uint32_t)(fe - p);
+    p = fe + 1;
+    // 1 FLAG
+    if (!field_uint(x, p, e, 0xFFFFFFFFull, v, fe) || fe == e) return FK_HOST;
+    const uint32_t sam_flags = (uint32_t)v;
+    p = fe + 1;
+    // 2 RNAME
+    r.ref_rel = (uint32_t)(p - s);
+    h = FNV_BASIS;
+    for (fe = p; fe < e; ++fe) {
+        const uint8_t c = x.at(fe);
+        if (c == '\t') break;
+        h = (h ^ c) * FNV_PRIME;
+    }
+    if (fe == e) return FK_HOST;
+    r.ref_hash = h;
+    r.ref_len = (uint32_t)(fe - p);
+    p = fe + 1;
+    // 3 POS
+    if (!field_uint(x, p, e, ~0ull, v, fe) || fe == e) return FK_HOST;
+    const uint64_t start = v > 0 ? v - 1 : 0;
+    p = fe + 1;
+    // 4 MAPQ
+    fe = field_end(x, p, e);
+    if (fe == e) return FK_HOST;
+    p = fe + 1;
+    // 5 CIGAR
+    const uint64_t cg = p;
+    fe = field_end(x, p, e);
+    if (fe == e) return FK_HOST;
+    const uint64_t cg_end = fe;
+    p = fe + 1;
+    // 6..9 must exist (column 10 may be the last)
+    for (int k = 0; k < 4; ++k) {
+        fe = field_end(x, p, e);
+        if (fe == e) return FK_HOST;
+        p = fe + 1;
+    }
+    if (sam_flags & 4) return FK_VERBATIM;                              // filter.rs:132
+    uint64_t end;
+    if (!cigar_ref_end(x, cg, cg_end, start, end) || end > 0xFFFFFFFEull) return FK_HOST;
+    r.ref_start = (uint32_t)start;
+    r.ref_end = (uint32_t)end;
+    r.rev = (sam_flags & 16) ? 1 : 0;
+    r.kind = FK_ALIGNED;
+    return FK_ALIGNED;
+}
+
+// Do two byte ranges of the text(s) hold the same string?
+TK_HD bool same_bytes(Txt& a, uint64_t pa, Txt& b, uint64_t pb, uint32_t len) {
+    for (uint32_t k = 0; k < len; ++k)
+        if (a.at(pa + k) != b.at(pb + k)) return false;
+    return true;
+}
+
 }  // namespace tok

@@ -153,3 +153,48 @@ def test_synth_filter_then_polish(ctx, oracle, tmp_path, seed):
     assert b"ZP:Z:fail" in open(f1, "rb").read()
     got = ctx.polish_files(fa, [f1, f2])
     assert got == oracle.polish(fa, [f1, f2])["fasta"]
+
+
+# ---- the device text path of `filter` (tok_kernels.cu) against the host text path -------------------------------------
+@pytest.mark.parametrize("seed", [31, 32, 33, 34])
+def test_device_and_host_text_paths_agree(ctx, oracle, tmp_path, seed):
+    """Same bytes from both text paths (pp_set_parser 0 / 1), and from the oracle: CRLF, shuffled groups, last line unterminated."""
+    t1, t2 = random_pairs(seed, n_pairs=500, eol="\r\n" if seed == 32 else "\n", shuffle_groups=(seed == 33))
+    if seed == 34:
+        t1, t2 = t1[:-1], t2[:-1]
+    i1, i2 = tmp_path / "i1.sam", tmp_path / "i2.sam"
+    i1.write_bytes(t1.encode()); i2.write_bytes(t2.encode())
+    exp = oracle.filter(i1, i2)
+    for mode in (0, 1):
+        o1, o2 = tmp_path / f"o1_{mode}.sam", tmp_path / f"o2_{mode}.sam"
+        ctx.set_parser(mode)
+        try:
+            ctx.filter_files(i1, i2, o1, o2)
+        finally:
+            ctx.set_parser(0)
+        assert open(o1, "rb").read() == exp["out1"] and open(o2, "rb").read() == exp["out2"]
+
+
+def test_device_text_path_large_files(ctx, oracle, tmp_path):
+    """~100 MB per mate: every pinned slot is reused in both directions, 0.6 M names are interned, the second file is parsed
+    while ... the first is already resident; the result is the oracle's, byte for byte."""
+    syn = api.Synth(seed=21, n_contigs=2, contig_len=400_000, depth=100.0)
+    fa, sams = syn.write(tmp_path)
+    o1, o2 = tmp_path / "o1.sam", tmp_path / "o2.sam"
+    ctx.filter_files(sams[0], sams[1], o1, o2)
+    exp = oracle.filter(sams[0], sams[1])
+    assert open(o1, "rb").read() == exp["out1"]
+    assert open(o2, "rb").read() == exp["out2"]
+    assert exp["out1"].count(b"\tZP:Z:fail") > 100
+
+
+def test_device_text_path_same_name_in_both_columns(ctx, oracle, tmp_path):
+    """A QNAME that is also an RNAME, an empty RNAME, names that differ only in the last byte: the interning keeps them apart."""
+    rows1 = ["ctgA\t0\tctgA\t100\t60\t50M\t*\t0\t0\tAC\tII", "ctgB\t0\tctgA\t500\t60\t50M\t*\t0\t0\tAC\tII", "x1\t0\t\t100\t60\t50M\t*\t0\t0\tAC\tII",
+             "x2\t0\tctgB\t100\t60\t50M\t*\t0\t0\tAC\tII", "x2\t256\tctgA\t9000\t60\t50M\t*\t0\t0\tAC\tII"]
+    rows2 = ["ctgA\t16\tctgA\t350\t60\t50M\t*\t0\t0\tAC\tII", "ctgB\t16\tctgA\t760\t60\t50M\t*\t0\t0\tAC\tII", "x1\t16\t\t340\t60\t50M\t*\t0\t0\tAC\tII",
+             "x2\t16\tctgB\t330\t60\t50M\t*\t0\t0\tAC\tII", "x2\t272\tctgA\t9300\t60\t50M\t*\t0\t0\tAC\tII", "x2\t272\tctgB\t50000\t60\t50M\t*\t0\t0\tAC\tII"]
+    more1, more2 = random_pairs(41, n_pairs=200)
+    i1, i2 = tmp_path / "i1.sam", tmp_path / "i2.sam"
+    i1.write_text(more1 + "\n".join(rows1) + "\n"); i2.write_text(more2 + "\n".join(rows2) + "\n")
+    run_both(ctx, oracle, i1, i2, tmp_path)

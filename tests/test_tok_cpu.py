@@ -241,3 +241,105 @@ def test_tok_logic_random_bytes_never_disagree(H, tmp_path):
         else:
             raise AssertionError(f"harness refused a text the host packer accepts: {t!r}")
     assert n_ok > 50 and n_host > 50
+
+
+# ---- `polypolish filter`: the quick parse (parse_line_quick) against a Python model of load_alignments_one_file ---------
+import re  # noqa: E402
+
+CIGAR_TOKEN = re.compile(rb"\d+[MIDNSHP=X]")
+
+
+def rust_parse_uint(b, maxv):
+    if b.startswith(b"+"):
+        b = b[1:]
+    if not b or not b.isdigit() or not all(48 <= c <= 57 for c in b):
+        return None
+    v = int(b)
+    return v if v <= maxv else None
+
+
+def model_quick(line):
+    """(kind, start, end, rev) for one line (bytes, no newline): filter.rs:122-137 + alignment.rs:102-149."""
+    if line.startswith(b"@"):
+        return (0, 0, 0, 0)
+    f = line.split(b"\t")
+    if len(f) < 11:
+        return (2, 0, 0, 0)
+    flag = rust_parse_uint(f[1], 0xFFFFFFFF)
+    pos = rust_parse_uint(f[3], (1 << 64) - 1)
+    if flag is None or pos is None:
+        return (2, 0, 0, 0)
+    if flag & 4:
+        return (0, 0, 0, 0)
+    start = pos - 1 if pos > 0 else 0
+    end = start
+    for m in CIGAR_TOKEN.finditer(f[5]):
+        t = m.group()
+        v = int(t[:-1])
+        if v >= 1 << 64:
+            return (2, 0, 0, 0)
+        if t[-1:] in b"MDN=X":
+            end = (end + v) & ((1 << 64) - 1)
+    if end > 0xFFFFFFFE:
+        return (2, 0, 0, 0)
+    return (1, start & 0xFFFFFFFF, end, 1 if flag & 16 else 0)
+
+
+def ftok_cpu(H, text):
+    nl = text.count(b"\n") + 2
+    kind = np.zeros(nl, np.uint8); rs = np.zeros(nl, np.uint32); re_ = np.zeros(nl, np.uint32); rev = np.zeros(nl, np.uint8)
+    nlen = np.zeros(nl, np.uint32); rrel = np.zeros(nl, np.uint32); rlen = np.zeros(nl, np.uint32); nh = np.zeros(nl, np.uint64)
+    n_out = C.c_uint64()
+    H.ftok_cpu.restype = C.c_int
+    rc = H.ftok_cpu(C.c_char_p(text), C.c_uint64(len(text)), C.c_uint64(nl), *[a.ctypes.data_as(C.c_void_p) for a in (kind, rs, re_, rev, nlen, rrel, rlen, nh)],
+                    C.byref(n_out))
+    assert rc == 0
+    n = n_out.value
+    return kind[:n], rs[:n], re_[:n], rev[:n], nlen[:n], rrel[:n], rlen[:n], nh[:n]
+
+
+def split_lines(text):
+    """str::lines(): split on \\n, strip one \\r before it, a final unterminated line is a line (and keeps its \\r)."""
+    out = []
+    parts = text.split(b"\n")
+    for i, p in enumerate(parts):
+        last = i == len(parts) - 1
+        if last:
+            if p:
+                out.append(p)
+        else:
+            out.append(p[:-1] if p.endswith(b"\r") else p)
+    return out
+
+
+def test_ftok_quick_parse_matches_model(H):
+    rng = random.Random(9)
+    cigars = ["4M", "2M1I1M", "10M2D5M", "3S7M", "5=1X4=", "*", "", "12", "M", "4M5", "9999999999M", "4294967295M", "18446744073709551616M", "1M1N1H1P",
+              "3Mjunk4D", "0M", "+4M", "4m"]
+    flags = ["0", "16", "4", "20", "256", "272", "+16", "x", "", "4294967295", "4294967296", "-1"]
+    poss = ["0", "1", "100", "+7", "4294967295", "4294967296", "18446744073709551615", "18446744073709551616", "a", ""]
+    lines = ["@HD\tVN:1.6", "", "@", "\t", "a\tb"]
+    for _ in range(600):
+        n_extra = rng.choice([0, 0, 0, 1, 3])
+        cols = [f"r{rng.randint(0, 50)}", rng.choice(flags), rng.choice(["c1", "c2", "", "*"]), rng.choice(poss), "60", rng.choice(cigars), "*", "0", "0",
+                "ACGT", "IIII"] + ["NM:i:0"] * n_extra
+        if rng.random() < 0.1:
+            cols = cols[:rng.randint(1, 10)]
+        lines.append("\t".join(cols))
+    for ending in (b"\n", b"\r\n"):
+        for final_newline in (True, False):
+            text = ending.join(x.encode() for x in lines) + (ending if final_newline else b"")
+            kind, rs, re_, rev, nlen, rrel, rlen, nh = ftok_cpu(H, text)
+            want = split_lines(text)
+            assert len(want) == len(kind)
+            for i, ln in enumerate(want):
+                k, s, e, r = model_quick(ln)
+                assert kind[i] == k, (i, ln)
+                if k == 1:
+                    assert (rs[i], re_[i], rev[i]) == (s, e, r), (i, ln)
+                    f = ln.split(b"\t")
+                    assert nlen[i] == len(f[0]) and rlen[i] == len(f[2]) and ln[rrel[i]:rrel[i] + rlen[i]] == f[2]
+    # equal names hash equal, different names (here) differ
+    text = b"".join(("\t".join([nm, "0", "c1", "1", "60", "4M", "*", "0", "0", "ACGT", "IIII"]) + "\n").encode() for nm in ["a", "b", "a", "ab", ""])
+    nh = ftok_cpu(H, text)[7]
+    assert nh[0] == nh[2] and len({int(nh[0]), int(nh[1]), int(nh[3]), int(nh[4])}) == 4

@@ -95,3 +95,28 @@ extern "C" int tok_cpu(const char* text_in, uint64_t n, const char* const* names
     counts[0] = A0 + n_al; counts[1] = O0 + n_ops; counts[2] = B0 + n_blk; counts[3] = R0 + rs[n_al - 1];
     return PP_OK;
 }
+
+// The quick parse of `polypolish filter` (tok_line.h parse_line_quick), line by line.
+extern "C" int ftok_cpu(const char* text_in, uint64_t n, uint64_t cap_lines, uint8_t* kind, uint32_t* ref_start, uint32_t* ref_end, uint8_t* rev,
+                        uint32_t* name_len, uint32_t* ref_rel, uint32_t* ref_len, uint64_t* name_hash, uint64_t* n_lines_out) {
+    std::vector<uint64_t> buf((n + 15) / 8 + 8, 0);
+    uint8_t* text = reinterpret_cast<uint8_t*>(buf.data());
+    memcpy(text, text_in, n);
+    const bool unterminated = n > 0 && text[n - 1] != '\n';
+    std::vector<uint64_t> line_start{0};
+    for (uint64_t p = 0; p < n; ++p) if (text[p] == '\n') line_start.push_back(p + 1);
+    const uint64_t n_lines = line_start.size() - 1 + (unterminated ? 1 : 0);
+    *n_lines_out = n_lines;
+    if (n_lines > cap_lines) return -1;
+    for (uint64_t i = 0; i < n_lines; ++i) {
+        uint64_t s = line_start[i], e;
+        if (i + 1 == n_lines && unterminated) e = n;
+        else { e = line_start[i + 1] - 1; if (e > s && text[e - 1] == '\r') e--; }
+        tok::Txt x(text);
+        tok::FLineRec r;
+        kind[i] = tok::parse_line_quick(x, s, e, r);
+        ref_start[i] = r.ref_start; ref_end[i] = r.ref_end; rev[i] = r.rev; name_len[i] = r.name_len; ref_rel[i] = r.ref_rel; ref_len[i] = r.ref_len;
+        name_hash[i] = r.name_hash;
+    }
+    return 0;
+}
