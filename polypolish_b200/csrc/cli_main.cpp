@@ -128,12 +128,14 @@ int main(int argc, char** argv) {
             else if (a == "--high") high = parse_f64("--high <HIGH>", need(i, "--high"));
             else if (a == "--device") device = (int)parse_u32("--device", need(i, "--device"));
             else if (a == "--quiet") quiet = true;
+            else if (a == "--host-parse") host_parse = true;
             else usage_error("unexpected argument '" + a + "' found");
         }
         if (in1.empty() || in2.empty() || out1.empty() || out2.empty())
             usage_error("the following required arguments were not provided:\n  --in1 <IN1>\n  --in2 <IN2>\n  --out1 <OUT1>\n  --out2 <OUT2>");
         pp_ctx* ctx = nullptr;
         if (pp_create(device, &ctx) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
+        if (host_parse) pp_set_parser(ctx, 1);
         if (!quiet) fprintf(stderr, "Starting Polypolish filter (B200 build %s)\n\n", pp_version());
         int rc = pp_filter_files(ctx, in1.c_str(), in2.c_str(), out1.c_str(), out2.c_str(), orientation.c_str(), low, high, quiet ? 0 : 1);
         if (rc != PP_OK) { std::string m = pp_last_error(ctx); pp_destroy(ctx); quit_with_error(m); }

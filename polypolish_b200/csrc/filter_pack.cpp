@@ -161,6 +161,8 @@ extern "C" int pp_filter_files(pp_ctx* ctx, const char* in1, const char* in2, co
                         thousands(fs.pass[0] + fs.pass[1]).c_str());
                 fprintf(stderr, "device text path: %.3f ms (SAM to HBM %.3f ms, filtered SAM to files %.3f ms), %u kernels; filter kernels %.3f ms\n", fs.total_ms,
                         fs.h2d_ms, fs.d2h_ms, fs.launches, res.timing.total_ms);
+                fprintf(stderr, "  phases (wall ms): upload+index+parse %.1f, intern+verify+emit %.1f, filter %.1f, output offsets %.1f, output bytes %.1f, download+write %.1f\n",
+                        fs.phase_ms[0], fs.phase_ms[1], fs.phase_ms[2], fs.phase_ms[3], fs.phase_ms[4], fs.phase_ms[5]);
             }
             return PP_OK;
         }

@@ -103,6 +103,7 @@ int pp_ctx_fail(pp_ctx* ctx, int code, const char* msg);
 struct pp_filter_file_stats {
     uint64_t alignments[2], pass[2], fail[2], text_bytes[2], out_bytes[2];
     float h2d_ms, d2h_ms, total_ms;
+    float phase_ms[6];     // wall: 0 upload+index+parse, 1 intern+verify+emit, 2 filter proper, 3 output lengths+scan, 4 output bytes, 5 download+write
     uint32_t launches;
 };
 int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2, const pp_filter_params* prm,
