@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""`polypolish filter` on synthetic paired SAM, timed per phase (the library's own stderr line), device text path vs host.
+"""`polypolish filter` then `polypolish polish` (the CLI binary, one process each) on synthetic paired SAM, timed per phase (the library's own stderr line), device text path vs host.
 usage: python tools/filter_bench.py [contig_len] [depth] [outdir (default /dev/shm)]"""
 import os
 import shutil
@@ -31,5 +31,14 @@ try:
             dt = time.perf_counter() - t0
             last = [ln for ln in p.stderr.strip().split("\n") if "device" in ln or "phases" in ln]
             print(f"{'host' if extra else 'device'} text path, process wall {dt * 1e3:.0f} ms rc={p.returncode}: {' | '.join(last) if last else p.stderr[-200:]}", flush=True)
+    # the whole `polypolish polish` process on the filtered files (CUDA start-up included), both parsers
+    for extra in ([], ["--host-parse"]):
+        for rep in range(2):
+            t0 = time.perf_counter()
+            p = subprocess.run([exe, "polish", fa, os.path.join(d, "o1.sam"), os.path.join(d, "o2.sam")] + extra, capture_output=True)
+            dt = time.perf_counter() - t0
+            err = p.stderr.decode(errors="replace")
+            last = [ln for ln in err.strip().split("\n") if "GPU job" in ln or "tokeniser" in ln]
+            print(f"polish, {'host' if extra else 'device'} parser, process wall {dt * 1e3:.0f} ms rc={p.returncode} out={len(p.stdout)} B: {' | '.join(last)}", flush=True)
 finally:
     shutil.rmtree(d, ignore_errors=True)
