@@ -314,7 +314,7 @@ def main():
         }
         if t3 is not None:
             line["t3"] = t3
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             v, dt, phases, bp = cpu_baseline(min(clen, 1_000_000), depth, seed=2)
             line["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": 1, "kind": "port",
                                     "sample": f"{bp} bp x {depth:g}x slice of the same generator, whole `polish` command from SAM text ({dt:.1f} s)",
