@@ -60,7 +60,7 @@ struct DevStatus {
     unsigned long long fix_count;    // (alignment, flagged tile) pairs found by k_collect
     unsigned int node_count;         // other-allele nodes allocated
     unsigned int flags;
-    unsigned int ticket_vote, ticket_collect, ticket_fix, pad1;
+    unsigned int ticket_vote, ticket_collect, ticket_fix, n_fix_tiles;
 };
 
 struct DevParams {                   // pp_polish_params, device resident (refreshed by a memcpy before each call)
@@ -714,25 +714,33 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* a, uint32_t 
 
 #define FX_WARPS 4
 #define FX_BATCH 128                 // list entries staged per round (4 per lane, their gathers in flight together)
-__global__ void __launch_bounds__(FX_WARPS * 32) k_depth_fixup(DevData d, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals) {
+
+// Where each flagged tile's run starts and ends in the sorted list, and the list of tiles that have one: one pass over the
+// sorted keys instead of a ticket per tile and two binary searches per flagged tile.
+__global__ void __launch_bounds__(256) k_fix_runs(DevData d, const uint32_t* __restrict__ keys, uint32_t* __restrict__ run_lo, uint32_t* __restrict__ run_hi,
+                                                  uint32_t* __restrict__ tiles) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.fix_cap) return;
+    const uint32_t k = keys[i];
+    if (!k) return;
+    if (i == 0 || keys[i - 1] != k) {
+        run_lo[k - 1] = i;
+        tiles[atomicAdd(&d.st->n_fix_tiles, 1u)] = k - 1;
+    }
+    if (i + 1 == d.fix_cap || keys[i + 1] != k) run_hi[k - 1] = i + 1;
+}
+
+__global__ void __launch_bounds__(FX_WARPS * 32) k_depth_fixup(DevData d, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ run_lo,
+                                                               const uint32_t* __restrict__ run_hi, const uint32_t* __restrict__ tiles) {
     // One WARP per flagged tile, four consecutive positions per lane (four independent dependent-add chains); the
     // tile's list is staged FX_BATCH entries at a time in the warp's own shared-memory slice.
     __shared__ uint2 s_rng[FX_WARPS][FX_BATCH];        // (start, length) of each staged entry
     __shared__ double s_inv[FX_WARPS][FX_BATCH];       // 1.0 / k
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    for (;;) {
-        // warps pull tiles from a shared ticket so that the few heavy (flagged, long-list) tiles spread over the chip;
-        // neighbouring tiles of one repeat land on different warps
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(&d.st->ticket_fix, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= d.n_tiles) break;
-        if (!((d.tileflag[tile >> 5] >> (tile & 31)) & 1u)) continue;
-        uint32_t lo = 0, hi = 0;
-        if (lane == 0) lo = lower_bound_u32(keys, d.fix_cap, tile + 1);
-        if (lane == 1) hi = lower_bound_u32(keys, d.fix_cap, tile + 2);
-        lo = __shfl_sync(0xffffffffu, lo, 0);
-        hi = __shfl_sync(0xffffffffu, hi, 1);
+    const uint32_t n_fix = d.st->n_fix_tiles;
+    for (uint32_t w = blockIdx.x * FX_WARPS + wib; w < n_fix; w += gridDim.x * FX_WARPS) {
+        const uint32_t tile = tiles[w];
+        const uint32_t lo = run_lo[tile], hi = run_hi[tile];
         const uint32_t p = tile * PP_TILE + lane * 4;
         double dep0 = 0.0, dep1 = 0.0, dep2 = 0.0, dep3 = 0.0;
         for (uint32_t base = lo; base < hi; base += FX_BATCH) {
@@ -1301,6 +1309,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         uint8_t* zp = ctx->b[B_ZEROPOOL].as<uint8_t>();
         CK(ctx->b[B_NODES].ensure((size_t)node_cap * sizeof(OthNode)));
         CK(ctx->b[B_FIXKEY2].ensure((size_t)fix_cap * 4)); CK(ctx->b[B_FIXVAL2].ensure((size_t)fix_cap * 4));
+        CK(ctx->b[B_FIXRUN].ensure((size_t)n_tiles * 12 + 64));
         CK(ctx->b[B_OUT].ensure(out_cap + 64));
         size_t cub_bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
@@ -1379,8 +1388,11 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
             k_collect<<<n_cchunks, CL_THREADS, 0, s>>>(d, cp);
             CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, cub_bytes, d.fix_key, ctx->b[B_FIXKEY2].as<uint32_t>(), d.fix_val,
                                                ctx->b[B_FIXVAL2].as<uint32_t>(), (int)fix_cap, 0, tile_bits, s));
-            k_depth_fixup<<<std::min<uint32_t>((n_tiles + FX_WARPS - 1) / FX_WARPS, ctx->sm_count * 16), FX_WARPS * 32, 0, s>>>(d, ctx->b[B_FIXKEY2].as<uint32_t>(), ctx->b[B_FIXVAL2].as<uint32_t>());
-            ctx->launches += 2;
+            uint32_t* runs = ctx->b[B_FIXRUN].as<uint32_t>();
+            k_fix_runs<<<(fix_cap + 255) / 256, 256, 0, s>>>(d, ctx->b[B_FIXKEY2].as<uint32_t>(), runs, runs + n_tiles, runs + 2 * (size_t)n_tiles);
+            k_depth_fixup<<<std::min<uint32_t>((n_tiles + FX_WARPS - 1) / FX_WARPS, ctx->sm_count * 16), FX_WARPS * 32, 0, s>>>(d, ctx->b[B_FIXVAL2].as<uint32_t>(), runs,
+                                                                                                                            runs + n_tiles, runs + 2 * (size_t)n_tiles);
+            ctx->launches += 3;
         }
         // ---- stage 5: vote; stage 4: compaction
         CK(cudaEventRecord(ctx->ev[4], s));
