@@ -41,7 +41,7 @@
 #define SC_SEQ_BYTES 12288           // smem window for the block's slice of the sequence pool (4-bit mode)
 #define SC_GROUP_SCAN_LIMIT 8192     // alignments of one read group a thread will scan outside its block for k
 #define CL_THREADS 256               // collect CTA
-#define CL_ITEMS 4
+#define CL_ITEMS 8
 #define CL_CHUNK (CL_THREADS * CL_ITEMS)
 #define VT_THREADS 256
 #define VT_ITEMS 8
@@ -1431,6 +1431,10 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         if (again) continue;
         if (hs.flags & FL_COUNTER_OVF)
             return ctx->fail(PP_ERR_INPUT, "a position is covered by 65536 or more alignments: not supported by this build's 16-bit allele counters");
+
+        // the side buffers shrink to what this dataset needs (sort length, zeroing); a later call with other options that
+        // needs more overflows once and grows them again
+        ctx->fix_cap = std::min<uint32_t>(ctx->fix_cap, (uint32_t)std::max<uint64_t>(1 << 16, hs.fix_count + hs.fix_count / 8 + 1024));
 
         ctx->have_debug = ctx->debug_on; ctx->last_head = d.oth_head; ctx->last_nodes = std::min(hs.node_count, node_cap);
         res->out_len = hs.out_len;
