@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -648,18 +649,11 @@ __device__ __forceinline__ uint32_t bankers_rounding(double x) {
 // (block scan + decoupled look-back).  A stable sort by tile then leaves each tile's list in SAM order, which is
 // the order the reference adds depth contributions in (pileup.rs:64).
 // ------------------------------------------------------------------------------------------------------
-struct CollectParams { uint32_t n_chunks; uint32_t* st; unsigned long long *agg, *inc; };
+struct CollectParams { uint32_t n_chunks; unsigned long long* chunk_off; };   // chunk_off[c]: pairs before chunk c (after the scan)
 
-__global__ void __launch_bounds__(CL_THREADS) k_collect(DevData d, CollectParams cp) {
-    __shared__ unsigned long long s_warp[CL_THREADS / 32];
-    __shared__ unsigned long long s_total, s_prefix;
-    __shared__ uint32_t s_chunk;
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) s_chunk = atomicAdd(&d.st->ticket_collect, 1u);
-    __syncthreads();
-    const uint32_t chunk = s_chunk;
-    if (chunk >= cp.n_chunks) return;
-    const unsigned long long a0 = (unsigned long long)chunk * CL_CHUNK + tid * CL_ITEMS;
+// Pairs of one thread's CL_ITEMS consecutive alignments: count, or write them at o.
+template <bool WRITE>
+__device__ __forceinline__ unsigned long long collect_items(const DevData& d, unsigned long long a0, unsigned long long o) {
     unsigned long long gn[CL_ITEMS];
     {
         const ulonglong2* q = reinterpret_cast<const ulonglong2*>(d.rec_gn + a0);     // rec_gn is padded to whole chunks
@@ -669,37 +663,46 @@ __global__ void __launch_bounds__(CL_THREADS) k_collect(DevData d, CollectParams
     unsigned long long cnt = 0;
 #pragma unroll
     for (int i = 0; i < CL_ITEMS; ++i) {
-        if (a0 + i >= d.n_aln) gn[i] = 0;
-        const uint32_t nk = (uint32_t)gn[i];
-        if (!nk) continue;
-        const uint32_t gs = (uint32_t)(gn[i] >> 32);
-        for (uint32_t t = gs >> PP_TILE_SHIFT; t <= ((gs + nk - 1) >> PP_TILE_SHIFT); ++t)
-            cnt += (d.tileflag[t >> 5] >> (t & 31)) & 1u;
-    }
-    const unsigned long long excl = block_exscan(cnt, s_warp, &s_total);
-    const unsigned long long total = s_total;
-    if (tid < 32) {
-        const unsigned long long pre = lookback(chunk, total, cp.st, cp.agg, cp.inc);
-        if (tid == 0) s_prefix = pre;
-    }
-    __syncthreads();
-    unsigned long long o = s_prefix + excl;
-    if (chunk == cp.n_chunks - 1 && tid == CL_THREADS - 1) {
-        d.st->fix_count = o + cnt;
-        if (o + cnt > d.fix_cap) atomicOr(&d.st->flags, FL_FIX_OVF);
-    }
-    if (!cnt) return;
-#pragma unroll
-    for (int i = 0; i < CL_ITEMS; ++i) {
+        if (a0 + i >= d.n_aln) continue;
         const uint32_t nk = (uint32_t)gn[i];
         if (!nk) continue;
         const uint32_t gs = (uint32_t)(gn[i] >> 32);
         for (uint32_t t = gs >> PP_TILE_SHIFT; t <= ((gs + nk - 1) >> PP_TILE_SHIFT); ++t)
             if ((d.tileflag[t >> 5] >> (t & 31)) & 1u) {
-                if (o < d.fix_cap) { d.fix_key[o] = t + 1; d.fix_val[o] = (uint32_t)(a0 + i); }
-                o++;
+                if (WRITE) {
+                    if (o < d.fix_cap) { d.fix_key[o] = t + 1; d.fix_val[o] = (uint32_t)(a0 + i); }
+                    o++;
+                }
+                cnt++;
             }
     }
+    return cnt;
+}
+
+// Pass 1: pairs per chunk of CL_CHUNK alignments (then one small device scan).  Pass 2: the pairs, written in alignment order.
+// (A single pass with a decoupled look-back spent most of its time waiting for the prefix wavefront: 79 us.)
+__global__ void __launch_bounds__(CL_THREADS) k_collect_count(DevData d, CollectParams cp) {
+    __shared__ unsigned long long s_warp[CL_THREADS / 32];
+    __shared__ unsigned long long s_total;
+    const uint32_t chunk = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long cnt = collect_items<false>(d, (unsigned long long)chunk * CL_CHUNK + tid * CL_ITEMS, 0);
+    block_exscan(cnt, s_warp, &s_total);
+    if (tid == 0) cp.chunk_off[chunk] = s_total;
+}
+
+__global__ void __launch_bounds__(CL_THREADS) k_collect(DevData d, CollectParams cp) {
+    __shared__ unsigned long long s_warp[CL_THREADS / 32];
+    __shared__ unsigned long long s_total;
+    const uint32_t chunk = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long a0 = (unsigned long long)chunk * CL_CHUNK + tid * CL_ITEMS;
+    const unsigned long long cnt = collect_items<false>(d, a0, 0);
+    const unsigned long long excl = block_exscan(cnt, s_warp, &s_total);
+    const unsigned long long o = cp.chunk_off[chunk] + excl;
+    if (chunk == cp.n_chunks - 1 && tid == CL_THREADS - 1) {
+        d.st->fix_count = o + cnt;
+        if (o + cnt > d.fix_cap) atomicOr(&d.st->flags, FL_FIX_OVF);
+    }
+    if (cnt) collect_items<true>(d, a0, o);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1314,7 +1317,11 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         size_t cub_bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                            (uint32_t*)nullptr, (int)fix_cap, 0, tile_bits, s));
-        CK(ctx->b[B_CUBTMP].ensure(cub_bytes));
+        {
+            size_t scan_bytes = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)std::max<uint32_t>(n_cchunks, 1)));
+            CK(ctx->b[B_CUBTMP].ensure(std::max(cub_bytes, scan_bytes) + 256));
+        }
 
         DevData d;
         d.n_aln = n_aln;
@@ -1383,16 +1390,21 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         CK(cudaEventRecord(ctx->ev[3], s));
         if (n_aln) {
             CollectParams cp;
-            cp.n_chunks = n_cchunks; cp.st = (uint32_t*)(zp + o_stc);
-            cp.agg = ctx->b[B_AGGC].as<unsigned long long>(); cp.inc = ctx->b[B_INCC].as<unsigned long long>();
+            cp.n_chunks = n_cchunks; cp.chunk_off = ctx->b[B_AGGC].as<unsigned long long>();
+            k_collect_count<<<n_cchunks, CL_THREADS, 0, s>>>(d, cp);
+            {
+                size_t tb = ctx->b[B_CUBTMP].cap;
+                CK(cub::DeviceScan::ExclusiveSum(ctx->b[B_CUBTMP].p, tb, cp.chunk_off, cp.chunk_off, (int)n_cchunks, s));
+            }
             k_collect<<<n_cchunks, CL_THREADS, 0, s>>>(d, cp);
+            ctx->launches += 2;          // (the scan and the sort are library launches, not counted)
             CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, cub_bytes, d.fix_key, ctx->b[B_FIXKEY2].as<uint32_t>(), d.fix_val,
                                                ctx->b[B_FIXVAL2].as<uint32_t>(), (int)fix_cap, 0, tile_bits, s));
             uint32_t* runs = ctx->b[B_FIXRUN].as<uint32_t>();
             k_fix_runs<<<(fix_cap + 255) / 256, 256, 0, s>>>(d, ctx->b[B_FIXKEY2].as<uint32_t>(), runs, runs + n_tiles, runs + 2 * (size_t)n_tiles);
             k_depth_fixup<<<std::min<uint32_t>((n_tiles + FX_WARPS - 1) / FX_WARPS, ctx->sm_count * 16), FX_WARPS * 32, 0, s>>>(d, ctx->b[B_FIXVAL2].as<uint32_t>(), runs,
                                                                                                                             runs + n_tiles, runs + 2 * (size_t)n_tiles);
-            ctx->launches += 3;
+            ctx->launches += 2;
         }
         // ---- stage 5: vote; stage 4: compaction
         CK(cudaEventRecord(ctx->ev[4], s));
