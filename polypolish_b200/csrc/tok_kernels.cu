@@ -555,8 +555,19 @@ static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path) {
     const uint64_t n = (uint64_t)sb.st_size;
     const int buf = T->next_buf;
     int rc = ring_ready(ctx, T);
-    if (rc == PP_OK) rc = text_buffer(ctx, T->text[buf], n);
     if (rc != PP_OK) { close(fd); return rc; }
+    if (T->text[buf].cap < n + 64) {
+        // The text, its line index / records and the arrays built from it must fit beside what is already resident; a file too
+        // large for that goes through the host parser (which needs no device memory for text).
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || (double)free_b + (double)T->text[buf].cap < 2.6 * (double)n + (256 << 20)) {
+            cudaGetLastError();
+            close(fd);
+            return PP_TOK_HOST;
+        }
+    }
+    rc = text_buffer(ctx, T->text[buf], n);
+    if (rc != PP_OK) { cudaGetLastError(); close(fd); return PP_TOK_HOST; }
     T->next_buf ^= 1;
     TokState::Prefetch& pf = T->pf;
     pf.active = true; pf.path = path; pf.buf = buf; pf.n = n; pf.last = '\n'; pf.rc = PP_OK; pf.cuda_err = 0; pf.ms = 0;
