@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -61,7 +62,15 @@ static uint32_t parse_u32(const char* flag, const char* s) {
     return (uint32_t)v;
 }
 
+// POLYPOLISH_TIMING=1: wall-clock marks on stderr (process start-up vs the command itself)
+static void mark(const char* what) {
+    static const auto t0 = std::chrono::steady_clock::now();
+    static const bool on = getenv("POLYPOLISH_TIMING") != nullptr;
+    if (on) fprintf(stderr, "[timing] %8.1f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+}
+
 int main(int argc, char** argv) {
+    mark("main");
     if (argc < 2) { help(); return 2; }
     std::string cmd = argv[1];
     if (cmd == "-h" || cmd == "--help") { help(); return 0; }
@@ -98,6 +107,7 @@ int main(int argc, char** argv) {
         std::vector<pp_ctx*> ctxs(gpus, nullptr);
         for (int g = 0; g < gpus; ++g)
             if (pp_create(device + g, &ctxs[g]) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
+        mark("contexts created");
         if (host_parse) pp_set_parser(ctxs[0], 1);
         std::vector<const char*> sams;
         for (size_t i = 1; i < pos.size(); ++i) sams.push_back(pos[i].c_str());
@@ -106,10 +116,12 @@ int main(int argc, char** argv) {
         if (!quiet) fprintf(stderr, "Starting Polypolish polish (B200 build %s, %d GPU%s)\n\n", pp_version(), gpus, gpus > 1 ? "s" : "");
         int rc = pp_polish_files_multi(ctxs.data(), gpus, pos[0].c_str(), sams.data(), (int)sams.size(), &prm, debug.empty() ? nullptr : debug.c_str(), &out, &n, quiet ? 0 : 1);
         if (rc != PP_OK) { std::string m = pp_last_error(ctxs[0]); for (auto c : ctxs) pp_destroy(c); quit_with_error(m); }
+        mark("polished");
         fwrite(out, 1, n, stdout);
         fflush(stdout);
         pp_free(out);
         for (auto c : ctxs) pp_destroy(c);
+        mark("contexts destroyed");
         if (!quiet) fprintf(stderr, "Finished!\n");
         return 0;
     }
