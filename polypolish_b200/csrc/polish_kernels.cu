@@ -786,7 +786,7 @@ struct VoteParams {
     unsigned long long out_cap;
     unsigned long long* out_off;     // [n_contigs+1]
     unsigned long long *changed, *zero_depth;   // [n_contigs]
-    uint32_t* st1; unsigned long long *agg1, *inc1;   // look-back descriptors of the difference-array prefix sum
+    const unsigned long long* chunk_pre;   // [n_chunks] sum of diff[] before the chunk (k_diff_sums + device scan, side stream)
     // per-position verdicts handed from k_vote to k_compact
     uint16_t* res;                    // [padG] low byte = character, high byte = output length (255: see rec_at)
     uint32_t* rec_at;                 // [G] other-allele node to emit at a position (only where res says so)
@@ -885,17 +885,28 @@ __device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const DevParam
     return o;
 }
 
+// Sum of the difference array over each vote chunk.  Depends on the scatter only, so it runs (with a small device scan) on
+// the side stream while the main stream does the fix-up; k_vote then starts from a known prefix instead of waiting for a
+// look-back wavefront (26 % of its stall samples).
+__global__ void __launch_bounds__(VT_THREADS) k_diff_sums(const unsigned long long* __restrict__ diff, unsigned long long* __restrict__ chunk_sum) {
+    __shared__ unsigned long long s_warp[VT_THREADS / 32];
+    __shared__ unsigned long long s_total;
+    const uint32_t p0 = blockIdx.x * VT_CHUNK + threadIdx.x * VT_ITEMS;
+    const ulonglong2* q = reinterpret_cast<const ulonglong2*>(diff + p0);
+    unsigned long long t = 0;
+#pragma unroll
+    for (int i = 0; i < VT_ITEMS / 2; ++i) { const ulonglong2 v = q[i]; t += v.x + v.y; }
+    block_exscan(t, s_warp, &s_total);
+    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = s_total;
+}
+
 template <int BITS>
 __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp) {
     __shared__ unsigned long long s_warp[VT_THREADS / 32];
-    __shared__ unsigned long long s_total, s_prefix;
+    __shared__ unsigned long long s_total;
     __shared__ long long s_delta[VT_THREADS / 32];
-    __shared__ uint32_t s_chunk;
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) s_chunk = atomicAdd(&d.st->ticket_vote, 1u);
-    __syncthreads();
-    const uint32_t chunk = s_chunk;
-    if (chunk >= vp.n_chunks) return;
+    const uint32_t chunk = blockIdx.x;
     const uint32_t p0 = chunk * VT_CHUNK + tid * VT_ITEMS;
     const DevParams prm = *d.prm;
 
@@ -910,15 +921,7 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
 #pragma unroll
     for (int i = 0; i < VT_ITEMS; ++i) { tsum += dv[i]; dv[i] = tsum; }     // thread-inclusive
     const unsigned long long texcl = block_exscan(tsum, s_warp, &s_total);
-    const unsigned long long total = s_total;
-    if (tid < 32) {
-        const unsigned long long pre = lookback(chunk, total, vp.st1, vp.agg1, vp.inc1);
-        if (tid == 0) s_prefix = pre;
-    }
-    __syncthreads();
-    const unsigned long long base = s_prefix + texcl;
-
-    // ---- 2. vote
+    const unsigned long long base = vp.chunk_pre[chunk] + texcl;
     unsigned long long exv[VT_ITEMS];
     uint32_t dlv[VT_ITEMS];
     {
@@ -930,6 +933,8 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
         for (int i = 0; i < VT_ITEMS / 4; ++i) { const uint4 v = r[i]; dlv[4 * i] = v.x; dlv[4 * i + 1] = v.y; dlv[4 * i + 2] = v.z; dlv[4 * i + 3] = v.w; }
     }
     const uint2 dr = *reinterpret_cast<const uint2*>(d.draft + p0);
+
+    // ---- 2. vote
     OthCtx oc;
     oc.nodes = d.nodes; oc.head = d.oth_head;
     oc.sr = SeqRef{d.seq_pool, d.seq_off, d.seq_len, d.flags};
@@ -1158,6 +1163,8 @@ extern "C" int pp_create(int device, pp_ctx** out) {
     if (ctx->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     for (auto& ev : ctx->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    for (auto& ev : ctx->side_ev) if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     if (cudaHostAlloc((void**)&ctx->h_status, sizeof(DevStatus), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     if (cudaHostAlloc((void**)&ctx->h_params, sizeof(DevParams), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     uint8_t comp[256];
@@ -1174,6 +1181,8 @@ extern "C" void pp_destroy(pp_ctx* ctx) {
     pp_tok_release(ctx);
     for (auto& b : ctx->b) b.release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->side_ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1318,6 +1327,11 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                            (uint32_t*)nullptr, (int)fix_cap, 0, tile_bits, s));
         {
+            size_t vscan = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, vscan, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)n_chunks));
+            CK(ctx->b[B_CUBTMP2].ensure(vscan + 256));
+        }
+        {
             size_t scan_bytes = 0;
             CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)std::max<uint32_t>(n_cchunks, 1)));
             CK(ctx->b[B_CUBTMP].ensure(std::max(cub_bytes, scan_bytes) + 256));
@@ -1388,6 +1402,16 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         }
         // ---- stage 3: ordered depth where k != 1 coverage exists: collect -> stable sort by tile -> ordered walk
         CK(cudaEventRecord(ctx->ev[3], s));
+        {   // beside it, on the side stream: the vote chunks' prefix of the difference array
+            CK(cudaEventRecord(ctx->side_ev[0], s));
+            CK(cudaStreamWaitEvent(ctx->side, ctx->side_ev[0], 0));
+            unsigned long long* pre = ctx->b[B_AGG1].as<unsigned long long>();
+            k_diff_sums<<<n_chunks, VT_THREADS, 0, ctx->side>>>(d.diff, pre);
+            size_t tb = ctx->b[B_CUBTMP2].cap;
+            CK(cub::DeviceScan::ExclusiveSum(ctx->b[B_CUBTMP2].p, tb, pre, pre, (int)n_chunks, ctx->side));
+            CK(cudaEventRecord(ctx->side_ev[1], ctx->side));
+            ctx->launches++;
+        }
         if (n_aln) {
             CollectParams cp;
             cp.n_chunks = n_cchunks; cp.chunk_off = ctx->b[B_AGGC].as<unsigned long long>();
@@ -1413,7 +1437,8 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         vp.out = ctx->b[B_OUT].as<uint8_t>(); vp.out_cap = out_cap;
         vp.out_off = ctx->b[B_OUTOFF].as<unsigned long long>();
         vp.changed = (unsigned long long*)(zp + o_chg); vp.zero_depth = (unsigned long long*)(zp + o_zero);
-        vp.st1 = (uint32_t*)(zp + o_st1); vp.agg1 = ctx->b[B_AGG1].as<unsigned long long>(); vp.inc1 = ctx->b[B_INC1].as<unsigned long long>();
+        vp.chunk_pre = ctx->b[B_AGG1].as<unsigned long long>();
+        CK(cudaStreamWaitEvent(s, ctx->side_ev[1], 0));
         vp.res = ctx->b[B_RES].as<uint16_t>(); vp.rec_at = ctx->b[B_RECAT].as<uint32_t>();
         vp.chunk_delta = ctx->b[B_CHUNKDELTA].as<long long>();
         vp.dbg = nullptr;
