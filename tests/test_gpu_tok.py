@@ -193,3 +193,66 @@ def test_tokeniser_unknown_reference_goes_to_the_polish_error(ctx, oracle, tmp_p
     with pytest.raises(pp.PolypolishError) as ei:
         ctx.polish_files(fa, [s])
     assert ei.value.msg == eo.value.msg and "c3" in ei.value.msg
+
+
+def test_tokeniser_many_contigs_three_files(ctx, oracle, tmp_path):
+    """3000 contig names (hash-table probing, names that are prefixes of each other), three SAM files, records of every file
+    hitting every contig; plus the polished bytes through both parsers."""
+    import random
+    rng = random.Random(77)
+    names = [f"c{i}" for i in range(1500)] + [f"c{i}_x" for i in range(1500)]
+    seqs = ["".join(rng.choice("ACGT") for _ in range(60)) for _ in names]
+    fa = tmp_path / "many.fasta"
+    fa.write_text("".join(f">{n}\n{s}\n" for n, s in zip(names, seqs)))
+    files = []
+    for k in range(3):
+        rows = []
+        for j in range(4000):
+            c = rng.randrange(len(names))
+            st = rng.randrange(0, 20)
+            rows.append("\t".join([f"r{k}_{j // 2}", str(rng.choice([0, 16])), names[c], str(st + 1), "60", "40M", "*", "0", "0", seqs[c][st:st + 40], "I" * 40,
+                                   "NM:i:0"]))
+        p = tmp_path / f"s{k}.sam"
+        p.write_text("\n".join(rows) + "\n")
+        files.append(p)
+    f, p = host_arrays(fa, files, False)
+    rc, dev, stats = device_arrays(ctx, f, files, False, 4)
+    assert rc == PP_OK and len(stats) == 3
+    assert_same(dev, p.arrays())
+    exp = oracle.polish(fa, files)["fasta"]
+    for mode in (0, 1):
+        ctx.set_parser(mode)
+        try:
+            assert ctx.polish_files(fa, files) == exp
+        finally:
+            ctx.set_parser(0)
+
+
+def test_tokeniser_slice_boundaries(ctx, tmp_path):
+    """Lines straddling the 4 MiB upload slices and the 16 KiB newline tiles, CRLF pairs split by a slice boundary, a last line
+    without newline: a text built so that '\\r' and '\\n' of one line end sit on either side of byte 4 Mi."""
+    fa = tmp_path / "a.fasta"
+    fa.write_text(FA)
+    body = []
+    total = 0
+    i = 0
+    target = 4 << 20
+    while total + 6000 < target:
+        ln = line(f"q{i}", seq="ACGT" * 10, cigar="40M", qual="I" * 40).replace("\n", "\r\n")
+        body.append(ln)
+        total += len(ln)
+        i += 1
+    want = target - total + 1                    # the filler line's '\r' lands on byte 4 Mi - 1, its '\n' on byte 4 Mi
+    filler = line("z", seq="ACGT" * 10, cigar="40M", qual="I" * 40, tags=("NM:i:0", "XX:Z:" + "y" * 4000))
+    base_len = len(filler.replace("\n", "\r\n"))
+    extra = want - base_len
+    filler = line("z", seq="ACGT" * 10, cigar="40M", qual="I" * 40, tags=("NM:i:0", "XX:Z:" + "y" * (4000 + extra))).replace("\n", "\r\n")
+    text = "".join(body) + filler + "".join(body[:500]) + line("last")[:-1]
+    raw = text.encode()
+    assert raw[target - 1:target + 1] == b"\r\n"
+    s = tmp_path / "b.sam"
+    s.write_bytes(raw)
+    f, p = host_arrays(fa, [s], False)
+    rc, dev, _ = device_arrays(ctx, f, [s], False, 4)
+    assert rc == PP_OK
+    assert_same(dev, p.arrays())
