@@ -206,7 +206,7 @@ class Packed:
 
     def _check(self, rc):
         if rc != PP_OK:
-            raise PolypolishError(rc, lib().pp_pack_error(self.h).decode())
+            raise PolypolishError(rc, lib().pp_pack_error(self.h).decode("utf-8", "replace"))
 
     def set_threads(self, n_threads, min_chunk_bytes=8 << 20):
         L = lib()
@@ -277,7 +277,7 @@ class Context:
         self.h = h
 
     def _err(self, rc):
-        return PolypolishError(rc, lib().pp_last_error(self.h).decode())
+        return PolypolishError(rc, lib().pp_last_error(self.h).decode("utf-8", "replace"))
 
     def close(self):
         if self.h:

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TK_LINE_THREADS) k_tok_emit(EmitArgs a) {
     a.name_len[la] = r.name_len;
     tok::Txt x(a.p.text);
     tok::emit_cigar(x, s, r, a.cigar_ops + co);
-    tok::emit_seq<BITS>(x, s, r, s_nib, a.seq_pool + bo * (BITS == 4 ? 16 : 32));
+    if (tok::emit_seq<BITS>(x, s, r, s_nib, a.seq_pool + bo * (BITS == 4 ? 16 : 32))) a.p.st->need8 = 1;
 }
 
 __global__ void __launch_bounds__(TK_LINE_THREADS) k_tok_heads(const uint8_t* __restrict__ text, uint64_t n_al, const unsigned long long* __restrict__ name_pos,
@@ -389,7 +389,6 @@ static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n
     const uint64_t n_al = T->h_tot[0], n_ops = T->h_tot[1], n_blk = T->h_tot[2];
     if (stats) stats->alignments = n_al;
     if (T->h_st->first_bad != ~0ull) return PP_TOK_HOST;
-    if (T->h_st->need8 && T->seq_bits == 4) return PP_TOK_NEED8;
     if (n_al == 0) return PP_TOK_HOST;                       // alignment.rs:268-270
     if (T->aln_base + n_al >= 0xFFFFFFFFull - 4096 || T->ops_base + n_ops > 0xFFFFFFFFull || T->blk_base + n_blk > 0xFFFFFFFFull) return PP_TOK_HOST;
 
@@ -445,6 +444,7 @@ static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n
     CK(cudaGetLastError());
     launches += 4;
     if (T->h_st->group_err) return PP_TOK_HOST;
+    if (T->h_st->need8 && T->seq_bits == 4) return PP_TOK_NEED8;   // found while the bases were converted (k_tok_emit)
     const uint64_t n_reads = *h_reads;
     if (T->read_base + n_reads >= 0xFFFFFFFFull) return PP_TOK_HOST;
     T->aln_base = A1; T->ops_base += n_ops; T->blk_base += n_blk; T->read_base += n_reads;

@@ -41,6 +41,26 @@ struct Txt {
         }
         return (uint8_t)(w >> (8 * (p & 7)));
     }
+    // Position of the first '\t' in [p, e), or e: eight bytes per step (exact zero-byte test on w ^ tabs; the buffer is padded,
+    // so a word that reaches past e is readable and a hit past e counts as "none").
+    TK_HD uint64_t find_tab(uint64_t p, uint64_t e) {
+        while (p < e) {
+            at(p);
+            const uint64_t y = w ^ 0x0909090909090909ull;
+            uint64_t m = ~(((y & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | y | 0x7F7F7F7F7F7F7F7Full);
+            m &= ~0ull << (8 * (p & 7));
+            if (m) {
+#ifdef __CUDA_ARCH__
+                const uint64_t pos = wpos + ((uint64_t)(__ffsll((long long)m) - 1) >> 3);
+#else
+                const uint64_t pos = wpos + ((uint64_t)__builtin_ctzll(m) >> 3);
+#endif
+                return pos < e ? pos : e;
+            }
+            p = wpos + 8;
+        }
+        return e;
+    }
 };
 
 // Contig names: open addressing on the FNV-1a hash of the name, confirmed byte by byte.
@@ -88,10 +108,7 @@ TK_HD bool field_uint(Txt& x, uint64_t p, uint64_t e, uint64_t maxv, uint64_t& v
     return any;
 }
 
-TK_HD uint64_t field_end(Txt& x, uint64_t p, uint64_t e) {
-    while (p < e && x.at(p) != '\t') ++p;
-    return p;
-}
+TK_HD uint64_t field_end(Txt& x, uint64_t p, uint64_t e) { return x.find_tab(p, e); }
 
 TK_HD uint8_t lower(uint8_t c) { return (c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c; }
 
@@ -172,14 +189,9 @@ TK_HD uint8_t parse_line(Txt& x, uint64_t s, uint64_t e, const ContigTable& ct, 
         if (fe == e) return LK_HOST;
         p = fe + 1;
     }
-    // 9 SEQ
+    // 9 SEQ (its alphabet is checked where the bases are converted: emit_seq)
     r.seq_rel = (uint32_t)(p - s);
-    uint8_t need8 = 0;
-    for (fe = p; fe < e; ++fe) {
-        const uint8_t c = x.at(fe);
-        if (c == '\t') break;
-        need8 |= (uint8_t)(nibtab[c] == 0);
-    }
+    fe = field_end(x, p, e);
     if (fe == e) return LK_HOST;
     const uint64_t slen = fe - p;
     const bool star = slen == 1 && x.at(p) == '*';
@@ -228,7 +240,7 @@ TK_HD uint8_t parse_line(Txt& x, uint64_t s, uint64_t e, const ContigTable& ct, 
     r.nops = nops;
     r.slen = star ? 0 : (uint32_t)slen;
     r.flags = (uint8_t)(((sam_flags & 16) ? PP_FLAG_REVERSE : 0) | (pass_qc ? 0 : PP_FLAG_ZPFAIL) | (star ? PP_FLAG_SEQSTAR : 0));
-    r.need8 = star ? 0 : need8;
+    r.need8 = 0;
     r.kind = LK_ALIGNED;
     return LK_ALIGNED;
 }
@@ -251,20 +263,22 @@ TK_HD void emit_cigar(Txt& x, uint64_t s, const LineRec& r, uint32_t* ops) {
 }
 
 // ... and its sequence: 4-bit BAM codes (16 bytes per block) or upper-cased bytes (32 bytes per block), zero padded.
+// Returns true (4-bit pool only) when a base has no 4-bit code: the pool must be rebuilt with 8-bit bases.
 template <int BITS>
-TK_HD void emit_seq(Txt& x, uint64_t s, const LineRec& r, const uint8_t* nibtab, uint8_t* dst) {
+TK_HD bool emit_seq(Txt& x, uint64_t s, const LineRec& r, const uint8_t* nibtab, uint8_t* dst) {
     const uint64_t b = s + r.seq_rel;
     const uint32_t n = r.slen, nblk = seq_blocks(r);
+    bool exotic = false;
     for (uint32_t blk = 0; blk < nblk; ++blk) {
         if (BITS == 4) {
             uint64_t lo = 0, hi = 0;
             for (uint32_t j = 0; j < 16; ++j) {
                 const uint32_t q = blk * 32 + j;
-                if (q < n) lo |= (uint64_t)nibtab[x.at(b + q)] << (4 * j);
+                if (q < n) { const uint8_t c = nibtab[x.at(b + q)]; exotic |= c == 0; lo |= (uint64_t)c << (4 * j); }
             }
             for (uint32_t j = 0; j < 16; ++j) {
                 const uint32_t q = blk * 32 + 16 + j;
-                if (q < n) hi |= (uint64_t)nibtab[x.at(b + q)] << (4 * j);
+                if (q < n) { const uint8_t c = nibtab[x.at(b + q)]; exotic |= c == 0; hi |= (uint64_t)c << (4 * j); }
             }
             uint64_t* d = reinterpret_cast<uint64_t*>(dst + (size_t)blk * 16);
             d[0] = lo; d[1] = hi;
@@ -283,6 +297,7 @@ TK_HD void emit_seq(Txt& x, uint64_t s, const LineRec& r, const uint8_t* nibtab,
             }
         }
     }
+    return exotic;
 }
 
 // Does alignment a open a new read group?  (alignment.rs:255: a record joins the open group iff the open name is empty

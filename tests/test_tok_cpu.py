@@ -202,9 +202,9 @@ def test_tok_logic_random_bytes_never_disagree(H, tmp_path):
     base = [line(f"q{i // 2}", rng.choice([0, 16, 4, 256, 272] if i % 2 else [0, 16]), rng.choice(["c1", "c2", "c10", "zz"]), rng.randint(0, 30),
                  rng.choice(["4M", "2M1I1M", "1M1D3M", "2S2M", "4="]), rng.choice(["ACGT", "*", "acgn"] if i % 2 else ["ACGT", "acgn"]),
                  (f"NM:i:{rng.randint(0, 12)}",) + (("ZP:Z:fail",) if rng.random() < 0.1 else ())) for i in range(40)]
-    alphabet = "\t\t\t0123456789MIDS=X*ACGTN:@+-\r zpZP"
+    alphabet = "\t\t\t0123456789MIDS=X*ACGTN:@+-\r zpZP\x08\x08\x01\x89\xff\x0a"   # \x08 = '\t' ^ 1: the word-wise tab search must stay exact
     n_ok = n_host = 0
-    for trial in range(300):
+    for trial in range(500):
         lines = list(base)
         for _ in range(rng.randint(1, 3)):
             j = rng.randrange(len(lines))

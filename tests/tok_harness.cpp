@@ -60,7 +60,6 @@ extern "C" int tok_cpu(const char* text_in, uint64_t n, const char* const* names
     const uint64_t n_al = s_al[n_lines], n_ops = s_ops[n_lines], n_blk = s_blk[n_lines];
     counts[5] = first_bad;
     if (first_bad != ~0ull) return PP_TOK_HOST;
-    if (need8 && bits == 4) return PP_TOK_NEED8;
     if (n_al == 0) return PP_TOK_HOST;
     const uint64_t A0 = counts[0], O0 = counts[1], B0 = counts[2], R0 = counts[3];
     const uint64_t blk_bytes = bits == 4 ? 16 : 32;
@@ -77,7 +76,7 @@ extern "C" int tok_cpu(const char* text_in, uint64_t n, const char* const* names
         name_pos[la] = s; name_len[la] = r.name_len;
         tok::Txt x(text);
         tok::emit_cigar(x, s, r, cigar_ops + co);
-        if (bits == 4) tok::emit_seq<4>(x, s, r, nibtab, seq_pool + bo * 16);
+        if (bits == 4) { if (tok::emit_seq<4>(x, s, r, nibtab, seq_pool + bo * 16)) need8 = true; }
         else tok::emit_seq<8>(x, s, r, nibtab, seq_pool + bo * 32);
     }
     for (uint64_t a = 0; a < n_al; ++a) {
@@ -92,6 +91,7 @@ extern "C" int tok_cpu(const char* text_in, uint64_t n, const char* const* names
         if (head[a] && !tok::close_group(a, n_al, head.data(), careful != 0, seq_off + A0, seq_len + A0, flags + A0)) group_err = true;
     }
     if (group_err) return PP_TOK_HOST;
+    if (need8 && bits == 4) return PP_TOK_NEED8;
     counts[0] = A0 + n_al; counts[1] = O0 + n_ops; counts[2] = B0 + n_blk; counts[3] = R0 + rs[n_al - 1];
     return PP_OK;
 }
