@@ -41,25 +41,11 @@ struct Txt {
         }
         return (uint8_t)(w >> (8 * (p & 7)));
     }
-    // Position of the first '\t' in [p, e), or e: eight bytes per step (exact zero-byte test on w ^ tabs; the buffer is padded,
-    // so a word that reaches past e is readable and a hit past e counts as "none").
+    // Position of the first '\t' in [p, e), or e.  (Word-at-a-time searches - a 64-bit zero-byte test, per-byte SIMD compares on
+    // the two halves - were measured slower on the device than this loop over the cached word: 1.68 / 2.6 ms against 1.50 ms.)
     TK_HD uint64_t find_tab(uint64_t p, uint64_t e) {
-        while (p < e) {
-            at(p);
-            const uint64_t y = w ^ 0x0909090909090909ull;
-            uint64_t m = ~(((y & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | y | 0x7F7F7F7F7F7F7F7Full);
-            m &= ~0ull << (8 * (p & 7));
-            if (m) {
-#ifdef __CUDA_ARCH__
-                const uint64_t pos = wpos + ((uint64_t)(__ffsll((long long)m) - 1) >> 3);
-#else
-                const uint64_t pos = wpos + ((uint64_t)__builtin_ctzll(m) >> 3);
-#endif
-                return pos < e ? pos : e;
-            }
-            p = wpos + 8;
-        }
-        return e;
+        while (p < e && at(p) != '\t') ++p;
+        return p;
     }
 };
 
