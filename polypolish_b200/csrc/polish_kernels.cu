@@ -12,14 +12,15 @@
 // 5 Mbp x 100x), which on any GPU is bound by atomic throughput, not by HBM.  Here the pileup of a position is
 // kept in a form that needs ~3 atomics per ALIGNMENT instead of ~150:
 //   * cover[p]  = number of good alignments whose kept entries include p  -> interval add (+v at start,
-//     -v at end) into a difference array, prefix-summed inside k_vote;
+//     -v at end) into a difference array, prefix-summed by k_diff_sums + a device scan (chunk level, side stream) and k_vote;
 //   * explicit[p][allele] = entries whose allele differs from the draft base -> one atomic per mismatch
 //     (~0.3 % of bases); count[draft base] = cover - sum(explicit);
 //   * alleles other than A,C,G,T,"-" (N / IUPAC bases, insertions) -> one node per distinct (position, allele) in a
 //     per-position chain with an exact count (the reference's HashMap<String,u32>, pileup.rs:40,62);
 //   * depth: where every covering alignment has k == 1 the f64 depth equals cover exactly; positions covered
 //     by a multi-mapped read (k != 1) get the reference's sequential f64 sum re-done in SAM order by
-//     k_depth_fixup (ordered walk over the alignments binned to that 128-position tile).
+//     k_collect_count / k_collect (pairs in alignment order) -> stable sort by tile -> k_fix_runs -> k_depth_fixup
+//     (ordered walk over the alignments binned to that 128-position tile).
 // The whole call is one stream of kernels with no host round trip in the middle.  All of it is integer / byte work
 // bounded by HBM bandwidth: no tensor cores.
 #include <cuda_runtime.h>
@@ -61,7 +62,7 @@ struct DevStatus {
     unsigned long long fix_count;    // (alignment, flagged tile) pairs found by k_collect
     unsigned int node_count;         // other-allele nodes allocated
     unsigned int flags;
-    unsigned int ticket_vote, ticket_collect, ticket_fix, n_fix_tiles;
+    unsigned int n_fix_tiles, pad1, pad2, pad3;   // flagged tiles that have a run in the sorted list (k_fix_runs)
 };
 
 struct DevParams {                   // pp_polish_params, device resident (refreshed by a memcpy before each call)
@@ -555,54 +556,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_scatter(DevData d) {
     if (lane == 0 && used) atomicAdd(&sh.n_good, (uint32_t)used);
     __syncthreads();
     if (tid == 0 && sh.n_good) atomicAdd(&d.st->n_used, (unsigned long long)sh.n_good);
-}
-
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_cg64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_cg64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Exclusive prefix of chunk `c` over all earlier chunks; publishes this chunk's aggregate / inclusive prefix.
-// Called by warp 0 only (all 32 lanes).
-__device__ __forceinline__ unsigned long long lookback(uint32_t c, unsigned long long aggregate, uint32_t* st,
-                                                       unsigned long long* agg, unsigned long long* inc) {
-    const uint32_t lane = threadIdx.x & 31;
-    if (c == 0) {
-        if (lane == 0) { st_cg64(&inc[0], aggregate); st_release(&st[0], 2u); }
-        return 0;
-    }
-    if (lane == 0) { st_cg64(&agg[c], aggregate); st_release(&st[c], 1u); }
-    unsigned long long prefix = 0;
-    int j = (int)c - 1;
-    for (;;) {
-        const int idx = j - (int)lane;
-        uint32_t s = 2;
-        if (idx >= 0) { do { s = ld_acquire(&st[idx]); } while (s == 0); }
-        unsigned long long v = 0;
-        if (idx >= 0) v = (s == 2) ? ld_cg64(&inc[idx]) : ld_cg64(&agg[idx]);
-        const unsigned m = __ballot_sync(0xffffffffu, s == 2);
-        const int first = __ffs(m) - 1;          // nearest predecessor with an inclusive prefix (m != 0 eventually: idx < 0 counts)
-        if (first >= 0 && (int)lane > first) v = 0;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        v = __shfl_sync(0xffffffffu, v, 0);
-        prefix += v;
-        if (m) break;
-        j -= 32;
-    }
-    if (lane == 0) { st_cg64(&inc[c], prefix + aggregate); st_release(&st[c], 2u); }
-    return prefix;
 }
 
 // block-wide exclusive scan of one u64 per thread (VT_THREADS threads); returns exclusive prefix, total in *total
@@ -1297,8 +1250,8 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
     CK(ctx->b[B_DEPTHFIX].ensure(((size_t)n_tiles * PP_TILE + 1) * 8));
     CK(ctx->b[B_RECGN].ensure(padA * 8)); CK(ctx->b[B_RECK].ensure(padA * 4));
     CK(ctx->b[B_OUTOFF].ensure(((size_t)ctx->n_contigs + 1) * 8));
-    CK(ctx->b[B_AGG1].ensure((size_t)n_chunks * 8)); CK(ctx->b[B_INC1].ensure((size_t)n_chunks * 8));
-    CK(ctx->b[B_AGGC].ensure((size_t)n_cchunks * 8 + 8)); CK(ctx->b[B_INCC].ensure((size_t)n_cchunks * 8 + 8));
+    CK(ctx->b[B_AGG1].ensure((size_t)n_chunks * 8 + 8));       // vote chunks: prefix of the difference array
+    CK(ctx->b[B_AGGC].ensure((size_t)n_cchunks * 8 + 8));      // collect chunks: pairs before the chunk
     CK(ctx->b[B_RES].ensure(padG * 2)); CK(ctx->b[B_RECAT].ensure((G + 1) * 4)); CK(ctx->b[B_CHUNKDELTA].ensure((size_t)n_chunks * 8));
     CK(ctx->b[B_PARAMS].ensure(sizeof(DevParams)));
 
@@ -1313,7 +1266,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         size_t zoff = 0;
         auto carve = [&](size_t bytes) { size_t o = zoff; zoff += (bytes + 255) & ~size_t(255); return o; };
         const size_t o_diff = carve(padG * 8), o_ex = carve(padG * 8), o_del = carve(padG * 4), o_head = carve((G + 1) * 4),
-                     o_tile = carve(((size_t)n_tiles / 32 + 2) * 4), o_st1 = carve((size_t)n_chunks * 4), o_stc = carve((size_t)n_cchunks * 4 + 4),
+                     o_tile = carve(((size_t)n_tiles / 32 + 2) * 4),
                      o_chg = carve((size_t)ctx->n_contigs * 8), o_zero = carve((size_t)ctx->n_contigs * 8), o_status = carve(sizeof(DevStatus)),
                      o_fkey = carve((size_t)fix_cap * 4), o_fval = carve((size_t)fix_cap * 4),
                      o_k = carve(ctx->global_k ? (ctx->n_reads + 1) * 4 : 4);

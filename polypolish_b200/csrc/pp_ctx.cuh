@@ -30,7 +30,7 @@ struct DevBuf {
 
 enum { B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL,
        B_DRAFT, B_CTGOFF, B_NIB, B_ZEROPOOL, B_DEPTHFIX, B_RECGN, B_RECK, B_NODES, B_FIXKEY2, B_FIXVAL2, B_FIXRUN, B_CUBTMP, B_OUT,
-       B_OUTOFF, B_DEBUG, B_AGG1, B_INC1, B_AGGC, B_INCC, B_RES, B_RECAT, B_CHUNKDELTA, B_PARAMS, B_SCRATCH, B_SCRATCH2, B_CUBTMP2,
+       B_OUTOFF, B_DEBUG, B_AGG1, B_AGGC, B_RES, B_RECAT, B_CHUNKDELTA, B_PARAMS, B_SCRATCH, B_SCRATCH2, B_CUBTMP2,
        B_TOKLINE, B_TOKTMP, B_TOKNAMES, B_COUNT };
 
 struct pp_ctx {
