@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 3 at full size: `polypolish filter` (insert size) then `polypolish polish` on 5 Mbp x 100x synthetic
 paired SAM, through the file-level C ABI calls, timed, and compared byte for byte with the CPU oracle on the same files.
-usage: python tools/config3.py [contig_len] [depth] [out.json]      (writes nothing else; temp files under /dev/shm)"""
+usage: python tests/manual/config3.py [contig_len] [depth] [out.json]      (writes nothing else; temp files under /dev/shm)"""
 import hashlib
 import json
 import os
@@ -10,7 +10,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as g  # noqa: E402

@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """`polypolish polish --gpus N` (contigs sharded over N GPUs, SAM tokenised on the first one) against the CPU oracle.
-usage: python tools/multi_gpu_check.py [n_gpus] [n_contigs] [contig_len] [depth]"""
+usage: python tests/manual/multi_gpu_check.py [n_gpus] [n_contigs] [contig_len] [depth]"""
 import os
 import subprocess
 import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as g  # noqa: E402
