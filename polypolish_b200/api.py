@@ -308,9 +308,35 @@ class Context:
         return dict(sequences=seqs, changed=keep["changed"].tolist(), zero_depth=keep["zero"].tolist(),
                     n_aln_used=res.n_aln_used, out_len=res.out_len, timing=res.timing.as_dict())
 
-    def polish_packed(self, contigs, alns, **opts):
-        """pp_polish: host SoA in, host bases out (H2D / D2H inside)."""
+    def pinned_result(self, n_contigs, cap):
+        """Caller-owned result buffers in pinned host memory (pp_host_alloc), reusable across pp_polish calls."""
+        L = lib()
+        nbytes = [8 * (n_contigs + 1), max(1, cap), 8 * n_contigs, 8 * n_contigs]
+        ptrs = [L.pp_host_alloc(n) for n in nbytes]
+        if not all(ptrs):
+            raise PolypolishError(PP_ERR_NOMEM, "pp_host_alloc failed")
+        keep = dict(off=np.ctypeslib.as_array(C.cast(ptrs[0], C.POINTER(C.c_uint64)), shape=(n_contigs + 1,)),
+                    bases=np.ctypeslib.as_array(C.cast(ptrs[1], C.POINTER(C.c_uint8)), shape=(max(1, cap),)),
+                    changed=np.ctypeslib.as_array(C.cast(ptrs[2], C.POINTER(C.c_uint64)), shape=(n_contigs,)),
+                    zero=np.ctypeslib.as_array(C.cast(ptrs[3], C.POINTER(C.c_uint64)), shape=(n_contigs,)), _pinned=ptrs)
+        res = PolishResult()
+        res.out_off, res.out_bases, res.out_cap, res.changed, res.zero_depth = ptrs[0], ptrs[1], cap, ptrs[2], ptrs[3]
+        return res, keep
+
+    def free_pinned_result(self, keep):
+        for p in keep.pop("_pinned", []):
+            lib().pp_host_free(p)
+
+    def polish_packed(self, contigs, alns, into=None, **opts):
+        """pp_polish: host SoA in, host bases out (H2D / D2H inside).  `into` = (res, keep) from pinned_result(): the
+        result lands in those buffers and only the statistics are returned (no per-call allocation)."""
         prm = _params(**opts)
+        if into is not None:
+            res, keep = into
+            rc = lib().pp_polish(self.h, C.byref(contigs), C.byref(alns), C.byref(prm), C.byref(res))
+            if rc != PP_OK:
+                raise self._err(rc)
+            return dict(n_aln_used=res.n_aln_used, out_len=res.out_len, timing=res.timing.as_dict())
         G = int(np.ctypeslib.as_array(C.cast(contigs.off, C.POINTER(C.c_uint64)), shape=(contigs.n_contigs + 1,))[-1])
         cap = G + (1 << 20)
         for _ in range(2):
