@@ -22,7 +22,8 @@ class PolypolishError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(ROOT, "build", "libpolypolish_b200.so")
+    """The in-tree library; POLYPOLISH_LIB selects another build of it (kernel experiments)."""
+    return os.environ.get("POLYPOLISH_LIB") or os.path.join(ROOT, "build", "libpolypolish_b200.so")
 
 
 class Alignments(C.Structure):
