@@ -288,7 +288,9 @@ void pp_shards_free(pp_shards* s);
 
 /* Whole commands (the functions the CLI calls; same behaviour, error text and exit status as the
  * reference's polish::polish (polish.rs:26-38) and filter::filter (filter.rs:26-37)).
- * out_fasta receives exactly what the reference prints to stdout; free with pp_free. */
+ * out_fasta receives exactly what the reference prints to stdout; free with pp_free.
+ * pp_polish_files parses its SAM files with the device tokeniser (pp_tok_*) unless pp_set_parser(ctx, 1), a --debug run, or
+ * PP_TOK_HOST / a data error send it through pp_pack_*; with several contexts the text is tokenised on ctxs[0]. */
 int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* const* sams, int n_sams,
                     const pp_polish_params* params, const char* debug_path, char** out_fasta,
                     uint64_t* out_len, int verbose /* 1: reference-style log on stderr */);
@@ -296,6 +298,10 @@ int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* const* sams, 
 int pp_polish_files_multi(pp_ctx* const* ctxs, int n_ctx, const char* assembly, const char* const* sams, int n_sams,
                           const pp_polish_params* params, const char* debug_path, char** out_fasta,
                           uint64_t* out_len, int verbose);
+/* `polypolish filter` (filter.rs:26-37).  With pp_set_parser(ctx, 0) (default) the SAM text stays on the device from parse to
+ * write (quick parse alignment.rs:102-149, QNAME/RNAME interning = the keys of filter.rs:110-145, pp_filter's kernels on the
+ * arrays in place, output text of filter.rs:296-349 assembled in HBM); anything unusual, and pp_set_parser(ctx, 1), use the host
+ * text code.  Same bytes and messages either way. */
 int pp_filter_files(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2,
                     const char* orientation, double low, double high, int verbose);
 void pp_free(void* p);
