@@ -20,12 +20,17 @@ bool read_file(const std::string& path, std::string& out) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) return false;
     std::string buf;
-    if (fseek(f, 0, SEEK_END) == 0) {
-        long sz = ftell(f);
-        if (sz > 0) buf.reserve((size_t)sz);
+    size_t have = 0;
+    if (fseek(f, 0, SEEK_END) == 0) {            // regular file: one read straight into the string
+        const long sz = ftell(f);
         fseek(f, 0, SEEK_SET);
+        if (sz > 0) {
+            buf.resize((size_t)sz);
+            have = fread(&buf[0], 1, (size_t)sz, f);
+            buf.resize(have);
+        }
     }
-    char tmp[1 << 16];
+    char tmp[1 << 16];                           // whatever is left (pipes, files that grew)
     size_t n;
     while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) buf.append(tmp, n);
     bool ok = !ferror(f);
@@ -200,11 +205,13 @@ extern "C" pp_fasta* pp_fasta_load(const char* path, char* err, size_t errcap) {
             return true;
         }
         if (!have_name) { bad_format = true; return false; }
-        size_t o = fa->bases.size();
-        fa->bases.append(text.data(), text.size());
-        for (size_t k = o; k < fa->bases.size(); ++k) {
-            char c = fa->bases[k];
-            if (c >= 'a' && c <= 'z') fa->bases[k] = (char)(c - 32);
+        const size_t o = fa->bases.size(), len = text.size();
+        fa->bases.resize(o + len);
+        char* dst = &fa->bases[o];
+        const char* src = text.data();
+        for (size_t k = 0; k < len; ++k) {           // ASCII upper-casing, branch-free so that it vectorises
+            const unsigned char c = (unsigned char)src[k];
+            dst[k] = (char)(c - (((unsigned)(c - 'a') < 26u) << 5));
         }
         return true;
     });
