@@ -32,6 +32,7 @@ WORKLOADS = {
     "50kbp_x100": (1, 50_000, 100.0),        # configs[0]
     "5Mbp_x1000": (1, 5_000_000, 1000.0),    # configs[3]
     "500kbp_x100": (1, 500_000, 100.0),
+    "6x5Mbp_x100": (6, 5_000_000, 100.0),    # one GPU's share of configs[4] (50 x 5 Mbp over 8 GPUs)
 }
 METRIC = "assembly Mbp polished/sec"
 
