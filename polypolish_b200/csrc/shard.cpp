@@ -12,8 +12,10 @@
 // Alignments whose RNAME is not in the assembly stay in shard 0 so that the reference's error (alignment.rs:298-300)
 // is still raised, once.
 #include <algorithm>
+#include <atomic>
 #include <numeric>
-#include <unordered_map>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "pp_internal.h"
@@ -63,60 +65,96 @@ extern "C" pp_shards* pp_shards_build(const pp_contigs* c, const pp_alignments* 
     }
     for (auto& sh : S->shards) sh.off.push_back(sh.bases.size());
 
-    auto copy_seq = [&](pp_shards::Shard& sh, uint32_t off_blk, uint32_t len) -> uint32_t {
-        const size_t blocks = ((size_t)len + PP_SEQ_BLOCK - 1) / PP_SEQ_BLOCK;
-        const uint32_t at = (uint32_t)sh.seq_blocks;
-        const size_t base = sh.seq_blocks * block_bytes;
-        sh.seq_pool.resize_zero(base + blocks * block_bytes);
-        if (blocks) memcpy(sh.seq_pool.p + base, a->seq_pool + (size_t)off_blk * block_bytes, blocks * block_bytes);
-        sh.seq_blocks += blocks;
-        return at;
+    // Every shard is built independently of the others (it only reads the inputs), so each gets its own thread: one pass over
+    // the read groups to size its arrays, one to fill them.
+    auto shard_of_rec = [&](uint64_t i) -> uint32_t {
+        const uint32_t ci = a->contig[i];
+        return (ci == PP_CONTIG_UNKNOWN || ci >= nc) ? 0u : shard_of[ci];
     };
-    std::vector<uint8_t> touched(n_shards);
-    std::vector<std::unordered_map<uint32_t, uint32_t>> seq_at(n_shards);     // per group: original seq_off -> shard seq_off
-    uint64_t g0 = 0;
-    while (g0 < a->n_aln) {
-        uint64_t g1 = g0 + 1;
-        while (g1 < a->n_aln && a->read_id[g1] == a->read_id[g0]) g1++;
-        std::fill(touched.begin(), touched.end(), 0);
-        for (uint64_t i = g0; i < g1; ++i) {
-            const uint32_t ci = a->contig[i];
-            touched[(ci == PP_CONTIG_UNKNOWN || ci >= nc) ? 0 : shard_of[ci]] = 1;
-        }
-        for (uint32_t s = 0; s < n_shards; ++s) {
-            if (!touched[s]) continue;
-            auto& sh = S->shards[s];
-            seq_at[s].clear();
-            const uint32_t rid = (uint32_t)sh.n_reads++;
-            for (uint64_t i = g0; i < g1; ++i) {
-                const uint32_t ci = a->contig[i];
-                const bool unknown = (ci == PP_CONTIG_UNKNOWN || ci >= nc);
-                const bool home = (unknown ? 0u : shard_of[ci]) == s;
-                uint8_t fl = a->flags[i];
-                uint32_t soff = 0;
-                if (home) {
-                    sh.n_home++;
-                    if (!(fl & PP_FLAG_NOSEQ)) {
-                        auto it = seq_at[s].find(a->seq_off[i]);
-                        if (it != seq_at[s].end() && (fl & PP_FLAG_SEQSTAR)) soff = it->second;
-                        else { soff = copy_seq(sh, a->seq_off[i], a->seq_len[i]); seq_at[s].emplace(a->seq_off[i], soff); }
-                    }
-                } else {
-                    fl |= PP_FLAG_GHOST;
+    auto build_one = [&](uint32_t s) {
+        auto& sh = S->shards[s];
+        uint64_t n_rec = 0, n_ops = 0, n_blk = 0;
+        for (uint64_t g0 = 0; g0 < a->n_aln;) {
+            uint64_t g1 = g0 + 1;
+            while (g1 < a->n_aln && a->read_id[g1] == a->read_id[g0]) g1++;
+            bool touched = false;
+            for (uint64_t i = g0; i < g1 && !touched; ++i) touched = shard_of_rec(i) == s;
+            if (touched) {
+                n_rec += g1 - g0;
+                for (uint64_t i = g0; i < g1; ++i) {
+                    n_ops += a->n_cigar[i];
+                    if (shard_of_rec(i) == s && !(a->flags[i] & PP_FLAG_NOSEQ)) n_blk += ((size_t)a->seq_len[i] + PP_SEQ_BLOCK - 1) / PP_SEQ_BLOCK;
                 }
-                sh.contig.push_back(home ? (unknown ? PP_CONTIG_UNKNOWN : local_of[ci]) : 0u);
-                sh.ref_start.push_back(a->ref_start[i]);
-                sh.read_id.push_back(rid);
-                sh.seq_off.push_back(soff);
-                sh.seq_len.push_back(a->seq_len[i]);
-                sh.cigar_off.push_back((uint32_t)sh.cigar_ops.size());
-                sh.n_cigar.push_back(a->n_cigar[i]);
-                sh.nm.push_back(a->nm[i]);
-                sh.flags.push_back(fl);
-                sh.cigar_ops.insert(sh.cigar_ops.end(), a->cigar_ops + a->cigar_off[i], a->cigar_ops + a->cigar_off[i] + a->n_cigar[i]);
             }
+            g0 = g1;
         }
-        g0 = g1;
+        sh.contig.reserve(n_rec); sh.ref_start.reserve(n_rec); sh.read_id.reserve(n_rec); sh.seq_off.reserve(n_rec);
+        sh.seq_len.reserve(n_rec); sh.cigar_off.reserve(n_rec); sh.n_cigar.reserve(n_rec); sh.nm.reserve(n_rec); sh.flags.reserve(n_rec);
+        sh.cigar_ops.reserve(n_ops);
+        sh.seq_pool.reserve(n_blk * block_bytes + 64);        // an upper bound: SEQ="*" records share their group's copy
+        auto copy_seq = [&](uint32_t off_blk, uint32_t len) -> uint32_t {
+            const size_t blocks = ((size_t)len + PP_SEQ_BLOCK - 1) / PP_SEQ_BLOCK;
+            const uint32_t at = (uint32_t)sh.seq_blocks;
+            const size_t base = sh.seq_blocks * block_bytes;
+            sh.seq_pool.resize_zero(base + blocks * block_bytes);
+            if (blocks) memcpy(sh.seq_pool.p + base, a->seq_pool + (size_t)off_blk * block_bytes, blocks * block_bytes);
+            sh.seq_blocks += blocks;
+            return at;
+        };
+        std::vector<std::pair<uint32_t, uint32_t>> seq_at;      // of the current group: original seq_off -> shard seq_off
+        for (uint64_t g0 = 0; g0 < a->n_aln;) {
+            uint64_t g1 = g0 + 1;
+            while (g1 < a->n_aln && a->read_id[g1] == a->read_id[g0]) g1++;
+            bool touched = false;
+            for (uint64_t i = g0; i < g1 && !touched; ++i) touched = shard_of_rec(i) == s;
+            if (touched) {
+                seq_at.clear();
+                const uint32_t rid = (uint32_t)sh.n_reads++;
+                for (uint64_t i = g0; i < g1; ++i) {
+                    const uint32_t ci = a->contig[i];
+                    const bool unknown = (ci == PP_CONTIG_UNKNOWN || ci >= nc);
+                    const bool home = shard_of_rec(i) == s;
+                    uint8_t fl = a->flags[i];
+                    uint32_t soff = 0;
+                    if (home) {
+                        sh.n_home++;
+                        if (!(fl & PP_FLAG_NOSEQ)) {
+                            const uint32_t key = a->seq_off[i];
+                            const std::pair<uint32_t, uint32_t>* hit = nullptr;
+                            for (const auto& kv : seq_at) if (kv.first == key) { hit = &kv; break; }
+                            if (hit && (fl & PP_FLAG_SEQSTAR)) soff = hit->second;
+                            else {
+                                soff = copy_seq(key, a->seq_len[i]);
+                                if (!hit) seq_at.emplace_back(key, soff);
+                            }
+                        }
+                    } else {
+                        fl |= PP_FLAG_GHOST;
+                    }
+                    sh.contig.push_back(home ? (unknown ? PP_CONTIG_UNKNOWN : local_of[ci]) : 0u);
+                    sh.ref_start.push_back(a->ref_start[i]);
+                    sh.read_id.push_back(rid);
+                    sh.seq_off.push_back(soff);
+                    sh.seq_len.push_back(a->seq_len[i]);
+                    sh.cigar_off.push_back((uint32_t)sh.cigar_ops.size());
+                    sh.n_cigar.push_back(a->n_cigar[i]);
+                    sh.nm.push_back(a->nm[i]);
+                    sh.flags.push_back(fl);
+                    sh.cigar_ops.insert(sh.cigar_ops.end(), a->cigar_ops + a->cigar_off[i], a->cigar_ops + a->cigar_off[i] + a->n_cigar[i]);
+                }
+            }
+            g0 = g1;
+        }
+    };
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n_threads = std::min<unsigned>(n_shards, hw);
+        std::atomic<uint32_t> next{0};
+        auto worker = [&]() { for (uint32_t s; (s = next.fetch_add(1)) < n_shards;) build_one(s); };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < n_threads; ++t) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
     }
     return S;
 }
