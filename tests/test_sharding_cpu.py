@@ -115,3 +115,85 @@ def test_world_size_2_gloo(tmp_path):
                         "--master-port", "29517", str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "OK" in r.stdout
+
+
+def model_shards(f, full, n_shards, seq_bits):
+    """Python restatement of the sharding rule (shard.cpp header): LPT bin packing of whole contigs on contig length + aligned bases,
+    every read group copied - in SAM order - to each shard one of its records lands on, foreign records as ghosts, one copy of
+    a sequence per (shard, group)."""
+    nc = f.view.n_contigs
+    blk = 16 if seq_bits == 4 else 32
+    weight = [int(f.off[i + 1] - f.off[i]) for i in range(nc)]
+    for c, L in zip(full["contig"].tolist(), full["seq_len"].tolist()):
+        if c != 0xFFFFFFFF and c < nc:
+            weight[c] += L
+    order = sorted(range(nc), key=lambda i: -weight[i])              # stable, like std::stable_sort
+    load, shard_of = [0] * n_shards, [0] * nc
+    for ci in order:
+        b = min(range(n_shards), key=lambda s: load[s])
+        shard_of[ci] = b
+        load[b] += weight[ci]
+    cmap = [[c for c in range(nc) if shard_of[c] == s] for s in range(n_shards)]
+    local = {c: cmap[shard_of[c]].index(c) for c in range(nc)}
+    out = [dict(contig=[], ref_start=[], read_id=[], seq_off=[], seq_len=[], cigar_off=[], n_cigar=[], nm=[], flags=[], cigar_ops=[],
+                pool=bytearray(), n_reads=0) for _ in range(n_shards)]
+    n = len(full["contig"])
+    rid = full["read_id"]
+    g0 = 0
+    while g0 < n:
+        g1 = g0 + 1
+        while g1 < n and rid[g1] == rid[g0]:
+            g1 += 1
+        sh_of = [0 if (full["contig"][i] == 0xFFFFFFFF or full["contig"][i] >= nc) else shard_of[int(full["contig"][i])] for i in range(g0, g1)]
+        for s in sorted(set(sh_of)):
+            o = out[s]
+            r = o["n_reads"]
+            o["n_reads"] += 1
+            seen = {}
+            for i, so in zip(range(g0, g1), sh_of):
+                fl = int(full["flags"][i])
+                c = int(full["contig"][i])
+                home = so == s
+                soff = 0
+                if home:
+                    if not fl & 0x10:                                   # PP_FLAG_NOSEQ
+                        key = int(full["seq_off"][i])
+                        if key in seen and fl & 0x04:                    # PP_FLAG_SEQSTAR shares the group's copy
+                            soff = seen[key]
+                        else:
+                            nb = (int(full["seq_len"][i]) + 31) // 32
+                            soff = len(o["pool"]) // blk
+                            o["pool"] += bytes(full["seq_pool"][key * blk:(key + nb) * blk])
+                            seen.setdefault(key, soff)
+                else:
+                    fl |= GHOST
+                unknown = c == 0xFFFFFFFF or c >= nc
+                o["contig"].append((0xFFFFFFFF if unknown else local[c]) if home else 0)
+                o["ref_start"].append(int(full["ref_start"][i])); o["read_id"].append(r); o["seq_off"].append(soff)
+                o["seq_len"].append(int(full["seq_len"][i])); o["cigar_off"].append(len(o["cigar_ops"])); o["n_cigar"].append(int(full["n_cigar"][i]))
+                o["nm"].append(int(full["nm"][i])); o["flags"].append(fl)
+                co = int(full["cigar_off"][i])
+                o["cigar_ops"] += full["cigar_ops"][co:co + int(full["n_cigar"][i])].tolist()
+        g0 = g1
+    return cmap, out
+
+
+@pytest.mark.parametrize("seed,n_shards", [(11, 2), (12, 3), (13, 4), (14, 7)])
+def test_shards_equal_python_model(tmp_path, seed, n_shards):
+    """Every array of every shard, against the restated rule (the sharder builds the shards on parallel threads)."""
+    case = fuzzgen.make_case(seed, n_contigs=4, multimap=0.6, exotic=0.5 if seed == 14 else 0.0)
+    fa, sams = case.write(tmp_path)
+    f = pp.load_fasta(fa)
+    p = pp.pack_sams(f, sams)
+    full = p.arrays()
+    cmap_m, out_m = model_shards(f, full, n_shards, int(full["seq_bits"]))
+    sh = api.Shards(f.view, p.view, n_shards)
+    for s in range(n_shards):
+        c, a, cmap, n_home = sh.get(s)
+        arr = api.view_arrays(a)
+        m = out_m[s]
+        assert cmap == cmap_m[s]
+        for k in ("contig", "ref_start", "read_id", "seq_off", "seq_len", "cigar_off", "n_cigar", "nm", "flags", "cigar_ops"):
+            assert arr[k].tolist() == m[k], (s, k)
+        assert bytes(arr["seq_pool"]) == bytes(m["pool"])
+        assert arr["n_reads"] == m["n_reads"]
