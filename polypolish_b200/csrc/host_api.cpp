@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <memory>
 #include <string>
 #include <thread>
 #include <utility>
@@ -159,20 +160,22 @@ static void run_shard(ShardJob* j, const pp_polish_params* prm) {
     if (j->rc != PP_OK) j->err = pp_last_error(j->ctx);
 }
 
-// The resident dataset of a context copied back into host vectors (pp_dataset_download).
+// The resident dataset of a context copied back into host arrays (pp_dataset_download).  Plain new[] without value
+// initialisation: the copy overwrites every byte, so zero-filling 0.4 GB first would only cost time.
 struct HostCopy {
-    std::vector<uint32_t> contig, ref_start, read_id, seq_off, cigar_off, nm, cigar_ops;
-    std::vector<uint16_t> seq_len, n_cigar;
-    std::vector<uint8_t> flags, seq_pool;
+    std::unique_ptr<uint32_t[]> contig, ref_start, read_id, seq_off, cigar_off, nm, cigar_ops;
+    std::unique_ptr<uint16_t[]> seq_len, n_cigar;
+    std::unique_ptr<uint8_t[]> flags, seq_pool;
     int fetch(pp_ctx* ctx, pp_alignments* v) {
         int rc = pp_dataset_sizes(ctx, v);
         if (rc != PP_OK) return rc;
-        const size_t n = (size_t)v->n_aln;
-        contig.resize(n); ref_start.resize(n); read_id.resize(n); seq_off.resize(n); cigar_off.resize(n); nm.resize(n);
-        seq_len.resize(n); n_cigar.resize(n); flags.resize(n); cigar_ops.resize((size_t)v->n_cigar_ops); seq_pool.resize((size_t)v->seq_pool_bytes + 64);
-        v->contig = contig.data(); v->ref_start = ref_start.data(); v->read_id = read_id.data(); v->seq_off = seq_off.data();
-        v->cigar_off = cigar_off.data(); v->nm = nm.data(); v->seq_len = seq_len.data(); v->n_cigar = n_cigar.data(); v->flags = flags.data();
-        v->cigar_ops = cigar_ops.data(); v->seq_pool = seq_pool.data();
+        const size_t n = (size_t)v->n_aln + 1;
+        contig.reset(new uint32_t[n]); ref_start.reset(new uint32_t[n]); read_id.reset(new uint32_t[n]); seq_off.reset(new uint32_t[n]);
+        cigar_off.reset(new uint32_t[n]); nm.reset(new uint32_t[n]); seq_len.reset(new uint16_t[n]); n_cigar.reset(new uint16_t[n]);
+        flags.reset(new uint8_t[n]); cigar_ops.reset(new uint32_t[(size_t)v->n_cigar_ops + 1]); seq_pool.reset(new uint8_t[(size_t)v->seq_pool_bytes + 64]);
+        v->contig = contig.get(); v->ref_start = ref_start.get(); v->read_id = read_id.get(); v->seq_off = seq_off.get();
+        v->cigar_off = cigar_off.get(); v->nm = nm.get(); v->seq_len = seq_len.get(); v->n_cigar = n_cigar.get(); v->flags = flags.get();
+        v->cigar_ops = cigar_ops.get(); v->seq_pool = seq_pool.get();
         return pp_dataset_download(ctx, v);
     }
 };
