@@ -255,6 +255,7 @@ typedef struct {
   float h2d_ms;                        /* wall time of getting the text into HBM (file read + pinned staging + PCIe) */
   float device_ms;                     /* CUDA-event time of the tokeniser kernels */
   uint32_t launches;
+  uint64_t h2d_bytes;                  /* bytes that crossed PCIe for this file (less than its size when QUAL was dropped) */
 } pp_tok_stats;
 int pp_tok_begin(pp_ctx* ctx, const pp_fasta* assembly, int careful, int seq_bits /* 4 | 8 */);
 int pp_tok_add_text(pp_ctx* ctx, const char* text, size_t len, pp_tok_stats* stats /* may be NULL */);
@@ -273,6 +274,11 @@ int pp_set_parser(pp_ctx* ctx, int mode);
 int pp_get_parser(const pp_ctx* ctx);
 /* Host threads pp_tok_add_file uses to stream a file into HBM (pread -> pinned slot -> PCIe); 0 = a quarter of the cores, 2..16. */
 int pp_tok_set_readers(pp_ctx* ctx, int n);
+/* pp_tok_add_file(s) / pp_tok_prefetch stage the text with QUAL (column 11: 45 % of a bwa-mem line, never read by polish,
+ * alignment.rs:49-98) replaced by "*", so that less crosses PCIe; 0 switches that off (default 1).  `filter`, which reproduces
+ * its input lines, always uploads byte for byte.  The line count reported in pp_tok_stats then includes one comment line per
+ * upload slice. */
+int pp_tok_set_strip_qual(pp_ctx* ctx, int on);
 /* The resident dataset read back (tests: equality with the host packer's arrays).  pp_dataset_sizes fills the counts of
  * `out`; pp_dataset_download copies into the caller's arrays (same counts; NULL pointers are skipped). */
 int pp_dataset_sizes(pp_ctx* ctx, pp_alignments* out);

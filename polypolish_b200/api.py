@@ -76,7 +76,7 @@ class FilterResult(C.Structure):
 
 class TokStats(C.Structure):
     _fields_ = [("lines", C.c_uint64), ("alignments", C.c_uint64), ("reads", C.c_uint64), ("h2d_ms", C.c_float),
-                ("device_ms", C.c_float), ("launches", C.c_uint32)]
+                ("device_ms", C.c_float), ("launches", C.c_uint32), ("h2d_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -144,6 +144,7 @@ def lib():
     L.pp_set_parser.argtypes = [C.c_void_p, C.c_int]
     L.pp_get_parser.argtypes = [C.c_void_p]
     L.pp_tok_set_readers.argtypes = [C.c_void_p, C.c_int]
+    L.pp_tok_set_strip_qual.argtypes = [C.c_void_p, C.c_int]
     L.pp_dataset_sizes.argtypes = [C.c_void_p, C.POINTER(Alignments)]
     L.pp_dataset_download.argtypes = [C.c_void_p, C.POINTER(Alignments)]
     if hasattr(L, "pp_filter"):
@@ -442,6 +443,10 @@ class Context:
     def set_readers(self, n):
         """Host threads streaming a SAM file into HBM (0 = automatic)."""
         lib().pp_tok_set_readers(self.h, int(n))
+
+    def set_strip_qual(self, on):
+        """Whether SAM files are uploaded without their QUAL column (default on; polish never reads it)."""
+        lib().pp_tok_set_strip_qual(self.h, int(bool(on)))
 
     def set_parser(self, mode):
         """0: pp_polish_files parses SAM on the device (default); 1: on the host."""

@@ -40,6 +40,7 @@
 #include "pp_ctx.cuh"
 #include "tok_line.h"
 #include "tok_table.h"
+#include "tok_strip.h"
 
 namespace {
 
@@ -48,6 +49,7 @@ constexpr int TK_THREADS = 256;
 constexpr int TK_LINE_THREADS = 128;  // threads (= lines) per CTA in the per-line passes
 constexpr int TK_READERS = 16;        // at most this many host threads stream a file into the device
 constexpr size_t TK_SLOT = 4u << 20;  // pinned bytes per slot (two slots per reader)
+constexpr size_t TK_LOOK = 1u << 20;  // QUAL-stripping upload: how far past its nominal slice a reader looks for the line end
 
 struct TokStatus {
     unsigned long long first_bad;     // smallest line index the device does not accept (~0 = none)
@@ -242,7 +244,11 @@ struct TokState {
         int rc = PP_OK;                   // PP_OK, PP_ERR_IO, PP_ERR_CUDA
         int cuda_err = 0;
         float ms = 0;
+        bool strip = false;               // uploaded with QUAL replaced by "*" (polish only: filter reproduces lines verbatim)
+        uint64_t sent = 0;                // bytes that crossed PCIe
     } pf;
+    bool strip_qual = true;               // pp_tok_set_strip_qual
+    uint8_t* h_nl = nullptr;              // pinned '\n'
     DevBuf cub;
     TokFilterBufs* fbufs = nullptr;   // device buffers of the filter text path
 };
@@ -263,6 +269,7 @@ void pp_tok_release(pp_ctx* ctx) {
         if (T->rstream[r]) cudaStreamDestroy(T->rstream[r]);
     }
     if (T->h_st) cudaFreeHost(T->h_st);
+    if (T->h_nl) cudaFreeHost(T->h_nl);
     if (T->h_tot) cudaFreeHost(T->h_tot);
     if (T->d_st) cudaFree(T->d_st);
     T->cub.release();
@@ -277,6 +284,8 @@ static int tok_state(pp_ctx* ctx, TokState** out) {
         CK(cudaHostAlloc((void**)&T->h_st, sizeof(TokStatus), cudaHostAllocDefault));
         CK(cudaHostAlloc((void**)&T->h_tot, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
         CK(cudaMalloc((void**)&T->d_st, sizeof(TokStatus)));
+        CK(cudaHostAlloc((void**)&T->h_nl, 64, cudaHostAllocDefault));
+        T->h_nl[0] = '\n';
     }
     *out = ctx->tok;
     return PP_OK;
@@ -482,7 +491,7 @@ extern "C" int pp_tok_add_text(pp_ctx* ctx, const char* text, size_t len, pp_tok
     CK(cudaStreamSynchronize(ctx->stream));
     const float h2d = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     rc = tok_process(ctx, T, tb.as<uint8_t>(), len, len > 0 && text[len - 1] != '\n', stats);
-    if (stats) stats->h2d_ms = h2d;
+    if (stats) { stats->h2d_ms = h2d; stats->h2d_bytes = len; }
     if (rc != PP_OK) T->active = false;
     return rc;
 }
@@ -527,6 +536,78 @@ static int upload_file(int device, TokState* T, uint8_t* dst, int fd, uint64_t n
     return err == 1 ? PP_ERR_IO : err == 2 ? PP_ERR_CUDA : PP_OK;
 }
 
+constexpr int PP_UPLOAD_LONG_LINE = 100;   // internal: a line longer than TK_LOOK, upload the file verbatim instead
+
+// The same for `polish`, with less on the wire: every reader owns the LINES that start in its nominal slice, replaces their
+// QUAL by "*" while staging them (tok_strip.h: 45 % of a bwa-mem line, never read on this path) and sends the shorter text
+// to the lines' original offset; the freed tail of the slice becomes one '@' comment line on the device ('@', blanks
+// written by a memset, '\n'), which every parser of this path skips (alignment.rs:241-242).  Offsets, and therefore the
+// independence of the readers, stay as they are.  A file whose last line is unterminated keeps its last slice verbatim.
+static int upload_file_stripped(int device, TokState* T, uint8_t* dst, int fd, uint64_t n, uint8_t* last_byte, int* cuda_err, uint64_t* sent) {
+    const int R = T->readers;
+    const uint64_t S = TK_SLOT - TK_LOOK;
+    const uint64_t n_slices = (n + S - 1) / S;
+    std::atomic<int> err{0}, cerr{0};              // 1 read error, 2 CUDA error, 3 long line
+    std::atomic<unsigned long long> bytes{0};
+    auto work = [&](int r) {
+        if (cudaSetDevice(device) != cudaSuccess) { err = 2; return; }
+        std::vector<uint8_t> rawbuf(TK_SLOT + 16);
+        uint8_t* raw = rawbuf.data();
+        uint64_t j = 0;
+        for (uint64_t k = (uint64_t)r; k < n_slices && !err; k += (uint64_t)R) {
+            const uint64_t o = k * S, e = std::min<uint64_t>(n, o + S);
+            const uint64_t rd0 = k ? o - 1 : 0, rd1 = std::min<uint64_t>(n, e + TK_LOOK - 1);
+            uint64_t got = 0;
+            while (got < rd1 - rd0) {
+                const ssize_t g = pread(fd, raw + got, (size_t)(rd1 - rd0 - got), (off_t)(rd0 + got));
+                if (g <= 0) { err = 1; return; }
+                got += (uint64_t)g;
+            }
+            // the slot is needed before the lines are staged into it
+            const int slot = (int)(j & 1);
+            if (j >= 2) {
+                cudaError_t ce = cudaEventSynchronize(T->rev[r][slot]);
+                if (ce != cudaSuccess) { cerr = (int)ce; err = 2; return; }
+            }
+            uint8_t* pin = T->pin[r][slot];
+            const tok::SliceOut so = tok::strip_slice(raw, rd0, rd1, k, e, n, pin);
+            if (so.status == 3) { err = 3; return; }
+            if (so.status == 1) continue;                          // one long line covers the whole slice: an earlier slice owns it
+            ++j;
+            if (so.ends_file) *last_byte = so.last;
+            const uint64_t a = so.a, b = so.b, c = so.c, gap = (b - a) - c;
+            cudaError_t ce = cudaSuccess;
+            if (gap == 0) {
+                ce = cudaMemcpyAsync(dst + a, pin, (size_t)c, cudaMemcpyHostToDevice, T->rstream[r]);
+            } else if (gap == 1) {
+                pin[c] = '\n';                                      // an empty line
+                ce = cudaMemcpyAsync(dst + a, pin, (size_t)c + 1, cudaMemcpyHostToDevice, T->rstream[r]);
+            } else {
+                pin[c] = '@';                                       // a comment line of gap bytes
+                ce = cudaMemcpyAsync(dst + a, pin, (size_t)c + 1, cudaMemcpyHostToDevice, T->rstream[r]);
+                if (ce == cudaSuccess && gap > 2) ce = cudaMemsetAsync(dst + a + c + 1, ' ', (size_t)(gap - 2), T->rstream[r]);
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(dst + b - 1, T->h_nl, 1, cudaMemcpyHostToDevice, T->rstream[r]);
+            }
+            if (ce == cudaSuccess) ce = cudaEventRecord(T->rev[r][slot], T->rstream[r]);
+            if (ce != cudaSuccess) { cerr = (int)ce; err = 2; return; }
+            bytes += c + (gap ? 2 : 0);
+        }
+        cudaError_t ce = cudaStreamSynchronize(T->rstream[r]);
+        if (ce != cudaSuccess) { cerr = (int)ce; err = 2; }
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < R; ++r) th.emplace_back(work, r);
+    work(0);
+    for (auto& t : th) t.join();
+    *cuda_err = cerr.load();
+    *sent = bytes.load();
+    if (err == 3) {                                   // let the copies that were issued finish before the verbatim upload reuses the slots
+        for (int r = 0; r < R; ++r) cudaStreamSynchronize(T->rstream[r]);
+        return PP_UPLOAD_LONG_LINE;
+    }
+    return err == 1 ? PP_ERR_IO : err == 2 ? PP_ERR_CUDA : PP_OK;
+}
+
 static int ring_ready(pp_ctx* ctx, TokState* T) {
     if (T->readers <= 0) {
         const unsigned hw = std::thread::hardware_concurrency();
@@ -545,7 +626,7 @@ static int ring_ready(pp_ctx* ctx, TokState* T) {
 
 // Starts streaming `path` into the next text buffer on a background thread.  PP_OK, PP_TOK_HOST (not a plain readable
 // file) or an error.
-static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path) {
+static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path, bool strip) {
     const int fd = open(path, O_RDONLY);
     struct stat sb;
     if (fd < 0 || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
@@ -571,12 +652,17 @@ static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path) {
     T->next_buf ^= 1;
     TokState::Prefetch& pf = T->pf;
     pf.active = true; pf.path = path; pf.buf = buf; pf.n = n; pf.last = '\n'; pf.rc = PP_OK; pf.cuda_err = 0; pf.ms = 0;
+    pf.strip = strip && T->strip_qual; pf.sent = 0;
     uint8_t* dst = T->text[buf].as<uint8_t>();
     const int device = ctx->device;
     pf.th = std::thread([T, dst, fd, n, device] {
         TokState::Prefetch& q = T->pf;
         const auto t0 = std::chrono::steady_clock::now();
-        if (n) q.rc = upload_file(device, T, dst, fd, n, &q.last, &q.cuda_err);
+        if (n && q.strip) {
+            q.rc = upload_file_stripped(device, T, dst, fd, n, &q.last, &q.cuda_err, &q.sent);
+            if (q.rc == PP_UPLOAD_LONG_LINE) q.strip = false;
+        }
+        if (n && !q.strip) { q.rc = upload_file(device, T, dst, fd, n, &q.last, &q.cuda_err); q.sent = n; }
         close(fd);
         q.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     });
@@ -584,14 +670,14 @@ static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path) {
 }
 
 // Waits for the text of `path` (starting its upload now if nobody asked for it before).
-static int prefetch_wait(pp_ctx* ctx, TokState* T, const char* path) {
+static int prefetch_wait(pp_ctx* ctx, TokState* T, const char* path, bool strip) {
     TokState::Prefetch& pf = T->pf;
-    if (pf.active && pf.path != path) {                       // something else was prefetched: let it finish, drop it
+    if (pf.active && (pf.path != path || (pf.strip && !strip))) {   // (text without QUAL is no use to `filter`)                       // something else was prefetched: let it finish, drop it
         if (pf.th.joinable()) pf.th.join();
         pf.active = false;
     }
     if (!pf.active) {
-        const int rc = prefetch_start(ctx, T, path);
+        const int rc = prefetch_start(ctx, T, path, strip);
         if (rc != PP_OK) return rc;
     }
     if (pf.th.joinable()) pf.th.join();
@@ -608,7 +694,7 @@ extern "C" int pp_tok_prefetch(pp_ctx* ctx, const char* path) {
     int rc = tok_state(ctx, &T);
     if (rc) return rc;
     if (T->pf.active) return PP_OK;                            // one outstanding upload at a time
-    rc = prefetch_start(ctx, T, path);
+    rc = prefetch_start(ctx, T, path, true);
     return rc == PP_TOK_HOST ? PP_OK : rc;                     // pp_tok_add_file(s) will say so
 }
 
@@ -630,18 +716,19 @@ extern "C" int pp_tok_add_files(pp_ctx* ctx, const char* const* paths, int n_pat
     if (stats) memset(stats, 0, sizeof(pp_tok_stats) * (size_t)n_paths);
     for (int i = 0; i < n_paths; ++i) {
         if (!paths[i]) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: null path");
-        int rc = prefetch_wait(ctx, T, paths[i]);
+        int rc = prefetch_wait(ctx, T, paths[i], true);
         if (rc != PP_OK) { T->active = false; return rc; }
         const int buf = T->pf.buf;
         const uint64_t n = T->pf.n;
         const bool unterminated = n > 0 && T->pf.last != '\n';
         const float h2d = T->pf.ms;
+        const uint64_t h2d_bytes = T->pf.sent;
         if (i + 1 < n_paths && paths[i + 1]) {                 // the next file streams in while this one is tokenised
-            rc = prefetch_start(ctx, T, paths[i + 1]);
+            rc = prefetch_start(ctx, T, paths[i + 1], true);
             if (rc < 0) { T->active = false; return rc; }
         }
         rc = tok_process(ctx, T, T->text[buf].as<uint8_t>(), n, unterminated, stats ? stats + i : nullptr);
-        if (stats) stats[i].h2d_ms = h2d;
+        if (stats) { stats[i].h2d_ms = h2d; stats[i].h2d_bytes = h2d_bytes; }
         if (rc != PP_OK) { T->active = false; return rc; }
     }
     return PP_OK;
@@ -665,6 +752,16 @@ extern "C" int pp_tok_set_readers(pp_ctx* ctx, int n) {
     int rc = tok_state(ctx, &T);
     if (rc) return rc;
     T->readers = n;
+    return PP_OK;
+}
+
+// 1 (default): pp_tok_add_file(s) / pp_tok_prefetch send the text without its QUAL column; 0: byte for byte.
+extern "C" int pp_tok_set_strip_qual(pp_ctx* ctx, int on) {
+    if (!ctx) return PP_ERR_ARG;
+    TokState* T = nullptr;
+    int rc = tok_state(ctx, &T);
+    if (rc) return rc;
+    T->strip_qual = on != 0;
     return PP_OK;
 }
 
@@ -990,9 +1087,9 @@ int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const 
     FileDev fd[2];
     uint32_t launches = 0;
     float h2d_ms = 0;
-    if (T->pf.active && T->pf.path != in1) { if (T->pf.th.joinable()) T->pf.th.join(); T->pf.active = false; }
+    if (T->pf.active && (T->pf.path != in1 || T->pf.strip)) { if (T->pf.th.joinable()) T->pf.th.join(); T->pf.active = false; }
     for (int k = 0; k < 2; ++k) {
-        rc = prefetch_wait(ctx, T, ins[k]);
+        rc = prefetch_wait(ctx, T, ins[k], false);
         if (rc != PP_OK) return rc;
         const int buf = T->pf.buf;
         const uint64_t n = T->pf.n;
@@ -1000,7 +1097,7 @@ int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const 
         h2d_ms += T->pf.ms;
         fs->text_bytes[k] = n;
         if (k == 0) {
-            rc = prefetch_start(ctx, T, ins[1]);
+            rc = prefetch_start(ctx, T, ins[1], false);
             if (rc != PP_OK) return rc;
         }
         rc = ftok_lines(ctx, T, k, T->text[buf].as<uint8_t>(), n, unterminated, B.lines[k], B.tmp[k], d_st, &fd[k], &launches);

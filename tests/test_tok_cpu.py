@@ -343,3 +343,126 @@ def test_ftok_quick_parse_matches_model(H):
     text = b"".join(("\t".join([nm, "0", "c1", "1", "60", "4M", "*", "0", "0", "ACGT", "IIII"]) + "\n").encode() for nm in ["a", "b", "a", "ab", ""])
     nh = ftok_cpu(H, text)[7]
     assert nh[0] == nh[2] and len({int(nh[0]), int(nh[1]), int(nh[3]), int(nh[4])}) == 4
+
+
+# ---- upload-side QUAL stripping (tok_strip.h): the tokenised arrays must not notice -------------------------------------
+def strip_cpu(H, text):
+    out = C.create_string_buffer(len(text) + 1)
+    H.strip_cpu.restype = C.c_uint64
+    n = H.strip_cpu(C.c_char_p(text), C.c_uint64(len(text)), out)
+    return out.raw[:n]
+
+
+def test_strip_qual_keeps_everything_but_qual(H):
+    rows = [line("a", qual="IIII"), line("b", qual="*"), line("c", qual=""), line("d", qual="I"), "@HD\tVN:1.6\n", "\n", "x\ty\n",
+            line("e", qual="II", tags=()), line("f", qual="IIIIII", tags=()).replace("\n", "\r\n"), line("g", qual="!!!!", tags=("NM:i:1", "XX:Z:q\x08")),
+            line("last", qual="ABCDEFG", tags=())[:-1]]
+    text = "".join(rows).encode("latin-1")
+    got = strip_cpu(H, text)
+    want = []
+    for r in rows:
+        eol = "\r\n" if r.endswith("\r\n") else ("\n" if r.endswith("\n") else "")
+        body = r[:len(r) - len(eol)]
+        f = body.split("\t")
+        if not body.startswith("@") and len(f) >= 11 and len(f[10]) >= 2:
+            f[10] = "*"
+            body = "\t".join(f)
+        want.append(body + eol)
+    assert got == "".join(want).encode("latin-1")
+    assert len(got) <= len(text) and got.count(b"\n") == text.count(b"\n")
+
+
+@pytest.mark.parametrize("seed", range(90, 102))
+def test_stripped_text_tokenises_to_the_same_arrays(H, tmp_path, seed):
+    case = fuzzgen.make_case(seed, exotic=0.5 if seed % 5 == 0 else 0.0, multimap=0.4)
+    texts = [t.encode("latin-1") for t in case.sam_texts]
+    if seed % 3 == 0:
+        texts = [t.replace(b"\n", b"\r\n") for t in texts]
+    if seed % 4 == 0:
+        texts = [t[:-1] if t.endswith(b"\n") and not t.endswith(b"\r\n") else t for t in texts]
+    careful = case.opts["careful"]
+    f, p = host_pack(tmp_path, case.fasta_text, texts, careful)
+    host = p.arrays()
+    stripped = [strip_cpu(H, t) for t in texts]
+    assert sum(map(len, stripped)) < 0.8 * sum(map(len, texts))
+    rc, dev, _ = tok_cpu(H, f.names, stripped, careful, int(host["seq_bits"]))
+    assert rc == PP_OK
+    assert_same(dev, host)
+
+
+def test_stripped_mutated_texts_agree_with_the_host_packer(H, tmp_path):
+    """The stripping never turns a text the host packer rejects into one the tokeniser accepts, nor changes the arrays."""
+    rng = random.Random(17)
+    base = [line(f"q{i // 2}", rng.choice([0, 16, 4, 256, 272] if i % 2 else [0, 16]), rng.choice(["c1", "c2", "c10", "zz"]), rng.randint(0, 30),
+                 rng.choice(["4M", "2M1I1M", "1M1D3M", "2S2M", "4="]), rng.choice(["ACGT", "*", "acgn"] if i % 2 else ["ACGT", "acgn"]),
+                 (f"NM:i:{rng.randint(0, 12)}",) + (("ZP:Z:fail",) if rng.random() < 0.1 else ())) for i in range(30)]
+    alphabet = "\t\t\t\t0123456789MIDS=X*ACGTN:@+-\r zpZP\x08\n"
+    n_ok = 0
+    for trial in range(400):
+        lines = list(base)
+        for _ in range(rng.randint(1, 3)):
+            j = rng.randrange(len(lines))
+            s = list(lines[j])
+            k = rng.randrange(len(s) - 1)
+            op = rng.random()
+            if op < 0.4:
+                s[k] = rng.choice(alphabet)
+            elif op < 0.7:
+                del s[k]
+            else:
+                s.insert(k, rng.choice(alphabet))
+            lines[j] = "".join(s)
+        t = "".join(lines).encode("latin-1")
+        try:
+            f, p = host_pack(tmp_path, FA, [t])
+            host = p.arrays()
+        except pp.PolypolishError:
+            host = None
+        rc, dev, _ = tok_cpu(H, NAMES, [strip_cpu(H, t)], False, 4)
+        if host is None:
+            assert rc in (PP_TOK_HOST, PP_TOK_NEED8), t
+        elif rc == PP_OK:
+            assert_same(dev, host)
+            n_ok += 1
+        else:
+            assert rc == PP_TOK_NEED8 and host["seq_bits"] == 8, t
+    assert n_ok > 50
+
+
+def upload_emulate(H, text, S, look):
+    out = C.create_string_buffer(len(text) + 1)
+    last = C.c_uint8(10)
+    sent = C.c_uint64()
+    H.upload_emulate.restype = C.c_int
+    rc = H.upload_emulate(C.c_char_p(text), C.c_uint64(len(text)), C.c_uint64(S), C.c_uint64(look), out, C.byref(last), C.byref(sent))
+    return rc, out.raw[:len(text)], last.value, sent.value
+
+
+@pytest.mark.parametrize("seed", range(110, 122))
+@pytest.mark.parametrize("S,look", [(64, 512), (97, 300), (1000, 400), (4096, 4096)])
+def test_stripping_upload_slices(H, tmp_path, seed, S, look):
+    """Tiny slices, so that nearly every line straddles one: every byte of the device text is written exactly once, it has the size
+    of the file, its last byte is the file's, and it tokenises to the host packer's arrays (the filler lines are skipped)."""
+    case = fuzzgen.make_case(seed, exotic=0.0, multimap=0.4)
+    texts = [t.encode("latin-1") for t in case.sam_texts]
+    if seed % 3 == 0 and not any(b"\r" in t for t in texts):
+        texts = [t.replace(b"\n", b"\r\n") for t in texts]
+    if seed % 4 == 1 and not any(b"\r" in t for t in texts):
+        texts = [t[:-1] for t in texts]
+    careful = case.opts["careful"]
+    f, p = host_pack(tmp_path, case.fasta_text, texts, careful)
+    host = p.arrays()
+    dev_texts = []
+    for t in texts:
+        rc, out, last, sent = upload_emulate(H, t, S, look)
+        longest = max(len(x) for x in t.split(b"\n")) + 1
+        if rc == 3:
+            assert longest >= look - 1
+            dev_texts.append(t)                       # the verbatim upload takes over
+            continue
+        assert rc == 0 and b"\xee" not in out and len(out) == len(t) and last == t[-1] and sent <= len(t)
+        assert out.count(b"\n") >= t.count(b"\n")
+        dev_texts.append(out)
+    rc, dev, _ = tok_cpu(H, f.names, dev_texts, careful, int(host["seq_bits"]))
+    assert rc == PP_OK
+    assert_same(dev, host)

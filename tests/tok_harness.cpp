@@ -2,6 +2,7 @@
 // kernels' bodies item by item in the order of the device pipeline (line index -> parse -> scans -> emit -> group heads ->
 // read ids -> group close), so that tests/test_tok_cpu.py can compare the arrays with the host packer's without a GPU.
 // Compiled by the test with g++.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -117,6 +118,33 @@ extern "C" int ftok_cpu(const char* text_in, uint64_t n, uint64_t cap_lines, uin
         kind[i] = tok::parse_line_quick(x, s, e, r);
         ref_start[i] = r.ref_start; ref_end[i] = r.ref_end; rev[i] = r.rev; name_len[i] = r.name_len; ref_rel[i] = r.ref_rel; ref_len[i] = r.ref_len;
         name_hash[i] = r.name_hash;
+    }
+    return 0;
+}
+
+// The upload-side QUAL stripping (tok_strip.h).
+#include "../polypolish_b200/csrc/tok_strip.h"
+extern "C" uint64_t strip_cpu(const char* src, uint64_t n, char* dst) {
+    return tok::strip_qual_lines(reinterpret_cast<const uint8_t*>(src), (size_t)n, reinterpret_cast<uint8_t*>(dst));
+}
+
+// The stripping upload, emulated: the same slice logic as upload_file_stripped (tok_kernels.cu) with nominal slices of S bytes
+// and a look-ahead of `look`, the copies applied to a host buffer.  Returns 0, or 3 when a line end is further than `look`.
+extern "C" int upload_emulate(const char* text_in, uint64_t n, uint64_t S, uint64_t look, char* out, uint8_t* last_byte, uint64_t* sent) {
+    const uint8_t* text = reinterpret_cast<const uint8_t*>(text_in);
+    std::vector<uint8_t> pin(S + look + 16);
+    memset(out, 0xEE, n);
+    *sent = 0;
+    const uint64_t n_slices = (n + S - 1) / S;
+    for (uint64_t k = 0; k < n_slices; ++k) {
+        const uint64_t o = k * S, e = std::min<uint64_t>(n, o + S);
+        const uint64_t rd0 = k ? o - 1 : 0, rd1 = std::min<uint64_t>(n, e + look - 1);
+        const tok::SliceOut so = tok::strip_slice(text + rd0, rd0, rd1, k, e, n, pin.data());
+        if (so.status == 3) return 3;
+        if (so.status == 1) continue;
+        if (so.ends_file) *last_byte = so.last;
+        tok::apply_slice(so, pin.data(), reinterpret_cast<uint8_t*>(out));
+        *sent += so.c;
     }
     return 0;
 }
