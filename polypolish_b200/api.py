@@ -445,7 +445,7 @@ class Context:
         lib().pp_tok_set_readers(self.h, int(n))
 
     def set_strip_qual(self, on):
-        """Whether SAM files are uploaded without their QUAL column (default on; polish never reads it)."""
+        """Whether SAM files are uploaded without their QUAL column (default off; polish never reads it, but the stripping is host-bound)."""
         lib().pp_tok_set_strip_qual(self.h, int(bool(on)))
 
     def set_parser(self, mode):

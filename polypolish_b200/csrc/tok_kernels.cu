@@ -247,7 +247,7 @@ struct TokState {
         bool strip = false;               // uploaded with QUAL replaced by "*" (polish only: filter reproduces lines verbatim)
         uint64_t sent = 0;                // bytes that crossed PCIe
     } pf;
-    bool strip_qual = true;               // pp_tok_set_strip_qual
+    bool strip_qual = false;              // pp_tok_set_strip_qual (off by default: measured host-bound, see profiles/README.md)
     uint8_t* h_nl = nullptr;              // pinned '\n'
     DevBuf cub;
     TokFilterBufs* fbufs = nullptr;   // device buffers of the filter text path
@@ -755,7 +755,7 @@ extern "C" int pp_tok_set_readers(pp_ctx* ctx, int n) {
     return PP_OK;
 }
 
-// 1 (default): pp_tok_add_file(s) / pp_tok_prefetch send the text without its QUAL column; 0: byte for byte.
+// 1: pp_tok_add_file(s) / pp_tok_prefetch send the text without its QUAL column; 0 (default): byte for byte.
 extern "C" int pp_tok_set_strip_qual(pp_ctx* ctx, int on) {
     if (!ctx) return PP_ERR_ARG;
     TokState* T = nullptr;
