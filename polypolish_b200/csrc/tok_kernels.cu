@@ -549,19 +549,27 @@ static int upload_file_stripped(int device, TokState* T, uint8_t* dst, int fd, u
     const uint64_t n_slices = (n + S - 1) / S;
     std::atomic<int> err{0}, cerr{0};              // 1 read error, 2 CUDA error, 3 long line
     std::atomic<unsigned long long> bytes{0};
+    // the lines are read through a private mapping of the file where that works (no copy before the strip), else pread
+    const uint8_t* map = nullptr;
+    {
+        void* m = n ? mmap(nullptr, (size_t)n, PROT_READ, MAP_PRIVATE, fd, 0) : MAP_FAILED;
+        if (m != MAP_FAILED) { map = (const uint8_t*)m; madvise(m, (size_t)n, MADV_SEQUENTIAL); }
+    }
     auto work = [&](int r) {
         if (cudaSetDevice(device) != cudaSuccess) { err = 2; return; }
-        std::vector<uint8_t> rawbuf(TK_SLOT + 16);
-        uint8_t* raw = rawbuf.data();
+        std::vector<uint8_t> rawbuf(map ? 16 : TK_SLOT + 16);
         uint64_t j = 0;
         for (uint64_t k = (uint64_t)r; k < n_slices && !err; k += (uint64_t)R) {
             const uint64_t o = k * S, e = std::min<uint64_t>(n, o + S);
             const uint64_t rd0 = k ? o - 1 : 0, rd1 = std::min<uint64_t>(n, e + TK_LOOK - 1);
-            uint64_t got = 0;
-            while (got < rd1 - rd0) {
-                const ssize_t g = pread(fd, raw + got, (size_t)(rd1 - rd0 - got), (off_t)(rd0 + got));
-                if (g <= 0) { err = 1; return; }
-                got += (uint64_t)g;
+            const uint8_t* raw = map ? map + rd0 : rawbuf.data();
+            if (!map) {
+                uint64_t got = 0;
+                while (got < rd1 - rd0) {
+                    const ssize_t g = pread(fd, rawbuf.data() + got, (size_t)(rd1 - rd0 - got), (off_t)(rd0 + got));
+                    if (g <= 0) { err = 1; return; }
+                    got += (uint64_t)g;
+                }
             }
             // the slot is needed before the lines are staged into it
             const int slot = (int)(j & 1);
@@ -599,6 +607,7 @@ static int upload_file_stripped(int device, TokState* T, uint8_t* dst, int fd, u
     for (int r = 1; r < R; ++r) th.emplace_back(work, r);
     work(0);
     for (auto& t : th) t.join();
+    if (map) munmap((void*)map, (size_t)n);
     *cuda_err = cerr.load();
     *sent = bytes.load();
     if (err == 3) {                                   // let the copies that were issued finish before the verbatim upload reuses the slots

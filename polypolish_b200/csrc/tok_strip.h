@@ -4,8 +4,34 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace tok {
+
+// Position just after the 10th '\t' of src[p, le), or 0 when the line has fewer than 10 tabs.  (SSE2: sixteen bytes per step;
+// the ten columns in front of QUAL are short, so ten memchr calls cost more than this one pass.)
+inline size_t after_tenth_tab(const uint8_t* src, size_t p, size_t le) {
+    int tabs = 0;
+    size_t t = p;
+#if defined(__SSE2__)
+    const __m128i tabv = _mm_set1_epi8('\t');
+    while (t + 16 <= le) {
+        unsigned m = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(src + t)), tabv));
+        const int c = __builtin_popcount(m);
+        if (tabs + c >= 10) {
+            for (int skip = 10 - tabs - 1; skip > 0; --skip) m &= m - 1;      // drop the tabs before the wanted one
+            return t + (size_t)__builtin_ctz(m) + 1;
+        }
+        tabs += c;
+        t += 16;
+    }
+#endif
+    for (; t < le; ++t)
+        if (src[t] == '\t' && ++tabs == 10) return t + 1;
+    return 0;
+}
 
 // src[0, len) holds whole lines (every line ends with '\n', except possibly the last).  Writes the same lines to dst with
 // the QUAL field of every record line that has one replaced by "*"; header lines ('@'), lines with fewer than 11
@@ -20,15 +46,8 @@ inline size_t strip_qual_lines(const uint8_t* src, size_t len, uint8_t* dst) {
         size_t q0 = 0, q1 = 0;
         bool strip = false;
         if (le > p && src[p] != '@') {
-            size_t t = p;
-            int tabs = 0;
-            while (tabs < 10) {
-                const uint8_t* tb = (const uint8_t*)memchr(src + t, '\t', le - t);
-                if (!tb) break;
-                t = (size_t)(tb - src) + 1;
-                tabs++;
-            }
-            if (tabs == 10) {
+            const size_t t = after_tenth_tab(src, p, le);
+            if (t) {
                 q0 = t;
                 const uint8_t* tb = (const uint8_t*)memchr(src + q0, '\t', le - q0);
                 q1 = tb ? (size_t)(tb - src) : le;
