@@ -42,6 +42,9 @@
 #include "tok_table.h"
 #include "tok_strip.h"
 
+// A temporary that does not fit in device memory is not an error of the data: the host text code takes over.
+#define TRY_ALLOC(x) do { if ((x) != cudaSuccess) { cudaGetLastError(); return PP_TOK_HOST; } } while (0)
+
 namespace {
 
 constexpr int TK_TILE = 16384;        // bytes of text per CTA in the newline passes
@@ -349,7 +352,7 @@ static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n
     size_t cub_bytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int64_t)std::max<uint64_t>(n_tiles + 1, 1)));
     CK(T->cub.ensure(cub_bytes + 256));
-    CK(ctx->b[B_TOKLINE].ensure((n_tiles + 2) * 8));
+    TRY_ALLOC(ctx->b[B_TOKLINE].ensure((n_tiles + 2) * 8));
     unsigned long long* tile_cnt = ctx->b[B_TOKLINE].as<unsigned long long>();
     uint64_t n_lines = 0;
     if (n_tiles) {
@@ -371,7 +374,7 @@ static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_ls = carve((n_lines + 2) * 8), o_rec = carve(n_lines * sizeof(tok::LineRec)), o_al = carve((n_lines + 1) * 8),
                  o_ops = carve((n_lines + 1) * 8), o_blk = carve((n_lines + 1) * 8);
-    CK(ctx->b[B_TOKTMP].ensure(off));
+    TRY_ALLOC(ctx->b[B_TOKTMP].ensure(off));
     uint8_t* tmp = ctx->b[B_TOKTMP].as<uint8_t>();
     ParseArgs pa;
     pa.text = text; pa.n = n; pa.line_start = (unsigned long long*)(tmp + o_ls); pa.n_lines = n_lines; pa.unterminated = unterminated ? 1 : 0;
@@ -420,7 +423,7 @@ static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n
     size_t off2 = 0;
     auto carve2 = [&](size_t bytes) { size_t o = off2; off2 += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_np = carve2(n_al * 8), o_nl = carve2(n_al * 4), o_hd = carve2(n_al * 4), o_rs = carve2(n_al * 4);
-    CK(ctx->b[B_SCRATCH].ensure(off2));
+    TRY_ALLOC(ctx->b[B_SCRATCH].ensure(off2));
     uint8_t* sc = ctx->b[B_SCRATCH].as<uint8_t>();
 
     EmitArgs ea;
@@ -1023,7 +1026,7 @@ static int ftok_lines(pp_ctx* ctx, TokState* T, int which, const uint8_t* text, 
     size_t cub_bytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int64_t)(n_tiles + 1)));
     CK(T->cub.ensure(cub_bytes + 256));
-    CK(ctx->b[B_TOKLINE].ensure((n_tiles + 2) * 8));
+    TRY_ALLOC(ctx->b[B_TOKLINE].ensure((n_tiles + 2) * 8));
     unsigned long long* tile_cnt = ctx->b[B_TOKLINE].as<unsigned long long>();
     CK(cudaMemsetAsync(tile_cnt + n_tiles, 0, 8, s));
     k_tok_count<<<(unsigned)n_tiles, TK_THREADS, 0, s>>>(text, n16, tile_cnt);
@@ -1035,11 +1038,11 @@ static int ftok_lines(pp_ctx* ctx, TokState* T, int which, const uint8_t* text, 
     CK(cudaStreamSynchronize(s));
     const uint64_t n_lines = T->h_tot[0] + (unterminated ? 1 : 0);
     if (n_lines == 0 || n_lines >= 0xFFFFFFF0ull) return PP_TOK_HOST;
-    CK(lines.ensure((n_lines + 2) * 8));
+    TRY_ALLOC(lines.ensure((n_lines + 2) * 8));
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_rec = carve(n_lines * sizeof(tok::FLineRec)), o_al = carve((n_lines + 1) * 8), o_ns = carve(n_lines * 4), o_rs = carve(n_lines * 4);
-    CK(tmp.ensure(off));
+    TRY_ALLOC(tmp.ensure(off));
     uint8_t* b = tmp.as<uint8_t>();
     fd->text = text; fd->n = n; fd->n_lines = n_lines; fd->unterminated = unterminated ? 1 : 0;
     fd->line_start = lines.as<unsigned long long>();
@@ -1131,7 +1134,7 @@ int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const 
     uint64_t cap = 1024;
     while (cap < 3 * (n_al[0] + n_al[1]) + 1024) cap <<= 1;
     if (cap > (1ull << 31)) return PP_TOK_HOST;
-    CK(B.table.ensure(cap * 16));
+    TRY_ALLOC(B.table.ensure(cap * 16));
     InternTable tb;
     tb.key = B.table.as<unsigned long long>(); tb.rep = tb.key + cap; tb.mask = (uint32_t)(cap - 1);
     CK(cudaMemsetAsync(tb.key, 0, cap * 8, s));
@@ -1142,7 +1145,7 @@ int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const 
     for (int k = 0; k < 2; ++k) {
         k_ftok_verify<<<(unsigned)((fd[k].n_lines + TK_LINE_THREADS - 1) / TK_LINE_THREADS), TK_LINE_THREADS, 0, s>>>(fd[0], fd[1], k, tb, d_st);
         const size_t na = (size_t)n_al[k];
-        CK(B.mate[k].ensure(na * 17 + 5 * 256));
+        TRY_ALLOC(B.mate[k].ensure(na * 17 + 5 * 256));
         uint8_t* mb = B.mate[k].as<uint8_t>();
         auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
         MateOut mo;
@@ -1191,7 +1194,7 @@ int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const 
         CK(cudaStreamSynchronize(s));
         const uint64_t out_n = T->h_tot[0];
         lap(3);
-        CK(B.out.ensure(out_n + 64));
+        TRY_ALLOC(B.out.ensure(out_n + 64));
         k_ftok_copy<<<(unsigned)((nl * 32 + 255) / 256), 256, 0, s>>>(fd[k], d_pass[k], out_off, B.out.as<uint8_t>());
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
