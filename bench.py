@@ -98,46 +98,64 @@ def algorithmic_bytes(arrs, G, out_len):
     return {"alignment_side": aln, "position_side": int(G + out_len), "total": int(aln + G + out_len)}
 
 
-def cpu_baseline(sample_bp, depth, seed, reps=1):
-    """The CPU oracle (C++ restatement of the reference, single thread like the reference) on a bounded slice."""
-    from polypolish_b200 import api
+def _shm_dir(prefix, need_gb):
+    import shutil
+    shm = "/dev/shm"
+    base = shm if os.path.isdir(shm) and shutil.disk_usage(shm).free > need_gb * (1 << 30) else None
+    return tempfile.mkdtemp(prefix=prefix, dir=base)
+
+
+def oracle_polish(fa, sams):
+    """One run of the CPU oracle's whole `polish` command (C++ restatement of the reference, single thread like the
+    reference) on SAM text that is already on disk / in the page cache.  Returns (seconds, result dict)."""
     from tests import oracle_lib
     o = oracle_lib.load()
-    with tempfile.TemporaryDirectory() as d:
-        syn = api.Synth(seed=seed, contig_len=sample_bp, depth=depth)
-        fa, sams = syn.write(d)
-        best, phases = None, None
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            r = o.polish(fa, sams)
-            dt = time.perf_counter() - t0
-            if best is None or dt < best:
-                best, phases = dt, r["secs"]
-        bp = syn.total_bp
-    return bp / 1e6 / best, best, phases, bp
+    t0 = time.perf_counter()
+    r = o.polish(fa, sams)
+    return time.perf_counter() - t0, r
+
+
+def reference_sample(workload):
+    """What the CPU arm runs: the workload itself when one run of it is bounded (5 Mbp x 100x: ~15 s), else a slice."""
+    n_c, clen, depth = WORKLOADS[workload]
+    if n_c * clen * depth <= 6e8:
+        return n_c, clen, depth, True
+    clen = min(clen, 1_000_000)
+    return 1, clen, (depth if clen * depth <= 6e8 else 100.0), False
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path on the host cores.  The Rust crate
-    cannot be built in this image (no cargo/rustc; 78 un-vendored crates), so this is the oracle port."""
+    cannot be built in this image (no cargo/rustc; 78 un-vendored crates), so this is the oracle port, one thread (the
+    reference has no threads).  Same config as the b200 arm's N=1 workload; the input files are generated once, outside
+    the timed steps; one step = the whole `polish` command on them (page cache warm)."""
     if rank != 0:
         return
-    n_c, clen, depth = WORKLOADS[args.workload]
-    sample = min(clen, 500_000)
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, dt, phases, bp = cpu_baseline(sample, depth, seed=2)
-        if i >= args.warmup:
-            vals.append((v, dt, phases))
+    import hashlib
+    import shutil
+    from polypolish_b200 import api
+    n_c, clen, depth, same = reference_sample(args.workload)
+    d = _shm_dir("pp_ref_", 6)
+    try:
+        syn = api.Synth(seed=2, n_contigs=n_c, contig_len=clen, depth=depth)
+        fa, sams = syn.write(d)
+        bp = syn.total_bp
+        vals, sha = [], None
+        for i in range(args.warmup + args.steps):
+            dt, r = oracle_polish(fa, sams)
+            sha = hashlib.sha256(r["fasta"]).hexdigest()
+            if i >= args.warmup:
+                vals.append((bp / 1e6 / dt, dt, r["secs"]))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
     v = sum(x[0] for x in vals) / len(vals)
     ms = 1e3 * sum(x[1] for x in vals) / len(vals)
+    sample = f"{bp} bp x {depth:g}x ({'the whole workload' if same else 'a slice of the workload'}), whole `polish` command on page-cache-warm SAM text"
     line = {"metric": METRIC, "value": v, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 counters, f64 depth",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "sample": f"{sample} bp x {depth:g}x slice of the workload per step (SAM text in, FASTA out)"},
-            "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": 1, "kind": "port",
-                             "sample": f"{sample} bp x {depth:g}x, whole `polish` command on page-cache-warm SAM text",
-                             "phases_s": vals[-1][2]},
+            "config": {"workload": args.workload, "same_config": same, "sample": sample, "fasta_sha256": sha},
+            "cpu_baseline": {"value": v, "unit": "Mbp/s", "cores": 1, "kind": "port", "sample": sample, "phases_s": vals[-1][2]},
             "e2e": {"value": v, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -256,32 +274,68 @@ def main():
     d2h_bytes = int(e["out_len"]) + 8 * (3 * n_c + 1)
 
     # ---------------- T3: the whole command, SAM/FASTA text on disk (page cache warm) -> polished FASTA bytes ----------------
-    t3 = None
-    if rank == 0 and world == 1 and not args.no_t3 and G * depth <= 6e8:
+    # ... and on the same files: the one-shot CLI process, the CPU oracle (cpu_baseline) and the parity check GPU == oracle.
+    t3 = cli = cpu = parity = None
+    if rank == 0 and world == 1:
+        import hashlib
         import shutil
-        shm = "/dev/shm"
-        base = shm if os.path.isdir(shm) and shutil.disk_usage(shm).free > 4 * (1 << 30) else None
-        d = tempfile.mkdtemp(prefix="pp_t3_", dir=base)
+        full = G * depth <= 6e8                              # the whole workload as text is bounded (<= ~1.3 GB, oracle ~15 s)
+        if full:
+            tsyn, tdesc = syn, "the whole workload"
+        else:
+            tsyn = api.Synth(seed=2, contig_len=min(clen, 1_000_000), depth=min(depth, 100.0))
+            tdesc = "a slice of the same generator"
+        d = _shm_dir("pp_t3_", 6)
         try:
-            fa_path, sam_paths = syn.write(d)
+            fa_path, sam_paths = tsyn.write(d)
+            tbp = int(tsyn.total_bp)
             sam_bytes = sum(os.path.getsize(x) for x in sam_paths)
-            outs, best = {}, {}
-            for mode, name, reps in ((0, "device_tokeniser", 4), (1, "host_packer", 2)):
-                ctx.set_parser(mode)
-                ts = []
-                for _ in range(reps):
-                    torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                    outs[name] = ctx.polish_files(fa_path, sam_paths)
-                    ts.append((time.perf_counter() - t0) * 1e3)
-                best[name] = min(ts)
-            ctx.set_parser(0)
-            rc_tok, tok_stats = ctx.tokenise(fasta, sam_paths)
-            t3 = {"value": G / 1e6 / (best["device_tokeniser"] / 1e3), "unit": "Mbp/s", "ms": best["device_tokeniser"],
-                  "host_packer_ms": best["host_packer"], "sam_text_bytes": int(sam_bytes), "files": len(sam_paths), "host_cores": os.cpu_count(),
-                  "identical_output": outs["device_tokeniser"] == outs["host_packer"],
-                  "tokeniser": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()} for st in tok_stats],
-                  "api": "pp_polish_files (FASTA + SAM paths in, FASTA bytes out), best of 4; host_packer = same call with pp_set_parser(1)"}
+            gpu_fasta = None
+            if not args.no_t3:
+                outs, best = {}, {}
+                for mode, name, reps in ((0, "device_tokeniser", 4), (1, "host_packer", 2)):
+                    ctx.set_parser(mode)
+                    ts = []
+                    for _ in range(reps):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        outs[name] = ctx.polish_files(fa_path, sam_paths)
+                        ts.append((time.perf_counter() - t0) * 1e3)
+                    best[name] = min(ts)
+                ctx.set_parser(0)
+                gpu_fasta = outs["device_tokeniser"]
+                rc_tok, tok_stats = ctx.tokenise(tsyn.fasta(), sam_paths)
+                t3 = {"value": tbp / 1e6 / (best["device_tokeniser"] / 1e3), "unit": "Mbp/s", "ms": best["device_tokeniser"],
+                      "host_packer_ms": best["host_packer"], "sam_text_bytes": int(sam_bytes), "files": len(sam_paths), "host_cores": os.cpu_count(),
+                      "input": f"{tbp} bp x {depth:g}x ({tdesc})", "parsers_agree": outs["device_tokeniser"] == outs["host_packer"],
+                      "tokeniser": [{k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()} for st in tok_stats],
+                      "api": "pp_polish_files (FASTA + SAM paths in, FASTA bytes out), best of 4; host_packer = same call with pp_set_parser(1)"}
+                # the drop-in command as a user runs it: a fresh process per call (CUDA start-up included)
+                exe = os.path.join(ROOT, "build", "polypolish")
+                if os.path.exists(exe):
+                    ts, cli_out = [], None
+                    for _ in range(3):
+                        t0 = time.perf_counter()
+                        pr = subprocess.run([exe, "polish", "--quiet", fa_path] + sam_paths, capture_output=True)
+                        ts.append((time.perf_counter() - t0) * 1e3)
+                        if pr.returncode != 0:
+                            raise RuntimeError("build/polypolish polish failed: " + pr.stderr.decode()[-400:])
+                        cli_out = pr.stdout
+                    cli = {"value": tbp / 1e6 / (min(ts) / 1e3), "unit": "Mbp/s", "wall_ms": min(ts), "wall_ms_all": [round(x, 1) for x in ts],
+                           "command": "build/polypolish polish --quiet draft.fasta reads_1.sam reads_2.sam > out.fasta (fresh process, page cache warm)",
+                           "identical_to_library_call": cli_out == gpu_fasta}
+            else:
+                gpu_fasta = ctx.polish_files(fa_path, sam_paths)
+            if not args.no_cpu_baseline:
+                dt, orc = oracle_polish(fa_path, sam_paths)
+                cpu = {"value": tbp / 1e6 / dt, "unit": "Mbp/s", "cores": 1, "kind": "port",
+                       "sample": f"{tbp} bp x {depth:g}x ({tdesc}), whole `polish` command from the same SAM text files ({dt:.1f} s)",
+                       "phases_s": orc["secs"]}
+                parity = {"checked": True, "identical": orc["fasta"] == gpu_fasta, "sha256": hashlib.sha256(gpu_fasta).hexdigest(),
+                          "oracle_sha256": hashlib.sha256(orc["fasta"]).hexdigest(), "bytes": len(gpu_fasta),
+                          "what": f"polished FASTA of pp_polish_files vs the CPU oracle on the same files, {tbp} bp x {depth:g}x ({tdesc})"}
+                if cli is not None:
+                    parity["cli_identical"] = cli_out == orc["fasta"]
             ctx.upload(fasta.view, packed.view)
         finally:
             shutil.rmtree(d, ignore_errors=True)
@@ -297,10 +351,12 @@ def main():
         hbm, how = peaks()
         ab = algorithmic_bytes(arrs, G, out_len)
         sc_ms = stage["scatter_ms"] / args.steps
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.workload)
+            tj = json.load(open(tp))
+            traffic = tj.get(args.workload)
+            traffic_src = "static, from profiles/traffic.json (%s); not measured in this run" % tj.get("source", "ncu --set full capture")
         line = {
             "metric": METRIC, "value": total_bp / 1e6 / (ms_step_max / 1e3), "unit": "Mbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step_max, "higher_is_better": True,
@@ -313,7 +369,7 @@ def main():
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes), "api": "pp_polish (host SoA in, host bases out)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_scatter<4>", "achieved": ab["alignment_side"] / 1e9 / (sc_ms / 1e3), "peak": hbm,
-                         "unit": "GB/s", "frac": ab["alignment_side"] / 1e9 / (sc_ms / 1e3) / hbm, "traffic": traffic, "peak_source": how,
+                         "unit": "GB/s", "frac": ab["alignment_side"] / 1e9 / (sc_ms / 1e3) / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": how,
                          "algorithmic_bytes_per_launch": ab["alignment_side"], "kernel_ms": sc_ms,
                          "whole_path": {"algorithmic_bytes": ab["total"], "ms": ms_step, "achieved": ab["total"] / 1e9 / (ms_step / 1e3),
                                         "frac": ab["total"] / 1e9 / (ms_step / 1e3) / hbm}},
@@ -322,12 +378,15 @@ def main():
         }
         if t3 is not None:
             line["t3"] = t3
-        if not args.no_cpu_baseline and world == 1:
-            v, dt, phases, bp = cpu_baseline(min(clen, 1_000_000), depth, seed=2)
-            line["cpu_baseline"] = {"value": v, "unit": "Mbp/s", "cores": 1, "kind": "port",
-                                    "sample": f"{bp} bp x {depth:g}x slice of the same generator, whole `polish` command from SAM text ({dt:.1f} s)",
-                                    "phases_s": phases}
+        if cli is not None:
+            line["cli"] = cli
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity"] = parity
         print(json.dumps(line), flush=True)
+        if parity is not None and not (parity["identical"] and parity.get("cli_identical", True)):
+            raise SystemExit("bench: the GPU FASTA differs from the CPU oracle's on the same input (parity broken)")
     for p in pinned:
         L.pp_host_free(p)
     ctx.close()

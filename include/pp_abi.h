@@ -122,6 +122,9 @@ typedef struct {
   uint64_t out_cap;     /* capacity of out_bases in bytes                                            */
   uint64_t* changed;    /* [n_contigs] positions with status Changed (polish.rs:173-176), may be NULL */
   uint64_t* zero_depth; /* [n_contigs] positions with depth == 0 (polish.rs:178-180), may be NULL     */
+  double* total_depth;  /* [n_contigs] sum over positions of the f64 depth (polish.rs:177; mean read depth of the log =
+                           total_depth / contig length), may be NULL.  Per-position depths are the reference's exactly; their
+                           sum is accumulated in parallel, so it can differ from the reference's sequential sum in the last bits */
   /* filled by the library */
   uint64_t out_len;     /* total polished bases (if > out_cap nothing was copied: PP_ERR_ARG)        */
   uint64_t n_aln_used;  /* Σ good alignments (alignment.rs:304, polish.rs:121)                       */
@@ -331,6 +334,9 @@ typedef struct {
 } pp_synth_params;
 typedef struct pp_synth pp_synth;
 pp_synth* pp_synth_create(const pp_synth_params* prm);
+/* the same, plus repeat families (3, 2, 5, 7 copies) whose copies lie on DIFFERENT contigs, covering `cross_contig_fraction`
+ * of the assembly: reads in them multi-map across contigs, so under contig sharding their k spans GPUs (BASELINE config 5). */
+pp_synth* pp_synth_create_shared(const pp_synth_params* prm, double cross_contig_fraction);
 void pp_synth_free(pp_synth* s);
 uint64_t pp_synth_total_bp(const pp_synth* s);    /* draft bases */
 uint64_t pp_synth_n_pairs(const pp_synth* s);

@@ -55,7 +55,7 @@ class Timing(C.Structure):
 
 class PolishResult(C.Structure):
     _fields_ = [("out_off", C.c_void_p), ("out_bases", C.c_void_p), ("out_cap", C.c_uint64), ("changed", C.c_void_p),
-                ("zero_depth", C.c_void_p), ("out_len", C.c_uint64), ("n_aln_used", C.c_uint64),
+                ("zero_depth", C.c_void_p), ("total_depth", C.c_void_p), ("out_len", C.c_uint64), ("n_aln_used", C.c_uint64),
                 ("error_aln", C.c_int64), ("timing", Timing)]
 
 
@@ -296,7 +296,9 @@ class Context:
     def _result(self, n_contigs, cap):
         res = PolishResult()
         keep = dict(off=np.zeros(n_contigs + 1, dtype=np.uint64), bases=np.zeros(max(1, cap), dtype=np.uint8),
-                    changed=np.zeros(n_contigs, dtype=np.uint64), zero=np.zeros(n_contigs, dtype=np.uint64))
+                    changed=np.zeros(n_contigs, dtype=np.uint64), zero=np.zeros(n_contigs, dtype=np.uint64),
+                    tdepth=np.zeros(n_contigs, dtype=np.float64))
+        res.total_depth = keep["tdepth"].ctypes.data
         res.out_off = keep["off"].ctypes.data
         res.out_bases = keep["bases"].ctypes.data
         res.out_cap = cap
@@ -308,7 +310,7 @@ class Context:
         off = keep["off"]
         seqs = [keep["bases"][int(off[i]):int(off[i + 1])].tobytes() for i in range(n_contigs)]
         return dict(sequences=seqs, changed=keep["changed"].tolist(), zero_depth=keep["zero"].tolist(),
-                    n_aln_used=res.n_aln_used, out_len=res.out_len, timing=res.timing.as_dict())
+                    total_depth=keep["tdepth"].tolist(), n_aln_used=res.n_aln_used, out_len=res.out_len, timing=res.timing.as_dict())
 
     def pinned_result(self, n_contigs, cap):
         """Caller-owned result buffers in pinned host memory (pp_host_alloc), reusable across pp_polish calls."""
@@ -505,7 +507,7 @@ class Synth:
 
     def __init__(self, seed=1, n_contigs=1, contig_len=50_000, depth=100.0, read_len=150, insert_mean=400.0,
                  insert_sd=40.0, draft_error_rate=1e-4, seq_sub_rate=2e-3, seq_indel_rate=1e-4, repeat_fraction=0.03,
-                 clip_rate=0.005, highnm_rate=0.005, unaligned_rate=0.005):
+                 clip_rate=0.005, highnm_rate=0.005, unaligned_rate=0.005, cross_contig=0.0):
         L = lib()
         L.pp_synth_create.restype = C.c_void_p
         L.pp_synth_create.argtypes = [C.POINTER(SynthParams)]
@@ -521,7 +523,9 @@ class Synth:
         L.pp_synth_feed_pack.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         prm = SynthParams(seed, n_contigs, read_len, contig_len, depth, insert_mean, insert_sd, draft_error_rate,
                           seq_sub_rate, seq_indel_rate, repeat_fraction, clip_rate, highnm_rate, unaligned_rate)
-        self.h = L.pp_synth_create(C.byref(prm))
+        L.pp_synth_create_shared.restype = C.c_void_p
+        L.pp_synth_create_shared.argtypes = [C.POINTER(SynthParams), C.c_double]
+        self.h = L.pp_synth_create_shared(C.byref(prm), float(cross_contig)) if cross_contig else L.pp_synth_create(C.byref(prm))
         if not self.h:
             raise PolypolishError(PP_ERR_ARG, "pp_synth_create: bad parameters")
         self.total_bp = L.pp_synth_total_bp(self.h)

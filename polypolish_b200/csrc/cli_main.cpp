@@ -36,16 +36,77 @@ static const char* BANNER =
     exit(2);
 }
 
-static void help() {
+static void help() {                      // `polypolish`, `polypolish -h`: the layout of clap 4's derived help (main.rs:23-42)
     fputs(BANNER, stdout);
-    puts("short-read polishing of long-read assemblies (B200-native build)\ngithub.com/rrwick/Polypolish\n");
+    puts("\nshort-read polishing of long-read assemblies\ngithub.com/rrwick/Polypolish\n");
     puts("Usage: polypolish <COMMAND>\n");
     puts("Commands:\n  filter  filter paired-end alignments based on insert size\n  polish  polish a long-read assembly using short-read alignments\n");
     puts("Options:\n  -h, --help     Print help\n  -V, --version  Print version");
-    puts("\npolypolish filter --in1 <IN1> --in2 <IN2> --out1 <OUT1> --out2 <OUT2> [--orientation <auto>] [--low <0.1>] [--high <99.9>]");
-    puts("polypolish polish [--debug <DEBUG>] [-i|--fraction_invalid <0.2>] [-v|--fraction_valid <0.5>] [-m|--max_errors <10>]");
-    puts("                  [-d|--min_depth <5>] [--careful] <ASSEMBLY> [SAM]...");
-    puts("Additive: --device <N> (first GPU, default 0), --gpus <N> (polish: shard contigs over N GPUs), --quiet, --host-parse");
+}
+
+static void help_filter() {               // main.rs:46-75
+    puts("filter paired-end alignments based on insert size\n");
+    puts("Usage: polypolish filter [OPTIONS] --in1 <IN1> --in2 <IN2> --out1 <OUT1> --out2 <OUT2>\n");
+    puts("Options:");
+    puts("      --in1 <IN1>                  Input SAM file - first read in pairs");
+    puts("      --in2 <IN2>                  Input SAM file - first second in pairs");
+    puts("      --out1 <OUT1>                Output SAM file - first read in pairs");
+    puts("      --out2 <OUT2>                Output SAM file - first second in pairs");
+    puts("      --orientation <ORIENTATION>  Expected pair orientation [default: auto]");
+    puts("      --low <LOW>                  Low percentile threshold [default: 0.1]");
+    puts("      --high <HIGH>                High percentile threshold [default: 99.9]");
+    puts("  -h, --help                       Print help");
+    puts("  -V, --version                    Print version");
+    puts("\nB200 build, additive options: --device <N> (GPU, default 0), --quiet, --host-parse");
+}
+
+static void help_polish() {               // main.rs:77-108
+    puts("polish a long-read assembly using short-read alignments\n");
+    puts("Usage: polypolish polish [OPTIONS] <ASSEMBLY> [SAM]...\n");
+    puts("Arguments:");
+    puts("  <ASSEMBLY>  Assembly to polish (one file in FASTA format)");
+    puts("  [SAM]...    Short read alignments (one or more files in SAM format)\n");
+    puts("Options:");
+    puts("      --debug <DEBUG>");
+    puts("          Optional file to store per-base information for debugging purposes");
+    puts("  -i, --fraction_invalid <FRACTION_INVALID>");
+    puts("          A base must make up less than this fraction of the read depth to be considered invalid [default: 0.2]");
+    puts("  -v, --fraction_valid <FRACTION_VALID>");
+    puts("          A base must make up at least this fraction of the read depth to be considered valid [default: 0.5]");
+    puts("  -m, --max_errors <MAX_ERRORS>");
+    puts("          Ignore alignments with more than this many mismatches and indels [default: 10]");
+    puts("  -d, --min_depth <MIN_DEPTH>");
+    puts("          A base must occur at least this many times in the pileup to be considered valid [default: 5]");
+    puts("      --careful");
+    puts("          Ignore any reads with multiple alignments");
+    puts("  -h, --help");
+    puts("          Print help");
+    puts("  -V, --version");
+    puts("          Print version");
+    puts("\nB200 build, additive options: --device <N> (first GPU, default 0), --gpus <N> (contigs shard over N GPUs), --quiet, --host-parse");
+}
+
+// clap accepts `--name=value`, `-m5` / `-m=5` and a `--` separator (everything after it is positional): normalise those forms
+// into separate tokens.  `value_shorts` = the short options that take a value.
+struct Token { std::string text; bool positional; };
+static std::vector<Token> normalise_args(int argc, char** argv, int first, const char* value_shorts) {
+    std::vector<Token> out;
+    bool rest = false;
+    for (int i = first; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (rest) { out.push_back({a, true}); continue; }
+        if (a == "--") { rest = true; continue; }
+        if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+            const size_t eq = a.find('=');
+            if (eq != std::string::npos) { out.push_back({a.substr(0, eq), false}); out.push_back({a.substr(eq + 1), true}); continue; }
+        } else if (a.size() > 2 && a[0] == '-' && a[1] != '-' && strchr(value_shorts, a[1])) {
+            out.push_back({a.substr(0, 2), false});
+            out.push_back({a.substr(a[2] == '=' ? 3 : 2), true});
+            continue;
+        }
+        out.push_back({a, false});
+    }
+    return out;
 }
 
 static double parse_f64(const char* flag, const char* s) {
@@ -77,17 +138,20 @@ int main(int argc, char** argv) {
     if (cmd == "-V" || cmd == "--version") { puts("Polypolish v0.6.1"); return 0; }
     int device = 0, gpus = 1;
     bool quiet = false, host_parse = false;
-    auto need = [&](int& i, const char* flag) -> const char* {
-        if (i + 1 >= argc) usage_error(std::string("a value is required for '") + flag + "' but none was supplied");
-        return argv[++i];
+    std::vector<Token> tok;
+    auto need = [&](size_t& i, const char* flag) -> const char* {
+        if (i + 1 >= tok.size()) usage_error(std::string("a value is required for '") + flag + "' but none was supplied");
+        return tok[++i].text.c_str();
     };
     if (cmd == "polish") {
         pp_polish_params prm{0.2, 0.5, 10, 5, 0};
         std::string debug;
         std::vector<std::string> pos;
-        for (int i = 2; i < argc; ++i) {
-            std::string a = argv[i];
-            if (a == "-h" || a == "--help") { help(); return 0; }
+        tok = normalise_args(argc, argv, 2, "ivmd");
+        for (size_t i = 0; i < tok.size(); ++i) {
+            const std::string& a = tok[i].text;
+            if (tok[i].positional) { pos.push_back(a); continue; }
+            if (a == "-h" || a == "--help") { help_polish(); return 0; }
             else if (a == "-V" || a == "--version") { puts("Polypolish-polish v0.6.1"); return 0; }
             else if (a == "--debug") debug = need(i, "--debug <DEBUG>");
             else if (a == "-i" || a == "--fraction_invalid") prm.fraction_invalid = parse_f64("--fraction_invalid <FRACTION_INVALID>", need(i, "--fraction_invalid"));
@@ -128,9 +192,12 @@ int main(int argc, char** argv) {
     if (cmd == "filter") {
         std::string in1, in2, out1, out2, orientation = "auto";
         double low = 0.1, high = 99.9;
-        for (int i = 2; i < argc; ++i) {
-            std::string a = argv[i];
-            if (a == "-h" || a == "--help") { help(); return 0; }
+        tok = normalise_args(argc, argv, 2, "");
+        for (size_t i = 0; i < tok.size(); ++i) {
+            const std::string& a = tok[i].text;
+            if (tok[i].positional) usage_error("unexpected argument '" + a + "' found");
+            if (a == "-h" || a == "--help") { help_filter(); return 0; }
+            else if (a == "-V" || a == "--version") { puts("Polypolish-filter v0.6.1"); return 0; }
             else if (a == "--in1") in1 = need(i, "--in1 <IN1>");
             else if (a == "--in2") in2 = need(i, "--in2 <IN2>");
             else if (a == "--out1") out1 = need(i, "--out1 <OUT1>");

@@ -54,11 +54,9 @@ bool read_gz_file(const std::string& path, std::string& out) {
     return true;
 }
 
-bool file_exists(const std::string& path) {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) return false;
-    fclose(f);
-    return true;
+bool file_exists(const std::string& path) {      // Path::exists (misc.rs:218-223): a stat, never an open (a FIFO would block / lose its writer)
+    struct stat sb;
+    return stat(path.c_str(), &sb) == 0;
 }
 
 uint64_t file_size(const std::string& path) {

@@ -29,6 +29,16 @@ std::string fmt_thousands(uint64_t v) {      // num_format Locale::en
     return o;
 }
 
+// polish.rs:290-300 qscore: "Q∞" at 100 %, "Q0" at or below 0 %, else Q{-10 log10(1 - identity/100)} with two decimals
+std::string qscore_text(double identity) {
+    if (identity >= 100.0) return "Q\xe2\x88\x9e";
+    if (identity <= 0.0) return "Q0";
+    const double errors = 1.0 - (identity / 100.0);
+    char tmp[64];
+    snprintf(tmp, sizeof tmp, "Q%.2f", -10.0 * std::log10(errors));
+    return tmp;
+}
+
 }  // namespace
 
 extern "C" void pp_free(void* p) { free(p); }
@@ -132,6 +142,7 @@ struct ShardJob {
     const uint32_t* contig_map = nullptr;
     bool resident = false;               // the dataset is already on the device (device tokeniser)
     std::vector<uint64_t> out_off, changed, zero;
+    std::vector<double> tdepth;
     std::vector<uint8_t> bases;
     pp_polish_result res;
     int rc = PP_OK;
@@ -143,6 +154,7 @@ static void run_shard(ShardJob* j, const pp_polish_params* prm) {
     j->out_off.assign(j->contigs.n_contigs + 1, 0);
     j->changed.assign(j->contigs.n_contigs, 0);
     j->zero.assign(j->contigs.n_contigs, 0);
+    j->tdepth.assign(j->contigs.n_contigs, 0.0);
     memset(&j->res, 0, sizeof j->res);
     // Output is at most G + inserted bases; start with G + 1 MiB and retry once with the exact size.
     uint64_t cap = G + (1u << 20);
@@ -153,6 +165,7 @@ static void run_shard(ShardJob* j, const pp_polish_params* prm) {
         j->res.out_cap = cap;
         j->res.changed = j->changed.data();
         j->res.zero_depth = j->zero.data();
+        j->res.total_depth = j->tdepth.data();
         j->rc = j->resident ? pp_polish_resident(j->ctx, prm, &j->res) : pp_polish(j->ctx, &j->contigs, &j->alns, prm, &j->res);
         if (j->rc == PP_ERR_ARG && j->res.out_len > cap) { cap = j->res.out_len; continue; }
         break;
@@ -378,10 +391,13 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
         if (verbose) {
             uint64_t len = contigs.off[i + 1] - contigs.off[i];
             fprintf(stderr, "Polishing %s (%s bp):\n", pp_fasta_name(fa, i), fmt_thousands(len).c_str());
+            fprintf(stderr, "  mean read depth: %.1fx\n", j.tdepth[lc] / (double)len);                       // polish.rs:208-210
             fprintf(stderr, "  %s bp %s a depth of zero (%.4f%% coverage)\n", fmt_thousands(j.zero[lc]).c_str(), j.zero[lc] == 1 ? "has" : "have",
                     100.0 * (double)(len - j.zero[lc]) / (double)len);
-            fprintf(stderr, "  %s %s changed (%.4f%% of total positions)\n\n", fmt_thousands(j.changed[lc]).c_str(),
+            fprintf(stderr, "  %s %s changed (%.4f%% of total positions)\n", fmt_thousands(j.changed[lc]).c_str(),
                     j.changed[lc] == 1 ? "position" : "positions", 100.0 * (double)j.changed[lc] / (double)len);
+            const double accuracy = 100.0 - 100.0 * (double)j.changed[lc] / (double)len;
+            fprintf(stderr, "  estimated pre-polishing sequence accuracy: %.4f%% (%s)\n\n", accuracy, qscore_text(accuracy).c_str());
         }
     }
     if (verbose) {

@@ -739,6 +739,7 @@ struct VoteParams {
     unsigned long long out_cap;
     unsigned long long* out_off;     // [n_contigs+1]
     unsigned long long *changed, *zero_depth;   // [n_contigs]
+    double* total_depth;             // [n_contigs] sum of the per-position depths (polish.rs:177; the log's mean read depth)
     const unsigned long long* chunk_pre;   // [n_chunks] sum of diff[] before the chunk (k_diff_sums + device scan, side stream)
     // per-position verdicts handed from k_vote to k_compact
     uint16_t* res;                    // [padG] low byte = character, high byte = output length (255: see rec_at)
@@ -894,6 +895,7 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
     PosOut po[VT_ITEMS];
     unsigned long long tlen = 0;
     uint32_t n_changed = 0, n_zero = 0;
+    double tdepth = 0.0;
     uint32_t ctg = 0;
     if (p0 < d.G) {
         uint32_t lo = 0, hi = d.n_contigs;           // largest c with contig_off[c] <= p0
@@ -909,7 +911,9 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
         while (p >= next_start) {
             if (n_changed) atomicAdd(&vp.changed[ctg], (unsigned long long)n_changed);
             if (n_zero) atomicAdd(&vp.zero_depth[ctg], (unsigned long long)n_zero);
+            if (tdepth != 0.0) atomicAdd(&vp.total_depth[ctg], tdepth);
             n_changed = n_zero = 0;
+            tdepth = 0.0;
             ctg++;
             next_start = (ctg + 1 < d.n_contigs) ? (uint32_t)d.contig_off[ctg + 1] : 0xFFFFFFFFu;
         }
@@ -930,6 +934,8 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
             continue;
         }
         if (cover >= 65536u) atomicOr(&d.st->flags, FL_COUNTER_OVF);
+        const double depth = multi ? d.depth_fix[p] : (double)cover;
+        tdepth += depth;
         const unsigned long long ex = exv[i];
         if (ex == 0 && dlv[i] == 0 && !vp.dbg) {
             // every covering entry equals the draft base: the only allele with a non-zero count is the draft's own, so
@@ -946,13 +952,13 @@ __global__ void __launch_bounds__(VT_THREADS, 3) k_vote(DevData d, VoteParams vp
         else if (orig == 'C') { cC += matched; matched = 0; }
         else if (orig == 'G') { cG += matched; matched = 0; }
         else if (orig == 'T') { cT += matched; matched = 0; }
-        const double depth = multi ? d.depth_fix[p] : (double)cover;
         po[i] = vote_position<BITS>(oc, prm, p, orig, depth, cA, cC, cG, cT, cDel, matched, n_other, vp.dbg ? vp.dbg + p : nullptr);
         n_changed += (po[i].packed >> 24) & 1u;
         tlen += po[i].packed & 0xFFFFu;
     }
     if (n_changed) atomicAdd(&vp.changed[ctg], (unsigned long long)n_changed);
     if (n_zero) atomicAdd(&vp.zero_depth[ctg], (unsigned long long)n_zero);
+    if (tdepth != 0.0) atomicAdd(&vp.total_depth[ctg], tdepth);
 
     // ---- 3. hand the verdicts to k_compact: 2 bytes per position + this chunk's length delta
     {
@@ -1267,7 +1273,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         auto carve = [&](size_t bytes) { size_t o = zoff; zoff += (bytes + 255) & ~size_t(255); return o; };
         const size_t o_diff = carve(padG * 8), o_ex = carve(padG * 8), o_del = carve(padG * 4), o_head = carve((G + 1) * 4),
                      o_tile = carve(((size_t)n_tiles / 32 + 2) * 4),
-                     o_chg = carve((size_t)ctx->n_contigs * 8), o_zero = carve((size_t)ctx->n_contigs * 8), o_status = carve(sizeof(DevStatus)),
+                     o_chg = carve((size_t)ctx->n_contigs * 8), o_zero = carve((size_t)ctx->n_contigs * 8), o_tdep = carve((size_t)ctx->n_contigs * 8), o_status = carve(sizeof(DevStatus)),
                      o_fkey = carve((size_t)fix_cap * 4), o_fval = carve((size_t)fix_cap * 4),
                      o_k = carve(ctx->global_k ? (ctx->n_reads + 1) * 4 : 4);
         CK(ctx->b[B_ZEROPOOL].ensure(zoff));
@@ -1389,7 +1395,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         vp.n_chunks = n_chunks;
         vp.out = ctx->b[B_OUT].as<uint8_t>(); vp.out_cap = out_cap;
         vp.out_off = ctx->b[B_OUTOFF].as<unsigned long long>();
-        vp.changed = (unsigned long long*)(zp + o_chg); vp.zero_depth = (unsigned long long*)(zp + o_zero);
+        vp.changed = (unsigned long long*)(zp + o_chg); vp.zero_depth = (unsigned long long*)(zp + o_zero); vp.total_depth = (double*)(zp + o_tdep);
         vp.chunk_pre = ctx->b[B_AGG1].as<unsigned long long>();
         CK(cudaStreamWaitEvent(s, ctx->side_ev[1], 0));
         vp.res = ctx->b[B_RES].as<uint16_t>(); vp.rec_at = ctx->b[B_RECAT].as<uint32_t>();
@@ -1448,6 +1454,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
             if (res->out_off) CK(cudaMemcpyAsync(res->out_off, vp.out_off, ((size_t)ctx->n_contigs + 1) * 8, cudaMemcpyDeviceToHost, s));
             if (res->changed) CK(cudaMemcpyAsync(res->changed, vp.changed, (size_t)ctx->n_contigs * 8, cudaMemcpyDeviceToHost, s));
             if (res->zero_depth) CK(cudaMemcpyAsync(res->zero_depth, vp.zero_depth, (size_t)ctx->n_contigs * 8, cudaMemcpyDeviceToHost, s));
+            if (res->total_depth) CK(cudaMemcpyAsync(res->total_depth, vp.total_depth, (size_t)ctx->n_contigs * 8, cudaMemcpyDeviceToHost, s));
             CK(cudaEventRecord(ctx->ev[8], s));
             CK(cudaStreamSynchronize(s));
             CK(cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]));

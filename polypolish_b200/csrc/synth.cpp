@@ -51,7 +51,7 @@ struct Rng {   // xoshiro256** seeded by splitmix64
 
 inline char comp(char c) { switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; } }
 
-struct Copy { uint64_t start, len; uint32_t family; bool rev; };
+struct Copy { uint64_t start, len; uint32_t family; bool rev; int32_t shared = -1; };   // shared: index of a cross-contig family, -1 = this contig only
 
 struct Contig {
     std::string name, truth, draft;
@@ -67,9 +67,12 @@ struct Rec { uint32_t pos; std::string cigar; std::string seq; uint32_t nm; bool
 
 }  // namespace
 
+struct SharedCopy { uint32_t contig; uint64_t start, len; bool rev; };
+
 struct pp_synth {
     pp_synth_params prm;
     std::vector<Contig> contigs;
+    std::vector<std::vector<SharedCopy>> shared;   // repeat families whose copies lie on different contigs (config 5: k spans GPUs)
     uint64_t total_draft = 0;
     uint64_t n_pairs = 0;
 };
@@ -108,6 +111,54 @@ void plant_repeats(Contig& c, Rng& rng, double frac) {
         if (T < 4000) break;
     }
     std::sort(c.copies.begin(), c.copies.end(), [](const Copy& a, const Copy& b) { return a.start < b.start; });
+}
+
+// Repeat families whose copies sit on DIFFERENT contigs (copy numbers 3, 2, 5, ...): reads inside them multi-map across
+// contigs, so with contig sharding their k spans GPUs (alignment.rs:283-288).
+void plant_shared(pp_synth* S, Rng& rng, double frac) {
+    const size_t nc = S->contigs.size();
+    if (nc < 2 || frac <= 0) return;
+    static const struct { uint32_t len, copies; } fam[] = {{3000, 3}, {2000, 2}, {1500, 5}, {1000, 7}};
+    uint64_t total = 0;
+    for (auto& c : S->contigs) total += c.truth.size();
+    const double scale = std::min(1.0, std::max(0.1, (double)S->contigs[0].truth.size() / 1e6));
+    const uint64_t target = (uint64_t)(frac * (double)total);
+    uint64_t placed = 0;
+    size_t next_contig = 0;
+    for (int round = 0; placed < target && round < 100000; ++round) {
+        const auto& f = fam[round % 4];
+        const uint64_t len = std::max<uint64_t>(200, (uint64_t)(f.len * scale));
+        const uint32_t copies = (uint32_t)std::min<size_t>(f.copies, nc);
+        std::string seg(len, 'A');
+        for (auto& ch : seg) ch = rng.base();
+        std::string rc(len, 'A');
+        for (uint64_t i = 0; i < len; ++i) rc[i] = comp(seg[len - 1 - i]);
+        std::vector<SharedCopy> fc;
+        for (uint32_t k = 0; k < copies; ++k) {
+            const uint32_t ci = (uint32_t)((next_contig + k) % nc);
+            Contig& c = S->contigs[ci];
+            const uint64_t T = c.truth.size();
+            if (len + 1000 > T) continue;
+            for (int tries = 0; tries < 200; ++tries) {
+                const uint64_t st = 200 + rng.below(T - len - 400);
+                bool clash = false;
+                for (auto& o : c.copies) if (st < o.start + o.len + 300 && o.start < st + len + 300) { clash = true; break; }
+                if (clash) continue;
+                const bool rev = (k > 0) && (rng.next() & 1);
+                c.truth.replace(st, len, rev ? rc : seg);
+                Copy cp{st, len, 0x40000000u + (uint32_t)S->shared.size(), rev};
+                cp.shared = (int32_t)S->shared.size();
+                c.copies.push_back(cp);
+                fc.push_back({ci, st, len, rev});
+                placed += len;
+                break;
+            }
+        }
+        next_contig = (next_contig + copies) % nc;
+        S->shared.push_back(std::move(fc));
+    }
+    for (auto& c : S->contigs)
+        std::sort(c.copies.begin(), c.copies.end(), [](const Copy& a, const Copy& b) { return a.start < b.start; });
 }
 
 void make_draft(Contig& c, Rng& rng, double err) {
@@ -288,8 +339,13 @@ bool generate(const pp_synth* S, int mate, const Sink& sink) {
             }
             if (!rec.ok) continue;
             const Copy* cp = containing_copy(c, ts, tlen);
-            std::vector<const Copy*> others;
-            if (cp && !clipped) for (auto& o : c.copies) if (o.family == cp->family && &o != cp) others.push_back(&o);
+            struct Other { const Contig* c; uint64_t start, len; bool rev; };
+            std::vector<Other> others;
+            if (cp && !clipped) {
+                if (cp->shared < 0) { for (auto& o : c.copies) if (o.family == cp->family && &o != cp) others.push_back({&c, o.start, o.len, o.rev}); }
+                else for (auto& o : S->shared[(size_t)cp->shared])
+                    if (o.contig != ci || o.start != cp->start) others.push_back({&S->contigs[o.contig], o.start, o.len, o.rev});
+            }
             n = snprintf(line, sizeof line, "\t%d\t%s\t%u\t%d\t", rev ? 16 : 0, c.name.c_str(), rec.pos + 1, others.empty() ? 60 : 0);
             out += qname; out.append(line, n); out += rec.cigar; out += "\t*\t0\t0\t"; out += rec.seq; out += '\t';
             out.append(qual.data(), rec.seq.size());
@@ -297,16 +353,16 @@ bool generate(const pp_synth* S, int mate, const Sink& sink) {
             out.append(line, n);
             // secondaries: the same read against the other copies of the repeat family
             const uint64_t off = cp ? ts - cp->start : 0;
-            for (const Copy* o : others) {
-                const bool flip = o->rev != cp->rev;
+            for (const Other& o : others) {
+                const bool flip = o.rev != cp->rev;
                 uint64_t ts2;
                 const std::vector<Col>* c2 = &cl;
-                if (!flip) ts2 = o->start + off;
-                else { ts2 = o->start + (o->len - off - tlen); revcomp_cols(cl, rcols); c2 = &rcols; }
-                align_cols(c, ts2, *c2, 0, rec);
+                if (!flip) ts2 = o.start + off;
+                else { ts2 = o.start + (o.len - off - tlen); revcomp_cols(cl, rcols); c2 = &rcols; }
+                align_cols(*o.c, ts2, *c2, 0, rec);
                 if (!rec.ok) continue;
                 const bool rev2 = rev != flip;
-                n = snprintf(line, sizeof line, "\t%d\t%s\t%u\t0\t", 256 | (rev2 ? 16 : 0), c.name.c_str(), rec.pos + 1);
+                n = snprintf(line, sizeof line, "\t%d\t%s\t%u\t0\t", 256 | (rev2 ? 16 : 0), o.c->name.c_str(), rec.pos + 1);
                 out += qname; out.append(line, n); out += rec.cigar;
                 n = snprintf(line, sizeof line, "\t*\t0\t0\t*\t*\tNM:i:%u\tAS:i:%d\n", rec.nm, (int)rec.seq.size() - 5 * (int)rec.nm);
                 out.append(line, n);
@@ -320,25 +376,35 @@ bool generate(const pp_synth* S, int mate, const Sink& sink) {
 
 }  // namespace
 
-extern "C" pp_synth* pp_synth_create(const pp_synth_params* prm) {
+// cross_contig_fraction = 0 gives exactly pp_synth_create's data (every contig keeps its own RNG stream).
+extern "C" pp_synth* pp_synth_create_shared(const pp_synth_params* prm, double cross_contig_fraction) {
     if (!prm || prm->n_contigs == 0 || prm->contig_len < 2000 || prm->read_len < 30 || prm->read_len > 1000) return nullptr;
     pp_synth* S = new pp_synth();
     S->prm = *prm;
+    std::vector<Rng> rngs;
     for (uint32_t ci = 0; ci < prm->n_contigs; ++ci) {
-        Rng rng(prm->seed * 1000003ull + 0xB2000001ull + ci);
+        rngs.emplace_back(prm->seed * 1000003ull + 0xB2000001ull + ci);
         Contig c;
         c.name = "contig_" + std::to_string(ci + 1);
         c.truth.resize(prm->contig_len);
-        for (auto& ch : c.truth) ch = rng.base();
-        plant_repeats(c, rng, prm->repeat_fraction);
-        make_draft(c, rng, prm->draft_error_rate);
-        S->total_draft += c.draft.size();
+        for (auto& ch : c.truth) ch = rngs[ci].base();
+        plant_repeats(c, rngs[ci], prm->repeat_fraction);
         S->contigs.push_back(std::move(c));
+    }
+    if (cross_contig_fraction > 0) {
+        Rng srng(prm->seed * 7919ull + 0xC5C5C5C5ull);
+        plant_shared(S, srng, cross_contig_fraction);
+    }
+    for (uint32_t ci = 0; ci < prm->n_contigs; ++ci) {
+        make_draft(S->contigs[ci], rngs[ci], prm->draft_error_rate);
+        S->total_draft += S->contigs[ci].draft.size();
     }
     S->n_pairs = (uint64_t)(prm->depth * (double)S->total_draft / (2.0 * prm->read_len));
     if (S->n_pairs == 0) S->n_pairs = 1;
     return S;
 }
+
+extern "C" pp_synth* pp_synth_create(const pp_synth_params* prm) { return pp_synth_create_shared(prm, 0.0); }
 
 extern "C" void pp_synth_free(pp_synth* s) { delete s; }
 extern "C" uint64_t pp_synth_total_bp(const pp_synth* s) { return s ? s->total_draft : 0; }

@@ -30,6 +30,7 @@
 #include <sys/statvfs.h>
 #include <unistd.h>
 
+#include <cerrno>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -639,8 +640,9 @@ static int ring_ready(pp_ctx* ctx, TokState* T) {
 // Starts streaming `path` into the next text buffer on a background thread.  PP_OK, PP_TOK_HOST (not a plain readable
 // file) or an error.
 static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path, bool strip) {
-    const int fd = open(path, O_RDONLY);
     struct stat sb;
+    if (stat(path, &sb) != 0 || !S_ISREG(sb.st_mode)) return PP_TOK_HOST;   // pipes, devices: never opened here (the host path streams them once)
+    const int fd = open(path, O_RDONLY);
     if (fd < 0 || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
         if (fd >= 0) close(fd);
         return PP_TOK_HOST;
@@ -1016,6 +1018,40 @@ static int download_file(int device, TokState* T, const uint8_t* src, int fd, ui
     return err == 1 ? PP_ERR_IO : err == 2 ? PP_ERR_CUDA : PP_OK;
 }
 
+// The same bytes to a descriptor that only takes sequential writes (pipe, FIFO, character device): one thread, two pinned slots,
+// the copy of slice i+1 in flight while slice i is written.  PP_OK / PP_ERR_IO / PP_ERR_CUDA.
+static int download_stream(int device, TokState* T, const uint8_t* src, int fd, uint64_t n, int* cuda_err) {
+    if (cudaSetDevice(device) != cudaSuccess) return PP_ERR_CUDA;
+    const uint64_t n_slices = (n + TK_SLOT - 1) / TK_SLOT;
+    auto put_all = [&](const uint8_t* p, uint64_t len) {
+        uint64_t put = 0;
+        while (put < len) {
+            const ssize_t g = write(fd, p + put, (size_t)(len - put));
+            if (g < 0 && errno == EINTR) continue;
+            if (g <= 0) return false;
+            put += (uint64_t)g;
+        }
+        return true;
+    };
+    uint64_t prev_len = 0;
+    for (uint64_t sl = 0; sl <= n_slices; ++sl) {
+        const int slot = (int)(sl & 1);
+        if (sl < n_slices) {
+            const uint64_t o = sl * TK_SLOT, len = std::min<uint64_t>(TK_SLOT, n - o);
+            cudaError_t e = cudaMemcpyAsync(T->pin[0][slot], src + o, (size_t)len, cudaMemcpyDeviceToHost, T->rstream[0]);
+            if (e == cudaSuccess) e = cudaEventRecord(T->rev[0][slot], T->rstream[0]);
+            if (e != cudaSuccess) { *cuda_err = (int)e; return PP_ERR_CUDA; }
+        }
+        if (sl > 0) {
+            const cudaError_t e = cudaEventSynchronize(T->rev[0][slot ^ 1]);
+            if (e != cudaSuccess) { *cuda_err = (int)e; return PP_ERR_CUDA; }
+            if (!put_all(T->pin[0][slot ^ 1], prev_len)) return PP_ERR_IO;
+        }
+        if (sl < n_slices) prev_len = std::min<uint64_t>(TK_SLOT, n - sl * TK_SLOT);
+    }
+    return PP_OK;
+}
+
 // Line index + quick parse of one file whose text is on the device.  Fills fd; PP_OK / PP_TOK_HOST / error.
 static int ftok_lines(pp_ctx* ctx, TokState* T, int which, const uint8_t* text, uint64_t n, bool unterminated, DevBuf& lines, DevBuf& tmp, FStatus* d_st,
                       FileDev* fd, uint32_t* launches) {
@@ -1200,20 +1236,28 @@ int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const 
         CK(cudaGetLastError());
         launches += 4;
         lap(4);
-        const int ofd = open(outs[k], O_RDWR | O_CREAT | O_TRUNC, 0666);
+        // A regular file gets its final size up front and is filled in parallel (shared mapping / pwrite at offsets).  Anything
+        // else - a FIFO, >(gzip ...), /dev/stdout into a pipe, /dev/null - cannot be truncated or written at offsets: it is
+        // streamed in order with write(), like the reference's BufWriter (filter.rs:296-349).
+        struct stat osb;
+        const bool special = stat(outs[k], &osb) == 0 && !S_ISREG(osb.st_mode);
+        const int ofd = special ? open(outs[k], O_WRONLY) : open(outs[k], O_RDWR | O_CREAT | O_TRUNC, 0666);
         if (ofd < 0) return ctx->fail(PP_ERR_IO, std::string("unable to write alignments to \"") + outs[k] + "\"");
         const auto t0 = std::chrono::steady_clock::now();
         int cuda_err = 0;
         int wrc = PP_OK;
-        if (out_n) {
-            if (ftruncate(ofd, (off_t)out_n) != 0) wrc = PP_ERR_IO;
+        bool stream_out = special;
+        if (out_n && !stream_out && ftruncate(ofd, (off_t)out_n) != 0) stream_out = true;
+        if (out_n && stream_out) {
+            wrc = download_stream(ctx->device, T, B.out.as<uint8_t>(), ofd, out_n, &cuda_err);
+        } else if (out_n) {
             // Stores into a mapping cannot report "no space left" (they raise SIGBUS), so the mapping is only used when the
             // file system has room to spare; otherwise pwrite() reports the error like the reference does (filter.rs:307-311).
             struct statvfs vfs;
             const bool roomy = fstatvfs(ofd, &vfs) == 0 && (uint64_t)vfs.f_bavail * (uint64_t)vfs.f_frsize > 2 * out_n + (64ull << 20);
-            void* map = (wrc == PP_OK && roomy) ? mmap(nullptr, (size_t)out_n, PROT_READ | PROT_WRITE, MAP_SHARED, ofd, 0) : MAP_FAILED;
+            void* map = roomy ? mmap(nullptr, (size_t)out_n, PROT_READ | PROT_WRITE, MAP_SHARED, ofd, 0) : MAP_FAILED;
             if (map == MAP_FAILED) map = nullptr;
-            if (wrc == PP_OK) wrc = download_file(ctx->device, T, B.out.as<uint8_t>(), ofd, (uint8_t*)map, out_n, &cuda_err);
+            wrc = download_file(ctx->device, T, B.out.as<uint8_t>(), ofd, (uint8_t*)map, out_n, &cuda_err);
             if (map && munmap(map, (size_t)out_n) != 0 && wrc == PP_OK) wrc = PP_ERR_IO;
         }
         if (close(ofd) != 0 && wrc == PP_OK) wrc = PP_ERR_IO;

@@ -198,3 +198,34 @@ def test_device_text_path_same_name_in_both_columns(ctx, oracle, tmp_path):
     i1, i2 = tmp_path / "i1.sam", tmp_path / "i2.sam"
     i1.write_text(more1 + "\n".join(rows1) + "\n"); i2.write_text(more2 + "\n".join(rows2) + "\n")
     run_both(ctx, oracle, i1, i2, tmp_path)
+
+
+def test_filter_to_pipes_and_devices(ctx, oracle, tmp_path):
+    """Outputs that are not regular files (the reference streams through a BufWriter, filter.rs:296-349): a named FIFO read
+    by another thread, and /dev/null.  The device text path cannot truncate or write those at offsets; it streams in order."""
+    import os
+    import threading
+    syn = api.Synth(seed=12, contig_len=40_000, depth=40)
+    fa, sams = syn.write(tmp_path)
+    exp = oracle.filter(sams[0], sams[1])
+    fifo = tmp_path / "out1.fifo"
+    os.mkfifo(fifo)
+    got = {}
+
+    def reader():
+        with open(fifo, "rb") as f:
+            got["out1"] = f.read()
+    t = threading.Thread(target=reader)
+    t.start()
+    ctx.set_parser(0)
+    ctx.filter_files(sams[0], sams[1], fifo, "/dev/null")
+    t.join(timeout=60)
+    assert not t.is_alive()
+    assert got["out1"] == exp["out1"]
+    # and the other way round, second output through the pipe
+    t = threading.Thread(target=reader)
+    t.start()
+    ctx.filter_files(sams[1], sams[0], fifo, tmp_path / "plain.sam")
+    t.join(timeout=60)
+    assert got["out1"] == exp["out2"]
+    assert open(tmp_path / "plain.sam", "rb").read() == exp["out1"]

@@ -174,7 +174,6 @@ def test_device_error_messages(ctx, oracle, tmp_path):
     assert_parity(ctx, oracle, fa, [s])
 
 
-@pytest.mark.skipif(not os.environ.get("PP_FULL"), reason="set PP_FULL=1 for the BASELINE-size runs")
 def test_full_size_properties(ctx):
     """BASELINE config 2 size (5 Mbp x 100x): size-independent properties instead of the oracle:
     determinism across runs and agreement of the host-buffer and device-resident entry points."""
@@ -273,10 +272,52 @@ def test_debug_tsv_synth(ctx, oracle, tmp_path):
     assert dbg.read_bytes() == exp["debug_tsv"]
 
 
-@pytest.mark.skipif(not os.environ.get("PP_FULL"), reason="set PP_FULL=1 for the BASELINE-size runs")
 def test_depth_1000_parity(ctx, oracle, tmp_path):
     """BASELINE config 4 in miniature (1000x depth: counter / atomic stress, long fix-up lists), against the oracle."""
     syn = api.Synth(seed=4, contig_len=200_000, depth=1000)
     fa, sams = syn.write(tmp_path)
     exp = oracle.polish(fa, sams)
     assert ctx.polish_files(fa, sams) == exp["fasta"]
+
+
+def test_cli_clap_argument_forms_and_log_numbers(oracle, tmp_path):
+    """clap accepts --name=value, -m5 and `--`; the stderr log carries the reference's per-contig numbers
+    (polish.rs:206-227: mean read depth, zero-depth bp, changed positions, estimated accuracy)."""
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "polypolish")
+    syn = api.Synth(seed=8, n_contigs=2, contig_len=30_000, depth=40)
+    fa, sams = syn.write(tmp_path)
+    exp = oracle.polish(fa, sams, max_errors=5, min_depth=4, fraction_invalid=0.1)
+    r = subprocess.run([exe, "polish", "-m5", "--min_depth=4", "-i=0.1", "--", fa] + sams, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == exp["fasta"]
+    log = r.stderr.decode()
+    depths = re.findall(r"mean read depth: ([0-9.]+)x", log)
+    lens = [len(s) for _, _, s in pp.load_fasta(fa).records()]
+    assert depths == ["%.1f" % (exp["total_depth"][i] / lens[i]) for i in range(2)]
+    changed = [int(x.replace(",", "")) for x in re.findall(r"([0-9,]+) positions? changed", log)]
+    assert changed == exp["changed"]
+    zero = [int(x.replace(",", "")) for x in re.findall(r"([0-9,]+) bp ha(?:s|ve) a depth of zero", log)]
+    assert zero == exp["zero_depth"]
+    assert len(re.findall(r"estimated pre-polishing sequence accuracy: [0-9.]+% \(Q[0-9.]+\)", log)) == 2
+    # filter: --low=..., --high=...
+    o1, o2 = tmp_path / "f1.sam", tmp_path / "f2.sam"
+    r = subprocess.run([exe, "filter", "--in1=" + sams[0], "--in2", sams[1], "--out1", str(o1), "--out2=" + str(o2), "--low=1", "--high=99"],
+                       capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    ef = oracle.filter(sams[0], sams[1], low=1.0, high=99.0)
+    assert open(o1, "rb").read() == ef["out1"] and open(o2, "rb").read() == ef["out2"]
+
+
+def test_total_depth_statistic(ctx, oracle, tmp_path):
+    """pp_polish_result.total_depth: the per-position f64 depths are the reference's; their per-contig sum agrees with the
+    oracle's sequential sum to rounding (multi-mapped reads make the depths fractional)."""
+    case = fuzzgen.make_case(303, n_contigs=2, contig_len=(200, 400), depth=(150, 300), multimap=0.8, opts=dict(careful=False))
+    fa, sams = case.write(tmp_path)
+    exp = oracle.polish(fa, sams, **case.opts)
+    f = pp.load_fasta(fa)
+    p = pp.pack_sams(f, sams)
+    r = ctx.polish_packed(f.view, p.view, **case.opts)
+    for got, want in zip(r["total_depth"], exp["total_depth"]):
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want))

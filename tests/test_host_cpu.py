@@ -230,3 +230,28 @@ def test_parallel_pack_errors(oracle, tmp_path, sam):
         p.add_file(s)
         p.finish()
     assert ei.value.msg == eo.value.msg
+
+
+def test_cli_help_and_version_need_no_gpu():
+    """`polypolish -h`, `polypolish polish -h`, `polypolish filter -h`, `-V` (main.rs:23-109): clap-style help with every
+    reference option and its default; none of them touches CUDA."""
+    import subprocess
+    import __graft_entry__ as g
+    g.build()
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "polypolish")
+    top = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert top.returncode == 0 and "Usage: polypolish <COMMAND>" in top.stdout and "filter" in top.stdout and "polish" in top.stdout
+    ph = subprocess.run([exe, "polish", "--help"], capture_output=True, text=True)
+    assert ph.returncode == 0
+    for frag in ["Usage: polypolish polish [OPTIONS] <ASSEMBLY> [SAM]...", "-i, --fraction_invalid <FRACTION_INVALID>", "[default: 0.2]",
+                 "-v, --fraction_valid <FRACTION_VALID>", "[default: 0.5]", "-m, --max_errors <MAX_ERRORS>", "[default: 10]",
+                 "-d, --min_depth <MIN_DEPTH>", "[default: 5]", "--careful", "--debug <DEBUG>"]:
+        assert frag in ph.stdout, frag
+    fh = subprocess.run([exe, "filter", "-h"], capture_output=True, text=True)
+    assert fh.returncode == 0
+    for frag in ["--in1 <IN1>", "--in2 <IN2>", "--out1 <OUT1>", "--out2 <OUT2>", "--orientation <ORIENTATION>", "[default: auto]",
+                 "--low <LOW>", "[default: 0.1]", "--high <HIGH>", "[default: 99.9]"]:
+        assert frag in fh.stdout, frag
+    assert subprocess.run([exe, "-V"], capture_output=True, text=True).stdout.strip() == "Polypolish v0.6.1"
+    bad = subprocess.run([exe, "polish", "--nope"], capture_output=True, text=True)
+    assert bad.returncode == 2 and "unexpected argument '--nope'" in bad.stderr
