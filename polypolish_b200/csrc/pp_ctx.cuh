@@ -29,15 +29,13 @@ struct DevBuf {
 };
 
 enum { B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL,
-       B_DRAFT, B_CTGOFF, B_NIB, B_ZEROPOOL, B_DEPTHFIX, B_RECGN, B_RECK, B_NODES, B_FIXKEY2, B_FIXVAL2, B_FIXRUN, B_CUBTMP, B_OUT,
-       B_OUTOFF, B_DEBUG, B_AGG1, B_AGGC, B_RES, B_RECAT, B_CHUNKDELTA, B_PARAMS, B_SCRATCH, B_SCRATCH2, B_CUBTMP2,
+       B_DRAFT, B_CTGOFF, B_ZEROPOOL, B_RECS, B_KEY, B_VAL, B_SKEY, B_SVAL, B_BINSTART, B_NK, B_NODES, B_CUBTMP, B_OUT,
+       B_OUTOFF, B_DEBUG, B_RES, B_RECAT, B_CHUNKDELTA, B_PARAMS, B_SCRATCH, B_SCRATCH2,
        B_TOKLINE, B_TOKTMP, B_TOKNAMES, B_COUNT };
 
 struct pp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side = nullptr;          // side stream: work that only depends on the scatter runs beside the fix-up stage
-    cudaEvent_t side_ev[2] = {};
     std::string err;
     DevBuf b[B_COUNT];
     cudaEvent_t ev[PP_N_STAGES + 4] = {};
@@ -48,10 +46,10 @@ struct pp_ctx {
     uint64_t n_aln = 0, n_reads = 0, n_ops = 0, seq_bytes = 0, G = 0;
     uint32_t n_contigs = 0, seq_bits = 4;
     int sm_count = 148;
-    size_t l2_persist_max = 0, l2_window_max = 0;
     uint32_t launches = 0;
     // sizes that adapt when a call overflows them (kept across calls on the same dataset)
-    uint32_t node_cap = 0, fix_cap = 0;
+    uint32_t node_cap = 0;
+    bool tile_attr_set = false;           // k_tile's dynamic shared memory opt-in done
     uint64_t out_cap = 0;
     bool global_k = false;
     bool debug_on = false, have_debug = false;
