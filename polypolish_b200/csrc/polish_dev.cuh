@@ -112,7 +112,7 @@ struct DevData {                     // everything the kernels read, by value
     uint32_t *key, *val;             // [n_aln] k_prep's (bin, alignment) pairs, SAM order
     const uint32_t* sval;            // [n_aln] alignment indices sorted by bin (stable)
     uint32_t* bin_start;             // [n_bins + 3] first sorted slot of every bin
-    uint32_t* nk;                    // [n_aln] kept entries of the alignment in sorted slot i
+    uint4* wrec;                     // [n_aln] per sorted slot: (alignment, first position, kept entries, k) - what the ordered depth walk reads
     uint32_t* oth_head;              // [G] 1 + index of the first OthNode of the position, 0 = none
     OthNode* nodes;
     uint32_t node_cap;
@@ -837,53 +837,62 @@ __device__ __forceinline__ TileRec load_rec(const DevData& d, uint32_t aln) {
     return r;
 }
 
-// The ordered depth of one 128-position sub-tile (pileup.rs:64 in SAM order): the alignments that can cover it live in
-// `nrun` runs of the sorted list (the bins that can reach it + the long list), each in SAM order; one warp merges them by
-// alignment index, window of 32 entries per run in registers, and adds 1/k with round-to-nearest in that order.
+// The ordered depth of one 128-position sub-tile (pileup.rs:64 in SAM order).  The alignments that can cover it live in up to
+// DW_RUNS runs of the sorted list - the bins that can reach it and the long list - each of them in SAM order.  One warp merges
+// the runs by alignment index: a window of 32 slots per run sits in registers (one coalesced 16-byte load per lane, the next
+// window prefetched), entries that do not overlap the sub-tile are skipped through a ballot mask, and 1/k is added with
+// round-to-nearest in merged (= SAM) order, four consecutive positions per lane.
 #define DW_RUNS 4
+#if defined(PP_EMULATE)
+#define PP_PREFETCH_L1(p) ((void)(p))
+#else
+#define PP_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#endif
 template <int BITS>
 __device__ void depth_walk(const DevData& d, TileShared& sh, uint32_t P0, uint32_t sub, uint32_t lb, uint32_t long_lo, uint32_t long_hi) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t s = P0 + sub * PP_SUB;
     const uint32_t bin = s >> PP_BIN_SHIFT;
-    uint32_t cur[DW_RUNS], end[DW_RUNS], wb[DW_RUNS], head[DW_RUNS];
+    uint32_t wb[DW_RUNS], end[DW_RUNS], mask[DW_RUNS], head[DW_RUNS];
     uint32_t w_aln[DW_RUNS], w_start[DW_RUNS], w_len[DW_RUNS];
     double w_inv[DW_RUNS];
+    // window of run r at slot wb[r]; windows without an overlapping entry are skipped
+    auto load_window = [&](int r) {
+        for (;;) {
+            if (wb[r] >= end[r]) { mask[r] = 0; head[r] = NONE32; return; }
+            const uint32_t slot = wb[r] + lane;
+            uint4 q = make_uint4(NONE32, 0, 0, 1);
+            if (slot < end[r]) {
+                q = d.wrec[slot];
+                if (slot + 32 < end[r]) PP_PREFETCH_L1(d.wrec + slot + 32);
+            }
+            uint32_t len = q.z;
+            if (r == DW_RUNS - 1 && slot < end[r]) {            // long list: this CTA walked the alignment only if it can touch the tile
+                const TileRec rec = load_rec<BITS>(d, d.sval[slot]);
+                const unsigned long long e_end = (unsigned long long)rec.gstart + rec.E;
+                q.x = d.sval[slot]; q.y = rec.gstart; q.w = rec.k;
+                len = (e_end > P0 && rec.gstart < P0 + (uint32_t)TL_T) ? q.z : 0u;
+            }
+            const bool ov = slot < end[r] && len != 0 && q.y < s + PP_SUB && q.y + len > s;
+            const uint32_t m = __ballot_sync(0xffffffffu, ov);
+            w_aln[r] = q.x; w_start[r] = q.y; w_len[r] = len;
+            w_inv[r] = __ddiv_rn(1.0, (double)q.w);             // 1.0 / good_alignments.len() as f64 (alignment.rs:288)
+            if (m) { mask[r] = m; head[r] = __shfl_sync(0xffffffffu, w_aln[r], __ffs((int)m) - 1); return; }
+            wb[r] += 32;
+        }
+    };
 #pragma unroll
     for (int r = 0; r < DW_RUNS; ++r) {
-        cur[r] = end[r] = 0;
+        wb[r] = end[r] = 0;
         if (r < DW_RUNS - 1) {
             if ((uint32_t)r <= lb && bin + (uint32_t)r >= lb) {
                 const uint32_t b = bin + (uint32_t)r - lb;
-                cur[r] = d.bin_start[b]; end[r] = d.bin_start[b + 1];
+                wb[r] = d.bin_start[b]; end[r] = d.bin_start[b + 1];
             }
-        } else { cur[r] = long_lo; end[r] = long_hi; }
-        wb[r] = cur[r];
+        } else { wb[r] = long_lo; end[r] = long_hi; }
         w_aln[r] = NONE32; w_start[r] = 0; w_len[r] = 0; w_inv[r] = 0.0;
-        head[r] = NONE32;
+        load_window(r);
     }
-    // (re)fill the window of run r from slot wb[r]
-    auto fill = [&](int r) {
-        const uint32_t slot = wb[r] + lane;
-        uint32_t aln = NONE32, st = 0, ln = 0;
-        double inv = 0.0;
-        if (slot < end[r]) {
-            aln = d.sval[slot];
-            const TileRec rec = load_rec<BITS>(d, aln);
-            st = rec.gstart;
-            bool usable = true;
-            if (r == DW_RUNS - 1) {                             // long list: this CTA walked it only if it can touch the tile
-                const unsigned long long e_end = (unsigned long long)rec.gstart + rec.E;
-                usable = e_end > P0 && rec.gstart < P0 + (uint32_t)TL_T;
-            }
-            ln = usable ? d.nk[slot] : 0u;
-            inv = __ddiv_rn(1.0, (double)rec.k);                // 1.0 / good_alignments.len() as f64 (alignment.rs:288)
-        }
-        w_aln[r] = aln; w_start[r] = st; w_len[r] = ln; w_inv[r] = inv;
-    };
-#pragma unroll
-    for (int r = 0; r < DW_RUNS; ++r)
-        if (cur[r] < end[r]) { fill(r); head[r] = __shfl_sync(0xffffffffu, w_aln[r], 0); }
     const uint32_t p = s + lane * 4;
     double dep0 = 0.0, dep1 = 0.0, dep2 = 0.0, dep3 = 0.0;
     for (;;) {
@@ -897,16 +906,13 @@ __device__ void depth_walk(const DevData& d, TileShared& sh, uint32_t P0, uint32
 #pragma unroll
         for (int r = 0; r < DW_RUNS; ++r) {
             if (r == rb) {                                      // warp-uniform
-                const int src = (int)(cur[r] - wb[r]);
+                const int src = __ffs((int)mask[r]) - 1;
                 st = __shfl_sync(0xffffffffu, w_start[r], src);
                 ln = __shfl_sync(0xffffffffu, w_len[r], src);
                 inv = __shfl_sync(0xffffffffu, w_inv[r], src);
-                cur[r]++;
-                if (cur[r] >= end[r]) head[r] = NONE32;
-                else {
-                    if (cur[r] - wb[r] == 32) { wb[r] = cur[r]; fill(r); }
-                    head[r] = __shfl_sync(0xffffffffu, w_aln[r], (int)(cur[r] - wb[r]));
-                }
+                mask[r] &= mask[r] - 1;
+                if (mask[r]) head[r] = __shfl_sync(0xffffffffu, w_aln[r], __ffs((int)mask[r]) - 1);
+                else { wb[r] += 32; load_window(r); }
             }
         }
         const uint32_t off = p - st;                            // position p + q is covered iff (off + q) < length (unsigned)
@@ -965,18 +971,33 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
         const uint32_t b0 = P0 >> PP_BIN_SHIFT;
         const uint32_t lo = d.bin_start[b0 >= lb ? b0 - lb : 0u];
         const uint32_t hi = d.bin_start[min(b0 + (uint32_t)(TL_T / PP_BIN), d.n_bins)];
-        for (uint32_t base = lo; base < hi; base += TL_THREADS) {
-            const uint32_t i = base + tid;
-            if (i < hi) {
-                const uint32_t aln = d.sval[i];
-                const TileRec r = load_rec<BITS>(d, aln);
-                uint32_t nk = NONE32;
-                if (BITS == 4 && (r.flags & TR_FAST)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), r, aln);
-                if (nk == NONE32) {
-                    const uint32_t q = atomicAdd(&sh.qn, 1u);
-                    if (q < TL_QCAP) sh.queue[q] = i;
-                    else { nk = general_walk<BITS>(S, r, aln); d.nk[i] = nk; }
-                } else d.nk[i] = nk;
+        {
+            // software pipeline over the gathers: the record of the next round and the index of the round after it are in
+            // flight while this round's alignment is walked
+            uint32_t aln_a = (lo + tid < hi) ? d.sval[lo + tid] : 0u;
+            uint32_t aln_b = (lo + tid + TL_THREADS < hi) ? d.sval[lo + tid + TL_THREADS] : 0u;
+            TileRec rec_a = load_rec<BITS>(d, aln_a);
+            for (uint32_t base = lo; base < hi; base += TL_THREADS) {
+                const uint32_t i = base + tid;
+                const TileRec rec_b = load_rec<BITS>(d, aln_b);                       // (slot 0's record when there is no next round)
+                const uint32_t aln_c = (i + 2 * TL_THREADS < hi) ? d.sval[i + 2 * TL_THREADS] : 0u;
+                if (i < hi) {
+                    const TileRec& r = rec_a;
+                    const uint32_t aln = aln_a;
+                    uint32_t nk = NONE32;
+                    if (BITS == 4 && (r.flags & TR_FAST)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), r, aln);
+                    if (nk == NONE32) {
+                        const uint32_t q = atomicAdd(&sh.qn, 1u);
+                        if (q < TL_QCAP) sh.queue[q] = i;
+                        else { nk = general_walk<BITS>(S, r, aln); d.wrec[i] = make_uint4(aln, r.gstart, nk, r.k); }
+                    } else d.wrec[i] = make_uint4(aln, r.gstart, nk, r.k);
+                }
+                if (BITS == 4 && i + TL_THREADS < hi && (rec_b.flags & TR_FAST)) {     // the next read's bases towards L2 / L1
+                    const uint8_t* nsp = d.seq_pool + (size_t)rec_b.seq_off * 16;
+                    PP_PREFETCH_L1(nsp);
+                    PP_PREFETCH_L1(nsp + 64);
+                }
+                rec_a = rec_b; aln_a = aln_b; aln_b = aln_c;
             }
         }
         __syncthreads();
@@ -987,14 +1008,14 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 const uint32_t i = sh.queue[q];
                 const uint32_t aln = d.sval[i];
                 const TileRec r = load_rec<BITS>(d, aln);
-                d.nk[i] = general_walk<BITS>(S, r, aln);
+                d.wrec[i] = make_uint4(aln, r.gstart, general_walk<BITS>(S, r, aln), r.k);
             }
             // the long list: alignments of more than TL_LONG_E entries, looked at by every tile
             for (uint32_t i = long_lo + tid; i < long_hi; i += TL_THREADS) {
                 const uint32_t aln = d.sval[i];
                 const TileRec r = load_rec<BITS>(d, aln);
                 const unsigned long long e_end = (unsigned long long)r.gstart + r.E;
-                if (e_end > P0 && r.gstart < P0 + (uint32_t)TL_T) d.nk[i] = general_walk<BITS>(S, r, aln);
+                if (e_end > P0 && r.gstart < P0 + (uint32_t)TL_T) d.wrec[i] = make_uint4(aln, r.gstart, general_walk<BITS>(S, r, aln), r.k);
             }
         }
         __syncthreads();
@@ -1086,9 +1107,20 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             n_changed += (po[i].packed >> 24) & 1u;
             tlen += po[i].packed & 0xFFFFu;
         }
-        if (n_changed) atomicAdd(&vp.changed[ctg], (unsigned long long)n_changed);
-        if (n_zero) atomicAdd(&vp.zero_depth[ctg], (unsigned long long)n_zero);
-        if (tdepth != 0.0) atomicAdd(&vp.total_depth[ctg], tdepth);
+        {   // per-contig statistics: one atomic per warp when the whole warp sits in one contig (nearly always)
+            const uint32_t ctg0 = __shfl_sync(0xffffffffu, ctg, 0);
+            if (__ballot_sync(0xffffffffu, ctg != ctg0) == 0u) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    n_changed += __shfl_down_sync(0xffffffffu, n_changed, o);
+                    n_zero += __shfl_down_sync(0xffffffffu, n_zero, o);
+                    tdepth += __shfl_down_sync(0xffffffffu, tdepth, o);
+                }
+                if (lane != 0) { n_changed = n_zero = 0; tdepth = 0.0; }
+            }
+            if (n_changed) atomicAdd(&vp.changed[ctg], (unsigned long long)n_changed);
+            if (n_zero) atomicAdd(&vp.zero_depth[ctg], (unsigned long long)n_zero);
+            if (tdepth != 0.0) atomicAdd(&vp.total_depth[ctg], tdepth);
+        }
         // hand the verdicts to k_compact: 2 bytes per position + this tile's length delta
         {
             uint32_t w2[TL_PER_THREAD / 2];

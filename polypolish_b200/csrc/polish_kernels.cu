@@ -175,7 +175,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
     CK(ctx->b[B_RECS].ensure(na * sizeof(TileRec)));
     CK(ctx->b[B_KEY].ensure(na * 4)); CK(ctx->b[B_VAL].ensure(na * 4));
     CK(ctx->b[B_SKEY].ensure(na * 4)); CK(ctx->b[B_SVAL].ensure(na * 4));
-    CK(ctx->b[B_NK].ensure(na * 4));
+    CK(ctx->b[B_NK].ensure(na * 16));
     CK(ctx->b[B_BINSTART].ensure(((size_t)n_bins + 4) * 4));
     CK(ctx->b[B_OUTOFF].ensure(((size_t)ctx->n_contigs + 1) * 8));
     CK(ctx->b[B_RES].ensure(padG * 2)); CK(ctx->b[B_RECAT].ensure((G + 1) * 4)); CK(ctx->b[B_CHUNKDELTA].ensure((size_t)n_tiles * 8));
@@ -221,7 +221,7 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         d.n_bins = n_bins; d.n_tiles = n_tiles;
         d.k = (uint32_t*)(zp + o_k);
         d.recs = ctx->b[B_RECS].as<TileRec>(); d.key = ctx->b[B_KEY].as<uint32_t>(); d.val = ctx->b[B_VAL].as<uint32_t>();
-        d.sval = ctx->b[B_SVAL].as<uint32_t>(); d.bin_start = ctx->b[B_BINSTART].as<uint32_t>(); d.nk = ctx->b[B_NK].as<uint32_t>();
+        d.sval = ctx->b[B_SVAL].as<uint32_t>(); d.bin_start = ctx->b[B_BINSTART].as<uint32_t>(); d.wrec = ctx->b[B_NK].as<uint4>();
         d.oth_head = (uint32_t*)(zp + o_head); d.nodes = ctx->b[B_NODES].as<OthNode>(); d.node_cap = node_cap;
         d.prm = ctx->b[B_PARAMS].as<DevParams>();
         d.st = (DevStatus*)(zp + o_status);
