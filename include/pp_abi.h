@@ -293,6 +293,10 @@ int pp_dataset_download(pp_ctx* ctx, const pp_alignments* into);
  * in SAM order; reads that also map to another shard's contigs keep their k through PP_FLAG_GHOST records. */
 typedef struct pp_shards pp_shards;
 pp_shards* pp_shards_build(const pp_contigs* contigs, const pp_alignments* alns, uint32_t n_shards);
+/* the same with the contig -> shard assignment given by the caller (NULL = the sharder's own longest-processing-time packing) and,
+ * when only_shard >= 0, only that shard built (the others stay empty): one rank of a multi-process run builds just its own. */
+pp_shards* pp_shards_build_assigned(const pp_contigs* contigs, const pp_alignments* alns, uint32_t n_shards,
+                                    const uint32_t* shard_of_contig, int32_t only_shard);
 int pp_shards_get(const pp_shards* s, uint32_t i, pp_contigs* contigs, pp_alignments* alns,
                   const uint32_t** contig_map /* original index of each shard contig */, uint64_t* n_home);
 void pp_shards_free(pp_shards* s);
@@ -338,6 +342,11 @@ pp_synth* pp_synth_create(const pp_synth_params* prm);
 /* the same, plus repeat families (3, 2, 5, 7 copies) whose copies lie on DIFFERENT contigs, covering `cross_contig_fraction`
  * of the assembly: reads in them multi-map across contigs, so under contig sharding their k spans GPUs (BASELINE config 5). */
 pp_synth* pp_synth_create_shared(const pp_synth_params* prm, double cross_contig_fraction);
+/* cross-contig data sets only: restrict the generated reads to those with a record on a contig of `shard` (contig i belongs to
+ * shard_of_contig[i], or i % n_shards when NULL); n_shards = 0 switches the restriction off.  What is emitted is, record for
+ * record, what pp_shards_build_assigned gives that shard from the whole data set - a rank of an N-GPU run can build its share of
+ * BASELINE config 5 without generating the other ranks' reads. */
+int pp_synth_set_shard_filter(pp_synth* s, uint32_t n_shards, uint32_t shard, const uint32_t* shard_of_contig);
 void pp_synth_free(pp_synth* s);
 uint64_t pp_synth_total_bp(const pp_synth* s);    /* draft bases */
 uint64_t pp_synth_n_pairs(const pp_synth* s);

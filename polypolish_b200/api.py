@@ -531,6 +531,17 @@ class Synth:
         self.total_bp = L.pp_synth_total_bp(self.h)
         self.n_pairs = L.pp_synth_n_pairs(self.h)
 
+    def set_shard_filter(self, n_shards, shard, shard_of_contig=None):
+        """Cross-contig data sets: emit only the reads with a record on a contig of `shard` (n_shards = 0: everything again)."""
+        L = lib()
+        L.pp_synth_set_shard_filter.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        arr = None
+        if shard_of_contig is not None:
+            arr = (C.c_uint32 * len(shard_of_contig))(*[int(x) for x in shard_of_contig])
+        rc = L.pp_synth_set_shard_filter(self.h, n_shards, shard, arr)
+        if rc != PP_OK:
+            raise PolypolishError(rc, "pp_synth_set_shard_filter: needs a cross-contig data set and shard < n_shards")
+
     def write(self, directory):
         """draft FASTA + one SAM per mate; returns (fasta, [sam1, sam2])."""
         d = str(directory)
@@ -581,15 +592,20 @@ class Synth:
 class Shards:
     """pp_shards_build: whole contigs per shard, alignments in SAM order, foreign records of a read as ghosts."""
 
-    def __init__(self, contigs, alns, n_shards):
+    def __init__(self, contigs, alns, n_shards, shard_of_contig=None, only_shard=-1):
         L = lib()
         L.pp_shards_build.restype = C.c_void_p
         L.pp_shards_build.argtypes = [C.POINTER(Contigs), C.POINTER(Alignments), C.c_uint32]
+        L.pp_shards_build_assigned.restype = C.c_void_p
+        L.pp_shards_build_assigned.argtypes = [C.POINTER(Contigs), C.POINTER(Alignments), C.c_uint32, C.POINTER(C.c_uint32), C.c_int32]
         L.pp_shards_free.argtypes = [C.c_void_p]
         L.pp_shards_get.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(Contigs), C.POINTER(Alignments),
                                     C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
         self.n = n_shards
-        self.h = L.pp_shards_build(C.byref(contigs), C.byref(alns), n_shards)
+        arr = None
+        if shard_of_contig is not None:
+            arr = (C.c_uint32 * len(shard_of_contig))(*[int(x) for x in shard_of_contig])
+        self.h = L.pp_shards_build_assigned(C.byref(contigs), C.byref(alns), n_shards, arr, only_shard)
         if not self.h:
             raise PolypolishError(PP_ERR_ARG, "pp_shards_build failed")
 

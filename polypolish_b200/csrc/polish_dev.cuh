@@ -38,7 +38,6 @@
 #define TL_THREADS 512
 #define TL_PER_THREAD (TL_T / TL_THREADS)
 #define TL_LONG_E 512                // alignments with more entries than this are not binned: every tile looks at the "long" list
-#define TL_QCAP 1024                 // deferred (indel-bearing / long-read) alignments per scatter round
 #define TL_FAST_LEN 192              // longest read the register-resident fast path takes
 #define PR_THREADS 256               // k_prep CTA: one alignment per thread
 #define SC_GROUP_SCAN_LIMIT 8192     // alignments of one read group a thread will scan outside its block for k
@@ -47,7 +46,7 @@
 #define VT_CHUNK (VT_THREADS * VT_ITEMS)
 #define NONE32 0xFFFFFFFFu
 static_assert(VT_CHUNK == TL_T, "k_tile hands k_compact one chunk per tile");
-static_assert(TL_T % PP_BIN == 0 && TL_T / PP_SUB <= 32, "tile = whole bins, at most 32 depth sub-tiles");
+static_assert(TL_T % PP_BIN == 0 && TL_T / PP_SUB == TL_THREADS / 32 && TL_PER_THREAD * 32 == PP_SUB, "tile = whole bins; warp w owns depth sub-tile w and votes on it");
 
 enum : unsigned {
     ERR_UNKNOWN_CONTIG = 1, ERR_SEQ_MISMATCH = 2, ERR_BAD_OP = 3, ERR_OOB = 4, ERR_NOSEQ = 5
@@ -575,6 +574,11 @@ __device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const DevParam
 #define TL_DN_HALO 32                                  // draft nibbles are staged for tile positions [-32, T + 32)
 #define TL_DN_WORDS ((TL_T + 2 * TL_DN_HALO) / 16)
 
+struct WalkStage {                                     // per warp: staging of the ordered-depth merge (depth_walk_two)
+    uint4 ent[64];                                     // start, kept entries, 1/k (two words)
+    uint32_t key[2][32];                               // alignment indices of the entries being merged, compacted, per run
+};
+
 struct TileShared {
     int cdiff[TL_T + 4];                               // cover: +1 / -1 at interval ends, after the prefix sum = cover[p]
     int mdiff[TL_T + 4];                               // the same restricted to alignments of reads with k != 1
@@ -583,11 +587,11 @@ struct TileShared {
     uint32_t oth[TL_T];                                // entries carrying any other allele (their distinct strings: the global chains)
     double depth[TL_T];                                // ordered f64 depth, valid in flagged sub-tiles
     unsigned long long dn[TL_DN_WORDS + 2];            // 4-bit draft codes, 16 per word, position -32 first
-    uint32_t queue[TL_QCAP];                           // sorted slots deferred to the general walk
+    WalkStage wstage[TL_THREADS / 32];                 // ordered-depth merge staging, one per warp
     unsigned long long s_warp[TL_THREADS / 32];
     unsigned long long s_total;
     long long s_delta[TL_THREADS / 32];
-    uint32_t qn;
+    uint32_t next;                                     // next chunk of the tile's list (phase B hands out 32 slots at a time)
     uint32_t tile;
     uint32_t subflags;                                 // sub-tiles that see k != 1 coverage
 };
@@ -754,25 +758,28 @@ __device__ uint32_t general_walk(TileCtx<BITS>& S, const TileRec& r, unsigned lo
     return nkept;
 }
 
-// The fast path: a 4-bit read of at most 192 bases whose CIGAR is one M / = run.  The read sits in 12 registers (six
-// 16-byte loads; a reverse-strand read is loaded back to front and bit-reversed, which is its reverse complement), the
-// draft comes from the tile's shared-memory copy, 16 bases per XOR.  Returns kept entries, or NONE32 = "take the general walk"
-// (a homopolymer tail of 32+ bases).
+// The fast path: a 4-bit read of at most 192 bases whose CIGAR is one M / = run.  The read sits in 24 registers (six
+// 16-byte loads; a reverse-strand read is loaded back to front and bit-reversed, which is its reverse complement); the draft
+// comes from the tile's shared-memory copy through one native 32-bit funnel shift per 8 bases.  Pass 1 XORs 8 bases at a time
+// and only records WHICH words differ (one bit per word: straight-line code, no divergence); pass 2 visits the few words that
+// do (about one word in two reads), reloads them and counts each differing base.  Returns kept entries, or NONE32 = "take the
+// general walk" (a homopolymer tail of 32+ bases).
 __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, unsigned long long aln) {
     const uint32_t len = r.len_nc & 0xFFFFu;
     const bool rc = r.flags & TR_RC;
     const uint4* sp = reinterpret_cast<const uint4*>(S.d.seq_pool + (size_t)r.seq_off * 16);
     const uint32_t nq = (len + 31) >> 5;                       // 16-byte quads that hold the read
-    unsigned long long w[12];
+    uint32_t w[24];                                            // effective read, 8 bases per word, base i = nibble pad + i
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         uint4 q = make_uint4(0, 0, 0, 0);
         if ((uint32_t)j < nq) q = __ldg(sp + (rc ? nq - 1 - j : (uint32_t)j));
-        const unsigned long long lo = (unsigned long long)q.x | ((unsigned long long)q.y << 32), hi = (unsigned long long)q.z | ((unsigned long long)q.w << 32);
-        w[2 * j] = rc ? pp_brev64(hi) : lo;
-        w[2 * j + 1] = rc ? pp_brev64(lo) : hi;
+        w[4 * j + 0] = rc ? __brev(q.w) : q.x;
+        w[4 * j + 1] = rc ? __brev(q.z) : q.y;
+        w[4 * j + 2] = rc ? __brev(q.y) : q.z;
+        w[4 * j + 3] = rc ? __brev(q.x) : q.w;
     }
-    const uint32_t pad = rc ? 32 * nq - len : 0;               // effective base i is nibble pad + i of w[]
+    const uint32_t pad = rc ? 32 * nq - len : 0;
     // ---- trim (alignment.rs:364-378) on the last min(len, 32) effective bases
     uint32_t run;
     {
@@ -797,31 +804,45 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
     const uint32_t nkept = (len - run >= 1) ? len - run - 1 : 0;
     if ((unsigned long long)r.gstart + nkept > r.cend) { report_error(S.d.st, aln, ERR_OOB); return 0; }
     S.add_interval(r.gstart, nkept, r.k != 1);
-    // ---- compare: word j holds nibbles [16 j, 16 j + 16) = tile-relative positions relq + 16 j ...
+    // ---- compare: word m holds nibbles [8 m, 8 m + 8) = tile-relative positions relq + 8 m ...
     const long long g0 = (long long)r.gstart - (long long)S.P0;
     const long long a64 = max(g0, 0ll), b64 = min(g0 + (long long)nkept, (long long)TL_T);
     if (b64 <= a64) return nkept;
-    const int a_rel = (int)a64, b_rel = (int)b64;
     const int relq = (int)g0 - (int)pad;
-    const uint32_t sh4 = (uint32_t)((relq + TL_DN_HALO) & 15) * 4;       // loop-invariant funnel shift of the draft words
+    const uint32_t first = (uint32_t)((int)a64 - relq), lastn = (uint32_t)((int)b64 - 1 - relq);   // first / last valid nibble of w[]
+    const uint32_t m_first = first >> 3, m_last = lastn >> 3;
+    const uint32_t fmask = 0xFFFFFFFFu << ((first & 7) * 4), lmask = 0xFFFFFFFFu >> ((7 - (lastn & 7)) * 4);
+    const uint32_t vmask = (2u << m_last) - (1u << m_first);    // words m_first .. m_last
+    const uint32_t emask = (1u << m_first) | (1u << m_last);
+    const uint32_t* dn32 = reinterpret_cast<const uint32_t*>(S.sh.dn);
+    const int o0 = relq + TL_DN_HALO;                           // nibble offset of word 0 in the staged draft (valid words: > 0)
+    const int i0 = o0 >> 3;                                     // floor
+    const uint32_t sh4 = (uint32_t)(o0 & 7) * 4;
+    uint32_t mm = 0;                                            // words that differ from the draft
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        const int wrel = relq + 16 * j;                        // position of the word's nibble 0
-        const int lo = a_rel - wrel, hi = b_rel - wrel;        // valid nibbles [lo, hi)
-        if (hi <= 0 || lo >= 16) continue;
-        const uint32_t o = (uint32_t)(wrel + TL_DN_HALO);       // >= 1 here: wrel > a_rel - 16 >= -16
-        const unsigned long long* p = S.sh.dn + (o >> 4);
-        unsigned long long dw = p[0];
-        if (sh4) dw = (dw >> sh4) | (p[1] << (64 - sh4));
-        unsigned long long mism = nibble_nonzero(w[j] ^ dw) & nibmask(hi) & ~nibmask(lo);
-        while (mism) {
-            const uint32_t t = (uint32_t)(__ffsll((long long)mism) - 1) >> 2;
-            mism &= mism - 1;
-            const uint32_t code = (uint32_t)(w[j] >> (4 * t)) & 15u;
-            const int c = Seq<4>::acgt(code);
-            const int rel = wrel + (int)t;
-            if (c >= 0) atomicAdd(&S.sh.ex[c][rel], 1u);
-            else S.push_other(S.P0 + (uint32_t)rel, aln, 16u * j + t - pad, 1, 1ull | ((unsigned long long)code << 4));
+    for (int m = 0; m < 24; ++m) {
+        if (vmask & (1u << m)) {
+            uint32_t x = w[m] ^ __funnelshift_r(dn32[i0 + m], dn32[i0 + m + 1], sh4);
+            if (emask & (1u << m)) { if ((uint32_t)m == m_first) x &= fmask; if ((uint32_t)m == m_last) x &= lmask; }
+            if (x) mm |= 1u << m;
+        }
+    }
+    while (mm) {
+        const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
+        mm &= mm - 1;
+        uint32_t wv = __ldg(reinterpret_cast<const uint32_t*>(sp) + (rc ? 4 * nq - 1 - m : m));
+        if (rc) wv = __brev(wv);
+        uint32_t x = wv ^ __funnelshift_r(dn32[i0 + (int)m], dn32[i0 + (int)m + 1], sh4);
+        if (m == m_first) x &= fmask;
+        if (m == m_last) x &= lmask;
+        uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+        while (nz) {
+            const uint32_t t = (uint32_t)(__ffs((int)nz) - 1) >> 2;
+            nz &= nz - 1;
+            const uint32_t code = (wv >> (4 * t)) & 15u;
+            const int rel = relq + 8 * (int)m + (int)t;
+            if ((code & (code - 1)) == 0) atomicAdd(&S.sh.ex[__ffs((int)code) - 1][rel], 1u);          // A, C, G, T = 1, 2, 4, 8
+            else S.push_other(S.P0 + (uint32_t)rel, aln, 8u * m + t - pad, 1, 1ull | ((unsigned long long)code << 4));
         }
     }
     return nkept;
@@ -849,7 +870,7 @@ __device__ __forceinline__ TileRec load_rec(const DevData& d, uint32_t aln) {
 #define PP_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #endif
 template <int BITS>
-__device__ void depth_walk(const DevData& d, TileShared& sh, uint32_t P0, uint32_t sub, uint32_t lb, uint32_t long_lo, uint32_t long_hi) {
+__device__ void depth_walk_steps(const DevData& d, TileShared& sh, uint32_t P0, uint32_t sub, uint32_t lb, uint32_t long_lo, uint32_t long_hi) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t s = P0 + sub * PP_SUB;
     const uint32_t bin = s >> PP_BIN_SHIFT;
@@ -925,6 +946,98 @@ __device__ void depth_walk(const DevData& d, TileShared& sh, uint32_t P0, uint32
     out[0] = dep0; out[1] = dep1; out[2] = dep2; out[3] = dep3;
 }
 
+// The same for the common case of at most two runs (reads of up to 256 entries, no long list): the merge is done 32 + 32 slots
+// at a time - every lane ranks its own two entries against the other run's window by binary search in shared memory, the
+// merged (start, length, 1/k) triples land in a per-warp staging area, and the ordered additions run over that area with
+// nothing but broadcast loads in the loop.
+template <int BITS>
+__device__ void depth_walk_two(const DevData& d, TileShared& sh, WalkStage& ws, uint32_t P0, uint32_t sub, uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t s = P0 + sub * PP_SUB;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t wb[2] = {lo0, lo1}, end[2] = {hi0, hi1}, mask[2] = {0, 0}, lastkey[2] = {0, 0};
+    uint32_t w_aln[2] = {NONE32, NONE32}, w_start[2] = {0, 0}, w_len[2] = {0, 0};
+    double w_inv[2] = {0.0, 0.0};
+    bool loaded[2] = {false, false};
+    const uint32_t p = s + lane * 4;
+    double dep0 = 0.0, dep1 = 0.0, dep2 = 0.0, dep3 = 0.0;
+    for (;;) {
+        // (re)load the windows that are used up; windows without an overlapping entry are skipped
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            while (mask[r] == 0 && (!loaded[r] || wb[r] < end[r])) {
+                if (loaded[r]) wb[r] += 32;
+                loaded[r] = true;
+                if (wb[r] >= end[r]) break;
+                const uint32_t slot = wb[r] + lane;
+                uint4 q = make_uint4(NONE32, 0, 0, 1);
+                if (slot < end[r]) {
+                    q = d.wrec[slot];
+                    if (slot + 32 < end[r]) PP_PREFETCH_L1(d.wrec + slot + 32);
+                }
+                const bool ov = slot < end[r] && q.z != 0 && q.y < s + PP_SUB && q.y + q.z > s;
+                mask[r] = __ballot_sync(0xffffffffu, ov);
+                w_aln[r] = q.x; w_start[r] = q.y; w_len[r] = q.z;
+                w_inv[r] = __ddiv_rn(1.0, (double)q.w);         // 1.0 / good_alignments.len() as f64 (alignment.rs:288)
+                // every entry of the run up to this key is in this window or behind us; NONE32 once the run has no further window
+                lastkey[r] = (wb[r] + 32 < end[r]) ? __shfl_sync(0xffffffffu, w_aln[r], 31) : NONE32;
+            }
+        }
+        if ((mask[0] | mask[1]) == 0) break;                   // both runs exhausted
+        // entries that can be merged now: alignment index <= the smaller "complete up to" key
+        const uint32_t lim0 = (mask[0] || wb[0] < end[0]) ? lastkey[0] : NONE32, lim1 = (mask[1] || wb[1] < end[1]) ? lastkey[1] : NONE32;
+        const uint32_t limit = min(lim0, lim1);
+        uint32_t e[2], rank[2], n[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            e[r] = mask[r] & __ballot_sync(0xffffffffu, w_aln[r] <= limit);
+            rank[r] = (uint32_t)__popc(e[r] & lt);
+            n[r] = (uint32_t)__popc(e[r]);
+            if ((e[r] >> lane) & 1u) ws.key[r][rank[r]] = w_aln[r];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if ((e[r] >> lane) & 1u) {
+                const uint32_t* ok = ws.key[r ^ 1];
+                uint32_t blo = 0, bhi = n[r ^ 1];               // entries of the other run that come first
+#pragma unroll
+                for (int it = 0; it < 6; ++it) {
+                    if (blo < bhi) { const uint32_t mid = (blo + bhi) >> 1; if (ok[mid] < w_aln[r]) blo = mid + 1; else bhi = mid; }
+                }
+                const unsigned long long iv = (unsigned long long)__double_as_longlong(w_inv[r]);
+                ws.ent[rank[r] + blo] = make_uint4(w_start[r], w_len[r], (uint32_t)iv, (uint32_t)(iv >> 32));
+            }
+            mask[r] &= ~e[r];
+        }
+        __syncwarp();
+        const uint32_t ntot = n[0] + n[1];
+        for (uint32_t j = 0; j < ntot; ++j) {
+            const uint4 q = ws.ent[j];
+            const double inv = __longlong_as_double((long long)((unsigned long long)q.z | ((unsigned long long)q.w << 32)));
+            const uint32_t off = p - q.x;                       // position p + i is covered iff (off + i) < length (unsigned)
+            if (off < q.y) dep0 = __dadd_rn(dep0, inv);
+            if (off + 1u < q.y) dep1 = __dadd_rn(dep1, inv);
+            if (off + 2u < q.y) dep2 = __dadd_rn(dep2, inv);
+            if (off + 3u < q.y) dep3 = __dadd_rn(dep3, inv);
+        }
+        __syncwarp();
+    }
+    double* out = sh.depth + (p - P0);
+    out[0] = dep0; out[1] = dep1; out[2] = dep2; out[3] = dep3;
+}
+
+template <int BITS>
+__device__ __forceinline__ void depth_walk(const DevData& d, TileShared& sh, WalkStage& ws, uint32_t P0, uint32_t sub, uint32_t lb, uint32_t long_lo, uint32_t long_hi) {
+    const uint32_t bin = (P0 + sub * PP_SUB) >> PP_BIN_SHIFT;
+    if (lb <= 1 && long_lo >= long_hi) {
+        const uint32_t lo1 = d.bin_start[bin], hi1 = d.bin_start[bin + 1];
+        uint32_t lo0 = 0, hi0 = 0;
+        if (lb == 1 && bin >= 1) { lo0 = d.bin_start[bin - 1]; hi0 = lo1; }
+        depth_walk_two<BITS>(d, sh, ws, P0, sub, lo0, hi0, lo1, hi1);
+    } else depth_walk_steps<BITS>(d, sh, P0, sub, lb, long_lo, long_hi);
+}
+
 template <int BITS>
 __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp, TileShared& sh) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -938,7 +1051,7 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
 
     for (;;) {
         __syncthreads();                                                       // everyone is done with the previous tile
-        if (tid == 0) { sh.tile = atomicAdd(&d.st->ticket, 1u); sh.qn = 0; sh.subflags = 0; }
+        if (tid == 0) { sh.tile = atomicAdd(&d.st->ticket, 1u); sh.next = 0; sh.subflags = 0; }
         __syncthreads();
         const uint32_t tile = sh.tile;
         if (tile >= d.n_tiles) break;
@@ -967,48 +1080,39 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             }
         }
         __syncthreads();
-        // ---- phase B: every alignment that can touch the tile, in sorted order: the bins of the tile and `lb` bins before it
+        // ---- phase B: every alignment that can touch the tile, in sorted order: the bins of the tile and `lb` bins before it.
+        // Warps take 32 consecutive slots at a time from a shared counter (no round is held up by one slow warp); the records of
+        // the chunk after the current one are already in flight while the current one is walked.  Reads with indels / long reads
+        // take the general walk right away, on their own lanes.
         const uint32_t b0 = P0 >> PP_BIN_SHIFT;
         const uint32_t lo = d.bin_start[b0 >= lb ? b0 - lb : 0u];
         const uint32_t hi = d.bin_start[min(b0 + (uint32_t)(TL_T / PP_BIN), d.n_bins)];
         {
-            // software pipeline over the gathers: the record of the next round and the index of the round after it are in
-            // flight while this round's alignment is walked
-            uint32_t aln_a = (lo + tid < hi) ? d.sval[lo + tid] : 0u;
-            uint32_t aln_b = (lo + tid + TL_THREADS < hi) ? d.sval[lo + tid + TL_THREADS] : 0u;
+            auto grab = [&]() -> uint32_t {
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(&sh.next, 32u);
+                return lo + __shfl_sync(0xffffffffu, c, 0);
+            };
+            uint32_t c_a = grab();
+            uint32_t aln_a = (c_a + lane < hi) ? d.sval[c_a + lane] : 0u;
             TileRec rec_a = load_rec<BITS>(d, aln_a);
-            for (uint32_t base = lo; base < hi; base += TL_THREADS) {
-                const uint32_t i = base + tid;
-                const TileRec rec_b = load_rec<BITS>(d, aln_b);                       // (slot 0's record when there is no next round)
-                const uint32_t aln_c = (i + 2 * TL_THREADS < hi) ? d.sval[i + 2 * TL_THREADS] : 0u;
+            while (c_a < hi) {
+                const uint32_t c_b = grab();
+                const uint32_t aln_b = (c_b + lane < hi) ? d.sval[c_b + lane] : 0u;
+                const TileRec rec_b = load_rec<BITS>(d, aln_b);                       // (alignment 0's record past the end of the list)
+                const uint32_t i = c_a + lane;
                 if (i < hi) {
-                    const TileRec& r = rec_a;
-                    const uint32_t aln = aln_a;
                     uint32_t nk = NONE32;
-                    if (BITS == 4 && (r.flags & TR_FAST)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), r, aln);
-                    if (nk == NONE32) {
-                        const uint32_t q = atomicAdd(&sh.qn, 1u);
-                        if (q < TL_QCAP) sh.queue[q] = i;
-                        else { nk = general_walk<BITS>(S, r, aln); d.wrec[i] = make_uint4(aln, r.gstart, nk, r.k); }
-                    } else d.wrec[i] = make_uint4(aln, r.gstart, nk, r.k);
+                    if (BITS == 4 && (rec_a.flags & TR_FAST)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), rec_a, aln_a);
+                    if (nk == NONE32) nk = general_walk<BITS>(S, rec_a, aln_a);
+                    d.wrec[i] = make_uint4(aln_a, rec_a.gstart, nk, rec_a.k);
                 }
-                if (BITS == 4 && i + TL_THREADS < hi && (rec_b.flags & TR_FAST)) {     // the next read's bases towards L2 / L1
+                if (BITS == 4 && c_b + lane < hi) {                                    // the next read's bases towards L1
                     const uint8_t* nsp = d.seq_pool + (size_t)rec_b.seq_off * 16;
                     PP_PREFETCH_L1(nsp);
                     PP_PREFETCH_L1(nsp + 64);
                 }
-                rec_a = rec_b; aln_a = aln_b; aln_b = aln_c;
-            }
-        }
-        __syncthreads();
-        // the deferred alignments (indels, long reads), consecutive lanes
-        {
-            const uint32_t qn = min(sh.qn, (uint32_t)TL_QCAP);
-            for (uint32_t q = tid; q < qn; q += TL_THREADS) {
-                const uint32_t i = sh.queue[q];
-                const uint32_t aln = d.sval[i];
-                const TileRec r = load_rec<BITS>(d, aln);
-                d.wrec[i] = make_uint4(aln, r.gstart, general_walk<BITS>(S, r, aln), r.k);
+                c_a = c_b; aln_a = aln_b; rec_a = rec_b;
             }
             // the long list: alignments of more than TL_LONG_E entries, looked at by every tile
             for (uint32_t i = long_lo + tid; i < long_hi; i += TL_THREADS) {
@@ -1036,13 +1140,10 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             if (anym) atomicOr(&sh.subflags, 1u << (rel0 >> PP_SUB_SHIFT));
         }
         __syncthreads();
-        // ---- phase D: ordered depth of the flagged sub-tiles, one warp each
-        {
-            const uint32_t flags = sh.subflags;
-            for (uint32_t sub = warp; sub < TL_T / PP_SUB; sub += TL_THREADS / 32)
-                if ((flags >> sub) & 1u) depth_walk<BITS>(d, sh, P0, sub, lb, long_lo, long_hi);
-        }
-        __syncthreads();
+        // ---- phase D: ordered depth where a sub-tile sees k != 1.  Warp w owns sub-tile w here AND in the vote below, so there is
+        // no block-wide barrier in between: warps of unflagged sub-tiles go straight on.
+        if ((sh.subflags >> warp) & 1u) depth_walk<BITS>(d, sh, sh.wstage[warp], P0, warp, lb, long_lo, long_hi);
+        __syncwarp();
         // ---- phase E: the vote, straight out of shared memory
         const uint32_t p0 = P0 + rel0;
         PosOut po[TL_PER_THREAD];
@@ -1097,6 +1198,18 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 po[i].packed = (orig == '-' ? 0u : 1u) | (orig << 16);
                 tlen += po[i].packed & 0xFFFFu;
                 continue;
+            }
+            if (!vp.dbg) {
+                // The emitted base differs from the draft only if an allele OTHER than the draft's reaches the valid threshold
+                // max(min_depth, round(depth * fraction_valid)) (pileup.rs:70-72,114-129).  No such allele can when the largest
+                // non-draft count is below min_depth, or below depth * fraction_valid by more than rounding can bridge: the
+                // position keeps its base whatever its status (kept / too_close / low_depth / none / multiple).
+                const uint32_t mx = max(max(max(cA, cC), max(cG, cT)), max(cDel, n_other));
+                if (mx < prm.min_depth || (double)mx + 2.0 < depth * prm.fv) {
+                    po[i].packed = (orig == '-' ? 0u : 1u) | (orig << 16);
+                    tlen += po[i].packed & 0xFFFFu;
+                    continue;
+                }
             }
             uint32_t matched = cov - (cA + cC + cG + cT + cDel + n_other);
             if (orig == 'A') { cA += matched; matched = 0; }

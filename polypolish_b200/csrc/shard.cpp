@@ -36,7 +36,13 @@ struct pp_shards {
 };
 
 extern "C" pp_shards* pp_shards_build(const pp_contigs* c, const pp_alignments* a, uint32_t n_shards) {
-    if (!c || !a || n_shards == 0) return nullptr;
+    return pp_shards_build_assigned(c, a, n_shards, nullptr, -1);
+}
+
+extern "C" pp_shards* pp_shards_build_assigned(const pp_contigs* c, const pp_alignments* a, uint32_t n_shards,
+                                               const uint32_t* assigned, int32_t only_shard) {
+    if (!c || !a || n_shards == 0 || only_shard >= (int32_t)n_shards) return nullptr;
+    if (assigned) for (uint32_t i = 0; i < c->n_contigs; ++i) if (assigned[i] >= n_shards) return nullptr;
     const uint32_t nc = c->n_contigs;
     pp_shards* S = new pp_shards();
     S->seq_bits = a->seq_bits;
@@ -52,7 +58,7 @@ extern "C" pp_shards* pp_shards_build(const pp_contigs* c, const pp_alignments* 
     std::vector<uint64_t> load(n_shards, 0);
     std::vector<uint32_t> shard_of(nc), local_of(nc);
     for (uint32_t ci : order) {
-        uint32_t best = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        uint32_t best = assigned ? assigned[ci] : (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
         shard_of[ci] = best;
         load[best] += weight[ci];
     }
@@ -150,7 +156,7 @@ extern "C" pp_shards* pp_shards_build(const pp_contigs* c, const pp_alignments* 
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const unsigned n_threads = std::min<unsigned>(n_shards, hw);
         std::atomic<uint32_t> next{0};
-        auto worker = [&]() { for (uint32_t s; (s = next.fetch_add(1)) < n_shards;) build_one(s); };
+        auto worker = [&]() { for (uint32_t s; (s = next.fetch_add(1)) < n_shards;) if (only_shard < 0 || (uint32_t)only_shard == s) build_one(s); };
         std::vector<std::thread> th;
         for (unsigned t = 1; t < n_threads; ++t) th.emplace_back(worker);
         worker();

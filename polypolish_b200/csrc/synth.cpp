@@ -73,6 +73,10 @@ struct pp_synth {
     pp_synth_params prm;
     std::vector<Contig> contigs;
     std::vector<std::vector<SharedCopy>> shared;   // repeat families whose copies lie on different contigs (config 5: k spans GPUs)
+    bool per_pair_rng = false;                     // every pair / mate draws from its own stream (seed, pair index): parts of the data
+                                                   // set can be generated without generating the rest
+    uint32_t filter_shards = 0, filter_shard = 0;  // > 0: only reads with a record on a contig of `filter_shard` are emitted
+    std::vector<uint32_t> shard_of_contig;
     uint64_t total_draft = 0;
     uint64_t n_pairs = 0;
 };
@@ -269,49 +273,69 @@ bool generate(const pp_synth* S, int mate, const Sink& sink) {
     const uint32_t L = P.read_len;
     const std::string qual(L + 64, 'I');
     char line[256];
+    const bool v2 = S->per_pair_rng;
+    const bool filt = v2 && S->filter_shards > 0;
+    auto mine = [&](size_t contig_index) { return S->shard_of_contig[contig_index] == S->filter_shard; };
+    std::string grp;                                             // the records of one read (primary + secondaries)
     for (uint64_t pi = 0; pi < S->n_pairs; ++pi) {
         // contig, fragment
-        double x = rng.uni() * tot;
+        Rng pair_rng(v2 ? (P.seed * 0xD1342543DE82EF95ull + pi * 0x9E3779B97F4A7C15ull + 77) : 0);
+        Rng& prng = v2 ? pair_rng : rng;
+        double x = prng.uni() * tot;
         size_t ci = 0;
         while (ci + 1 < cum.size() && x >= cum[ci]) ci++;
         const Contig& c = S->contigs[ci];
         const uint64_t T = c.truth.size();
-        double isz_d = P.insert_mean + P.insert_sd * rng.normal();
+        double isz_d = P.insert_mean + P.insert_sd * prng.normal();
         uint64_t isz = (uint64_t)std::min(700.0, std::max(200.0, isz_d));
         if (isz < L + 10) isz = L + 10;
         if (isz + 2 * L + 64 > T) isz = T > 3 * (uint64_t)L + 128 ? T - 2 * L - 64 : L + 10;
-        uint64_t fs = rng.below(T - isz - L - 32);
-        bool first_is_left = rng.next() & 1;
-        // both mates are always generated so that the RNG stream is identical for mate 1 and mate 2 passes
+        uint64_t fs = prng.below(T - isz - L - 32);
+        bool first_is_left = prng.next() & 1;
+        // legacy streams: both mates are always generated so that the RNG stream is identical for the mate 1 and mate 2 passes;
+        // per-pair streams: every mate has its own, the other one is simply not generated
         for (int m = 0; m < 2; ++m) {
             const bool left = (m == 0);                      // m = 0: leftmost (forward) read, m = 1: rightmost (reverse)
             const int this_mate = (left == first_is_left) ? 1 : 2;
+            if (v2 && this_mate != mate) continue;
             const uint64_t ts = left ? fs : fs + isz - L;
+            if (filt && !mine(ci)) {
+                // can this read have a record on one of my contigs?  Only through a cross-contig repeat family whose copy
+                // contains the read's start (a superset of the exact rule below)
+                const Copy* near = containing_copy(c, ts, 1);
+                bool maybe = false;
+                if (near && near->shared >= 0)
+                    for (auto& o : S->shared[(size_t)near->shared]) maybe |= mine(o.contig);
+                if (!maybe) continue;
+            }
+            Rng mate_rng(v2 ? (P.seed * 0xA0761D6478BD642Full + (pi * 2 + (uint64_t)m) * 0xE7037ED1A0B428DBull + 5) : 0);
+            Rng& mrng = v2 ? mate_rng : rng;
             std::vector<Col>& cl = cols[m];
             cl.clear();
             uint32_t nb = 0;
             uint64_t tlen = 0;
-            double special = rng.uni();
+            double special = mrng.uni();
             const bool unaligned = special < P.unaligned_rate;
             const bool clipped = !unaligned && special < P.unaligned_rate + P.clip_rate;
             const bool highnm = !unaligned && !clipped && special < P.unaligned_rate + P.clip_rate + P.highnm_rate;
             while (nb < L && ts + tlen < T) {
-                double r = rng.uni();
+                double r = mrng.uni();
                 char b = c.truth[ts + tlen];
                 if (r < P.seq_indel_rate * 0.5) { cl.push_back({C_DEL, 0}); tlen++; continue; }
-                if (r < P.seq_indel_rate * 0.5 + P.seq_sub_rate) b = rng.other(b);
+                if (r < P.seq_indel_rate * 0.5 + P.seq_sub_rate) b = mrng.other(b);
                 cl.push_back({C_M, b}); nb++; tlen++;
-                if (nb < L && rng.uni() < P.seq_indel_rate * 0.5) { cl.push_back({C_INS, rng.base()}); nb++; }
+                if (nb < L && mrng.uni() < P.seq_indel_rate * 0.5) { cl.push_back({C_INS, mrng.base()}); nb++; }
             }
             while (!cl.empty() && cl.back().type == C_DEL) { cl.pop_back(); tlen--; }
-            if (highnm) for (int k = 0; k < 14; ++k) { Col& q = cl[rng.below(cl.size())]; if (q.type == C_M) q.base = rng.other(q.base); }
-            const uint32_t clipn = clipped ? 3 + (uint32_t)rng.below(8) : 0;
-            const bool clip_left = rng.next() & 1;
+            if (highnm) for (int k = 0; k < 14; ++k) { Col& q = cl[mrng.below(cl.size())]; if (q.type == C_M) q.base = mrng.other(q.base); }
+            const uint32_t clipn = clipped ? 3 + (uint32_t)mrng.below(8) : 0;
+            const bool clip_left = mrng.next() & 1;
             if (this_mate != mate) continue;
             const bool rev = !left;
             int n = snprintf(line, sizeof line, "r%llu", (unsigned long long)pi);
             const std::string qname(line, n);
             if (unaligned) {
+                if (filt && !mine(ci)) continue;
                 std::string seq;
                 for (auto& q : cl) if (q.type != C_DEL) seq.push_back(q.base);
                 out += qname + "\t4\t*\t0\t0\t*\t*\t0\t0\t" + seq + "\t" + qual.substr(0, seq.size()) + "\n";
@@ -338,19 +362,21 @@ bool generate(const pp_synth* S, int mate, const Sink& sink) {
                 align_cols(c, ts, cl, clipped ? clipn : 0, rec);
             }
             if (!rec.ok) continue;
+            bool touches = !filt || mine(ci);
+            grp.clear();
             const Copy* cp = containing_copy(c, ts, tlen);
-            struct Other { const Contig* c; uint64_t start, len; bool rev; };
+            struct Other { const Contig* c; uint32_t contig; uint64_t start, len; bool rev; };
             std::vector<Other> others;
             if (cp && !clipped) {
-                if (cp->shared < 0) { for (auto& o : c.copies) if (o.family == cp->family && &o != cp) others.push_back({&c, o.start, o.len, o.rev}); }
+                if (cp->shared < 0) { for (auto& o : c.copies) if (o.family == cp->family && &o != cp) others.push_back({&c, (uint32_t)ci, o.start, o.len, o.rev}); }
                 else for (auto& o : S->shared[(size_t)cp->shared])
-                    if (o.contig != ci || o.start != cp->start) others.push_back({&S->contigs[o.contig], o.start, o.len, o.rev});
+                    if (o.contig != ci || o.start != cp->start) others.push_back({&S->contigs[o.contig], o.contig, o.start, o.len, o.rev});
             }
             n = snprintf(line, sizeof line, "\t%d\t%s\t%u\t%d\t", rev ? 16 : 0, c.name.c_str(), rec.pos + 1, others.empty() ? 60 : 0);
-            out += qname; out.append(line, n); out += rec.cigar; out += "\t*\t0\t0\t"; out += rec.seq; out += '\t';
-            out.append(qual.data(), rec.seq.size());
+            grp += qname; grp.append(line, n); grp += rec.cigar; grp += "\t*\t0\t0\t"; grp += rec.seq; grp += '\t';
+            grp.append(qual.data(), rec.seq.size());
             n = snprintf(line, sizeof line, "\tNM:i:%u\tAS:i:%d\tXS:i:%d\n", rec.nm, (int)rec.seq.size() - 5 * (int)rec.nm, others.empty() ? 0 : (int)rec.seq.size() - 5 * (int)rec.nm);
-            out.append(line, n);
+            grp.append(line, n);
             // secondaries: the same read against the other copies of the repeat family
             const uint64_t off = cp ? ts - cp->start : 0;
             for (const Other& o : others) {
@@ -361,12 +387,14 @@ bool generate(const pp_synth* S, int mate, const Sink& sink) {
                 else { ts2 = o.start + (o.len - off - tlen); revcomp_cols(cl, rcols); c2 = &rcols; }
                 align_cols(*o.c, ts2, *c2, 0, rec);
                 if (!rec.ok) continue;
+                if (filt && mine(o.contig)) touches = true;
                 const bool rev2 = rev != flip;
                 n = snprintf(line, sizeof line, "\t%d\t%s\t%u\t0\t", 256 | (rev2 ? 16 : 0), o.c->name.c_str(), rec.pos + 1);
-                out += qname; out.append(line, n); out += rec.cigar;
+                grp += qname; grp.append(line, n); grp += rec.cigar;
                 n = snprintf(line, sizeof line, "\t*\t0\t0\t*\t*\tNM:i:%u\tAS:i:%d\n", rec.nm, (int)rec.seq.size() - 5 * (int)rec.nm);
-                out.append(line, n);
+                grp.append(line, n);
             }
+            if (touches) out += grp;
         }
         if (out.size() > (1u << 22)) { if (!sink(out.data(), out.size())) return false; out.clear(); }
     }
@@ -394,6 +422,7 @@ extern "C" pp_synth* pp_synth_create_shared(const pp_synth_params* prm, double c
     if (cross_contig_fraction > 0) {
         Rng srng(prm->seed * 7919ull + 0xC5C5C5C5ull);
         plant_shared(S, srng, cross_contig_fraction);
+        S->per_pair_rng = true;
     }
     for (uint32_t ci = 0; ci < prm->n_contigs; ++ci) {
         make_draft(S->contigs[ci], rngs[ci], prm->draft_error_rate);
@@ -405,6 +434,18 @@ extern "C" pp_synth* pp_synth_create_shared(const pp_synth_params* prm, double c
 }
 
 extern "C" pp_synth* pp_synth_create(const pp_synth_params* prm) { return pp_synth_create_shared(prm, 0.0); }
+
+// Only for data sets made by pp_synth_create_shared with a cross-contig fraction > 0 (per-pair random streams): from now on
+// pp_synth_write_sam / pp_synth_feed_pack emit only the reads that have a record on a contig of `shard` - exactly the reads the
+// contig sharder would hand that shard (pp_shards_build_assigned with the same assignment), without generating the others.
+extern "C" int pp_synth_set_shard_filter(pp_synth* s, uint32_t n_shards, uint32_t shard, const uint32_t* shard_of_contig) {
+    if (!s || !s->per_pair_rng || (n_shards && shard >= n_shards)) return PP_ERR_ARG;
+    s->filter_shards = n_shards;
+    s->filter_shard = shard;
+    s->shard_of_contig.resize(s->contigs.size());
+    for (size_t i = 0; i < s->contigs.size(); ++i) s->shard_of_contig[i] = n_shards ? (shard_of_contig ? shard_of_contig[i] : (uint32_t)(i % n_shards)) : 0u;
+    return PP_OK;
+}
 
 extern "C" void pp_synth_free(pp_synth* s) { delete s; }
 extern "C" uint64_t pp_synth_total_bp(const pp_synth* s) { return s ? s->total_draft : 0; }

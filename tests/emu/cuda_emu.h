@@ -163,6 +163,9 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (shift & 31)); }
+static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
+static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
