@@ -319,6 +319,13 @@ int pp_polish_files_multi(pp_ctx* const* ctxs, int n_ctx, const char* assembly, 
  * text code.  Same bytes and messages either way. */
 int pp_filter_files(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2,
                     const char* orientation, double low, double high, int verbose);
+/* `polypolish filter` followed by `polypolish polish` on its output, as ONE call: both SAM files cross PCIe once,
+ * the filter's verdict stays in HBM as the ZP flag of the tokenised records (what the ZP:Z:fail tag carries through the intermediate
+ * files: filter.rs:334-342, alignment.rs:72-74), and the polished FASTA is byte for byte that of the two commands.  out1 / out2 may
+ * be NULL: the filtered SAM files are then not written at all.  Anything unusual falls back to the two commands through files. */
+int pp_filter_polish_files(pp_ctx* ctx, const char* assembly, const char* in1, const char* in2, const char* out1, const char* out2,
+                           const char* orientation, double low, double high, const pp_polish_params* params, char** out_fasta,
+                           uint64_t* out_len, int verbose);
 void pp_free(void* p);
 
 /* ------------------------------------------------------------------------------------------------------

@@ -468,6 +468,22 @@ class Context:
         lib().pp_free(out)
         return data
 
+    def filter_polish_files(self, assembly, in1, in2, out1=None, out2=None, orientation="auto", low=0.1, high=99.9, verbose=False, **opts):
+        """pp_filter_polish_files: `filter` then `polish` in one call (the filtered SAM files are written only when named)."""
+        L = lib()
+        L.pp_filter_polish_files.argtypes = [C.c_void_p] + [C.c_char_p] * 6 + [C.c_double, C.c_double, C.POINTER(PolishParams),
+                                                                              C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]
+        prm = _params(**opts)
+        out, n = C.c_void_p(), C.c_uint64()
+        rc = L.pp_filter_polish_files(self.h, str(assembly).encode(), str(in1).encode(), str(in2).encode(),
+                                      str(out1).encode() if out1 else None, str(out2).encode() if out2 else None, orientation.encode(),
+                                      low, high, C.byref(prm), C.byref(out), C.byref(n), int(verbose))
+        if rc != PP_OK:
+            raise self._err(rc)
+        data = C.string_at(out, n.value)
+        L.pp_free(out)
+        return data
+
     def filter_files(self, in1, in2, out1, out2, orientation="auto", low=0.1, high=99.9, verbose=False):
         rc = lib().pp_filter_files(self.h, str(in1).encode(), str(in2).encode(), str(out1).encode(), str(out2).encode(),
                                    orientation.encode(), low, high, int(verbose))

@@ -150,7 +150,7 @@ extern "C" int pp_filter_files(pp_ctx* ctx, const char* in1, const char* in2, co
     // device path leaves to the host code below (malformed line, empty file, ...), which words the reference's messages.
     if (pp_get_parser(ctx) == 0) {
         pp_filter_file_stats fs;
-        int rc = pp_filter_files_device(ctx, in1, in2, out1, out2, &prm, &res, &fs);
+        int rc = pp_filter_files_device(ctx, in1, in2, out1, out2, &prm, &res, &fs, nullptr);
         if (rc == PP_OK) {
             if (verbose) {
                 for (int k = 0; k < 2; ++k) fprintf(stderr, "%s: %s alignments\n", ins[k], thousands(fs.alignments[k]).c_str());

@@ -6,6 +6,7 @@
 // Text (FASTA/SAM) is handled here on the host; all per-alignment / per-position work is behind
 // pp_polish() / pp_filter() on the device.  There is no CPU fallback for that work.
 #include <cmath>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -223,9 +224,17 @@ static int tokenise_files(pp_ctx* ctx, const pp_fasta* fa, const char* const* sa
     return PP_TOK_HOST;
 }
 
+// `filter` in front of `polish` in the same call (pp_filter_polish_files): the two SAM files are `sams`, this says what to filter with
+struct FusedFilter {
+    pp_filter_params prm;
+    std::string orientation;
+    const char *out1, *out2;             // filtered SAM files, or null: not written
+};
+
 // polish::polish (polish.rs:26-38) over one or several GPUs (contigs shard across them).
 static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembly, const char* const* sams, int n_sams,
-                             const pp_polish_params* prm, const char* debug_path, char** out_fasta, uint64_t* out_len, int verbose) {
+                             const pp_polish_params* prm, const char* debug_path, char** out_fasta, uint64_t* out_len, int verbose,
+                             const FusedFilter* ff = nullptr) {
     pp_ctx* ctx = ctxs[0];
     if (!assembly || !prm || !out_fasta || !out_len || n_sams < 0) return pp_ctx_fail(ctx, PP_ERR_ARG, "pp_polish_files: bad arguments");
     *out_fasta = nullptr;
@@ -247,7 +256,7 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     struct FileCloser { FILE*& f; ~FileCloser() { if (f) fclose(f); } } closer{debug_file};
 
     // the first SAM file starts streaming into HBM while the assembly is loaded
-    if (!debug && n_sams > 0 && pp_get_parser(ctx) == 0) pp_tok_prefetch(ctx, sams[0]);
+    if (n_sams > 0 && pp_get_parser(ctx) == 0) pp_tok_prefetch(ctx, sams[0]);
     char ebuf[1024];
     pp_fasta* fa = pp_fasta_load(assembly, ebuf, sizeof ebuf);
     if (!fa) return pp_ctx_fail(ctx, PP_ERR_INPUT, ebuf);
@@ -269,20 +278,48 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     pp_shards* shards = nullptr;
     std::string tok_timing;
     HostCopy tok_copy;                       // the tokenised arrays back on the host (several GPUs: the sharder works there)
+    bool need_host_filter = false;
     if (debug) pp_polish_set_debug(ctx, 1);
     // Pass 0 parses the SAM text in HBM (tok_kernels.cu).  Anything unusual - PP_TOK_HOST, or a data error raised by the polish
     // kernels, whose message needs read / reference names - repeats the load with the host packer (pass 1), which decides.
-    for (int pass = (!debug && n_sams > 0 && pp_get_parser(ctx) == 0) ? 0 : 1; pass < 2; ++pass) {
+    for (int pass = ((n_sams > 0 && pp_get_parser(ctx) == 0) || ff) ? 0 : 1; pass < 2; ++pass) {
+        if (ff && (pass == 1 || pp_get_parser(ctx) != 0)) { need_host_filter = true; break; }
         jobs.assign(n_shards, ShardJob());
         memset(&alns, 0, sizeof alns);
         bool resident = false;
         rc = PP_OK;
         std::string log;
-        if (pass == 0) {
+        if (pass == 0 && ff) {
+            // filter (filter.rs:26-37) and the load of polish in one pass over the text: both files go to HBM once, the filter's
+            // verdict becomes the ZP flag of the tokenised records (what ZP:Z:fail does after a round trip through two files)
+            pp_filter_result fres;
+            pp_filter_file_stats fs;
+            memset(&fres, 0, sizeof fres);
+            pp_fused_polish fuse;
+            memset(&fuse, 0, sizeof fuse);
+            fuse.fasta = fa; fuse.careful = prm->careful;
+            rc = pp_filter_files_device(ctx, sams[0], sams[1], ff->out1, ff->out2, &ff->prm, &fres, &fs, &fuse);
+            if (rc == PP_OK && fuse.rc == PP_TOK_HOST) rc = PP_TOK_HOST;
+            if (rc == PP_TOK_HOST) { need_host_filter = true; pass = 0; break; }
+            if (rc != PP_OK) { pp_fasta_free(fa); return rc; }
+            static const char* nm[4] = {"fr", "rf", "ff", "rr"};
+            char tmp[512];
+            for (int k = 0; k < 2; ++k) {
+                snprintf(tmp, sizeof tmp, "%s: %s alignments, %s pass the insert-size filter, %s fail\n", sams[k], fmt_thousands(fs.alignments[k]).c_str(),
+                         fmt_thousands(fs.pass[k]).c_str(), fmt_thousands(fs.fail[k]).c_str());
+                log += tmp;
+            }
+            snprintf(tmp, sizeof tmp, "orientation %s, insert size thresholds %u - %u\n", fres.orientation < 4 ? nm[fres.orientation] : ff->orientation.c_str(), fres.low, fres.high);
+            log += tmp;
+            if (n_shards > 1 || debug) rc = tok_copy.fetch(ctx, &alns);
+            if (rc != PP_OK) { pp_fasta_free(fa); return rc; }
+            resident = n_shards == 1;
+            alns.n_aln = fuse.n_aln;
+        } else if (pass == 0) {
             uint64_t n_aln = 0;
             rc = tokenise_files(ctx, fa, sams, n_sams, prm->careful != 0, log, tok_timing, &n_aln);
             if (rc == PP_TOK_HOST) continue;
-            if (rc == PP_OK && n_shards > 1) rc = tok_copy.fetch(ctx, &alns);
+            if (rc == PP_OK && (n_shards > 1 || debug)) rc = tok_copy.fetch(ctx, &alns);   // several GPUs: the sharder; --debug: allele strings of the TSV
             if (rc != PP_OK) { pp_fasta_free(fa); return rc; }
             resident = n_shards == 1;
             alns.n_aln = n_aln;
@@ -322,10 +359,30 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
         if (pass == 0 && data_error) {
             if (shards) { pp_shards_free(shards); shards = nullptr; }
             tok_timing.clear();
+            if (ff) { need_host_filter = true; break; }
             continue;
         }
         if (verbose) fputs(log.c_str(), stderr);
         break;
+    }
+    if (need_host_filter) {
+        // Something the fused device path leaves to the text code (a malformed line, an empty file, host parsing asked for, a data
+        // error whose message needs names): the two commands one after the other, through files, exactly like the reference.
+        if (shards) { pp_shards_free(shards); shards = nullptr; }
+        pp_fasta_free(fa);
+        if (debug) pp_polish_set_debug(ctx, 0);
+        std::string t1 = ff->out1 ? ff->out1 : "", t2 = ff->out2 ? ff->out2 : "";
+        char tmpl1[] = "/tmp/polypolish_filtered_1_XXXXXX", tmpl2[] = "/tmp/polypolish_filtered_2_XXXXXX";
+        if (t1.empty()) { int fd = mkstemp(tmpl1); if (fd < 0) return pp_ctx_fail(ctx, PP_ERR_IO, "unable to create a temporary file for the filtered alignments"); close(fd); t1 = tmpl1; }
+        if (t2.empty()) { int fd = mkstemp(tmpl2); if (fd < 0) return pp_ctx_fail(ctx, PP_ERR_IO, "unable to create a temporary file for the filtered alignments"); close(fd); t2 = tmpl2; }
+        int frc = pp_filter_files(ctx, sams[0], sams[1], t1.c_str(), t2.c_str(), ff->orientation.c_str(), ff->prm.low_pct, ff->prm.high_pct, verbose);
+        if (frc == PP_OK) {
+            const char* fsams[2] = {t1.c_str(), t2.c_str()};
+            frc = polish_files_impl(ctxs, n_ctx, assembly, fsams, 2, prm, debug_path, out_fasta, out_len, verbose, nullptr);
+        }
+        if (!ff->out1) unlink(t1.c_str());
+        if (!ff->out2) unlink(t2.c_str());
+        return frc;
     }
     uint64_t n_used = 0;
     for (uint32_t s = 0; s < n_shards && rc == PP_OK; ++s) {
@@ -419,6 +476,32 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     *out_fasta = buf;
     *out_len = out.size();
     return PP_OK;
+}
+
+// filter::filter (filter.rs:26-37) then polish::polish (polish.rs:26-38) on its output, as one call: same FASTA as running the two
+// commands through intermediate files, which are only written when the caller names them.
+extern "C" int pp_filter_polish_files(pp_ctx* ctx, const char* assembly, const char* in1, const char* in2, const char* out1, const char* out2,
+                                      const char* orientation, double low, double high, const pp_polish_params* prm, char** out_fasta,
+                                      uint64_t* out_len, int verbose) {
+    if (!ctx) return PP_ERR_ARG;
+    if (!in1 || !in2 || !orientation) return pp_ctx_fail(ctx, PP_ERR_ARG, "pp_filter_polish_files: null argument");
+    {   // check_inputs filter.rs:40-53
+        std::vector<std::string> a = {in1, in2};
+        if (out1) a.push_back(out1);
+        if (out2) a.push_back(out2);
+        for (size_t i = 0; i < a.size(); ++i)
+            for (size_t j = 0; j < i; ++j)
+                if (a[i] == a[j]) return pp_ctx_fail(ctx, PP_ERR_INPUT, "--in1, --in2, --out1 and --out2 must all have unique values");
+    }
+    if (!(low > 0.0 && low < 50.0)) return pp_ctx_fail(ctx, PP_ERR_INPUT, "--low must be greater than 0 and less than 50");
+    if (!(high > 50.0 && high < 100.0)) return pp_ctx_fail(ctx, PP_ERR_INPUT, "--high must be greater than 50 and less than 100");
+    FusedFilter ff;
+    ff.orientation = orientation;
+    ff.prm.orientation = ff.orientation == "auto" ? -1 : ff.orientation == "fr" ? 0 : ff.orientation == "rf" ? 1 : ff.orientation == "ff" ? 2 : ff.orientation == "rr" ? 3 : 4;
+    ff.prm.low_pct = low; ff.prm.high_pct = high; ff.prm.n_names = 0;
+    ff.out1 = out1; ff.out2 = out2;
+    const char* sams[2] = {in1, in2};
+    return polish_files_impl(&ctx, 1, assembly, sams, 2, prm, nullptr, out_fasta, out_len, verbose, &ff);
 }
 
 extern "C" int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* const* sams, int n_sams,

@@ -190,12 +190,10 @@ __device__ __forceinline__ unsigned long long make_sig(const uint8_t* pool, uint
 }
 
 __device__ __forceinline__ uint32_t asc2nib(uint32_t c) {   // ASCII draft base -> BAM code, 0 = not one of the 15 letters (never equals a read code)
-    switch (c) {
-        case 'A': return 1; case 'C': return 2; case 'M': return 3; case 'G': return 4; case 'R': return 5;
-        case 'S': return 6; case 'V': return 7; case 'T': return 8; case 'W': return 9; case 'Y': return 10;
-        case 'H': return 11; case 'K': return 12; case 'D': return 13; case 'B': return 14; case 'N': return 15;
-        default: return 0;
-    }
+    // codes of 'A'..'P' (lo) and 'Q'..'Z' (hi), four bits per letter: A1 B14 C2 D13 G4 H11 K12 M3 N15 | R5 S6 T8 V7 W9 Y10
+    const unsigned long long lo = 0xf30c00b400d2e1ull, hi = 0xa09708650ull;
+    const uint32_t i = c - 'A';
+    return i < 26u ? (uint32_t)((i < 16u ? lo >> (4 * i) : hi >> (4 * (i - 16u))) & 15ull) : 0u;
 }
 
 // block-wide exclusive scan of one u64 per thread (NT threads); returns exclusive prefix, total in *total
@@ -588,6 +586,7 @@ struct TileShared {
     double depth[TL_T];                                // ordered f64 depth, valid in flagged sub-tiles
     unsigned long long dn[TL_DN_WORDS + 2];            // 4-bit draft codes, 16 per word, position -32 first
     WalkStage wstage[TL_THREADS / 32];                 // ordered-depth merge staging, one per warp
+    uint32_t wqueue[TL_THREADS / 32][64];              // per warp: sorted slots waiting for the general walk
     unsigned long long s_warp[TL_THREADS / 32];
     unsigned long long s_total;
     long long s_delta[TL_THREADS / 32];
@@ -758,50 +757,34 @@ __device__ uint32_t general_walk(TileCtx<BITS>& S, const TileRec& r, unsigned lo
     return nkept;
 }
 
-// The fast path: a 4-bit read of at most 192 bases whose CIGAR is one M / = run.  The read sits in 24 registers (six
-// 16-byte loads; a reverse-strand read is loaded back to front and bit-reversed, which is its reverse complement); the draft
-// comes from the tile's shared-memory copy through one native 32-bit funnel shift per 8 bases.  Pass 1 XORs 8 bases at a time
-// and only records WHICH words differ (one bit per word: straight-line code, no divergence); pass 2 visits the few words that
-// do (about one word in two reads), reloads them and counts each differing base.  Returns kept entries, or NONE32 = "take the
-// general walk" (a homopolymer tail of 32+ bases).
+// The fast path: a 4-bit read of at most 192 bases whose CIGAR is one M / = run.  The effective read is a stream of 32-bit
+// words, 8 bases each, base i = nibble pad + i (a reverse-strand read is taken back to front and bit-reversed, which is its
+// reverse complement); the draft comes from the tile's shared-memory copy through one native funnel shift per word.
+//   pass 1: sixteen bytes of the read at a time (L1: the chunk loop prefetched them), XOR against the draft, and only record
+//           WHICH words differ - straight-line code, no divergence, a dozen live registers;
+//   pass 2: the two edge words (partly outside the kept entries or the tile) and the few words that differ (about one word in
+//           two reads) are reloaded and every differing base is counted.
+// Returns kept entries, or NONE32 = "take the general walk" (a homopolymer tail of 8+ bases, a read shorter than 8).
 __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, unsigned long long aln) {
     const uint32_t len = r.len_nc & 0xFFFFu;
     const bool rc = r.flags & TR_RC;
     const uint4* sp = reinterpret_cast<const uint4*>(S.d.seq_pool + (size_t)r.seq_off * 16);
+    const uint32_t* sp32 = reinterpret_cast<const uint32_t*>(sp);
     const uint32_t nq = (len + 31) >> 5;                       // 16-byte quads that hold the read
-    uint32_t w[24];                                            // effective read, 8 bases per word, base i = nibble pad + i
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if ((uint32_t)j < nq) q = __ldg(sp + (rc ? nq - 1 - j : (uint32_t)j));
-        w[4 * j + 0] = rc ? __brev(q.w) : q.x;
-        w[4 * j + 1] = rc ? __brev(q.z) : q.y;
-        w[4 * j + 2] = rc ? __brev(q.y) : q.z;
-        w[4 * j + 3] = rc ? __brev(q.x) : q.w;
-    }
     const uint32_t pad = rc ? 32 * nq - len : 0;
-    // ---- trim (alignment.rs:364-378) on the last min(len, 32) effective bases
+    if (len < 8) return NONE32;
+    // ---- trim (alignment.rs:364-378): how many of the last bases equal the last one.  The last 8 effective bases as one word.
     uint32_t run;
     {
-        unsigned long long t0, t1;
-        uint32_t tl, nf;                                       // window nibble of the last base; first window nibble that is a base
-        const uint32_t avail = min(len, 32u);
-        if (!rc) {
-            load_nib32(reinterpret_cast<const unsigned long long*>(sp), len > 32 ? len - 32 : 0u, t0, t1);
-            tl = avail - 1; nf = 0;
-        } else {
-            const unsigned long long* s64 = reinterpret_cast<const unsigned long long*>(sp);
-            t0 = pp_brev64(s64[1]); t1 = pp_brev64(s64[0]);
-            tl = 31; nf = 32 - avail;
-        }
-        const uint32_t lastc = (uint32_t)((tl < 16 ? t0 >> (4 * tl) : t1 >> (4 * (tl - 16))) & 15ull);
-        const unsigned long long pat = 0x1111111111111111ull * lastc;
-        unsigned long long m0 = nibble_nonzero(t0 ^ pat) & nibmask((int)tl + 1), m1 = nibble_nonzero(t1 ^ pat) & nibmask((int)tl + 1 - 16);
-        int nd = m1 ? 16 + ((63 - __clzll((long long)m1)) >> 2) : (m0 ? ((63 - __clzll((long long)m0)) >> 2) : -1);
-        if (nd < (int)nf) { if (len > 32) return NONE32; run = avail; }
-        else run = tl - (uint32_t)nd;
+        uint32_t t8;
+        if (rc) t8 = __brev(__ldg(sp32));                      // effective base len-8+n = complement of stored base 7-n
+        else { const uint32_t o = len - 8; t8 = __funnelshift_r(__ldg(sp32 + (o >> 3)), __ldg(sp32 + (o >> 3) + 1), (o & 7) * 4); }
+        const uint32_t x = t8 ^ ((t8 >> 28) * 0x11111111u);
+        const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+        if (nz == 0) return NONE32;                            // 8+ equal bases at the end: the general walk counts them
+        run = 7u - ((31u - (uint32_t)__clz((int)nz)) >> 2);
     }
-    const uint32_t nkept = (len - run >= 1) ? len - run - 1 : 0;
+    const uint32_t nkept = len - run - 1;                       // run < 8 <= len
     if ((unsigned long long)r.gstart + nkept > r.cend) { report_error(S.d.st, aln, ERR_OOB); return 0; }
     S.add_interval(r.gstart, nkept, r.k != 1);
     // ---- compare: word m holds nibbles [8 m, 8 m + 8) = tile-relative positions relq + 8 m ...
@@ -809,28 +792,34 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
     const long long a64 = max(g0, 0ll), b64 = min(g0 + (long long)nkept, (long long)TL_T);
     if (b64 <= a64) return nkept;
     const int relq = (int)g0 - (int)pad;
-    const uint32_t first = (uint32_t)((int)a64 - relq), lastn = (uint32_t)((int)b64 - 1 - relq);   // first / last valid nibble of w[]
+    const uint32_t first = (uint32_t)((int)a64 - relq), lastn = (uint32_t)((int)b64 - 1 - relq);   // first / last valid nibble of the stream
     const uint32_t m_first = first >> 3, m_last = lastn >> 3;
     const uint32_t fmask = 0xFFFFFFFFu << ((first & 7) * 4), lmask = 0xFFFFFFFFu >> ((7 - (lastn & 7)) * 4);
-    const uint32_t vmask = (2u << m_last) - (1u << m_first);    // words m_first .. m_last
     const uint32_t emask = (1u << m_first) | (1u << m_last);
+    const uint32_t inner = ((2u << m_last) - (1u << m_first)) & ~emask;   // words strictly between the edge words
     const uint32_t* dn32 = reinterpret_cast<const uint32_t*>(S.sh.dn);
-    const int o0 = relq + TL_DN_HALO;                           // nibble offset of word 0 in the staged draft (valid words: > 0)
-    const int i0 = o0 >> 3;                                     // floor
+    const int o0 = relq + TL_DN_HALO;                           // nibble offset of word 0 in the staged draft
+    const int i0 = o0 >> 3;                                     // floor; i0 + m >= 0 for every word of a group that holds a valid word
     const uint32_t sh4 = (uint32_t)(o0 & 7) * 4;
-    uint32_t mm = 0;                                            // words that differ from the draft
+    uint32_t bits = 0;
 #pragma unroll
-    for (int m = 0; m < 24; ++m) {
-        if (vmask & (1u << m)) {
-            uint32_t x = w[m] ^ __funnelshift_r(dn32[i0 + m], dn32[i0 + m + 1], sh4);
-            if (emask & (1u << m)) { if ((uint32_t)m == m_first) x &= fmask; if ((uint32_t)m == m_last) x &= lmask; }
-            if (x) mm |= 1u << m;
+    for (int g = 0; g < 6; ++g) {
+        if ((inner >> (4 * g)) & 15u) {
+            const uint4 q = __ldg(sp + (rc ? nq - 1 - g : (uint32_t)g));
+            const uint32_t w0 = rc ? __brev(q.w) : q.x, w1 = rc ? __brev(q.z) : q.y, w2 = rc ? __brev(q.y) : q.z, w3 = rc ? __brev(q.x) : q.w;
+            const uint32_t* dp = dn32 + (i0 + 4 * g);
+            const uint32_t d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3], d4 = dp[4];
+            if (w0 != __funnelshift_r(d0, d1, sh4)) bits |= 1u << (4 * g);
+            if (w1 != __funnelshift_r(d1, d2, sh4)) bits |= 2u << (4 * g);
+            if (w2 != __funnelshift_r(d2, d3, sh4)) bits |= 4u << (4 * g);
+            if (w3 != __funnelshift_r(d3, d4, sh4)) bits |= 8u << (4 * g);
         }
     }
+    uint32_t mm = (bits & inner) | emask;
     while (mm) {
         const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
         mm &= mm - 1;
-        uint32_t wv = __ldg(reinterpret_cast<const uint32_t*>(sp) + (rc ? 4 * nq - 1 - m : m));
+        uint32_t wv = __ldg(sp32 + (rc ? 4 * nq - 1 - m : m));
         if (rc) wv = __brev(wv);
         uint32_t x = wv ^ __funnelshift_r(dn32[i0 + (int)m], dn32[i0 + (int)m + 1], sh4);
         if (m == m_first) x &= fmask;
@@ -1063,19 +1052,19 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             const uint32_t nz = (uint32_t)((size_t)((char*)sh.depth - (char*)sh.cdiff) / 16);   // cdiff, mdiff, ex, del, oth
             for (uint32_t i = tid; i < nz; i += TL_THREADS) z[i] = make_uint4(0, 0, 0, 0);
             if (BITS == 4) {
-                for (uint32_t wi = tid; wi < TL_DN_WORDS + 2; wi += TL_THREADS) {
-                    const long long g0 = (long long)P0 - TL_DN_HALO + 16ll * wi;
-                    unsigned long long v = 0;
-                    if (g0 >= 0 && g0 + 16 <= (long long)d.G) {
-                        const uint4 q = *reinterpret_cast<const uint4*>(d.draft + g0);   // draft is 16 B aligned, g0 a multiple of 16
-                        const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+                uint32_t* dn32w = reinterpret_cast<uint32_t*>(sh.dn);
+                for (uint32_t wi = tid; wi < 2 * (TL_DN_WORDS + 2); wi += TL_THREADS) {      // 8 positions per 32-bit word
+                    const long long g0 = (long long)P0 - TL_DN_HALO + 8ll * wi;
+                    uint32_t v = 0;
+                    if (g0 >= 0 && g0 + 8 <= (long long)d.G) {
+                        const uint2 q = *reinterpret_cast<const uint2*>(d.draft + g0);       // draft is 16 B aligned, g0 a multiple of 8
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v |= (unsigned long long)asc2nib((ws[i >> 2] >> ((i & 3) * 8)) & 255u) << (4 * i);
+                        for (int i = 0; i < 8; ++i) v |= asc2nib(((i < 4 ? q.x : q.y) >> ((i & 3) * 8)) & 255u) << (4 * i);
                     } else {
-                        for (int i = 0; i < 16; ++i)
-                            if (g0 + i >= 0 && g0 + i < (long long)d.G) v |= (unsigned long long)asc2nib(d.draft[g0 + i]) << (4 * i);
+                        for (int i = 0; i < 8; ++i)
+                            if (g0 + i >= 0 && g0 + i < (long long)d.G) v |= asc2nib(d.draft[g0 + i]) << (4 * i);
                     }
-                    sh.dn[wi] = v;
+                    dn32w[wi] = v;
                 }
             }
         }
@@ -1093,27 +1082,63 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 if (lane == 0) c = atomicAdd(&sh.next, 32u);
                 return lo + __shfl_sync(0xffffffffu, c, 0);
             };
-            uint32_t c_a = grab();
-            uint32_t aln_a = (c_a + lane < hi) ? d.sval[c_a + lane] : 0u;
-            TileRec rec_a = load_rec<BITS>(d, aln_a);
-            while (c_a < hi) {
-                const uint32_t c_b = grab();
-                const uint32_t aln_b = (c_b + lane < hi) ? d.sval[c_b + lane] : 0u;
-                const TileRec rec_b = load_rec<BITS>(d, aln_b);                       // (alignment 0's record past the end of the list)
-                const uint32_t i = c_a + lane;
-                if (i < hi) {
-                    uint32_t nk = NONE32;
-                    if (BITS == 4 && (rec_a.flags & TR_FAST)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), rec_a, aln_a);
-                    if (nk == NONE32) nk = general_walk<BITS>(S, rec_a, aln_a);
-                    d.wrec[i] = make_uint4(aln_a, rec_a.gstart, nk, rec_a.k);
+            // reads that need the general walk (indels, long reads, homopolymer tails) are queued per warp and walked 32 at a
+            // time on consecutive lanes instead of one lane at a time
+            uint32_t* wq = sh.wqueue[warp];
+            uint32_t nq_w = 0;                                                         // warp-uniform
+            auto drain = [&](uint32_t upto) {                                          // walks the first min(nq_w, 32) queued slots
+                const uint32_t take = min(nq_w, upto);
+                if (lane < take) {
+                    const uint32_t i = wq[lane];
+                    const uint32_t aln = d.sval[i];
+                    const TileRec r = load_rec<BITS>(d, aln);
+                    d.wrec[i] = make_uint4(aln, r.gstart, general_walk<BITS>(S, r, aln), r.k);
                 }
-                if (BITS == 4 && c_b + lane < hi) {                                    // the next read's bases towards L1
+                __syncwarp();
+                const uint32_t rest = nq_w - take;
+                const uint32_t keep = (lane < rest) ? wq[take + lane] : 0u;
+                __syncwarp();
+                if (lane < rest) wq[lane] = keep;
+                __syncwarp();
+                nq_w = rest;
+            };
+            // three chunks in flight: a is walked, b's records arrived (its bases are prefetched now), c's indices arrived (its
+            // records are requested now), d's indices are requested
+            uint32_t c_a = grab(), c_b = grab(), c_c = grab();
+            uint32_t aln_a = (c_a + lane < hi) ? d.sval[c_a + lane] : 0u;
+            uint32_t aln_b = (c_b + lane < hi) ? d.sval[c_b + lane] : 0u;
+            uint32_t aln_c = (c_c + lane < hi) ? d.sval[c_c + lane] : 0u;
+            TileRec rec_a = load_rec<BITS>(d, aln_a);
+            TileRec rec_b = load_rec<BITS>(d, aln_b);
+            while (c_a < hi) {
+                const uint32_t c_d = grab();
+                const uint32_t aln_d = (c_d + lane < hi) ? d.sval[c_d + lane] : 0u;
+                const TileRec rec_c = load_rec<BITS>(d, aln_c);                       // (alignment 0's record past the end of the list)
+                if (BITS == 4 && c_b + lane < hi) {                                    // the next chunk's bases towards L1
                     const uint8_t* nsp = d.seq_pool + (size_t)rec_b.seq_off * 16;
                     PP_PREFETCH_L1(nsp);
                     PP_PREFETCH_L1(nsp + 64);
                 }
-                c_a = c_b; aln_a = aln_b; rec_a = rec_b;
+                const uint32_t i = c_a + lane;
+                bool defer = false;
+                if (i < hi) {
+                    uint32_t nk = NONE32;
+                    if (BITS == 4 && (rec_a.flags & TR_FAST)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), rec_a, aln_a);
+                    if (nk == NONE32) defer = true;
+                    else d.wrec[i] = make_uint4(aln_a, rec_a.gstart, nk, rec_a.k);
+                }
+                const uint32_t dm = __ballot_sync(0xffffffffu, defer);
+                if (dm) {
+                    if (defer) wq[nq_w + (uint32_t)__popc(dm & ((1u << lane) - 1u))] = i;
+                    nq_w += (uint32_t)__popc(dm);
+                    __syncwarp();
+                    if (nq_w >= 32) drain(32);
+                }
+                c_a = c_b; c_b = c_c; c_c = c_d;
+                aln_a = aln_b; aln_b = aln_c; aln_c = aln_d;
+                rec_a = rec_b; rec_b = rec_c;
             }
+            while (nq_w) drain(32);
             // the long list: alignments of more than TL_LONG_E entries, looked at by every tile
             for (uint32_t i = long_lo + tid; i < long_hi; i += TL_THREADS) {
                 const uint32_t aln = d.sval[i];

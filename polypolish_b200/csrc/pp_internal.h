@@ -106,5 +106,13 @@ struct pp_filter_file_stats {
     float phase_ms[6];     // wall: 0 upload+index+parse, 1 intern+verify+emit, 2 filter proper, 3 output lengths+scan, 4 output bytes, 5 download+write
     uint32_t launches;
 };
+// filter + polish without the intermediate files: the request to tokenise the resident texts for polish, and what came of it
+struct pp_fused_polish {
+    const pp_fasta* fasta;
+    int careful;
+    pp_tok_stats stats[2];
+    uint64_t n_aln;
+    int rc;                // PP_OK: the filtered alignments are the resident dataset; PP_TOK_HOST: the host text path must do it
+};
 int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2, const pp_filter_params* prm,
-                           pp_filter_result* res, pp_filter_file_stats* fs);
+                           pp_filter_result* res, pp_filter_file_stats* fs, pp_fused_polish* fuse);

@@ -1097,19 +1097,28 @@ static int ftok_lines(pp_ctx* ctx, TokState* T, int which, const uint8_t* text, 
 }
 
 struct TokFilterBufs {                 // device buffers of the filter text path, kept in the tokeniser state
-    DevBuf lines[2], tmp[2], mate[2], table, out, status;
+    DevBuf lines[2], tmp[2], mate[2], table, out, status, passkeep;
 };
 
 static void free_filter_bufs(TokFilterBufs* b) {
     for (int k = 0; k < 2; ++k) { b->lines[k].release(); b->tmp[k].release(); b->mate[k].release(); }
-    b->table.release(); b->out.release(); b->status.release();
+    b->table.release(); b->out.release(); b->status.release(); b->passkeep.release();
     delete b;
 }
 
+// The filter's verdict as the polish records' ZP flag (alignment.rs:72-74): alignment i of the file failed -> PP_FLAG_ZPFAIL.
+__global__ void __launch_bounds__(256) k_apply_pass(uint8_t* __restrict__ flags, const uint8_t* __restrict__ pass, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n && !pass[i]) flags[i] |= PP_FLAG_ZPFAIL;
+}
+
 // `polypolish filter` with the SAM text handled on the device.  PP_OK, PP_TOK_HOST (the host path must do it) or an error
-// (the filter's own: no usable pairs, ambiguous orientation; I/O; CUDA).
+// (the filter's own: no usable pairs, ambiguous orientation; I/O; CUDA).  out1 / out2 may be null (no filtered SAM is written).
+// With `fuse`: the two texts, still resident, are then tokenised for `polish` (pp_tok_*) with the filter's verdict taking the
+// place of the ZP:Z:fail tag the reference would have written and re-read (filter.rs:334-342, alignment.rs:72-74): the resident
+// dataset is what `polish` would load from the filtered files.  fuse->rc = PP_OK / PP_TOK_HOST for that second part.
 int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2, const pp_filter_params* prm_in,
-                           pp_filter_result* res, pp_filter_file_stats* fs) {
+                           pp_filter_result* res, pp_filter_file_stats* fs, pp_fused_polish* fuse) {
     CK(cudaSetDevice(ctx->device));
     TokState* T = nullptr;
     int rc = tok_state(ctx, &T);
@@ -1214,6 +1223,9 @@ int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const 
     // ---- output text, file by file: lengths -> offsets -> bytes -> the output file
     float d2h_ms = 0;
     for (int k = 0; k < 2; ++k) {
+        fs->pass[k] = np[k];
+        fs->fail[k] = n_al[k] - np[k];
+        if (!outs[k]) continue;
         const uint64_t nl = fd[k].n_lines;
         DevBuf& offs = B.table;                                                 // the intern table is done with: reuse it
         CK(offs.ensure((nl + 2) * 8));
@@ -1265,13 +1277,45 @@ int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const 
         if (wrc == PP_ERR_IO) return ctx->fail(PP_ERR_IO, std::string("unable to write alignments to \"") + outs[k] + "\"");
         if (wrc == PP_ERR_CUDA) return ctx->fail_cuda((cudaError_t)cuda_err, "filtered SAM download", __FILE__, __LINE__);
         lap(5);
-        fs->pass[k] = np[k];
-        fs->fail[k] = n_al[k] - np[k];
         fs->out_bytes[k] = out_n;
     }
     fs->h2d_ms = h2d_ms;
     fs->d2h_ms = d2h_ms;
-    fs->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     fs->launches = launches;
+    if (fuse) {
+        // the verdicts move out of the context's scratch buffer (the tokeniser uses it), then both texts are tokenised in place
+        CK(B.passkeep.ensure(n_al[0] + n_al[1] + 64));
+        uint8_t* keep = B.passkeep.as<uint8_t>();
+        CK(cudaMemcpyAsync(keep, d_pass[0], n_al[0], cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(keep + n_al[0], d_pass[1], n_al[1], cudaMemcpyDeviceToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        fuse->rc = PP_TOK_HOST;
+        int bits = 4;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            rc = pp_tok_begin(ctx, fuse->fasta, fuse->careful, bits);
+            if (rc != PP_OK) return rc;
+            T->expect_total = fd[0].n + fd[1].n;
+            memset(fuse->stats, 0, sizeof fuse->stats);
+            for (int k = 0; k < 2 && rc == PP_OK; ++k) {
+                rc = tok_process(ctx, T, fd[k].text, fd[k].n, fd[k].unterminated != 0, &fuse->stats[k]);
+                if (rc == PP_OK && fuse->stats[k].alignments != n_al[k]) rc = PP_TOK_HOST;      // (cannot happen: same lines, same rule)
+            }
+            if (rc == PP_TOK_NEED8 && bits == 4) { bits = 8; continue; }
+            if (rc == PP_TOK_NEED8) rc = PP_TOK_HOST;
+            if (rc < 0) return rc;
+            if (rc == PP_OK) {
+                const uint64_t n = n_al[0] + n_al[1];
+                k_apply_pass<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctx->b[B_FLAGS].as<uint8_t>(), keep, n);
+                CK(cudaStreamSynchronize(s));
+                CK(cudaGetLastError());
+                rc = pp_tok_finish(ctx);
+                if (rc < 0) return rc;
+                fuse->n_aln = n;
+            }
+            fuse->rc = rc;
+            break;
+        }
+    }
+    fs->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return PP_OK;
 }

@@ -229,3 +229,42 @@ def test_filter_to_pipes_and_devices(ctx, oracle, tmp_path):
     t.join(timeout=60)
     assert got["out1"] == exp["out2"]
     assert open(tmp_path / "plain.sam", "rb").read() == exp["out1"]
+
+
+@pytest.mark.parametrize("seed,opts", [(14, {}), (15, dict(careful=True)), (16, dict(max_errors=3, min_depth=3))])
+def test_filter_then_polish_in_one_call(ctx, oracle, tmp_path, seed, opts):
+    """pp_filter_polish_files: `filter` + `polish` without the intermediate files == the two reference commands
+    one after the other (filter.rs:334-342 writes ZP:Z:fail, alignment.rs:72-74 reads it back)."""
+    syn = api.Synth(seed=seed, n_contigs=2, contig_len=30_000, depth=40)
+    fa, sams = syn.write(tmp_path)
+    fo = oracle.filter(sams[0], sams[1])
+    o1, o2 = tmp_path / "o1.sam", tmp_path / "o2.sam"
+    o1.write_bytes(fo["out1"])
+    o2.write_bytes(fo["out2"])
+    assert fo["out1"].count(b"ZP:Z:fail") + fo["out2"].count(b"ZP:Z:fail") > 20
+    exp = oracle.polish(fa, [o1, o2], **opts)["fasta"]
+    ctx.set_parser(0)
+    assert ctx.filter_polish_files(fa, sams[0], sams[1], **opts) == exp                     # nothing written
+    f1, f2 = tmp_path / "f1.sam", tmp_path / "f2.sam"
+    assert ctx.filter_polish_files(fa, sams[0], sams[1], f1, f2, **opts) == exp             # filtered files written on the way
+    assert f1.read_bytes() == fo["out1"] and f2.read_bytes() == fo["out2"]
+    ctx.set_parser(1)                                                                       # host text path: the two commands through files
+    try:
+        assert ctx.filter_polish_files(fa, sams[0], sams[1], **opts) == exp
+    finally:
+        ctx.set_parser(0)
+
+
+def test_filter_then_polish_errors_and_odd_text(ctx, oracle, tmp_path):
+    """The fused call hands anything unusual to the text code: same errors as the reference's two commands."""
+    syn = api.Synth(seed=18, contig_len=20_000, depth=30)
+    fa, sams = syn.write(tmp_path)
+    # a read group without SEQ in file 1 -> polish's error, worded by the host path
+    bad = tmp_path / "bad_1.sam"
+    bad.write_bytes(open(sams[0], "rb").read() + b"zz\t0\tcontig_1\t100\t60\t50M\t*\t0\t0\t*\t*\tNM:i:0\n")
+    with pytest.raises(pp.PolypolishError) as e:
+        ctx.filter_polish_files(fa, bad, sams[1])
+    assert "no alignments for read zz contain sequence" in e.value.msg
+    with pytest.raises(pp.PolypolishError) as e:
+        ctx.filter_polish_files(fa, sams[0], sams[1], low=60.0)
+    assert "--low must be greater than 0 and less than 50" in e.value.msg

@@ -91,6 +91,8 @@ def test_config3_filter_then_polish_full_size(ctx, oracle, config2):
     assert _sha_file(f1) == _sha_file(o1) and _sha_file(f2) == _sha_file(o2)
     exp = oracle.polish(fa, [o1, o2])
     assert _sha(ctx.polish_files(fa, [f1, f2])) == _sha(exp["fasta"])
+    # and as one call, without the 1.25 GB of intermediate files (pp_filter_polish_files)
+    assert _sha(ctx.filter_polish_files(fa, sams[0], sams[1])) == _sha(exp["fasta"])
     for p in (f1, f2, o1, o2):
         os.remove(p)
 
