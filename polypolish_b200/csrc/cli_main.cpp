@@ -123,6 +123,26 @@ static uint32_t parse_u32(const char* flag, const char* s) {
     return (uint32_t)v;
 }
 
+// A one-shot process pays CUDA's start-up for every GPU the driver shows it (about a second on an 8-GPU box).  Before the first
+// CUDA call the process is therefore narrowed to the GPUs it will use: CUDA_VISIBLE_DEVICES = entries [device, device + gpus) of
+// the caller's own list (or of 0, 1, 2, ... when the variable is not set).  Inside the process the devices are then 0 .. gpus-1.
+static bool restrict_visible_devices(int device, int gpus) {   // true: the chosen GPUs are now devices 0 .. gpus-1 of this process
+    std::vector<std::string> ids;
+    if (const char* cur = getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string s = cur, item;
+        for (size_t i = 0; i <= s.size(); ++i) {
+            if (i == s.size() || s[i] == ',') { if (!item.empty()) ids.push_back(item); item.clear(); }
+            else item += s[i];
+        }
+        if ((int)ids.size() < device + gpus) return false;    // not enough entries: leave it to pp_create to report
+    } else {
+        for (int i = 0; i < device + gpus; ++i) ids.push_back(std::to_string(i));
+    }
+    std::string v;
+    for (int i = device; i < device + gpus; ++i) { if (!v.empty()) v += ','; v += ids[(size_t)i]; }
+    return setenv("CUDA_VISIBLE_DEVICES", v.c_str(), 1) == 0;
+}
+
 // POLYPOLISH_TIMING=1: wall-clock marks on stderr (process start-up vs the command itself)
 static void mark(const char* what) {
     static const auto t0 = std::chrono::steady_clock::now();
@@ -168,9 +188,10 @@ int main(int argc, char** argv) {
         }
         if (pos.empty()) usage_error("the following required arguments were not provided:\n  <ASSEMBLY>");
         if (gpus < 1) gpus = 1;
+        const int base = restrict_visible_devices(device, gpus) ? 0 : device;
         std::vector<pp_ctx*> ctxs(gpus, nullptr);
         for (int g = 0; g < gpus; ++g)
-            if (pp_create(device + g, &ctxs[g]) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
+            if (pp_create(base + g, &ctxs[g]) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
         mark("contexts created");
         if (host_parse) pp_set_parser(ctxs[0], 1);
         std::vector<const char*> sams;
@@ -212,8 +233,9 @@ int main(int argc, char** argv) {
         }
         if (in1.empty() || in2.empty() || out1.empty() || out2.empty())
             usage_error("the following required arguments were not provided:\n  --in1 <IN1>\n  --in2 <IN2>\n  --out1 <OUT1>\n  --out2 <OUT2>");
+        const int base = restrict_visible_devices(device, 1) ? 0 : device;
         pp_ctx* ctx = nullptr;
-        if (pp_create(device, &ctx) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
+        if (pp_create(base, &ctx) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
         if (host_parse) pp_set_parser(ctx, 1);
         if (!quiet) fprintf(stderr, "Starting Polypolish filter (B200 build %s)\n\n", pp_version());
         int rc = pp_filter_files(ctx, in1.c_str(), in2.c_str(), out1.c_str(), out2.c_str(), orientation.c_str(), low, high, quiet ? 0 : 1);

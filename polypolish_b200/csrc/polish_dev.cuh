@@ -760,8 +760,8 @@ __device__ uint32_t general_walk(TileCtx<BITS>& S, const TileRec& r, unsigned lo
 // The fast path: a 4-bit read of at most 192 bases whose CIGAR is one M / = run.  The effective read is a stream of 32-bit
 // words, 8 bases each, base i = nibble pad + i (a reverse-strand read is taken back to front and bit-reversed, which is its
 // reverse complement); the draft comes from the tile's shared-memory copy through one native funnel shift per word.
-//   pass 1: sixteen bytes of the read at a time (L1: the chunk loop prefetched them), XOR against the draft, and only record
-//           WHICH words differ - straight-line code, no divergence, a dozen live registers;
+//   pass 1: the read in six 16-byte loads issued together, XOR against the draft four words at a time, and only record WHICH
+//           words differ - straight-line code, no divergence;
 //   pass 2: the two edge words (partly outside the kept entries or the tile) and the few words that differ (about one word in
 //           two reads) are reloaded and every differing base is counted.
 // Returns kept entries, or NONE32 = "take the general walk" (a homopolymer tail of 8+ bases, a read shorter than 8).
@@ -801,12 +801,19 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
     const int o0 = relq + TL_DN_HALO;                           // nibble offset of word 0 in the staged draft
     const int i0 = o0 >> 3;                                     // floor; i0 + m >= 0 for every word of a group that holds a valid word
     const uint32_t sh4 = (uint32_t)(o0 & 7) * 4;
+    // all six 16-byte loads of the read are issued before the first one is needed (memory-level parallelism: with both CTAs'
+    // shared memory there is next to no L1 left to prefetch into)
+    uint4 q[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g) {
+        q[g] = make_uint4(0, 0, 0, 0);
+        if ((inner >> (4 * g)) & 15u) q[g] = __ldg(sp + (rc ? nq - 1 - g : (uint32_t)g));
+    }
     uint32_t bits = 0;
 #pragma unroll
     for (int g = 0; g < 6; ++g) {
         if ((inner >> (4 * g)) & 15u) {
-            const uint4 q = __ldg(sp + (rc ? nq - 1 - g : (uint32_t)g));
-            const uint32_t w0 = rc ? __brev(q.w) : q.x, w1 = rc ? __brev(q.z) : q.y, w2 = rc ? __brev(q.y) : q.z, w3 = rc ? __brev(q.x) : q.w;
+            const uint32_t w0 = rc ? __brev(q[g].w) : q[g].x, w1 = rc ? __brev(q[g].z) : q[g].y, w2 = rc ? __brev(q[g].y) : q[g].z, w3 = rc ? __brev(q[g].x) : q[g].w;
             const uint32_t* dp = dn32 + (i0 + 4 * g);
             const uint32_t d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3], d4 = dp[4];
             if (w0 != __funnelshift_r(d0, d1, sh4)) bits |= 1u << (4 * g);
@@ -855,8 +862,10 @@ __device__ __forceinline__ TileRec load_rec(const DevData& d, uint32_t aln) {
 #define DW_RUNS 4
 #if defined(PP_EMULATE)
 #define PP_PREFETCH_L1(p) ((void)(p))
+#define PP_PREFETCH_L2(p) ((void)(p))
 #else
 #define PP_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#define PP_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #endif
 template <int BITS>
 __device__ void depth_walk_steps(const DevData& d, TileShared& sh, uint32_t P0, uint32_t sub, uint32_t lb, uint32_t long_lo, uint32_t long_hi) {
@@ -1114,10 +1123,10 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 const uint32_t c_d = grab();
                 const uint32_t aln_d = (c_d + lane < hi) ? d.sval[c_d + lane] : 0u;
                 const TileRec rec_c = load_rec<BITS>(d, aln_c);                       // (alignment 0's record past the end of the list)
-                if (BITS == 4 && c_b + lane < hi) {                                    // the next chunk's bases towards L1
+                if (BITS == 4 && c_b + lane < hi) {                                    // the next chunk's bases towards L2
                     const uint8_t* nsp = d.seq_pool + (size_t)rec_b.seq_off * 16;
-                    PP_PREFETCH_L1(nsp);
-                    PP_PREFETCH_L1(nsp + 64);
+                    PP_PREFETCH_L2(nsp);
+                    PP_PREFETCH_L2(nsp + 64);
                 }
                 const uint32_t i = c_a + lane;
                 bool defer = false;
