@@ -763,7 +763,7 @@ __device__ uint32_t general_walk(TileCtx<BITS>& S, const TileRec& r, unsigned lo
 //   pass 1: the read in six 16-byte loads issued together, XOR against the draft four words at a time, and only record WHICH
 //           words differ - straight-line code, no divergence;
 //   pass 2: the two edge words (partly outside the kept entries or the tile) and the few words that differ (about one word in
-//           two reads) are reloaded and every differing base is counted.
+//           two reads) are picked out of the registers again and every differing base is counted.
 // Returns kept entries, or NONE32 = "take the general walk" (a homopolymer tail of 8+ bases, a read shorter than 8).
 __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, unsigned long long aln) {
     const uint32_t len = r.len_nc & 0xFFFFu;
@@ -807,7 +807,7 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
 #pragma unroll
     for (int g = 0; g < 6; ++g) {
         q[g] = make_uint4(0, 0, 0, 0);
-        if ((inner >> (4 * g)) & 15u) q[g] = __ldg(sp + (rc ? nq - 1 - g : (uint32_t)g));
+        if (((inner | emask) >> (4 * g)) & 15u) q[g] = __ldg(sp + (rc ? nq - 1 - g : (uint32_t)g));
     }
     uint32_t bits = 0;
 #pragma unroll
@@ -826,8 +826,14 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
     while (mm) {
         const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
         mm &= mm - 1;
-        uint32_t wv = __ldg(sp32 + (rc ? 4 * nq - 1 - m : m));
-        if (rc) wv = __brev(wv);
+        // word m of the effective read, out of the registers (a select tree: no second trip to memory)
+        const uint32_t g = m >> 2, t4 = m & 3;
+        uint4 qq = q[0];
+#pragma unroll
+        for (int k = 1; k < 6; ++k) if (g == (uint32_t)k) qq = q[k];
+        uint32_t wv;
+        if (rc) { wv = t4 == 0 ? qq.w : t4 == 1 ? qq.z : t4 == 2 ? qq.y : qq.x; wv = __brev(wv); }
+        else wv = t4 == 0 ? qq.x : t4 == 1 ? qq.y : t4 == 2 ? qq.z : qq.w;
         uint32_t x = wv ^ __funnelshift_r(dn32[i0 + (int)m], dn32[i0 + (int)m + 1], sh4);
         if (m == m_first) x &= fmask;
         if (m == m_last) x &= lmask;
@@ -1079,17 +1085,16 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
         }
         __syncthreads();
         // ---- phase B: every alignment that can touch the tile, in sorted order: the bins of the tile and `lb` bins before it.
-        // Warps take 32 consecutive slots at a time from a shared counter (no round is held up by one slow warp); the records of
-        // the chunk after the current one are already in flight while the current one is walked.  Reads with indels / long reads
-        // take the general walk right away, on their own lanes.
+        // Warps take chunks of 32 consecutive slots round robin; three chunks are in flight per warp (indices, records, walk).
         const uint32_t b0 = P0 >> PP_BIN_SHIFT;
         const uint32_t lo = d.bin_start[b0 >= lb ? b0 - lb : 0u];
         const uint32_t hi = d.bin_start[min(b0 + (uint32_t)(TL_T / PP_BIN), d.n_bins)];
         {
+            uint32_t next_chunk = warp;                                                // chunks of 32 slots, dealt round robin to the warps
             auto grab = [&]() -> uint32_t {
-                uint32_t c = 0;
-                if (lane == 0) c = atomicAdd(&sh.next, 32u);
-                return lo + __shfl_sync(0xffffffffu, c, 0);
+                const uint32_t c = lo + 32u * next_chunk;
+                next_chunk += TL_THREADS / 32;
+                return c < lo ? 0xFFFFFFE0u : c;                                       // (wrap-around guard: past every list)
             };
             // reads that need the general walk (indels, long reads, homopolymer tails) are queued per warp and walked 32 at a
             // time on consecutive lanes instead of one lane at a time
@@ -1138,7 +1143,11 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 }
                 const uint32_t dm = __ballot_sync(0xffffffffu, defer);
                 if (dm) {
-                    if (defer) wq[nq_w + (uint32_t)__popc(dm & ((1u << lane) - 1u))] = i;
+                    if (defer) {
+                        wq[nq_w + (uint32_t)__popc(dm & ((1u << lane) - 1u))] = i;
+                        PP_PREFETCH_L2(d.cigar_ops + rec_a.cigar_off);                  // what the general walk will chase
+                        PP_PREFETCH_L2(d.seq_pool + (size_t)rec_a.seq_off * (BITS == 4 ? 16 : 32));
+                    }
                     nq_w += (uint32_t)__popc(dm);
                     __syncwarp();
                     if (nq_w >= 32) drain(32);
