@@ -109,9 +109,9 @@ typedef struct {
 #define PP_N_STAGES 8
 typedef struct {
   float total_ms;               /* CUDA-event time of the whole device path of this call            */
-  float stage_ms[PP_N_STAGES];  /* 0 reset (chain heads, status), 1 classify (fallback k pre-pass, normally 0), 2 prep (goodness, k,
-                                   records + bin keys, sort by bin), 3 tile (CIGAR walk, pileup in shared memory, ordered depth,
-                                   vote), 4 compaction, 5 unused, 6 h2d, 7 d2h */
+  float stage_ms[PP_N_STAGES];  /* 0 reset (chain heads, status), 1 classify (fallback k pre-pass, normally 0), 2 goodness / k of every
+                                   alignment under the call's options, 3 tile (CIGAR walk, pileup in shared memory, ordered depth,
+                                   vote), 4 compaction, 5 unused, 6 h2d (pp_polish: upload + position binning of the dataset), 7 d2h */
   uint32_t launches;            /* kernels of this library launched during the call                 */
   uint32_t reserved;
 } pp_timing;

@@ -11,7 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PP_OK, PP_ERR_CUDA, PP_ERR_ARG, PP_ERR_INPUT, PP_ERR_NOMEM, PP_ERR_IO = 0, -1, -2, -3, -4, -5
 N_STAGES = 8
-STAGES = ["reset", "classify", "prep", "tile", "compact", "unused", "h2d", "d2h"]
+STAGES = ["reset", "classify", "goodk", "tile", "compact", "unused", "h2d", "d2h"]
 
 
 class PolypolishError(RuntimeError):

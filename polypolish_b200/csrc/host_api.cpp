@@ -461,7 +461,7 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
         fputs(tok_timing.c_str(), stderr);
         for (uint32_t s = 0; s < n_shards; ++s) {
             const pp_timing& t = jobs[s].res.timing;
-            fprintf(stderr, "GPU job %u: %u contigs, %s alignments; device path %.3f ms (h2d %.3f, prep + sort %.3f, tile %.3f, compact %.3f, d2h %.3f), %u kernels\n",
+            fprintf(stderr, "GPU job %u: %u contigs, %s alignments; device path %.3f ms (h2d + binning %.3f, goodness/k %.3f, tile %.3f, compact %.3f, d2h %.3f), %u kernels\n",
                     s, jobs[s].contigs.n_contigs, fmt_thousands(jobs[s].alns.n_aln).c_str(), t.total_ms, t.stage_ms[6], t.stage_ms[2], t.stage_ms[3],
                     t.stage_ms[4], t.stage_ms[7], t.launches);
         }

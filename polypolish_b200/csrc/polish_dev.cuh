@@ -60,7 +60,7 @@ struct DevStatus {
     unsigned long long out_len;      // polished bases
     unsigned int node_count;         // other-allele nodes allocated
     unsigned int flags;
-    unsigned int max_ext;            // largest entry count of a binned alignment: how many bins a tile looks back
+    unsigned int max_ext;            // (binning) largest entry count of a binned alignment: how many bins a tile looks back
     unsigned int ticket;             // next tile (k_tile's dynamic schedule)
     unsigned int pad0, pad1;
 };
@@ -80,17 +80,19 @@ struct OthNode {
     uint32_t next;                   // next node of the same position, NONE32 = end
 };
 
-// What k_tile needs to know about one contributing alignment (written by k_prep, gathered through the sorted index).
+// What k_tile needs to know about one alignment that can contribute.  Written once per dataset by k_bin (SAM order) and moved
+// into bin order by k_permute; everything in it is independent of the polish options.
 struct __align__(16) TileRec {
     uint32_t gstart;                 // global position of the first entry
-    uint32_t seq_off;                // PP_SEQ_BLOCK units
+    uint32_t seq_off;                // PP_SEQ_BLOCK units (general walk; the fast path reads the slot's own copy of the bases)
     uint32_t cigar_off;
     uint32_t len_nc;                 // seq_len | n_cigar << 16
-    uint32_t k;                      // good alignments of the read group (alignment.rs:288)
+    uint32_t aln;                    // index in SAM order
     uint32_t E;                      // entries before the trim (saturated)
     uint32_t flags;                  // TR_*
     uint32_t cend;                   // end of the contig (global position)
 };
+#define TL_SEQ_QUADS 6               // 16-byte quads of a slot's copy of its read (fast path: <= 192 bases)
 
 struct DevData {                     // everything the kernels read, by value
     // alignments
@@ -107,10 +109,17 @@ struct DevData {                     // everything the kernels read, by value
     uint32_t n_tiles;
     // work
     uint32_t* k;                     // [n_reads] good alignments per read (only in the global-k fallback mode)
-    TileRec* recs;                   // [n_aln]
-    uint32_t *key, *val;             // [n_aln] k_prep's (bin, alignment) pairs, SAM order
-    const uint32_t* sval;            // [n_aln] alignment indices sorted by bin (stable)
+    // the dataset in bin order (built once per dataset: k_bin -> stable sort -> k_bin_bounds -> k_permute / k_permute_seq)
+    TileRec* recs;                   // [n_aln] SAM order (binning scratch)
+    uint32_t *key, *val;             // [n_aln] (bin, alignment) pairs, SAM order (binning scratch)
+    const uint32_t* sval;            // [n_aln] alignment indices sorted by bin (stable: SAM order inside a bin)
     uint32_t* bin_start;             // [n_bins + 3] first sorted slot of every bin
+    TileRec* srec;                   // [n_slots] records in slot (= bin, then SAM) order
+    uint4* sseq;                     // [n_slots * 6] 4-bit mode: every fast-path read again, forward strand, base 0 at nibble 0
+    uint32_t n_slots;                // alignments that can contribute (slots before the "nothing" key)
+    uint32_t max_ext;                // largest entry count of a binned alignment (how many bins a tile looks back)
+    // per call
+    uint32_t* kf;                    // [n_aln] k of the alignment's read group if it contributes under the current options, else 0
     uint4* wrec;                     // [n_aln] per sorted slot: (alignment, first position, kept entries, k) - what the ordered depth walk reads
     uint32_t* oth_head;              // [G] 1 + index of the first OthNode of the position, 0 = none
     OthNode* nodes;
@@ -261,9 +270,90 @@ __global__ void __launch_bounds__(256) k_classify_multi(DevData d) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_prep: process_one_read (alignment.rs:275-305) for every alignment, one per thread, every input array read coalesced.
-// Writes, per alignment, the 256-position bin of its first entry (or "long" / "contributes nothing") and the 32-byte record
-// k_tile gathers.  GLOBALK = false: k of a multi-record group is counted right here (its records are consecutive alignments);
+// Once per dataset: k_bin.  One alignment per thread, every input array read coalesced: the 256-position bin of its first
+// entry (or "long" / "can never contribute") and the record k_tile will read, none of which depends on the polish options.
+// ------------------------------------------------------------------------------------------------------
+template <int BITS>
+__device__ __forceinline__ void bin_body(const DevData& d) {
+    uint32_t max_ext = 0;
+    for (unsigned long long aln = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; aln < d.n_aln; aln += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t key = d.n_bins + 1;                            // can never contribute (k_goodk raises the error if it is "good")
+        const uint32_t c = d.contig[aln];
+        const uint8_t fl = d.flags[aln];
+        const uint32_t ncig = d.n_cigar[aln], cigoff = d.cigar_off[aln];
+        if (c != PP_CONTIG_UNKNOWN && !(fl & (PP_FLAG_NOSEQ | PP_FLAG_GHOST)) && ncig != 0) {
+            const unsigned long long gs = d.contig_off[c] + d.ref_start[aln];
+            const unsigned long long ce = d.contig_off[c + 1];
+            const uint32_t len = d.seq_len[aln];
+            // E = entries (one per consumed reference position), R = read bases consumed (alignment.rs:175-198)
+            unsigned long long E = 0, R = 0;
+            bool bad = false;
+            const uint32_t* ops = d.cigar_ops + cigoff;
+            for (uint32_t p = 0; p < ncig; ++p) {
+                const uint32_t op = ops[p], o = op & 15u, l = op >> 4;
+                if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X) { E += l; R += l; }
+                else if (o == PP_OP_I) R += l;
+                else if (o == PP_OP_D) E += l;
+                else bad = true;
+            }
+            if (gs < ce && !bad && R == len && len != 0) {
+                const bool is_long = E > TL_LONG_E;
+                const uint32_t f0 = ops[0] & 15u;
+                const bool fast = BITS == 4 && ncig == 1 && (f0 == PP_OP_M || f0 == PP_OP_EQ) && len <= TL_FAST_LEN;
+                const uint32_t flags = ((fl & PP_FLAG_RC) ? TR_RC : 0u) | (fast ? TR_FAST : 0u) | (is_long ? TR_LONG : 0u);
+                uint4* dst = reinterpret_cast<uint4*>(d.recs + aln);
+                dst[0] = make_uint4((uint32_t)gs, d.seq_off[aln], cigoff, len | (ncig << 16));
+                dst[1] = make_uint4((uint32_t)aln, (uint32_t)min(E, 0xFFFFFFFFull), flags, (uint32_t)ce);
+                key = is_long ? d.n_bins : (uint32_t)(gs >> PP_BIN_SHIFT);
+                if (!is_long) max_ext = max(max_ext, (uint32_t)E);
+            }
+        }
+        d.key[aln] = key; d.val[aln] = (uint32_t)aln;
+    }
+    for (int o = 16; o > 0; o >>= 1) max_ext = max(max_ext, __shfl_down_sync(0xffffffffu, max_ext, o));
+    if ((threadIdx.x & 31) == 0 && max_ext) atomicMax(&d.st->max_ext, max_ext);
+}
+
+// Slot i of the binned dataset: the record of the alignment the stable sort put there.
+__device__ __forceinline__ void permute_body(const DevData& d) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_slots) return;
+    const uint4* src = reinterpret_cast<const uint4*>(d.recs + d.sval[i]);
+    uint4* dst = reinterpret_cast<uint4*>(d.srec + i);
+    dst[0] = src[0]; dst[1] = src[1];
+}
+
+// ... and its bases (4-bit mode, fast-path reads): the EFFECTIVE read - the stored one, or its reverse complement for
+// PP_FLAG_RC records (alignment.rs:161-167: complementing a BAM nibble = reversing its 4 bits, so the whole thing is one bit
+// reversal) - forward, base 0 at nibble 0, zero padded to 192 bases.  One thread per 32-bit word (8 bases).
+__device__ __forceinline__ void permute_seq_body(const DevData& d) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long i = t / (4 * TL_SEQ_QUADS);
+    const uint32_t m = (uint32_t)(t % (4 * TL_SEQ_QUADS));
+    if (i >= d.n_slots) return;
+    const TileRec& r = d.srec[i];
+    uint32_t out = 0;
+    if (r.flags & TR_FAST) {
+        const uint32_t len = r.len_nc & 0xFFFFu, nw = (len + 7) >> 3;                     // words that hold bases
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(d.seq_pool + (size_t)r.seq_off * 16);
+        if (!(r.flags & TR_RC)) { if (m < nw) out = s32[m]; }
+        else {
+            // effective nibble e = complement of stored nibble len-1-e = nibble (8 nw - len + e) of the word-reversed, bit-reversed words
+            const uint32_t pad = 8 * nw - len;
+            auto V = [&](uint32_t x) -> uint32_t { return x < nw ? __brev(s32[nw - 1 - x]) : 0u; };
+            if (m < nw) out = __funnelshift_r(V(m + (pad >> 3)), V(m + (pad >> 3) + 1), (pad & 7) * 4);
+        }
+        if (m == nw - 1 && (len & 7)) out &= 0xFFFFFFFFu >> ((8 - (len & 7)) * 4);         // nothing but zeros past the last base
+        if (m >= nw) out = 0;
+    }
+    reinterpret_cast<uint32_t*>(d.sseq)[t] = out;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Per call: k_goodk = process_one_read (alignment.rs:275-305) for every alignment, one per thread, SAM order, coalesced:
+// goodness under the current options, k = good records of the consecutive-QNAME group, --careful, and the errors the reference
+// raises for a good alignment.  kf[aln] = k if the alignment adds to the pileup, else 0.
+// GLOBALK = false: k of a multi-record group is counted right here (its records are consecutive alignments);
 // GLOBALK = true: k comes from k_classify_multi (fallback for huge groups).
 // ------------------------------------------------------------------------------------------------------
 struct PrepShared {
@@ -272,12 +362,11 @@ struct PrepShared {
     uint32_t n_good;
 };
 
-template <int BITS, bool GLOBALK>
-__device__ __forceinline__ void prep_body(const DevData& d, PrepShared& sh) {
+template <bool GLOBALK>
+__device__ __forceinline__ void goodk_body(const DevData& d, PrepShared& sh) {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const unsigned long long n_blocks = (d.n_aln + PR_THREADS - 1) / PR_THREADS;
     unsigned long long used = 0;
-    uint32_t max_ext = 0;
     for (unsigned long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         const unsigned long long blk0 = blk * PR_THREADS;
         const unsigned long long aln = blk0 + tid;
@@ -324,7 +413,7 @@ __device__ __forceinline__ void prep_body(const DevData& d, PrepShared& sh) {
             }
         }
         if (fl & PP_FLAG_GHOST) good = false;                   // another shard scatters it; it only counted towards k
-        uint32_t key = d.n_bins + 1;                            // contributes nothing
+        uint32_t kf = 0;
         if (good) {
             used++;
             const uint32_t c = d.contig[aln];
@@ -334,55 +423,40 @@ __device__ __forceinline__ void prep_body(const DevData& d, PrepShared& sh) {
                 const unsigned long long gs = d.contig_off[c] + d.ref_start[aln];
                 const unsigned long long ce = d.contig_off[c + 1];
                 const uint32_t len = d.seq_len[aln];
-                // E = entries (one per consumed reference position), R = read bases consumed (alignment.rs:175-198)
-                unsigned long long E = 0, R = 0;
+                unsigned long long R = 0;
                 bool bad = false;
                 const uint32_t* ops = d.cigar_ops + cigoff;
                 for (uint32_t p = 0; p < ncig; ++p) {
                     const uint32_t op = ops[p], o = op & 15u, l = op >> 4;
-                    if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X) { E += l; R += l; }
-                    else if (o == PP_OP_I) R += l;
-                    else if (o == PP_OP_D) E += l;
-                    else bad = true;                                   // alignment.rs:187-193
+                    if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X || o == PP_OP_I) R += l;
+                    else if (o != PP_OP_D) bad = true;                 // alignment.rs:187-193
                 }
                 if (gs >= ce) report_error(d.st, aln, ERR_OOB);
                 else if (bad) report_error(d.st, aln, ERR_BAD_OP);
                 else if (R != len) report_error(d.st, aln, ERR_SEQ_MISMATCH);                 // :195-198
-                else {
-                    TileRec r;
-                    r.gstart = (uint32_t)gs; r.seq_off = d.seq_off[aln]; r.cigar_off = cigoff; r.len_nc = len | (ncig << 16);
-                    r.k = k; r.E = (uint32_t)min(E, 0xFFFFFFFFull); r.cend = (uint32_t)ce;
-                    const bool is_long = E > TL_LONG_E;
-                    r.flags = ((fl & PP_FLAG_RC) ? TR_RC : 0u) | ((BITS == 4 && ncig == 1 && len <= TL_FAST_LEN) ? TR_FAST : 0u) | (is_long ? TR_LONG : 0u);
-                    uint4* dst = reinterpret_cast<uint4*>(d.recs + aln);
-                    dst[0] = make_uint4(r.gstart, r.seq_off, r.cigar_off, r.len_nc);
-                    dst[1] = make_uint4(r.k, r.E, r.flags, r.cend);
-                    key = is_long ? d.n_bins : (uint32_t)(gs >> PP_BIN_SHIFT);
-                    if (!is_long) max_ext = max(max_ext, (uint32_t)E);
-                }
+                else kf = k;
             }
         }
-        if (aln < d.n_aln) { d.key[aln] = key; d.val[aln] = (uint32_t)aln; }
+        if (aln < d.n_aln) d.kf[aln] = kf;
         __syncthreads();
     }
-    // good alignments (alignment.rs:304) and the largest binned extent: block reduce, one atomic per CTA
+    // good alignments (alignment.rs:304): block reduce, one atomic per CTA
     if (tid == 0) sh.n_good = 0;
     __syncthreads();
-    for (int o = 16; o > 0; o >>= 1) {
-        used += __shfl_down_sync(0xffffffffu, used, o);
-        max_ext = max(max_ext, __shfl_down_sync(0xffffffffu, max_ext, o));
-    }
+    for (int o = 16; o > 0; o >>= 1) used += __shfl_down_sync(0xffffffffu, used, o);
     if (lane == 0 && used) atomicAdd(&sh.n_good, (uint32_t)used);
-    if (lane == 0 && max_ext) atomicMax(&d.st->max_ext, max_ext);
     __syncthreads();
     if (tid == 0 && sh.n_good) atomicAdd(&d.st->n_used, (unsigned long long)sh.n_good);
 }
 
 #if !defined(PP_EMULATE)
-template <int BITS, bool GLOBALK>
-__global__ void __launch_bounds__(PR_THREADS) k_prep(DevData d) {
+template <int BITS> __global__ void __launch_bounds__(256) k_bin(DevData d) { bin_body<BITS>(d); }
+__global__ void __launch_bounds__(256) k_permute(DevData d) { permute_body(d); }
+__global__ void __launch_bounds__(256) k_permute_seq(DevData d) { permute_seq_body(d); }
+template <bool GLOBALK>
+__global__ void __launch_bounds__(PR_THREADS) k_goodk(DevData d) {
     __shared__ PrepShared sh;
-    prep_body<BITS, GLOBALK>(d, sh);
+    goodk_body<GLOBALK>(d, sh);
 }
 #endif
 
@@ -590,7 +664,6 @@ struct TileShared {
     unsigned long long s_warp[TL_THREADS / 32];
     unsigned long long s_total;
     long long s_delta[TL_THREADS / 32];
-    uint32_t next;                                     // next chunk of the tile's list (phase B hands out 32 slots at a time)
     uint32_t tile;
     uint32_t subflags;                                 // sub-tiles that see k != 1 coverage
 };
@@ -673,8 +746,9 @@ template <int BITS> struct TileCtx {
 // The general CIGAR walk of one alignment (alignment.rs:175-201, 364-378; pileup.rs:189-200), restricted to the tile.
 // Returns the number of kept entries.
 template <int BITS>
-__device__ uint32_t general_walk(TileCtx<BITS>& S, const TileRec& r, unsigned long long aln) {
+__device__ uint32_t general_walk(TileCtx<BITS>& S, const TileRec& r, uint32_t k) {
     const DevData& d = S.d;
+    const unsigned long long aln = r.aln;
     const uint32_t len = r.len_nc & 0xFFFFu, ncig = r.len_nc >> 16;
     const bool rc = r.flags & TR_RC;
     const uint32_t gstart = r.gstart;
@@ -712,7 +786,7 @@ __device__ uint32_t general_walk(TileCtx<BITS>& S, const TileRec& r, unsigned lo
     const unsigned long long nk64 = (E - run >= 1) ? (E - run - 1) : 0;
     if ((unsigned long long)gstart + nk64 > r.cend) { report_error(d.st, aln, ERR_OOB); return 0; }
     const uint32_t nkept = (uint32_t)nk64;
-    S.add_interval(gstart, nkept, r.k != 1);
+    S.add_interval(gstart, nkept, k != 1);
     // positions of this tile the alignment can touch: entries [e_lo, e_hi)
     const long long off = (long long)S.P0 - (long long)gstart;
     const unsigned long long e_lo = off > 0 ? (unsigned long long)off : 0ull;
@@ -757,28 +831,33 @@ __device__ uint32_t general_walk(TileCtx<BITS>& S, const TileRec& r, unsigned lo
     return nkept;
 }
 
-// The fast path: a 4-bit read of at most 192 bases whose CIGAR is one M / = run.  The effective read is a stream of 32-bit
-// words, 8 bases each, base i = nibble pad + i (a reverse-strand read is taken back to front and bit-reversed, which is its
-// reverse complement); the draft comes from the tile's shared-memory copy through one native funnel shift per word.
-//   pass 1: the read in six 16-byte loads issued together, XOR against the draft four words at a time, and only record WHICH
-//           words differ - straight-line code, no divergence;
+// The fast path: a 4-bit read of at most 192 bases whose CIGAR is one M / = run.  Its bases were copied into slot order when the
+// dataset was binned - forward strand, base i = nibble i (k_permute_seq) - so slot i's read is the 96 bytes at sseq + 6 i, next to
+// its neighbours' in the tile's list: the six 16-byte loads of a warp's 32 reads cover 3 KB of consecutive memory.  The draft
+// comes from the tile's shared-memory copy through one native funnel shift per 8 bases.
+//   pass 1: XOR against the draft four words at a time and only record WHICH words differ - straight-line code, no divergence;
 //   pass 2: the two edge words (partly outside the kept entries or the tile) and the few words that differ (about one word in
 //           two reads) are picked out of the registers again and every differing base is counted.
 // Returns kept entries, or NONE32 = "take the general walk" (a homopolymer tail of 8+ bases, a read shorter than 8).
-__device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, unsigned long long aln) {
+__device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, uint32_t slot, uint32_t k) {
     const uint32_t len = r.len_nc & 0xFFFFu;
-    const bool rc = r.flags & TR_RC;
-    const uint4* sp = reinterpret_cast<const uint4*>(S.d.seq_pool + (size_t)r.seq_off * 16);
+    const unsigned long long aln = r.aln;
+    const uint4* sp = S.d.sseq + (size_t)slot * TL_SEQ_QUADS;
     const uint32_t* sp32 = reinterpret_cast<const uint32_t*>(sp);
-    const uint32_t nq = (len + 31) >> 5;                       // 16-byte quads that hold the read
-    const uint32_t pad = rc ? 32 * nq - len : 0;
     if (len < 8) return NONE32;
-    // ---- trim (alignment.rs:364-378): how many of the last bases equal the last one.  The last 8 effective bases as one word.
+    // all six loads of the read are issued before the first one is needed
+    uint4 q[TL_SEQ_QUADS];
+    const uint32_t nq = (len + 31) >> 5;
+#pragma unroll
+    for (int g = 0; g < TL_SEQ_QUADS; ++g) {
+        q[g] = make_uint4(0, 0, 0, 0);
+        if ((uint32_t)g < nq) q[g] = __ldg(sp + g);
+    }
+    // ---- trim (alignment.rs:364-378): how many of the last bases equal the last one.  The last 8 bases as one word.
     uint32_t run;
     {
-        uint32_t t8;
-        if (rc) t8 = __brev(__ldg(sp32));                      // effective base len-8+n = complement of stored base 7-n
-        else { const uint32_t o = len - 8; t8 = __funnelshift_r(__ldg(sp32 + (o >> 3)), __ldg(sp32 + (o >> 3) + 1), (o & 7) * 4); }
+        const uint32_t o = len - 8;
+        const uint32_t t8 = __funnelshift_r(__ldg(sp32 + (o >> 3)), __ldg(sp32 + (o >> 3) + 1), (o & 7) * 4);   // (word 24 of the last slot: the pool is padded)
         const uint32_t x = t8 ^ ((t8 >> 28) * 0x11111111u);
         const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
         if (nz == 0) return NONE32;                            // 8+ equal bases at the end: the general walk counts them
@@ -786,13 +865,13 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
     }
     const uint32_t nkept = len - run - 1;                       // run < 8 <= len
     if ((unsigned long long)r.gstart + nkept > r.cend) { report_error(S.d.st, aln, ERR_OOB); return 0; }
-    S.add_interval(r.gstart, nkept, r.k != 1);
-    // ---- compare: word m holds nibbles [8 m, 8 m + 8) = tile-relative positions relq + 8 m ...
+    S.add_interval(r.gstart, nkept, k != 1);
+    // ---- compare: word m holds bases [8 m, 8 m + 8) = tile-relative positions relq + 8 m ...
     const long long g0 = (long long)r.gstart - (long long)S.P0;
     const long long a64 = max(g0, 0ll), b64 = min(g0 + (long long)nkept, (long long)TL_T);
     if (b64 <= a64) return nkept;
-    const int relq = (int)g0 - (int)pad;
-    const uint32_t first = (uint32_t)((int)a64 - relq), lastn = (uint32_t)((int)b64 - 1 - relq);   // first / last valid nibble of the stream
+    const int relq = (int)g0;
+    const uint32_t first = (uint32_t)((int)a64 - relq), lastn = (uint32_t)((int)b64 - 1 - relq);   // first / last valid base
     const uint32_t m_first = first >> 3, m_last = lastn >> 3;
     const uint32_t fmask = 0xFFFFFFFFu << ((first & 7) * 4), lmask = 0xFFFFFFFFu >> ((7 - (lastn & 7)) * 4);
     const uint32_t emask = (1u << m_first) | (1u << m_last);
@@ -801,39 +880,28 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
     const int o0 = relq + TL_DN_HALO;                           // nibble offset of word 0 in the staged draft
     const int i0 = o0 >> 3;                                     // floor; i0 + m >= 0 for every word of a group that holds a valid word
     const uint32_t sh4 = (uint32_t)(o0 & 7) * 4;
-    // all six 16-byte loads of the read are issued before the first one is needed (memory-level parallelism: with both CTAs'
-    // shared memory there is next to no L1 left to prefetch into)
-    uint4 q[6];
-#pragma unroll
-    for (int g = 0; g < 6; ++g) {
-        q[g] = make_uint4(0, 0, 0, 0);
-        if (((inner | emask) >> (4 * g)) & 15u) q[g] = __ldg(sp + (rc ? nq - 1 - g : (uint32_t)g));
-    }
     uint32_t bits = 0;
 #pragma unroll
-    for (int g = 0; g < 6; ++g) {
+    for (int g = 0; g < TL_SEQ_QUADS; ++g) {
         if ((inner >> (4 * g)) & 15u) {
-            const uint32_t w0 = rc ? __brev(q[g].w) : q[g].x, w1 = rc ? __brev(q[g].z) : q[g].y, w2 = rc ? __brev(q[g].y) : q[g].z, w3 = rc ? __brev(q[g].x) : q[g].w;
             const uint32_t* dp = dn32 + (i0 + 4 * g);
             const uint32_t d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3], d4 = dp[4];
-            if (w0 != __funnelshift_r(d0, d1, sh4)) bits |= 1u << (4 * g);
-            if (w1 != __funnelshift_r(d1, d2, sh4)) bits |= 2u << (4 * g);
-            if (w2 != __funnelshift_r(d2, d3, sh4)) bits |= 4u << (4 * g);
-            if (w3 != __funnelshift_r(d3, d4, sh4)) bits |= 8u << (4 * g);
+            if (q[g].x != __funnelshift_r(d0, d1, sh4)) bits |= 1u << (4 * g);
+            if (q[g].y != __funnelshift_r(d1, d2, sh4)) bits |= 2u << (4 * g);
+            if (q[g].z != __funnelshift_r(d2, d3, sh4)) bits |= 4u << (4 * g);
+            if (q[g].w != __funnelshift_r(d3, d4, sh4)) bits |= 8u << (4 * g);
         }
     }
     uint32_t mm = (bits & inner) | emask;
     while (mm) {
         const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
         mm &= mm - 1;
-        // word m of the effective read, out of the registers (a select tree: no second trip to memory)
+        // word m of the read, out of the registers (a select tree: no second trip to memory)
         const uint32_t g = m >> 2, t4 = m & 3;
         uint4 qq = q[0];
 #pragma unroll
-        for (int k = 1; k < 6; ++k) if (g == (uint32_t)k) qq = q[k];
-        uint32_t wv;
-        if (rc) { wv = t4 == 0 ? qq.w : t4 == 1 ? qq.z : t4 == 2 ? qq.y : qq.x; wv = __brev(wv); }
-        else wv = t4 == 0 ? qq.x : t4 == 1 ? qq.y : t4 == 2 ? qq.z : qq.w;
+        for (int j = 1; j < TL_SEQ_QUADS; ++j) if (g == (uint32_t)j) qq = q[j];
+        const uint32_t wv = t4 == 0 ? qq.x : t4 == 1 ? qq.y : t4 == 2 ? qq.z : qq.w;
         uint32_t x = wv ^ __funnelshift_r(dn32[i0 + (int)m], dn32[i0 + (int)m + 1], sh4);
         if (m == m_first) x &= fmask;
         if (m == m_last) x &= lmask;
@@ -844,19 +912,18 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
             const uint32_t code = (wv >> (4 * t)) & 15u;
             const int rel = relq + 8 * (int)m + (int)t;
             if ((code & (code - 1)) == 0) atomicAdd(&S.sh.ex[__ffs((int)code) - 1][rel], 1u);          // A, C, G, T = 1, 2, 4, 8
-            else S.push_other(S.P0 + (uint32_t)rel, aln, 8u * m + t - pad, 1, 1ull | ((unsigned long long)code << 4));
+            else S.push_other(S.P0 + (uint32_t)rel, aln, 8u * m + t, 1, 1ull | ((unsigned long long)code << 4));
         }
     }
     return nkept;
 }
 
-// One alignment of the tile's list: sorted slot i.
-template <int BITS>
-__device__ __forceinline__ TileRec load_rec(const DevData& d, uint32_t aln) {
-    const uint4* src = reinterpret_cast<const uint4*>(d.recs + aln);
+// The record of sorted slot i (coalesced: consecutive lanes, consecutive 32-byte records).
+__device__ __forceinline__ TileRec load_srec(const DevData& d, uint32_t slot) {
+    const uint4* src = reinterpret_cast<const uint4*>(d.srec + slot);
     const uint4 a = __ldg(src), b = __ldg(src + 1);
     TileRec r;
-    r.gstart = a.x; r.seq_off = a.y; r.cigar_off = a.z; r.len_nc = a.w; r.k = b.x; r.E = b.y; r.flags = b.z; r.cend = b.w;
+    r.gstart = a.x; r.seq_off = a.y; r.cigar_off = a.z; r.len_nc = a.w; r.aln = b.x; r.E = b.y; r.flags = b.z; r.cend = b.w;
     return r;
 }
 
@@ -893,10 +960,13 @@ __device__ void depth_walk_steps(const DevData& d, TileShared& sh, uint32_t P0, 
             }
             uint32_t len = q.z;
             if (r == DW_RUNS - 1 && slot < end[r]) {            // long list: this CTA walked the alignment only if it can touch the tile
-                const TileRec rec = load_rec<BITS>(d, d.sval[slot]);
+                const TileRec rec = load_srec(d, slot);
                 const unsigned long long e_end = (unsigned long long)rec.gstart + rec.E;
-                q.x = d.sval[slot]; q.y = rec.gstart; q.w = rec.k;
-                len = (e_end > P0 && rec.gstart < P0 + (uint32_t)TL_T) ? q.z : 0u;
+                const uint32_t kk = d.kf[rec.aln];
+                // this CTA wrote the slot only if the alignment contributes and can touch the tile
+                const bool mine = kk != 0 && e_end > P0 && rec.gstart < P0 + (uint32_t)TL_T;
+                q.x = rec.aln; q.y = rec.gstart; q.w = mine ? kk : 1u;
+                len = mine ? q.z : 0u;
             }
             const bool ov = slot < end[r] && len != 0 && q.y < s + PP_SUB && q.y + len > s;
             const uint32_t m = __ballot_sync(0xffffffffu, ov);
@@ -1046,8 +1116,7 @@ template <int BITS>
 __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp, TileShared& sh) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevParams prm = *d.prm;
-    const uint32_t max_ext = d.st->max_ext;
-    const uint32_t lb = (max_ext + PP_BIN - 1) >> PP_BIN_SHIFT;               // bins a tile looks back (<= 2)
+    const uint32_t lb = (d.max_ext + PP_BIN - 1) >> PP_BIN_SHIFT;               // bins a tile looks back (<= 2)
     const uint32_t long_lo = d.bin_start[d.n_bins], long_hi = d.bin_start[d.n_bins + 1];
     OthCtx oc;
     oc.nodes = d.nodes; oc.head = d.oth_head;
@@ -1055,7 +1124,7 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
 
     for (;;) {
         __syncthreads();                                                       // everyone is done with the previous tile
-        if (tid == 0) { sh.tile = atomicAdd(&d.st->ticket, 1u); sh.next = 0; sh.subflags = 0; }
+        if (tid == 0) { sh.tile = atomicAdd(&d.st->ticket, 1u); sh.subflags = 0; }
         __syncthreads();
         const uint32_t tile = sh.tile;
         if (tile >= d.n_tiles) break;
@@ -1084,29 +1153,24 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             }
         }
         __syncthreads();
-        // ---- phase B: every alignment that can touch the tile, in sorted order: the bins of the tile and `lb` bins before it.
-        // Warps take chunks of 32 consecutive slots round robin; three chunks are in flight per warp (indices, records, walk).
+        // ---- phase B: every alignment that can touch the tile: the slots of the tile's bins and of the `lb` bins before it - one
+        // contiguous range of the binned dataset.  Warps take chunks of 32 consecutive slots round robin: records and bases stream
+        // in coalesced; the only gather is the 4-byte "k / contributes" word of the current options, fetched one chunk ahead.
         const uint32_t b0 = P0 >> PP_BIN_SHIFT;
         const uint32_t lo = d.bin_start[b0 >= lb ? b0 - lb : 0u];
         const uint32_t hi = d.bin_start[min(b0 + (uint32_t)(TL_T / PP_BIN), d.n_bins)];
         {
-            uint32_t next_chunk = warp;                                                // chunks of 32 slots, dealt round robin to the warps
-            auto grab = [&]() -> uint32_t {
-                const uint32_t c = lo + 32u * next_chunk;
-                next_chunk += TL_THREADS / 32;
-                return c < lo ? 0xFFFFFFE0u : c;                                       // (wrap-around guard: past every list)
-            };
             // reads that need the general walk (indels, long reads, homopolymer tails) are queued per warp and walked 32 at a
             // time on consecutive lanes instead of one lane at a time
             uint32_t* wq = sh.wqueue[warp];
             uint32_t nq_w = 0;                                                         // warp-uniform
-            auto drain = [&](uint32_t upto) {                                          // walks the first min(nq_w, 32) queued slots
-                const uint32_t take = min(nq_w, upto);
+            auto drain = [&]() {                                                       // walks the first min(nq_w, 32) queued slots
+                const uint32_t take = min(nq_w, 32u);
                 if (lane < take) {
                     const uint32_t i = wq[lane];
-                    const uint32_t aln = d.sval[i];
-                    const TileRec r = load_rec<BITS>(d, aln);
-                    d.wrec[i] = make_uint4(aln, r.gstart, general_walk<BITS>(S, r, aln), r.k);
+                    const TileRec r = load_srec(d, i);
+                    const uint32_t k = d.kf[r.aln];
+                    d.wrec[i] = make_uint4(r.aln, r.gstart, general_walk<BITS>(S, r, k), k);
                 }
                 __syncwarp();
                 const uint32_t rest = nq_w - take;
@@ -1116,30 +1180,33 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 __syncwarp();
                 nq_w = rest;
             };
-            // three chunks in flight: a is walked, b's records arrived (its bases are prefetched now), c's indices arrived (its
-            // records are requested now), d's indices are requested
-            uint32_t c_a = grab(), c_b = grab(), c_c = grab();
-            uint32_t aln_a = (c_a + lane < hi) ? d.sval[c_a + lane] : 0u;
-            uint32_t aln_b = (c_b + lane < hi) ? d.sval[c_b + lane] : 0u;
-            uint32_t aln_c = (c_c + lane < hi) ? d.sval[c_c + lane] : 0u;
-            TileRec rec_a = load_rec<BITS>(d, aln_a);
-            TileRec rec_b = load_rec<BITS>(d, aln_b);
+            const uint32_t stride = 32u * (TL_THREADS / 32);
+            uint32_t c_a = lo + 32u * warp;
+            TileRec rec_a, rec_b;
+            uint32_t k_a = 0;
+            rec_a = load_srec(d, min(c_a + lane, d.n_slots ? d.n_slots - 1 : 0u));
+            if (c_a + lane < hi) k_a = d.kf[rec_a.aln];
+            rec_b = load_srec(d, min(c_a + stride + lane, d.n_slots ? d.n_slots - 1 : 0u));
             while (c_a < hi) {
-                const uint32_t c_d = grab();
-                const uint32_t aln_d = (c_d + lane < hi) ? d.sval[c_d + lane] : 0u;
-                const TileRec rec_c = load_rec<BITS>(d, aln_c);                       // (alignment 0's record past the end of the list)
-                if (BITS == 4 && c_b + lane < hi) {                                    // the next chunk's bases towards L2
-                    const uint8_t* nsp = d.seq_pool + (size_t)rec_b.seq_off * 16;
+                const uint32_t c_b = c_a + stride, c_c = c_b + stride;
+                // next chunk: its k word (the record arrived during the previous round); the chunk after: its records
+                uint32_t k_b = 0;
+                if (c_b + lane < hi) k_b = d.kf[rec_b.aln];
+                const TileRec rec_c = load_srec(d, min(c_c + lane, d.n_slots ? d.n_slots - 1 : 0u));
+                if (BITS == 4 && c_b + lane < hi) {                                    // and its bases towards L2 (contiguous: exact lines)
+                    const uint8_t* nsp = reinterpret_cast<const uint8_t*>(d.sseq + (size_t)(c_b + lane) * TL_SEQ_QUADS);
                     PP_PREFETCH_L2(nsp);
-                    PP_PREFETCH_L2(nsp + 64);
                 }
                 const uint32_t i = c_a + lane;
                 bool defer = false;
                 if (i < hi) {
-                    uint32_t nk = NONE32;
-                    if (BITS == 4 && (rec_a.flags & TR_FAST)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), rec_a, aln_a);
-                    if (nk == NONE32) defer = true;
-                    else d.wrec[i] = make_uint4(aln_a, rec_a.gstart, nk, rec_a.k);
+                    if (k_a == 0) d.wrec[i] = make_uint4(rec_a.aln, rec_a.gstart, 0u, 1u);           // adds nothing under these options
+                    else {
+                        uint32_t nk = NONE32;
+                        if (BITS == 4 && (rec_a.flags & TR_FAST)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), rec_a, i, k_a);
+                        if (nk == NONE32) defer = true;
+                        else d.wrec[i] = make_uint4(rec_a.aln, rec_a.gstart, nk, k_a);
+                    }
                 }
                 const uint32_t dm = __ballot_sync(0xffffffffu, defer);
                 if (dm) {
@@ -1150,19 +1217,17 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                     }
                     nq_w += (uint32_t)__popc(dm);
                     __syncwarp();
-                    if (nq_w >= 32) drain(32);
+                    if (nq_w >= 32) drain();
                 }
-                c_a = c_b; c_b = c_c; c_c = c_d;
-                aln_a = aln_b; aln_b = aln_c; aln_c = aln_d;
-                rec_a = rec_b; rec_b = rec_c;
+                c_a = c_b; rec_a = rec_b; rec_b = rec_c; k_a = k_b;
             }
-            while (nq_w) drain(32);
+            while (nq_w) drain();
             // the long list: alignments of more than TL_LONG_E entries, looked at by every tile
             for (uint32_t i = long_lo + tid; i < long_hi; i += TL_THREADS) {
-                const uint32_t aln = d.sval[i];
-                const TileRec r = load_rec<BITS>(d, aln);
+                const TileRec r = load_srec(d, i);
                 const unsigned long long e_end = (unsigned long long)r.gstart + r.E;
-                if (e_end > P0 && r.gstart < P0 + (uint32_t)TL_T) d.wrec[i] = make_uint4(aln, r.gstart, general_walk<BITS>(S, r, aln), r.k);
+                const uint32_t k = d.kf[r.aln];
+                if (k != 0 && e_end > P0 && r.gstart < P0 + (uint32_t)TL_T) d.wrec[i] = make_uint4(r.aln, r.gstart, general_walk<BITS>(S, r, k), k);
             }
         }
         __syncthreads();

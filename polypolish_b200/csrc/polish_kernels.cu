@@ -111,6 +111,85 @@ int pp_ctx_upload_contigs(pp_ctx* ctx, const pp_contigs* c) {
     return PP_OK;
 }
 
+// The input side of DevData (alignment arrays, assembly, the binned dataset).
+static void fill_data(pp_ctx* ctx, DevData& d) {
+    const uint64_t G = ctx->G;
+    memset(&d, 0, sizeof d);
+    d.n_aln = ctx->n_aln;
+    d.contig = ctx->b[B_CONTIG].as<uint32_t>(); d.ref_start = ctx->b[B_REFSTART].as<uint32_t>();
+    d.read_id = ctx->b[B_READID].as<uint32_t>(); d.seq_off = ctx->b[B_SEQOFF].as<uint32_t>();
+    d.cigar_off = ctx->b[B_CIGOFF].as<uint32_t>(); d.nm = ctx->b[B_NM].as<uint32_t>();
+    d.cigar_ops = ctx->b[B_CIGOPS].as<uint32_t>(); d.seq_len = ctx->b[B_SEQLEN].as<uint16_t>();
+    d.n_cigar = ctx->b[B_NCIG].as<uint16_t>(); d.flags = ctx->b[B_FLAGS].as<uint8_t>();
+    d.seq_pool = ctx->b[B_SEQPOOL].as<uint8_t>(); d.draft = ctx->b[B_DRAFT].as<uint8_t>();
+    d.contig_off = ctx->b[B_CTGOFF].as<unsigned long long>(); d.n_contigs = ctx->n_contigs; d.G = (uint32_t)G;
+    d.n_bins = (uint32_t)((G + PP_BIN - 1) >> PP_BIN_SHIFT); d.n_tiles = (uint32_t)((G + TL_T - 1) / TL_T);
+    d.recs = ctx->b[B_RECS].as<TileRec>(); d.key = ctx->b[B_KEY].as<uint32_t>(); d.val = ctx->b[B_VAL].as<uint32_t>();
+    d.sval = ctx->b[B_SVAL].as<uint32_t>(); d.bin_start = ctx->b[B_BINSTART].as<uint32_t>();
+    d.srec = ctx->b[B_SREC].as<TileRec>(); d.sseq = ctx->b[B_SSEQ].as<uint4>();
+    d.n_slots = ctx->n_slots; d.max_ext = ctx->max_ext;
+    d.kf = ctx->b[B_KF].as<uint32_t>(); d.wrec = ctx->b[B_NK].as<uint4>();
+}
+
+// Once per dataset (pp_dataset_upload, pp_tok_finish): the alignments binned by position.  k_bin (record + 256-position bin key of
+// every alignment that can ever contribute) -> stable radix sort of (key, alignment) -> k_bin_bounds -> k_permute (records into
+// slot order) -> k_permute_seq (the bases of the fast-path reads into slot order, forward strand).  Nothing here depends on the
+// polish options: repeated pp_polish_resident calls reuse it, and pp_polish pays for it inside its own call.
+template <int BITS>
+static int bin_dataset(pp_ctx* ctx) {
+    cudaStream_t s = ctx->stream;
+    const uint64_t n_aln = ctx->n_aln, G = ctx->G;
+    const uint32_t n_bins = (uint32_t)((G + PP_BIN - 1) >> PP_BIN_SHIFT);
+    int key_bits = 1;
+    while ((1ull << key_bits) < (uint64_t)n_bins + 2) key_bits++;
+    const size_t na = (size_t)n_aln + 16;
+    CK(ctx->b[B_RECS].ensure(na * sizeof(TileRec)));
+    CK(ctx->b[B_KEY].ensure(na * 4)); CK(ctx->b[B_VAL].ensure(na * 4));
+    CK(ctx->b[B_SKEY].ensure(na * 4)); CK(ctx->b[B_SVAL].ensure(na * 4));
+    CK(ctx->b[B_BINSTART].ensure(((size_t)n_bins + 4) * 4));
+    CK(ctx->b[B_PARAMS].ensure(sizeof(DevParams) + 256 + sizeof(DevStatus)));
+    size_t cub_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                       (uint32_t*)nullptr, (int)n_aln, 0, key_bits, s));
+    CK(ctx->b[B_CUBTMP].ensure(cub_bytes + 256));
+    ctx->n_slots = 0; ctx->max_ext = 0;
+    DevData d;
+    fill_data(ctx, d);
+    d.st = (DevStatus*)(ctx->b[B_PARAMS].as<uint8_t>() + 256);
+    CK(cudaMemsetAsync(d.st, 0, sizeof(DevStatus), s));
+    if (n_aln) {
+        k_bin<BITS><<<(uint32_t)std::min<uint64_t>((n_aln + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, s>>>(d);
+        CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, cub_bytes, d.key, ctx->b[B_SKEY].as<uint32_t>(), d.val,
+                                           ctx->b[B_SVAL].as<uint32_t>(), (int)n_aln, 0, key_bits, s));   // stable: SAM order inside a bin
+    }
+    k_bin_bounds<<<(uint32_t)((n_aln + 1 + 255) / 256), 256, 0, s>>>(ctx->b[B_SKEY].as<uint32_t>(), (uint32_t)n_aln, n_bins + 2, d.bin_start);
+    CK(cudaMemcpyAsync(ctx->h_status, d.st, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+    uint32_t* h_slots = reinterpret_cast<uint32_t*>(ctx->h_params);            // (pinned scratch; rewritten before every polish call)
+    CK(cudaMemcpyAsync(h_slots, d.bin_start + n_bins + 1, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    ctx->max_ext = ctx->h_status->max_ext;
+    ctx->n_slots = *h_slots;
+    const size_t ns = (size_t)ctx->n_slots + 16;
+    CK(ctx->b[B_SREC].ensure(ns * sizeof(TileRec)));
+    CK(ctx->b[B_SSEQ].ensure(BITS == 4 ? ns * TL_SEQ_QUADS * 16 + 256 : 256));
+    CK(ctx->b[B_NK].ensure(ns * 16));
+    CK(ctx->b[B_KF].ensure(na * 4));
+    fill_data(ctx, d);
+    if (ctx->n_slots) {
+        k_permute<<<(ctx->n_slots + 255) / 256, 256, 0, s>>>(d);
+        if (BITS == 4) {
+            const uint64_t words = (uint64_t)ctx->n_slots * 4 * TL_SEQ_QUADS;
+            k_permute_seq<<<(uint32_t)((words + 255) / 256), 256, 0, s>>>(d);
+        }
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    // the SAM-order scratch of the binning is not needed again
+    ctx->b[B_RECS].release(); ctx->b[B_KEY].release(); ctx->b[B_VAL].release(); ctx->b[B_SKEY].release();
+    return PP_OK;
+}
+
 // The alignment arrays in ctx->b[B_CONTIG..B_SEQPOOL] become the resident dataset.
 int pp_ctx_commit_dataset(pp_ctx* ctx, uint64_t n_aln, uint64_t n_reads, uint64_t n_ops, uint64_t seq_bytes, uint32_t seq_bits) {
     if (n_aln >= 0x7FFFFFFFull - 4096) return ctx->fail(PP_ERR_ARG, "more than 2^31-4096 alignments in one call");
@@ -119,6 +198,8 @@ int pp_ctx_commit_dataset(pp_ctx* ctx, uint64_t n_aln, uint64_t n_reads, uint64_
     ctx->node_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, n_aln / 8 + ctx->G / 64));
     ctx->out_cap = ctx->G + ctx->G / 16 + (1u << 20);
     ctx->global_k = false;
+    int rc = ctx->seq_bits == 4 ? bin_dataset<4>(ctx) : bin_dataset<8>(ctx);
+    if (rc != PP_OK) return rc;
     ctx->have_ds = true;
     return PP_OK;
 }
@@ -166,24 +247,11 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
     cudaStream_t s = ctx->stream;
     const uint64_t G = ctx->G, n_aln = ctx->n_aln;
     const uint32_t n_tiles = (uint32_t)((G + TL_T - 1) / TL_T);              // = vote / compaction chunks
-    const uint32_t n_bins = (uint32_t)((G + PP_BIN - 1) >> PP_BIN_SHIFT);
     const size_t padG = (size_t)n_tiles * TL_T + 16;                          // k_tile / k_compact move whole chunks with vector accesses
-    int key_bits = 1;
-    while ((1ull << key_bits) < (uint64_t)n_bins + 2) key_bits++;
 
-    const size_t na = (size_t)n_aln + 16;
-    CK(ctx->b[B_RECS].ensure(na * sizeof(TileRec)));
-    CK(ctx->b[B_KEY].ensure(na * 4)); CK(ctx->b[B_VAL].ensure(na * 4));
-    CK(ctx->b[B_SKEY].ensure(na * 4)); CK(ctx->b[B_SVAL].ensure(na * 4));
-    CK(ctx->b[B_NK].ensure(na * 16));
-    CK(ctx->b[B_BINSTART].ensure(((size_t)n_bins + 4) * 4));
     CK(ctx->b[B_OUTOFF].ensure(((size_t)ctx->n_contigs + 1) * 8));
     CK(ctx->b[B_RES].ensure(padG * 2)); CK(ctx->b[B_RECAT].ensure((G + 1) * 4)); CK(ctx->b[B_CHUNKDELTA].ensure((size_t)n_tiles * 8));
     CK(ctx->b[B_PARAMS].ensure(sizeof(DevParams)));
-    size_t cub_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                       (uint32_t*)nullptr, (int)n_aln, 0, key_bits, s));
-    CK(ctx->b[B_CUBTMP].ensure(cub_bytes + 256));
     if (!ctx->tile_attr_set) {
         CK(cudaFuncSetAttribute(k_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
         CK(cudaFuncSetAttribute(k_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
@@ -210,18 +278,8 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         CK(ctx->b[B_OUT].ensure(out_cap + 64));
 
         DevData d;
-        d.n_aln = n_aln;
-        d.contig = ctx->b[B_CONTIG].as<uint32_t>(); d.ref_start = ctx->b[B_REFSTART].as<uint32_t>();
-        d.read_id = ctx->b[B_READID].as<uint32_t>(); d.seq_off = ctx->b[B_SEQOFF].as<uint32_t>();
-        d.cigar_off = ctx->b[B_CIGOFF].as<uint32_t>(); d.nm = ctx->b[B_NM].as<uint32_t>();
-        d.cigar_ops = ctx->b[B_CIGOPS].as<uint32_t>(); d.seq_len = ctx->b[B_SEQLEN].as<uint16_t>();
-        d.n_cigar = ctx->b[B_NCIG].as<uint16_t>(); d.flags = ctx->b[B_FLAGS].as<uint8_t>();
-        d.seq_pool = ctx->b[B_SEQPOOL].as<uint8_t>(); d.draft = ctx->b[B_DRAFT].as<uint8_t>();
-        d.contig_off = ctx->b[B_CTGOFF].as<unsigned long long>(); d.n_contigs = ctx->n_contigs; d.G = (uint32_t)G;
-        d.n_bins = n_bins; d.n_tiles = n_tiles;
+        fill_data(ctx, d);
         d.k = (uint32_t*)(zp + o_k);
-        d.recs = ctx->b[B_RECS].as<TileRec>(); d.key = ctx->b[B_KEY].as<uint32_t>(); d.val = ctx->b[B_VAL].as<uint32_t>();
-        d.sval = ctx->b[B_SVAL].as<uint32_t>(); d.bin_start = ctx->b[B_BINSTART].as<uint32_t>(); d.wrec = ctx->b[B_NK].as<uint4>();
         d.oth_head = (uint32_t*)(zp + o_head); d.nodes = ctx->b[B_NODES].as<OthNode>(); d.node_cap = node_cap;
         d.prm = ctx->b[B_PARAMS].as<DevParams>();
         d.st = (DevStatus*)(zp + o_status);
@@ -238,18 +296,14 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
             k_classify_multi<<<(uint32_t)std::min<uint64_t>((n_aln + 255) / 256, (uint64_t)ctx->sm_count * 8), 256, 0, s>>>(d);
             ctx->launches++;
         }
-        // ---- stage 2: per-alignment pass (goodness, k, records, bin keys), then the alignments in bin order
+        // ---- stage 2: goodness / k of every alignment under these options (SAM order, coalesced)
         CK(cudaEventRecord(ctx->ev[2], s));
         if (n_aln) {
             const uint32_t grid = (uint32_t)std::min<uint64_t>((n_aln + PR_THREADS - 1) / PR_THREADS, (uint64_t)ctx->sm_count * 8);
-            if (ctx->global_k) k_prep<BITS, true><<<grid, PR_THREADS, 0, s>>>(d);
-            else k_prep<BITS, false><<<grid, PR_THREADS, 0, s>>>(d);
+            if (ctx->global_k) k_goodk<true><<<grid, PR_THREADS, 0, s>>>(d);
+            else k_goodk<false><<<grid, PR_THREADS, 0, s>>>(d);
             ctx->launches++;
-            CK(cub::DeviceRadixSort::SortPairs(ctx->b[B_CUBTMP].p, cub_bytes, d.key, ctx->b[B_SKEY].as<uint32_t>(), d.val,
-                                               ctx->b[B_SVAL].as<uint32_t>(), (int)n_aln, 0, key_bits, s));   // stable: SAM order inside a bin
         }
-        k_bin_bounds<<<(uint32_t)((n_aln + 1 + 255) / 256), 256, 0, s>>>(ctx->b[B_SKEY].as<uint32_t>(), (uint32_t)n_aln, n_bins + 2, d.bin_start);
-        ctx->launches++;
         // ---- stage 3: scatter + ordered depth + vote, one tile of positions at a time, counters in shared memory
         CK(cudaEventRecord(ctx->ev[3], s));
         VoteParams vp;

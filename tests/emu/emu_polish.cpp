@@ -34,9 +34,10 @@ int run(const pp_contigs* c, const pp_alignments* a, const pp_polish_params* prm
     std::vector<uint32_t> cigar_ops(a->n_cigar_ops + 16, 0);
     if (a->n_cigar_ops) memcpy(cigar_ops.data(), a->cigar_ops, a->n_cigar_ops * 4);
 
-    std::vector<TileRec> recs(n_aln + 16);
-    std::vector<uint32_t> key(n_aln + 16), val(n_aln + 16), skey(n_aln + 16), sval(n_aln + 16), bin_start(n_bins + 4, 0);
+    std::vector<TileRec> recs(n_aln + 16), srec(n_aln + 16);
+    std::vector<uint32_t> key(n_aln + 16), val(n_aln + 16), skey(n_aln + 16), sval(n_aln + 16), bin_start(n_bins + 4, 0), kf(n_aln + 16, 0xDEADBEEFu);
     std::vector<uint4> wrec(n_aln + 16, make_uint4(0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu));
+    std::vector<uint4> sseq((n_aln + 16) * TL_SEQ_QUADS + 16, make_uint4(0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu));
     std::vector<uint32_t> oth_head(G + 1, 0), kcount(a->n_reads + 2, 0);
     std::vector<OthNode> nodes(std::max<uint64_t>(1 << 16, n_aln * 4 + G));
     std::vector<unsigned long long> changed(c->n_contigs, 0), zero(c->n_contigs, 0), out_off(c->n_contigs + 1, 0);
@@ -52,30 +53,42 @@ int run(const pp_contigs* c, const pp_alignments* a, const pp_polish_params* prm
     DevParams dp{prm->fraction_valid, prm->fraction_invalid, prm->min_depth, prm->max_errors, prm->careful ? 1 : 0, 0};
 
     DevData d;
+    memset(&d, 0, sizeof d);
     d.n_aln = n_aln;
     d.contig = a->contig; d.ref_start = a->ref_start; d.read_id = a->read_id; d.seq_off = a->seq_off; d.cigar_off = a->cigar_off; d.nm = a->nm;
     d.cigar_ops = cigar_ops.data(); d.seq_len = a->seq_len; d.n_cigar = a->n_cigar; d.flags = a->flags;
     d.seq_pool = (const uint8_t*)pool16.data(); d.draft = (const uint8_t*)draft16.data();
     d.contig_off = (const unsigned long long*)c->off; d.n_contigs = c->n_contigs; d.G = (uint32_t)G; d.n_bins = n_bins; d.n_tiles = n_tiles;
     d.k = kcount.data(); d.recs = recs.data(); d.key = key.data(); d.val = val.data(); d.sval = sval.data(); d.bin_start = bin_start.data();
+    d.srec = srec.data(); d.sseq = sseq.data(); d.kf = kf.data();
     d.wrec = wrec.data(); d.oth_head = oth_head.data(); d.nodes = nodes.data(); d.node_cap = (uint32_t)nodes.size(); d.prm = &dp; d.st = &st;
     VoteParams vp;
     vp.n_chunks = n_tiles; vp.out = out.data(); vp.out_cap = out_cap; vp.out_off = out_off.data(); vp.changed = changed.data();
     vp.zero_depth = zero.data(); vp.total_depth = tdepth.data(); vp.res = resv.data(); vp.rec_at = rec_at.data(); vp.chunk_delta = chunk_delta.data();
     vp.dbg = nullptr;
 
-    if (n_aln && global_k) emu::launch(2, 256, 0, [&] { k_classify_multi(d); });
+    // ---- once per dataset: bin, stable sort, bounds, permute
     if (n_aln) {
-        emu::launch(2, PR_THREADS, sizeof(PrepShared), [&] {
-            PrepShared& sh = *(PrepShared*)emu::shared_base();
-            if (global_k) prep_body<BITS, true>(d, sh); else prep_body<BITS, false>(d, sh);
-        });
+        emu::launch(3, 256, 0, [&] { bin_body<BITS>(d); });
         std::vector<uint32_t> order(n_aln);
         std::iota(order.begin(), order.end(), 0u);
         std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return key[x] < key[y]; });   // = the stable radix sort
         for (uint64_t i = 0; i < n_aln; ++i) { skey[i] = key[order[i]]; sval[i] = val[order[i]]; }
     }
     emu::launch((unsigned)((n_aln + 1 + 255) / 256), 256, 0, [&] { bin_bounds_body(skey.data(), (uint32_t)n_aln, n_bins + 2, bin_start.data()); });
+    d.n_slots = bin_start[n_bins + 1];
+    d.max_ext = st.max_ext;
+    if (d.n_slots) {
+        emu::launch((d.n_slots + 255) / 256, 256, 0, [&] { permute_body(d); });
+        if (BITS == 4) emu::launch((unsigned)(((uint64_t)d.n_slots * 4 * TL_SEQ_QUADS + 255) / 256), 256, 0, [&] { permute_seq_body(d); });
+    }
+    // ---- per call
+    if (n_aln && global_k) emu::launch(2, 256, 0, [&] { k_classify_multi(d); });
+    if (n_aln)
+        emu::launch(2, PR_THREADS, sizeof(PrepShared), [&] {
+            PrepShared& sh = *(PrepShared*)emu::shared_base();
+            if (global_k) goodk_body<true>(d, sh); else goodk_body<false>(d, sh);
+        });
     emu::launch((unsigned)std::max(1, std::min<int>(grid_tiles, (int)n_tiles)), TL_THREADS, sizeof(TileShared), [&] {
         tile_body<BITS>(d, vp, *(TileShared*)emu::shared_base());
     });
