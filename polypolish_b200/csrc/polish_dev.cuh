@@ -117,6 +117,7 @@ struct DevData {                     // everything the kernels read, by value
     TileRec* srec;                   // [n_slots] records in slot (= bin, then SAM) order
     uint4* sseq;                     // [n_slots * 6] 4-bit mode: every fast-path read again, forward strand, base 0 at nibble 0
     uint32_t n_slots;                // alignments that can contribute (slots before the "nothing" key)
+    const uint32_t* tile_order;      // [n_tiles] tiles by decreasing slot count: the ticket order (heavy tiles first, no long tail)
     uint32_t max_ext;                // largest entry count of a binned alignment (how many bins a tile looks back)
     // per call
     uint32_t* kf;                    // [n_aln] k of the alignment's read group if it contributes under the current options, else 0
@@ -348,6 +349,19 @@ __device__ __forceinline__ void permute_seq_body(const DevData& d) {
     }
     reinterpret_cast<uint32_t*>(d.sseq)[t] = out;
 }
+
+// Slots a tile has to look at (its own bins + the look-back): the weight the tiles are handed out by, heaviest first.
+__device__ __forceinline__ void tile_weight_body(const DevData& d, uint32_t* __restrict__ weight, uint32_t* __restrict__ index) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.n_tiles) return;
+    const uint32_t lb = (d.max_ext + PP_BIN - 1) >> PP_BIN_SHIFT;
+    const uint32_t b0 = (t * (uint32_t)TL_T) >> PP_BIN_SHIFT;
+    weight[t] = d.bin_start[min(b0 + (uint32_t)(TL_T / PP_BIN), d.n_bins)] - d.bin_start[b0 >= lb ? b0 - lb : 0u];
+    index[t] = t;
+}
+#if !defined(PP_EMULATE)
+__global__ void __launch_bounds__(256) k_tile_weight(DevData d, uint32_t* __restrict__ weight, uint32_t* __restrict__ index) { tile_weight_body(d, weight, index); }
+#endif
 
 // ------------------------------------------------------------------------------------------------------
 // Per call: k_goodk = process_one_read (alignment.rs:275-305) for every alignment, one per thread, SAM order, coalesced:
@@ -1126,8 +1140,8 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
         __syncthreads();                                                       // everyone is done with the previous tile
         if (tid == 0) { sh.tile = atomicAdd(&d.st->ticket, 1u); sh.subflags = 0; }
         __syncthreads();
-        const uint32_t tile = sh.tile;
-        if (tile >= d.n_tiles) break;
+        if (sh.tile >= d.n_tiles) break;
+        const uint32_t tile = d.tile_order[sh.tile];
         const uint32_t P0 = tile * (uint32_t)TL_T;
         TileCtx<BITS> S{d, sh, P0};
         // ---- phase A: clear the counters, stage the draft as 4-bit codes

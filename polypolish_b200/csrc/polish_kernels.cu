@@ -128,6 +128,7 @@ static void fill_data(pp_ctx* ctx, DevData& d) {
     d.sval = ctx->b[B_SVAL].as<uint32_t>(); d.bin_start = ctx->b[B_BINSTART].as<uint32_t>();
     d.srec = ctx->b[B_SREC].as<TileRec>(); d.sseq = ctx->b[B_SSEQ].as<uint4>();
     d.n_slots = ctx->n_slots; d.max_ext = ctx->max_ext;
+    d.tile_order = ctx->b[B_TILEORDER].as<uint32_t>();
     d.kf = ctx->b[B_KF].as<uint32_t>(); d.wrec = ctx->b[B_NK].as<uint4>();
 }
 
@@ -182,6 +183,21 @@ static int bin_dataset(pp_ctx* ctx) {
             const uint64_t words = (uint64_t)ctx->n_slots * 4 * TL_SEQ_QUADS;
             k_permute_seq<<<(uint32_t)((words + 255) / 256), 256, 0, s>>>(d);
         }
+    }
+    {   // tiles by decreasing slot count (the persistent kernel hands them out in that order)
+        const uint32_t n_tiles = d.n_tiles;
+        CK(ctx->b[B_TILEORDER].ensure(((size_t)n_tiles + 4) * 4));
+        CK(ctx->b[B_KEY].ensure(((size_t)n_tiles + 4) * 8)); CK(ctx->b[B_VAL].ensure(((size_t)n_tiles + 4) * 4));
+        uint32_t* w_in = ctx->b[B_KEY].as<uint32_t>();
+        uint32_t* w_out = w_in + n_tiles + 2;
+        uint32_t* idx_in = ctx->b[B_VAL].as<uint32_t>();
+        fill_data(ctx, d);
+        k_tile_weight<<<(n_tiles + 255) / 256, 256, 0, s>>>(d, w_in, idx_in);
+        size_t tb = 0;
+        CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_tiles, 0, 32, s));
+        CK(ctx->b[B_CUBTMP].ensure(tb + 256));
+        tb = ctx->b[B_CUBTMP].cap;
+        CK(cub::DeviceRadixSort::SortPairsDescending(ctx->b[B_CUBTMP].p, tb, w_in, w_out, idx_in, ctx->b[B_TILEORDER].as<uint32_t>(), (int)n_tiles, 0, 32, s));
     }
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());

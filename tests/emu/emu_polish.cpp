@@ -82,6 +82,15 @@ int run(const pp_contigs* c, const pp_alignments* a, const pp_polish_params* prm
         emu::launch((d.n_slots + 255) / 256, 256, 0, [&] { permute_body(d); });
         if (BITS == 4) emu::launch((unsigned)(((uint64_t)d.n_slots * 4 * TL_SEQ_QUADS + 255) / 256), 256, 0, [&] { permute_seq_body(d); });
     }
+    std::vector<uint32_t> tweight(n_tiles + 1), tindex(n_tiles + 1), torder(n_tiles + 1);
+    emu::launch((n_tiles + 255) / 256, 256, 0, [&] { tile_weight_body(d, tweight.data(), tindex.data()); });
+    {
+        std::vector<uint32_t> o(n_tiles);
+        std::iota(o.begin(), o.end(), 0u);
+        std::stable_sort(o.begin(), o.end(), [&](uint32_t x, uint32_t y) { return tweight[x] > tweight[y]; });
+        for (uint32_t i = 0; i < n_tiles; ++i) torder[i] = tindex[o[i]];
+    }
+    d.tile_order = torder.data();
     // ---- per call
     if (n_aln && global_k) emu::launch(2, 256, 0, [&] { k_classify_multi(d); });
     if (n_aln)
