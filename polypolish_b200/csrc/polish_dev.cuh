@@ -52,7 +52,7 @@ enum : unsigned {
     ERR_UNKNOWN_CONTIG = 1, ERR_SEQ_MISMATCH = 2, ERR_BAD_OP = 3, ERR_OOB = 4, ERR_NOSEQ = 5
 };
 enum : unsigned { FL_NODE_OVF = 1, FL_OUT_OVF = 8, FL_BIGGROUP = 16 };
-enum : unsigned { TR_RC = 1, TR_FAST = 2, TR_LONG = 4 };
+enum : unsigned { TR_RC = 1, TR_FAST = 2, TR_LONG = 4, TR_FAST1 = 8 };   // TR_FAST1: aM bI|bD cM, a in bits 8..15, b in 16..27, D in bit 28
 
 struct DevStatus {
     unsigned long long err;          // min over (aln << 8 | code); ~0 = none
@@ -301,7 +301,14 @@ __device__ __forceinline__ void bin_body(const DevData& d) {
                 const bool is_long = E > TL_LONG_E;
                 const uint32_t f0 = ops[0] & 15u;
                 const bool fast = BITS == 4 && ncig == 1 && (f0 == PP_OP_M || f0 == PP_OP_EQ) && len <= TL_FAST_LEN;
-                const uint32_t flags = ((fl & PP_FLAG_RC) ? TR_RC : 0u) | (fast ? TR_FAST : 0u) | (is_long ? TR_LONG : 0u);
+                uint32_t flags = ((fl & PP_FLAG_RC) ? TR_RC : 0u) | (fast ? TR_FAST : 0u) | (is_long ? TR_LONG : 0u);
+                if (BITS == 4 && ncig == 3 && len <= TL_FAST_LEN && !is_long) {
+                    // one insertion or one deletion between two match runs: aM bI cM / aM bD cM with a trim that stays in the last run
+                    const uint32_t o1 = ops[1] & 15u, o2 = ops[2] & 15u, la = ops[0] >> 4, lb2 = ops[1] >> 4, lc = ops[2] >> 4;
+                    if ((f0 == PP_OP_M || f0 == PP_OP_EQ) && (o1 == PP_OP_I || o1 == PP_OP_D) && (o2 == PP_OP_M || o2 == PP_OP_EQ) &&
+                        la >= 1 && la <= 255 && lb2 >= 1 && lb2 <= 4095 && lc >= 9)
+                        flags |= TR_FAST | TR_FAST1 | (la << 8) | (lb2 << 16) | (o1 == PP_OP_D ? 1u << 28 : 0u);
+                }
                 uint4* dst = reinterpret_cast<uint4*>(d.recs + aln);
                 dst[0] = make_uint4((uint32_t)gs, d.seq_off[aln], cigoff, len | (ncig << 16));
                 dst[1] = make_uint4((uint32_t)aln, (uint32_t)min(E, 0xFFFFFFFFull), flags, (uint32_t)ce);
@@ -877,57 +884,79 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
         if (nz == 0) return NONE32;                            // 8+ equal bases at the end: the general walk counts them
         run = 7u - ((31u - (uint32_t)__clz((int)nz)) >> 2);
     }
-    const uint32_t nkept = len - run - 1;                       // run < 8 <= len
+    // one insertion / deletion between two match runs (TR_FAST1): the last run has 9+ entries, so the trim (at most 8) stays in it
+    const bool one = r.flags & TR_FAST1;
+    const uint32_t ia = (r.flags >> 8) & 0xFFu, ib = (r.flags >> 16) & 0xFFFu;
+    const bool is_del = (r.flags >> 28) & 1u;
+    const uint32_t E = one ? (is_del ? len + ib : len - ib) : len;
+    const uint32_t nkept = E - run - 1;                         // run < 8 < entries of the last run
     if ((unsigned long long)r.gstart + nkept > r.cend) { report_error(S.d.st, aln, ERR_OOB); return 0; }
     S.add_interval(r.gstart, nkept, k != 1);
-    // ---- compare: word m holds bases [8 m, 8 m + 8) = tile-relative positions relq + 8 m ...
     const long long g0 = (long long)r.gstart - (long long)S.P0;
-    const long long a64 = max(g0, 0ll), b64 = min(g0 + (long long)nkept, (long long)TL_T);
-    if (b64 <= a64) return nkept;
-    const int relq = (int)g0;
-    const uint32_t first = (uint32_t)((int)a64 - relq), lastn = (uint32_t)((int)b64 - 1 - relq);   // first / last valid base
-    const uint32_t m_first = first >> 3, m_last = lastn >> 3;
-    const uint32_t fmask = 0xFFFFFFFFu << ((first & 7) * 4), lmask = 0xFFFFFFFFu >> ((7 - (lastn & 7)) * 4);
-    const uint32_t emask = (1u << m_first) | (1u << m_last);
-    const uint32_t inner = ((2u << m_last) - (1u << m_first)) & ~emask;   // words strictly between the edge words
+    if (g0 >= (long long)TL_T || g0 + (long long)nkept <= 0) return nkept;
     const uint32_t* dn32 = reinterpret_cast<const uint32_t*>(S.sh.dn);
-    const int o0 = relq + TL_DN_HALO;                           // nibble offset of word 0 in the staged draft
-    const int i0 = o0 >> 3;                                     // floor; i0 + m >= 0 for every word of a group that holds a valid word
-    const uint32_t sh4 = (uint32_t)(o0 & 7) * 4;
-    uint32_t bits = 0;
+    // Bases [b_lo, b_hi) of the read are single-base entries at tile-relative positions relq + base: XOR against the draft 8 bases per
+    // native funnel shift and only record WHICH words differ (straight-line code), then revisit those words and the two edge words.
+    auto segment = [&](int relq, int b_lo, int b_hi) {
+        const int lo_b = max(b_lo, -relq), hi_b = min(b_hi, (int)TL_T - relq);
+        if (hi_b <= lo_b) return;
+        const uint32_t first = (uint32_t)lo_b, lastn = (uint32_t)(hi_b - 1);       // first / last valid base
+        const uint32_t m_first = first >> 3, m_last = lastn >> 3;
+        const uint32_t fmask = 0xFFFFFFFFu << ((first & 7) * 4), lmask = 0xFFFFFFFFu >> ((7 - (lastn & 7)) * 4);
+        const uint32_t emask = (1u << m_first) | (1u << m_last);
+        const uint32_t inner = ((2u << m_last) - (1u << m_first)) & ~emask;        // words strictly between the edge words
+        const int o0 = relq + TL_DN_HALO;                       // nibble offset of word 0 in the staged draft
+        const int i0 = o0 >> 3;                                 // floor; i0 + m >= 0 for every word of a group that holds a valid word
+        const uint32_t sh4 = (uint32_t)(o0 & 7) * 4;
+        uint32_t bits = 0;
 #pragma unroll
-    for (int g = 0; g < TL_SEQ_QUADS; ++g) {
-        if ((inner >> (4 * g)) & 15u) {
-            const uint32_t* dp = dn32 + (i0 + 4 * g);
-            const uint32_t d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3], d4 = dp[4];
-            if (q[g].x != __funnelshift_r(d0, d1, sh4)) bits |= 1u << (4 * g);
-            if (q[g].y != __funnelshift_r(d1, d2, sh4)) bits |= 2u << (4 * g);
-            if (q[g].z != __funnelshift_r(d2, d3, sh4)) bits |= 4u << (4 * g);
-            if (q[g].w != __funnelshift_r(d3, d4, sh4)) bits |= 8u << (4 * g);
+        for (int g = 0; g < TL_SEQ_QUADS; ++g) {
+            if ((inner >> (4 * g)) & 15u) {
+                const uint32_t* dp = dn32 + (i0 + 4 * g);
+                const uint32_t d0 = dp[0], d1 = dp[1], d2 = dp[2], d3 = dp[3], d4 = dp[4];
+                if (q[g].x != __funnelshift_r(d0, d1, sh4)) bits |= 1u << (4 * g);
+                if (q[g].y != __funnelshift_r(d1, d2, sh4)) bits |= 2u << (4 * g);
+                if (q[g].z != __funnelshift_r(d2, d3, sh4)) bits |= 4u << (4 * g);
+                if (q[g].w != __funnelshift_r(d3, d4, sh4)) bits |= 8u << (4 * g);
+            }
         }
-    }
-    uint32_t mm = (bits & inner) | emask;
-    while (mm) {
-        const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
-        mm &= mm - 1;
-        // word m of the read, out of the registers (a select tree: no second trip to memory)
-        const uint32_t g = m >> 2, t4 = m & 3;
-        uint4 qq = q[0];
+        uint32_t mm = (bits & inner) | emask;
+        while (mm) {
+            const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
+            mm &= mm - 1;
+            // word m of the read, out of the registers (a select tree: no second trip to memory)
+            const uint32_t g = m >> 2, t4 = m & 3;
+            uint4 qq = q[0];
 #pragma unroll
-        for (int j = 1; j < TL_SEQ_QUADS; ++j) if (g == (uint32_t)j) qq = q[j];
-        const uint32_t wv = t4 == 0 ? qq.x : t4 == 1 ? qq.y : t4 == 2 ? qq.z : qq.w;
-        uint32_t x = wv ^ __funnelshift_r(dn32[i0 + (int)m], dn32[i0 + (int)m + 1], sh4);
-        if (m == m_first) x &= fmask;
-        if (m == m_last) x &= lmask;
-        uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
-        while (nz) {
-            const uint32_t t = (uint32_t)(__ffs((int)nz) - 1) >> 2;
-            nz &= nz - 1;
-            const uint32_t code = (wv >> (4 * t)) & 15u;
-            const int rel = relq + 8 * (int)m + (int)t;
-            if ((code & (code - 1)) == 0) atomicAdd(&S.sh.ex[__ffs((int)code) - 1][rel], 1u);          // A, C, G, T = 1, 2, 4, 8
-            else S.push_other(S.P0 + (uint32_t)rel, aln, 8u * m + t, 1, 1ull | ((unsigned long long)code << 4));
+            for (int j = 1; j < TL_SEQ_QUADS; ++j) if (g == (uint32_t)j) qq = q[j];
+            const uint32_t wv = t4 == 0 ? qq.x : t4 == 1 ? qq.y : t4 == 2 ? qq.z : qq.w;
+            uint32_t x = wv ^ __funnelshift_r(dn32[i0 + (int)m], dn32[i0 + (int)m + 1], sh4);
+            if (m == m_first) x &= fmask;
+            if (m == m_last) x &= lmask;
+            uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+            while (nz) {
+                const uint32_t t = (uint32_t)(__ffs((int)nz) - 1) >> 2;
+                nz &= nz - 1;
+                const uint32_t code = (wv >> (4 * t)) & 15u;
+                const int rel = relq + 8 * (int)m + (int)t;
+                if ((code & (code - 1)) == 0) atomicAdd(&S.sh.ex[__ffs((int)code) - 1][rel], 1u);      // A, C, G, T = 1, 2, 4, 8
+                else S.push_other(S.P0 + (uint32_t)rel, aln, 8u * m + t, 1, 1ull | ((unsigned long long)code << 4));
+            }
         }
+    };
+    if (!one) segment((int)g0, 0, (int)nkept);
+    else if (!is_del) {
+        // aM bI cM: entry a-1 carries 1 + b bases (an "other" allele); the last run's bases sit b further along the read
+        segment((int)g0, 0, (int)ia - 1);
+        const uint8_t* pool = S.d.seq_pool;
+        S.push_other(r.gstart + ia - 1, aln, ia - 1, 1 + ib, make_sig<4>(pool, r.seq_off, len, r.flags & TR_RC, ia - 1, 1 + ib));
+        segment((int)g0 - (int)ib, (int)(ia + ib), (int)(nkept + ib));
+    } else {
+        // aM bD cM: b "-" entries, then the last run's bases sit b positions further along the reference
+        segment((int)g0, 0, (int)ia);
+        const long long t_lo = max(0ll, -(g0 + (long long)ia)), t_hi = min((long long)ib, (long long)TL_T - (g0 + (long long)ia));
+        for (long long t = t_lo; t < t_hi; ++t) atomicAdd(&S.sh.del[(int)(g0 + ia + t)], 1u);
+        segment((int)g0 + (int)ib, (int)ia, (int)nkept - (int)ib);
     }
     return nkept;
 }
