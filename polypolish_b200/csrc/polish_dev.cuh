@@ -1213,7 +1213,10 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                     const uint32_t i = wq[lane];
                     const TileRec r = load_srec(d, i);
                     const uint32_t k = d.kf[r.aln];
-                    d.wrec[i] = make_uint4(r.aln, r.gstart, general_walk<BITS>(S, r, k), k);
+                    uint32_t nk = NONE32;
+                    if (BITS == 4 && (r.flags & TR_FAST1)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), r, i, k);   // one indel: two segments
+                    if (nk == NONE32) nk = general_walk<BITS>(S, r, k);
+                    d.wrec[i] = make_uint4(r.aln, r.gstart, nk, k);
                 }
                 __syncwarp();
                 const uint32_t rest = nq_w - take;
@@ -1246,7 +1249,7 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                     if (k_a == 0) d.wrec[i] = make_uint4(rec_a.aln, rec_a.gstart, 0u, 1u);           // adds nothing under these options
                     else {
                         uint32_t nk = NONE32;
-                        if (BITS == 4 && (rec_a.flags & TR_FAST)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), rec_a, i, k_a);
+                        if (BITS == 4 && (rec_a.flags & (TR_FAST | TR_FAST1)) == TR_FAST) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), rec_a, i, k_a);   // (one-indel reads wait for the queue: the chunk loop stays uniform)
                         if (nk == NONE32) defer = true;
                         else d.wrec[i] = make_uint4(rec_a.aln, rec_a.gstart, nk, k_a);
                     }
