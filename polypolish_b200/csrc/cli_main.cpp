@@ -244,5 +244,58 @@ int main(int argc, char** argv) {
         if (!quiet) fprintf(stderr, "Finished!\n");
         return 0;
     }
+    if (cmd == "filter-polish") {
+        // ADDITIVE (not in the reference): `filter` and `polish` of its output as one command, no intermediate files unless named
+        pp_polish_params prm{0.2, 0.5, 10, 5, 0};
+        std::string in1, in2, out1, out2, orientation = "auto";
+        double low = 0.1, high = 99.9;
+        std::vector<std::string> pos;
+        tok = normalise_args(argc, argv, 2, "ivmd");
+        for (size_t i = 0; i < tok.size(); ++i) {
+            const std::string& a = tok[i].text;
+            if (tok[i].positional) { pos.push_back(a); continue; }
+            if (a == "-h" || a == "--help") {
+                puts("filter paired-end alignments based on insert size, then polish the assembly with the filtered alignments (one pass, B200 build only)\n");
+                puts("Usage: polypolish filter-polish [OPTIONS] --in1 <IN1> --in2 <IN2> <ASSEMBLY>\n");
+                puts("Options: those of `filter` (--out1 / --out2 optional: written only when given) and of `polish` (except --debug)");
+                return 0;
+            }
+            else if (a == "--in1") in1 = need(i, "--in1 <IN1>");
+            else if (a == "--in2") in2 = need(i, "--in2 <IN2>");
+            else if (a == "--out1") out1 = need(i, "--out1 <OUT1>");
+            else if (a == "--out2") out2 = need(i, "--out2 <OUT2>");
+            else if (a == "--orientation") orientation = need(i, "--orientation <ORIENTATION>");
+            else if (a == "--low") low = parse_f64("--low <LOW>", need(i, "--low"));
+            else if (a == "--high") high = parse_f64("--high <HIGH>", need(i, "--high"));
+            else if (a == "-i" || a == "--fraction_invalid") prm.fraction_invalid = parse_f64("--fraction_invalid <FRACTION_INVALID>", need(i, "--fraction_invalid"));
+            else if (a == "-v" || a == "--fraction_valid") prm.fraction_valid = parse_f64("--fraction_valid <FRACTION_VALID>", need(i, "--fraction_valid"));
+            else if (a == "-m" || a == "--max_errors") prm.max_errors = parse_u32("--max_errors <MAX_ERRORS>", need(i, "--max_errors"));
+            else if (a == "-d" || a == "--min_depth") prm.min_depth = parse_u32("--min_depth <MIN_DEPTH>", need(i, "--min_depth"));
+            else if (a == "--careful") prm.careful = 1;
+            else if (a == "--device") device = (int)parse_u32("--device", need(i, "--device"));
+            else if (a == "--quiet") quiet = true;
+            else if (a == "--host-parse") host_parse = true;
+            else if (a.size() > 1 && a[0] == '-' && a != "-") usage_error("unexpected argument '" + a + "' found");
+            else pos.push_back(a);
+        }
+        if (in1.empty() || in2.empty() || pos.size() != 1)
+            usage_error("the following required arguments were not provided:\n  --in1 <IN1>\n  --in2 <IN2>\n  <ASSEMBLY>");
+        const int base = restrict_visible_devices(device, 1) ? 0 : device;
+        pp_ctx* ctx = nullptr;
+        if (pp_create(base, &ctx) != PP_OK) quit_with_error("no usable Blackwell (sm_100) GPU: this build has no CPU fallback");
+        if (host_parse) pp_set_parser(ctx, 1);
+        if (!quiet) fprintf(stderr, "Starting Polypolish filter + polish (B200 build %s)\n\n", pp_version());
+        char* out = nullptr;
+        uint64_t n = 0;
+        int rc = pp_filter_polish_files(ctx, pos[0].c_str(), in1.c_str(), in2.c_str(), out1.empty() ? nullptr : out1.c_str(), out2.empty() ? nullptr : out2.c_str(),
+                                        orientation.c_str(), low, high, &prm, &out, &n, quiet ? 0 : 1);
+        if (rc != PP_OK) { std::string m = pp_last_error(ctx); pp_destroy(ctx); quit_with_error(m); }
+        fwrite(out, 1, n, stdout);
+        fflush(stdout);
+        pp_free(out);
+        pp_destroy(ctx);
+        if (!quiet) fprintf(stderr, "Finished!\n");
+        return 0;
+    }
     usage_error("unrecognized subcommand '" + cmd + "'");
 }

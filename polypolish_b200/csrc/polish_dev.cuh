@@ -2,8 +2,8 @@
 // for logic checks without a GPU, by tests/emu/emu_polish.cpp (g++ with tests/emu/cuda_emu.h standing in for CUDA).
 //
 // Replaces, on the device (reference = /root/reference/src):
-//   process_one_read            alignment.rs:275-305  -> k_prep (goodness, k = #good per read group, --careful, unknown-contig /
-//                                                         CIGAR errors) which also bins every contributing alignment by position
+//   process_one_read            alignment.rs:275-305  -> k_goodk (goodness, k = #good per read group, --careful, unknown-contig /
+//                                                         CIGAR errors), per call, SAM order
 //   get_read_bases_for_each_target_base + trim_bases_for_homopolymers
 //                               alignment.rs:175-201, 364-378 -> k_tile scatter phase (CIGAR walk, right-end trim)
 //   Pileup::add_alignment / PileupBase::add_seq   pileup.rs:189-200, 56-65 -> k_tile (counters in shared memory)
@@ -11,9 +11,11 @@
 //   polish_one_sequence's join + replace("-","")  polish.rs:185-188 -> k_compact
 //
 // Design: the reference's pileup is one counter increment per aligned base into a 80 B/bp array, in read
-// order.  Here the alignments are first binned by reference position (k_prep: one 32-byte record + a 256-position bin key per
-// alignment; a stable radix sort of (key, alignment index) keeps SAM order inside every bin), then ONE persistent kernel
-// (k_tile) owns 2048 consecutive positions at a time with every counter of those positions in shared memory:
+// order.  Here the alignments are binned by reference position ONCE PER DATASET (k_bin: one 32-byte record + a 256-position bin
+// key per alignment; a stable radix sort of (key, alignment index) keeps SAM order inside every bin; k_permute / k_permute_seq
+// move records and the bases of the common reads into that order, forward strand), and per polish call ONE persistent kernel
+// (k_tile) owns 2048 consecutive positions at a time with every counter of those positions in shared memory, streaming the
+// tile's slot range coalesced:
 //   * cover[p]   = good alignments whose kept entries include p: interval add (+1 / -1) + in-tile prefix sum;
 //   * explicit[p][A,C,G,T], del[p] = entries that differ from the draft base: one shared-memory atomic per mismatch
 //     (~0.3 % of bases); count[draft base] = cover - sum(everything explicit); 32-bit counters (pileup.rs:33-37);

@@ -268,3 +268,20 @@ def test_filter_then_polish_errors_and_odd_text(ctx, oracle, tmp_path):
     with pytest.raises(pp.PolypolishError) as e:
         ctx.filter_polish_files(fa, sams[0], sams[1], low=60.0)
     assert "--low must be greater than 0 and less than 50" in e.value.msg
+
+
+def test_cli_filter_polish(oracle, tmp_path):
+    """The additive `polypolish filter-polish` command = `filter` then `polish` of its output."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "polypolish")
+    syn = api.Synth(seed=19, contig_len=25_000, depth=40)
+    fa, sams = syn.write(tmp_path)
+    fo = oracle.filter(sams[0], sams[1])
+    o1, o2 = tmp_path / "o1.sam", tmp_path / "o2.sam"
+    o1.write_bytes(fo["out1"])
+    o2.write_bytes(fo["out2"])
+    exp = oracle.polish(fa, [o1, o2], min_depth=4)["fasta"]
+    r = subprocess.run([exe, "filter-polish", "--in1", sams[0], "--in2=" + sams[1], "-d4", "--quiet", fa], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == exp
