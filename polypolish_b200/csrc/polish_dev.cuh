@@ -40,6 +40,7 @@
 #define TL_THREADS 512
 #define TL_PER_THREAD (TL_T / TL_THREADS)
 #define TL_LONG_E 512                // alignments with more entries than this are not binned: every tile looks at the "long" list
+#define TL_QCAP 1024                 // queued reads per tile (more are walked in place)
 #define TL_FAST_LEN 192              // longest read the register-resident fast path takes
 #define PR_THREADS 256               // k_prep CTA: one alignment per thread
 #define SC_GROUP_SCAN_LIMIT 8192     // alignments of one read group a thread will scan outside its block for k
@@ -683,7 +684,8 @@ struct TileShared {
     double depth[TL_T];                                // ordered f64 depth, valid in flagged sub-tiles
     unsigned long long dn[TL_DN_WORDS + 2];            // 4-bit draft codes, 16 per word, position -32 first
     WalkStage wstage[TL_THREADS / 32];                 // ordered-depth merge staging, one per warp
-    uint32_t wqueue[TL_THREADS / 32][64];              // per warp: sorted slots waiting for the general walk
+    uint32_t queue[TL_QCAP];                           // sorted slots waiting for the two-segment / general walk
+    uint32_t qn;
     unsigned long long s_warp[TL_THREADS / 32];
     unsigned long long s_total;
     long long s_delta[TL_THREADS / 32];
@@ -1169,7 +1171,7 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
 
     for (;;) {
         __syncthreads();                                                       // everyone is done with the previous tile
-        if (tid == 0) { sh.tile = atomicAdd(&d.st->ticket, 1u); sh.subflags = 0; }
+        if (tid == 0) { sh.tile = atomicAdd(&d.st->ticket, 1u); sh.subflags = 0; sh.qn = 0; }
         __syncthreads();
         if (sh.tile >= d.n_tiles) break;
         const uint32_t tile = d.tile_order[sh.tile];
@@ -1205,29 +1207,9 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
         const uint32_t lo = d.bin_start[b0 >= lb ? b0 - lb : 0u];
         const uint32_t hi = d.bin_start[min(b0 + (uint32_t)(TL_T / PP_BIN), d.n_bins)];
         {
-            // reads that need the general walk (indels, long reads, homopolymer tails) are queued per warp and walked 32 at a
-            // time on consecutive lanes instead of one lane at a time
-            uint32_t* wq = sh.wqueue[warp];
-            uint32_t nq_w = 0;                                                         // warp-uniform
-            auto drain = [&]() {                                                       // walks the first min(nq_w, 32) queued slots
-                const uint32_t take = min(nq_w, 32u);
-                if (lane < take) {
-                    const uint32_t i = wq[lane];
-                    const TileRec r = load_srec(d, i);
-                    const uint32_t k = d.kf[r.aln];
-                    uint32_t nk = NONE32;
-                    if (BITS == 4 && (r.flags & TR_FAST1)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), r, i, k);   // one indel: two segments
-                    if (nk == NONE32) nk = general_walk<BITS>(S, r, k);
-                    d.wrec[i] = make_uint4(r.aln, r.gstart, nk, k);
-                }
-                __syncwarp();
-                const uint32_t rest = nq_w - take;
-                const uint32_t keep = (lane < rest) ? wq[take + lane] : 0u;
-                __syncwarp();
-                if (lane < rest) wq[lane] = keep;
-                __syncwarp();
-                nq_w = rest;
-            };
+            // reads that need more than the plain fast walk (one indel: the two-segment fast walk; more indels, long reads,
+            // homopolymer tails: the general walk) go to a block-wide queue and are taken on consecutive lanes after the chunk
+            // loop, which therefore runs the same straight-line code on every lane
             const uint32_t stride = 32u * (TL_THREADS / 32);
             uint32_t c_a = lo + 32u * warp;
             TileRec rec_a, rec_b;
@@ -1256,20 +1238,34 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                         else d.wrec[i] = make_uint4(rec_a.aln, rec_a.gstart, nk, k_a);
                     }
                 }
-                const uint32_t dm = __ballot_sync(0xffffffffu, defer);
-                if (dm) {
-                    if (defer) {
-                        wq[nq_w + (uint32_t)__popc(dm & ((1u << lane) - 1u))] = i;
+                if (defer) {
+                    const uint32_t qi = atomicAdd(&sh.qn, 1u);
+                    if (qi < TL_QCAP) {
+                        sh.queue[qi] = i;
                         PP_PREFETCH_L2(d.cigar_ops + rec_a.cigar_off);                  // what the general walk will chase
                         PP_PREFETCH_L2(d.seq_pool + (size_t)rec_a.seq_off * (BITS == 4 ? 16 : 32));
+                    } else {                                                           // (a tile with more than TL_QCAP such reads)
+                        uint32_t nk = NONE32;
+                        if (BITS == 4 && (rec_a.flags & TR_FAST1)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), rec_a, i, k_a);
+                        if (nk == NONE32) nk = general_walk<BITS>(S, rec_a, k_a);
+                        d.wrec[i] = make_uint4(rec_a.aln, rec_a.gstart, nk, k_a);
                     }
-                    nq_w += (uint32_t)__popc(dm);
-                    __syncwarp();
-                    if (nq_w >= 32) drain();
                 }
                 c_a = c_b; rec_a = rec_b; rec_b = rec_c; k_a = k_b;
             }
-            while (nq_w) drain();
+        }
+        __syncthreads();
+        {
+            const uint32_t qn = min(sh.qn, (uint32_t)TL_QCAP);
+            for (uint32_t qi = tid; qi < qn; qi += TL_THREADS) {
+                const uint32_t i = sh.queue[qi];
+                const TileRec r = load_srec(d, i);
+                const uint32_t k = d.kf[r.aln];
+                uint32_t nk = NONE32;
+                if (BITS == 4 && (r.flags & TR_FAST1)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), r, i, k);   // one indel: two segments
+                if (nk == NONE32) nk = general_walk<BITS>(S, r, k);
+                d.wrec[i] = make_uint4(r.aln, r.gstart, nk, k);
+            }
             // the long list: alignments of more than TL_LONG_E entries, looked at by every tile
             for (uint32_t i = long_lo + tid; i < long_hi; i += TL_THREADS) {
                 const TileRec r = load_srec(d, i);
