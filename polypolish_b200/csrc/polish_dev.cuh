@@ -122,6 +122,7 @@ struct DevData {                     // everything the kernels read, by value
     uint32_t n_slots;                // alignments that can contribute (slots before the "nothing" key)
     const uint32_t* tile_order;      // [n_tiles] tiles by decreasing slot count: the ticket order (heavy tiles first, no long tail)
     uint32_t max_ext;                // largest entry count of a binned alignment (how many bins a tile looks back)
+    uint8_t* errc;                   // [n_aln] 0, or the error the reference raises IF the alignment is good (alignment.rs:187-198,298-300)
     // per call
     uint32_t* kf;                    // [n_aln] k of the alignment's read group if it contributes under the current options, else 0
     uint4* wrec;                     // [n_aln] per sorted slot: (alignment, first position, kept entries, k) - what the ordered depth walk reads
@@ -281,11 +282,15 @@ template <int BITS>
 __device__ __forceinline__ void bin_body(const DevData& d) {
     uint32_t max_ext = 0;
     for (unsigned long long aln = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; aln < d.n_aln; aln += (unsigned long long)gridDim.x * blockDim.x) {
-        uint32_t key = d.n_bins + 1;                            // can never contribute (k_goodk raises the error if it is "good")
+        uint32_t key = d.n_bins + 1;                            // can never contribute (k_goodk raises `err` if it is "good")
+        uint32_t err = 0;
         const uint32_t c = d.contig[aln];
         const uint8_t fl = d.flags[aln];
         const uint32_t ncig = d.n_cigar[aln], cigoff = d.cigar_off[aln];
-        if (c != PP_CONTIG_UNKNOWN && !(fl & (PP_FLAG_NOSEQ | PP_FLAG_GHOST)) && ncig != 0) {
+        if (c == PP_CONTIG_UNKNOWN) err = ERR_UNKNOWN_CONTIG;                      // alignment.rs:298-300
+        else if (fl & PP_FLAG_NOSEQ) err = ERR_NOSEQ;
+        else if (ncig == 0) err = ERR_BAD_OP;                                      // the packer never emits this
+        else {
             const unsigned long long gs = d.contig_off[c] + d.ref_start[aln];
             const unsigned long long ce = d.contig_off[c + 1];
             const uint32_t len = d.seq_len[aln];
@@ -298,9 +303,12 @@ __device__ __forceinline__ void bin_body(const DevData& d) {
                 if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X) { E += l; R += l; }
                 else if (o == PP_OP_I) R += l;
                 else if (o == PP_OP_D) E += l;
-                else bad = true;
+                else bad = true;                                                   // alignment.rs:187-193
             }
-            if (gs < ce && !bad && R == len && len != 0) {
+            if (gs >= ce) err = ERR_OOB;
+            else if (bad) err = ERR_BAD_OP;
+            else if (R != len) err = ERR_SEQ_MISMATCH;                             // :195-198
+            else if (!(fl & PP_FLAG_GHOST) && len != 0) {
                 const bool is_long = E > TL_LONG_E;
                 const uint32_t f0 = ops[0] & 15u;
                 const bool fast = BITS == 4 && ncig == 1 && (f0 == PP_OP_M || f0 == PP_OP_EQ) && len <= TL_FAST_LEN;
@@ -319,6 +327,7 @@ __device__ __forceinline__ void bin_body(const DevData& d) {
                 if (!is_long) max_ext = max(max_ext, (uint32_t)E);
             }
         }
+        d.errc[aln] = (uint8_t)err;
         d.key[aln] = key; d.val[aln] = (uint32_t)aln;
     }
     for (int o = 16; o > 0; o >>= 1) max_ext = max(max_ext, __shfl_down_sync(0xffffffffu, max_ext, o));
@@ -440,26 +449,9 @@ __device__ __forceinline__ void goodk_body(const DevData& d, PrepShared& sh) {
         uint32_t kf = 0;
         if (good) {
             used++;
-            const uint32_t c = d.contig[aln];
-            if (c == PP_CONTIG_UNKNOWN) report_error(d.st, aln, ERR_UNKNOWN_CONTIG);       // alignment.rs:298-300
-            else if (fl & PP_FLAG_NOSEQ) report_error(d.st, aln, ERR_NOSEQ);
-            else {
-                const unsigned long long gs = d.contig_off[c] + d.ref_start[aln];
-                const unsigned long long ce = d.contig_off[c + 1];
-                const uint32_t len = d.seq_len[aln];
-                unsigned long long R = 0;
-                bool bad = false;
-                const uint32_t* ops = d.cigar_ops + cigoff;
-                for (uint32_t p = 0; p < ncig; ++p) {
-                    const uint32_t op = ops[p], o = op & 15u, l = op >> 4;
-                    if (o == PP_OP_M || o == PP_OP_EQ || o == PP_OP_X || o == PP_OP_I) R += l;
-                    else if (o != PP_OP_D) bad = true;                 // alignment.rs:187-193
-                }
-                if (gs >= ce) report_error(d.st, aln, ERR_OOB);
-                else if (bad) report_error(d.st, aln, ERR_BAD_OP);
-                else if (R != len) report_error(d.st, aln, ERR_SEQ_MISMATCH);                 // :195-198
-                else kf = k;
-            }
+            const uint32_t e = d.errc[aln];                     // what the reference raises for a good alignment (found once, by k_bin)
+            if (e) report_error(d.st, aln, e);
+            else kf = k;
         }
         if (aln < d.n_aln) d.kf[aln] = kf;
         __syncthreads();

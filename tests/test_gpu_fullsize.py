@@ -132,3 +132,22 @@ def test_config5_contig_sharded_cross_contig_multimaps(ctx, oracle):
         assert ghosts > 1000
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_depth_70000_counters_are_32_bit(ctx, oracle):
+    """A 2 kbp contig at 70,000x (amplicon / plasmid depths): more than 65,535 alignments over every position.  The reference
+    counts in u32 (pileup.rs:33-37) and so do the tile's shared-memory counters; one tile holds the whole contig (a list of
+    ~950,000 alignments, far more queued reads than the queue holds, depth walks over lists of 10^5 entries)."""
+    d = _workdir(2)
+    try:
+        syn = api.Synth(seed=7, contig_len=2_000, depth=70_000)
+        fa, sams = syn.write(d)
+        exp = oracle.polish(fa, sams)
+        assert max(exp["total_depth"]) / 2000 > 60_000
+        assert ctx.polish_files(fa, sams) == exp["fasta"]
+        f = syn.fasta()
+        p = syn.pack(f)
+        r = ctx.polish_packed(f.view, p.view)
+        assert r["changed"] == exp["changed"] and r["zero_depth"] == exp["zero_depth"]
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
