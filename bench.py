@@ -397,7 +397,8 @@ def main():
                        "timing": "CUDA events on the library stream, max over ranks",
                        "cache": "inputs (%.0f MB packed) larger than the 126 MB L2" % (h2d_bytes / 1e6)},
             "e2e": {"value": total_bp / 1e6 / (e2e_ms_max / 1e3), "unit": "Mbp/s", "ms_per_step": e2e_ms_max,
-                    "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total), "api": "pp_polish (host SoA in, host bases out)"},
+                    "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total), "api": "pp_polish (host SoA in, host bases out)",
+                    "last_step_ms": {k: round(v, 3) for k, v in e["timing"].items() if k.endswith("_ms") and v}},   # h2d = upload + position binning
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_tile<4>", "achieved": k_bytes / 1e9 / (sc_ms / 1e3), "peak": hbm,
                          "unit": "GB/s", "frac": k_bytes / 1e9 / (sc_ms / 1e3) / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": how,
