@@ -387,7 +387,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            traffic = tj.get(args.workload)
+            traffic = tj.get(args.workload) if world == 1 else None
             traffic_src = "static, from profiles/traffic.json (%s); not measured in this run" % tj.get("source", "ncu --set full capture")
         line = {
             "metric": METRIC, "value": total_bp / 1e6 / (ms_step_max / 1e3), "unit": "Mbp/s", "n_gpus": world,

@@ -345,28 +345,36 @@ __device__ __forceinline__ void permute_body(const DevData& d) {
 
 // ... and its bases (4-bit mode, fast-path reads): the EFFECTIVE read - the stored one, or its reverse complement for
 // PP_FLAG_RC records (alignment.rs:161-167: complementing a BAM nibble = reversing its 4 bits, so the whole thing is one bit
-// reversal) - forward, base 0 at nibble 0, zero padded to 192 bases.  One thread per 32-bit word (8 bases).
+// reversal) - forward, base 0 at nibble 0, zero padded to 192 bases.  One thread per 16-byte quad (32 bases).
 __device__ __forceinline__ void permute_seq_body(const DevData& d) {
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long i = t / (4 * TL_SEQ_QUADS);
-    const uint32_t m = (uint32_t)(t % (4 * TL_SEQ_QUADS));
+    const unsigned long long i = t / TL_SEQ_QUADS;
+    const uint32_t g = (uint32_t)(t % TL_SEQ_QUADS);
     if (i >= d.n_slots) return;
     const TileRec& r = d.srec[i];
-    uint32_t out = 0;
-    if (r.flags & TR_FAST) {
-        const uint32_t len = r.len_nc & 0xFFFFu, nw = (len + 7) >> 3;                     // words that hold bases
-        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(d.seq_pool + (size_t)r.seq_off * 16);
-        if (!(r.flags & TR_RC)) { if (m < nw) out = s32[m]; }
-        else {
-            // effective nibble e = complement of stored nibble len-1-e = nibble (8 nw - len + e) of the word-reversed, bit-reversed words
-            const uint32_t pad = 8 * nw - len;
-            auto V = [&](uint32_t x) -> uint32_t { return x < nw ? __brev(s32[nw - 1 - x]) : 0u; };
-            if (m < nw) out = __funnelshift_r(V(m + (pad >> 3)), V(m + (pad >> 3) + 1), (pad & 7) * 4);
-        }
-        if (m == nw - 1 && (len & 7)) out &= 0xFFFFFFFFu >> ((8 - (len & 7)) * 4);         // nothing but zeros past the last base
-        if (m >= nw) out = 0;
+    if (!(r.flags & TR_FAST)) return;                           // the general walk reads the pool itself
+    const uint32_t len = r.len_nc & 0xFFFFu, nw = (len + 7) >> 3;                         // words that hold bases
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(d.seq_pool + (size_t)r.seq_off * 16);
+    uint32_t out[4];
+    if (!(r.flags & TR_RC)) {
+        const uint4 q = *reinterpret_cast<const uint4*>(s32 + 4 * g);                       // (reads past the last word stay inside the padded pool)
+        out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+    } else {
+        // effective nibble e = complement of stored nibble len-1-e = nibble (8 nw - len + e) of the word-reversed, bit-reversed words
+        const uint32_t pad = 8 * nw - len;                      // 0 .. 7
+        uint32_t v[5];
+#pragma unroll
+        for (int w = 0; w < 5; ++w) { const uint32_t x = 4 * g + (uint32_t)w; v[w] = x < nw ? __brev(s32[nw - 1 - x]) : 0u; }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) out[w] = __funnelshift_r(v[w], v[w + 1], pad * 4);
     }
-    reinterpret_cast<uint32_t*>(d.sseq)[t] = out;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t m = 4 * g + (uint32_t)w;
+        if (m >= nw) out[w] = 0;
+        else if (m == nw - 1 && (len & 7)) out[w] &= 0xFFFFFFFFu >> ((8 - (len & 7)) * 4);  // nothing but zeros past the last base
+    }
+    d.sseq[t] = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 // Slots a tile has to look at (its own bins + the look-back): the weight the tiles are handed out by, heaviest first.

@@ -181,8 +181,8 @@ static int bin_dataset(pp_ctx* ctx) {
     if (ctx->n_slots) {
         k_permute<<<(ctx->n_slots + 255) / 256, 256, 0, s>>>(d);
         if (BITS == 4) {
-            const uint64_t words = (uint64_t)ctx->n_slots * 4 * TL_SEQ_QUADS;
-            k_permute_seq<<<(uint32_t)((words + 255) / 256), 256, 0, s>>>(d);
+            const uint64_t quads = (uint64_t)ctx->n_slots * TL_SEQ_QUADS;
+            k_permute_seq<<<(uint32_t)((quads + 255) / 256), 256, 0, s>>>(d);
         }
     }
     {   // tiles by decreasing slot count (the persistent kernel hands them out in that order)

@@ -81,7 +81,7 @@ int run(const pp_contigs* c, const pp_alignments* a, const pp_polish_params* prm
     d.max_ext = st.max_ext;
     if (d.n_slots) {
         emu::launch((d.n_slots + 255) / 256, 256, 0, [&] { permute_body(d); });
-        if (BITS == 4) emu::launch((unsigned)(((uint64_t)d.n_slots * 4 * TL_SEQ_QUADS + 255) / 256), 256, 0, [&] { permute_seq_body(d); });
+        if (BITS == 4) emu::launch((unsigned)(((uint64_t)d.n_slots * TL_SEQ_QUADS + 255) / 256), 256, 0, [&] { permute_seq_body(d); });
     }
     std::vector<uint32_t> tweight(n_tiles + 1), tindex(n_tiles + 1), torder(n_tiles + 1);
     emu::launch((n_tiles + 255) / 256, 256, 0, [&] { tile_weight_body(d, tweight.data(), tindex.data()); });

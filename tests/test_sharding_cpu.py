@@ -197,3 +197,32 @@ def test_shards_equal_python_model(tmp_path, seed, n_shards):
             assert arr[k].tolist() == m[k], (s, k)
         assert bytes(arr["seq_pool"]) == bytes(m["pool"])
         assert arr["n_reads"] == m["n_reads"]
+
+
+def test_filtered_generation_equals_the_sharders_shard(built):
+    """bench.py --gpus N: every rank generates only the reads of the ONE data set that have a record on its contigs
+    (pp_synth_set_shard_filter, per-pair random streams) and runs the sharder on them.  That must be, array for array, the
+    shard the sharder makes from the whole data set - ghost records included."""
+    syn = api.Synth(seed=5, n_contigs=6, contig_len=40_000, depth=30, cross_contig=0.05)
+    f = syn.fasta()
+    full = syn.pack(f)
+    n = 3
+    assign = [c % n for c in range(6)]
+    whole = api.Shards(f.view, full.view, n, shard_of_contig=assign)
+    total_home = 0
+    for s in range(n):
+        syn.set_shard_filter(n, s, assign)
+        part = syn.pack(f)
+        mine = api.Shards(f.view, part.view, n, shard_of_contig=assign, only_shard=s)
+        c1, a1, m1, h1 = whole.get(s)
+        c2, a2, m2, h2 = mine.get(s)
+        x, y = api.view_arrays(a1), api.view_arrays(a2)
+        assert m1 == m2 and h1 == h2 and a1.n_aln == a2.n_aln and a1.n_aln > h1 > 0          # ghosts exist
+        for k in x:
+            if isinstance(x[k], np.ndarray):
+                assert np.array_equal(x[k], y[k]), k
+        assert part.view.n_aln < full.view.n_aln
+        total_home += h1
+    assert total_home == full.view.n_aln
+    syn.set_shard_filter(0, 0)
+    assert syn.pack(f).view.n_aln == full.view.n_aln
