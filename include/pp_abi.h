@@ -53,6 +53,8 @@ void pp_host_free(void* p);
 #define PP_FLAG_NOSEQ   0x10 /* no record of the group carried a sequence (only legal when the group is skipped by --careful) */
 #define PP_FLAG_GHOST   0x20 /* record of a read that lives on another GPU's contigs: counts for goodness / k / --careful,
                                 adds nothing to the pileup (contig sharding, pp_shards_build) */
+#define PP_FLAG_ESC     0x40 /* seq_bits == 2 only: the sequence has a base other than A, C, G, T and lives in esc_pool (4-bit
+                                codes); seq_off then counts esc_pool blocks */
 
 /* CIGAR op codes in cigar_ops (BAM numbering): len << 4 | op.  Zero-length ops are dropped by the packer
  * (they contribute nothing to the expanded CIGAR of alignment.rs:325-346). */
@@ -85,10 +87,23 @@ typedef struct {
   const uint32_t* cigar_ops; /* pool                                                                          */
   uint32_t seq_bits;         /* 4: BAM nibble codes "=ACMGRSVTWYHKDBN", 2 per byte, low nibble first, code 0
                                 never used; 8: upper-cased ASCII bytes (any read with a character outside the
-                                15 letters forces 8-bit mode so that parity holds for arbitrary SEQ bytes)   */
+                                15 letters forces 8-bit mode so that parity holds for arbitrary SEQ bytes);
+                                2: the wire format of pp_alignments_to_2bit - A,C,G,T = 0..3, 4 per byte, low bits
+                                first, 8 bytes per PP_SEQ_BLOCK (same block numbering as the 4-bit pool); sequences
+                                with any other base are PP_FLAG_ESC records in esc_pool.  Expanded to 4-bit on the
+                                device right after the upload: 38 % fewer bytes cross PCIe                       */
   uint64_t seq_pool_bytes;
   const uint8_t* seq_pool;   /* 16-byte aligned                                                               */
+  uint64_t esc_pool_bytes;   /* seq_bits == 2: 4-bit sequences of the PP_FLAG_ESC records (else 0 / NULL)        */
+  const uint8_t* esc_pool;
 } pp_alignments;
+
+/* The 2-bit wire format of a 4-bit batch (host side, done once per batch like the packing itself): *out shares every array
+ * with `in` except flags, seq_off, seq_pool and esc_pool, which belong to *owner (free with pp_2bit_free).  PP_ERR_ARG unless
+ * in->seq_bits == 4. */
+typedef struct pp_2bit pp_2bit;
+int pp_alignments_to_2bit(const pp_alignments* in, pp_alignments* out, pp_2bit** owner);
+void pp_2bit_free(pp_2bit* owner);
 
 /* The assembly: Pileup::new input (pileup.rs:178-187) as loaded by misc::load_fasta (misc.rs:38-167). */
 typedef struct {
@@ -272,6 +287,13 @@ int pp_tok_prefetch(pp_ctx* ctx, const char* path);
 /* Optional, after pp_tok_begin: total bytes of all the files to come, so that the arrays are sized once. */
 int pp_tok_expect(pp_ctx* ctx, uint64_t total_text_bytes);
 int pp_tok_finish(pp_ctx* ctx);        /* the tokenised alignments + the assembly become the resident dataset */
+/* Optional, between pp_tok_begin and pp_tok_finish: this context keeps only a SHARD of the assembly (contig sharding without the
+ * host in the middle: every GPU tokenises the text itself, over its own PCIe link).  local_of[c], c < the assembly's contig count:
+ * the contig's index inside shard_contigs, or 0xFFFFFFFF = another shard's.  At pp_tok_finish the records of foreign contigs
+ * become PP_FLAG_GHOST records (they still count for goodness / k / --careful, exactly like pp_shards_build's), the others are
+ * renumbered, and shard_contigs replaces the assembly as the resident draft.  takes_unknown: the one shard that keeps records whose
+ * RNAME is not in the assembly, so that the reference's error is raised once.  The arrays are copied during the call. */
+int pp_tok_set_shard(pp_ctx* ctx, const uint32_t* local_of, uint32_t n_contigs_total, const pp_contigs* shard_contigs, int takes_unknown);
 /* Which parser pp_polish_files uses for its SAM files: 0 (default) the device tokeniser, with the host packer taking over
  * on PP_TOK_HOST and for --debug / multi-GPU runs; 1 the host packer only.  Both give the same bytes. */
 int pp_set_parser(pp_ctx* ctx, int mode);

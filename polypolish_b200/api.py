@@ -31,7 +31,8 @@ class Alignments(C.Structure):
                 ("contig", C.c_void_p), ("ref_start", C.c_void_p), ("read_id", C.c_void_p), ("seq_off", C.c_void_p),
                 ("seq_len", C.c_void_p), ("cigar_off", C.c_void_p), ("n_cigar", C.c_void_p), ("nm", C.c_void_p),
                 ("flags", C.c_void_p), ("n_cigar_ops", C.c_uint64), ("cigar_ops", C.c_void_p),
-                ("seq_bits", C.c_uint32), ("seq_pool_bytes", C.c_uint64), ("seq_pool", C.c_void_p)]
+                ("seq_bits", C.c_uint32), ("seq_pool_bytes", C.c_uint64), ("seq_pool", C.c_void_p),
+                ("esc_pool_bytes", C.c_uint64), ("esc_pool", C.c_void_p)]
 
 
 class Contigs(C.Structure):
@@ -660,16 +661,46 @@ def view_arrays(v):
                 seq_len=arr(v.seq_len, C.c_uint16, n), cigar_off=arr(v.cigar_off, C.c_uint32, n),
                 n_cigar=arr(v.n_cigar, C.c_uint16, n), nm=arr(v.nm, C.c_uint32, n), flags=arr(v.flags, C.c_uint8, n),
                 cigar_ops=arr(v.cigar_ops, C.c_uint32, v.n_cigar_ops), seq_pool=arr(v.seq_pool, C.c_uint8, v.seq_pool_bytes),
-                seq_bits=v.seq_bits, n_reads=v.n_reads)
+                esc_pool=arr(v.esc_pool, C.c_uint8, v.esc_pool_bytes), seq_bits=v.seq_bits, n_reads=v.n_reads)
 
 
-def polish_files_multi(assembly, sams, devices, verbose=False, **opts):
-    """pp_polish_files_multi: contigs shard over one context per entry of `devices` (entries may repeat)."""
+class TwoBit:
+    """pp_alignments_to_2bit: the 2-bit wire format of a 4-bit batch.  `view` shares every array with the source batch (keep it
+    alive) except flags, seq_off, seq_pool and esc_pool, which this object owns."""
+
+    def __init__(self, aview):
+        L = lib()
+        L.pp_alignments_to_2bit.argtypes = [C.POINTER(Alignments), C.POINTER(Alignments), C.POINTER(C.c_void_p)]
+        L.pp_2bit_free.argtypes = [C.c_void_p]
+        L.pp_2bit_free.restype = None
+        self.view = Alignments()
+        self.h = C.c_void_p()
+        rc = L.pp_alignments_to_2bit(C.byref(aview), C.byref(self.view), C.byref(self.h))
+        if rc != PP_OK:
+            raise ValueError("pp_alignments_to_2bit: rc %d (the source must be a 4-bit batch)" % rc)
+        self._src = aview
+
+    def close(self):
+        if self.h:
+            lib().pp_2bit_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def polish_files_multi(assembly, sams, devices, verbose=False, parser=0, **opts):
+    """pp_polish_files_multi: contigs shard over one context per entry of `devices` (entries may repeat).  parser 0 (default): every
+    context tokenises the text itself and keeps its shard (pp_tok_set_shard); 1: host packer + host sharder."""
     L = lib()
     L.pp_polish_files_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_int,
                                         C.POINTER(PolishParams), C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]
     ctxs = [Context(d) for d in devices]
     try:
+        ctxs[0].set_parser(parser)
         arr_ctx = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
         prm = _params(**opts)
         arr = (C.c_char_p * max(1, len(sams)))(*[str(s).encode() for s in sams])

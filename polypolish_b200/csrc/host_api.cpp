@@ -148,6 +148,10 @@ struct ShardJob {
     pp_polish_result res;
     int rc = PP_OK;
     std::string err;
+    // a shard made on the device (every GPU tokenises the text itself): the shard's contigs live here
+    std::vector<uint32_t> own_map, own_local;
+    std::vector<uint64_t> own_off;
+    std::vector<uint8_t> own_bases;
 };
 
 static void run_shard(ShardJob* j, const pp_polish_params* prm) {
@@ -196,8 +200,9 @@ struct HostCopy {
 
 // SAM files -> resident dataset through the device tokeniser (tok_kernels.cu).  PP_OK, PP_TOK_HOST (the host packer must
 // look at the text), or an error.  `log` collects the per-file lines add_to_pileup prints (alignment.rs:266-271).
+struct DeviceShard { const uint32_t* local_of; uint32_t n_total; pp_contigs contigs; bool takes_unknown; };
 static int tokenise_files(pp_ctx* ctx, const pp_fasta* fa, const char* const* sams, int n_sams, bool careful, std::string& log,
-                          std::string& timing, uint64_t* n_aln) {
+                          std::string& timing, uint64_t* n_aln, const DeviceShard* shard = nullptr) {
     int bits = 4;
     for (int attempt = 0; attempt < 2; ++attempt) {
         log.clear(); timing.clear();
@@ -206,6 +211,7 @@ static int tokenise_files(pp_ctx* ctx, const pp_fasta* fa, const char* const* sa
         uint64_t total = 0;
         for (int i = 0; i < n_sams; ++i) total += pp::file_size(sams[i]);
         if (rc == PP_OK) rc = pp_tok_expect(ctx, total);
+        if (rc == PP_OK && shard) rc = pp_tok_set_shard(ctx, shard->local_of, shard->n_total, &shard->contigs, shard->takes_unknown ? 1 : 0);
         std::vector<pp_tok_stats> st((size_t)n_sams);
         if (rc == PP_OK) rc = pp_tok_add_files(ctx, sams, n_sams, st.data());
         for (int i = 0; i < n_sams && rc == PP_OK; ++i) {
@@ -286,7 +292,7 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
         if (ff && (pass == 1 || pp_get_parser(ctx) != 0)) { need_host_filter = true; break; }
         jobs.assign(n_shards, ShardJob());
         memset(&alns, 0, sizeof alns);
-        bool resident = false;
+        bool resident = false, device_shards = false;
         rc = PP_OK;
         std::string log;
         if (pass == 0 && ff) {
@@ -315,6 +321,58 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
             if (rc != PP_OK) { pp_fasta_free(fa); return rc; }
             resident = n_shards == 1;
             alns.n_aln = fuse.n_aln;
+        } else if (pass == 0 && n_shards > 1) {
+            // Several GPUs, no host in the middle: every GPU streams the text in over its own PCIe link and tokenises it itself; a
+            // contig -> shard map (longest contig first onto the lightest shard) tells it which records are its own, the rest become
+            // ghost records on the device (pp_tok_set_shard).  Nothing is read back, nothing is sharded on the host.
+            std::vector<uint32_t> order(contigs.n_contigs), owner(contigs.n_contigs);
+            for (uint32_t i = 0; i < contigs.n_contigs; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return contigs.off[x + 1] - contigs.off[x] > contigs.off[y + 1] - contigs.off[y]; });
+            std::vector<uint64_t> load(n_shards, 0);
+            for (uint32_t ci : order) {
+                const uint32_t best = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+                owner[ci] = best;
+                load[best] += contigs.off[ci + 1] - contigs.off[ci];
+            }
+            for (uint32_t s = 0; s < n_shards; ++s) {
+                ShardJob& j = jobs[s];
+                j.ctx = ctxs[s];
+                j.own_local.assign(contigs.n_contigs, 0xFFFFFFFFu);
+                j.own_off.assign(1, 0);
+                for (uint32_t ci = 0; ci < contigs.n_contigs; ++ci) {
+                    if (owner[ci] != s) continue;
+                    j.own_local[ci] = (uint32_t)j.own_map.size();
+                    j.own_map.push_back(ci);
+                    j.own_bases.insert(j.own_bases.end(), contigs.bases + contigs.off[ci], contigs.bases + contigs.off[ci + 1]);
+                    j.own_off.push_back(j.own_bases.size());
+                }
+                j.contigs.n_contigs = (uint32_t)j.own_map.size(); j.contigs.off = j.own_off.data(); j.contigs.bases = j.own_bases.data();
+                j.contig_map = j.own_map.data();
+                j.resident = true;
+            }
+            std::vector<int> trc(n_shards, PP_OK);
+            std::vector<std::string> tlog(n_shards), ttime(n_shards);
+            std::vector<uint64_t> tn(n_shards, 0);
+            auto work = [&](uint32_t s) {
+                const DeviceShard ds{jobs[s].own_local.data(), contigs.n_contigs, jobs[s].contigs, s == 0};
+                trc[s] = tokenise_files(ctxs[s], fa, sams, n_sams, prm->careful != 0, tlog[s], ttime[s], &tn[s], &ds);
+                if (trc[s] != PP_OK && trc[s] != PP_TOK_HOST) jobs[s].err = pp_last_error(ctxs[s]);
+            };
+            {
+                std::vector<std::thread> tt;
+                for (uint32_t s = 1; s < n_shards; ++s) tt.emplace_back(work, s);
+                work(0);
+                for (auto& t : tt) t.join();
+            }
+            bool host = false;
+            for (uint32_t s = 0; s < n_shards; ++s) host |= trc[s] == PP_TOK_HOST;
+            if (host) continue;
+            for (uint32_t s = 0; s < n_shards; ++s)
+                if (trc[s] != PP_OK) { rc = pp_ctx_fail(ctx, trc[s], jobs[s].err.c_str()); pp_fasta_free(fa); return rc; }
+            log = tlog[0];
+            for (uint32_t s = 0; s < n_shards; ++s) { tok_timing += ttime[s]; jobs[s].alns.n_aln = tn[s]; }
+            alns.n_aln = tn[0];
+            device_shards = true;
         } else if (pass == 0) {
             uint64_t n_aln = 0;
             rc = tokenise_files(ctx, fa, sams, n_sams, prm->careful != 0, log, tok_timing, &n_aln);
@@ -341,7 +399,9 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
                 return rc;
             }
         }
-        if (n_shards == 1) {
+        if (device_shards) {
+            // (the jobs are set up: each context holds its shard)
+        } else if (n_shards == 1) {
             jobs[0].ctx = ctx; jobs[0].contigs = contigs; jobs[0].alns = alns; jobs[0].resident = resident;
         } else {
             shards = pp_shards_build(&contigs, &alns, n_shards);

@@ -66,6 +66,9 @@ struct DevStatus {
     unsigned int max_ext;            // (binning) largest entry count of a binned alignment: how many bins a tile looks back
     unsigned int ticket;             // next tile (k_tile's dynamic schedule)
     unsigned int pad0, pad1;
+#ifdef PP_TILE_PROF
+    unsigned long long prof[8];      // cycles of thread 0 per phase (A, B, queue, C, D+E), queued reads, tiles, largest queue
+#endif
 };
 
 struct DevParams {                   // pp_polish_params, device resident (refreshed by a memcpy before each call)
@@ -880,9 +883,11 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
     }
     // ---- trim (alignment.rs:364-378): how many of the last bases equal the last one.  The last 8 bases as one word.
     uint32_t run;
+    const uint32_t tw = (len - 8) >> 3;                          // the two words the trim looks at: tw, tw + 1
+    const uint32_t tw0 = __ldg(sp32 + tw), tw1 = __ldg(sp32 + tw + 1);   // (word 24 of the last slot: the pool is padded)
     {
         const uint32_t o = len - 8;
-        const uint32_t t8 = __funnelshift_r(__ldg(sp32 + (o >> 3)), __ldg(sp32 + (o >> 3) + 1), (o & 7) * 4);   // (word 24 of the last slot: the pool is padded)
+        const uint32_t t8 = __funnelshift_r(tw0, tw1, (o & 7) * 4);
         const uint32_t x = t8 ^ ((t8 >> 28) * 0x11111111u);
         const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
         if (nz == 0) return NONE32;                            // 8+ equal bases at the end: the general walk counts them
@@ -907,8 +912,10 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
         const uint32_t first = (uint32_t)lo_b, lastn = (uint32_t)(hi_b - 1);       // first / last valid base
         const uint32_t m_first = first >> 3, m_last = lastn >> 3;
         const uint32_t fmask = 0xFFFFFFFFu << ((first & 7) * 4), lmask = 0xFFFFFFFFu >> ((7 - (lastn & 7)) * 4);
-        const uint32_t emask = (1u << m_first) | (1u << m_last);
-        const uint32_t inner = ((2u << m_last) - (1u << m_first)) & ~emask;        // words strictly between the edge words
+        // an edge word needs its own visit only when it is partly outside [first, lastn] (a read that starts inside the tile starts
+        // on a word boundary: its first word is a whole word like any other)
+        const uint32_t emask = ((first & 7) ? 1u << m_first : 0u) | ((lastn & 7) != 7 ? 1u << m_last : 0u);
+        const uint32_t inner = ((2u << m_last) - (1u << m_first)) & ~emask;        // whole words
         const int o0 = relq + TL_DN_HALO;                       // nibble offset of word 0 in the staged draft
         const int i0 = o0 >> 3;                                 // floor; i0 + m >= 0 for every word of a group that holds a valid word
         const uint32_t sh4 = (uint32_t)(o0 & 7) * 4;
@@ -924,16 +931,8 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
                 if (q[g].w != __funnelshift_r(d3, d4, sh4)) bits |= 8u << (4 * g);
             }
         }
-        uint32_t mm = (bits & inner) | emask;
-        while (mm) {
-            const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
-            mm &= mm - 1;
-            // word m of the read, out of the registers (a select tree: no second trip to memory)
-            const uint32_t g = m >> 2, t4 = m & 3;
-            uint4 qq = q[0];
-#pragma unroll
-            for (int j = 1; j < TL_SEQ_QUADS; ++j) if (g == (uint32_t)j) qq = q[j];
-            const uint32_t wv = t4 == 0 ? qq.x : t4 == 1 ? qq.y : t4 == 2 ? qq.z : qq.w;
+        // every base of word m (value wv) that differs from the draft inside [first, lastn]
+        auto count_word = [&](uint32_t m, uint32_t wv) {
             uint32_t x = wv ^ __funnelshift_r(dn32[i0 + (int)m], dn32[i0 + (int)m + 1], sh4);
             if (m == m_first) x &= fmask;
             if (m == m_last) x &= lmask;
@@ -946,6 +945,22 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
                 if ((code & (code - 1)) == 0) atomicAdd(&S.sh.ex[__ffs((int)code) - 1][rel], 1u);      // A, C, G, T = 1, 2, 4, 8
                 else S.push_other(S.P0 + (uint32_t)rel, aln, 8u * m + t, 1, 1ull | ((unsigned long long)code << 4));
             }
+        };
+        uint32_t mm = (bits & inner) | emask;
+        // the partial last word of a read that ends inside the tile is one of the two words the trim already holds: straight-line
+        if (((emask >> m_last) & 1u) && m_last - tw < 2u) {
+            mm &= ~(1u << m_last);
+            count_word(m_last, m_last == tw ? tw0 : tw1);
+        }
+        while (mm) {                                           // words that differ (about one word in two reads), clipped edge words
+            const uint32_t m = (uint32_t)__ffs((int)mm) - 1;
+            mm &= mm - 1;
+            // word m of the read, out of the registers (a select tree: no second trip to memory)
+            const uint32_t g = m >> 2, t4 = m & 3;
+            uint4 qq = q[0];
+#pragma unroll
+            for (int j = 1; j < TL_SEQ_QUADS; ++j) if (g == (uint32_t)j) qq = q[j];
+            count_word(m, t4 == 0 ? qq.x : t4 == 1 ? qq.y : t4 == 2 ? qq.z : qq.w);
         }
     };
     if (!one) segment((int)g0, 0, (int)nkept);
@@ -1177,6 +1192,10 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
         const uint32_t tile = d.tile_order[sh.tile];
         const uint32_t P0 = tile * (uint32_t)TL_T;
         TileCtx<BITS> S{d, sh, P0};
+#ifdef PP_TILE_PROF
+        long long pt[6];
+        pt[0] = clock64();
+#endif
         // ---- phase A: clear the counters, stage the draft as 4-bit codes
         {
             uint4* z = reinterpret_cast<uint4*>(sh.cdiff);
@@ -1200,6 +1219,9 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             }
         }
         __syncthreads();
+#ifdef PP_TILE_PROF
+        pt[1] = clock64();
+#endif
         // ---- phase B: every alignment that can touch the tile: the slots of the tile's bins and of the `lb` bins before it - one
         // contiguous range of the binned dataset.  Warps take chunks of 32 consecutive slots round robin: records and bases stream
         // in coalesced; the only gather is the 4-byte "k / contributes" word of the current options, fetched one chunk ahead.
@@ -1255,9 +1277,15 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             }
         }
         __syncthreads();
+#ifdef PP_TILE_PROF
+        pt[2] = clock64();
+#endif
         {
+            // Each of these walks is a chain of dependent loads with its own branches: 32 of them on one warp run in lock step through
+            // the union of their paths (measured: 38 queued reads per tile took a third of the tile's time on two warps).  So the
+            // queue is dealt one read per WARP first - lane 0 of every warp, then lane 1, ... - and the walks overlap instead.
             const uint32_t qn = min(sh.qn, (uint32_t)TL_QCAP);
-            for (uint32_t qi = tid; qi < qn; qi += TL_THREADS) {
+            for (uint32_t qi = lane * (TL_THREADS / 32) + warp; qi < qn; qi += TL_THREADS) {
                 const uint32_t i = sh.queue[qi];
                 const TileRec r = load_srec(d, i);
                 const uint32_t k = d.kf[r.aln];
@@ -1274,7 +1302,11 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 if (k != 0 && e_end > P0 && r.gstart < P0 + (uint32_t)TL_T) d.wrec[i] = make_uint4(r.aln, r.gstart, general_walk<BITS>(S, r, k), k);
             }
         }
+        __syncwarp();          // lanes that had a queued read rejoin their warp here: without it the warp may run phase C in two groups
         __syncthreads();
+#ifdef PP_TILE_PROF
+        pt[3] = clock64();
+#endif
         // ---- phase C: difference arrays -> cover / multi per position
         const uint32_t rel0 = tid * TL_PER_THREAD;
         uint32_t cover[TL_PER_THREAD], multi[TL_PER_THREAD];
@@ -1292,6 +1324,9 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             if (anym) atomicOr(&sh.subflags, 1u << (rel0 >> PP_SUB_SHIFT));
         }
         __syncthreads();
+#ifdef PP_TILE_PROF
+        pt[4] = clock64();
+#endif
         // ---- phase D: ordered depth where a sub-tile sees k != 1.  Warp w owns sub-tile w here AND in the vote below, so there is
         // no block-wide barrier in between: warps of unflagged sub-tiles go straight on.
         if ((sh.subflags >> warp) & 1u) depth_walk<BITS>(d, sh, sh.wstage[warp], P0, warp, lb, long_lo, long_hi);
@@ -1408,6 +1443,13 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             long long t = 0;
             for (int i = 0; i < TL_THREADS / 32; ++i) t += sh.s_delta[i];
             vp.chunk_delta[tile] = t;
+#ifdef PP_TILE_PROF
+            pt[5] = clock64();
+            for (int i = 0; i < 5; ++i) atomicAdd(&d.st->prof[i], (unsigned long long)(pt[i + 1] - pt[i]));
+            atomicAdd(&d.st->prof[5], (unsigned long long)sh.qn);
+            atomicAdd(&d.st->prof[6], 1ull);
+            atomicMax(&d.st->prof[7], (unsigned long long)sh.qn);
+#endif
         }
     }
 }

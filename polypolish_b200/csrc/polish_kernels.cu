@@ -6,6 +6,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <functional>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -48,6 +49,9 @@ extern "C" int pp_create(int device, pp_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) { delete ctx; return PP_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->ev_small, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_seq, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     for (auto& ev : ctx->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     if (cudaHostAlloc((void**)&ctx->h_status, sizeof(DevStatus), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     if (cudaHostAlloc((void**)&ctx->h_params, sizeof(DevParams), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
@@ -67,6 +71,9 @@ extern "C" void pp_destroy(pp_ctx* ctx) {
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
+    if (ctx->ev_small) cudaEventDestroy(ctx->ev_small);
+    if (ctx->ev_seq) cudaEventDestroy(ctx->ev_seq);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -136,8 +143,9 @@ static void fill_data(pp_ctx* ctx, DevData& d) {
 // every alignment that can ever contribute) -> stable radix sort of (key, alignment) -> k_bin_bounds -> k_permute (records into
 // slot order) -> k_permute_seq (the bases of the fast-path reads into slot order, forward strand).  Nothing here depends on the
 // polish options: repeated pp_polish_resident calls reuse it, and pp_polish pays for it inside its own call.
+// `seq_ready`: run right before the first kernel that reads the sequence pool (pp_dataset_upload finishes the pool's upload there).
 template <int BITS>
-static int bin_dataset(pp_ctx* ctx) {
+static int bin_dataset(pp_ctx* ctx, const std::function<int()>& seq_ready) {
     cudaStream_t s = ctx->stream;
     const uint64_t n_aln = ctx->n_aln, G = ctx->G;
     const uint32_t n_bins = (uint32_t)((G + PP_BIN - 1) >> PP_BIN_SHIFT);
@@ -178,8 +186,9 @@ static int bin_dataset(pp_ctx* ctx) {
     CK(ctx->b[B_NK].ensure(ns * 16));
     CK(ctx->b[B_KF].ensure(na * 4));
     fill_data(ctx, d);
+    if (ctx->n_slots) k_permute<<<(ctx->n_slots + 255) / 256, 256, 0, s>>>(d);
+    if (seq_ready) { const int rc = seq_ready(); if (rc != PP_OK) return rc; }
     if (ctx->n_slots) {
-        k_permute<<<(ctx->n_slots + 255) / 256, 256, 0, s>>>(d);
         if (BITS == 4) {
             const uint64_t quads = (uint64_t)ctx->n_slots * TL_SEQ_QUADS;
             k_permute_seq<<<(uint32_t)((quads + 255) / 256), 256, 0, s>>>(d);
@@ -202,20 +211,55 @@ static int bin_dataset(pp_ctx* ctx) {
     }
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
-    // the SAM-order scratch of the binning is not needed again
-    ctx->b[B_RECS].release(); ctx->b[B_KEY].release(); ctx->b[B_VAL].release(); ctx->b[B_SKEY].release();
+    // the SAM-order scratch of the binning is not needed again; small ones stay for the next dataset (pp_polish per batch: no
+    // cudaMalloc / cudaFree on the path)
+    if (ctx->b[B_RECS].cap + ctx->b[B_KEY].cap + ctx->b[B_VAL].cap + ctx->b[B_SKEY].cap > (1ull << 30)) {
+        ctx->b[B_RECS].release(); ctx->b[B_KEY].release(); ctx->b[B_VAL].release(); ctx->b[B_SKEY].release();
+    }
     return PP_OK;
 }
 
+// seq_bits == 2 uploads (pp_alignments_to_2bit): 8 bytes of 2-bit codes -> the 16 bytes of one-hot BAM nibbles (A=1 C=2 G=4 T=8) the
+// kernels read.  One thread per 32-base block; the tail of a read's last block expands to 'A's, which nothing reads (every consumer
+// masks by the read length).
+__device__ __forceinline__ unsigned long long expand16(uint32_t v) {
+    unsigned long long x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;                 // code c of base i in bits 4i..4i+1
+    const unsigned long long one = 0x1111111111111111ull;
+    const unsigned long long b0 = x & one, b1 = (x >> 1) & one, n0 = b0 ^ one, n1 = b1 ^ one;
+    return (n1 & n0) | ((n1 & b0) << 1) | ((b1 & n0) << 2) | ((b1 & b0) << 3);
+}
+__global__ void k_expand2(const uint2* __restrict__ in, uint4* __restrict__ out, uint64_t n_blocks) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_blocks; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint2 v = __ldg(in + i);
+        const unsigned long long lo = expand16(v.x), hi = expand16(v.y);
+        out[i] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+    }
+}
+// PP_FLAG_ESC records: their sequences sit behind the expanded pool.
+__global__ void k_esc_offsets(uint32_t* __restrict__ seq_off, const uint8_t* __restrict__ flags, uint64_t n_aln, uint32_t first_esc_block) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_aln; i += (uint64_t)gridDim.x * blockDim.x)
+        if (flags[i] & PP_FLAG_ESC) seq_off[i] += first_esc_block;
+}
+
 // The alignment arrays in ctx->b[B_CONTIG..B_SEQPOOL] become the resident dataset.
+static int commit_dataset(pp_ctx* ctx, uint64_t n_aln, uint64_t n_reads, uint64_t n_ops, uint64_t seq_bytes, uint32_t seq_bits,
+                          const std::function<int()>& seq_ready);
 int pp_ctx_commit_dataset(pp_ctx* ctx, uint64_t n_aln, uint64_t n_reads, uint64_t n_ops, uint64_t seq_bytes, uint32_t seq_bits) {
+    return commit_dataset(ctx, n_aln, n_reads, n_ops, seq_bytes, seq_bits, nullptr);
+}
+static int commit_dataset(pp_ctx* ctx, uint64_t n_aln, uint64_t n_reads, uint64_t n_ops, uint64_t seq_bytes, uint32_t seq_bits,
+                          const std::function<int()>& seq_ready) {
     if (n_aln >= 0x7FFFFFFFull - 4096) return ctx->fail(PP_ERR_ARG, "more than 2^31-4096 alignments in one call");
     ctx->n_aln = n_aln; ctx->n_reads = n_reads; ctx->n_ops = n_ops; ctx->seq_bytes = seq_bytes; ctx->seq_bits = seq_bits;
     // first guesses; a call that overflows one of them grows it and repeats itself
     ctx->node_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFFFull, std::max<uint64_t>(1 << 16, n_aln / 8 + ctx->G / 64));
     ctx->out_cap = ctx->G + ctx->G / 16 + (1u << 20);
     ctx->global_k = false;
-    int rc = ctx->seq_bits == 4 ? bin_dataset<4>(ctx) : bin_dataset<8>(ctx);
+    int rc = ctx->seq_bits == 4 ? bin_dataset<4>(ctx, seq_ready) : bin_dataset<8>(ctx, seq_ready);
     if (rc != PP_OK) return rc;
     ctx->have_ds = true;
     return PP_OK;
@@ -227,7 +271,11 @@ extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alig
     if (a->n_aln && (!a->contig || !a->ref_start || !a->read_id || !a->seq_off || !a->seq_len || !a->cigar_off ||
                      !a->n_cigar || !a->nm || !a->flags || !a->cigar_ops))
         return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: null alignment array");
-    if (a->seq_bits != 4 && a->seq_bits != 8) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: seq_bits must be 4 or 8");
+    if (a->seq_bits != 4 && a->seq_bits != 8 && a->seq_bits != 2) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: seq_bits must be 4, 8 or 2");
+    const bool two_bit = a->seq_bits == 2;
+    if (two_bit && ((a->seq_pool_bytes & 7) || (a->esc_pool_bytes & 15) || (a->esc_pool_bytes && !a->esc_pool) ||
+                    a->seq_pool_bytes / 8 + a->esc_pool_bytes / 16 >= 0xFFFFFFFFull))
+        return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: 2-bit pool must be whole 8-byte blocks, esc_pool whole 16-byte blocks");
     if (a->n_aln >= 0x7FFFFFFFull - 4096) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: more than 2^31-4096 alignments in one call");
     CK(cudaSetDevice(ctx->device));
     ctx->have_ds = false;
@@ -242,10 +290,36 @@ extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alig
     if ((rc = upload(ctx, B_NM, a->nm, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_FLAGS, a->flags, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_CIGOPS, a->cigar_ops, a->n_cigar_ops))) return rc;
-    if ((rc = upload(ctx, B_SEQPOOL, a->seq_pool, a->seq_pool_bytes, 256))) return rc;
     if ((rc = pp_ctx_upload_contigs(ctx, c))) { ctx->err = "pp_dataset_upload: " + ctx->err; return rc; }
-    CK(cudaStreamSynchronize(ctx->stream));
-    return pp_ctx_commit_dataset(ctx, a->n_aln, a->n_reads, a->n_cigar_ops, a->seq_pool_bytes, a->seq_bits);
+    // The sequence pool - two thirds of the bytes - goes last, on its own stream: the binning of the records (k_bin, the sort, k_permute)
+    // needs none of it and runs while it crosses PCIe; the stream joins right before k_permute_seq.
+    const uint64_t n_blocks2 = a->seq_pool_bytes / 8;
+    const uint64_t seq_bytes = two_bit ? n_blocks2 * 16 + a->esc_pool_bytes : a->seq_pool_bytes;
+    CK(ctx->b[B_SEQPOOL].ensure(seq_bytes + 256));
+    if (two_bit) CK(ctx->b[B_SEQ2].ensure(a->seq_pool_bytes + 256));
+    CK(cudaEventRecord(ctx->ev_small, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_small, 0));                   // (after the small arrays: they are needed first)
+    if (!two_bit) {
+        if (a->seq_pool_bytes) CK(cudaMemcpyAsync(ctx->b[B_SEQPOOL].p, a->seq_pool, a->seq_pool_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+        if (a->seq_pool_bytes) CK(cudaMemcpyAsync(ctx->b[B_SEQ2].p, a->seq_pool, a->seq_pool_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (a->esc_pool_bytes)
+            CK(cudaMemcpyAsync(ctx->b[B_SEQPOOL].as<uint8_t>() + n_blocks2 * 16, a->esc_pool, a->esc_pool_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (a->esc_pool_bytes && a->n_aln)
+            k_esc_offsets<<<(uint32_t)std::min<uint64_t>((a->n_aln + 255) / 256, (uint64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
+                ctx->b[B_SEQOFF].as<uint32_t>(), ctx->b[B_FLAGS].as<uint8_t>(), a->n_aln, (uint32_t)n_blocks2);
+    }
+    CK(cudaEventRecord(ctx->ev_seq, ctx->copy_stream));
+    auto seq_ready = [&]() -> int {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_seq, 0));
+        if (two_bit && n_blocks2)
+            k_expand2<<<(uint32_t)std::min<uint64_t>((n_blocks2 + 255) / 256, (uint64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
+                ctx->b[B_SEQ2].as<uint2>(), ctx->b[B_SEQPOOL].as<uint4>(), n_blocks2);
+        return PP_OK;
+    };
+    rc = commit_dataset(ctx, a->n_aln, a->n_reads, a->n_cigar_ops, seq_bytes, two_bit ? 4u : a->seq_bits, seq_ready);
+    if (rc != PP_OK) cudaStreamSynchronize(ctx->copy_stream);                      // (the caller's buffers are free again on every return)
+    return rc;
 }
 
 static const char* err_text(unsigned code) {
@@ -348,6 +422,11 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
         const DevStatus hs = *ctx->h_status;
+#ifdef PP_TILE_PROF
+        fprintf(stderr, "[tile prof] tiles %llu; cycles/tile: A %.0f B %.0f queue %.0f C %.0f D+E %.0f; queued reads/tile %.1f (max %llu)\n", hs.prof[6],
+                (double)hs.prof[0] / hs.prof[6], (double)hs.prof[1] / hs.prof[6], (double)hs.prof[2] / hs.prof[6], (double)hs.prof[3] / hs.prof[6],
+                (double)hs.prof[4] / hs.prof[6], (double)hs.prof[5] / hs.prof[6], hs.prof[7]);
+#endif
         if (hs.err != ~0ull) {
             res->error_aln = (int64_t)(hs.err >> 8);
             return ctx->fail(PP_ERR_INPUT, std::string(err_text((unsigned)(hs.err & 0xFF))) + " (alignment " + std::to_string(hs.err >> 8) + ")");

@@ -571,3 +571,63 @@ extern "C" int pp_pack_file_stats(const pp_pack* p, uint32_t file, uint64_t* ali
     if (reads) *reads = p->files[file].reads;
     return PP_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------------
+// The 2-bit wire format (pp_abi.h: seq_bits == 2): a read of A/C/G/T only needs 2 bits per base on its way over PCIe; the device
+// expands it to the 4-bit codes every kernel works on.  Sequences with any other base (N, IUPAC) stay 4-bit in esc_pool.
+// ------------------------------------------------------------------------------------------------------
+struct pp_2bit {
+    std::vector<uint8_t> flags;
+    std::vector<uint32_t> seq_off;
+    pp::AlignedBytes pool2, esc;
+};
+
+extern "C" int pp_alignments_to_2bit(const pp_alignments* in, pp_alignments* out, pp_2bit** owner) {
+    if (!in || !out || !owner || in->seq_bits != 4) return PP_ERR_ARG;
+    pp_2bit* W = new pp_2bit();
+    const uint64_t n = in->n_aln;
+    const uint64_t n_blocks = in->seq_pool_bytes / 16;
+    W->flags.assign(in->flags, in->flags + n);
+    W->seq_off.assign(in->seq_off, in->seq_off + n);
+    W->pool2.resize_zero(n_blocks * 8 + 64);
+    std::unordered_map<uint32_t, uint32_t> esc_at;                 // 4-bit block offset of an escaped sequence -> its esc_pool block
+    uint64_t esc_blocks = 0;
+    static const uint8_t two[16] = {0xFF, 0, 1, 0xFF, 2, 0xFF, 0xFF, 0xFF, 3, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF};   // A=1 C=2 G=4 T=8
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint8_t fl = in->flags[i];
+        if (fl & (PP_FLAG_SEQSTAR | PP_FLAG_NOSEQ)) continue;       // shares its group's sequence / has none
+        const uint32_t off = in->seq_off[i], len = in->seq_len[i];
+        const uint8_t* src = in->seq_pool + (size_t)off * 16;
+        uint8_t* dst = W->pool2.p + (size_t)off * 8;
+        bool plain = true;
+        for (uint32_t b = 0; b < len && plain; ++b) plain = two[(src[b >> 1] >> ((b & 1) * 4)) & 15] != 0xFF;
+        if (plain) {
+            for (uint32_t b = 0; b < len; ++b) dst[b >> 2] |= (uint8_t)(two[(src[b >> 1] >> ((b & 1) * 4)) & 15] << ((b & 3) * 2));
+        } else {
+            const uint64_t blocks = ((uint64_t)len + PP_SEQ_BLOCK - 1) / PP_SEQ_BLOCK;
+            W->esc.resize_zero((esc_blocks + blocks) * 16);
+            memcpy(W->esc.p + esc_blocks * 16, src, blocks * 16);
+            esc_at.emplace(off, (uint32_t)esc_blocks);
+            esc_blocks += blocks;
+        }
+    }
+    if (!esc_at.empty())
+        for (uint64_t i = 0; i < n; ++i) {
+            if (in->flags[i] & PP_FLAG_NOSEQ) continue;
+            auto it = esc_at.find(in->seq_off[i]);
+            if (it != esc_at.end()) { W->flags[i] |= PP_FLAG_ESC; W->seq_off[i] = it->second; }
+        }
+    *out = *in;
+    out->flags = W->flags.data();
+    out->seq_off = W->seq_off.data();
+    out->seq_bits = 2;
+    out->seq_pool = W->pool2.p;
+    out->seq_pool_bytes = n_blocks * 8;
+    out->esc_pool = W->esc.p;
+    out->esc_pool_bytes = esc_blocks * 16;
+    *owner = W;
+    return PP_OK;
+}
+
+extern "C" void pp_2bit_free(pp_2bit* owner) { delete owner; }

@@ -42,6 +42,7 @@ extern "C" pp_shards* pp_shards_build(const pp_contigs* c, const pp_alignments* 
 extern "C" pp_shards* pp_shards_build_assigned(const pp_contigs* c, const pp_alignments* a, uint32_t n_shards,
                                                const uint32_t* assigned, int32_t only_shard) {
     if (!c || !a || n_shards == 0 || only_shard >= (int32_t)n_shards) return nullptr;
+    if (a->seq_bits != 4 && a->seq_bits != 8) return nullptr;      // (the 2-bit wire format is made per shard, after sharding)
     if (assigned) for (uint32_t i = 0; i < c->n_contigs; ++i) if (assigned[i] >= n_shards) return nullptr;
     const uint32_t nc = c->n_contigs;
     pp_shards* S = new pp_shards();

@@ -255,6 +255,12 @@ struct TokState {
     uint8_t* h_nl = nullptr;              // pinned '\n'
     DevBuf cub;
     TokFilterBufs* fbufs = nullptr;   // device buffers of the filter text path
+    // pp_tok_set_shard: this context keeps one shard of the assembly
+    bool shard_on = false, shard_unknown = false;
+    DevBuf shard_map;                 // local_of[c] on the device
+    uint32_t shard_n_total = 0;
+    std::vector<uint64_t> shard_off;
+    std::vector<uint8_t> shard_bases;
 };
 
 static void free_filter_bufs(TokFilterBufs* b);
@@ -277,6 +283,7 @@ void pp_tok_release(pp_ctx* ctx) {
     if (T->h_tot) cudaFreeHost(T->h_tot);
     if (T->d_st) cudaFree(T->d_st);
     T->cub.release();
+    T->shard_map.release();
     delete T;
     ctx->tok = nullptr;
 }
@@ -338,6 +345,40 @@ extern "C" int pp_tok_begin(pp_ctx* ctx, const pp_fasta* fa, int careful, int se
     T->aln_base = T->ops_base = T->blk_base = T->read_base = 0;
     T->expect_total = 0;
     T->active = true;
+    T->shard_on = false;
+    return PP_OK;
+}
+
+// Records of contigs this shard does not hold become ghosts (shard.cpp does the same on the host: contig 0, PP_FLAG_GHOST); the rest
+// get the shard's contig numbers.
+__global__ void k_shard_mark(uint32_t* __restrict__ contig, uint8_t* __restrict__ flags, uint64_t n_aln, const uint32_t* __restrict__ local_of,
+                             uint32_t n_total, int takes_unknown) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_aln; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = contig[i];
+        uint32_t l = 0xFFFFFFFFu;
+        if (c == PP_CONTIG_UNKNOWN || c >= n_total) { if (takes_unknown) continue; }
+        else l = local_of[c];
+        if (l == 0xFFFFFFFFu) { contig[i] = 0; flags[i] |= PP_FLAG_GHOST; }
+        else contig[i] = l;
+    }
+}
+
+extern "C" int pp_tok_set_shard(pp_ctx* ctx, const uint32_t* local_of, uint32_t n_contigs_total, const pp_contigs* sc, int takes_unknown) {
+    if (!ctx) return PP_ERR_ARG;
+    TokState* T = ctx->tok;
+    if (!T || !T->active) return ctx->fail(PP_ERR_ARG, "pp_tok_set_shard: no pp_tok_begin");
+    if (!local_of || !sc || !sc->off || !sc->bases || sc->n_contigs == 0) return ctx->fail(PP_ERR_ARG, "pp_tok_set_shard: null or empty shard");
+    for (uint32_t c = 0; c < n_contigs_total; ++c)
+        if (local_of[c] != 0xFFFFFFFFu && local_of[c] >= sc->n_contigs) return ctx->fail(PP_ERR_ARG, "pp_tok_set_shard: local index outside the shard");
+    CK(cudaSetDevice(ctx->device));
+    CK(T->shard_map.ensure((size_t)n_contigs_total * 4 + 16));
+    CK(cudaMemcpyAsync(T->shard_map.p, local_of, (size_t)n_contigs_total * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    T->shard_off.assign(sc->off, sc->off + sc->n_contigs + 1);
+    T->shard_bases.assign(sc->bases, sc->bases + sc->off[sc->n_contigs]);
+    T->shard_n_total = n_contigs_total;
+    T->shard_unknown = takes_unknown != 0;
+    T->shard_on = true;
     return PP_OK;
 }
 
@@ -784,6 +825,21 @@ extern "C" int pp_tok_finish(pp_ctx* ctx) {
     TokState* T = ctx->tok;
     if (!T || !T->active) return ctx->fail(PP_ERR_ARG, "pp_tok_finish: no tokenised text");
     T->active = false;
+    if (T->shard_on) {
+        T->shard_on = false;
+        CK(cudaSetDevice(ctx->device));
+        if (T->aln_base)
+            k_shard_mark<<<(uint32_t)std::min<uint64_t>((T->aln_base + 255) / 256, (uint64_t)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
+                ctx->b[B_CONTIG].as<uint32_t>(), ctx->b[B_FLAGS].as<uint8_t>(), T->aln_base, T->shard_map.as<uint32_t>(), T->shard_n_total,
+                T->shard_unknown ? 1 : 0);
+        pp_contigs sc;
+        sc.n_contigs = (uint32_t)T->shard_off.size() - 1; sc.off = T->shard_off.data(); sc.bases = T->shard_bases.data();
+        int rc = pp_ctx_upload_contigs(ctx, &sc);           // the shard's contigs are the draft from here on
+        if (rc != PP_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));             // (pageable sources)
+        CK(cudaGetLastError());
+        std::vector<uint8_t>().swap(T->shard_bases);
+    }
     return pp_ctx_commit_dataset(ctx, T->aln_base, T->read_base, T->ops_base, T->blk_base * (T->seq_bits == 4 ? 16 : 32), (uint32_t)T->seq_bits);
 }
 

@@ -228,6 +228,44 @@ def test_multi_context_file_path(oracle, tmp_path):
     assert api.polish_files_multi(fa2, sams2, devices=[0, 0, 0]) == oracle.polish(fa2, sams2)["fasta"]
 
 
+@pytest.mark.parametrize("seed", range(40, 52))
+def test_device_side_shards_fuzz(oracle, tmp_path, seed):
+    """Several contexts, no host in the middle: every context tokenises the text and keeps its own contigs (pp_tok_set_shard: foreign
+    records become ghosts on the device).  Same FASTA as the oracle, as the host packer + host sharder, and the reference's errors."""
+    case = fuzzgen.make_case(seed, n_contigs=2 + seed % 3, multimap=0.6, exotic=0.5 if seed % 4 == 0 else 0.0,
+                             opts=dict(careful=(seed % 3 == 0)))
+    fa, sams = case.write(tmp_path)
+    try:
+        exp = ("ok", oracle.polish(fa, sams, **case.opts)["fasta"])
+    except Exception as e:
+        exp = ("err", e.msg)
+    for parser in (0, 1):
+        for n in (2, 3):
+            try:
+                got = ("ok", api.polish_files_multi(fa, sams, devices=[0] * n, parser=parser, **case.opts))
+            except pp.PolypolishError as e:
+                got = ("err", e.msg)
+            assert got == exp, (parser, n)
+
+
+def test_device_side_shards_errors(oracle, tmp_path):
+    """Data errors under device-side sharding are the reference's, raised once: an RNAME that is not in the assembly, a CIGAR that does
+    not match its SEQ, on a record of the second shard."""
+    fa = tmp_path / "a.fasta"
+    fa.write_text(">c1\n" + "ACGTTGCAAGCTTAGGCATCGATTACGGATCCATGCAAGTCCGATAGGCT" * 2 + "\n>c2\n" + "TTGACCGTAGCTAGGATCCGATCGGATTAGCCTAGGCTTAACGGATCGAT" + "\n")
+    good = "r1\t0\tc1\t1\t60\t20M\t*\t0\t0\tACGTTGCAAGCTTAGGCATC\t*\tNM:i:0"
+    for bad in ("r2\t0\tnope\t1\t60\t10M\t*\t0\t0\tACGTTGCAAG\t*\tNM:i:0",
+                "r2\t0\tc2\t1\t60\t12M\t*\t0\t0\tTTGACCGTAG\t*\tNM:i:0",
+                "r2\t0\tc2\t45\t60\t10M\t*\t0\t0\tGATCGATTTT\t*\tNM:i:0"):
+        sam = tmp_path / "a.sam"
+        sam.write_text(good + "\n" + bad + "\n")
+        with pytest.raises(Exception) as e1:
+            oracle.polish(str(fa), [str(sam)])
+        with pytest.raises(pp.PolypolishError) as e2:
+            api.polish_files_multi(str(fa), [str(sam)], devices=[0, 0])
+        assert e2.value.msg == e1.value.msg
+
+
 def test_cli_binary(oracle, tmp_path):
     """The drop-in command line: same flags as the reference, FASTA on stdout, Error + exit 1 on user errors."""
     import subprocess
