@@ -293,6 +293,10 @@ int pp_tok_finish(pp_ctx* ctx);        /* the tokenised alignments + the assembl
  * become PP_FLAG_GHOST records (they still count for goodness / k / --careful, exactly like pp_shards_build's), the others are
  * renumbered, and shard_contigs replaces the assembly as the resident draft.  takes_unknown: the one shard that keeps records whose
  * RNAME is not in the assembly, so that the reference's error is raised once.  The arrays are copied during the call. */
+/* n byte ranges of a SAM file for n GPUs: cuts[0] = 0, cuts[n] = the file size, every other cut is the start of a line whose QNAME
+ * differs from the line before it, so that no read group (alignment.rs:214-272) is split.  PP_ERR_IO: not a plain file / a line longer
+ * than 1 MiB.  (pp_polish_files_multi gives range g of every file to GPU g, then the GPUs exchange read groups by contig.) */
+int pp_sam_split_ranges(const char* path, int n, uint64_t* cuts /* [n + 1] */);
 int pp_tok_set_shard(pp_ctx* ctx, const uint32_t* local_of, uint32_t n_contigs_total, const pp_contigs* shard_contigs, int takes_unknown);
 /* Which parser pp_polish_files uses for its SAM files: 0 (default) the device tokeniser, with the host packer taking over
  * on PP_TOK_HOST and for --debug / multi-GPU runs; 1 the host packer only.  Both give the same bytes. */

@@ -692,13 +692,14 @@ class TwoBit:
             pass
 
 
-def polish_files_multi(assembly, sams, devices, verbose=False, parser=0, **opts):
-    """pp_polish_files_multi: contigs shard over one context per entry of `devices` (entries may repeat).  parser 0 (default): every
-    context tokenises the text itself and keeps its shard (pp_tok_set_shard); 1: host packer + host sharder."""
+def polish_files_multi(assembly, sams, devices=None, verbose=False, parser=0, contexts=None, **opts):
+    """pp_polish_files_multi: contigs shard over one context per entry of `devices` (entries may repeat), or over the given `contexts`
+    (reused across calls like a long-running host would).  parser 0 (default): every context tokenises the text itself and keeps its
+    shard (pp_tok_set_shard); 1: host packer + host sharder."""
     L = lib()
     L.pp_polish_files_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.POINTER(C.c_char_p), C.c_int,
                                         C.POINTER(PolishParams), C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int]
-    ctxs = [Context(d) for d in devices]
+    ctxs = contexts if contexts is not None else [Context(d) for d in devices]
     try:
         ctxs[0].set_parser(parser)
         arr_ctx = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
@@ -713,5 +714,6 @@ def polish_files_multi(assembly, sams, devices, verbose=False, parser=0, **opts)
         L.pp_free(out)
         return data
     finally:
-        for c in ctxs:
-            c.close()
+        if contexts is None:
+            for c in ctxs:
+                c.close()

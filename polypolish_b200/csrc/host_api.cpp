@@ -5,7 +5,10 @@
 //   filter::filter            /root/reference/src/filter.rs:26-37   (+ :273-349 SAM re-streaming)
 // Text (FASTA/SAM) is handled here on the host; all per-alignment / per-position work is behind
 // pp_polish() / pp_filter() on the device.  There is no CPU fallback for that work.
+#include <chrono>
 #include <cmath>
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
@@ -200,6 +203,73 @@ struct HostCopy {
 
 // SAM files -> resident dataset through the device tokeniser (tok_kernels.cu).  PP_OK, PP_TOK_HOST (the host packer must
 // look at the text), or an error.  `log` collects the per-file lines add_to_pileup prints (alignment.rs:266-271).
+// Cuts a SAM file into n byte ranges for n GPUs: cut[0] = 0, cut[n] = size, every other cut is the start of a line whose QNAME differs from
+// the line before it (a read group - consecutive lines of one QNAME, alignment.rs:214-272 - is never split).  false: not a plain file,
+// or a line longer than the window (the caller lets one GPU read the whole file instead).
+static bool split_ranges(const char* path, int n, std::vector<uint64_t>& cut) {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { close(fd); return false; }
+    const uint64_t S = (uint64_t)sb.st_size;
+    cut.assign((size_t)n + 1, S);
+    cut[0] = 0;
+    const size_t W = 1 << 20;
+    std::vector<char> buf(W);
+    bool ok = true;
+    // the line starting at `pos` (a line start): its QNAME and where the next line starts
+    auto line_at = [&](uint64_t pos, std::string& qname, uint64_t& next) -> bool {
+        if (pos >= S) return false;
+        const size_t want = (size_t)std::min<uint64_t>(W, S - pos);
+        size_t got = 0;
+        while (got < want) {
+            const ssize_t r = pread(fd, buf.data() + got, want - got, (off_t)(pos + got));
+            if (r <= 0) { ok = false; return false; }
+            got += (size_t)r;
+        }
+        const char* nl = (const char*)memchr(buf.data(), '\n', got);
+        if (!nl && pos + got < S) { ok = false; return false; }                  // longer than the window
+        const size_t len = nl ? (size_t)(nl - buf.data()) : got;
+        const char* tab = (const char*)memchr(buf.data(), '\t', len);
+        qname.assign(buf.data(), tab ? (size_t)(tab - buf.data()) : len);
+        next = pos + len + 1;
+        return true;
+    };
+    for (int g = 1; g < n && ok; ++g) {
+        uint64_t pos = std::max<uint64_t>(S / (uint64_t)n * (uint64_t)g, cut[g - 1]);
+        if (pos >= S) { cut[g] = S; continue; }
+        // the first line start at or after pos
+        if (pos > 0) {
+            std::string q; uint64_t nx = 0;
+            if (!line_at(pos - 1, q, nx)) { if (!ok) break; cut[g] = S; continue; }       // (the rest of the line that holds byte pos - 1)
+            pos = std::min(nx, S);
+        }
+        // ... then on to the first line whose QNAME differs from its predecessor's
+        std::string qa, qb;
+        uint64_t na = 0, nb = 0;
+        if (!line_at(pos, qa, na)) { if (!ok) break; cut[g] = S; continue; }
+        uint64_t cand = std::min(na, S);
+        for (;;) {
+            if (cand >= S || !line_at(cand, qb, nb)) { cand = S; break; }
+            if (qb != qa || (!qb.empty() && qb[0] == '@')) break;
+            qa.swap(qb);
+            cand = std::min(nb, S);
+        }
+        if (!ok) break;
+        cut[g] = std::max(cand, cut[g - 1]);
+    }
+    close(fd);
+    return ok;
+}
+
+extern "C" int pp_sam_split_ranges(const char* path, int n, uint64_t* cuts) {
+    if (!path || n < 1 || !cuts) return PP_ERR_ARG;
+    std::vector<uint64_t> c;
+    if (!split_ranges(path, n, c)) return PP_ERR_IO;
+    std::copy(c.begin(), c.end(), cuts);
+    return PP_OK;
+}
+
 struct DeviceShard { const uint32_t* local_of; uint32_t n_total; pp_contigs contigs; bool takes_unknown; };
 static int tokenise_files(pp_ctx* ctx, const pp_fasta* fa, const char* const* sams, int n_sams, bool careful, std::string& log,
                           std::string& timing, uint64_t* n_aln, const DeviceShard* shard = nullptr) {
@@ -262,7 +332,7 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     struct FileCloser { FILE*& f; ~FileCloser() { if (f) fclose(f); } } closer{debug_file};
 
     // the first SAM file starts streaming into HBM while the assembly is loaded
-    if (n_sams > 0 && pp_get_parser(ctx) == 0) pp_tok_prefetch(ctx, sams[0]);
+    if (n_sams > 0 && pp_get_parser(ctx) == 0 && n_ctx == 1) pp_tok_prefetch(ctx, sams[0]);
     char ebuf[1024];
     pp_fasta* fa = pp_fasta_load(assembly, ebuf, sizeof ebuf);
     if (!fa) return pp_ctx_fail(ctx, PP_ERR_INPUT, ebuf);
@@ -276,7 +346,7 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
     }
 
     // one job per GPU; with one GPU the job is the whole assembly
-    const uint32_t n_shards = debug ? 1u : (uint32_t)std::max(1, std::min<int>(n_ctx, (int)contigs.n_contigs));   // the debug TSV is written from one GPU
+    uint32_t n_shards = debug ? 1u : (uint32_t)std::max(1, std::min<int>(n_ctx, (int)contigs.n_contigs));   // the debug TSV is written from one GPU
     std::vector<ShardJob> jobs;
     int rc = PP_OK;
     pp_alignments alns;
@@ -322,9 +392,8 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
             resident = n_shards == 1;
             alns.n_aln = fuse.n_aln;
         } else if (pass == 0 && n_shards > 1) {
-            // Several GPUs, no host in the middle: every GPU streams the text in over its own PCIe link and tokenises it itself; a
-            // contig -> shard map (longest contig first onto the lightest shard) tells it which records are its own, the rest become
-            // ghost records on the device (pp_tok_set_shard).  Nothing is read back, nothing is sharded on the host.
+            // Several GPUs, no host in the middle: the host only decides which contig goes where (longest contig first onto the lightest
+            // shard) and where to cut the files; the text, the records and the shards never pass through host memory as arrays.
             std::vector<uint32_t> order(contigs.n_contigs), owner(contigs.n_contigs);
             for (uint32_t i = 0; i < contigs.n_contigs; ++i) order[i] = i;
             std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return contigs.off[x + 1] - contigs.off[x] > contigs.off[y + 1] - contigs.off[y]; });
@@ -350,28 +419,78 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
                 j.contig_map = j.own_map.data();
                 j.resident = true;
             }
+            // every GPU reads ITS byte range of every file (cut between read groups), tokenises it, and the read groups are exchanged
+            // between the GPUs (tok_kernels.cu pp_tok_exchange_finish): 1/N of the text per PCIe link
+            std::vector<std::vector<uint64_t>> cuts((size_t)n_sams);
+            bool ranges_ok = n_sams > 0;
+            for (int i = 0; i < n_sams && ranges_ok; ++i) { ranges_ok = split_ranges(sams[i], (int)n_shards, cuts[(size_t)i]); }
+            if (!ranges_ok) continue;
             std::vector<int> trc(n_shards, PP_OK);
-            std::vector<std::string> tlog(n_shards), ttime(n_shards);
-            std::vector<uint64_t> tn(n_shards, 0);
-            auto work = [&](uint32_t s) {
-                const DeviceShard ds{jobs[s].own_local.data(), contigs.n_contigs, jobs[s].contigs, s == 0};
-                trc[s] = tokenise_files(ctxs[s], fa, sams, n_sams, prm->careful != 0, tlog[s], ttime[s], &tn[s], &ds);
-                if (trc[s] != PP_OK && trc[s] != PP_TOK_HOST) jobs[s].err = pp_last_error(ctxs[s]);
-            };
-            {
+            std::vector<std::vector<pp_tok_stats>> tst(n_shards, std::vector<pp_tok_stats>((size_t)n_sams));
+            int bits = 4;
+            bool host = false;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                auto work = [&](uint32_t s) {
+                    pp_ctx* c = ctxs[s];
+                    std::vector<uint64_t> off((size_t)n_sams), len((size_t)n_sams);
+                    uint64_t mine = 0;
+                    for (int i = 0; i < n_sams; ++i) { off[(size_t)i] = cuts[(size_t)i][s]; len[(size_t)i] = cuts[(size_t)i][s + 1] - cuts[(size_t)i][s]; mine += len[(size_t)i]; }
+                    int r = pp_tok_begin(c, fa, prm->careful ? 1 : 0, bits);
+                    if (r == PP_OK) r = pp_tok_expect(c, mine);
+                    if (r == PP_OK) r = pp_tok_set_ranges(c, off.data(), len.data(), n_sams);
+                    if (r == PP_OK) r = pp_tok_add_files(c, sams, n_sams, tst[s].data());
+                    trc[s] = r;
+                    if (r != PP_OK && r != PP_TOK_HOST && r != PP_TOK_NEED8) jobs[s].err = pp_last_error(c);
+                };
                 std::vector<std::thread> tt;
                 for (uint32_t s = 1; s < n_shards; ++s) tt.emplace_back(work, s);
                 work(0);
                 for (auto& t : tt) t.join();
+                bool need8 = false;
+                host = false;
+                for (uint32_t s = 0; s < n_shards; ++s) { need8 |= trc[s] == PP_TOK_NEED8; host |= trc[s] == PP_TOK_HOST; }
+                if (need8 && bits == 4 && !host) { bits = 8; continue; }
+                host |= need8;
+                break;
             }
-            bool host = false;
-            for (uint32_t s = 0; s < n_shards; ++s) host |= trc[s] == PP_TOK_HOST;
             if (host) continue;
             for (uint32_t s = 0; s < n_shards; ++s)
                 if (trc[s] != PP_OK) { rc = pp_ctx_fail(ctx, trc[s], jobs[s].err.c_str()); pp_fasta_free(fa); return rc; }
-            log = tlog[0];
-            for (uint32_t s = 0; s < n_shards; ++s) { tok_timing += ttime[s]; jobs[s].alns.n_aln = tn[s]; }
-            alns.n_aln = tn[0];
+            bool empty_file = false;
+            for (int i = 0; i < n_sams; ++i) {
+                uint64_t na = 0, nr = 0, nl = 0;
+                float h2d = 0, dev = 0;
+                for (uint32_t s = 0; s < n_shards; ++s) {
+                    const pp_tok_stats& t = tst[s][(size_t)i];
+                    na += t.alignments; nr += t.reads; nl += t.lines; h2d = std::max(h2d, t.h2d_ms); dev = std::max(dev, t.device_ms);
+                }
+                empty_file |= na == 0;                                         // "no alignments in <file>" (alignment.rs:268-270): the host path words it
+                log += std::string(sams[i]) + ": " + fmt_thousands(na) + " alignments from " + fmt_thousands(nr) + " reads\n";
+                char tmp[256];
+                snprintf(tmp, sizeof tmp, "SAM tokeniser %s: %s lines in %u byte ranges, text to HBM %.3f ms, kernels %.3f ms (slowest GPU)\n", sams[i],
+                         fmt_thousands(nl).c_str(), n_shards, h2d, dev);
+                tok_timing += tmp;
+            }
+            if (empty_file) continue;
+            {
+                std::vector<const uint32_t*> lo(n_shards);
+                std::vector<pp_contigs> sc(n_shards);
+                for (uint32_t s = 0; s < n_shards; ++s) { lo[s] = jobs[s].own_local.data(); sc[s] = jobs[s].contigs; }
+                uint64_t n_all = 0;
+                const auto t0 = std::chrono::steady_clock::now();
+                rc = pp_tok_exchange_finish(ctxs, (int)n_shards, owner.data(), contigs.n_contigs, lo.data(), sc.data(), &n_all);
+                if (rc == PP_TOK_HOST) continue;
+                if (rc != PP_OK) { pp_fasta_free(fa); return rc; }
+                char tmp[160];
+                snprintf(tmp, sizeof tmp, "read groups exchanged between %u GPUs and binned: %.3f ms\n", n_shards,
+                         std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count());
+                tok_timing += tmp;
+                alns.n_aln = n_all;
+                for (uint32_t s = 0; s < n_shards; ++s) {
+                    pp_alignments v;
+                    if (pp_dataset_sizes(ctxs[s], &v) == PP_OK) jobs[s].alns.n_aln = v.n_aln;
+                }
+            }
             device_shards = true;
         } else if (pass == 0) {
             uint64_t n_aln = 0;
@@ -421,6 +540,15 @@ static int polish_files_impl(pp_ctx* const* ctxs, int n_ctx, const char* assembl
             tok_timing.clear();
             if (ff) { need_host_filter = true; break; }
             continue;
+        }
+        if (data_error && n_shards > 1) {
+            // the message names the read / reference of the offending line (alignment.rs:190-198,298-300): its index in the unsharded
+            // arrays is what the packer can look up, so the failing job runs once more as one shard
+            pp_shards_free(shards); shards = nullptr;
+            n_shards = 1;
+            jobs.assign(1, ShardJob());
+            jobs[0].ctx = ctx; jobs[0].contigs = contigs; jobs[0].alns = alns; jobs[0].resident = false;
+            run_shard(&jobs[0], prm);
         }
         if (verbose) fputs(log.c_str(), stderr);
         break;

@@ -67,7 +67,7 @@ struct DevStatus {
     unsigned int ticket;             // next tile (k_tile's dynamic schedule)
     unsigned int pad0, pad1;
 #ifdef PP_TILE_PROF
-    unsigned long long prof[8];      // cycles of thread 0 per phase (A, B, queue, C, D+E), queued reads, tiles, largest queue
+    unsigned long long prof[12];     // cycles of thread 0 per phase (A, B, queue, C, D+E), queued reads, tiles, largest queue, depth-walk cycles, walks, tiles with a walk
 #endif
 };
 
@@ -980,6 +980,18 @@ __device__ __forceinline__ uint32_t fast_walk(TileCtx<4>& S, const TileRec& r, u
     return nkept;
 }
 
+// Everything that is not the plain fast walk (queued reads, the long list, a queue that overflowed): the two-segment fast walk for
+// one-indel reads, else the general walk.  (Inlined on purpose: as an out-of-line function - half the code size - the calls cost
+// the hot loop its registers, k_tile 0.53 -> 0.75 ms.)
+template <int BITS>
+__device__ __forceinline__ uint32_t slow_walk(const DevData* d, TileShared* sh, uint32_t P0, TileRec r, uint32_t slot, uint32_t k) {
+    TileCtx<BITS> S{*d, *sh, P0};
+    uint32_t nk = NONE32;
+    if (BITS == 4 && (r.flags & TR_FAST1)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), r, slot, k);
+    if (nk == NONE32) nk = general_walk<BITS>(S, r, k);
+    return nk;
+}
+
 // The record of sorted slot i (coalesced: consecutive lanes, consecutive 32-byte records).
 __device__ __forceinline__ TileRec load_srec(const DevData& d, uint32_t slot) {
     const uint4* src = reinterpret_cast<const uint4*>(d.srec + slot);
@@ -1196,6 +1208,18 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
         long long pt[6];
         pt[0] = clock64();
 #endif
+        // The slots of the tile's bins and of the `lb` bins before it - one contiguous range of the binned dataset - and the first two
+        // chunks' records: a chain of four dependent trips to memory (bin bounds, record, its k word, ...) that now runs under phase A.
+        const uint32_t b0 = P0 >> PP_BIN_SHIFT;
+        const uint32_t lo = d.bin_start[b0 >= lb ? b0 - lb : 0u];
+        const uint32_t hi = d.bin_start[min(b0 + (uint32_t)(TL_T / PP_BIN), d.n_bins)];
+        const uint32_t stride = 32u * (TL_THREADS / 32);
+        uint32_t c_a = lo + 32u * warp;
+        TileRec rec_a, rec_b;
+        uint32_t k_a = 0;
+        rec_a = load_srec(d, min(c_a + lane, d.n_slots ? d.n_slots - 1 : 0u));
+        rec_b = load_srec(d, min(c_a + stride + lane, d.n_slots ? d.n_slots - 1 : 0u));
+        if (BITS == 4 && c_a + lane < hi) PP_PREFETCH_L2(reinterpret_cast<const uint8_t*>(d.sseq + (size_t)(c_a + lane) * TL_SEQ_QUADS));
         // ---- phase A: clear the counters, stage the draft as 4-bit codes
         {
             uint4* z = reinterpret_cast<uint4*>(sh.cdiff);
@@ -1218,6 +1242,7 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 }
             }
         }
+        if (c_a + lane < hi) k_a = d.kf[rec_a.aln];            // (the record has arrived while the counters were cleared)
         __syncthreads();
 #ifdef PP_TILE_PROF
         pt[1] = clock64();
@@ -1225,20 +1250,10 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
         // ---- phase B: every alignment that can touch the tile: the slots of the tile's bins and of the `lb` bins before it - one
         // contiguous range of the binned dataset.  Warps take chunks of 32 consecutive slots round robin: records and bases stream
         // in coalesced; the only gather is the 4-byte "k / contributes" word of the current options, fetched one chunk ahead.
-        const uint32_t b0 = P0 >> PP_BIN_SHIFT;
-        const uint32_t lo = d.bin_start[b0 >= lb ? b0 - lb : 0u];
-        const uint32_t hi = d.bin_start[min(b0 + (uint32_t)(TL_T / PP_BIN), d.n_bins)];
         {
             // reads that need more than the plain fast walk (one indel: the two-segment fast walk; more indels, long reads,
-            // homopolymer tails: the general walk) go to a block-wide queue and are taken on consecutive lanes after the chunk
+            // homopolymer tails: the general walk) go to a block-wide queue and are dealt to the warps after the chunk
             // loop, which therefore runs the same straight-line code on every lane
-            const uint32_t stride = 32u * (TL_THREADS / 32);
-            uint32_t c_a = lo + 32u * warp;
-            TileRec rec_a, rec_b;
-            uint32_t k_a = 0;
-            rec_a = load_srec(d, min(c_a + lane, d.n_slots ? d.n_slots - 1 : 0u));
-            if (c_a + lane < hi) k_a = d.kf[rec_a.aln];
-            rec_b = load_srec(d, min(c_a + stride + lane, d.n_slots ? d.n_slots - 1 : 0u));
             while (c_a < hi) {
                 const uint32_t c_b = c_a + stride, c_c = c_b + stride;
                 // next chunk: its k word (the record arrived during the previous round); the chunk after: its records
@@ -1266,12 +1281,8 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                         sh.queue[qi] = i;
                         PP_PREFETCH_L2(d.cigar_ops + rec_a.cigar_off);                  // what the general walk will chase
                         PP_PREFETCH_L2(d.seq_pool + (size_t)rec_a.seq_off * (BITS == 4 ? 16 : 32));
-                    } else {                                                           // (a tile with more than TL_QCAP such reads)
-                        uint32_t nk = NONE32;
-                        if (BITS == 4 && (rec_a.flags & TR_FAST1)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), rec_a, i, k_a);
-                        if (nk == NONE32) nk = general_walk<BITS>(S, rec_a, k_a);
-                        d.wrec[i] = make_uint4(rec_a.aln, rec_a.gstart, nk, k_a);
-                    }
+                    } else                                                             // (a tile with more than TL_QCAP such reads)
+                        d.wrec[i] = make_uint4(rec_a.aln, rec_a.gstart, slow_walk<BITS>(&d, &sh, P0, rec_a, i, k_a), k_a);
                 }
                 c_a = c_b; rec_a = rec_b; rec_b = rec_c; k_a = k_b;
             }
@@ -1289,17 +1300,14 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 const uint32_t i = sh.queue[qi];
                 const TileRec r = load_srec(d, i);
                 const uint32_t k = d.kf[r.aln];
-                uint32_t nk = NONE32;
-                if (BITS == 4 && (r.flags & TR_FAST1)) nk = fast_walk(reinterpret_cast<TileCtx<4>&>(S), r, i, k);   // one indel: two segments
-                if (nk == NONE32) nk = general_walk<BITS>(S, r, k);
-                d.wrec[i] = make_uint4(r.aln, r.gstart, nk, k);
+                d.wrec[i] = make_uint4(r.aln, r.gstart, slow_walk<BITS>(&d, &sh, P0, r, i, k), k);
             }
             // the long list: alignments of more than TL_LONG_E entries, looked at by every tile
             for (uint32_t i = long_lo + tid; i < long_hi; i += TL_THREADS) {
                 const TileRec r = load_srec(d, i);
                 const unsigned long long e_end = (unsigned long long)r.gstart + r.E;
                 const uint32_t k = d.kf[r.aln];
-                if (k != 0 && e_end > P0 && r.gstart < P0 + (uint32_t)TL_T) d.wrec[i] = make_uint4(r.aln, r.gstart, general_walk<BITS>(S, r, k), k);
+                if (k != 0 && e_end > P0 && r.gstart < P0 + (uint32_t)TL_T) d.wrec[i] = make_uint4(r.aln, r.gstart, slow_walk<BITS>(&d, &sh, P0, r, i, k), k);
             }
         }
         __syncwarp();          // lanes that had a queued read rejoin their warp here: without it the warp may run phase C in two groups
@@ -1329,7 +1337,14 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
 #endif
         // ---- phase D: ordered depth where a sub-tile sees k != 1.  Warp w owns sub-tile w here AND in the vote below, so there is
         // no block-wide barrier in between: warps of unflagged sub-tiles go straight on.
+#ifdef PP_TILE_PROF
+        const long long dw0 = clock64();
+#endif
         if ((sh.subflags >> warp) & 1u) depth_walk<BITS>(d, sh, sh.wstage[warp], P0, warp, lb, long_lo, long_hi);
+#ifdef PP_TILE_PROF
+        if (lane == 0 && ((sh.subflags >> warp) & 1u)) { atomicAdd(&d.st->prof[8], (unsigned long long)(clock64() - dw0)); atomicAdd(&d.st->prof[9], 1ull); }
+        if (tid == 0 && sh.subflags) atomicAdd(&d.st->prof[10], 1ull);
+#endif
         __syncwarp();
         // ---- phase E: the vote, straight out of shared memory
         const uint32_t p0 = P0 + rel0;

@@ -248,6 +248,7 @@ struct TokState {
         int rc = PP_OK;                   // PP_OK, PP_ERR_IO, PP_ERR_CUDA
         int cuda_err = 0;
         float ms = 0;
+        uint64_t off = 0;                 // first byte of the file that is sent (pp_tok_set_ranges)
         bool strip = false;               // uploaded with QUAL replaced by "*" (polish only: filter reproduces lines verbatim)
         uint64_t sent = 0;                // bytes that crossed PCIe
     } pf;
@@ -255,6 +256,12 @@ struct TokState {
     uint8_t* h_nl = nullptr;              // pinned '\n'
     DevBuf cub;
     TokFilterBufs* fbufs = nullptr;   // device buffers of the filter text path
+    // pp_tok_set_ranges: this context tokenises one byte range of every file (multi-GPU ingestion); marks[f] = the dataset's
+    // (alignments, ops, sequence blocks, reads) when file f started, marks.back() = now
+    bool ranges_on = false;
+    std::vector<uint64_t> range_off, range_len;
+    struct Mark { uint64_t aln, ops, blk, reads; };
+    std::vector<Mark> marks;
     // pp_tok_set_shard: this context keeps one shard of the assembly
     bool shard_on = false, shard_unknown = false;
     DevBuf shard_map;                 // local_of[c] on the device
@@ -346,6 +353,22 @@ extern "C" int pp_tok_begin(pp_ctx* ctx, const pp_fasta* fa, int careful, int se
     T->expect_total = 0;
     T->active = true;
     T->shard_on = false;
+    T->ranges_on = false;
+    T->marks.clear();
+    return PP_OK;
+}
+
+// Optional, after pp_tok_begin: the i-th path of pp_tok_add_files contributes only bytes [off[i], off[i] + len[i]) - a range that
+// starts at a line start and ends behind a line end, cut between two read groups (the caller's job: host_api.cpp split_ranges).
+// A range without alignments is fine (the file as a whole is the caller's to check).
+extern "C" int pp_tok_set_ranges(pp_ctx* ctx, const uint64_t* off, const uint64_t* len, int n) {
+    if (!ctx) return PP_ERR_ARG;
+    TokState* T = ctx->tok;
+    if (!T || !T->active) return ctx->fail(PP_ERR_ARG, "pp_tok_set_ranges: no pp_tok_begin");
+    if (n < 0 || (n && (!off || !len))) return ctx->fail(PP_ERR_ARG, "pp_tok_set_ranges: null ranges");
+    T->range_off.assign(off, off + n);
+    T->range_len.assign(len, len + n);
+    T->ranges_on = true;
     return PP_OK;
 }
 
@@ -383,7 +406,7 @@ extern "C" int pp_tok_set_shard(pp_ctx* ctx, const uint32_t* local_of, uint32_t 
 }
 
 // The text is on the device (n bytes, zero padded).  Appends its alignments to the dataset under construction.
-static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n, bool unterminated, pp_tok_stats* stats) {
+static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n, bool unterminated, pp_tok_stats* stats, bool part_of_file = false) {
     cudaStream_t s = ctx->stream;
     uint32_t launches = 0;
     CK(cudaEventRecord(ctx->ev[0], s));
@@ -408,7 +431,7 @@ static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n
         n_lines = T->h_tot[0] + (unterminated ? 1 : 0);
     }
     if (stats) stats->lines = n_lines;
-    if (n_lines == 0) return PP_TOK_HOST;                    // "no alignments in <file>": the host packer words it
+    if (n_lines == 0) return part_of_file ? PP_OK : PP_TOK_HOST;   // "no alignments in <file>": the host packer words it (a byte range may be empty)
     if (n_lines >= 0xFFFFFFF0ull) return PP_TOK_HOST;
 
     // scratch: line starts | line records | three scan arrays
@@ -443,7 +466,7 @@ static int tok_process(pp_ctx* ctx, TokState* T, const uint8_t* text, uint64_t n
     const uint64_t n_al = T->h_tot[0], n_ops = T->h_tot[1], n_blk = T->h_tot[2];
     if (stats) stats->alignments = n_al;
     if (T->h_st->first_bad != ~0ull) return PP_TOK_HOST;
-    if (n_al == 0) return PP_TOK_HOST;                       // alignment.rs:268-270
+    if (n_al == 0) return part_of_file ? PP_OK : PP_TOK_HOST;      // alignment.rs:268-270
     if (T->aln_base + n_al >= 0xFFFFFFFFull - 4096 || T->ops_base + n_ops > 0xFFFFFFFFull || T->blk_base + n_blk > 0xFFFFFFFFull) return PP_TOK_HOST;
 
     // ---- dataset arrays (kept across files)
@@ -544,7 +567,7 @@ extern "C" int pp_tok_add_text(pp_ctx* ctx, const char* text, size_t len, pp_tok
 // Streams a file into dst: T->readers host threads, each pread()s its slices into its two pinned slots and sends them on
 // its own stream, so that page-cache reads, pinned staging and PCIe overlap.  Runs on the caller's thread or on the
 // prefetch thread; touches neither ctx->err nor ctx->stream.  Returns PP_OK / PP_ERR_IO / PP_ERR_CUDA (+ *cuda_err).
-static int upload_file(int device, TokState* T, uint8_t* dst, int fd, uint64_t n, uint8_t* last_byte, int* cuda_err) {
+static int upload_file(int device, TokState* T, uint8_t* dst, int fd, uint64_t n, uint8_t* last_byte, int* cuda_err, uint64_t foff = 0) {
     const int R = T->readers;
     const uint64_t n_slices = (n + TK_SLOT - 1) / TK_SLOT;
     std::atomic<int> err{0};           // 1 = read error, 2 = CUDA error
@@ -561,7 +584,7 @@ static int upload_file(int device, TokState* T, uint8_t* dst, int fd, uint64_t n
             const uint64_t o = sl * TK_SLOT, len = std::min<uint64_t>(TK_SLOT, n - o);
             uint64_t got = 0;
             while (got < len) {
-                const ssize_t g = pread(fd, T->pin[r][slot] + got, (size_t)(len - got), (off_t)(o + got));
+                const ssize_t g = pread(fd, T->pin[r][slot] + got, (size_t)(len - got), (off_t)(foff + o + got));
                 if (g <= 0) { err = 1; return; }
                 got += (uint64_t)g;
             }
@@ -680,7 +703,7 @@ static int ring_ready(pp_ctx* ctx, TokState* T) {
 
 // Starts streaming `path` into the next text buffer on a background thread.  PP_OK, PP_TOK_HOST (not a plain readable
 // file) or an error.
-static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path, bool strip) {
+static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path, bool strip, int range = -1) {
     struct stat sb;
     if (stat(path, &sb) != 0 || !S_ISREG(sb.st_mode)) return PP_TOK_HOST;   // pipes, devices: never opened here (the host path streams them once)
     const int fd = open(path, O_RDONLY);
@@ -688,7 +711,12 @@ static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path, bool strip
         if (fd >= 0) close(fd);
         return PP_TOK_HOST;
     }
-    const uint64_t n = (uint64_t)sb.st_size;
+    uint64_t n = (uint64_t)sb.st_size, foff = 0;
+    if (range >= 0) {
+        if ((size_t)range >= T->range_off.size() || T->range_off[range] + T->range_len[range] > n) { close(fd); return PP_TOK_HOST; }
+        foff = T->range_off[range]; n = T->range_len[range];
+        strip = false;                                           // (the stripping upload works on whole files)
+    }
     const int buf = T->next_buf;
     int rc = ring_ready(ctx, T);
     if (rc != PP_OK) { close(fd); return rc; }
@@ -707,17 +735,17 @@ static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path, bool strip
     T->next_buf ^= 1;
     TokState::Prefetch& pf = T->pf;
     pf.active = true; pf.path = path; pf.buf = buf; pf.n = n; pf.last = '\n'; pf.rc = PP_OK; pf.cuda_err = 0; pf.ms = 0;
-    pf.strip = strip && T->strip_qual; pf.sent = 0;
+    pf.strip = strip && T->strip_qual; pf.sent = 0; pf.off = foff;
     uint8_t* dst = T->text[buf].as<uint8_t>();
     const int device = ctx->device;
-    pf.th = std::thread([T, dst, fd, n, device] {
+    pf.th = std::thread([T, dst, fd, n, device, foff] {
         TokState::Prefetch& q = T->pf;
         const auto t0 = std::chrono::steady_clock::now();
         if (n && q.strip) {
             q.rc = upload_file_stripped(device, T, dst, fd, n, &q.last, &q.cuda_err, &q.sent);
             if (q.rc == PP_UPLOAD_LONG_LINE) q.strip = false;
         }
-        if (n && !q.strip) { q.rc = upload_file(device, T, dst, fd, n, &q.last, &q.cuda_err); q.sent = n; }
+        if (n && !q.strip) { q.rc = upload_file(device, T, dst, fd, n, &q.last, &q.cuda_err, foff); q.sent = n; }
         close(fd);
         q.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     });
@@ -725,14 +753,15 @@ static int prefetch_start(pp_ctx* ctx, TokState* T, const char* path, bool strip
 }
 
 // Waits for the text of `path` (starting its upload now if nobody asked for it before).
-static int prefetch_wait(pp_ctx* ctx, TokState* T, const char* path, bool strip) {
+static int prefetch_wait(pp_ctx* ctx, TokState* T, const char* path, bool strip, int range = -1) {
     TokState::Prefetch& pf = T->pf;
-    if (pf.active && (pf.path != path || (pf.strip && !strip))) {   // (text without QUAL is no use to `filter`)                       // something else was prefetched: let it finish, drop it
+    const bool other_range = range >= 0 && (size_t)range < T->range_off.size() && (pf.off != T->range_off[range] || pf.n != T->range_len[range]);
+    if (pf.active && (pf.path != path || (pf.strip && !strip) || other_range || (range < 0 && pf.off != 0))) {   // (text without QUAL is no use to `filter`)                       // something else was prefetched: let it finish, drop it
         if (pf.th.joinable()) pf.th.join();
         pf.active = false;
     }
     if (!pf.active) {
-        const int rc = prefetch_start(ctx, T, path, strip);
+        const int rc = prefetch_start(ctx, T, path, strip, range);
         if (rc != PP_OK) return rc;
     }
     if (pf.th.joinable()) pf.th.join();
@@ -769,9 +798,12 @@ extern "C" int pp_tok_add_files(pp_ctx* ctx, const char* const* paths, int n_pat
     if (!paths || n_paths < 0) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: null paths");
     CK(cudaSetDevice(ctx->device));
     if (stats) memset(stats, 0, sizeof(pp_tok_stats) * (size_t)n_paths);
+    if (T->ranges_on && T->range_off.size() != (size_t)n_paths) return ctx->fail(PP_ERR_ARG, "pp_tok_add_files: as many paths as pp_tok_set_ranges ranges");
+    const bool ranges = T->ranges_on;
     for (int i = 0; i < n_paths; ++i) {
         if (!paths[i]) return ctx->fail(PP_ERR_ARG, "pp_tok_add_file: null path");
-        int rc = prefetch_wait(ctx, T, paths[i], true);
+        T->marks.push_back({T->aln_base, T->ops_base, T->blk_base, T->read_base});
+        int rc = prefetch_wait(ctx, T, paths[i], true, ranges ? i : -1);
         if (rc != PP_OK) { T->active = false; return rc; }
         const int buf = T->pf.buf;
         const uint64_t n = T->pf.n;
@@ -779,13 +811,14 @@ extern "C" int pp_tok_add_files(pp_ctx* ctx, const char* const* paths, int n_pat
         const float h2d = T->pf.ms;
         const uint64_t h2d_bytes = T->pf.sent;
         if (i + 1 < n_paths && paths[i + 1]) {                 // the next file streams in while this one is tokenised
-            rc = prefetch_start(ctx, T, paths[i + 1], true);
+            rc = prefetch_start(ctx, T, paths[i + 1], true, ranges ? i + 1 : -1);
             if (rc < 0) { T->active = false; return rc; }
         }
-        rc = tok_process(ctx, T, T->text[buf].as<uint8_t>(), n, unterminated, stats ? stats + i : nullptr);
+        rc = tok_process(ctx, T, T->text[buf].as<uint8_t>(), n, unterminated, stats ? stats + i : nullptr, ranges);
         if (stats) { stats[i].h2d_ms = h2d; stats[i].h2d_bytes = h2d_bytes; }
         if (rc != PP_OK) { T->active = false; return rc; }
     }
+    T->marks.push_back({T->aln_base, T->ops_base, T->blk_base, T->read_base});
     return PP_OK;
 }
 
@@ -841,6 +874,284 @@ extern "C" int pp_tok_finish(pp_ctx* ctx) {
         std::vector<uint8_t>().swap(T->shard_bases);
     }
     return pp_ctx_commit_dataset(ctx, T->aln_base, T->read_base, T->ops_base, T->blk_base * (T->seq_bits == 4 ? 16 : 32), (uint32_t)T->seq_bits);
+}
+
+// =====================================================================================================================
+// Multi-GPU ingestion without the host in the middle (SURVEY.md §8e at file level).  Every context has tokenised ITS byte range of
+// every SAM file (pp_tok_set_ranges; the ranges are cut between read groups).  pp_tok_exchange_finish then gives every GPU its
+// shard: a read group goes - whole, so that k still spans contigs - to every GPU that owns a contig one of its records lies on.
+// Per source GPU g and destination o: a bit mask per group (k_x_touch), four exclusive scans over the kept records (records, CIGAR
+// ops, sequence blocks, groups), a compaction into staging arrays with every offset already renumbered for its place in o's
+// dataset (k_x_pack*), and device-to-device copies (cudaMemcpyPeerAsync, NVLink where the box has it) into o's arrays at
+// [file f][range g] - global SAM order is (file, range, line), which is what the ordered depth needs.  The host only adds up
+// the piece sizes.  Then pp_tok_set_shard / pp_tok_finish on every GPU: foreign records become ghosts, the shard is binned.
+// =====================================================================================================================
+#define X_MAX_FILES 64
+struct XPlan {                       // per (source, destination): where the pieces of each file go
+    uint32_t n_files;
+    uint32_t mark_aln[X_MAX_FILES + 1];                                   // first local record of file f
+    uint32_t dst_aln[X_MAX_FILES], dst_ops[X_MAX_FILES], dst_blk[X_MAX_FILES], dst_grp[X_MAX_FILES];   // position in the destination's dataset
+};
+
+__global__ void k_x_touch(const uint32_t* __restrict__ contig, const uint32_t* __restrict__ read_id, uint64_t n, const uint32_t* __restrict__ owner,
+                          uint32_t n_total, uint32_t read0, uint32_t* __restrict__ touch) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = contig[i];
+        const uint32_t o = (c == PP_CONTIG_UNKNOWN || c >= n_total) ? 0u : owner[c];      // unknown RNAMEs stay with shard 0 (shard.cpp)
+        atomicOr(&touch[read_id[i] - read0], 1u << o);
+    }
+}
+
+// kept record -> (1, its ops, its own sequence blocks, 1 if it starts a group); element n is the scans' total slot
+__global__ void k_x_flags(const uint32_t* __restrict__ read_id, const uint16_t* __restrict__ n_cigar, const uint16_t* __restrict__ seq_len,
+                          const uint8_t* __restrict__ flags, uint64_t n, uint32_t read0, const uint32_t* __restrict__ touch, uint32_t dest,
+                          uint32_t* __restrict__ f_rec, uint32_t* __restrict__ f_ops, uint32_t* __restrict__ f_blk, uint32_t* __restrict__ f_grp) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t r = 0, o = 0, b = 0, g = 0;
+        if (i < n && ((touch[read_id[i] - read0] >> dest) & 1u)) {
+            r = 1; o = n_cigar[i];
+            if (!(flags[i] & (PP_FLAG_SEQSTAR | PP_FLAG_NOSEQ))) b = ((uint32_t)seq_len[i] + PP_SEQ_BLOCK - 1) / PP_SEQ_BLOCK;
+            g = (i == 0 || read_id[i] != read_id[i - 1]) ? 1u : 0u;
+        }
+        f_rec[i] = r; f_ops[i] = o; f_blk[i] = b; f_grp[i] = g;
+    }
+}
+
+__global__ void k_x_marks(const uint32_t* __restrict__ s_rec, const uint32_t* __restrict__ s_ops, const uint32_t* __restrict__ s_blk,
+                          const uint32_t* __restrict__ s_grp, XPlan plan, uint32_t* __restrict__ out) {
+    const uint32_t f = threadIdx.x;
+    if (f <= plan.n_files) {
+        const uint32_t i = plan.mark_aln[f];
+        out[4 * f + 0] = s_rec[i]; out[4 * f + 1] = s_ops[i]; out[4 * f + 2] = s_blk[i]; out[4 * f + 3] = s_grp[i];
+    }
+}
+
+struct XArrays {
+    const uint32_t *contig, *ref_start, *read_id, *seq_off, *cigar_off, *nm, *cigar_ops;
+    const uint16_t *seq_len, *n_cigar;
+    const uint8_t *flags, *seq_pool;
+};
+struct XStage {
+    uint32_t *contig, *ref_start, *read_id, *seq_off, *cigar_off, *nm, *cigar_ops;
+    uint16_t *seq_len, *n_cigar;
+    uint8_t *flags, *seq_pool;
+};
+
+// records that own their sequence: where its first block goes (indexed by the OLD block offset, local to this source)
+__global__ void k_x_blockmap(XArrays a, uint64_t n, uint32_t blk0, const uint32_t* __restrict__ s_rec_flag, const uint32_t* __restrict__ s_rec,
+                             const uint32_t* __restrict__ s_blk, uint32_t* __restrict__ blockmap) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (s_rec[i + 1] == s_rec[i]) continue;                                        // not kept
+        if (a.flags[i] & (PP_FLAG_SEQSTAR | PP_FLAG_NOSEQ)) continue;
+        blockmap[a.seq_off[i] - blk0] = s_blk[i];
+    }
+}
+
+__global__ void k_x_pack(XArrays a, XStage st, uint64_t n, uint32_t blk0, uint32_t blk_bytes, XPlan plan, const uint32_t* __restrict__ s_rec,
+                         const uint32_t* __restrict__ s_ops, const uint32_t* __restrict__ s_blk, const uint32_t* __restrict__ s_grp,
+                         const uint32_t* __restrict__ blockmap, const uint32_t* __restrict__ marks /* scans at the file starts */) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t j = s_rec[i];
+        if (s_rec[i + 1] == j) continue;                                               // not kept
+        uint32_t f = 0;
+        while (f + 1 < plan.n_files && i >= plan.mark_aln[f + 1]) ++f;
+        const uint32_t m_ops = marks[4 * f + 1], m_blk = marks[4 * f + 2], m_grp = marks[4 * f + 3];
+        const uint8_t fl = a.flags[i];
+        const bool starts = (i == 0 || a.read_id[i] != a.read_id[i - 1]);
+        st.contig[j] = a.contig[i]; st.ref_start[j] = a.ref_start[i]; st.nm[j] = a.nm[i];
+        st.seq_len[j] = a.seq_len[i]; st.n_cigar[j] = a.n_cigar[i]; st.flags[j] = fl;
+        st.read_id[j] = plan.dst_grp[f] + (s_grp[i] + (starts ? 1u : 0u) - 1u - m_grp);
+        st.cigar_off[j] = plan.dst_ops[f] + (s_ops[i] - m_ops);
+        uint32_t so = 0;
+        if (!(fl & PP_FLAG_NOSEQ)) so = plan.dst_blk[f] + (blockmap[a.seq_off[i] - blk0] - m_blk);
+        st.seq_off[j] = so;
+        const uint32_t nc = a.n_cigar[i], co = a.cigar_off[i];
+        for (uint32_t t = 0; t < nc; ++t) st.cigar_ops[s_ops[i] + t] = a.cigar_ops[co + t];
+    }
+}
+
+// the sequence blocks of kept owners, 16 bytes per thread
+__global__ void k_x_pack_seq(XArrays a, XStage st, uint64_t n, uint32_t blk_bytes, const uint32_t* __restrict__ s_rec, const uint32_t* __restrict__ s_blk) {
+    const uint32_t per = blk_bytes / 16;
+    for (uint64_t i = blockIdx.x * (uint64_t)(blockDim.x / 8) + threadIdx.x / 8; i < n; i += (uint64_t)gridDim.x * (blockDim.x / 8)) {
+        if (s_rec[i + 1] == s_rec[i]) continue;
+        const uint32_t nb = s_blk[i + 1] - s_blk[i];                                   // 0 for records without their own sequence
+        if (!nb) continue;
+        const uint4* src = reinterpret_cast<const uint4*>(a.seq_pool + (size_t)a.seq_off[i] * blk_bytes);
+        uint4* dst = reinterpret_cast<uint4*>(st.seq_pool + (size_t)s_blk[i] * blk_bytes);
+        for (uint32_t q = threadIdx.x & 7; q < nb * per; q += 8) dst[q] = src[q];
+    }
+}
+
+namespace {
+struct XSource {                     // one context's tokenised ranges, moved out of the dataset buffers
+    DevBuf b[11];                    // B_CONTIG .. B_SEQPOOL, in the enum's order
+    DevBuf stage[11], touch, fl[4], sc[4], blockmap, marks, cubtmp;
+    uint64_t n = 0, ops = 0, blk = 0, reads = 0;
+    std::vector<TokState::Mark> mk;
+    void release() { for (auto& x : b) x.release(); for (auto& x : stage) x.release(); touch.release(); for (auto& x : fl) x.release();
+                     for (auto& x : sc) x.release(); blockmap.release(); marks.release(); cubtmp.release(); }
+};
+const int X_BUFS[11] = {B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL};
+}
+
+#define XCK(ctx_, x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = (ctx_)->fail_cuda(e_, #x, __FILE__, __LINE__); goto done; } } while (0)
+
+extern "C" int pp_tok_exchange_finish(pp_ctx* const* ctxs, int n_ctx, const uint32_t* owner, uint32_t n_total, const uint32_t* const* local_of,
+                                      const pp_contigs* shard_contigs, uint64_t* n_aln_total) {
+    if (!ctxs || n_ctx < 1 || n_ctx > 32 || !owner || !local_of || !shard_contigs) return PP_ERR_ARG;
+    pp_ctx* c0 = ctxs[0];
+    int rc = PP_OK;
+    std::vector<XSource> src((size_t)n_ctx);
+    const int seq_bits = c0->tok ? c0->tok->seq_bits : 4;
+    const uint32_t blk_bytes = seq_bits == 4 ? 16 : 32;
+    size_t n_files = 0;
+    // counts[g][o][f][4]: what source g sends destination o out of file f
+    std::vector<uint32_t> counts;
+    std::vector<DevBuf> d_owner((size_t)n_ctx);
+    uint32_t* h_marks = nullptr;
+    uint64_t total_aln = 0;
+    // ---- the tokenised arrays leave the dataset buffers (those will receive the shard)
+    for (int g = 0; g < n_ctx; ++g) {
+        pp_ctx* ctx = ctxs[g];
+        TokState* T = ctx->tok;
+        if (!T || !T->active || T->marks.size() < 2 || T->seq_bits != seq_bits) { rc = c0->fail(PP_ERR_ARG, "pp_tok_exchange_finish: a context without tokenised ranges"); goto done; }
+        if (g == 0) n_files = T->marks.size() - 1;
+        if (T->marks.size() - 1 != n_files || n_files > X_MAX_FILES) { rc = PP_TOK_HOST; goto done; }
+        XSource& S = src[g];
+        S.n = T->aln_base; S.ops = T->ops_base; S.blk = T->blk_base; S.reads = T->read_base; S.mk = T->marks;
+        for (int k = 0; k < 11; ++k) std::swap(S.b[k], ctx->b[X_BUFS[k]]);
+        total_aln += S.n;
+    }
+    counts.assign((size_t)n_ctx * n_ctx * n_files * 4, 0);
+    XCK(c0, cudaHostAlloc((void**)&h_marks, (X_MAX_FILES + 1) * 4 * sizeof(uint32_t), cudaHostAllocDefault));
+
+    for (int pass = 0; pass < 2; ++pass) {
+        // pass 0: sizes of every piece; (host: where every piece goes, destination arrays); pass 1: pack and send
+        std::vector<std::vector<XPlan>> plans;
+        if (pass == 1) {
+            plans.assign((size_t)n_ctx, std::vector<XPlan>((size_t)n_ctx));
+            for (int o = 0; o < n_ctx; ++o) {
+                uint64_t at[4] = {0, 0, 0, 0};
+                for (size_t f = 0; f < n_files; ++f)
+                    for (int g = 0; g < n_ctx; ++g) {
+                        XPlan& P = plans[g][o];
+                        P.dst_aln[f] = (uint32_t)at[0]; P.dst_ops[f] = (uint32_t)at[1]; P.dst_blk[f] = (uint32_t)at[2]; P.dst_grp[f] = (uint32_t)at[3];
+                        const uint32_t* c = &counts[(((size_t)g * n_ctx + o) * n_files + f) * 4];
+                        for (int k = 0; k < 4; ++k) at[k] += c[k];
+                    }
+                if (at[0] >= 0x7FFFFFFFull - 4096 || at[1] > 0xFFFFFFFFull || at[2] > 0xFFFFFFFFull || at[3] >= 0xFFFFFFFFull) { rc = PP_TOK_HOST; goto done; }
+                pp_ctx* ctx = ctxs[o];
+                XCK(ctx, cudaSetDevice(ctx->device));
+                const size_t each[11] = {4, 4, 4, 4, 2, 4, 2, 4, 1, 4, blk_bytes};
+                const uint64_t cnt[11] = {at[0], at[0], at[0], at[0], at[0], at[0], at[0], at[0], at[0], at[1], at[2]};
+                for (int k = 0; k < 11; ++k) XCK(ctx, ctx->b[X_BUFS[k]].ensure((size_t)cnt[k] * each[k] + 256));
+                TokState* T = ctx->tok;
+                T->aln_base = at[0]; T->ops_base = at[1]; T->blk_base = at[2]; T->read_base = at[3];
+            }
+        }
+        for (int g = 0; g < n_ctx; ++g) {
+            pp_ctx* ctx = ctxs[g];
+            XSource& S = src[g];
+            cudaStream_t st = ctx->stream;
+            XCK(ctx, cudaSetDevice(ctx->device));
+            const uint64_t n = S.n;
+            const uint32_t read0 = 0, blk0 = 0;
+            const unsigned grid = (unsigned)std::min<uint64_t>((n + 256) / 256 + 1, (uint64_t)ctx->sm_count * 32);
+            XArrays A{S.b[0].as<uint32_t>(), S.b[1].as<uint32_t>(), S.b[2].as<uint32_t>(), S.b[3].as<uint32_t>(), S.b[5].as<uint32_t>(), S.b[7].as<uint32_t>(),
+                      S.b[9].as<uint32_t>(), S.b[4].as<uint16_t>(), S.b[6].as<uint16_t>(), S.b[8].as<uint8_t>(), S.b[10].as<uint8_t>()};
+            if (pass == 0) {
+                XCK(ctx, d_owner[g].ensure((size_t)n_total * 4 + 16));
+                XCK(ctx, cudaMemcpyAsync(d_owner[g].p, owner, (size_t)n_total * 4, cudaMemcpyHostToDevice, st));
+                XCK(ctx, S.touch.ensure((size_t)S.reads * 4 + 16));
+                XCK(ctx, cudaMemsetAsync(S.touch.p, 0, (size_t)S.reads * 4 + 16, st));
+                for (int k = 0; k < 4; ++k) { XCK(ctx, S.fl[k].ensure((n + 2) * 4)); XCK(ctx, S.sc[k].ensure((n + 2) * 4)); }
+                XCK(ctx, S.marks.ensure((X_MAX_FILES + 1) * 16));
+                size_t tb = 0;
+                XCK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)(n + 1), st));
+                XCK(ctx, S.cubtmp.ensure(tb + 256));
+                if (n) k_x_touch<<<grid, 256, 0, st>>>(A.contig, A.read_id, n, d_owner[g].as<uint32_t>(), n_total, read0, S.touch.as<uint32_t>());
+            } else {
+                const size_t each[11] = {4, 4, 4, 4, 2, 4, 2, 4, 1, 4, blk_bytes};
+                const uint64_t cnt[11] = {n, n, n, n, n, n, n, n, n, S.ops, S.blk};
+                for (int k = 0; k < 11; ++k) XCK(ctx, S.stage[k].ensure((size_t)cnt[k] * each[k] + 256));
+                XCK(ctx, S.blockmap.ensure((size_t)S.blk * 4 + 16));
+            }
+            XPlan base;
+            memset(&base, 0, sizeof base);
+            base.n_files = (uint32_t)n_files;
+            for (size_t f = 0; f <= n_files; ++f) base.mark_aln[f] = (uint32_t)S.mk[f].aln;
+            for (int o = 0; o < n_ctx; ++o) {
+                uint32_t* fl[4] = {S.fl[0].as<uint32_t>(), S.fl[1].as<uint32_t>(), S.fl[2].as<uint32_t>(), S.fl[3].as<uint32_t>()};
+                uint32_t* sc[4] = {S.sc[0].as<uint32_t>(), S.sc[1].as<uint32_t>(), S.sc[2].as<uint32_t>(), S.sc[3].as<uint32_t>()};
+                k_x_flags<<<grid, 256, 0, st>>>(A.read_id, A.n_cigar, A.seq_len, A.flags, n, read0, S.touch.as<uint32_t>(), (uint32_t)o, fl[0], fl[1], fl[2], fl[3]);
+                for (int k = 0; k < 4; ++k) {
+                    size_t tb = S.cubtmp.cap;
+                    XCK(ctx, cub::DeviceScan::ExclusiveSum(S.cubtmp.p, tb, fl[k], sc[k], (int64_t)(n + 1), st));
+                }
+                XPlan P = pass == 1 ? plans[g][o] : base;
+                P.n_files = base.n_files;
+                memcpy(P.mark_aln, base.mark_aln, sizeof base.mark_aln);
+                k_x_marks<<<1, X_MAX_FILES + 1, 0, st>>>(sc[0], sc[1], sc[2], sc[3], P, S.marks.as<uint32_t>());
+                if (pass == 0) {
+                    XCK(ctx, cudaMemcpyAsync(h_marks, S.marks.p, (n_files + 1) * 16, cudaMemcpyDeviceToHost, st));
+                    XCK(ctx, cudaStreamSynchronize(st));
+                    for (size_t f = 0; f < n_files; ++f)
+                        for (int k = 0; k < 4; ++k)
+                            counts[(((size_t)g * n_ctx + o) * n_files + f) * 4 + k] = h_marks[4 * (f + 1) + k] - h_marks[4 * f + k];
+                    continue;
+                }
+                XStage Z{S.stage[0].as<uint32_t>(), S.stage[1].as<uint32_t>(), S.stage[2].as<uint32_t>(), S.stage[3].as<uint32_t>(), S.stage[5].as<uint32_t>(),
+                         S.stage[7].as<uint32_t>(), S.stage[9].as<uint32_t>(), S.stage[4].as<uint16_t>(), S.stage[6].as<uint16_t>(), S.stage[8].as<uint8_t>(),
+                         S.stage[10].as<uint8_t>()};
+                if (n) {
+                    k_x_blockmap<<<grid, 256, 0, st>>>(A, n, blk0, fl[0], sc[0], sc[2], S.blockmap.as<uint32_t>());
+                    k_x_pack<<<grid, 256, 0, st>>>(A, Z, n, blk0, blk_bytes, P, sc[0], sc[1], sc[2], sc[3], S.blockmap.as<uint32_t>(), S.marks.as<uint32_t>());
+                    k_x_pack_seq<<<(unsigned)std::min<uint64_t>((n + 31) / 32 + 1, (uint64_t)ctx->sm_count * 64), 256, 0, st>>>(A, Z, n, blk_bytes, sc[0], sc[2]);
+                }
+                // the pieces travel: file f's kept records are one contiguous run of the staging arrays
+                XCK(ctx, cudaMemcpyAsync(h_marks, S.marks.p, (n_files + 1) * 16, cudaMemcpyDeviceToHost, st));
+                XCK(ctx, cudaStreamSynchronize(st));
+                pp_ctx* dctx = ctxs[o];
+                const size_t each[11] = {4, 4, 4, 4, 2, 4, 2, 4, 1, 4, blk_bytes};
+                for (size_t f = 0; f < n_files; ++f) {
+                    const uint32_t* m0 = h_marks + 4 * f;
+                    const uint32_t* m1 = h_marks + 4 * (f + 1);
+                    for (int k = 0; k < 11; ++k) {
+                        const int q = k == 9 ? 1 : k == 10 ? 2 : 0;                   // which scan measures this array
+                        const uint64_t from = m0[q], cntk = (uint64_t)m1[q] - m0[q];
+                        const uint64_t to = q == 0 ? P.dst_aln[f] : q == 1 ? P.dst_ops[f] : P.dst_blk[f];
+                        if (!cntk) continue;
+                        uint8_t* dst = dctx->b[X_BUFS[k]].as<uint8_t>() + (size_t)to * each[k];
+                        const uint8_t* sp = S.stage[k].as<uint8_t>() + (size_t)from * each[k];
+                        if (dctx->device == ctx->device) XCK(ctx, cudaMemcpyAsync(dst, sp, (size_t)cntk * each[k], cudaMemcpyDeviceToDevice, st));
+                        else XCK(ctx, cudaMemcpyPeerAsync(dst, dctx->device, sp, ctx->device, (size_t)cntk * each[k], st));
+                    }
+                }
+                XCK(ctx, cudaStreamSynchronize(st));                                   // (the staging arrays are reused for the next destination)
+            }
+        }
+    }
+    // ---- every GPU holds its groups in global SAM order: ghosts, the shard's contigs, binning
+    for (int o = 0; o < n_ctx && rc == PP_OK; ++o) {
+        pp_ctx* ctx = ctxs[o];
+        src[o].release();
+        d_owner[o].release();
+        if (cudaSetDevice(ctx->device) != cudaSuccess) { rc = PP_ERR_CUDA; break; }
+        rc = pp_tok_set_shard(ctx, local_of[o], n_total, &shard_contigs[o], o == 0);
+        if (rc == PP_OK) rc = pp_tok_finish(ctx);
+        if (rc != PP_OK && ctx != c0) c0->err = ctx->err;
+    }
+    if (n_aln_total) *n_aln_total = total_aln;
+done:
+    for (int g = 0; g < n_ctx; ++g) {
+        cudaSetDevice(ctxs[g]->device);
+        src[g].release();
+        d_owner[g].release();
+        if (rc != PP_OK && ctxs[g]->tok) ctxs[g]->tok->active = false;
+    }
+    if (h_marks) cudaFreeHost(h_marks);
+    return rc;
 }
 
 // ---- the resident dataset, read back (tests compare it with the host packer's arrays)

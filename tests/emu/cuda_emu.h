@@ -21,6 +21,7 @@
 #define __global__
 #define __forceinline__ inline
 #define __noinline__
+#define __grid_constant__
 #define __restrict__
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)

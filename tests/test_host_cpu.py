@@ -255,3 +255,35 @@ def test_cli_help_and_version_need_no_gpu():
     assert subprocess.run([exe, "-V"], capture_output=True, text=True).stdout.strip() == "Polypolish v0.6.1"
     bad = subprocess.run([exe, "polish", "--nope"], capture_output=True, text=True)
     assert bad.returncode == 2 and "unexpected argument '--nope'" in bad.stderr
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_sam_split_ranges_cut_between_read_groups(tmp_path, seed):
+    """pp_sam_split_ranges (multi-GPU ingestion): every cut is a line start whose QNAME differs from the previous line's."""
+    import ctypes as C
+    import random
+    from polypolish_b200 import api
+    rng = random.Random(seed)
+    lines = ["@HD\tVN:1.6", "@SQ\tSN:c1\tLN:1000"] if seed % 2 == 0 else []
+    for r in range(rng.randint(1, 400)):
+        for _ in range(rng.choice([1, 1, 1, 2, 3, 8, 40] if seed != 3 else [200])):
+            lines.append("read%d\t0\tc1\t%d\t60\t10M\t*\t0\t0\t%s\t*" % (r, rng.randint(1, 900), "ACGT" * rng.randint(1, 30)))
+    text = "\n".join(lines) + ("\n" if seed != 5 else "")
+    p = tmp_path / "x.sam"
+    p.write_text(text)
+    data = text.encode()
+    L = api.lib()
+    L.pp_sam_split_ranges.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
+    for n in (1, 2, 3, 8, 32):
+        cuts = (C.c_uint64 * (n + 1))()
+        assert L.pp_sam_split_ranges(str(p).encode(), n, cuts) == 0
+        cuts = list(cuts)
+        assert cuts[0] == 0 and cuts[-1] == len(data) and cuts == sorted(cuts)
+        for c in cuts[1:-1]:
+            if c == len(data):
+                continue
+            assert data[c - 1:c] == b"\n"
+            prev = data[:c - 1].rsplit(b"\n", 1)[-1].split(b"\t")[0]
+            here = data[c:].split(b"\n", 1)[0].split(b"\t")[0]
+            assert prev != here or here.startswith(b"@")
+    assert L.pp_sam_split_ranges(str(tmp_path / "missing.sam").encode(), 2, (C.c_uint64 * 3)()) != 0
