@@ -262,6 +262,8 @@ struct TokState {
     std::vector<uint64_t> range_off, range_len;
     struct Mark { uint64_t aln, ops, blk, reads; };
     std::vector<Mark> marks;
+    struct XState;                    // buffers of pp_tok_exchange_finish, kept between calls (no cudaMalloc in the steady state)
+    XState* xs = nullptr;
     // pp_tok_set_shard: this context keeps one shard of the assembly
     bool shard_on = false, shard_unknown = false;
     DevBuf shard_map;                 // local_of[c] on the device
@@ -271,6 +273,7 @@ struct TokState {
 };
 
 static void free_filter_bufs(TokFilterBufs* b);
+static void free_xstate(TokState* T);
 
 void pp_tok_release(pp_ctx* ctx) {
     TokState* T = ctx->tok;
@@ -291,6 +294,7 @@ void pp_tok_release(pp_ctx* ctx) {
     if (T->d_st) cudaFree(T->d_st);
     T->cub.release();
     T->shard_map.release();
+    free_xstate(T);
     delete T;
     ctx->tok = nullptr;
 }
@@ -983,15 +987,20 @@ __global__ void k_x_pack_seq(XArrays a, XStage st, uint64_t n, uint32_t blk_byte
     }
 }
 
-namespace {
-struct XSource {                     // one context's tokenised ranges, moved out of the dataset buffers
+struct TokState::XState {            // one context's tokenised ranges, moved out of the dataset buffers
     DevBuf b[11];                    // B_CONTIG .. B_SEQPOOL, in the enum's order
     DevBuf stage[11], touch, fl[4], sc[4], blockmap, marks, cubtmp;
     uint64_t n = 0, ops = 0, blk = 0, reads = 0;
     std::vector<TokState::Mark> mk;
+    DevBuf d_owner;
+    uint32_t* h_marks = nullptr;     // pinned
     void release() { for (auto& x : b) x.release(); for (auto& x : stage) x.release(); touch.release(); for (auto& x : fl) x.release();
-                     for (auto& x : sc) x.release(); blockmap.release(); marks.release(); cubtmp.release(); }
+                     for (auto& x : sc) x.release(); blockmap.release(); marks.release(); cubtmp.release(); d_owner.release();
+                     if (h_marks) cudaFreeHost(h_marks); h_marks = nullptr; }
 };
+static void free_xstate(TokState* T) { if (T->xs) { T->xs->release(); delete T->xs; T->xs = nullptr; } }
+namespace {
+typedef TokState::XState XSource;
 const int X_BUFS[11] = {B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL};
 }
 
@@ -1002,14 +1011,12 @@ extern "C" int pp_tok_exchange_finish(pp_ctx* const* ctxs, int n_ctx, const uint
     if (!ctxs || n_ctx < 1 || n_ctx > 32 || !owner || !local_of || !shard_contigs) return PP_ERR_ARG;
     pp_ctx* c0 = ctxs[0];
     int rc = PP_OK;
-    std::vector<XSource> src((size_t)n_ctx);
+    std::vector<XSource*> src((size_t)n_ctx, nullptr);
     const int seq_bits = c0->tok ? c0->tok->seq_bits : 4;
     const uint32_t blk_bytes = seq_bits == 4 ? 16 : 32;
     size_t n_files = 0;
     // counts[g][o][f][4]: what source g sends destination o out of file f
     std::vector<uint32_t> counts;
-    std::vector<DevBuf> d_owner((size_t)n_ctx);
-    uint32_t* h_marks = nullptr;
     uint64_t total_aln = 0;
     // ---- the tokenised arrays leave the dataset buffers (those will receive the shard)
     for (int g = 0; g < n_ctx; ++g) {
@@ -1018,13 +1025,24 @@ extern "C" int pp_tok_exchange_finish(pp_ctx* const* ctxs, int n_ctx, const uint
         if (!T || !T->active || T->marks.size() < 2 || T->seq_bits != seq_bits) { rc = c0->fail(PP_ERR_ARG, "pp_tok_exchange_finish: a context without tokenised ranges"); goto done; }
         if (g == 0) n_files = T->marks.size() - 1;
         if (T->marks.size() - 1 != n_files || n_files > X_MAX_FILES) { rc = PP_TOK_HOST; goto done; }
-        XSource& S = src[g];
+        if (!T->xs) T->xs = new XSource();
+        src[g] = T->xs;
+        XSource& S = *src[g];
         S.n = T->aln_base; S.ops = T->ops_base; S.blk = T->blk_base; S.reads = T->read_base; S.mk = T->marks;
         for (int k = 0; k < 11; ++k) std::swap(S.b[k], ctx->b[X_BUFS[k]]);
         total_aln += S.n;
     }
     counts.assign((size_t)n_ctx * n_ctx * n_files * 4, 0);
-    XCK(c0, cudaHostAlloc((void**)&h_marks, (X_MAX_FILES + 1) * 4 * sizeof(uint32_t), cudaHostAllocDefault));
+    for (int g = 0; g < n_ctx; ++g) {
+        XCK(ctxs[g], cudaSetDevice(ctxs[g]->device));
+        if (!src[g]->h_marks) XCK(ctxs[g], cudaHostAlloc((void**)&src[g]->h_marks, (X_MAX_FILES + 1) * 4 * sizeof(uint32_t), cudaHostAllocDefault));
+        for (int o = 0; o < n_ctx; ++o)                                                // NVLink between the GPUs where the box has it
+            if (ctxs[o]->device != ctxs[g]->device) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, ctxs[g]->device, ctxs[o]->device) == cudaSuccess && can) cudaDeviceEnablePeerAccess(ctxs[o]->device, 0);
+                cudaGetLastError();                                                    // (already enabled is fine)
+            }
+    }
 
     for (int pass = 0; pass < 2; ++pass) {
         // pass 0: sizes of every piece; (host: where every piece goes, destination arrays); pass 1: pack and send
@@ -1050,73 +1068,73 @@ extern "C" int pp_tok_exchange_finish(pp_ctx* const* ctxs, int n_ctx, const uint
                 T->aln_base = at[0]; T->ops_base = at[1]; T->blk_base = at[2]; T->read_base = at[3];
             }
         }
-        for (int g = 0; g < n_ctx; ++g) {
+        // every source GPU works through its destinations on its own stream, driven by its own host thread
+        auto per_source = [&](int g) -> int {
             pp_ctx* ctx = ctxs[g];
-            XSource& S = src[g];
+            XSource& S = *src[g];
             cudaStream_t st = ctx->stream;
-            XCK(ctx, cudaSetDevice(ctx->device));
+            uint32_t* hm = S.h_marks;
+            CK(cudaSetDevice(ctx->device));
             const uint64_t n = S.n;
             const uint32_t read0 = 0, blk0 = 0;
             const unsigned grid = (unsigned)std::min<uint64_t>((n + 256) / 256 + 1, (uint64_t)ctx->sm_count * 32);
             XArrays A{S.b[0].as<uint32_t>(), S.b[1].as<uint32_t>(), S.b[2].as<uint32_t>(), S.b[3].as<uint32_t>(), S.b[5].as<uint32_t>(), S.b[7].as<uint32_t>(),
                       S.b[9].as<uint32_t>(), S.b[4].as<uint16_t>(), S.b[6].as<uint16_t>(), S.b[8].as<uint8_t>(), S.b[10].as<uint8_t>()};
+            const size_t each[11] = {4, 4, 4, 4, 2, 4, 2, 4, 1, 4, blk_bytes};
             if (pass == 0) {
-                XCK(ctx, d_owner[g].ensure((size_t)n_total * 4 + 16));
-                XCK(ctx, cudaMemcpyAsync(d_owner[g].p, owner, (size_t)n_total * 4, cudaMemcpyHostToDevice, st));
-                XCK(ctx, S.touch.ensure((size_t)S.reads * 4 + 16));
-                XCK(ctx, cudaMemsetAsync(S.touch.p, 0, (size_t)S.reads * 4 + 16, st));
-                for (int k = 0; k < 4; ++k) { XCK(ctx, S.fl[k].ensure((n + 2) * 4)); XCK(ctx, S.sc[k].ensure((n + 2) * 4)); }
-                XCK(ctx, S.marks.ensure((X_MAX_FILES + 1) * 16));
+                CK(S.d_owner.ensure((size_t)n_total * 4 + 16));
+                CK(cudaMemcpyAsync(S.d_owner.p, owner, (size_t)n_total * 4, cudaMemcpyHostToDevice, st));
+                CK(S.touch.ensure((size_t)S.reads * 4 + 16));
+                CK(cudaMemsetAsync(S.touch.p, 0, (size_t)S.reads * 4 + 16, st));
+                for (int k = 0; k < 4; ++k) { CK(S.fl[k].ensure((n + 2) * 4)); CK(S.sc[k].ensure((n + 2) * 4)); }
+                CK(S.marks.ensure((X_MAX_FILES + 1) * 16));
                 size_t tb = 0;
-                XCK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)(n + 1), st));
-                XCK(ctx, S.cubtmp.ensure(tb + 256));
-                if (n) k_x_touch<<<grid, 256, 0, st>>>(A.contig, A.read_id, n, d_owner[g].as<uint32_t>(), n_total, read0, S.touch.as<uint32_t>());
+                CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)(n + 1), st));
+                CK(S.cubtmp.ensure(tb + 256));
+                if (n) k_x_touch<<<grid, 256, 0, st>>>(A.contig, A.read_id, n, S.d_owner.as<uint32_t>(), n_total, read0, S.touch.as<uint32_t>());
             } else {
-                const size_t each[11] = {4, 4, 4, 4, 2, 4, 2, 4, 1, 4, blk_bytes};
                 const uint64_t cnt[11] = {n, n, n, n, n, n, n, n, n, S.ops, S.blk};
-                for (int k = 0; k < 11; ++k) XCK(ctx, S.stage[k].ensure((size_t)cnt[k] * each[k] + 256));
-                XCK(ctx, S.blockmap.ensure((size_t)S.blk * 4 + 16));
+                for (int k = 0; k < 11; ++k) CK(S.stage[k].ensure((size_t)cnt[k] * each[k] + 256));
+                CK(S.blockmap.ensure((size_t)S.blk * 4 + 16));
             }
             XPlan base;
             memset(&base, 0, sizeof base);
             base.n_files = (uint32_t)n_files;
             for (size_t f = 0; f <= n_files; ++f) base.mark_aln[f] = (uint32_t)S.mk[f].aln;
-            for (int o = 0; o < n_ctx; ++o) {
+            for (int oo = 0; oo < n_ctx; ++oo) {
+                const int o = (g + oo) % n_ctx;                                        // (the sources start on different destinations)
                 uint32_t* fl[4] = {S.fl[0].as<uint32_t>(), S.fl[1].as<uint32_t>(), S.fl[2].as<uint32_t>(), S.fl[3].as<uint32_t>()};
                 uint32_t* sc[4] = {S.sc[0].as<uint32_t>(), S.sc[1].as<uint32_t>(), S.sc[2].as<uint32_t>(), S.sc[3].as<uint32_t>()};
                 k_x_flags<<<grid, 256, 0, st>>>(A.read_id, A.n_cigar, A.seq_len, A.flags, n, read0, S.touch.as<uint32_t>(), (uint32_t)o, fl[0], fl[1], fl[2], fl[3]);
                 for (int k = 0; k < 4; ++k) {
                     size_t tb = S.cubtmp.cap;
-                    XCK(ctx, cub::DeviceScan::ExclusiveSum(S.cubtmp.p, tb, fl[k], sc[k], (int64_t)(n + 1), st));
+                    CK(cub::DeviceScan::ExclusiveSum(S.cubtmp.p, tb, fl[k], sc[k], (int64_t)(n + 1), st));
                 }
                 XPlan P = pass == 1 ? plans[g][o] : base;
                 P.n_files = base.n_files;
                 memcpy(P.mark_aln, base.mark_aln, sizeof base.mark_aln);
                 k_x_marks<<<1, X_MAX_FILES + 1, 0, st>>>(sc[0], sc[1], sc[2], sc[3], P, S.marks.as<uint32_t>());
-                if (pass == 0) {
-                    XCK(ctx, cudaMemcpyAsync(h_marks, S.marks.p, (n_files + 1) * 16, cudaMemcpyDeviceToHost, st));
-                    XCK(ctx, cudaStreamSynchronize(st));
-                    for (size_t f = 0; f < n_files; ++f)
-                        for (int k = 0; k < 4; ++k)
-                            counts[(((size_t)g * n_ctx + o) * n_files + f) * 4 + k] = h_marks[4 * (f + 1) + k] - h_marks[4 * f + k];
-                    continue;
-                }
-                XStage Z{S.stage[0].as<uint32_t>(), S.stage[1].as<uint32_t>(), S.stage[2].as<uint32_t>(), S.stage[3].as<uint32_t>(), S.stage[5].as<uint32_t>(),
-                         S.stage[7].as<uint32_t>(), S.stage[9].as<uint32_t>(), S.stage[4].as<uint16_t>(), S.stage[6].as<uint16_t>(), S.stage[8].as<uint8_t>(),
-                         S.stage[10].as<uint8_t>()};
-                if (n) {
+                if (pass == 1 && n) {
+                    XStage Z{S.stage[0].as<uint32_t>(), S.stage[1].as<uint32_t>(), S.stage[2].as<uint32_t>(), S.stage[3].as<uint32_t>(), S.stage[5].as<uint32_t>(),
+                             S.stage[7].as<uint32_t>(), S.stage[9].as<uint32_t>(), S.stage[4].as<uint16_t>(), S.stage[6].as<uint16_t>(), S.stage[8].as<uint8_t>(),
+                             S.stage[10].as<uint8_t>()};
                     k_x_blockmap<<<grid, 256, 0, st>>>(A, n, blk0, fl[0], sc[0], sc[2], S.blockmap.as<uint32_t>());
                     k_x_pack<<<grid, 256, 0, st>>>(A, Z, n, blk0, blk_bytes, P, sc[0], sc[1], sc[2], sc[3], S.blockmap.as<uint32_t>(), S.marks.as<uint32_t>());
                     k_x_pack_seq<<<(unsigned)std::min<uint64_t>((n + 31) / 32 + 1, (uint64_t)ctx->sm_count * 64), 256, 0, st>>>(A, Z, n, blk_bytes, sc[0], sc[2]);
                 }
+                CK(cudaMemcpyAsync(hm, S.marks.p, (n_files + 1) * 16, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (pass == 0) {
+                    for (size_t f = 0; f < n_files; ++f)
+                        for (int k = 0; k < 4; ++k)
+                            counts[(((size_t)g * n_ctx + o) * n_files + f) * 4 + k] = hm[4 * (f + 1) + k] - hm[4 * f + k];
+                    continue;
+                }
                 // the pieces travel: file f's kept records are one contiguous run of the staging arrays
-                XCK(ctx, cudaMemcpyAsync(h_marks, S.marks.p, (n_files + 1) * 16, cudaMemcpyDeviceToHost, st));
-                XCK(ctx, cudaStreamSynchronize(st));
                 pp_ctx* dctx = ctxs[o];
-                const size_t each[11] = {4, 4, 4, 4, 2, 4, 2, 4, 1, 4, blk_bytes};
                 for (size_t f = 0; f < n_files; ++f) {
-                    const uint32_t* m0 = h_marks + 4 * f;
-                    const uint32_t* m1 = h_marks + 4 * (f + 1);
+                    const uint32_t* m0 = hm + 4 * f;
+                    const uint32_t* m1 = hm + 4 * (f + 1);
                     for (int k = 0; k < 11; ++k) {
                         const int q = k == 9 ? 1 : k == 10 ? 2 : 0;                   // which scan measures this array
                         const uint64_t from = m0[q], cntk = (uint64_t)m1[q] - m0[q];
@@ -1124,19 +1142,27 @@ extern "C" int pp_tok_exchange_finish(pp_ctx* const* ctxs, int n_ctx, const uint
                         if (!cntk) continue;
                         uint8_t* dst = dctx->b[X_BUFS[k]].as<uint8_t>() + (size_t)to * each[k];
                         const uint8_t* sp = S.stage[k].as<uint8_t>() + (size_t)from * each[k];
-                        if (dctx->device == ctx->device) XCK(ctx, cudaMemcpyAsync(dst, sp, (size_t)cntk * each[k], cudaMemcpyDeviceToDevice, st));
-                        else XCK(ctx, cudaMemcpyPeerAsync(dst, dctx->device, sp, ctx->device, (size_t)cntk * each[k], st));
+                        if (dctx->device == ctx->device) CK(cudaMemcpyAsync(dst, sp, (size_t)cntk * each[k], cudaMemcpyDeviceToDevice, st));
+                        else CK(cudaMemcpyPeerAsync(dst, dctx->device, sp, ctx->device, (size_t)cntk * each[k], st));
                     }
                 }
-                XCK(ctx, cudaStreamSynchronize(st));                                   // (the staging arrays are reused for the next destination)
+                CK(cudaStreamSynchronize(st));                                         // (the staging arrays are reused for the next destination)
             }
+            return PP_OK;
+        };
+        std::vector<int> prc((size_t)n_ctx, PP_OK);
+        {
+            std::vector<std::thread> th;
+            for (int g = 1; g < n_ctx; ++g) th.emplace_back([&, g] { prc[(size_t)g] = per_source(g); });
+            prc[0] = per_source(0);
+            for (auto& t : th) t.join();
         }
+        for (int g = 0; g < n_ctx; ++g)
+            if (prc[(size_t)g] != PP_OK) { rc = prc[(size_t)g]; if (ctxs[g] != c0) c0->err = ctxs[g]->err; goto done; }
     }
     // ---- every GPU holds its groups in global SAM order: ghosts, the shard's contigs, binning
     for (int o = 0; o < n_ctx && rc == PP_OK; ++o) {
         pp_ctx* ctx = ctxs[o];
-        src[o].release();
-        d_owner[o].release();
         if (cudaSetDevice(ctx->device) != cudaSuccess) { rc = PP_ERR_CUDA; break; }
         rc = pp_tok_set_shard(ctx, local_of[o], n_total, &shard_contigs[o], o == 0);
         if (rc == PP_OK) rc = pp_tok_finish(ctx);
@@ -1145,12 +1171,9 @@ extern "C" int pp_tok_exchange_finish(pp_ctx* const* ctxs, int n_ctx, const uint
     if (n_aln_total) *n_aln_total = total_aln;
 done:
     for (int g = 0; g < n_ctx; ++g) {
-        cudaSetDevice(ctxs[g]->device);
-        src[g].release();
-        d_owner[g].release();
+        // (the buffers stay with the context: the range arrays that were swapped out are the spare capacity of the next call)
         if (rc != PP_OK && ctxs[g]->tok) ctxs[g]->tok->active = false;
     }
-    if (h_marks) cudaFreeHost(h_marks);
     return rc;
 }
 

@@ -53,6 +53,9 @@ def main():
         timed("%d_gpus_device_shards" % n_gpu, lambda: api.polish_files_multi(fa, sams, contexts=ctxs, parser=0), reps=4)
         timed("%d_gpus_host_packer_host_sharder" % n_gpu, lambda: api.polish_files_multi(fa, sams, contexts=ctxs, parser=1), reps=2)
         ctxs[0].set_parser(0)
+        os.environ["POLYPOLISH_TIMING"] = "1"
+        api.polish_files_multi(fa, sams, contexts=ctxs, parser=0, verbose=True)          # the library's own timing lines -> stderr
+        os.environ.pop("POLYPOLISH_TIMING")
         if n_gpu == 1:
             four = [pp.Context(0) for _ in range(4)]
             timed("4_contexts_one_gpu_device_shards", lambda: api.polish_files_multi(fa, sams, contexts=four, parser=0), reps=3)
