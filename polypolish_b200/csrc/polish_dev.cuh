@@ -1121,7 +1121,7 @@ __device__ void depth_walk_two(const DevData& d, TileShared& sh, WalkStage& ws, 
                 uint4 q = make_uint4(NONE32, 0, 0, 1);
                 if (slot < end[r]) {
                     q = d.wrec[slot];
-                    if (slot + 32 < end[r]) PP_PREFETCH_L1(d.wrec + slot + 32);
+                    if (slot + 32 < end[r]) PP_PREFETCH_L2(d.wrec + slot + 32);    // (requesting the next window into registers instead was measured: no faster)
                 }
                 const bool ov = slot < end[r] && q.z != 0 && q.y < s + PP_SUB && q.y + q.z > s;
                 mask[r] = __ballot_sync(0xffffffffu, ov);
@@ -1210,15 +1210,20 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
 #endif
         // The slots of the tile's bins and of the `lb` bins before it - one contiguous range of the binned dataset - and the first two
         // chunks' records: a chain of four dependent trips to memory (bin bounds, record, its k word, ...) that now runs under phase A.
+        // (taking the next tile's ticket a tile early, to hide these trips, was measured: the greedy heaviest-first schedule then
+        // looks one tile ahead and the kernel's tail grows - 0.504 -> 0.548 ms)
         const uint32_t b0 = P0 >> PP_BIN_SHIFT;
         const uint32_t lo = d.bin_start[b0 >= lb ? b0 - lb : 0u];
         const uint32_t hi = d.bin_start[min(b0 + (uint32_t)(TL_T / PP_BIN), d.n_bins)];
         const uint32_t stride = 32u * (TL_THREADS / 32);
         uint32_t c_a = lo + 32u * warp;
-        TileRec rec_a, rec_b;
+        // Only two words per lane travel from one round of the chunk loop to the next - the SAM index of the NEXT chunk's record (what
+        // its k word is gathered with) and that k word.  (Carrying whole records two chunks ahead cost 16 registers the fast walk does
+        // not have: they lived on the stack, and every round began with their reloads from local memory.)
+        const uint32_t last_slot = d.n_slots ? d.n_slots - 1 : 0u;
         uint32_t k_a = 0;
-        rec_a = load_srec(d, min(c_a + lane, d.n_slots ? d.n_slots - 1 : 0u));
-        rec_b = load_srec(d, min(c_a + stride + lane, d.n_slots ? d.n_slots - 1 : 0u));
+        const uint32_t aln_a = __ldg(&d.srec[min(c_a + lane, last_slot)].aln);
+        uint32_t aln_b = __ldg(&d.srec[min(c_a + stride + lane, last_slot)].aln);
         if (BITS == 4 && c_a + lane < hi) PP_PREFETCH_L2(reinterpret_cast<const uint8_t*>(d.sseq + (size_t)(c_a + lane) * TL_SEQ_QUADS));
         // ---- phase A: clear the counters, stage the draft as 4-bit codes
         {
@@ -1242,7 +1247,7 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                 }
             }
         }
-        if (c_a + lane < hi) k_a = d.kf[rec_a.aln];            // (the record has arrived while the counters were cleared)
+        if (c_a + lane < hi) k_a = d.kf[aln_a];                // (the record has arrived while the counters were cleared)
         __syncthreads();
 #ifdef PP_TILE_PROF
         pt[1] = clock64();
@@ -1256,10 +1261,12 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
             // loop, which therefore runs the same straight-line code on every lane
             while (c_a < hi) {
                 const uint32_t c_b = c_a + stride, c_c = c_b + stride;
-                // next chunk: its k word (the record arrived during the previous round); the chunk after: its records
+                // next chunk: its k word (its SAM index arrived during the previous round); the chunk after: its SAM index (which also
+                // brings the 32-byte record into L2); this chunk: its records, requested together with the bases
                 uint32_t k_b = 0;
-                if (c_b + lane < hi) k_b = d.kf[rec_b.aln];
-                const TileRec rec_c = load_srec(d, min(c_c + lane, d.n_slots ? d.n_slots - 1 : 0u));
+                if (c_b + lane < hi) k_b = d.kf[aln_b];
+                const uint32_t aln_c = __ldg(&d.srec[min(c_c + lane, last_slot)].aln);
+                const TileRec rec_a = load_srec(d, min(c_a + lane, last_slot));
                 if (BITS == 4 && c_b + lane < hi) {                                    // and its bases towards L2 (contiguous: exact lines)
                     const uint8_t* nsp = reinterpret_cast<const uint8_t*>(d.sseq + (size_t)(c_b + lane) * TL_SEQ_QUADS);
                     PP_PREFETCH_L2(nsp);
@@ -1284,7 +1291,7 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
                     } else                                                             // (a tile with more than TL_QCAP such reads)
                         d.wrec[i] = make_uint4(rec_a.aln, rec_a.gstart, slow_walk<BITS>(&d, &sh, P0, rec_a, i, k_a), k_a);
                 }
-                c_a = c_b; rec_a = rec_b; rec_b = rec_c; k_a = k_b;
+                c_a = c_b; aln_b = aln_c; k_a = k_b;
             }
         }
         __syncthreads();
