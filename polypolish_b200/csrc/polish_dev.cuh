@@ -126,6 +126,7 @@ struct DevData {                     // everything the kernels read, by value
     const uint32_t* tile_order;      // [n_tiles] tiles by decreasing slot count: the ticket order (heavy tiles first, no long tail)
     uint32_t max_ext;                // largest entry count of a binned alignment (how many bins a tile looks back)
     uint8_t* errc;                   // [n_aln] 0, or the error the reference raises IF the alignment is good (alignment.rs:187-198,298-300)
+    uint16_t* gq;                    // [n_aln] everything k_goodk needs that does not depend on the options (GQ_* bits; high byte min(NM, 255))
     // per call
     uint32_t* kf;                    // [n_aln] k of the alignment's read group if it contributes under the current options, else 0
     uint4* wrec;                     // [n_aln] per sorted slot: (alignment, first position, kept entries, k) - what the ordered depth walk reads
@@ -266,6 +267,21 @@ __device__ __forceinline__ bool alignment_is_good(const DevData& d, unsigned lon
            !(fl & PP_FLAG_ZPFAIL) && !(d.prm->careful && multi);
 }
 
+// The same from the per-alignment summary k_bin leaves behind (written once per dataset): bit 0 first and last CIGAR op are M / =,
+// 1 ZP:Z:fail, 2 ghost, 3 the read group has more than one aligned record, 4 no CIGAR ops at all, 5..7 the error a GOOD alignment
+// raises (errc), 8..15 min(NM, 255).
+#define GQ_ENDS 1u
+#define GQ_ZP 2u
+#define GQ_GHOST 4u
+#define GQ_MULTI 8u
+#define GQ_NOOPS 16u
+__device__ __forceinline__ bool good_from_summary(const DevData& d, const DevParams& prm, unsigned long long a, uint32_t q) {
+    if (q & GQ_NOOPS) { report_error(d.st, a, ERR_BAD_OP); return false; }             // the packer never emits this
+    uint32_t nm = q >> 8;
+    if (nm == 255u && prm.max_errors >= 255u) nm = d.nm[a];
+    return (q & GQ_ENDS) && nm <= prm.max_errors && !(q & GQ_ZP) && !(prm.careful && (q & GQ_MULTI));
+}
+
 // k_classify_multi: FALLBACK pre-pass, only launched when a read group was too large for k_prep's in-kernel scan
 // (FL_BIGGROUP): k = #good of every multi-record group into a global array (alignment.rs:288).
 __global__ void __launch_bounds__(256) k_classify_multi(DevData d) {
@@ -331,6 +347,16 @@ __device__ __forceinline__ void bin_body(const DevData& d) {
             }
         }
         d.errc[aln] = (uint8_t)err;
+        {
+            uint32_t q = (fl & PP_FLAG_ZPFAIL ? GQ_ZP : 0u) | (fl & PP_FLAG_GHOST ? GQ_GHOST : 0u) | (ncig == 0 ? GQ_NOOPS : 0u) | (err << 5) |
+                         (min(d.nm[aln], 255u) << 8);
+            if (ncig) {
+                const uint32_t f = d.cigar_ops[cigoff] & 15u, l = d.cigar_ops[cigoff + ncig - 1] & 15u;
+                if ((f == PP_OP_M || f == PP_OP_EQ) && (l == PP_OP_M || l == PP_OP_EQ)) q |= GQ_ENDS;
+            }
+            if (group_is_multi(d, aln, d.read_id[aln])) q |= GQ_MULTI;
+            d.gq[aln] = (uint16_t)q;
+        }
         d.key[aln] = key; d.val[aln] = (uint32_t)aln;
     }
     for (int o = 16; o > 0; o >>= 1) max_ext = max(max_ext, __shfl_down_sync(0xffffffffu, max_ext, o));
@@ -410,21 +436,19 @@ template <bool GLOBALK>
 __device__ __forceinline__ void goodk_body(const DevData& d, PrepShared& sh) {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const unsigned long long n_blocks = (d.n_aln + PR_THREADS - 1) / PR_THREADS;
+    const DevParams prm = *d.prm;
     unsigned long long used = 0;
     for (unsigned long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         const unsigned long long blk0 = blk * PR_THREADS;
         const unsigned long long aln = blk0 + tid;
         const uint32_t nvalid = (uint32_t)min((unsigned long long)PR_THREADS, d.n_aln - blk0);
         bool good = false, grp = false;
-        uint32_t rid = 0, cigoff = 0, ncig = 0;
-        uint8_t fl = 0;
+        uint32_t rid = 0, q = 0;
         if (aln < d.n_aln) {
             rid = d.read_id[aln];
-            grp = group_is_multi(d, aln, rid);
-            cigoff = d.cigar_off[aln];
-            ncig = d.n_cigar[aln];
-            fl = d.flags[aln];
-            good = alignment_is_good(d, aln, grp, cigoff, ncig, fl);
+            q = d.gq[aln];                                      // 6 bytes per alignment in all: the rest was settled by k_bin
+            grp = q & GQ_MULTI;
+            good = good_from_summary(d, prm, aln, q);
         }
         sh.rid[tid] = rid;
         sh.good[tid] = good ? 1 : 0;
@@ -440,7 +464,7 @@ __device__ __forceinline__ void goodk_body(const DevData& d, PrepShared& sh) {
                 if (i == 0) {
                     for (unsigned long long a2 = blk0; a2 > 0 && d.read_id[a2 - 1] == rid;) {
                         --a2;
-                        count += alignment_is_good(d, a2, true, d.cigar_off[a2], d.n_cigar[a2], d.flags[a2]) ? 1 : 0;
+                        count += good_from_summary(d, prm, a2, d.gq[a2]) ? 1 : 0;
                         if (++steps > SC_GROUP_SCAN_LIMIT) { atomicOr(&d.st->flags, (unsigned)FL_BIGGROUP); break; }
                     }
                 }
@@ -449,18 +473,18 @@ __device__ __forceinline__ void goodk_body(const DevData& d, PrepShared& sh) {
                 if (i == (int)nvalid - 1) {
                     for (unsigned long long a2 = blk0 + nvalid - 1; a2 + 1 < d.n_aln && d.read_id[a2 + 1] == rid;) {
                         ++a2;
-                        count += alignment_is_good(d, a2, true, d.cigar_off[a2], d.n_cigar[a2], d.flags[a2]) ? 1 : 0;
+                        count += good_from_summary(d, prm, a2, d.gq[a2]) ? 1 : 0;
                         if (++steps > SC_GROUP_SCAN_LIMIT) { atomicOr(&d.st->flags, (unsigned)FL_BIGGROUP); break; }
                     }
                 }
                 k = count;
             }
         }
-        if (fl & PP_FLAG_GHOST) good = false;                   // another shard scatters it; it only counted towards k
+        if (q & GQ_GHOST) good = false;                         // another shard scatters it; it only counted towards k
         uint32_t kf = 0;
         if (good) {
             used++;
-            const uint32_t e = d.errc[aln];                     // what the reference raises for a good alignment (found once, by k_bin)
+            const uint32_t e = (q >> 5) & 7u;                   // what the reference raises for a good alignment (found once, by k_bin)
             if (e) report_error(d.st, aln, e);
             else kf = k;
         }
@@ -670,7 +694,8 @@ __device__ __forceinline__ PosOut vote_position(const OthCtx& oc, const DevParam
 // ------------------------------------------------------------------------------------------------------
 // k_tile
 // ------------------------------------------------------------------------------------------------------
-#define TL_DN_HALO 32                                  // draft nibbles are staged for tile positions [-32, T + 32)
+#define TL_DN_HALO 32
+#define TL_INV_K 32                                  // draft nibbles are staged for tile positions [-32, T + 32)
 #define TL_DN_WORDS ((TL_T + 2 * TL_DN_HALO) / 16)
 
 struct WalkStage {                                     // per warp: staging of the ordered-depth merge (depth_walk_two)
@@ -694,6 +719,7 @@ struct TileShared {
     long long s_delta[TL_THREADS / 32];
     uint32_t tile;
     uint32_t subflags;                                 // sub-tiles that see k != 1 coverage
+    double inv_k[TL_INV_K + 1];                        // 1.0 / k for small k (the ordered-depth walk divides once per slot otherwise)
 };
 
 template <int BITS> struct TileCtx {
@@ -1045,7 +1071,7 @@ __device__ void depth_walk_steps(const DevData& d, TileShared& sh, uint32_t P0, 
             const bool ov = slot < end[r] && len != 0 && q.y < s + PP_SUB && q.y + len > s;
             const uint32_t m = __ballot_sync(0xffffffffu, ov);
             w_aln[r] = q.x; w_start[r] = q.y; w_len[r] = len;
-            w_inv[r] = __ddiv_rn(1.0, (double)q.w);             // 1.0 / good_alignments.len() as f64 (alignment.rs:288)
+            w_inv[r] = q.w <= (uint32_t)TL_INV_K ? sh.inv_k[q.w] : __ddiv_rn(1.0, (double)q.w);             // 1.0 / good_alignments.len() as f64 (alignment.rs:288)
             if (m) { mask[r] = m; head[r] = __shfl_sync(0xffffffffu, w_aln[r], __ffs((int)m) - 1); return; }
             wb[r] += 32;
         }
@@ -1126,7 +1152,7 @@ __device__ void depth_walk_two(const DevData& d, TileShared& sh, WalkStage& ws, 
                 const bool ov = slot < end[r] && q.z != 0 && q.y < s + PP_SUB && q.y + q.z > s;
                 mask[r] = __ballot_sync(0xffffffffu, ov);
                 w_aln[r] = q.x; w_start[r] = q.y; w_len[r] = q.z;
-                w_inv[r] = __ddiv_rn(1.0, (double)q.w);         // 1.0 / good_alignments.len() as f64 (alignment.rs:288)
+                w_inv[r] = q.w <= (uint32_t)TL_INV_K ? sh.inv_k[q.w] : __ddiv_rn(1.0, (double)q.w);         // 1.0 / good_alignments.len() as f64 (alignment.rs:288)
                 // every entry of the run up to this key is in this window or behind us; NONE32 once the run has no further window
                 lastkey[r] = (wb[r] + 32 < end[r]) ? __shfl_sync(0xffffffffu, w_aln[r], 31) : NONE32;
             }
@@ -1196,6 +1222,7 @@ __device__ __forceinline__ void tile_body(const DevData& d, const VoteParams& vp
     oc.nodes = d.nodes; oc.head = d.oth_head;
     oc.sr = SeqRef{d.seq_pool, d.seq_off, d.seq_len, d.flags};
 
+    if (tid <= (uint32_t)TL_INV_K) sh.inv_k[tid] = tid ? __ddiv_rn(1.0, (double)tid) : 0.0;   // the same correctly rounded quotients, made once
     for (;;) {
         __syncthreads();                                                       // everyone is done with the previous tile
         if (tid == 0) { sh.tile = atomicAdd(&d.st->ticket, 1u); sh.subflags = 0; sh.qn = 0; }

@@ -136,7 +136,7 @@ static void fill_data(pp_ctx* ctx, DevData& d) {
     d.srec = ctx->b[B_SREC].as<TileRec>(); d.sseq = ctx->b[B_SSEQ].as<uint4>();
     d.n_slots = ctx->n_slots; d.max_ext = ctx->max_ext;
     d.tile_order = ctx->b[B_TILEORDER].as<uint32_t>();
-    d.kf = ctx->b[B_KF].as<uint32_t>(); d.wrec = ctx->b[B_NK].as<uint4>(); d.errc = ctx->b[B_ERRC].as<uint8_t>();
+    d.kf = ctx->b[B_KF].as<uint32_t>(); d.wrec = ctx->b[B_NK].as<uint4>(); d.errc = ctx->b[B_ERRC].as<uint8_t>(); d.gq = ctx->b[B_GQ].as<uint16_t>();
 }
 
 // Once per dataset (pp_dataset_upload, pp_tok_finish): the alignments binned by position.  k_bin (record + 256-position bin key of
@@ -156,7 +156,7 @@ static int bin_dataset(pp_ctx* ctx, const std::function<int()>& seq_ready) {
     CK(ctx->b[B_KEY].ensure(na * 4)); CK(ctx->b[B_VAL].ensure(na * 4));
     CK(ctx->b[B_SKEY].ensure(na * 4)); CK(ctx->b[B_SVAL].ensure(na * 4));
     CK(ctx->b[B_BINSTART].ensure(((size_t)n_bins + 4) * 4));
-    CK(ctx->b[B_ERRC].ensure(na));
+    CK(ctx->b[B_ERRC].ensure(na)); CK(ctx->b[B_GQ].ensure(na * 2));
     CK(ctx->b[B_PARAMS].ensure(sizeof(DevParams) + 256 + sizeof(DevStatus)));
     size_t cub_bytes = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
