@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <cstddef>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -36,6 +37,8 @@ extern "C" void* pp_host_alloc(size_t bytes) {
 }
 extern "C" void pp_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+#define PP_INIT_IMAGE (64u << 10)     // the per-call reset block (statistics, status, options) travels as ONE small copy when it fits
+
 extern "C" int pp_create(int device, pp_ctx** out) {
     if (!out) return PP_ERR_ARG;
     *out = nullptr;
@@ -55,6 +58,7 @@ extern "C" int pp_create(int device, pp_ctx** out) {
     for (auto& ev : ctx->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     if (cudaHostAlloc((void**)&ctx->h_status, sizeof(DevStatus), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     if (cudaHostAlloc((void**)&ctx->h_params, sizeof(DevParams), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
+    if (cudaHostAlloc((void**)&ctx->h_init, PP_INIT_IMAGE, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
     uint8_t comp[256];
     init_comp_table(comp);
     if (cudaMemcpyToSymbol(c_comp, comp, 256) != cudaSuccess) { delete ctx; return PP_ERR_CUDA; }
@@ -71,6 +75,7 @@ extern "C" void pp_destroy(pp_ctx* ctx) {
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_params) cudaFreeHost(ctx->h_params);
+    if (ctx->h_init) cudaFreeHost(ctx->h_init);
     if (ctx->ev_small) cudaEventDestroy(ctx->ev_small);
     if (ctx->ev_seq) cudaEventDestroy(ctx->ev_seq);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -356,14 +361,16 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
     for (int attempt = 0; attempt < 8; ++attempt) {
         const uint32_t node_cap = ctx->node_cap;
         const uint64_t out_cap = ctx->out_cap;
-        // everything that must be zero at the start of a call lives in one pool: one memset (4 B per position of chain heads;
-        // the counters themselves live in shared memory)
+        // everything that must be zero at the start of a call lives in one small pool: one memset (the counters live in shared
+        // memory, and the 4 B per position of chain heads are zeroed tile by tile inside k_tile)
         size_t zoff = 0;
         auto carve = [&](size_t bytes) { size_t o = zoff; zoff += (bytes + 255) & ~size_t(255); return o; };
-        const size_t o_head = carve((G + 1) * 4), o_chg = carve((size_t)ctx->n_contigs * 8), o_zero = carve((size_t)ctx->n_contigs * 8),
+        const size_t o_chg = carve((size_t)ctx->n_contigs * 8), o_zero = carve((size_t)ctx->n_contigs * 8),
                      o_tdep = carve((size_t)ctx->n_contigs * 8), o_status = carve(sizeof(DevStatus)),
-                     o_k = carve(ctx->global_k ? (ctx->n_reads + 1) * 4 : 4);
+                     o_k = carve(ctx->global_k ? (ctx->n_reads + 1) * 4 : 4), o_prm = carve(sizeof(DevParams));
+        const bool one_copy = zoff <= PP_INIT_IMAGE;         // (not with thousands of contigs or the global-k fallback: then memsets)
         CK(ctx->b[B_ZEROPOOL].ensure(zoff));
+        CK(ctx->b[B_HEADS].ensure(padG * 4 + 64));
         uint8_t* zp = ctx->b[B_ZEROPOOL].as<uint8_t>();
         CK(ctx->b[B_NODES].ensure((size_t)node_cap * sizeof(OthNode)));
         CK(ctx->b[B_OUT].ensure(out_cap + 64));
@@ -371,16 +378,23 @@ static int run_polish(pp_ctx* ctx, const pp_polish_params* prm, pp_polish_result
         DevData d;
         fill_data(ctx, d);
         d.k = (uint32_t*)(zp + o_k);
-        d.oth_head = (uint32_t*)(zp + o_head); d.nodes = ctx->b[B_NODES].as<OthNode>(); d.node_cap = node_cap;
-        d.prm = ctx->b[B_PARAMS].as<DevParams>();
+        d.oth_head = ctx->b[B_HEADS].as<uint32_t>(); d.nodes = ctx->b[B_NODES].as<OthNode>(); d.node_cap = node_cap;
+        d.prm = one_copy ? (DevParams*)(zp + o_prm) : ctx->b[B_PARAMS].as<DevParams>();
         d.st = (DevStatus*)(zp + o_status);
         ctx->launches = 0;
 
         // ---- stage 0: reset
         CK(cudaEventRecord(ctx->ev[0], s));
-        CK(cudaMemcpyAsync(ctx->b[B_PARAMS].p, ctx->h_params, sizeof(DevParams), cudaMemcpyHostToDevice, s));
-        CK(cudaMemsetAsync(zp, 0, zoff, s));
-        CK(cudaMemsetAsync(&d.st->err, 0xFF, 8, s));
+        if (one_copy) {                                      // zeros, the options and "no error" in one host-to-device copy
+            memset(ctx->h_init, 0, zoff);
+            memcpy(ctx->h_init + o_prm, ctx->h_params, sizeof(DevParams));
+            memset(ctx->h_init + o_status + offsetof(DevStatus, err), 0xFF, 8);
+            CK(cudaMemcpyAsync(zp, ctx->h_init, zoff, cudaMemcpyHostToDevice, s));
+        } else {
+            CK(cudaMemcpyAsync(ctx->b[B_PARAMS].p, ctx->h_params, sizeof(DevParams), cudaMemcpyHostToDevice, s));
+            CK(cudaMemsetAsync(zp, 0, zoff, s));
+            CK(cudaMemsetAsync(&d.st->err, 0xFF, 8, s));
+        }
         // ---- stage 1: (fallback only) global k of multi-record groups
         CK(cudaEventRecord(ctx->ev[1], s));
         if (n_aln && ctx->global_k) {

@@ -29,7 +29,7 @@ struct DevBuf {
 };
 
 enum { B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CIGOFF, B_NCIG, B_NM, B_FLAGS, B_CIGOPS, B_SEQPOOL,
-       B_DRAFT, B_CTGOFF, B_ZEROPOOL, B_RECS, B_KEY, B_VAL, B_SKEY, B_SVAL, B_BINSTART, B_SREC, B_SSEQ, B_KF, B_NK, B_TILEORDER, B_ERRC, B_GQ, B_NODES, B_CUBTMP, B_SEQ2, B_OUT,
+       B_DRAFT, B_CTGOFF, B_ZEROPOOL, B_RECS, B_KEY, B_VAL, B_SKEY, B_SVAL, B_BINSTART, B_SREC, B_SSEQ, B_KF, B_NK, B_TILEORDER, B_ERRC, B_GQ, B_HEADS, B_NODES, B_CUBTMP, B_SEQ2, B_OUT,
        B_OUTOFF, B_DEBUG, B_RES, B_RECAT, B_CHUNKDELTA, B_PARAMS, B_SCRATCH, B_SCRATCH2,
        B_TOKLINE, B_TOKTMP, B_TOKNAMES, B_COUNT };
 
@@ -43,6 +43,7 @@ struct pp_ctx {
     cudaEvent_t ev[PP_N_STAGES + 4] = {};
     DevStatus* h_status = nullptr;        // pinned
     DevParams* h_params = nullptr;        // pinned
+    uint8_t* h_init = nullptr;            // pinned image of the per-call reset block (run_polish)
     bool have_ds = false;
     // dataset facts
     uint64_t n_aln = 0, n_reads = 0, n_ops = 0, seq_bytes = 0, G = 0;

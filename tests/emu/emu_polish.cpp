@@ -40,7 +40,7 @@ int run(const pp_contigs* c, const pp_alignments* a, const pp_polish_params* prm
     std::vector<uint4> sseq((n_aln + 16) * TL_SEQ_QUADS + 16, make_uint4(0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu, 0xCDCDCDCDu));
     std::vector<uint8_t> errc(n_aln + 16, 0xEE);
     std::vector<uint16_t> gq(n_aln + 16, 0xEEEE);
-    std::vector<uint32_t> oth_head(G + 1, 0), kcount(a->n_reads + 2, 0);
+    std::vector<uint32_t> oth_head(((size_t)(G + TL_T - 1) / TL_T) * TL_T + 16, 0xEEEEEEEEu), kcount(a->n_reads + 2, 0);   // (k_tile zeroes the heads itself)
     std::vector<OthNode> nodes(std::max<uint64_t>(1 << 16, n_aln * 4 + G));
     std::vector<unsigned long long> changed(c->n_contigs, 0), zero(c->n_contigs, 0), out_off(c->n_contigs + 1, 0);
     std::vector<double> tdepth(c->n_contigs, 0.0);
