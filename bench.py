@@ -250,7 +250,8 @@ def main():
     hv = api.Alignments()
     C.memmove(C.byref(hv), C.byref(wire_view), C.sizeof(api.Alignments))
     for name in wire_names:
-        setattr(hv, name, pin(wire[name]))
+        if getattr(wire_view, name) or name == "esc_pool":      # (cigar_off / read_id stay null in the 2-bit format: the device rebuilds them)
+            setattr(hv, name, pin(wire[name]))
     h2d_bytes = sum(wire[n].nbytes for n in wire_names) + G + 8 * (n_c + 1)
     h2d_bytes_4bit = sum(arrs[n].nbytes for n in wire_names if n in arrs) + G + 8 * (n_c + 1)
 
@@ -420,7 +421,7 @@ def main():
                        "cache": "inputs (%.0f MB packed) larger than the 126 MB L2" % (h2d_bytes / 1e6)},
             "e2e": {"value": total_bp / 1e6 / (e2e_ms_max / 1e3), "unit": "Mbp/s", "ms_per_step": e2e_ms_max,
                     "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total), "api": "pp_polish (host SoA in, host bases out)",
-                    "wire": ("2-bit read bases (pp_alignments_to_2bit once per batch, outside the timed region like the packing; %d B/step as 4-bit)" % h2d_bytes_4bit
+                    "wire": ("2-bit read bases, cigar_off and read_id rebuilt on the device (pp_alignments_to_2bit once per batch, outside the timed region like the packing; %d B/step as 4-bit)" % h2d_bytes_4bit
                              if two_bit else "%d-bit read bases" % aview.seq_bits),
                     "ms_per_step_median_rank0": round(e2e_median, 3),     # (a shared box can stall single H2D copies; the value above is the mean)
                     "last_step_ms": {k: round(v, 3) for k, v in e["timing"].items() if k.endswith("_ms") and v}},   # h2d = upload + position binning

@@ -55,6 +55,8 @@ void pp_host_free(void* p);
                                 adds nothing to the pileup (contig sharding, pp_shards_build) */
 #define PP_FLAG_ESC     0x40 /* seq_bits == 2 only: the sequence has a base other than A, C, G, T and lives in esc_pool (4-bit
                                 codes); seq_off then counts esc_pool blocks */
+#define PP_FLAG_NEWGROUP 0x80 /* seq_bits == 2 only, and only where read_id == NULL: the first record of a read group (read_id is then
+                                 rebuilt on the device as the number of such records so far, minus one) */
 
 /* CIGAR op codes in cigar_ops (BAM numbering): len << 4 | op.  Zero-length ops are dropped by the packer
  * (they contribute nothing to the expanded CIGAR of alignment.rs:325-346). */
@@ -91,7 +93,9 @@ typedef struct {
                                 2: the wire format of pp_alignments_to_2bit - A,C,G,T = 0..3, 4 per byte, low bits
                                 first, 8 bytes per PP_SEQ_BLOCK (same block numbering as the 4-bit pool); sequences
                                 with any other base are PP_FLAG_ESC records in esc_pool.  Expanded to 4-bit on the
-                                device right after the upload: 38 % fewer bytes cross PCIe                       */
+                                device right after the upload: 38 % fewer bytes cross PCIe.  In this format two arrays
+                                may be NULL because the device can rebuild them: cigar_off (= exclusive prefix sums of
+                                n_cigar, when the ops lie in record order without gaps) and read_id (PP_FLAG_NEWGROUP) */
   uint64_t seq_pool_bytes;
   const uint8_t* seq_pool;   /* 16-byte aligned                                                               */
   uint64_t esc_pool_bytes;   /* seq_bits == 2: 4-bit sequences of the PP_FLAG_ESC records (else 0 / NULL)        */

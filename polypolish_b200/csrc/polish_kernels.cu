@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <functional>
@@ -244,6 +245,18 @@ __global__ void k_expand2(const uint2* __restrict__ in, uint4* __restrict__ out,
         out[i] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
     }
 }
+// seq_bits == 2 uploads may leave cigar_off / read_id at home (pp_abi.h): prefix sums on the device.
+__global__ void k_scan_inputs(const uint16_t* __restrict__ n_cigar, const uint8_t* __restrict__ flags, uint32_t* __restrict__ cigar_off,
+                              uint32_t* __restrict__ read_id, uint64_t n) {         // (null = that array came with the batch)
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (cigar_off) cigar_off[i] = n_cigar[i];
+        if (read_id) read_id[i] = (flags[i] >> 7) & 1u;
+    }
+}
+__global__ void k_ids_from_scan(uint32_t* __restrict__ read_id, uint64_t n) {      // inclusive count of group starts -> dense group id
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) read_id[i] -= 1u;
+}
+
 // PP_FLAG_ESC records: their sequences sit behind the expanded pool.
 __global__ void k_esc_offsets(uint32_t* __restrict__ seq_off, const uint8_t* __restrict__ flags, uint64_t n_aln, uint32_t first_esc_block) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_aln; i += (uint64_t)gridDim.x * blockDim.x)
@@ -273,7 +286,8 @@ static int commit_dataset(pp_ctx* ctx, uint64_t n_aln, uint64_t n_reads, uint64_
 extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alignments* a) {
     if (!ctx) return PP_ERR_ARG;
     if (!c || !a || !c->off || !c->bases || c->n_contigs == 0) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: null or empty contigs");
-    if (a->n_aln && (!a->contig || !a->ref_start || !a->read_id || !a->seq_off || !a->seq_len || !a->cigar_off ||
+    const bool derive_ok = a->seq_bits == 2;                      // (the 2-bit wire format may leave cigar_off / read_id to the device)
+    if (a->n_aln && (!a->contig || !a->ref_start || (!a->read_id && !derive_ok) || !a->seq_off || !a->seq_len || (!a->cigar_off && !derive_ok) ||
                      !a->n_cigar || !a->nm || !a->flags || !a->cigar_ops))
         return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: null alignment array");
     if (a->seq_bits != 4 && a->seq_bits != 8 && a->seq_bits != 2) return ctx->fail(PP_ERR_ARG, "pp_dataset_upload: seq_bits must be 4, 8 or 2");
@@ -287,14 +301,31 @@ extern "C" int pp_dataset_upload(pp_ctx* ctx, const pp_contigs* c, const pp_alig
     int rc;
     if ((rc = upload(ctx, B_CONTIG, a->contig, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_REFSTART, a->ref_start, a->n_aln))) return rc;
-    if ((rc = upload(ctx, B_READID, a->read_id, a->n_aln))) return rc;
+    if (a->read_id) { if ((rc = upload(ctx, B_READID, a->read_id, a->n_aln))) return rc; }
+    else CK(ctx->b[B_READID].ensure((size_t)a->n_aln * 4 + 64));
     if ((rc = upload(ctx, B_SEQOFF, a->seq_off, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_SEQLEN, a->seq_len, a->n_aln))) return rc;
-    if ((rc = upload(ctx, B_CIGOFF, a->cigar_off, a->n_aln))) return rc;
+    if (a->cigar_off) { if ((rc = upload(ctx, B_CIGOFF, a->cigar_off, a->n_aln))) return rc; }
+    else CK(ctx->b[B_CIGOFF].ensure((size_t)a->n_aln * 4 + 64));
     if ((rc = upload(ctx, B_NCIG, a->n_cigar, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_NM, a->nm, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_FLAGS, a->flags, a->n_aln))) return rc;
     if ((rc = upload(ctx, B_CIGOPS, a->cigar_ops, a->n_cigar_ops))) return rc;
+    if (a->n_aln && (!a->cigar_off || !a->read_id)) {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((a->n_aln + 255) / 256, (uint64_t)ctx->sm_count * 32);
+        uint32_t* co = a->cigar_off ? nullptr : ctx->b[B_CIGOFF].as<uint32_t>();
+        uint32_t* ri = a->read_id ? nullptr : ctx->b[B_READID].as<uint32_t>();
+        k_scan_inputs<<<grid, 256, 0, ctx->stream>>>(ctx->b[B_NCIG].as<uint16_t>(), ctx->b[B_FLAGS].as<uint8_t>(), co, ri, a->n_aln);
+        size_t tb = 0;
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)a->n_aln, ctx->stream));
+        CK(ctx->b[B_CUBTMP].ensure(tb + 256));
+        if (co) { tb = ctx->b[B_CUBTMP].cap; CK(cub::DeviceScan::ExclusiveSum(ctx->b[B_CUBTMP].p, tb, co, co, (int64_t)a->n_aln, ctx->stream)); }
+        if (ri) {
+            tb = ctx->b[B_CUBTMP].cap;
+            CK(cub::DeviceScan::InclusiveSum(ctx->b[B_CUBTMP].p, tb, ri, ri, (int64_t)a->n_aln, ctx->stream));
+            k_ids_from_scan<<<grid, 256, 0, ctx->stream>>>(ri, a->n_aln);
+        }
+    }
     if ((rc = pp_ctx_upload_contigs(ctx, c))) { ctx->err = "pp_dataset_upload: " + ctx->err; return rc; }
     // The sequence pool - two thirds of the bytes - goes last, on its own stream: the binning of the records (k_bin, the sort, k_permute)
     // needs none of it and runs while it crosses PCIe; the stream joins right before k_permute_seq.

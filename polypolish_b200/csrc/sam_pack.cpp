@@ -618,7 +618,24 @@ extern "C" int pp_alignments_to_2bit(const pp_alignments* in, pp_alignments* out
             auto it = esc_at.find(in->seq_off[i]);
             if (it != esc_at.end()) { W->flags[i] |= PP_FLAG_ESC; W->seq_off[i] = it->second; }
         }
+    // Two arrays the device can rebuild stay at home when they are what the packer makes them: CIGAR ops in record order without
+    // gaps (cigar_off = prefix sums of n_cigar) and dense group ids (read_id = number of group starts so far - 1).
+    bool dense_ops = true, dense_ids = n == 0 || in->read_id[0] == 0;
+    {
+        uint64_t at = 0;
+        for (uint64_t i = 0; i < n && (dense_ops || dense_ids); ++i) {
+            if (in->cigar_off[i] != at) dense_ops = false;
+            at += in->n_cigar[i];
+            if (i && in->read_id[i] != in->read_id[i - 1] && in->read_id[i] != in->read_id[i - 1] + 1) dense_ids = false;
+        }
+        if (at != in->n_cigar_ops) dense_ops = false;
+    }
+    if (dense_ids)
+        for (uint64_t i = 0; i < n; ++i)
+            if (i == 0 || in->read_id[i] != in->read_id[i - 1]) W->flags[i] |= PP_FLAG_NEWGROUP;
     *out = *in;
+    if (dense_ops) out->cigar_off = nullptr;
+    if (dense_ids) out->read_id = nullptr;
     out->flags = W->flags.data();
     out->seq_off = W->seq_off.data();
     out->seq_bits = 2;

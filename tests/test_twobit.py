@@ -8,7 +8,7 @@ from polypolish_b200 import api
 from tests import fuzzgen
 
 NIB = "=ACMGRSVTWYHKDBN"
-PP_FLAG_SEQSTAR, PP_FLAG_NOSEQ, PP_FLAG_ESC = 0x04, 0x10, 0x40
+PP_FLAG_SEQSTAR, PP_FLAG_NOSEQ, PP_FLAG_ESC, PP_FLAG_NEWGROUP = 0x04, 0x10, 0x40, 0x80
 
 
 def _flag_values():
@@ -19,7 +19,7 @@ def _flag_values():
 
 def test_flag_constants_match_the_header():
     f = _flag_values()
-    assert (f["SEQSTAR"], f["NOSEQ"], f["ESC"]) == (PP_FLAG_SEQSTAR, PP_FLAG_NOSEQ, PP_FLAG_ESC)
+    assert (f["SEQSTAR"], f["NOSEQ"], f["ESC"], f["NEWGROUP"]) == (PP_FLAG_SEQSTAR, PP_FLAG_NOSEQ, PP_FLAG_ESC, PP_FLAG_NEWGROUP)
 
 
 def _seq4(pool, off, n):
@@ -40,7 +40,7 @@ def _check_roundtrip(p):
     n_esc = 0
     for i in range(p.view.n_aln):
         fl = int(src["flags"][i])
-        assert int(two["flags"][i]) & ~PP_FLAG_ESC == fl
+        assert int(two["flags"][i]) & ~(PP_FLAG_ESC | PP_FLAG_NEWGROUP) == fl
         if fl & PP_FLAG_NOSEQ:
             assert not int(two["flags"][i]) & PP_FLAG_ESC
             continue
@@ -54,6 +54,18 @@ def _check_roundtrip(p):
             assert not set(want) - set("ACGT")
             assert two["seq_off"][i] == src["seq_off"][i]
             assert _seq2(two["seq_pool"], int(two["seq_off"][i]), n) == want
+    # the two arrays the device rebuilds: left out exactly when they are what the packer makes them, and then recoverable
+    n = p.view.n_aln
+    if not tb.view.cigar_off:
+        assert list(np.concatenate(([0], np.cumsum(src["n_cigar"].astype(np.int64))[:-1]))) == list(src["cigar_off"]) if n else True
+    else:
+        assert list(two["cigar_off"]) == list(src["cigar_off"])
+    if not tb.view.read_id:
+        starts = (two["flags"].astype(np.int64) >> 7) & 1
+        assert list(np.cumsum(starts) - 1) == list(src["read_id"])
+    else:
+        assert list(two["read_id"]) == list(src["read_id"]) and not (two["flags"] & PP_FLAG_NEWGROUP).any()
+    assert (not tb.view.cigar_off) and (not tb.view.read_id)        # (the host packer's batches always qualify)
     # untouched arrays are shared, not copied
     assert tb.view.contig == p.view.contig and tb.view.cigar_ops == p.view.cigar_ops
     tb.close()
