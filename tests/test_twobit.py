@@ -180,3 +180,19 @@ def test_two_bit_argument_errors(ctx, tmp_path):
     with pytest.raises(Exception):
         api.Shards(f.view, tb.view, 2)
     tb.close()
+
+
+def test_sharded_batches_convert_too():
+    """What bench.py --gpus N puts on the wire: a contig shard (ghost records included) in the 2-bit format, both rebuilt arrays left out."""
+    syn = api.Synth(seed=5, n_contigs=4, contig_len=20_000, depth=30, cross_contig=0.05)
+    f = syn.fasta()
+    p = syn.pack(f)
+    sh = api.Shards(f.view, p.view, 2)
+    for s in range(2):
+        c, a, cmap, n_home = sh.get(s)
+        tb = api.TwoBit(a)
+        two, src = api.view_arrays(tb.view), api.view_arrays(a)
+        assert not tb.view.cigar_off and not tb.view.read_id
+        assert list(np.cumsum((two["flags"].astype(np.int64) >> 7) & 1) - 1) == list(src["read_id"])
+        assert list(np.concatenate(([0], np.cumsum(src["n_cigar"].astype(np.int64))[:-1]))) == list(src["cigar_off"])
+        tb.close()
