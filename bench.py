@@ -9,9 +9,12 @@ synthetic workload (default: BASELINE configs[1], one 5 Mbp contig at 100x, mult
   e2e        the same metric through the reference-facing C-ABI call with HOST buffers (pp_polish): pinned-host
              H2D of the packed alignments and D2H of the polished bases inside the timed region
   roofline   the dominant kernel (k_tile: CIGAR walk + pileup + ordered depth + vote): algorithmic bytes / CUDA-event duration vs the measured HBM peak
-  cpu_baseline  the CPU oracle (C++ restatement of the reference, 1 thread) on a bounded slice of the workload
-With N > 1 (torchrun, one rank per GPU) contigs shard across ranks with no collective on the data path: every
-rank polishes its own 5 Mbp contig (weak scaling); time = max over ranks.
+  t3 / cli   the whole command from SAM text (pp_polish_files in a resident process / a fresh build/polypolish process)
+  cpu_baseline  the CPU oracle (C++ restatement of the reference, 1 thread) on the same SAM text files (the whole
+             workload when that is bounded - 5 Mbp x 100x: ~15 s - else a slice); `parity` compares its FASTA with the GPU's
+With N > 1 (torchrun, one rank per GPU) the contigs of ONE config-5-shaped assembly (6.25 N contigs of 5 Mbp, repeat
+families that cross contigs) shard across the ranks with no collective on the data path: every rank polishes its
+shard, ghost records included (weak scaling); time = max over ranks.
 --impl reference times the reference's CPU path (the oracle; the Rust reference cannot be built here) on rank 0.
 """
 import argparse
