@@ -297,11 +297,22 @@ int pp_tok_finish(pp_ctx* ctx);        /* the tokenised alignments + the assembl
  * become PP_FLAG_GHOST records (they still count for goodness / k / --careful, exactly like pp_shards_build's), the others are
  * renumbered, and shard_contigs replaces the assembly as the resident draft.  takes_unknown: the one shard that keeps records whose
  * RNAME is not in the assembly, so that the reference's error is raised once.  The arrays are copied during the call. */
+int pp_tok_set_shard(pp_ctx* ctx, const uint32_t* local_of, uint32_t n_contigs_total, const pp_contigs* shard_contigs, int takes_unknown);
 /* n byte ranges of a SAM file for n GPUs: cuts[0] = 0, cuts[n] = the file size, every other cut is the start of a line whose QNAME
  * differs from the line before it, so that no read group (alignment.rs:214-272) is split.  PP_ERR_IO: not a plain file / a line longer
  * than 1 MiB.  (pp_polish_files_multi gives range g of every file to GPU g, then the GPUs exchange read groups by contig.) */
 int pp_sam_split_ranges(const char* path, int n, uint64_t* cuts /* [n + 1] */);
-int pp_tok_set_shard(pp_ctx* ctx, const uint32_t* local_of, uint32_t n_contigs_total, const pp_contigs* shard_contigs, int takes_unknown);
+/* Multi-GPU ingestion, the building blocks of pp_polish_files_multi (polish.rs:109-134 load_alignments over N GPUs).  Per context g:
+ *   pp_tok_begin -> pp_tok_set_ranges(off, len, n_files): this context reads only bytes [off[f], off[f] + len[f]) of file f
+ *   (range g of pp_sam_split_ranges) -> pp_tok_add_files(the same n_files paths on every context).
+ * Then ONE call for all contexts, instead of pp_tok_finish: pp_tok_exchange_finish hands every read group, whole, to each GPU that
+ * owns a contig one of its records lies on (owner[c] = context of contig c, local_of[g][c] = index of contig c inside
+ * shard_contigs[g] or 0xFFFFFFFF; peer copies on the device, global SAM order = (file, range, line)), marks the foreign records
+ * PP_FLAG_GHOST, installs shard_contigs[g] as context g's draft and bins: every context is then ready for pp_polish_resident.
+ * PP_TOK_HOST: more than 32 contexts / 64 files, or something the host path must look at.  n_aln_total = aligned records read. */
+int pp_tok_set_ranges(pp_ctx* ctx, const uint64_t* off, const uint64_t* len, int n_files);
+int pp_tok_exchange_finish(pp_ctx* const* ctxs, int n_ctx, const uint32_t* owner, uint32_t n_contigs_total, const uint32_t* const* local_of,
+                           const pp_contigs* shard_contigs /* [n_ctx] */, uint64_t* n_aln_total);
 /* Which parser pp_polish_files uses for its SAM files: 0 (default) the device tokeniser, with the host packer taking over
  * on PP_TOK_HOST and for --debug / multi-GPU runs; 1 the host packer only.  Both give the same bytes. */
 int pp_set_parser(pp_ctx* ctx, int mode);
@@ -335,11 +346,12 @@ void pp_shards_free(pp_shards* s);
  * reference's polish::polish (polish.rs:26-38) and filter::filter (filter.rs:26-37)).
  * out_fasta receives exactly what the reference prints to stdout; free with pp_free.
  * pp_polish_files parses its SAM files with the device tokeniser (pp_tok_*) unless pp_set_parser(ctx, 1), a --debug run, or
- * PP_TOK_HOST / a data error send it through pp_pack_*; with several contexts the text is tokenised on ctxs[0]. */
+ * PP_TOK_HOST / a data error send it through pp_pack_*. */
 int pp_polish_files(pp_ctx* ctx, const char* assembly, const char* const* sams, int n_sams,
                     const pp_polish_params* params, const char* debug_path, char** out_fasta,
                     uint64_t* out_len, int verbose /* 1: reference-style log on stderr */);
-/* the same command over several GPUs of one box: contigs shard across ctxs[0..n_ctx) (one host thread per GPU) */
+/* the same command over several GPUs of one box: contigs shard across ctxs[0..n_ctx) (one host thread per GPU); every GPU tokenises
+ * its byte range of every SAM file and the read groups change GPUs on the device (pp_tok_set_ranges / pp_tok_exchange_finish) */
 int pp_polish_files_multi(pp_ctx* const* ctxs, int n_ctx, const char* assembly, const char* const* sams, int n_sams,
                           const pp_polish_params* params, const char* debug_path, char** out_fasta,
                           uint64_t* out_len, int verbose);

@@ -254,7 +254,10 @@ __global__ void k_scan_inputs(const uint16_t* __restrict__ n_cigar, const uint8_
     }
 }
 __global__ void k_ids_from_scan(uint32_t* __restrict__ read_id, uint64_t n) {      // inclusive count of group starts -> dense group id
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) read_id[i] -= 1u;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = read_id[i];
+        read_id[i] = v ? v - 1u : 0u;       // (records before the first PP_FLAG_NEWGROUP - a batch the packer did not make - join group 0: never an id of -1)
+    }
 }
 
 // PP_FLAG_ESC records: their sequences sit behind the expanded pool.

@@ -114,9 +114,5 @@ struct pp_fused_polish {
     uint64_t n_aln;
     int rc;                // PP_OK: the filtered alignments are the resident dataset; PP_TOK_HOST: the host text path must do it
 };
-// multi-GPU ingestion (tok_kernels.cu): byte ranges of the files per context, then the device-side exchange of read groups
-extern "C" int pp_tok_set_ranges(pp_ctx* ctx, const uint64_t* off, const uint64_t* len, int n);
-extern "C" int pp_tok_exchange_finish(pp_ctx* const* ctxs, int n_ctx, const uint32_t* owner, uint32_t n_total, const uint32_t* const* local_of,
-                                      const pp_contigs* shard_contigs, uint64_t* n_aln_total);
 int pp_filter_files_device(pp_ctx* ctx, const char* in1, const char* in2, const char* out1, const char* out2, const pp_filter_params* prm,
                            pp_filter_result* res, pp_filter_file_stats* fs, pp_fused_polish* fuse);

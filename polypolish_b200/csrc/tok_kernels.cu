@@ -1008,7 +1008,8 @@ const int X_BUFS[11] = {B_CONTIG, B_REFSTART, B_READID, B_SEQOFF, B_SEQLEN, B_CI
 
 extern "C" int pp_tok_exchange_finish(pp_ctx* const* ctxs, int n_ctx, const uint32_t* owner, uint32_t n_total, const uint32_t* const* local_of,
                                       const pp_contigs* shard_contigs, uint64_t* n_aln_total) {
-    if (!ctxs || n_ctx < 1 || n_ctx > 32 || !owner || !local_of || !shard_contigs) return PP_ERR_ARG;
+    if (!ctxs || n_ctx < 1 || !owner || !local_of || !shard_contigs) return PP_ERR_ARG;
+    if (n_ctx > 32) return PP_TOK_HOST;                                                // (one bit per destination in a group's mask: the host sharder takes over)
     pp_ctx* c0 = ctxs[0];
     int rc = PP_OK;
     std::vector<XSource*> src((size_t)n_ctx, nullptr);

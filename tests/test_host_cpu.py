@@ -29,6 +29,12 @@ def test_abi_symbols_exported():
     L = pp.lib()
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
+    # ... and the other way round: no C-linkage pp_* entry point that the header does not declare
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", pp.lib()._name], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[2] for ln in out.splitlines() if len(ln.split()) == 3 and ln.split()[1] == "T" and ln.split()[2].startswith("pp_")})
+    undeclared = [n for n in exported if n not in names]
+    assert not undeclared, undeclared
 
 
 def test_no_cpu_fallback():
