@@ -220,6 +220,7 @@ def main():
         assign = [c % world for c in range(n_total)]
         syn = api.Synth(seed=5, n_contigs=n_total, contig_len=clen, depth=depth, cross_contig=0.01)
         syn.set_shard_filter(world, rank, assign)
+        syn.set_threads(max(1, min(16, (os.cpu_count() or 8) // world)))     # (setup only: the same bytes whatever the count)
         fasta = syn.fasta()
         packed = syn.pack(fasta)
         shards = api.Shards(fasta.view, packed.view, world, shard_of_contig=assign, only_shard=rank)

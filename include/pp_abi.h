@@ -396,6 +396,9 @@ pp_synth* pp_synth_create_shared(const pp_synth_params* prm, double cross_contig
  * record, what pp_shards_build_assigned gives that shard from the whole data set - a rank of an N-GPU run can build its share of
  * BASELINE config 5 without generating the other ranks' reads. */
 int pp_synth_set_shard_filter(pp_synth* s, uint32_t n_shards, uint32_t shard, const uint32_t* shard_of_contig);
+/* worker threads of pp_synth_write_sam / pp_synth_feed_pack for data sets with per-pair streams (pp_synth_create_shared with a
+ * cross-contig fraction > 0); 0 = one per hardware thread.  The bytes produced do not depend on it. */
+int pp_synth_set_threads(pp_synth* s, uint32_t n_threads);
 void pp_synth_free(pp_synth* s);
 uint64_t pp_synth_total_bp(const pp_synth* s);    /* draft bases */
 uint64_t pp_synth_n_pairs(const pp_synth* s);

@@ -559,6 +559,12 @@ class Synth:
         if rc != PP_OK:
             raise PolypolishError(rc, "pp_synth_set_shard_filter: needs a cross-contig data set and shard < n_shards")
 
+    def set_threads(self, n_threads):
+        """Generator threads (cross-contig data sets only; same bytes whatever the count).  0 = one per hardware thread."""
+        L = lib()
+        L.pp_synth_set_threads.argtypes = [C.c_void_p, C.c_uint32]
+        L.pp_synth_set_threads(self.h, int(n_threads))
+
     def write(self, directory):
         """draft FASTA + one SAM per mate; returns (fasta, [sam1, sam2])."""
         d = str(directory)

@@ -226,3 +226,21 @@ def test_filtered_generation_equals_the_sharders_shard(built):
     assert total_home == full.view.n_aln
     syn.set_shard_filter(0, 0)
     assert syn.pack(f).view.n_aln == full.view.n_aln
+
+
+def test_threaded_generation_gives_the_same_bytes(built, tmp_path):
+    """pp_synth_set_threads (bench.py --gpus N uses it to shorten its setup): blocks of pairs generated by worker threads and
+    emitted in pair order are byte for byte the sequential generator's text, with and without the shard filter."""
+    import hashlib
+
+    def digests(threads, filt):
+        syn = api.Synth(seed=9, n_contigs=5, contig_len=30_000, depth=40, cross_contig=0.05)
+        if filt:
+            syn.set_shard_filter(2, 1, [c % 2 for c in range(5)])
+        syn.set_threads(threads)
+        fa, sams = syn.write(str(tmp_path))
+        out = [hashlib.sha256(open(p, "rb").read()).hexdigest() for p in sams]
+        syn.close()
+        return out
+    for filt in (False, True):
+        assert digests(1, filt) == digests(3, filt) == digests(0, filt)
