@@ -138,6 +138,8 @@ def run_reference(args, rank, world):
     import shutil
     from polypolish_b200 import api
     n_c, clen, depth, same = reference_sample(args.workload)
+    if world > 1:
+        same = False         # the b200 arm's N > 1 workload is 6.25 N such contigs (config 5): one of them is the bounded CPU sample
     d = _shm_dir("pp_ref_", 6)
     try:
         syn = api.Synth(seed=2, n_contigs=n_c, contig_len=clen, depth=depth)
@@ -153,7 +155,8 @@ def run_reference(args, rank, world):
         shutil.rmtree(d, ignore_errors=True)
     v = sum(x[0] for x in vals) / len(vals)
     ms = 1e3 * sum(x[1] for x in vals) / len(vals)
-    sample = f"{bp} bp x {depth:g}x ({'the whole workload' if same else 'a slice of the workload'}), whole `polish` command on page-cache-warm SAM text"
+    what = "the whole workload" if same else ("one contig of the %d-GPU workload's %d" % (world, (25 * world) // 4) if world > 1 else "a slice of the workload")
+    sample = f"{bp} bp x {depth:g}x ({what}), whole `polish` command on page-cache-warm SAM text"
     line = {"metric": METRIC, "value": v, "unit": "Mbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 counters, f64 depth",
             "data": "synthetic", "impl": "reference",
