@@ -593,24 +593,64 @@ extern "C" int pp_alignments_to_2bit(const pp_alignments* in, pp_alignments* out
     W->pool2.resize_zero(n_blocks * 8 + 64);
     std::unordered_map<uint32_t, uint32_t> esc_at;                 // 4-bit block offset of an escaped sequence -> its esc_pool block
     uint64_t esc_blocks = 0;
-    static const uint8_t two[16] = {0xFF, 0, 1, 0xFF, 2, 0xFF, 0xFF, 0xFF, 3, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF};   // A=1 C=2 G=4 T=8
-    for (uint64_t i = 0; i < n; ++i) {
-        const uint8_t fl = in->flags[i];
-        if (fl & (PP_FLAG_SEQSTAR | PP_FLAG_NOSEQ)) continue;       // shares its group's sequence / has none
-        const uint32_t off = in->seq_off[i], len = in->seq_len[i];
-        const uint8_t* src = in->seq_pool + (size_t)off * 16;
-        uint8_t* dst = W->pool2.p + (size_t)off * 8;
-        bool plain = true;
-        for (uint32_t b = 0; b < len && plain; ++b) plain = two[(src[b >> 1] >> ((b & 1) * 4)) & 15] != 0xFF;
-        if (plain) {
-            for (uint32_t b = 0; b < len; ++b) dst[b >> 2] |= (uint8_t)(two[(src[b >> 1] >> ((b & 1) * 4)) & 15] << ((b & 3) * 2));
-        } else {
-            const uint64_t blocks = ((uint64_t)len + PP_SEQ_BLOCK - 1) / PP_SEQ_BLOCK;
-            W->esc.resize_zero((esc_blocks + blocks) * 16);
-            memcpy(W->esc.p + esc_blocks * 16, src, blocks * 16);
-            esc_at.emplace(off, (uint32_t)esc_blocks);
-            esc_blocks += blocks;
+    // 16 one-hot BAM nibbles (A=1 C=2 G=4 T=8) of one 64-bit word -> 16 two-bit codes (A=0 C=1 G=2 T=3) in 32 bits, word-parallel:
+    // code bit 0 = the nibble is C or T (its bits 1 | 3), code bit 1 = G or T (bits 2 | 3); `count` nibbles from the bottom count, the
+    // rest (padding past the read's end) must come out as zero.  *ok turns false on a nibble that is not exactly one of the four.
+    auto pack16 = [](uint64_t x, uint32_t count, bool* ok) -> uint32_t {
+        const uint64_t one = 0x1111111111111111ull;
+        const uint64_t keep = count >= 16 ? ~0ull : ((1ull << (4 * count)) - 1ull);
+        x &= keep;
+        const uint64_t a = x & one, c = (x >> 1) & one, g = (x >> 2) & one, t = (x >> 3) & one;
+        if ((a + c + g + t) != (one & keep)) *ok = false;             // per nibble: exactly one bit set (sums stay below 16: no carries)
+        uint64_t y = (c | t) | ((g | t) << 1);                         // the code of base i in bits 4i, 4i + 1
+        y = (y | (y >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+        y = (y | (y >> 4)) & 0x00FF00FF00FF00FFull;
+        y = (y | (y >> 8)) & 0x0000FFFF0000FFFFull;
+        y = (y | (y >> 16)) & 0x00000000FFFFFFFFull;
+        return (uint32_t)y;
+    };
+    // pass 1, in parallel over ranges of records: every sequence of A/C/G/T only is converted where it stands (a read's blocks are its
+    // own); the others are only marked - their order in esc_pool is record order, settled by the sequential pass below
+    std::vector<uint8_t> escaped((size_t)n, 0);
+    auto convert = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            const uint8_t fl = in->flags[i];
+            if (fl & (PP_FLAG_SEQSTAR | PP_FLAG_NOSEQ)) continue;   // shares its group's sequence / has none
+            const uint32_t off = in->seq_off[i], len = in->seq_len[i];
+            const uint8_t* src = in->seq_pool + (size_t)off * 16;
+            uint8_t* dst = W->pool2.p + (size_t)off * 8;
+            bool plain = true;
+            const uint32_t words = (len + 15) / 16;
+            for (uint32_t w = 0; w < words; ++w) {
+                uint64_t x;
+                memcpy(&x, src + 8 * (size_t)w, 8);                 // (little-endian hosts: base j of the word in bits 4j)
+                const uint32_t v = pack16(x, std::min<uint32_t>(16, len - 16 * w), &plain);
+                memcpy(dst + 4 * (size_t)w, &v, 4);
+            }
+            if (!plain) {
+                escaped[(size_t)i] = 1;
+                memset(dst, 0, (size_t)((len + PP_SEQ_BLOCK - 1) / PP_SEQ_BLOCK) * 8);   // nothing reads these blocks; keep them zero
+            }
         }
+    };
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned nt = (unsigned)std::min<uint64_t>(std::min(16u, hw), n / 65536 + 1);
+        if (nt <= 1) convert(0, n);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back(convert, n * t / nt, n * (t + 1) / nt);
+            for (auto& t : th) t.join();
+        }
+    }
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!escaped[(size_t)i]) continue;
+        const uint32_t off = in->seq_off[i], len = in->seq_len[i];
+        const uint64_t blocks = ((uint64_t)len + PP_SEQ_BLOCK - 1) / PP_SEQ_BLOCK;
+        W->esc.resize_zero((esc_blocks + blocks) * 16);
+        memcpy(W->esc.p + esc_blocks * 16, in->seq_pool + (size_t)off * 16, blocks * 16);
+        esc_at.emplace(off, (uint32_t)esc_blocks);
+        esc_blocks += blocks;
     }
     if (!esc_at.empty())
         for (uint64_t i = 0; i < n; ++i) {
