@@ -7,6 +7,10 @@
 //   get_read_seq_from_alignments :311-322 and add_read_seq :161-167 (source sequence of SEQ="*" records)
 // Everything downstream (goodness, k, CIGAR walk, trim, pileup, vote) happens on the device.
 #include <algorithm>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <thread>
@@ -354,6 +358,16 @@ int pack_text_parallel(pp_pack* P, const char* data, size_t n, const std::string
         for (size_t c = 0; c < nc; ++c) th.emplace_back([&, c] {
             ChunkOut& o = out[c];
             o.tmp.fasta = P->fasta; o.tmp.careful = P->careful; o.tmp.seq_bits = P->seq_bits;
+            {   // every array sized once from the chunk's line count: growing them by reallocation means mmap / munmap calls that
+                // serialise the threads on the process's address-space lock (measured: 8 threads no faster than one)
+                pp_pack& t = o.tmp;
+                const size_t nl = (size_t)o.n_lines + 1, bytes = cut[c + 1] - cut[c];
+                t.contig.reserve(nl); t.ref_start.reserve(nl); t.read_id.reserve(nl); t.seq_off.reserve(nl); t.cigar_off.reserve(nl);
+                t.nm.reserve(nl); t.seq_len.reserve(nl); t.n_cigar.reserve(nl); t.flags.reserve(nl);
+                t.cigar_ops.reserve(nl + nl / 2);
+                t.seq_pool.reserve((t.seq_bits == 4 ? bytes / 2 : bytes) + 32 * nl);     // an upper bound; untouched pages cost nothing
+                o.groups.reserve(nl / 2 + 1);
+            }
             Packer pk{&o.tmp, fname};
             pk.deferred = &o.groups;
             pk.line_count = o.first_line;
@@ -368,6 +382,15 @@ int pack_text_parallel(pp_pack* P, const char* data, size_t n, const std::string
     // merge in file order
     GroupState carry;                              // the open group of the stream so far
     uint64_t reads = 0, alignments = 0;
+    {   // the destination arrays grow once, to the sum of the chunks
+        size_t na = P->contig.size(), no = P->cigar_ops.size(), nb = P->seq_pool.n, ng = 0;
+        for (size_t c = 0; c < nc; ++c) { na += out[c].tmp.contig.size(); no += out[c].tmp.cigar_ops.size(); nb += out[c].tmp.seq_pool.n; ng += out[c].groups.size(); }
+        P->contig.reserve(na); P->ref_start.reserve(na); P->read_id.reserve(na); P->seq_off.reserve(na); P->cigar_off.reserve(na);
+        P->nm.reserve(na); P->seq_len.reserve(na); P->n_cigar.reserve(na); P->flags.reserve(na);
+        P->cigar_ops.reserve(no);
+        P->seq_pool.reserve(nb + 64);
+        P->group_name_off.reserve(P->group_name_off.size() + ng);
+    }
     auto close_carry = [&]() -> bool {
         if (carry.n == 0) return true;
         reads++;
@@ -441,16 +464,35 @@ extern "C" void pp_pack_free(pp_pack* p) { delete p; }
 
 extern "C" int pp_pack_add_sam_file(pp_pack* P, const char* path) {
     if (!P || !path) return PP_ERR_ARG;
+    // a regular file is mapped (the page cache's own pages: no copy); anything else - a pipe, a device - is read into a string
     std::string data;
-    if (!pp::read_file(path, data)) {
-        P->error = std::string("unable to load alignments from \"") + path + "\"";   // alignment.rs:219
-        P->error_code = PP_ERR_IO;
-        return PP_ERR_IO;
+    const char* text = nullptr;
+    size_t len = 0;
+    void* map = nullptr;
+    {
+        struct stat sb;                                   // (stat first: a FIFO must be opened exactly once, by read_file below)
+        if (stat(path, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+            const int fd = open(path, O_RDONLY);
+            if (fd >= 0) {
+                void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+                if (m != MAP_FAILED) { map = m; text = (const char*)m; len = (size_t)sb.st_size; }
+                close(fd);
+            }
+        }
+    }
+    if (!map) {
+        if (!pp::read_file(path, data)) {
+            P->error = std::string("unable to load alignments from \"") + path + "\"";   // alignment.rs:219
+            P->error_code = PP_ERR_IO;
+            return PP_ERR_IO;
+        }
+        text = data.data(); len = data.size();
     }
     if (!P->replaying) P->sources.push_back({true, path, std::string()});
     unsigned nt = P->threads ? P->threads : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    if (nt > 1 && data.size() >= 2 * P->min_chunk) return pack_text_parallel(P, data.data(), data.size(), path, nt, P->min_chunk);
-    return pack_text(P, data.data(), data.size(), path);
+    const int rc = (nt > 1 && len >= 2 * P->min_chunk) ? pack_text_parallel(P, text, len, path, nt, P->min_chunk) : pack_text(P, text, len, path);
+    if (map) munmap(map, len);
+    return rc;
 }
 
 // Parsing threads for pp_pack_add_sam_file (0 = one per hardware thread, at most 16) and the smallest chunk a thread gets.

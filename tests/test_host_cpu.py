@@ -293,3 +293,31 @@ def test_sam_split_ranges_cut_between_read_groups(tmp_path, seed):
             here = data[c:].split(b"\n", 1)[0].split(b"\t")[0]
             assert prev != here or here.startswith(b"@")
     assert L.pp_sam_split_ranges(str(tmp_path / "missing.sam").encode(), 2, (C.c_uint64 * 3)()) != 0
+
+
+def test_packer_reads_a_fifo_once(tmp_path):
+    """pp_pack_add_sam_file maps regular files and streams anything else: a named pipe is opened exactly once (a second open
+    would block for ever, or break the writer's pipe) and gives the same arrays as the file."""
+    import threading
+    syn = api.Synth(seed=3, n_contigs=1, contig_len=20_000, depth=20.0)
+    fa, sams = syn.write(str(tmp_path))
+    f = api.Fasta(fa)
+    ref = api.pack_sams(f, sams)
+    fifo = str(tmp_path / "reads.fifo")
+    os.mkfifo(fifo)
+
+    def writer():
+        with open(fifo, "wb") as o:
+            o.write(open(sams[0], "rb").read())
+    t = threading.Thread(target=writer)
+    t.start()
+    p = api.Packed(f, False)
+    p.add_file(fifo)
+    t.join(timeout=30)
+    assert not t.is_alive()
+    p.add_file(sams[1])
+    p.finish()
+    a, b = api.view_arrays(ref.view), api.view_arrays(p.view)
+    for k in a:
+        if isinstance(a[k], np.ndarray):
+            assert np.array_equal(a[k], b[k]), k
