@@ -8,7 +8,6 @@
 // Everything downstream (goodness, k, CIGAR walk, trim, pileup, vote) happens on the device.
 #include <algorithm>
 #include <fcntl.h>
-#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <cstdio>
@@ -464,23 +463,40 @@ extern "C" void pp_pack_free(pp_pack* p) { delete p; }
 
 extern "C" int pp_pack_add_sam_file(pp_pack* P, const char* path) {
     if (!P || !path) return PP_ERR_ARG;
-    // a regular file is mapped (the page cache's own pages: no copy); anything else - a pipe, a device - is read into a string
+    // A big regular file is read by several threads, each pread()ing its slice straight into one buffer (one pass, the page faults of
+    // the buffer spread over the threads); anything else - a small file, a pipe, a device - is read into a string.  (Not mmap: a
+    // file that another process truncates while it is parsed would raise SIGBUS; a short read is simply handled.)
     std::string data;
+    pp::AlignedBytes big;
     const char* text = nullptr;
     size_t len = 0;
-    void* map = nullptr;
     {
         struct stat sb;                                   // (stat first: a FIFO must be opened exactly once, by read_file below)
-        if (stat(path, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+        const unsigned rt = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        if (stat(path, &sb) == 0 && S_ISREG(sb.st_mode) && (uint64_t)sb.st_size >= (32ull << 20) && rt > 1) {
             const int fd = open(path, O_RDONLY);
             if (fd >= 0) {
-                void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
-                if (m != MAP_FAILED) { map = m; text = (const char*)m; len = (size_t)sb.st_size; }
+                const size_t size = (size_t)sb.st_size;
+                big.reserve(size + 64);
+                std::vector<char> whole(rt, 0);
+                std::vector<std::thread> th;
+                for (unsigned t = 0; t < rt; ++t) th.emplace_back([&, t] {
+                    size_t at = size * t / rt;
+                    const size_t end = size * (t + 1) / rt;
+                    while (at < end) {
+                        const ssize_t r = pread(fd, big.p + at, end - at, (off_t)at);
+                        if (r <= 0) return;                     // shorter than stat said (or an error): the sequential reader decides
+                        at += (size_t)r;
+                    }
+                    whole[t] = 1;
+                });
+                for (auto& t : th) t.join();
                 close(fd);
+                if (std::all_of(whole.begin(), whole.end(), [](char c) { return c != 0; })) { big.n = size; text = (const char*)big.p; len = size; }
             }
         }
     }
-    if (!map) {
+    if (!text) {
         if (!pp::read_file(path, data)) {
             P->error = std::string("unable to load alignments from \"") + path + "\"";   // alignment.rs:219
             P->error_code = PP_ERR_IO;
@@ -490,9 +506,7 @@ extern "C" int pp_pack_add_sam_file(pp_pack* P, const char* path) {
     }
     if (!P->replaying) P->sources.push_back({true, path, std::string()});
     unsigned nt = P->threads ? P->threads : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    const int rc = (nt > 1 && len >= 2 * P->min_chunk) ? pack_text_parallel(P, text, len, path, nt, P->min_chunk) : pack_text(P, text, len, path);
-    if (map) munmap(map, len);
-    return rc;
+    return (nt > 1 && len >= 2 * P->min_chunk) ? pack_text_parallel(P, text, len, path, nt, P->min_chunk) : pack_text(P, text, len, path);
 }
 
 // Parsing threads for pp_pack_add_sam_file (0 = one per hardware thread, at most 16) and the smallest chunk a thread gets.
